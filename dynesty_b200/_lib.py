@@ -1,0 +1,170 @@
+"""ctypes binding of libb200nest.so (C ABI: include/b200nest.h).
+
+There is NO CPU fallback: if the library is missing or no CUDA device is
+available every entry point raises ``B200Unavailable``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(HERE, 'libb200nest.so')
+
+PTR_HOST, PTR_DEVICE = 0, 1
+DIM_PERIODIC, DIM_REFLECTIVE = 1, 2
+PRIOR_IDENTITY, PRIOR_UNIFORM, PRIOR_NORMAL_PPF = 0, 1, 2
+LIKE_GAUSS_PREC, LIKE_GAUSS_DIAG, LIKE_EGGBOX, LIKE_SHELLS = 0, 1, 2, 3
+WARN_IDENTITY_FALLBACK, WARN_DOUBLING, WARN_Q0_SLACK, WARN_UNIF_INEFFICIENT = 1, 2, 4, 8
+
+(OK, ERR_CUDA, ERR_ARG, ERR_SINGLE_POINT, ERR_SINGULAR, ERR_ELL_INIT, ERR_INVALID_REGION,
+ ERR_Q0, ERR_SLICE_FAIL, ERR_NOMEM, ERR_UNSUPPORTED, ERR_TOO_MANY_ELLS) = range(12)
+
+
+class B200Unavailable(RuntimeError):
+    """libb200nest.so / a CUDA device is missing.  The B200 path has no CPU fallback."""
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [('ndim', C.c_int32), ('prior_kind', C.c_int32), ('like_kind', C.c_int32),
+                ('reserved', C.c_int32), ('prior_p0', C.c_void_p), ('prior_p1', C.c_void_p),
+                ('like_vec0', C.c_void_p), ('like_vec1', C.c_void_p), ('like_mat', C.c_void_p),
+                ('like_s0', C.c_double), ('like_s1', C.c_double), ('like_s2', C.c_double)]
+
+
+class ChainArgs(C.Structure):
+    _fields_ = [('nchain', C.c_int64), ('ndim', C.c_int32), ('ncdim', C.c_int32),
+                ('model_id', C.c_int32), ('reserved', C.c_int32), ('u0', C.c_void_p),
+                ('ell', C.c_void_p), ('dimflags', C.c_void_p), ('loglstar', C.c_double),
+                ('scale', C.c_double), ('seed', C.c_uint64), ('chain0', C.c_uint64)]
+
+
+# every symbol include/b200nest.h declares: (restype, argtypes)
+_P, _I, _L, _D, _U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_uint64
+SYMBOLS = {
+    'b2n_init': (C.c_int, [C.c_int, C.POINTER(_P)]),
+    'b2n_free': (None, [_P]),
+    'b2n_set_stream': (C.c_int, [_P, _P]),
+    'b2n_set_pointer_mode': (C.c_int, [_P, C.c_int]),
+    'b2n_synchronize': (C.c_int, [_P]),
+    'b2n_strerror': (C.c_char_p, [C.c_int]),
+    'b2n_last_error': (C.c_char_p, [_P]),
+    'b2n_version': (C.c_char_p, []),
+    'b2n_launch_count': (C.c_int64, [_P]),
+    'b2n_model_create': (C.c_int, [_P, C.POINTER(ModelDesc), C.POINTER(_I)]),
+    'b2n_model_eval': (C.c_int, [_P, _I, _P, _L, _P, _P]),
+    'b2n_membership': (C.c_int, [_P, _P, _L, _I, _P, _P, _I, _I, _P, _P, _P]),
+    'b2n_bounding_ellipsoid': (C.c_int, [_P, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
+    'b2n_multi_decompose': (C.c_int, [_P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'b2n_scale_to_logvol': (C.c_int, [_P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    'b2n_bootstrap_expand': (C.c_int, [_P, _P, _L, _I, _I, _I, _U64, _U64, _P]),
+    'b2n_bound_set': (C.c_int, [_P, _I, _I, _P, _P, _P, _P]),
+    'b2n_rwalk_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _I, _P, _P, _P, _P, _P, _P]),
+    'b2n_rslice_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    'b2n_slice_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    'b2n_unif_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _P, _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the library and bind every declared symbol (no CUDA calls)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBPATH):
+        raise B200Unavailable(
+            "%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback." % LIBPATH)
+    lib = C.CDLL(LIBPATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+_EXC = {
+    ERR_ARG: ValueError, ERR_SINGLE_POINT: ValueError, ERR_SINGULAR: ValueError,
+    ERR_ELL_INIT: RuntimeError, ERR_INVALID_REGION: RuntimeError, ERR_Q0: RuntimeError,
+    ERR_SLICE_FAIL: RuntimeError, ERR_NOMEM: MemoryError, ERR_UNSUPPORTED: NotImplementedError,
+    ERR_TOO_MANY_ELLS: RuntimeError,
+}
+
+
+def ptr(a):
+    """Address of a numpy array / torch tensor / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        assert a.flags['C_CONTIGUOUS'], "array must be C-contiguous"
+        return a.ctypes.data
+    return a.data_ptr()      # torch tensor
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """Owns one b2n_ctx (one per process / GPU)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        st = self.lib.b2n_init(int(device), C.byref(h))
+        if st != OK:
+            raise B200Unavailable(
+                "b2n_init(device=%d) failed: %s -- the B200 path needs a CUDA device; "
+                "there is no CPU fallback" % (device, self.lib.b2n_strerror(st).decode()))
+        self.h = h
+        self.device = device
+        self.mode = PTR_HOST
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.b2n_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, st):
+        if st == OK:
+            return
+        msg = self.lib.b2n_strerror(st).decode()
+        detail = self.lib.b2n_last_error(self.h).decode()
+        if st == ERR_CUDA or detail:
+            msg = "%s (%s)" % (msg, detail)
+        raise _EXC.get(st, RuntimeError)(msg)
+
+    def set_stream(self, stream):
+        self.check(self.lib.b2n_set_stream(self.h, stream))
+
+    def set_pointer_mode(self, mode):
+        self.check(self.lib.b2n_set_pointer_mode(self.h, mode))
+        self.mode = mode
+
+    def synchronize(self):
+        self.check(self.lib.b2n_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.lib.b2n_launch_count(self.h))
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    if device is None:
+        device = int(os.environ.get('LOCAL_RANK', '0'))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

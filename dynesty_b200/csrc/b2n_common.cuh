@@ -1,0 +1,178 @@
+// b2n_common.cuh -- context, scratch memory and small device helpers shared by
+// all translation units of libb200nest.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include "../../include/b200nest.h"
+
+#define B2N_WARP 32
+#define B2N_FULL 0xffffffffu
+
+// ---- device-side model descriptor (passed by value to kernels) -------------
+struct B2nModel {
+    int ndim, prior_kind, like_kind, pad;
+    const double* pp0;   // device
+    const double* pp1;
+    const double* lv0;
+    const double* lv1;
+    const double* lmat;
+    double s0, s1, s2;
+};
+
+// growable device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct b2n_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int ptr_mode = B2N_PTR_HOST;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+    int64_t launches = 0;
+    char err[512] = {0};
+    std::vector<B2nModel> models;
+    std::vector<void*> model_allocs;
+    // resident bound
+    int bK = 0, bn = 0;
+    DevBuf b_ctrs, b_ams, b_axesT, b_logvols;
+    std::vector<double> h_logvols;
+    // staging (host-pointer mode) and scratch
+    DevBuf in0, in1, in2, in3, out0, out1, out2, out3, out4, out5, out6, out7;
+    DevBuf scratch0, scratch1, scratch2, scratch3, scratch4, scratch5;
+    DevBuf work0, work1;
+    void* pinned = nullptr;     // small pinned host mailbox
+    size_t pinned_cap = 0;
+};
+
+#define B2N_CUDA(ctx, call)                                                        \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) {                                                   \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__,     \
+                     __LINE__, #call, cudaGetErrorString(e_));                     \
+            return B2N_ERR_CUDA;                                                   \
+        }                                                                          \
+    } while (0)
+
+#define B2N_TRY(call)                         \
+    do {                                      \
+        int s_ = (call);                      \
+        if (s_ != B2N_OK) return s_;          \
+    } while (0)
+
+#define B2N_LAUNCH_CHECK(ctx)                 \
+    do {                                      \
+        (ctx)->launches++;                    \
+        B2N_CUDA(ctx, cudaGetLastError());    \
+    } while (0)
+
+static inline int b2n_fail(b2n_ctx* ctx, int status, const char* msg) {
+    snprintf(ctx->err, sizeof(ctx->err), "%s", msg);
+    return status;
+}
+
+// Input staging: returns a device pointer for `src` (copying when in host mode).
+static inline int b2n_in(b2n_ctx* ctx, DevBuf& buf, const void* src, size_t bytes,
+                         const void** dev) {
+    if (ctx->ptr_mode == B2N_PTR_DEVICE || src == nullptr || bytes == 0) {
+        *dev = src;
+        return B2N_OK;
+    }
+    B2N_CUDA(ctx, buf.ensure(bytes));
+    B2N_CUDA(ctx, cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = buf.p;
+    return B2N_OK;
+}
+// Host-resident argument that is needed on the device in both modes.
+static inline int b2n_in_host(b2n_ctx* ctx, DevBuf& buf, const void* src, size_t bytes,
+                              const void** dev) {
+    if (src == nullptr || bytes == 0) { *dev = nullptr; return B2N_OK; }
+    B2N_CUDA(ctx, buf.ensure(bytes));
+    B2N_CUDA(ctx, cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = buf.p;
+    return B2N_OK;
+}
+// Output staging: device pointer to write into.
+static inline int b2n_out(b2n_ctx* ctx, DevBuf& buf, void* dst, size_t bytes, void** dev) {
+    if (dst == nullptr) { *dev = nullptr; return B2N_OK; }
+    if (ctx->ptr_mode == B2N_PTR_DEVICE) { *dev = dst; return B2N_OK; }
+    B2N_CUDA(ctx, buf.ensure(bytes));
+    *dev = buf.p;
+    return B2N_OK;
+}
+static inline int b2n_out_done(b2n_ctx* ctx, void* dst, const void* dev, size_t bytes) {
+    if (dst == nullptr || ctx->ptr_mode == B2N_PTR_DEVICE) return B2N_OK;
+    B2N_CUDA(ctx, cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return B2N_OK;
+}
+static inline int b2n_finish(b2n_ctx* ctx) {
+    if (ctx->ptr_mode == B2N_PTR_HOST) B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B2N_OK;
+}
+
+// ---- warp helpers ----------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(B2N_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_prod(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(B2N_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(B2N_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(B2N_FULL, v, o));
+    return v;
+}
+
+// y_i = sum_j M[j*ld + i] * x[j] for the two rows i0 = base+lane, i1 = i0+32
+// (column-major panel: lanes read consecutive addresses; x is a warp broadcast).
+// Four accumulators per row keep the FP64 pipe busy despite the DFMA latency.
+__device__ __forceinline__ void warp_matvec2(const double* __restrict__ M, int ld, int ncols,
+                                             const double* __restrict__ x, int i0, int nrows,
+                                             double& y0, double& y1) {
+    const int i1 = i0 + 32;
+    const bool r0 = i0 < nrows, r1 = i1 < nrows;
+    const int a0 = r0 ? i0 : 0, a1 = r1 ? i1 : 0;
+    double p0 = 0, p1 = 0, q0 = 0, q1 = 0;
+    int j = 0;
+    for (; j + 1 < ncols; j += 2) {
+        const double xa = x[j], xb = x[j + 1];
+        p0 = fma(M[(size_t)j * ld + a0], xa, p0);
+        p1 = fma(M[(size_t)j * ld + a1], xa, p1);
+        q0 = fma(M[(size_t)(j + 1) * ld + a0], xb, q0);
+        q1 = fma(M[(size_t)(j + 1) * ld + a1], xb, q1);
+    }
+    if (j < ncols) {
+        const double xa = x[j];
+        p0 = fma(M[(size_t)j * ld + a0], xa, p0);
+        p1 = fma(M[(size_t)j * ld + a1], xa, p1);
+    }
+    y0 = r0 ? p0 + q0 : 0.0;
+    y1 = r1 ? p1 + q1 : 0.0;
+}

@@ -1,0 +1,241 @@
+// b2n_rwalk.cu -- batched random-walk proposal chains (one warp per chain).
+//
+// Replaces RWalkSampler.sample -> generic_random_walk -> propose_ball_point
+// (reference internal_samplers.py:505-561, 866-986, 989-1035) for a whole queue
+// of chains in ONE launch.  Per chain and per step:
+//   1. fresh U(0,1) on the non-clustered dims (:1011-1013)       [vector uniform event]
+//   2. dr = randsphere(ncdim) (bounding.py:1288-1297)            [normal event + uniform event]
+//   3. u' = u + scale * axes @ dr on the clustered dims (:1020-1021)
+//   4. periodic wrap / reflect (:1024-1029), unitcheck (:1032); an out-of-cube
+//      proposal counts as a call and a reject WITHOUT a likelihood call (:951-954)
+//   5. v = prior_transform(u'), logl = loglikelihood(v), accept iff logl > loglstar
+// exactly `walks` steps; with zero accepts v/logl are recomputed at the start (:970-975).
+//
+// Mapping: a CTA handles chains that share one ellipsoid; its axes^T (and the
+// precision matrix of a GAUSS_PREC model) are staged ONCE into shared memory and
+// every warp then streams them from there `walks` times -- HBM sees each matrix
+// once per CTA.  Lane i owns rows i, i+32, ... of each mat-vec; the proposal
+// vector is a warp-private shared vector read as a broadcast.
+#include "b2n_device.cuh"
+#include <algorithm>
+
+struct RwalkParams {
+    B2nModel m;
+    int n, nc, walks;
+    const double* u0;
+    const int* order;      // chains grouped by ellipsoid
+    const int3* cta;       // (first, count, ell) per CTA
+    const double* axesT;   // K x nc x nc, transposed (column-major axes)
+    const uint32_t* dimflags;
+    double loglstar, scale;
+    uint64_t seed, chain0;
+    double *u, *v, *logl;
+    int *nacc, *nrej, *ncall;
+};
+
+template <int LIKE, bool AX_SMEM, bool PREC_SMEM>
+__global__ void __launch_bounds__(256) rwalk_kernel(const RwalkParams p) {
+    extern __shared__ double sm[];
+    const int n = p.n, nc = p.nc;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int3 cd = p.cta[blockIdx.x];
+    double* s = sm;
+    const double* A = p.axesT + (size_t)cd.z * nc * nc;
+    if (AX_SMEM) {
+        for (int i = threadIdx.x; i < nc * nc; i += blockDim.x) s[i] = A[i];
+        A = s;
+        s += nc * nc;
+    }
+    const double* P = p.m.lmat;
+    if (LIKE == B2N_LIKE_GAUSS_PREC && PREC_SMEM) {
+        for (int i = threadIdx.x; i < n * n; i += blockDim.x) s[i] = P[i];
+        P = s;
+        s += n * n;
+    }
+    uint32_t* fl = reinterpret_cast<uint32_t*>(s);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) fl[i] = p.dimflags ? p.dimflags[i] : 0u;
+    s += (n + 1) / 2;
+    __syncthreads();
+
+    double* ucur = s + (size_t)warp * 5 * n;
+    double* uprop = ucur + n;
+    double* vcur = uprop + n;
+    double* vprop = vcur + n;
+    double* x = vprop + n;    // direction vector, later likelihood scratch
+    const double inv_nc = 1.0 / (double)nc;
+
+    for (int c = warp; c < cd.y; c += nwarps) {
+        const int q = p.order[cd.x + c];
+        ChainRng g;
+        g.init(p.seed, p.chain0 + (uint64_t)q);
+        for (int i = lane; i < n; i += 32) ucur[i] = p.u0[(size_t)q * n + i];
+        __syncwarp();
+        int nacc = 0, nrej = 0;
+        double lcur = 0.0;
+        for (int step = 0; step < p.walks; step++) {
+            // (1) non-clustered dims: one vector uniform event (only if there are any)
+            if (n > nc) {
+                for (int e = lane; e < n - nc; e += 32) uprop[nc + e] = rng_uniform_elem(g, e);
+                g.tick++;
+            }
+            // (2) uniform point in the unit nc-ball
+            const double ss = rng_normals_to(g, x, nc, lane);
+            const double U = rng_uniform(g);
+            const double fac = p.scale * (pow(U, inv_nc) / sqrt(ss));
+            __syncwarp();
+            // (3) clustered dims: u' = u + fac * axes @ z ; (4) boundaries
+            bool ok = true;
+            for (int base = 0; base < nc; base += 64) {
+                double y0, y1;
+                warp_matvec2(A, nc, nc, x, base + lane, nc, y0, y1);
+                const int i0 = base + lane, i1 = i0 + 32;
+                if (i0 < nc) uprop[i0] = fma(fac, y0, ucur[i0]);
+                if (i1 < nc) uprop[i1] = fma(fac, y1, ucur[i1]);
+            }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                double t = uprop[i];
+                const uint32_t f = fl[i];
+                if (f & B2N_DIM_PERIODIC) t = mod1(t);
+                if (f & B2N_DIM_REFLECTIVE) t = reflect1(t);
+                ok = ok && in_cube(t, f);
+                uprop[i] = t;
+            }
+            ok = __all_sync(B2N_FULL, ok);
+            if (!ok) { nrej++; continue; }
+            // (5) prior transform + likelihood
+            for (int i = lane; i < n; i += 32) vprop[i] = prior_1d(p.m, i, uprop[i]);
+            __syncwarp();
+            const double l = warp_loglike<LIKE>(p.m, P, vprop, x, lane);
+            if (l > p.loglstar) {
+                double* t = ucur; ucur = uprop; uprop = t;
+                t = vcur; vcur = vprop; vprop = t;
+                lcur = l;
+                nacc++;
+            } else {
+                nrej++;
+            }
+        }
+        if (nacc == 0) {
+            for (int i = lane; i < n; i += 32) vcur[i] = prior_1d(p.m, i, ucur[i]);
+            __syncwarp();
+            lcur = warp_loglike<LIKE>(p.m, P, vcur, x, lane);
+        }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            p.u[(size_t)q * n + i] = ucur[i];
+            p.v[(size_t)q * n + i] = vcur[i];
+        }
+        if (lane == 0) {
+            p.logl[q] = lcur;
+            p.nacc[q] = nacc;
+            p.nrej[q] = nrej;
+            p.ncall[q] = p.walks;
+        }
+        __syncwarp();
+    }
+}
+
+// Host-side grouping of chains by ellipsoid -> per-CTA work descriptors.
+// (shared with the slice kernels)
+int b2n_build_worklist(b2n_ctx* ctx, int64_t Q, const int32_t* ell, int K, int chains_per_cta,
+                       std::vector<int>& order, std::vector<int3>& cta) {
+    order.resize(Q);
+    cta.clear();
+    std::vector<int64_t> count(K + 1, 0);
+    if (ell) {
+        for (int64_t q = 0; q < Q; q++) {
+            if (ell[q] < 0 || ell[q] >= K) return b2n_fail(ctx, B2N_ERR_ARG, "chain ellipsoid index out of range");
+            count[ell[q] + 1]++;
+        }
+    } else {
+        count[1] = Q;
+    }
+    for (int k = 0; k < K; k++) count[k + 1] += count[k];
+    std::vector<int64_t> pos(count.begin(), count.end() - 1);
+    for (int64_t q = 0; q < Q; q++) order[pos[ell ? ell[q] : 0]++] = (int)q;
+    for (int k = 0; k < K; k++)
+        for (int64_t f = count[k]; f < count[k + 1]; f += chains_per_cta)
+            cta.push_back(make_int3((int)f, (int)std::min<int64_t>(chains_per_cta, count[k + 1] - f), k));
+    return B2N_OK;
+}
+
+extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t walks, double* u,
+                               double* v, double* logl, int32_t* n_accept, int32_t* n_reject,
+                               int32_t* ncall) {
+    if (!ctx || !a || !u || !v || !logl || !n_accept || !n_reject || !ncall) return B2N_ERR_ARG;
+    if (a->model_id < 0 || a->model_id >= (int)ctx->models.size()) return B2N_ERR_ARG;
+    const B2nModel m = ctx->models[a->model_id];
+    const int n = a->ndim, nc = a->ncdim;
+    const int64_t Q = a->nchain;
+    if (n != m.ndim || nc < 1 || nc > n || walks < 1 || Q < 0 || !a->u0) return B2N_ERR_ARG;
+    if (ctx->bK < 1 || ctx->bn != nc) return b2n_fail(ctx, B2N_ERR_ARG, "resident bound missing or of wrong dimension (b2n_bound_set)");
+    if (Q == 0) return B2N_OK;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    // shared-memory plan: per-warp state always; matrices when they fit
+    const int warps = 8;
+    const size_t per_warp = (size_t)5 * n * sizeof(double);
+    const size_t fixed = per_warp * warps + (size_t)((n + 1) / 2) * sizeof(double);
+    const size_t ax_b = (size_t)nc * nc * sizeof(double);
+    const size_t pr_b = (m.like_kind == B2N_LIKE_GAUSS_PREC) ? (size_t)n * n * sizeof(double) : 0;
+    const size_t limit = (size_t)ctx->max_smem_optin;
+    if (fixed > limit) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for the rwalk kernel");
+    // prefer CTAs that leave room for >= 2 resident CTAs per SM
+    bool ax_s = fixed + ax_b <= limit;
+    bool pr_s = pr_b > 0 && fixed + (ax_s ? ax_b : 0) + pr_b <= limit;
+    const size_t smem = fixed + (ax_s ? ax_b : 0) + (pr_s ? pr_b : 0);
+
+    std::vector<int> order;
+    std::vector<int3> cta;
+    B2N_TRY(b2n_build_worklist(ctx, Q, a->ell, ctx->bK, warps, order, cta));
+
+    RwalkParams p;
+    p.m = m; p.n = n; p.nc = nc; p.walks = walks;
+    p.loglstar = a->loglstar; p.scale = a->scale; p.seed = a->seed; p.chain0 = a->chain0;
+    p.axesT = ctx->b_axesT.as<double>();
+    const void *du0, *dorder, *dcta, *dfl = nullptr;
+    B2N_TRY(b2n_in(ctx, ctx->in0, a->u0, (size_t)Q * n * sizeof(double), &du0));
+    B2N_TRY(b2n_in_host(ctx, ctx->work0, order.data(), order.size() * sizeof(int), &dorder));
+    B2N_TRY(b2n_in_host(ctx, ctx->work1, cta.data(), cta.size() * sizeof(int3), &dcta));
+    std::vector<uint32_t> fl;
+    if (a->dimflags) {
+        fl.assign(a->dimflags, a->dimflags + n);
+        B2N_TRY(b2n_in_host(ctx, ctx->in3, fl.data(), fl.size() * sizeof(uint32_t), &dfl));
+    }
+    void *du, *dv, *dl, *dna, *dnr, *dncl;
+    B2N_TRY(b2n_out(ctx, ctx->out0, u, (size_t)Q * n * sizeof(double), &du));
+    B2N_TRY(b2n_out(ctx, ctx->out1, v, (size_t)Q * n * sizeof(double), &dv));
+    B2N_TRY(b2n_out(ctx, ctx->out2, logl, (size_t)Q * sizeof(double), &dl));
+    B2N_TRY(b2n_out(ctx, ctx->out3, n_accept, (size_t)Q * sizeof(int), &dna));
+    B2N_TRY(b2n_out(ctx, ctx->out4, n_reject, (size_t)Q * sizeof(int), &dnr));
+    B2N_TRY(b2n_out(ctx, ctx->out5, ncall, (size_t)Q * sizeof(int), &dncl));
+    p.u0 = (const double*)du0; p.order = (const int*)dorder; p.cta = (const int3*)dcta;
+    p.dimflags = (const uint32_t*)dfl;
+    p.u = (double*)du; p.v = (double*)dv; p.logl = (double*)dl;
+    p.nacc = (int*)dna; p.nrej = (int*)dnr; p.ncall = (int*)dncl;
+
+    const unsigned grid = (unsigned)cta.size();
+#define LAUNCH(L, AXS, PRS)                                                                       \
+    do {                                                                                          \
+        B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_kernel<L, AXS, PRS>,                             \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        rwalk_kernel<L, AXS, PRS><<<grid, warps * 32, smem, ctx->stream>>>(p);                    \
+    } while (0)
+#define CALL(L)                                                        \
+    if (ax_s && pr_s) LAUNCH(L, true, true);                           \
+    else if (ax_s) LAUNCH(L, true, false);                             \
+    else if (pr_s) LAUNCH(L, false, true);                             \
+    else LAUNCH(L, false, false);
+    B2N_DISPATCH_LIKE(m.like_kind, CALL)
+#undef CALL
+#undef LAUNCH
+    B2N_LAUNCH_CHECK(ctx);
+    B2N_TRY(b2n_out_done(ctx, u, du, (size_t)Q * n * sizeof(double)));
+    B2N_TRY(b2n_out_done(ctx, v, dv, (size_t)Q * n * sizeof(double)));
+    B2N_TRY(b2n_out_done(ctx, logl, dl, (size_t)Q * sizeof(double)));
+    B2N_TRY(b2n_out_done(ctx, n_accept, dna, (size_t)Q * sizeof(int)));
+    B2N_TRY(b2n_out_done(ctx, n_reject, dnr, (size_t)Q * sizeof(int)));
+    B2N_TRY(b2n_out_done(ctx, ncall, dncl, (size_t)Q * sizeof(int)));
+    return b2n_finish(ctx);
+}

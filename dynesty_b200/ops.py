@@ -1,0 +1,196 @@
+"""numpy-level wrappers of the C ABI (host-pointer mode).  Every function here is a
+single C call; array-in/array-out, the reference's exceptions on failure."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ChainArgs, ptr, f64
+
+
+def _ctx(ctx):
+    return ctx if ctx is not None else _lib.default_context()
+
+
+def model_eval(model, u, want_v=True, ctx=None):
+    """(v, logl) for the rows of u (M, ndim)."""
+    ctx = _ctx(ctx)
+    u = f64(np.atleast_2d(u))
+    M, n = u.shape
+    v = np.empty((M, n)) if want_v else None
+    logl = np.empty(M)
+    ctx.check(ctx.lib.b2n_model_eval(ctx.h, model, ptr(u), M, ptr(v), ptr(logl)))
+    return v, logl
+
+
+def membership(x, ctrs, ams, strict=True, want_d2=False, ctx=None):
+    """mask (M, K) bool, q (M,) int32 [, d2 (M, K)]  (bounding.py:502-523)."""
+    ctx = _ctx(ctx)
+    x = f64(np.atleast_2d(x))
+    ctrs = f64(np.atleast_2d(ctrs))
+    ams = f64(ams).reshape(ctrs.shape[0], ctrs.shape[1], ctrs.shape[1])
+    M, n = x.shape
+    K = ctrs.shape[0]
+    mask = np.empty((M, K), dtype=np.uint8)
+    q = np.empty(M, dtype=np.int32)
+    d2 = np.empty((M, K)) if want_d2 else None
+    ctx.check(ctx.lib.b2n_membership(ctx.h, ptr(x), M, n, ptr(ctrs), ptr(ams), K, int(bool(strict)),
+                                     ptr(mask), ptr(q), ptr(d2)))
+    out = (mask.astype(bool), q)
+    return out + (d2,) if want_d2 else out
+
+
+def bounding_ellipsoid(points, ctx=None):
+    """dict(ctr, cov, am, axes, axlens, logvol, warn)  (bounding.py:1387-1461)."""
+    ctx = _ctx(ctx)
+    points = f64(points)
+    N, n = points.shape
+    o = dict(ctr=np.empty(n), cov=np.empty((n, n)), am=np.empty((n, n)), axes=np.empty((n, n)),
+             axlens=np.empty(n))
+    lv = np.empty(1)
+    warn = C.c_uint32(0)
+    ctx.check(ctx.lib.b2n_bounding_ellipsoid(ctx.h, ptr(points), N, n, ptr(o['ctr']), ptr(o['cov']),
+                                             ptr(o['am']), ptr(o['axes']), ptr(o['axlens']), ptr(lv),
+                                             C.addressof(warn)))
+    o['logvol'] = float(lv[0])
+    o['warn'] = warn.value
+    return o
+
+
+def multi_decompose(points, max_ells=None, ctx=None):
+    """dict(nells, labels, ctrs, covs, ams, axes, axlens, logvols, warn)  (bounding.py:665-686)."""
+    ctx = _ctx(ctx)
+    points = f64(points)
+    N, n = points.shape
+    if max_ells is None:
+        max_ells = max(1, N // max(2 * n, 1))
+    K = int(max_ells)
+    o = dict(labels=np.empty(N, dtype=np.int32), ctrs=np.empty((K, n)), covs=np.empty((K, n, n)),
+             ams=np.empty((K, n, n)), axes=np.empty((K, n, n)), axlens=np.empty((K, n)),
+             logvols=np.empty(K))
+    nells = C.c_int32(0)
+    warn = C.c_uint32(0)
+    ctx.check(ctx.lib.b2n_multi_decompose(ctx.h, ptr(points), N, n, K, C.addressof(nells),
+                                          ptr(o['labels']), ptr(o['ctrs']), ptr(o['covs']), ptr(o['ams']),
+                                          ptr(o['axes']), ptr(o['axlens']), ptr(o['logvols']),
+                                          C.addressof(warn)))
+    k = nells.value
+    for key in ('ctrs', 'covs', 'ams', 'axes', 'axlens', 'logvols'):
+        o[key] = o[key][:k].copy()
+    o['nells'] = k
+    o['warn'] = warn.value
+    return o
+
+
+def scale_to_logvol(covs, ams, axes, axlens, logvols, targets, ctx=None):
+    """In-place Ellipsoid.scale_to_logvol on K stacked ellipsoids (bounding.py:242-276)."""
+    ctx = _ctx(ctx)
+    K, n = axlens.shape
+    targets = f64(targets)
+    for a in (covs, ams, axes, axlens, logvols):
+        assert a.dtype == np.float64 and a.flags['C_CONTIGUOUS']
+    ctx.check(ctx.lib.b2n_scale_to_logvol(ctx.h, K, n, ptr(covs), ptr(ams), ptr(axes), ptr(axlens),
+                                          ptr(logvols), ptr(targets)))
+
+
+def bootstrap_expand(points, multi, nboot, seed, chain0, ctx=None):
+    ctx = _ctx(ctx)
+    points = f64(points)
+    N, n = points.shape
+    out = np.empty(nboot)
+    ctx.check(ctx.lib.b2n_bootstrap_expand(ctx.h, ptr(points), N, n, int(bool(multi)), nboot, seed,
+                                           chain0, ptr(out)))
+    return out
+
+
+def bound_set(axes, ctrs=None, ams=None, logvols=None, ctx=None):
+    """Make K ellipsoids resident for the proposal kernels (axes: (K, nc, nc))."""
+    ctx = _ctx(ctx)
+    axes = f64(axes)
+    if axes.ndim == 2:
+        axes = axes[None]
+    K, nc, _ = axes.shape
+    if ctrs is not None:
+        ctrs, ams, logvols = f64(ctrs).reshape(K, nc), f64(ams).reshape(K, nc, nc), f64(logvols).reshape(K)
+    ctx.check(ctx.lib.b2n_bound_set(ctx.h, K, nc, ptr(ctrs), ptr(ams), ptr(axes), ptr(logvols)))
+
+
+def _chain_args(model, u0, ncdim, loglstar, scale, seed, chain0, ell, dimflags, Q=None, ndim=None):
+    a = ChainArgs()
+    keep = []
+    if u0 is not None:
+        u0 = f64(np.atleast_2d(u0))
+        Q, ndim = u0.shape
+        keep.append(u0)
+    a.nchain, a.ndim, a.ncdim, a.model_id = Q, ndim, (ncdim or ndim), model
+    a.u0 = ptr(u0)
+    if ell is not None:
+        ell = np.ascontiguousarray(ell, dtype=np.int32)
+        keep.append(ell)
+    a.ell = ptr(ell)
+    if dimflags is not None:
+        dimflags = np.ascontiguousarray(dimflags, dtype=np.uint8)
+        keep.append(dimflags)
+    a.dimflags = ptr(dimflags)
+    a.loglstar, a.scale, a.seed, a.chain0 = float(loglstar), float(scale), int(seed), int(chain0)
+    return a, keep, Q, ndim
+
+
+def dimflags_from(ndim, periodic=None, reflective=None):
+    """B2N_DIM_* flags from dynesty's periodic / reflective index lists."""
+    if periodic is None and reflective is None:
+        return None
+    f = np.zeros(ndim, dtype=np.uint8)
+    if periodic is not None:
+        f[np.asarray(periodic, dtype=int)] |= _lib.DIM_PERIODIC
+    if reflective is not None:
+        f[np.asarray(reflective, dtype=int)] |= _lib.DIM_REFLECTIVE
+    return f
+
+
+def rwalk_batch(model, u0, loglstar, scale, walks, seed, chain0=0, ncdim=None, ell=None,
+                dimflags=None, ctx=None):
+    """RWalkSampler.sample for every row of u0 (internal_samplers.py:505-561)."""
+    ctx = _ctx(ctx)
+    a, keep, Q, n = _chain_args(model, u0, ncdim, loglstar, scale, seed, chain0, ell, dimflags)
+    o = dict(u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q),
+             n_accept=np.empty(Q, dtype=np.int32), n_reject=np.empty(Q, dtype=np.int32),
+             ncall=np.empty(Q, dtype=np.int32))
+    ctx.check(ctx.lib.b2n_rwalk_batch(ctx.h, C.byref(a), int(walks), ptr(o['u']), ptr(o['v']),
+                                      ptr(o['logl']), ptr(o['n_accept']), ptr(o['n_reject']),
+                                      ptr(o['ncall'])))
+    return o
+
+
+def _slice_batch(fn, model, u0, loglstar, scale, slices, seed, chain0, doubling, ell, ctx):
+    ctx = _ctx(ctx)
+    a, keep, Q, n = _chain_args(model, u0, None, loglstar, scale, seed, chain0, ell, None)
+    o = dict(u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q),
+             n_expand=np.empty(Q, dtype=np.int32), n_contract=np.empty(Q, dtype=np.int32),
+             ncall=np.empty(Q, dtype=np.int32), flags=np.empty(Q, dtype=np.uint32))
+    ctx.check(getattr(ctx.lib, fn)(ctx.h, C.byref(a), int(slices), int(bool(doubling)), ptr(o['u']),
+                                   ptr(o['v']), ptr(o['logl']), ptr(o['n_expand']), ptr(o['n_contract']),
+                                   ptr(o['ncall']), ptr(o['flags'])))
+    return o
+
+
+def rslice_batch(model, u0, loglstar, scale, slices, seed, chain0=0, doubling=False, ell=None, ctx=None):
+    """RSliceSampler.sample per row of u0 (internal_samplers.py:745-855)."""
+    return _slice_batch('b2n_rslice_batch', model, u0, loglstar, scale, slices, seed, chain0, doubling, ell, ctx)
+
+
+def slice_batch(model, u0, loglstar, scale, slices, seed, chain0=0, doubling=False, ell=None, ctx=None):
+    """SliceSampler.sample per row of u0 (internal_samplers.py:593-709)."""
+    return _slice_batch('b2n_slice_batch', model, u0, loglstar, scale, slices, seed, chain0, doubling, ell, ctx)
+
+
+def unif_batch(model, nchain, ndim, loglstar, seed, chain0=0, ncdim=None, dimflags=None, ctx=None):
+    """UniformBoundSampler.sample x nchain on the resident bound (internal_samplers.py:243-340)."""
+    ctx = _ctx(ctx)
+    a, keep, Q, n = _chain_args(model, None, ncdim, loglstar, 1.0, seed, chain0, None, dimflags,
+                                Q=int(nchain), ndim=int(ndim))
+    o = dict(u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q), ncall=np.empty(Q, dtype=np.int32),
+             nprop=np.empty(Q, dtype=np.int32), flags=np.empty(Q, dtype=np.uint32))
+    ctx.check(ctx.lib.b2n_unif_batch(ctx.h, C.byref(a), ptr(o['u']), ptr(o['v']), ptr(o['logl']),
+                                     ptr(o['ncall']), ptr(o['nprop']), ptr(o['flags'])))
+    return o

@@ -1,0 +1,210 @@
+/* b200nest.h -- C ABI of libb200nest.so: the B200 (sm_100a) implementation of
+ * dynesty's bounding-and-proposal hot path.
+ *
+ * The reference (joshspeagle/dynesty @ 99451618, pure Python) has no FFI; its
+ * extension seams are three Python duck-types:
+ *   bound=<Bound>            py/dynesty/bounding.py:76-122
+ *   sample=<InternalSampler> py/dynesty/internal_samplers.py:36-203
+ *   pool=<obj with .map>     py/dynesty/utils.py:2358-2381
+ * Each entry point below replaces the numeric body of the reference function
+ * cited next to it; the Python classes in dynesty_b200/ (ctypes) mirror the
+ * three duck-types and call these.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - all matrices row-major float64; u = unit-cube coordinates (N, n).
+ *   - every function returns a b2n_status (0 = ok); the library never returns
+ *     owned memory: the caller allocates all outputs.
+ *   - pointer mode (b2n_set_pointer_mode): B2N_PTR_HOST (default) = array
+ *     arguments are host pointers, the call copies in/out and synchronises
+ *     before returning; B2N_PTR_DEVICE = array arguments are device pointers on
+ *     the ctx device, work is enqueued on the ctx stream and NOT synchronised
+ *     (functions that must return a host scalar synchronise and say so).
+ *     Arguments documented "host" are host pointers in both modes.
+ *   - one caller thread per ctx (the reference's master is single-threaded,
+ *     calls are strictly serialised from Sampler, sampler.py:676-778).
+ */
+#ifndef B200NEST_H_
+#define B200NEST_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2n_ctx b2n_ctx;
+
+/* ---- status codes; the Python layer maps them 1:1 onto the reference's
+ *      exceptions (file:line of the raise in the reference) ---------------- */
+typedef enum {
+    B2N_OK = 0,
+    B2N_ERR_CUDA = 1,            /* CUDA runtime failure (b2n_last_error)           */
+    B2N_ERR_ARG = 2,             /* bad argument                                    */
+    B2N_ERR_SINGLE_POINT = 3,    /* ValueError   bounding.py:1405-1407, RuntimeError :666-668 */
+    B2N_ERR_SINGULAR = 4,        /* ValueError   bounding.py:218-222                */
+    B2N_ERR_ELL_INIT = 5,        /* RuntimeError bounding.py:1451-1453              */
+    B2N_ERR_INVALID_REGION = 6,  /* RuntimeError bounding.py:683-685                */
+    B2N_ERR_Q0 = 7,              /* RuntimeError bounding.py:570-574                */
+    B2N_ERR_SLICE_FAIL = 8,      /* RuntimeError internal_samplers.py:1191-1203     */
+    B2N_ERR_NOMEM = 9,
+    B2N_ERR_UNSUPPORTED = 10,
+    B2N_ERR_TOO_MANY_ELLS = 11   /* max_ells too small for the decomposition        */
+} b2n_status;
+
+/* warning bits (the reference issues warnings.warn at the cited lines) */
+#define B2N_WARN_IDENTITY_FALLBACK 1u /* bounding.py:1373-1378                       */
+#define B2N_WARN_DOUBLING          2u /* internal_samplers.py:694, 839, 1144         */
+#define B2N_WARN_Q0_SLACK          4u /* bounding.py:576-579                         */
+#define B2N_WARN_UNIF_INEFFICIENT  8u /* internal_samplers.py:316-320                */
+
+#define B2N_PTR_HOST   0
+#define B2N_PTR_DEVICE 1
+
+/* per-dimension boundary flags (utils.py:950-976 get_nonbounded) */
+#define B2N_DIM_PERIODIC   1u
+#define B2N_DIM_REFLECTIVE 2u
+
+int  b2n_init(int device, b2n_ctx** ctx);
+void b2n_free(b2n_ctx* ctx);
+int  b2n_set_stream(b2n_ctx* ctx, void* cuda_stream);   /* cudaStream_t; NULL = own stream */
+int  b2n_set_pointer_mode(b2n_ctx* ctx, int mode);
+int  b2n_synchronize(b2n_ctx* ctx);
+const char* b2n_strerror(int status);
+const char* b2n_last_error(b2n_ctx* ctx);
+const char* b2n_version(void);
+/* number of kernel launches issued through this ctx since b2n_init (bench.py gpu_launches) */
+int64_t b2n_launch_count(b2n_ctx* ctx);
+
+/* ---- device models: the "device-side likelihood callback" -----------------
+ * The reference evaluates user Python callables prior_transform(u) and
+ * loglikelihood(v) once per proposal (internal_samplers.py:957-958, 1116-1117,
+ * 328-329).  Inside a kernel that callback is a closed registry:            */
+#define B2N_PRIOR_IDENTITY   0  /* v = u                                          */
+#define B2N_PRIOR_UNIFORM    1  /* v = p0[i] + p1[i]*u   (lo, width)               */
+#define B2N_PRIOR_NORMAL_PPF 2  /* v = p0[i] + p1[i]*ndtri(u)  (mu, sigma)         */
+#define B2N_LIKE_GAUSS_PREC  0  /* -0.5 (v-vec0)^T mat (v-vec0) + s0              */
+#define B2N_LIKE_GAUSS_DIAG  1  /* -0.5 sum vec1[i] (v-vec0)[i]^2 + s0            */
+#define B2N_LIKE_EGGBOX      2  /* (2 + prod cos((2 s0 v - s0)/2))^s1  (tmax, power) */
+#define B2N_LIKE_SHELLS      3  /* logaddexp of two shells: centres vec0, vec1, radius s0, width s1 */
+
+typedef struct {
+    int32_t ndim;
+    int32_t prior_kind;
+    int32_t like_kind;
+    int32_t reserved;
+    const double* prior_p0;  /* host, ndim (or NULL) */
+    const double* prior_p1;  /* host, ndim (or NULL) */
+    const double* like_vec0; /* host, ndim (or NULL) */
+    const double* like_vec1; /* host, ndim (or NULL) */
+    const double* like_mat;  /* host, ndim*ndim symmetric (or NULL) */
+    double like_s0, like_s1, like_s2;
+} b2n_model_desc;
+
+/* copies the parameters to the device; *model_id is a small integer handle. host args. */
+int b2n_model_create(b2n_ctx* ctx, const b2n_model_desc* desc, int32_t* model_id);
+
+/* v = prior_transform(u), logl = loglikelihood(v) for M points (u: M x ndim).
+ * Replaces the pool.map of the two callables in sampler.py:148-158. v may be NULL. */
+int b2n_model_eval(b2n_ctx* ctx, int32_t model_id, const double* u, int64_t M,
+                   double* v, double* logl);
+
+/* ---- ellipsoid membership: MultiEllipsoid.within/overlap/contains
+ *      (bounding.py:502-523), Ellipsoid.distance_many/contains (:286-305) ----
+ * d2[m,k] = (x_m - c_k)^T A_k (x_m - c_k); mask[m,k] = d2 < 1 (strict != 0) or
+ * d2 <= 1 (strict == 0); q[m] = number of ellipsoids containing x_m.
+ * mask / q / d2 may each be NULL. */
+int b2n_membership(b2n_ctx* ctx, const double* x, int64_t M, int32_t n,
+                   const double* ctrs, const double* ams, int32_t K, int32_t strict,
+                   uint8_t* mask, int32_t* q, double* d2);
+
+/* ---- bounding construction ------------------------------------------------
+ * bounding_ellipsoid (bounding.py:1387-1461) incl. improve_covar_mat
+ * (:1311-1384) and the Ellipsoid constructor (:201-240).  Outputs: ctr (n),
+ * cov/am/axes (n x n; axes[:,i] = i-th principal axis scaled by its length,
+ * columns ordered by ascending eigenvalue), axlens (n), logvol (1).
+ * *warn receives B2N_WARN_* bits (host int, may be NULL).  Synchronises. */
+int b2n_bounding_ellipsoid(b2n_ctx* ctx, const double* points, int64_t N, int32_t n,
+                           double* ctr, double* cov, double* am, double* axes,
+                           double* axlens, double* logvol, uint32_t* warn);
+
+/* MultiEllipsoid.update without bootstrap: bounding_ellipsoid + the recursive
+ * 2-means split _bounding_ellipsoids (bounding.py:665-686, 1464-1563) + the
+ * all-points-contained check (:683-685).  labels[N] = index of the leaf
+ * ellipsoid each point was assigned to.  nells: host int out.  Arrays sized
+ * for max_ells.  Synchronises. */
+int b2n_multi_decompose(b2n_ctx* ctx, const double* points, int64_t N, int32_t n,
+                        int32_t max_ells, int32_t* nells, int32_t* labels,
+                        double* ctrs, double* covs, double* ams, double* axes,
+                        double* axlens, double* logvols, uint32_t* warn);
+
+/* Ellipsoid.scale_to_logvol for K ellipsoids (bounding.py:242-276, 478-495).
+ * target_logvols: host, K.  covs/ams/axes/axlens/logvols updated in place. */
+int b2n_scale_to_logvol(b2n_ctx* ctx, int32_t K, int32_t n, double* covs, double* ams,
+                        double* axes, double* axlens, double* logvols,
+                        const double* target_logvols);
+
+/* _ellipsoid_bootstrap_expand for nboot replicas (bounding.py:1593-1648):
+ * replica r resamples with the B2N stream (seed, chain0 + r) (one integers
+ * event, oracle/philox.py), fits in-bag, expand[r] = max(1, max out-of-bag
+ * min-over-ellipsoids distance).  expands: host, nboot.  Synchronises. */
+int b2n_bootstrap_expand(b2n_ctx* ctx, const double* points, int64_t N, int32_t n,
+                         int32_t multi, int32_t nboot, uint64_t seed, uint64_t chain0,
+                         double* expands);
+
+/* ---- resident bound for the proposal kernels --------------------------------
+ * Uploads K ellipsoids of dimension ncdim (what Sampler ships to every task as
+ * `axes` / kwargs['bound'], sampler.py:708-717, internal_samplers.py:229-233).
+ * host pointers in both modes.  ctrs/ams/logvols may be NULL if only
+ * rwalk/slice are used. */
+int b2n_bound_set(b2n_ctx* ctx, int32_t K, int32_t ncdim, const double* ctrs,
+                  const double* ams, const double* axes, const double* logvols);
+
+/* ---- proposal chains ----------------------------------------------------------
+ * One chain per queue slot (sampler.py:690-717).  Chain q consumes the B2N
+ * Philox stream (seed, chain0 + q) -- see oracle/philox.py for the layout. */
+typedef struct {
+    int64_t nchain;          /* Q                                                   */
+    int32_t ndim;            /* n                                                   */
+    int32_t ncdim;           /* clustered dims (axes are ncdim x ncdim)              */
+    int32_t model_id;
+    int32_t reserved;
+    const double* u0;        /* Q x ndim start points (live points with logl > loglstar) */
+    const int32_t* ell;      /* HOST, Q: index into the resident bound of the axes of
+                                each chain (get_random_axes, bounding.py:726-731); NULL = 0 */
+    const uint8_t* dimflags; /* HOST, ndim B2N_DIM_* flags or NULL                      */
+    double loglstar;
+    double scale;
+    uint64_t seed;
+    uint64_t chain0;
+} b2n_chain_args;
+
+/* RWalkSampler.sample -> generic_random_walk (internal_samplers.py:505-561,
+ * 866-986, propose_ball_point :989-1035): exactly `walks` proposals per chain.
+ * Outputs per chain: u, v (Q x ndim), logl, n_accept, n_reject, ncall (Q). */
+int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t walks,
+                    double* u, double* v, double* logl,
+                    int32_t* n_accept, int32_t* n_reject, int32_t* ncall);
+
+/* RSliceSampler.sample (internal_samplers.py:745-855) / SliceSampler.sample
+ * (:593-709) -> generic_slice_step (:1075-1206).  flags[q]: B2N_WARN_DOUBLING if
+ * the chain switched to doubling; status B2N_ERR_SLICE_FAIL if any chain's
+ * interval collapsed. */
+int b2n_rslice_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slices,
+                     int32_t doubling, double* u, double* v, double* logl,
+                     int32_t* n_expand, int32_t* n_contract, int32_t* ncall,
+                     uint32_t* flags);
+int b2n_slice_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slices,
+                    int32_t doubling, double* u, double* v, double* logl,
+                    int32_t* n_expand, int32_t* n_contract, int32_t* ncall,
+                    uint32_t* flags);
+
+/* UniformBoundSampler.sample (internal_samplers.py:243-340) with
+ * MultiEllipsoid.sample (bounding.py:525-590) as the bound draw; u0/ell/scale
+ * unused.  nprop[q] = draws from the bound incl. out-of-cube ones. */
+int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, double* v,
+                   double* logl, int32_t* ncall, int32_t* nprop, uint32_t* flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NEST_H_ */

@@ -1,0 +1,125 @@
+"""GPU: batched rwalk chains vs (a) fixtures produced by the UNMODIFIED reference
+driven with the scripted Philox stream, (b) the oracle on fresh seeded inputs,
+(c) size-independent properties at the BASELINE C2 size.
+
+float64 tolerance: device libm (log, sincospi, pow) and FMA contraction differ
+from numpy/glibc in the last bits, so chain end points are compared at
+rtol 1e-9; accept/reject COUNTS must agree exactly for all but a vanishing
+fraction of chains (a proposal whose logl is within ~1e-13 of loglstar can flip).
+"""
+import numpy as np
+import pytest
+
+from dynesty_b200 import ops
+from helpers import MODELS, device_model, close, SEED
+from oracle import samplers as OS, philox, bounding as OB
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('name', ['g6', 'g6nc', 'wall', 'g50', 'n200'])
+def test_rwalk_golden(golden, name):
+    g = golden['chains']
+    p = 'rwalk_%s_' % name
+    m = MODELS[name]
+    dm = device_model(m)
+    per, ref = g[p + 'periodic'], g[p + 'reflective']
+    flags = ops.dimflags_from(m.ndim, per if len(per) else None, ref if len(ref) else None)
+    ops.bound_set(g[p + 'axes'])
+    o = ops.rwalk_batch(dm.model_id(), g[p + 'u0'], float(g[p + 'loglstar']), float(g[p + 'scale']),
+                        int(g[p + 'walks']), SEED, chain0=int(g[p + 'chain0']),
+                        ncdim=int(g[p + 'ncdim']), dimflags=flags)
+    assert np.array_equal(o['n_accept'], g[p + 'accept'])
+    assert np.array_equal(o['n_reject'], g[p + 'reject'])
+    assert np.array_equal(o['ncall'], g[p + 'ncall'])
+    close(o['u'], g[p + 'u'], rtol=1e-9)
+    close(o['v'], g[p + 'v'], rtol=1e-9)
+    np.testing.assert_allclose(o['logl'], g[p + 'logl'], rtol=1e-9, atol=1e-9)
+
+
+def _cloud(rng, npts, n, spread):
+    C = np.full((n, n), 0.4)
+    np.fill_diagonal(C, 1.0)
+    return 0.5 + spread * rng.standard_normal((npts, n)) @ np.linalg.cholesky(C).T
+
+
+def test_rwalk_vs_oracle_multi_ellipsoid():
+    """Chains spread over K=3 ellipsoids (grouping by ellipsoid must not change results)."""
+    m = MODELS['g6']
+    dm = device_model(m)
+    rng = np.random.default_rng(11)
+    pts = _cloud(rng, 400, 6, 0.06)
+    ells = [OB.bounding_ellipsoid(pts[i::3]) for i in range(3)]
+    axes = np.array([e.axes for e in ells])
+    logl = m.loglike(m.prior_transform(pts))
+    loglstar = float(np.quantile(logl, 0.4))
+    u0 = pts[logl > loglstar][:100]
+    ell = rng.integers(3, size=len(u0)).astype(np.int32)
+    ops.bound_set(axes)
+    o = ops.rwalk_batch(dm.model_id(), u0, loglstar, 0.9, 20, 777, chain0=5000, ell=ell)
+    bad = 0
+    for i in range(len(u0)):
+        r = OS.rwalk_chain(u0[i], loglstar, axes[ell[i]], 0.9, m, philox.ChainStream(777, 5000 + i), 20)
+        if r['n_accept'] != o['n_accept'][i]:
+            bad += 1
+            continue
+        close(o['u'][i], r['u'], rtol=1e-9)
+        assert abs(o['logl'][i] - r['logl']) < 1e-9 * max(1, abs(r['logl']))
+    assert bad == 0
+
+
+def test_rwalk_c2_properties():
+    """BASELINE C2 size (50-D, 2000 chains x 70 walks): size-independent properties."""
+    m = MODELS['g50']
+    dm = device_model(m)
+    rng = np.random.default_rng(5)
+    pts = _cloud(rng, 2000, 50, 0.02)
+    e = OB.bounding_ellipsoid(pts)
+    logl = m.loglike(m.prior_transform(pts))
+    loglstar = float(np.quantile(logl, 0.2))
+    u0 = pts[logl > loglstar]
+    u0 = u0[rng.integers(len(u0), size=2000)]
+    ops.bound_set(e.axes)
+    o = ops.rwalk_batch(dm.model_id(), u0, loglstar, 0.3, 70, SEED, chain0=0)
+    assert np.all(o['ncall'] == 70)
+    assert np.all(o['n_accept'] + o['n_reject'] == 70)
+    assert np.all((o['u'] > 0) & (o['u'] < 1))
+    # every returned point satisfies the constraint and (v, logl) are consistent with u
+    assert np.all(o['logl'] > loglstar)
+    v0 = m.prior_transform(o['u'])
+    close(o['v'], v0, rtol=1e-13)
+    np.testing.assert_allclose(o['logl'], m.loglike(v0), rtol=1e-10)
+    # chains that never accepted stay at their start
+    stay = o['n_accept'] == 0
+    assert np.array_equal(o['u'][stay], u0[stay])
+    assert 0.05 < o['n_accept'].mean() / 70 < 0.95
+    # determinism + independence of the batch composition (counter-based RNG)
+    o2 = ops.rwalk_batch(dm.model_id(), u0[100:200], loglstar, 0.3, 70, SEED, chain0=100)
+    assert np.array_equal(o2['u'], o['u'][100:200])
+    # spot-check 8 chains against the oracle
+    for i in (0, 1, 500, 999, 1000, 1500, 1998, 1999):
+        r = OS.rwalk_chain(u0[i], loglstar, e.axes, 0.3, m, philox.ChainStream(SEED, i), 70)
+        assert r['n_accept'] == o['n_accept'][i]
+        close(o['u'][i], r['u'], rtol=1e-9)
+
+
+def test_rwalk_edge_cases():
+    m = MODELS['g6']
+    dm = device_model(m)
+    ops.bound_set(np.eye(6) * 0.01)
+    # empty batch
+    o = ops.rwalk_batch(dm.model_id(), np.empty((0, 6)), -1e300, 1.0, 5, 1)
+    assert o['u'].shape == (0, 6)
+    # impossible constraint: nothing accepted, start returned with its own logl
+    u0 = np.full((3, 6), 0.5)
+    o = ops.rwalk_batch(dm.model_id(), u0, 1e300, 1.0, 9, 1)
+    assert np.all(o['n_accept'] == 0) and np.all(o['n_reject'] == 9)
+    assert np.array_equal(o['u'], u0)
+    np.testing.assert_allclose(o['logl'], m.loglike(m.prior_transform(u0)), rtol=1e-12)
+    # huge scale: every proposal leaves the cube -> rejects without likelihood calls
+    o = ops.rwalk_batch(dm.model_id(), u0, -1e300, 1e6, 9, 1)
+    assert np.all(o['n_reject'] >= 8)
+    # wrong resident bound dimension is an argument error, not a silent fallback
+    ops.bound_set(np.eye(4))
+    with pytest.raises(ValueError):
+        ops.rwalk_batch(dm.model_id(), u0, 0.0, 1.0, 5, 1)
