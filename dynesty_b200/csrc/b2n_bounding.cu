@@ -1,0 +1,720 @@
+// b2n_bounding.cu -- bounding-ellipsoid construction kernels + entry points.
+//
+//   moments      : mean and ddof=1 covariance of each node (np.mean / np.cov, reference
+//                  bounding.py:1410-1411), two-pass (centered) and deterministic:
+//                  per-job partials reduced in a fixed order, no atomics.
+//   eig_ladder   : parallel cyclic Jacobi eigen-decomposition of the n x n covariance in
+//                  shared memory + the improve_covar_mat repair ladder (:1311-1384) +
+//                  am = V diag(1/l) V^T and axes = V sqrt(l)                (:1353, 1381)
+//   fmax / scale : max_i d_i^T am d_i (:1438) and the (1 - 1e-3) safety rescale (:1444-1450),
+//                  then the Ellipsoid constructor quantities axlens / logvol (:212-217).
+// LAPACK's ?syevr (what scipy.linalg.eigh calls in the reference) is a third-party
+// dependency; Jacobi is used here because it maps onto one CTA with the matrix resident
+// in shared memory and is at least as accurate for SPD matrices.  Eigenvalues come out
+// in ascending order like LAPACK; eigenvector SIGNS are not defined by either.
+#include "b2n_bounding.cuh"
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+// ------------------------------------------------------------------ moments
+struct JobL {   // MomentJob + perm level
+    int node, r0, r1, slot, level, pad0, pad1, pad2;
+};
+
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const double* __restrict__ P, const int* __restrict__ perm,
+                                                             int64_t N, int n, const JobL* __restrict__ jobs,
+                                                             double* __restrict__ partial) {
+    extern __shared__ double sm[];   // 8 x n
+    const JobL jb = jobs[blockIdx.x];
+    const int* pm = perm + (size_t)jb.level * N;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = tx; i < n; i += 32) {
+        double s = 0.0;
+        for (int r = jb.r0 + ty; r < jb.r1; r += 8) s += P[(size_t)pm[r] * n + i];
+        sm[ty * n + i] = s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double s = 0.0;
+        for (int g = 0; g < 8; g++) s += sm[g * n + i];
+        partial[(size_t)jb.slot * n + i] = s;
+    }
+}
+
+__global__ void mean_finalize_kernel(const NodeRef* __restrict__ refs, int n, const double* __restrict__ partial,
+                                     double* __restrict__ mean) {
+    const NodeRef nr = refs[blockIdx.x];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < nr.nslots; k++) s += partial[(size_t)(nr.slot0 + k) * n + i];
+        mean[(size_t)nr.node * n + i] = s / (double)nr.count;
+    }
+}
+
+// C_partial[slot] = sum_{r in job} d_r d_r^T on one 64x64 output tile; 16x16 threads, 4x4
+// register tile each; centred rows staged through shared memory 16 at a time.
+__global__ void __launch_bounds__(256) cov_partial_kernel(const double* __restrict__ P, const int* __restrict__ perm,
+                                                          int64_t N, int n, const JobL* __restrict__ jobs,
+                                                          const double* __restrict__ mean,
+                                                          double* __restrict__ partial, int ntile) {
+    __shared__ double As[B2N_TK][B2N_TILE + 1];
+    __shared__ double Bs[B2N_TK][B2N_TILE + 1];
+    const JobL jb = jobs[blockIdx.x];
+    const int* pm = perm + (size_t)jb.level * N;
+    const double* mu = mean + (size_t)jb.node * n;
+    int ib = 0, jt = blockIdx.y;          // decode upper-triangular tile index
+    while (jt >= ntile - ib) { jt -= ntile - ib; ib++; }
+    const int jbk = ib + jt;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+    for (int k0 = jb.r0; k0 < jb.r1; k0 += B2N_TK) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int idx = threadIdx.x + e * 256;
+            const int kk = idx >> 6, c = idx & 63;
+            const int r = k0 + kk;
+            double a = 0.0, b = 0.0;
+            if (r < jb.r1) {
+                const size_t row = (size_t)pm[r] * n;
+                const int ca = ib * B2N_TILE + c, cb = jbk * B2N_TILE + c;
+                if (ca < n) a = P[row + ca] - mu[ca];
+                if (cb < n) b = P[row + cb] - mu[cb];
+            }
+            As[kk][c] = a;
+            Bs[kk][c] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < B2N_TK; kk++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) { a[t] = As[kk][ty * 4 + t]; b[t] = Bs[kk][tx * 4 + t]; }
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+        }
+        __syncthreads();
+    }
+    double* out = partial + (size_t)jb.slot * n * n;
+#pragma unroll
+    for (int x = 0; x < 4; x++)
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            const int i = ib * B2N_TILE + ty * 4 + x, j = jbk * B2N_TILE + tx * 4 + y;
+            if (i < n && j < n) {
+                out[(size_t)i * n + j] = acc[x][y];
+                if (ib != jbk) out[(size_t)j * n + i] = acc[x][y];
+            }
+        }
+}
+
+__global__ void cov_finalize_kernel(const NodeRef* __restrict__ refs, int n, const double* __restrict__ partial,
+                                    double* __restrict__ covraw) {
+    const NodeRef nr = refs[blockIdx.x];
+    const size_t nn = (size_t)n * n;
+    const double inv = 1.0 / (double)(nr.count - 1);
+    for (size_t e = (size_t)blockIdx.y * blockDim.x + threadIdx.x; e < nn; e += (size_t)gridDim.y * blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < nr.nslots; k++) s += partial[(size_t)(nr.slot0 + k) * nn + e];
+        covraw[(size_t)nr.node * nn + e] = s * inv;
+    }
+}
+
+// ------------------------------------------------------------------ Jacobi eigensolver
+// round-robin pairing: m players (m even), round r in [0, m-1), slot k in [0, m/2)
+__device__ __forceinline__ void rr_pair(int m, int r, int k, int& p, int& q) {
+    int a, b;
+    if (k == 0) { a = m - 1; b = r; }
+    else { a = (r + k) % (m - 1); b = (r - k + (m - 1)) % (m - 1); }
+    p = min(a, b);
+    q = max(a, b);
+}
+
+__device__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < nw; i++) t += red[i];
+    return t;
+}
+
+// In-place: A (n x n, ld) -> diagonal ; VT rows = eigenvectors.  Returns sweeps used.
+__device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* cc, double* ss, double* red) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int m = (n + 1) & ~1, half = m >> 1;
+    int sweep = 0;
+    for (; sweep < 60; sweep++) {
+        double off = 0.0, dg = 0.0;
+        for (int e = tid; e < n * n; e += T) {
+            const int i = e / n, j = e - i * n;
+            const double a = A[(size_t)i * ld + j];
+            if (i == j) dg = fma(a, a, dg); else off = fma(a, a, off);
+        }
+        off = block_sum(off, red);
+        dg = block_sum(dg, red);
+        const double tot = off + dg;
+        if (!(tot < INFINITY) || tot == 0.0) break;      // NaN/Inf or all-zero matrix
+        if (off <= 1e-31 * tot) break;
+        for (int r = 0; r < m - 1; r++) {
+            for (int k = tid; k < half; k += T) {
+                int p, q;
+                rr_pair(m, r, k, p, q);
+                double c = 1.0, s = 0.0;
+                if (q < n) {
+                    const double app = A[(size_t)p * ld + p], aqq = A[(size_t)q * ld + q], apq = A[(size_t)p * ld + q];
+                    if (apq != 0.0 && fabs(apq) > 1e-20 * sqrt(fabs(app * aqq))) {
+                        const double tau = (aqq - app) / (2.0 * apq);
+                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
+                        c = 1.0 / sqrt(fma(t, t, 1.0));
+                        s = t * c;
+                    }
+                }
+                cc[k] = c;
+                ss[k] = s;
+            }
+            __syncthreads();
+            for (int e = tid; e < half * n; e += T) {        // rows p,q of A and of VT
+                const int k = e / n, j = e - k * n;
+                const double s = ss[k];
+                if (s != 0.0) {
+                    int p, q;
+                    rr_pair(m, r, k, p, q);
+                    const double c = cc[k];
+                    double a = A[(size_t)p * ld + j], b = A[(size_t)q * ld + j];
+                    A[(size_t)p * ld + j] = c * a - s * b;
+                    A[(size_t)q * ld + j] = s * a + c * b;
+                    a = VT[(size_t)p * ld + j];
+                    b = VT[(size_t)q * ld + j];
+                    VT[(size_t)p * ld + j] = c * a - s * b;
+                    VT[(size_t)q * ld + j] = s * a + c * b;
+                }
+            }
+            __syncthreads();
+            for (int e = tid; e < half * n; e += T) {        // columns p,q of A
+                const int k = e / n, i = e - k * n;
+                const double s = ss[k];
+                if (s != 0.0) {
+                    int p, q;
+                    rr_pair(m, r, k, p, q);
+                    const double c = cc[k];
+                    const double a = A[(size_t)i * ld + p], b = A[(size_t)i * ld + q];
+                    A[(size_t)i * ld + p] = c * a - s * b;
+                    A[(size_t)i * ld + q] = s * a + c * b;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    return sweep;
+}
+
+// improve_covar_mat (bounding.py:1311-1384) for one node per CTA.
+// pass 0: input = covraw ; pass 1: input = current cov (after the pass-0 rescale).
+__global__ void __launch_bounds__(512) eig_ladder_kernel(NodeArrays na, const int* __restrict__ nodelist, int pass,
+                                                         double* __restrict__ gwork, int use_smem) {
+    extern __shared__ double sm[];
+    const int n = na.n, ld = na.ld, tid = threadIdx.x, T = blockDim.x;
+    const int node = nodelist[blockIdx.x];
+    const size_t nn = (size_t)n * n;
+    double* small = sm;                       // cc[half] ss[half] lamv[n] rank/tmp[n] red[32]
+    const int half = ((n + 1) & ~1) >> 1;
+    double* cc = small;
+    double* ss = cc + half;
+    double* lamv = ss + half;
+    double* tmpv = lamv + n;
+    double* red = tmpv + n;
+    double* A = use_smem ? red + 32 : gwork + (size_t)blockIdx.x * 2 * n * ld;
+    double* VT = A + (size_t)n * ld;
+    __shared__ int s_failed, s_sweeps;
+    __shared__ double s_mx;
+
+    double* Cm = na.cov + (size_t)node * nn;
+    if (pass == 0) {
+        const double* src = na.covraw + (size_t)node * nn;
+        for (size_t e = tid; e < nn; e += T) Cm[e] = src[e];
+    }
+    __syncthreads();
+    int failed = 0, trial = 0;
+    for (trial = 0; trial < 100; trial++) {
+        for (size_t e = tid; e < nn; e += T) {
+            const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+            A[(size_t)i * ld + j] = Cm[e];
+            VT[(size_t)i * ld + j] = (i == j) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        const int sw = jacobi_eig(A, VT, n, ld, cc, ss, red);
+        for (int k = tid; k < n; k += T) lamv[k] = A[(size_t)k * ld + k];
+        __syncthreads();
+        if (tid == 0) {
+            bool fin = true;
+            double mx = -INFINITY, mn = INFINITY;
+            for (int k = 0; k < n; k++) {
+                const double l = lamv[k];
+                fin = fin && (l == l) && (fabs(l) < INFINITY);
+                mx = fmax(mx, l);
+                mn = fmin(mn, l);
+            }
+            int f = 0;
+            if (!fin) f = 2;
+            else if (mx <= 0) f = 2;
+            else if (mn < mx / 1e12) f = 1;
+            s_failed = f;
+            s_mx = mx;
+            s_sweeps = sw;
+        }
+        __syncthreads();
+        failed = s_failed;
+        if (failed == 0) break;
+        if (failed == 1) {
+            const double floorv = 10.0 * s_mx / 1e12;
+            for (int k = tid; k < n; k += T) tmpv[k] = fmax(lamv[k], floorv);
+            __syncthreads();
+            for (size_t e = tid; e < nn; e += T) {
+                const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+                double s = 0.0;
+                for (int k = 0; k < n; k++) s = fma(VT[(size_t)k * ld + i] * tmpv[k], VT[(size_t)k * ld + j], s);
+                Cm[e] = s;
+            }
+        } else {
+            const double coeff = 1e-10 * pow(1e10, (double)trial / 99.0);
+            for (size_t e = tid; e < nn; e += T) {
+                const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+                Cm[e] = (1.0 - coeff) * Cm[e] + ((i == j) ? coeff : 0.0);
+            }
+        }
+        __syncthreads();
+    }
+    double* AM = na.am + (size_t)node * nn;
+    double* AX = na.axes + (size_t)node * nn;
+    double* LM = na.lam + (size_t)node * n;
+    NodeStat* st = na.stat + node;
+    if (failed > 0) {               // identity fallback (:1373-1378)
+        for (size_t e = tid; e < nn; e += T) {
+            const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+            const double v = (i == j) ? 1.0 : 0.0;
+            Cm[e] = v; AM[e] = v; AX[e] = v;
+        }
+        for (int k = tid; k < n; k += T) LM[k] = 1.0;
+        if (tid == 0) { st->good = 0; st->fallback = 1; st->sweeps = s_sweeps; }
+        return;
+    }
+    // rank-sort eigenvalues ascending (LAPACK order); tmpv[k] = rank of eigenpair k
+    for (int k = tid; k < n; k += T) {
+        const double l = lamv[k];
+        int rk = 0;
+        for (int j = 0; j < n; j++) rk += (lamv[j] < l || (lamv[j] == l && j < k)) ? 1 : 0;
+        tmpv[k] = (double)rk;
+        LM[rk] = l;
+    }
+    __syncthreads();
+    for (size_t e = tid; e < nn; e += T) {
+        const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+        double s = 0.0;
+        for (int k = 0; k < n; k++) s = fma(VT[(size_t)k * ld + i] / lamv[k], VT[(size_t)k * ld + j], s);
+        AM[e] = s;
+        // here j plays the role of the eigen index: axes[i][rank_j] = V[i][j] sqrt(l_j)
+        AX[(size_t)i * n + (int)tmpv[j]] = VT[(size_t)j * ld + i] * sqrt(lamv[j]);
+    }
+    if (tid == 0) {
+        if (pass == 0) st->good = (trial == 0) ? 1 : 0;
+        st->fallback = 0;
+        st->sweeps = s_sweeps;
+    }
+}
+
+// ------------------------------------------------------------------ fmax + rescale + finish
+__global__ void __launch_bounds__(256) fmax_partial_kernel(const double* __restrict__ P, const int* __restrict__ perm,
+                                                           int64_t N, NodeArrays na, const JobL* __restrict__ jobs,
+                                                           double* __restrict__ partial) {
+    extern __shared__ double sm[];     // 8 warps x n
+    __shared__ double wmax[8];
+    const int n = na.n;
+    const JobL jb = jobs[blockIdx.x];
+    const int* pm = perm + (size_t)jb.level * N;
+    const double* mu = na.mean + (size_t)jb.node * n;
+    const double* AM = na.am + (size_t)jb.node * n * n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* d = sm + (size_t)warp * n;
+    double best = -INFINITY;
+    for (int r = jb.r0 + warp; r < jb.r1; r += 8) {
+        const size_t row = (size_t)pm[r] * n;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) d[i] = P[row + i] - mu[i];
+        __syncwarp();
+        double s = 0.0;
+        for (int base = 0; base < n; base += 64) {
+            double y0, y1;
+            warp_matvec2(AM, n, n, d, base + lane, n, y0, y1);
+            if (base + lane < n) s = fma(d[base + lane], y0, s);
+            if (base + lane + 32 < n) s = fma(d[base + lane + 32], y1, s);
+        }
+        s = warp_sum(s);
+        best = fmax(best, s);
+    }
+    if (lane == 0) wmax[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double b = wmax[0];
+        for (int w = 1; w < 8; w++) b = fmax(b, wmax[w]);
+        partial[jb.slot] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256) scale_finish_kernel(NodeArrays na, const NodeRef* __restrict__ refs,
+                                                           const double* __restrict__ partial, int pass,
+                                                           double logvol_pref) {
+    __shared__ double s_mult;
+    __shared__ double red[32];
+    const int n = na.n, tid = threadIdx.x, T = blockDim.x;
+    const NodeRef nr = refs[blockIdx.x];
+    const size_t nn = (size_t)n * n;
+    NodeStat* st = na.stat + nr.node;
+    if (tid == 0) {
+        double fm = -INFINITY;
+        for (int k = 0; k < nr.nslots; k++) fm = fmax(fm, partial[nr.slot0 + k]);
+        st->fmax = fm;
+        double mult = 1.0;
+        if (pass == 0) {
+            if (fm > 1.0 - 1e-3) mult = fm / (1.0 - 1e-3);
+            st->mult = mult;
+            st->error = 0;
+        } else if (fm >= 1.0) {
+            st->error = B2N_ERR_ELL_INIT;
+        }
+        s_mult = mult;
+    }
+    __syncthreads();
+    const double mult = s_mult;
+    double* Cm = na.cov + (size_t)nr.node * nn;
+    double* AM = na.am + (size_t)nr.node * nn;
+    double* AX = na.axes + (size_t)nr.node * nn;
+    double* LM = na.lam + (size_t)nr.node * n;
+    if (mult != 1.0) {
+        const double sq = sqrt(mult);
+        for (size_t e = tid; e < nn; e += T) { Cm[e] *= mult; AM[e] /= mult; AX[e] *= sq; }
+        for (int k = tid; k < n; k += T) LM[k] *= mult;
+    }
+    __syncthreads();
+    // Ellipsoid.__init__ (:212-222): axlens, logvol, singularity check
+    double part = 0.0;
+    int bad = 0;
+    for (int k = tid; k < n; k += T) {
+        const double l = LM[k];
+        if (!(l > 0.0) || !(l < INFINITY)) bad = 1;
+        na.axlens[(size_t)nr.node * n + k] = sqrt(l);
+        part += log(l);
+    }
+    const double tot = block_sum(part, red);
+    const double nbad = block_sum((double)bad, red);
+    if (tid == 0) {
+        st->logvol = logvol_pref + 0.5 * tot;
+        if (nbad > 0 && st->error == 0) st->error = B2N_ERR_SINGULAR;
+    }
+}
+
+// ------------------------------------------------------------------ host orchestration
+
+static double logvol_prefactor(int n) {   // bounding.py:1271-1285 (p = 2)
+    return n * log(2.0) + n * lgamma(1.5) - lgamma(n / 2.0 + 1.0);
+}
+
+static size_t align8(size_t x) { return (x + 7) & ~(size_t)7; }
+
+int b2n_boundwork_init(b2n_ctx* ctx, BoundWork& w, const double* dP, int64_t N, int n, int cap) {
+    w.ctx = ctx; w.P = dP; w.N = N; w.n = n; w.cap = cap;
+    w.logvol_pref = logvol_prefactor(n);
+    const size_t nn = (size_t)n * n;
+    size_t bytes = 0;
+    const size_t o_mean = bytes; bytes += align8((size_t)cap * n * sizeof(double));
+    const size_t o_covraw = bytes; bytes += (size_t)cap * nn * sizeof(double);
+    const size_t o_cov = bytes; bytes += (size_t)cap * nn * sizeof(double);
+    const size_t o_am = bytes; bytes += (size_t)cap * nn * sizeof(double);
+    const size_t o_axes = bytes; bytes += (size_t)cap * nn * sizeof(double);
+    const size_t o_lam = bytes; bytes += align8((size_t)cap * n * sizeof(double));
+    const size_t o_axl = bytes; bytes += align8((size_t)cap * n * sizeof(double));
+    const size_t o_stat = bytes; bytes += align8((size_t)cap * sizeof(NodeStat));
+    B2N_CUDA(ctx, ctx->scratch0.ensure(bytes));
+    char* b = ctx->scratch0.as<char>();
+    w.na.n = n;
+    w.na.ld = n | 1;
+    w.na.mean = (double*)(b + o_mean); w.na.covraw = (double*)(b + o_covraw);
+    w.na.cov = (double*)(b + o_cov); w.na.am = (double*)(b + o_am); w.na.axes = (double*)(b + o_axes);
+    w.na.lam = (double*)(b + o_lam); w.na.axlens = (double*)(b + o_axl); w.na.stat = (NodeStat*)(b + o_stat);
+    B2N_CUDA(ctx, ctx->scratch3.ensure((size_t)2 * N * sizeof(int)));
+    w.perm = ctx->scratch3.as<int>();
+    return B2N_OK;
+}
+
+// Full bounding_ellipsoid (bounding.py:1387-1461) for every node in `refs`.
+// On return `stats` holds the per-node NodeStat (host copy); the stream is synchronised.
+int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::vector<NodeStat>& stats) {
+    b2n_ctx* ctx = w.ctx;
+    const int n = w.n;
+    const size_t nn = (size_t)n * n;
+    std::vector<NodeRef> refs = refs_in;
+    std::vector<JobL> jobs;
+    int slot = 0;
+    for (auto& r : refs) {
+        r.slot0 = slot;
+        for (int a = r.start; a < r.start + r.count; a += B2N_ROWS_PER_JOB) {
+            JobL j;
+            memset(&j, 0, sizeof(j));
+            j.node = r.node; j.r0 = a; j.r1 = std::min(a + B2N_ROWS_PER_JOB, r.start + r.count);
+            j.slot = slot++; j.level = r.level;
+            jobs.push_back(j);
+        }
+        r.nslots = slot - r.slot0;
+    }
+    const int nnodes = (int)refs.size(), njobs = (int)jobs.size();
+    if (nnodes == 0) return B2N_OK;
+    std::vector<int> nodelist(nnodes);
+    for (int i = 0; i < nnodes; i++) nodelist[i] = refs[i].node;
+
+    const void *djobs, *drefs, *dlist;
+    B2N_TRY(b2n_in_host(ctx, ctx->scratch4, jobs.data(), jobs.size() * sizeof(JobL), &djobs));
+    B2N_TRY(b2n_in_host(ctx, ctx->scratch5, refs.data(), refs.size() * sizeof(NodeRef), &drefs));
+    B2N_TRY(b2n_in_host(ctx, ctx->work0, nodelist.data(), nodelist.size() * sizeof(int), &dlist));
+    B2N_CUDA(ctx, ctx->scratch1.ensure((size_t)njobs * std::max(nn, (size_t)n) * sizeof(double)));
+    double* partial = ctx->scratch1.as<double>();
+    cudaStream_t st = ctx->stream;
+
+    // moments
+    colsum_partial_kernel<<<njobs, 256, (size_t)8 * n * sizeof(double), st>>>(w.P, w.perm, w.N, n, (const JobL*)djobs, partial);
+    B2N_LAUNCH_CHECK(ctx);
+    mean_finalize_kernel<<<nnodes, 128, 0, st>>>((const NodeRef*)drefs, n, partial, w.na.mean);
+    B2N_LAUNCH_CHECK(ctx);
+    const int ntile = (n + B2N_TILE - 1) / B2N_TILE;
+    cov_partial_kernel<<<dim3(njobs, ntile * (ntile + 1) / 2), 256, 0, st>>>(w.P, w.perm, w.N, n, (const JobL*)djobs,
+                                                                            w.na.mean, partial, ntile);
+    B2N_LAUNCH_CHECK(ctx);
+    cov_finalize_kernel<<<dim3(nnodes, (unsigned)std::min<size_t>((nn + 255) / 256, 64)), 256, 0, st>>>(
+        (const NodeRef*)drefs, n, partial, w.na.covraw);
+    B2N_LAUNCH_CHECK(ctx);
+
+    // eigen + ladder
+    const int ld = w.na.ld, half = ((n + 1) & ~1) / 2;
+    const size_t small_b = (size_t)(2 * half + 2 * n + 32) * sizeof(double);
+    const size_t mats_b = (size_t)2 * n * ld * sizeof(double);
+    const int use_smem = small_b + mats_b <= (size_t)ctx->max_smem_optin ? 1 : 0;
+    const size_t eig_smem = small_b + (use_smem ? mats_b : 0);
+    double* gwork = nullptr;
+    if (!use_smem) {
+        B2N_CUDA(ctx, ctx->scratch2.ensure((size_t)nnodes * mats_b));
+        gwork = ctx->scratch2.as<double>();
+    }
+    B2N_CUDA(ctx, cudaFuncSetAttribute(eig_ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem));
+    const int eig_threads = n <= 16 ? 64 : (n <= 48 ? 256 : 512);
+    const size_t fm_smem = (size_t)8 * n * sizeof(double);
+
+    std::vector<NodeStat> hs(nnodes);
+    for (int pass = 0; pass < 2; pass++) {
+        const void* plist = dlist;
+        const void* prefs = drefs;
+        const void* pjobs = djobs;
+        int pn = nnodes, pj = njobs;
+        std::vector<NodeRef> refs2;
+        std::vector<JobL> jobs2;
+        std::vector<int> list2;
+        if (pass == 1) {
+            // second pass only for nodes whose matrix needed repair (:1454-1457)
+            int s2 = 0;
+            for (int i = 0; i < nnodes; i++) {
+                if (hs[i].good || hs[i].error) continue;
+                NodeRef r = refs[i];
+                r.slot0 = s2;
+                for (int a = r.start; a < r.start + r.count; a += B2N_ROWS_PER_JOB) {
+                    JobL j;
+                    memset(&j, 0, sizeof(j));
+                    j.node = r.node; j.r0 = a; j.r1 = std::min(a + B2N_ROWS_PER_JOB, r.start + r.count);
+                    j.slot = s2++; j.level = r.level;
+                    jobs2.push_back(j);
+                }
+                r.nslots = s2 - r.slot0;
+                refs2.push_back(r);
+                list2.push_back(r.node);
+            }
+            if (refs2.empty()) break;
+            B2N_TRY(b2n_in_host(ctx, ctx->scratch4, jobs2.data(), jobs2.size() * sizeof(JobL), &pjobs));
+            B2N_TRY(b2n_in_host(ctx, ctx->scratch5, refs2.data(), refs2.size() * sizeof(NodeRef), &prefs));
+            B2N_TRY(b2n_in_host(ctx, ctx->work0, list2.data(), list2.size() * sizeof(int), &plist));
+            pn = (int)refs2.size();
+            pj = (int)jobs2.size();
+        }
+        eig_ladder_kernel<<<pn, eig_threads, eig_smem, st>>>(w.na, (const int*)plist, pass, gwork, use_smem);
+        B2N_LAUNCH_CHECK(ctx);
+        fmax_partial_kernel<<<pj, 256, fm_smem, st>>>(w.P, w.perm, w.N, w.na, (const JobL*)pjobs, partial);
+        B2N_LAUNCH_CHECK(ctx);
+        scale_finish_kernel<<<pn, 256, 0, st>>>(w.na, (const NodeRef*)prefs, partial, pass, w.logvol_pref);
+        B2N_LAUNCH_CHECK(ctx);
+        // read back the node stats (one copy of the whole small array)
+        B2N_CUDA(ctx, cudaStreamSynchronize(st));
+        std::vector<NodeStat> all(w.cap);
+        B2N_CUDA(ctx, cudaMemcpy(all.data(), w.na.stat, (size_t)w.cap * sizeof(NodeStat), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < nnodes; i++) {
+            if (pass == 1 && (hs[i].good || hs[i].error)) continue;
+            hs[i] = all[refs[i].node];
+        }
+    }
+    stats = hs;
+    return B2N_OK;
+}
+
+static int init_identity_perm(BoundWork& w) {
+    std::vector<int> id(w.N);
+    for (int64_t i = 0; i < w.N; i++) id[i] = (int)i;
+    B2N_CUDA(w.ctx, cudaMemcpyAsync(w.perm, id.data(), w.N * sizeof(int), cudaMemcpyHostToDevice, w.ctx->stream));
+    return B2N_OK;
+}
+
+// copy node `node` arrays to caller outputs (device or host according to pointer mode)
+static int emit_node(BoundWork& w, int node, int k, double* ctr, double* cov, double* am, double* axes,
+                     double* axlens) {
+    b2n_ctx* ctx = w.ctx;
+    const size_t n = w.n, nn = n * n;
+    const cudaMemcpyKind kind = ctx->ptr_mode == B2N_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (ctr) B2N_CUDA(ctx, cudaMemcpyAsync(ctr + k * n, w.na.mean + node * n, n * sizeof(double), kind, ctx->stream));
+    if (cov) B2N_CUDA(ctx, cudaMemcpyAsync(cov + k * nn, w.na.cov + node * nn, nn * sizeof(double), kind, ctx->stream));
+    if (am) B2N_CUDA(ctx, cudaMemcpyAsync(am + k * nn, w.na.am + node * nn, nn * sizeof(double), kind, ctx->stream));
+    if (axes) B2N_CUDA(ctx, cudaMemcpyAsync(axes + k * nn, w.na.axes + node * nn, nn * sizeof(double), kind, ctx->stream));
+    if (axlens) B2N_CUDA(ctx, cudaMemcpyAsync(axlens + k * n, w.na.axlens + node * n, n * sizeof(double), kind, ctx->stream));
+    return B2N_OK;
+}
+
+int b2n_emit_node(BoundWork& w, int node, int k, double* ctr, double* cov, double* am, double* axes, double* axlens) {
+    return emit_node(w, node, k, ctr, cov, am, axes, axlens);
+}
+int b2n_init_identity_perm(BoundWork& w) { return init_identity_perm(w); }
+
+extern "C" int b2n_bounding_ellipsoid(b2n_ctx* ctx, const double* points, int64_t N, int32_t n, double* ctr,
+                                      double* cov, double* am, double* axes, double* axlens, double* logvol,
+                                      uint32_t* warn) {
+    if (!ctx || !points || N < 1 || n < 1) return B2N_ERR_ARG;
+    if (N == 1) return B2N_ERR_SINGLE_POINT;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* dP;
+    B2N_TRY(b2n_in(ctx, ctx->in0, points, (size_t)N * n * sizeof(double), &dP));
+    BoundWork w;
+    B2N_TRY(b2n_boundwork_init(ctx, w, (const double*)dP, N, n, 1));
+    B2N_TRY(init_identity_perm(w));
+    std::vector<NodeRef> refs(1);
+    memset(&refs[0], 0, sizeof(NodeRef));
+    refs[0].node = 0; refs[0].start = 0; refs[0].count = (int)N; refs[0].level = 0;
+    std::vector<NodeStat> hs;
+    B2N_TRY(b2n_process_nodes(w, refs, hs));
+    if (warn) *warn = hs[0].fallback ? B2N_WARN_IDENTITY_FALLBACK : 0u;
+    if (hs[0].error) return hs[0].error;
+    B2N_TRY(emit_node(w, 0, 0, ctr, cov, am, axes, axlens));
+    if (logvol) {
+        if (ctx->ptr_mode == B2N_PTR_DEVICE)
+            B2N_CUDA(ctx, cudaMemcpyAsync(logvol, &hs[0].logvol, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        else
+            *logvol = hs[0].logvol;
+    }
+    B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B2N_OK;
+}
+
+// ------------------------------------------------------------------ scale_to_logvol
+// Ellipsoid.scale_to_logvol (bounding.py:242-276); one CTA per ellipsoid.
+__global__ void __launch_bounds__(256) scale_to_logvol_kernel(int n, double* __restrict__ covs, double* __restrict__ ams,
+                                                              double* __restrict__ axes, double* __restrict__ axlens,
+                                                              double* __restrict__ logvols,
+                                                              const double* __restrict__ targets) {
+    extern __shared__ double sm[];     // fax[n], lam[n], order[n]
+    double* fax = sm;
+    double* lam = fax + n;
+    int* order = reinterpret_cast<int*>(lam + n);
+    __shared__ int s_iso;
+    __shared__ double s_f;
+    const int k = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const size_t nn = (size_t)n * n;
+    double* Cm = covs + k * nn;
+    double* AM = ams + k * nn;
+    double* AX = axes + k * nn;
+    double* AL = axlens + (size_t)k * n;
+    const double logf = targets[k] - logvols[k];
+    const double max_log_axlen = log(sqrt((double)n) / 2.0);
+    if (tid == 0) {
+        double mx = -INFINITY;
+        for (int i = 0; i < n; i++) mx = fmax(mx, log(AL[i]));
+        s_iso = (mx < max_log_axlen - logf / n) ? 1 : 0;
+        s_f = exp(logf / n);
+    }
+    for (int i = tid; i < n; i += T) lam[i] = AL[i] * AL[i];
+    __syncthreads();
+    if (s_iso) {
+        const double f = s_f, f2 = f * f, if2 = 1.0 / f2;
+        for (size_t e = tid; e < nn; e += T) { Cm[e] *= f2; AM[e] *= if2; AX[e] *= f; }
+        for (int i = tid; i < n; i += T) AL[i] *= f;
+    } else {
+        // water-filling from the largest eigenvalue down (:258-275)
+        for (int i = tid; i < n; i += T) {
+            int rk = 0;   // rank in DESCENDING eigenvalue order (np.argsort(l)[::-1])
+            for (int j = 0; j < n; j++) rk += (lam[j] > lam[i] || (lam[j] == lam[i] && j > i)) ? 1 : 0;
+            order[rk] = i;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double cur = logf;
+            int left = n;
+            for (int r = 0; r < n; r++) {
+                const int i = order[r];
+                const double delta = fmax(fmin(max_log_axlen - log(AL[i]), cur / left), 0.0);
+                fax[i] = exp(delta);
+                cur -= delta;
+                left -= 1;
+            }
+        }
+        __syncthreads();
+        // cov = sum_k a_k a_k^T fax_k^2 ; am = sum_k a_k a_k^T / (lam_k^2 fax_k^2),  a_k = axes[:,k]
+        for (size_t e = tid; e < nn; e += T) {
+            const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+            double c = 0.0, a = 0.0;
+            for (int q = 0; q < n; q++) {
+                const double pr = AX[(size_t)i * n + q] * AX[(size_t)j * n + q];
+                const double f2 = fax[q] * fax[q];
+                c = fma(pr, f2, c);
+                a = fma(pr, 1.0 / (lam[q] * lam[q] * f2), a);
+            }
+            Cm[e] = c;
+            AM[e] = a;
+        }
+        __syncthreads();
+        for (size_t e = tid; e < nn; e += T) AX[e] *= fax[e % n];
+        for (int i = tid; i < n; i += T) AL[i] *= fax[i];
+    }
+    if (tid == 0) logvols[k] = targets[k];
+}
+
+extern "C" int b2n_scale_to_logvol(b2n_ctx* ctx, int32_t K, int32_t n, double* covs, double* ams, double* axes,
+                                   double* axlens, double* logvols, const double* targets) {
+    if (!ctx || K < 1 || n < 1 || !covs || !ams || !axes || !axlens || !logvols || !targets) return B2N_ERR_ARG;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nn = (size_t)n * n;
+    const void *ci, *ai, *xi, *li, *vi, *ti;
+    B2N_TRY(b2n_in(ctx, ctx->out0, covs, K * nn * sizeof(double), &ci));
+    B2N_TRY(b2n_in(ctx, ctx->out1, ams, K * nn * sizeof(double), &ai));
+    B2N_TRY(b2n_in(ctx, ctx->out2, axes, K * nn * sizeof(double), &xi));
+    B2N_TRY(b2n_in(ctx, ctx->out3, axlens, (size_t)K * n * sizeof(double), &li));
+    B2N_TRY(b2n_in(ctx, ctx->out4, logvols, (size_t)K * sizeof(double), &vi));
+    B2N_TRY(b2n_in_host(ctx, ctx->in3, targets, (size_t)K * sizeof(double), &ti));
+    const size_t smem = (size_t)(3 * n + 2) * sizeof(double);
+    scale_to_logvol_kernel<<<K, 256, smem, ctx->stream>>>(n, (double*)ci, (double*)ai, (double*)xi, (double*)li,
+                                                          (double*)vi, (const double*)ti);
+    B2N_LAUNCH_CHECK(ctx);
+    B2N_TRY(b2n_out_done(ctx, covs, ci, K * nn * sizeof(double)));
+    B2N_TRY(b2n_out_done(ctx, ams, ai, K * nn * sizeof(double)));
+    B2N_TRY(b2n_out_done(ctx, axes, xi, K * nn * sizeof(double)));
+    B2N_TRY(b2n_out_done(ctx, axlens, li, (size_t)K * n * sizeof(double)));
+    B2N_TRY(b2n_out_done(ctx, logvols, vi, (size_t)K * sizeof(double)));
+    return b2n_finish(ctx);
+}

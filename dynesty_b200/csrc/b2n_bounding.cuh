@@ -1,0 +1,70 @@
+// b2n_bounding.cuh -- node-batched bounding-ellipsoid construction (shared by the
+// single-ellipsoid, multi-ellipsoid and bootstrap entry points).
+//
+// A "node" is a subset of the live points: a contiguous segment [start, start+count)
+// of an index array `perm` into the (N, n) row-major point block.  All kernels take
+// a list of nodes so that the siblings of one recursion level of
+// _bounding_ellipsoids (reference bounding.py:1464-1563) are processed by ONE
+// launch per stage.
+#pragma once
+#include "b2n_device.cuh"
+
+#define B2N_ROWS_PER_JOB 512     // rows of a node handled by one moment / fmax job
+#define B2N_TILE 64              // covariance output tile edge
+#define B2N_TK 16                // rows per shared-memory stage of the covariance kernel
+
+struct NodeStat {
+    int good;        // improve_covar_mat returned good_mat (trial == 0)   bounding.py:1382
+    int fallback;    // identity fallback taken                              bounding.py:1373-1378
+    int error;       // b2n_status for this node (0 ok)
+    int sweeps;      // Jacobi sweeps of the last decomposition (diagnostic)
+    double fmax;     // max_i delta_i^T am delta_i                           bounding.py:1438
+    double mult;     // covariance scaling applied after pass 0              bounding.py:1444-1450
+    double logvol;
+};
+
+struct MomentJob {   // one CTA-sized slice of one node
+    int node;        // index into the node arrays
+    int r0, r1;      // rows [r0, r1) of perm
+    int slot;        // partial-result slot
+};
+
+struct NodeRef {     // per-node view used by finalize kernels
+    int node;
+    int start, count;
+    int slot0, nslots;
+    int level;       // which perm buffer holds this node's indices
+};
+
+// Node-indexed device arrays (capacity `cap` nodes)
+struct NodeArrays {
+    int n, ld;               // dimension, leading dim of the eigen workspaces
+    double* mean;            // cap x n
+    double* covraw;          // cap x n x n   sample covariance (ddof = 1)
+    double* cov;             // cap x n x n   "safe" covariance (after ladder + scaling)
+    double* am;              // cap x n x n   precision
+    double* axes;            // cap x n x n   axes[i][k] = V[i][k] * sqrt(lam_k), ascending lam
+    double* lam;             // cap x n       eigenvalues of cov, ascending
+    double* axlens;          // cap x n
+    NodeStat* stat;          // cap
+};
+
+struct BoundWork {
+    b2n_ctx* ctx;
+    const double* P;     // device points (N x n)
+    int64_t N;
+    int n, cap;
+    NodeArrays na;
+    int* perm;           // 2 x N ping-pong index buffers ("levels" 0 / 1)
+    double logvol_pref;
+};
+#ifdef __cplusplus
+#include <vector>
+int b2n_boundwork_init(b2n_ctx* ctx, BoundWork& w, const double* dP, int64_t N, int n, int cap);
+int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs, std::vector<NodeStat>& stats);
+int b2n_emit_node(BoundWork& w, int node, int k, double* ctr, double* cov, double* am, double* axes, double* axlens);
+int b2n_init_identity_perm(BoundWork& w);
+#endif
+
+int b2n_membership_dev(b2n_ctx* ctx, const double* x, int64_t M, int n, const double* ctrs,
+                       const double* ams, int K, int strict, uint8_t* mask, int* q, double* d2);

@@ -2,10 +2,6 @@
 // return B2N_ERR_UNSUPPORTED (loud failure, never a CPU fallback).
 #include "b2n_common.cuh"
 extern "C" {
-int b2n_bounding_ellipsoid(b2n_ctx*, const double*, int64_t, int32_t, double*, double*, double*, double*, double*, double*, uint32_t*) { return B2N_ERR_UNSUPPORTED; }
-int b2n_multi_decompose(b2n_ctx*, const double*, int64_t, int32_t, int32_t, int32_t*, int32_t*, double*, double*, double*, double*, double*, double*, uint32_t*) { return B2N_ERR_UNSUPPORTED; }
-int b2n_scale_to_logvol(b2n_ctx*, int32_t, int32_t, double*, double*, double*, double*, double*, const double*) { return B2N_ERR_UNSUPPORTED; }
-int b2n_bootstrap_expand(b2n_ctx*, const double*, int64_t, int32_t, int32_t, int32_t, uint64_t, uint64_t, double*) { return B2N_ERR_UNSUPPORTED; }
 int b2n_rslice_batch(b2n_ctx*, const b2n_chain_args*, int32_t, int32_t, double*, double*, double*, int32_t*, int32_t*, int32_t*, uint32_t*) { return B2N_ERR_UNSUPPORTED; }
 int b2n_slice_batch(b2n_ctx*, const b2n_chain_args*, int32_t, int32_t, double*, double*, double*, int32_t*, int32_t*, int32_t*, uint32_t*) { return B2N_ERR_UNSUPPORTED; }
 int b2n_unif_batch(b2n_ctx*, const b2n_chain_args*, double*, double*, double*, int32_t*, int32_t*, uint32_t*) { return B2N_ERR_UNSUPPORTED; }

@@ -1,0 +1,142 @@
+"""GPU: bounding-ellipsoid construction / decomposition vs fixtures produced by the
+UNMODIFIED reference (tests/golden, oracle/make_golden.py) and vs the oracle.
+
+float64 tolerances (stated): the reference uses LAPACK eigh, the CUDA path a cyclic
+Jacobi solver -> eigenvector signs / order in degenerate subspaces are not comparable;
+sign-invariant quantities are compared: ctr, cov, logvol 1e-9; am 1e-7 (am carries the
+condition number); axes through axes @ axes.T = cov and sorted axis lengths."""
+import numpy as np
+import pytest
+
+from dynesty_b200 import ops
+from helpers import close, SEED
+from oracle import bounding as OB, philox
+
+pytestmark = pytest.mark.gpu
+
+
+def check_ell(o, g, p, am_rtol=1e-7):
+    close(o['ctr'], g[p + 'ctr'])
+    close(o['cov'], g[p + 'cov'])
+    close(o['am'], g[p + 'am'], rtol=am_rtol)
+    close(o['axes'] @ o['axes'].T, g[p + 'cov'])
+    close(np.sort(o['axlens']), np.sort(g[p + 'axlens']))
+    assert abs(o['logvol'] - float(g[p + 'logvol'])) < 1e-8
+    # internal consistency of the CUDA eigen-decomposition
+    close(o['cov'] @ o['am'], np.eye(len(o['ctr'])), rtol=1e-6)
+    assert np.all(np.diff(o['axlens']) >= 0)           # ascending like LAPACK
+    close(np.linalg.norm(o['axes'], axis=0), o['axlens'])
+
+
+@pytest.mark.parametrize('name', ['g20', 'g3', 'g50', 'few', 'illcond'])
+def test_bounding_ellipsoid_golden(golden, name):
+    g = golden['bounding']
+    pts = g['be_%s_points' % name]
+    o = ops.bounding_ellipsoid(pts)
+    check_ell(o, g, 'be_%s_' % name, am_rtol=1e-6 if name == 'illcond' else 1e-7)
+    d2 = ops.membership(pts, o['ctr'], o['am'], want_d2=True)[2]
+    assert d2.max() < 1                                  # bounding.py:1438-1453
+    assert o['warn'] == 0
+
+
+def test_bounding_rank_deficient(golden):
+    """tests/test_ellipsoid.py:258-264 (test_bounding_crazy): must not raise and must
+    still bound every point; ndim 1, 10, 100."""
+    g = golden['bounding']
+    pts = g['be_rank1_points']
+    o = ops.bounding_ellipsoid(pts)
+    assert ops.membership(pts, o['ctr'], o['am'], want_d2=True)[2].max() < 1
+    assert np.all(np.linalg.eigvalsh(o['cov']) > 0)
+    close(np.sort(o['axlens'])[-1], np.sort(g['be_rank1_axlens'])[-1], rtol=1e-6)
+    rng = np.random.default_rng(1)
+    for ndim in (1, 10, 100):
+        x = rng.random(200)
+        p = 0.5 + (x[:, None] - 0.5) * np.ones((1, ndim)) * 0.2
+        o = ops.bounding_ellipsoid(p)
+        assert ops.membership(p, o['ctr'], o['am'], want_d2=True)[2].max() < 1
+
+
+def test_bounding_errors():
+    with pytest.raises(ValueError):                       # bounding.py:1405-1407
+        ops.bounding_ellipsoid(np.full((1, 3), 0.5))
+    with pytest.raises(ValueError):
+        ops.multi_decompose(np.full((1, 3), 0.5))
+
+
+@pytest.mark.parametrize('N,n', [(2000, 50), (8000, 200), (500, 3), (64, 2)])
+def test_bounding_vs_oracle_sizes(N, n):
+    """BASELINE sizes (C2 2000x50, C4 8000x200): compared with the oracle directly."""
+    rng = np.random.default_rng(N + n)
+    A = rng.standard_normal((n, n)) / np.sqrt(n)
+    pts = 0.5 + 0.05 * rng.standard_normal((N, n)) @ (np.eye(n) + 0.5 * A)
+    o = ops.bounding_ellipsoid(pts)
+    e = OB.bounding_ellipsoid(pts)
+    close(o['ctr'], e.ctr, rtol=1e-12)
+    close(o['cov'], e.cov, rtol=1e-9)
+    close(o['am'], e.am, rtol=1e-7)
+    close(np.sort(o['axlens']), np.sort(e.axlens), rtol=1e-9)
+    assert abs(o['logvol'] - e.logvol) < 1e-8
+    close(o['axes'] @ o['axes'].T, e.cov, rtol=1e-9)
+
+
+@pytest.mark.parametrize('name', ['iso', 'cap', 'shrink'])
+def test_scale_to_logvol_golden(golden, name):
+    g = golden['bounding']
+    # the CUDA routine needs axes/axlens in matching (ascending) order: rebuild from cov
+    o = ops.bounding_ellipsoid(g['be_g20_points'])
+    covs, ams, axes = o['cov'][None].copy(), o['am'][None].copy(), o['axes'][None].copy()
+    axlens, logvols = o['axlens'][None].copy(), np.array([o['logvol']])
+    target = logvols + float(g['stl_%s_dlv' % name])
+    ops.scale_to_logvol(covs, ams, axes, axlens, logvols, target)
+    p = 'stl_%s_' % name
+    close(covs[0], g[p + 'cov'])
+    close(ams[0], g[p + 'am'], rtol=1e-7)
+    close(np.sort(axlens[0]), np.sort(g[p + 'axlens']))
+    close(axes[0] @ axes[0].T, g[p + 'cov'])
+    assert abs(logvols[0] - float(g[p + 'logvol'])) < 1e-9
+
+
+@pytest.mark.parametrize('name', ['c8', 'c2', 'blob', 'ring'])
+def test_multi_decompose_golden(golden, name):
+    g = golden['multi']
+    p = 'me_%s_' % name
+    pts = g[p + 'points']
+    o = ops.multi_decompose(pts)
+    assert o['nells'] == len(g[p + 'logvols'])
+    # leaf ORDER depends on eigenvector signs (see tests/test_oracle_golden.py): compare as sets
+    o1, o2 = np.argsort(o['ctrs'][:, 0]), np.argsort(g[p + 'ctrs'][:, 0])
+    close(o['ctrs'][o1], g[p + 'ctrs'][o2])
+    close(o['covs'][o1], g[p + 'covs'][o2])
+    close(o['ams'][o1], g[p + 'ams'][o2], rtol=1e-7)
+    close(o['logvols'][o1], g[p + 'logvols'][o2], rtol=1e-10)
+    # labels: every point is inside the ellipsoid it is assigned to
+    lab = o['labels']
+    assert lab.min() >= 0 and lab.max() < o['nells']
+    mask = ops.membership(pts, o['ctrs'], o['ams'])[0]
+    assert mask[np.arange(len(pts)), lab].all()
+    # enlarge like Sampler.update_bound (sampler.py:506-508): scalar target -> per-ellipsoid shift
+    from scipy.special import logsumexp
+    covs, ams, axes = o['covs'].copy(), o['ams'].copy(), o['axes'].copy()
+    axlens, logvols = o['axlens'].copy(), o['logvols'].copy()
+    ops.scale_to_logvol(covs, ams, axes, axlens, logvols, logvols + np.log(1.25))
+    close(logvols[o1], g[p + 'enl_logvols'][o2], rtol=1e-10)
+    close(ams[o1], g[p + 'enl_ams'][o2], rtol=1e-7)
+    assert abs(logsumexp(logvols) - (float(g[p + 'logvol']) + np.log(1.25))) < 1e-9
+
+
+def test_number_clusters():
+    """tests/test_ellipsoid.py:267-286: 6^4 grid clusters recovered within 10 %."""
+    rng = np.random.default_rng(SEED)
+    ndim, npt, nper = 4, 30, 6
+    g1 = np.linspace(0, 1, nper + 2)[1:-1]
+    grid = np.array(np.meshgrid(*[g1] * ndim)).reshape(ndim, -1).T
+    pts = (grid[:, None, :] + 1e-4 * rng.standard_normal((len(grid), npt, ndim))).reshape(-1, ndim)
+    o = ops.multi_decompose(pts, max_ells=4000)
+    assert abs(o['nells'] / len(grid) - 1) < 0.1
+
+
+@pytest.mark.parametrize('multi', [0, 1])
+def test_bootstrap_expand_golden(golden, multi):
+    g = golden['multi']
+    got = ops.bootstrap_expand(g['me_c2_points'], multi, 4, SEED, 1000)
+    np.testing.assert_allclose(got, g['boot_%d_expand' % multi], rtol=1e-8)
