@@ -1,0 +1,340 @@
+// b2n_slice.cu -- batched slice-sampling chains (one warp per chain).
+//
+// Replaces RSliceSampler.sample (reference internal_samplers.py:745-855) and
+// SliceSampler.sample (:593-709), both built on generic_slice_step (:1075-1206) and the
+// Neal (2003) doubling acceptance test _slice_doubling_accept (:1038-1072).
+//
+// All control flow of a slice step (stepping out, doubling, shrinking) depends only on
+// warp-uniform scalars (log-likelihood values, uniforms that every lane derives from the
+// same Philox counter), so the 32 lanes of a chain stay converged while they cooperate on
+// the vector work: u + x*d, the unit-cube test, the prior transform and the likelihood.
+// NOTE (reference behaviour kept): the slice samplers read kwargs['nonperiodic'], which
+// the 3.0 sampler never sets (:654, 804), so every dimension is hard-bounded to (0, 1).
+#include "b2n_device.cuh"
+#include <algorithm>
+#include <vector>
+
+int b2n_build_worklist(b2n_ctx* ctx, int64_t Q, const int32_t* ell, int K, int chains_per_cta,
+                       std::vector<int>& order, std::vector<int3>& cta);
+
+#define B2N_MAX_EXPAND 4000000      // hard stop against a runaway stepping-out loop
+
+struct SliceParams {
+    B2nModel m;
+    int n, slices, doubling;
+    const double* u0;
+    const int* order;
+    const int3* cta;
+    const double* axesT;
+    double loglstar, scale;
+    uint64_t seed, chain0;
+    double *u, *v, *logl;
+    int *nexp, *ncon, *ncall;
+    uint32_t* flags;
+};
+
+template <int LIKE>
+struct SliceEval {        // F(x) of generic_slice_step (:1112-1123)
+    const B2nModel& m;
+    const double* P;
+    const double* u;
+    const double* d;
+    double* un;
+    double* vn;
+    double* work;
+    int lane, n;
+    int nc;
+    __device__ __forceinline__ double operator()(double x) {
+        bool ok = true;
+        for (int i = lane; i < n; i += 32) {
+            const double t = fma(x, d[i], u[i]);
+            un[i] = t;
+            ok = ok && (t > 0.0 && t < 1.0);
+        }
+        nc++;
+        ok = __all_sync(B2N_FULL, ok);
+        if (!ok) return -INFINITY;
+        for (int i = lane; i < n; i += 32) vn[i] = prior_1d(m, i, un[i]);
+        __syncwarp();
+        const double l = warp_loglike<LIKE>(m, P, vn, work, lane);
+        return l;
+    }
+};
+
+template <int LIKE>
+__device__ bool doubling_accept(SliceEval<LIKE>& F, double x1, double loglstar, double L, double R, double fL,
+                                double fR) {
+    double lhat = L, rhat = R, fl = fL, fr = fR;
+    bool D = false;
+    while (rhat - lhat > 1.1) {
+        const double M = (lhat + rhat) / 2.0;
+        if ((0.0 < M && M <= x1) || (x1 < M && M <= 0.0)) D = true;
+        if (x1 < M) { rhat = M; fr = F(rhat); }
+        else { lhat = M; fl = F(lhat); }
+        if (D && loglstar >= fl && loglstar >= fr) return false;
+    }
+    return true;
+}
+
+// one generic_slice_step along d (already scaled, not yet length-capped).  On success the
+// new point is left in F.un / its logl returned; `status` gets error / warning bits.
+template <int LIKE>
+__device__ double slice_step(SliceEval<LIKE>& F, ChainRng& g, double* d, double loglstar, bool doubling,
+                             int& n_expand, int& n_contract, bool& expansion_warning, int& err) {
+    const int n = F.n, lane = F.lane;
+    const double rand0 = rng_uniform(g);                        // :1099
+    double ss = 0.0;
+    for (int i = lane; i < n; i += 32) ss = fma(d[i], d[i], ss);
+    const double dirlen = sqrt(warp_sum(ss));
+    const double maxlen = sqrt((double)n) / 2.0;
+    if (dirlen > maxlen) {                                      // :1103-1108
+        const double dn = dirlen / maxlen;
+        for (int i = lane; i < n; i += 32) d[i] = d[i] / dn;
+    }
+    __syncwarp();
+    double xl = -rand0, xr = 1.0 - rand0;                       // :1126-1127
+    double fl = F(xl), fr = F(xr);
+    double L = 0, R = 0, fL = 0, fR = 0;
+    int nexp = 0;
+    expansion_warning = false;
+    if (!doubling) {
+        while (fl > loglstar) {                                 // :1134-1137
+            xl -= 1.0; fl = F(xl); nexp++;
+            if (nexp > B2N_MAX_EXPAND) { err = B2N_ERR_SLICE_FAIL; break; }
+        }
+        while (fr > loglstar && !err) {
+            xr += 1.0; fr = F(xr); nexp++;
+            if (nexp > B2N_MAX_EXPAND) { err = B2N_ERR_SLICE_FAIL; break; }
+        }
+        if (nexp > 1000) expansion_warning = true;              // :1142-1145
+    } else {
+        int K = 1;                                              // :1149-1163
+        while (fl > loglstar || fr > loglstar) {
+            const double V = rng_uniform(g);
+            if (V < 0.5) { xl -= (xr - xl); fl = F(xl); }
+            else { xr += (xr - xl); fr = F(xr); }
+            nexp += K;
+            if (K < (1 << 28)) K *= 2;
+        }
+        L = xl; R = xr; fL = fl; fR = fr;
+    }
+    n_expand += nexp;
+    double lp = -INFINITY;
+    for (int it = 0; !err; it++) {                              // :1168-1203
+        const double xp = xl + rng_uniform(g) * (xr - xl);
+        lp = F(xp);
+        n_contract++;
+        if (lp > loglstar && (!doubling || doubling_accept<LIKE>(F, xp, loglstar, L, R, fL, fR))) {
+            if (doubling) {   // the acceptance test moved F.un: restore the accepted point
+                lp = F(xp);
+                F.nc--;
+            }
+            break;
+        }
+        if (xp < 0.0) xl = xp;
+        else if (xp > 0.0) xr = xp;
+        else err = B2N_ERR_SLICE_FAIL;                          // :1191-1203
+        if (it > 100000) err = B2N_ERR_SLICE_FAIL;
+    }
+    return lp;
+}
+
+template <int LIKE, bool RANDOM_DIR, bool AX_SMEM, bool PREC_SMEM>
+__global__ void __launch_bounds__(256) slice_kernel(const SliceParams p) {
+    extern __shared__ double sm[];
+    const int n = p.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int3 cd = p.cta[blockIdx.x];
+    double* s = sm;
+    const double* A = p.axesT + (size_t)cd.z * n * n;
+    if (AX_SMEM) {
+        for (int i = threadIdx.x; i < n * n; i += blockDim.x) s[i] = A[i];
+        A = s;
+        s += n * n;
+    }
+    const double* P = p.m.lmat;
+    if (LIKE == B2N_LIKE_GAUSS_PREC && PREC_SMEM) {
+        for (int i = threadIdx.x; i < n * n; i += blockDim.x) s[i] = P[i];
+        P = s;
+        s += n * n;
+    }
+    __syncthreads();
+    double* ucur = s + (size_t)warp * 6 * n;
+    double* d = ucur + n;
+    double* un = d + n;
+    double* vn = un + n;
+    double* work = vn + n;       // likelihood scratch; also z / uniform vector
+    int* idxs = reinterpret_cast<int*>(work + n);   // n ints (permutation)
+
+    for (int c = warp; c < cd.y; c += nwarps) {
+        const int q = p.order[cd.x + c];
+        ChainRng g;
+        g.init(p.seed, p.chain0 + (uint64_t)q);
+        for (int i = lane; i < n; i += 32) ucur[i] = p.u0[(size_t)q * n + i];
+        __syncwarp();
+        SliceEval<LIKE> F{p.m, P, ucur, d, un, vn, work, lane, n, 0};
+        int nexp = 0, ncon = 0, err = 0;
+        bool doubling = p.doubling != 0, warned = false;
+        double lcur = 0.0;
+        for (int sl = 0; sl < p.slices && !err; sl++) {
+            const int nsub = RANDOM_DIR ? 1 : n;
+            if (!RANDOM_DIR && n > 1) {
+                // rstate.shuffle(idxs) (:673-674): argsort (stable) of one uniform vector event
+                for (int e = lane; e < n; e += 32) work[e] = rng_uniform_elem(g, e);
+                g.tick++;
+                __syncwarp();
+                for (int e = lane; e < n; e += 32) {
+                    const double ve = work[e];
+                    int rk = 0;
+                    for (int f = 0; f < n; f++) rk += (work[f] < ve || (work[f] == ve && f < e)) ? 1 : 0;
+                    idxs[rk] = e;
+                }
+                __syncwarp();
+            } else if (!RANDOM_DIR) {
+                if (lane == 0) idxs[0] = 0;
+                __syncwarp();
+            }
+            for (int sub = 0; sub < nsub && !err; sub++) {
+                if (RANDOM_DIR) {
+                    // drhat = z / |z| ; direction = axes @ drhat * scale (:820-824)
+                    const double ss = rng_normals_to(g, work, n, lane);
+                    const double inv = 1.0 / sqrt(ss);
+                    __syncwarp();
+                    for (int i = lane; i < n; i += 32) work[i] *= inv;
+                    __syncwarp();
+                    for (int base = 0; base < n; base += 64) {
+                        double y0, y1;
+                        warp_matvec2(A, n, n, work, base + lane, n, y0, y1);
+                        if (base + lane < n) d[base + lane] = y0 * p.scale;
+                        if (base + lane + 32 < n) d[base + lane + 32] = y1 * p.scale;
+                    }
+                } else {
+                    // axes = scale * axes.T ; axis = axes[idx] (:665, 680) = column idx of the axes matrix
+                    const int idx = idxs[sub];
+                    for (int i = lane; i < n; i += 32) d[i] = p.scale * A[(size_t)idx * n + i];
+                }
+                __syncwarp();
+                bool ew = false;
+                const double l = slice_step<LIKE>(F, g, d, p.loglstar, doubling, nexp, ncon, ew, err);
+                if (err) break;
+                lcur = l;
+                for (int i = lane; i < n; i += 32) ucur[i] = un[i];     // u = u_prop
+                __syncwarp();
+                if (ew && !doubling) { doubling = true; warned = true; }   // :689-693, 836-838
+            }
+        }
+        // v_prop = prior_transform(u_prop) (:1204)
+        for (int i = lane; i < n; i += 32) {
+            p.u[(size_t)q * n + i] = ucur[i];
+            p.v[(size_t)q * n + i] = prior_1d(p.m, i, ucur[i]);
+        }
+        if (lane == 0) {
+            p.logl[q] = lcur;
+            p.nexp[q] = nexp;
+            p.ncon[q] = ncon;
+            p.ncall[q] = F.nc;
+            p.flags[q] = (warned ? B2N_WARN_DOUBLING : 0u) | (err ? 0x80000000u : 0u);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void any_error_kernel(const uint32_t* flags, int64_t Q, int* out) {
+    int bad = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Q; i += (int64_t)gridDim.x * blockDim.x)
+        bad |= (flags[i] & 0x80000000u) ? 1 : 0;
+    if (bad) atomicOr(out, 1);
+}
+
+template <bool RANDOM_DIR>
+static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slices, int32_t doubling, double* u,
+                            double* v, double* logl, int32_t* n_expand, int32_t* n_contract, int32_t* ncall,
+                            uint32_t* flags) {
+    if (!ctx || !a || !u || !v || !logl || !n_expand || !n_contract || !ncall || !flags) return B2N_ERR_ARG;
+    if (a->model_id < 0 || a->model_id >= (int)ctx->models.size()) return B2N_ERR_ARG;
+    const B2nModel m = ctx->models[a->model_id];
+    const int n = a->ndim;
+    const int64_t Q = a->nchain;
+    if (n != m.ndim || a->ncdim != n || slices < 1 || Q < 0 || !a->u0)
+        return b2n_fail(ctx, B2N_ERR_ARG, "slice samplers need ncdim == ndim (internal_samplers.py:658, 809)");
+    if (ctx->bK < 1 || ctx->bn != n) return b2n_fail(ctx, B2N_ERR_ARG, "resident bound missing or of wrong dimension");
+    if (Q == 0) return B2N_OK;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int warps = 8;
+    const size_t per_warp = (size_t)6 * n * sizeof(double);
+    const size_t fixed = per_warp * warps;
+    const size_t ax_b = (size_t)n * n * sizeof(double);
+    const size_t pr_b = (m.like_kind == B2N_LIKE_GAUSS_PREC) ? ax_b : 0;
+    const size_t limit = (size_t)ctx->max_smem_optin;
+    if (fixed > limit) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for the slice kernel");
+    const bool ax_s = fixed + ax_b <= limit;
+    const bool pr_s = pr_b > 0 && fixed + (ax_s ? ax_b : 0) + pr_b <= limit;
+    const size_t smem = fixed + (ax_s ? ax_b : 0) + (pr_s ? pr_b : 0);
+    std::vector<int> order;
+    std::vector<int3> cta;
+    B2N_TRY(b2n_build_worklist(ctx, Q, a->ell, ctx->bK, warps, order, cta));
+    SliceParams p;
+    p.m = m; p.n = n; p.slices = slices; p.doubling = doubling;
+    p.loglstar = a->loglstar; p.scale = a->scale; p.seed = a->seed; p.chain0 = a->chain0;
+    p.axesT = ctx->b_axesT.as<double>();
+    const void *du0, *dorder, *dcta;
+    B2N_TRY(b2n_in(ctx, ctx->in0, a->u0, (size_t)Q * n * sizeof(double), &du0));
+    B2N_TRY(b2n_in_host(ctx, ctx->work0, order.data(), order.size() * sizeof(int), &dorder));
+    B2N_TRY(b2n_in_host(ctx, ctx->work1, cta.data(), cta.size() * sizeof(int3), &dcta));
+    void *du, *dv, *dl, *dne, *dnc, *dncl, *dfl;
+    B2N_TRY(b2n_out(ctx, ctx->out0, u, (size_t)Q * n * sizeof(double), &du));
+    B2N_TRY(b2n_out(ctx, ctx->out1, v, (size_t)Q * n * sizeof(double), &dv));
+    B2N_TRY(b2n_out(ctx, ctx->out2, logl, (size_t)Q * sizeof(double), &dl));
+    B2N_TRY(b2n_out(ctx, ctx->out3, n_expand, (size_t)Q * sizeof(int), &dne));
+    B2N_TRY(b2n_out(ctx, ctx->out4, n_contract, (size_t)Q * sizeof(int), &dnc));
+    B2N_TRY(b2n_out(ctx, ctx->out5, ncall, (size_t)Q * sizeof(int), &dncl));
+    B2N_TRY(b2n_out(ctx, ctx->out6, flags, (size_t)Q * sizeof(uint32_t), &dfl));
+    p.u0 = (const double*)du0; p.order = (const int*)dorder; p.cta = (const int3*)dcta;
+    p.u = (double*)du; p.v = (double*)dv; p.logl = (double*)dl;
+    p.nexp = (int*)dne; p.ncon = (int*)dnc; p.ncall = (int*)dncl; p.flags = (uint32_t*)dfl;
+    const unsigned grid = (unsigned)cta.size();
+#define LAUNCH(L, AXS, PRS)                                                                          \
+    do {                                                                                             \
+        B2N_CUDA(ctx, cudaFuncSetAttribute(slice_kernel<L, RANDOM_DIR, AXS, PRS>,                     \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        slice_kernel<L, RANDOM_DIR, AXS, PRS><<<grid, warps * 32, smem, ctx->stream>>>(p);            \
+    } while (0)
+#define CALL(L)                                \
+    if (ax_s && pr_s) LAUNCH(L, true, true);   \
+    else if (ax_s) LAUNCH(L, true, false);     \
+    else if (pr_s) LAUNCH(L, false, true);     \
+    else LAUNCH(L, false, false);
+    B2N_DISPATCH_LIKE(m.like_kind, CALL)
+#undef CALL
+#undef LAUNCH
+    B2N_LAUNCH_CHECK(ctx);
+    // error summary (a collapsed interval anywhere = RuntimeError in the reference)
+    int* derr = reinterpret_cast<int*>(ctx->pinned);
+    *derr = 0;
+    B2N_CUDA(ctx, ctx->out7.ensure(64));
+    B2N_CUDA(ctx, cudaMemsetAsync(ctx->out7.p, 0, sizeof(int), ctx->stream));
+    any_error_kernel<<<64, 256, 0, ctx->stream>>>((const uint32_t*)dfl, Q, ctx->out7.as<int>());
+    B2N_LAUNCH_CHECK(ctx);
+    B2N_CUDA(ctx, cudaMemcpyAsync(derr, ctx->out7.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    B2N_TRY(b2n_out_done(ctx, u, du, (size_t)Q * n * sizeof(double)));
+    B2N_TRY(b2n_out_done(ctx, v, dv, (size_t)Q * n * sizeof(double)));
+    B2N_TRY(b2n_out_done(ctx, logl, dl, (size_t)Q * sizeof(double)));
+    B2N_TRY(b2n_out_done(ctx, n_expand, dne, (size_t)Q * sizeof(int)));
+    B2N_TRY(b2n_out_done(ctx, n_contract, dnc, (size_t)Q * sizeof(int)));
+    B2N_TRY(b2n_out_done(ctx, ncall, dncl, (size_t)Q * sizeof(int)));
+    B2N_TRY(b2n_out_done(ctx, flags, dfl, (size_t)Q * sizeof(uint32_t)));
+    B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the error word is a host result
+    if (*derr) return B2N_ERR_SLICE_FAIL;
+    return B2N_OK;
+}
+
+extern "C" int b2n_rslice_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slices, int32_t doubling,
+                                double* u, double* v, double* logl, int32_t* n_expand, int32_t* n_contract,
+                                int32_t* ncall, uint32_t* flags) {
+    return slice_batch_impl<true>(ctx, a, slices, doubling, u, v, logl, n_expand, n_contract, ncall, flags);
+}
+extern "C" int b2n_slice_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slices, int32_t doubling, double* u,
+                               double* v, double* logl, int32_t* n_expand, int32_t* n_contract, int32_t* ncall,
+                               uint32_t* flags) {
+    return slice_batch_impl<false>(ctx, a, slices, doubling, u, v, logl, n_expand, n_contract, ncall, flags);
+}

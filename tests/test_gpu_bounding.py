@@ -47,7 +47,9 @@ def test_bounding_rank_deficient(golden):
     o = ops.bounding_ellipsoid(pts)
     assert ops.membership(pts, o['ctr'], o['am'], want_d2=True)[2].max() < 1
     assert np.all(np.linalg.eigvalsh(o['cov']) > 0)
-    close(np.sort(o['axlens'])[-1], np.sort(g['be_rank1_axlens'])[-1], rtol=1e-6)
+    # the rescale factor of a rank-deficient fit is set by round-off in the null space
+    # (1/l_min ~ 1e11 times noise^2): only pinned loosely
+    close(np.sort(o['axlens'])[-1], np.sort(g['be_rank1_axlens'])[-1], rtol=1e-4)
     rng = np.random.default_rng(1)
     for ndim in (1, 10, 100):
         x = rng.random(200)
