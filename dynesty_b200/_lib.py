@@ -51,6 +51,8 @@ SYMBOLS = {
     'b2n_last_error': (C.c_char_p, [_P]),
     'b2n_version': (C.c_char_p, []),
     'b2n_launch_count': (C.c_int64, [_P]),
+    'b2n_set_timing': (C.c_int, [_P, C.c_int]),
+    'b2n_last_kernel_ms': (C.c_double, [_P]),
     'b2n_model_create': (C.c_int, [_P, C.POINTER(ModelDesc), C.POINTER(_I)]),
     'b2n_model_eval': (C.c_int, [_P, _I, _P, _L, _P, _P]),
     'b2n_membership': (C.c_int, [_P, _P, _L, _I, _P, _P, _I, _I, _P, _P, _P]),
@@ -154,6 +156,12 @@ class Context:
 
     def synchronize(self):
         self.check(self.lib.b2n_synchronize(self.h))
+
+    def set_timing(self, enabled):
+        self.check(self.lib.b2n_set_timing(self.h, int(bool(enabled))))
+
+    def last_kernel_ms(self):
+        return float(self.lib.b2n_last_kernel_ms(self.h))
 
     def launch_count(self):
         return int(self.lib.b2n_launch_count(self.h))

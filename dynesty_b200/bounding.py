@@ -1,0 +1,265 @@
+"""B200 bounds: drop-in mirrors of dynesty's ``Ellipsoid`` / ``MultiEllipsoid``.
+
+Interface = the reference's ``Bound`` duck-type (bounding.py:76-122) plus the public
+attributes its other code reads (``ctr/cov/am/axes/axlens`` and ``ells/ctrs/covs/ams/
+logvol_ells/nells``, bounding.py:201-240, 440-476; plotting.py:1710, 2035).  Every
+numeric method is one call into libb200nest.so; the objects hold plain numpy arrays,
+so ``copy.deepcopy`` (sampler.py:510) and ``pickle`` (utils.py:2343) just work.
+"""
+import math
+import warnings
+
+import numpy as np
+
+from . import ops, _lib
+from ._compat import BoundBase
+
+__all__ = ['B200Ellipsoid', 'B200MultiEllipsoid', 'TaggedAxes']
+
+
+class TaggedAxes(np.ndarray):
+    """``get_random_axes`` result: the (ncdim, ncdim) axes matrix that also remembers
+    which ellipsoid of which bound it belongs to, so that the batched samplers can
+    address the device-resident copy instead of re-uploading Q matrices per queue fill
+    (the reference pickles the matrix into every task, sampler.py:708-717)."""
+
+    def __new__(cls, arr, bound, ell):
+        obj = np.asarray(arr).view(cls)
+        obj.bound = bound
+        obj.ell = int(ell)
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.bound = getattr(obj, 'bound', None)
+        self.ell = getattr(obj, 'ell', 0)
+
+    def __reduce__(self):            # pickles as a plain array
+        return (np.asarray, (np.array(self),))
+
+    def __deepcopy__(self, memo):
+        return np.array(self)
+
+
+def _seed_from(rstate):
+    """64-bit Philox seed drawn from the caller's numpy Generator."""
+    if rstate is None:
+        rstate = np.random.default_rng()
+    return int(rstate.integers(0, 2**63 - 1))
+
+
+class _EllView:
+    """Read-only view of one ellipsoid of a B200MultiEllipsoid (plotting compatibility)."""
+
+    def __init__(self, parent, k):
+        self.ndim = parent.ndim
+        self.ctr, self.cov, self.am = parent.ctrs[k], parent.covs[k], parent.ams[k]
+        self.axes, self.axlens = parent.axes_all[k], parent.axlens_all[k]
+        self.logvol = float(parent.logvol_ells[k])
+        self.funit = 1
+
+
+class B200MultiEllipsoid(BoundBase):
+    """``MultiEllipsoid`` (bounding.py:420-731) built and queried on the GPU."""
+
+    def __init__(self, ndim, ctx=None):
+        super().__init__(ndim)
+        self._ctx = ctx
+        n = ndim
+        # Ellipsoid(ndim) default: centre 0 (sic), cov = I n/4 (bounding.py:203-205)
+        cov = np.identity(n) * n / 4
+        self.nells = 1
+        self.ctrs = np.zeros((1, n))
+        self.covs = cov[None].copy()
+        self.ams = np.linalg.inv(cov)[None]
+        self.axes_all = (np.identity(n) * math.sqrt(n / 4.))[None]
+        self.axlens_all = np.full((1, n), math.sqrt(n / 4.))
+        from scipy.special import gammaln
+        pref = n * math.log(2.) + n * gammaln(1.5) - gammaln(n / 2. + 1)
+        self.logvol_ells = np.array([pref + 0.5 * n * math.log(n / 4.)])
+        self.logvol = float(self.logvol_ells[0])
+        self.funit = 1
+        self.labels = None
+        self.version = 0           # bumped whenever the arrays change (device cache key)
+
+    # -- pickling / deepcopy: drop the (per-process) context handle -----------------
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d['_ctx'] = None
+        return d
+
+    @property
+    def ells(self):
+        return [_EllView(self, k) for k in range(self.nells)]
+
+    def _refresh_logvol(self):
+        from scipy.special import logsumexp
+        self.logvol = float(logsumexp(self.logvol_ells))     # ignores overlap (:466)
+        self.version += 1
+
+    # -- Bound interface -----------------------------------------------------------------
+    def contains(self, x):
+        """bounding.py:520-523 (strict <)."""
+        _, q = ops.membership(np.asarray(x, dtype=float)[None], self.ctrs, self.ams, strict=True, ctx=self._ctx)
+        return bool(q[0] > 0)
+
+    def contains_many(self, x):
+        """Batched ``contains`` (one launch for a whole queue of start points)."""
+        return ops.membership(x, self.ctrs, self.ams, strict=True, ctx=self._ctx)[1] > 0
+
+    def within(self, x, j=None):
+        mask, _ = ops.membership(np.asarray(x, dtype=float)[None], self.ctrs, self.ams, ctx=self._ctx)
+        m = mask[0].copy()
+        if j is not None:
+            m[j] = False
+        return np.nonzero(m)[0]
+
+    def overlap(self, x, j=None):
+        return len(self.within(x, j=j))
+
+    def make_resident(self):
+        ops.bound_set(self.axes_all, self.ctrs, self.ams, self.logvol_ells, ctx=self._ctx)
+
+    def samples(self, nsamples, rstate=None):
+        """bounding.py:592-606: uniform draws from the union (no cube test)."""
+        self.make_resident()
+        o = ops.unif_batch(-1, nsamples, self.ndim, -np.inf, _seed_from(rstate), draw_only=True,
+                           ncdim=self.ndim, ctx=self._ctx)
+        return o['u']
+
+    def sample(self, rstate=None, return_q=False):
+        x = self.samples(1, rstate=rstate)[0]
+        idx = int(np.argmin(np.einsum('ki,kij,kj->k', x - self.ctrs, self.ams, x - self.ctrs)))
+        if return_q:
+            return x, idx, self.overlap(x)
+        return x, idx
+
+    def get_random_axes(self, rstate):
+        """bounding.py:726-731: axes of an ellipsoid picked with probability ~ volume."""
+        if self.nells == 1:
+            k = 0
+        else:
+            probs = np.exp(self.logvol_ells - self.logvol)
+            k = min(int(np.searchsorted(np.cumsum(probs), rstate.random())), self.nells - 1)
+        return TaggedAxes(self.axes_all[k], self, k)
+
+    def random_ells(self, rstate, size):
+        """Vectorised ``get_random_axes``: `size` volume-weighted ellipsoid indices."""
+        if self.nells == 1:
+            return np.zeros(size, dtype=np.int32)
+        probs = np.exp(self.logvol_ells - self.logvol)
+        k = np.searchsorted(np.cumsum(probs), rstate.random(size))
+        return np.minimum(k, self.nells - 1).astype(np.int32)
+
+    def scale_to_logvol(self, logvol):
+        """bounding.py:478-495: scalar = new total, iterable = per-ellipsoid targets."""
+        if np.ndim(logvol) > 0:
+            target = np.asarray(logvol, dtype=float)
+        else:
+            target = self.logvol_ells + (float(logvol) - self.logvol)
+        ops.scale_to_logvol(self.covs, self.ams, self.axes_all, self.axlens_all, self.logvol_ells,
+                            target, ctx=self._ctx)
+        self._refresh_logvol()
+
+    def update(self, points, rstate=None, bootstrap=0, pool=None, mc_integrate=False):
+        """bounding.py:632-724.  `pool` is ignored: the bootstrap replicas run on the GPU."""
+        points = np.ascontiguousarray(points, dtype=float)
+        npoints, ndim = points.shape
+        if npoints == 1:
+            raise RuntimeError('Cannot compute the bounding ellipsoid of a single point.')
+        o = ops.multi_decompose(points, ctx=self._ctx)
+        if o['warn'] & _lib.WARN_IDENTITY_FALLBACK:
+            warnings.warn("Failed to guarantee the ellipsoid axes will be non-singular. "
+                          "Defaulting to a sphere.")
+        self.nells = o['nells']
+        self.ctrs, self.covs, self.ams = o['ctrs'], o['covs'], o['ams']
+        self.axes_all, self.axlens_all, self.logvol_ells = o['axes'], o['axlens'], o['logvols']
+        self.labels = o['labels']
+        self._refresh_logvol()
+        if bootstrap > 0:
+            expands = ops.bootstrap_expand(points, True, int(bootstrap), _seed_from(rstate), 0, ctx=self._ctx)
+            expand = float(expands.max())
+            if math.log10(expand) * ndim > 2:                              # :705-714
+                warnings.warn('The enlargement factor for the ellipsoidal bounds determined '
+                              'from bootstrapping is very large.')
+            if expand > 1.:
+                self.scale_to_logvol(self.logvol_ells + ndim * math.log(expand))
+        if mc_integrate:
+            raise NotImplementedError("mc_integrate is never requested by Sampler (sampler.py:502-505)")
+
+
+class B200Ellipsoid(BoundBase):
+    """``Ellipsoid`` (bounding.py:182-417) built and queried on the GPU."""
+
+    def __init__(self, ndim, ctx=None):
+        super().__init__(ndim)
+        self._m = B200MultiEllipsoid(ndim, ctx=ctx)
+        self.funit = 1
+
+    def __getattr__(self, name):
+        m = self.__dict__.get('_m')
+        if m is None:
+            raise AttributeError(name)
+        one = {'ctr': 'ctrs', 'cov': 'covs', 'am': 'ams', 'axes': 'axes_all', 'axlens': 'axlens_all'}
+        if name in one:
+            return getattr(m, one[name])[0]
+        if name in ('version', 'nells', 'ctrs', 'ams', 'covs', 'axes_all', 'axlens_all', 'logvol_ells'):
+            return getattr(m, name)
+        raise AttributeError(name)
+
+    @property
+    def logvol(self):
+        return float(self._m.logvol_ells[0])
+
+    @logvol.setter
+    def logvol(self, v):       # BoundBase.__init__ assigns 0 before _m exists
+        pass
+
+    def contains(self, x):
+        """bounding.py:302-305 (non-strict: distance <= 1)."""
+        return bool(ops.membership(np.asarray(x, dtype=float)[None], self._m.ctrs, self._m.ams,
+                                   strict=False, ctx=self._m._ctx)[1][0] > 0)
+
+    def contains_many(self, x):
+        return ops.membership(x, self._m.ctrs, self._m.ams, strict=False, ctx=self._m._ctx)[1] > 0
+
+    def distance_many(self, x):
+        return np.sqrt(ops.membership(x, self._m.ctrs, self._m.ams, want_d2=True, ctx=self._m._ctx)[2][:, 0])
+
+    def make_resident(self):
+        self._m.make_resident()
+
+    def samples(self, nsamples, rstate=None):
+        return self._m.samples(nsamples, rstate=rstate)
+
+    def sample(self, rstate=None):
+        return self._m.samples(1, rstate=rstate)[0]
+
+    def get_random_axes(self, rstate):
+        return TaggedAxes(self._m.axes_all[0], self, 0)
+
+    def random_ells(self, rstate, size):
+        return np.zeros(size, dtype=np.int32)
+
+    def scale_to_logvol(self, logvol):
+        self._m.scale_to_logvol(np.array([float(logvol)]))
+
+    def update(self, points, rstate=None, bootstrap=0, pool=None, mc_integrate=False):
+        """bounding.py:345-414."""
+        points = np.ascontiguousarray(points, dtype=float)
+        o = ops.bounding_ellipsoid(points, ctx=self._m._ctx)
+        if o['warn'] & _lib.WARN_IDENTITY_FALLBACK:
+            warnings.warn("Failed to guarantee the ellipsoid axes will be non-singular. "
+                          "Defaulting to a sphere.")
+        m = self._m
+        m.nells = 1
+        m.ctrs, m.covs, m.ams = o['ctr'][None], o['cov'][None], o['am'][None]
+        m.axes_all, m.axlens_all = o['axes'][None], o['axlens'][None]
+        m.logvol_ells = np.array([o['logvol']])
+        m._refresh_logvol()
+        if bootstrap > 0:
+            expands = ops.bootstrap_expand(points, False, int(bootstrap), _seed_from(rstate), 0, ctx=m._ctx)
+            expand = float(expands.max())
+            if expand > 1.:
+                self.scale_to_logvol(self.logvol + self.ndim * math.log(expand))
+        if mc_integrate:
+            raise NotImplementedError("mc_integrate is never requested by Sampler")

@@ -47,6 +47,9 @@ struct b2n_ctx {
     int sm_count = 148;
     int max_smem_optin = 0;
     int64_t launches = 0;
+    int timing = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
     char err[512] = {0};
     std::vector<B2nModel> models;
     std::vector<void*> model_allocs;
@@ -77,6 +80,9 @@ struct b2n_ctx {
         int s_ = (call);                      \
         if (s_ != B2N_OK) return s_;          \
     } while (0)
+
+#define B2N_TIME_BEGIN(ctx) do { if ((ctx)->timing) cudaEventRecord((ctx)->ev0, (ctx)->stream); } while (0)
+#define B2N_TIME_END(ctx) do { if ((ctx)->timing) { cudaEventRecord((ctx)->ev1, (ctx)->stream); (ctx)->ev_valid = true; } } while (0)
 
 #define B2N_LAUNCH_CHECK(ctx)                 \
     do {                                      \

@@ -65,6 +65,7 @@ void b2n_free(b2n_ctx* ctx) {
                       &ctx->scratch5, &ctx->work0, &ctx->work1};
     for (DevBuf* b : bufs) b->release();
     for (void* p : ctx->model_allocs) cudaFree(p);
+    if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -98,6 +99,26 @@ int b2n_synchronize(b2n_ctx* ctx) {
 }
 
 int64_t b2n_launch_count(b2n_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b2n_set_timing(b2n_ctx* ctx, int enabled) {
+    if (!ctx) return B2N_ERR_ARG;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (enabled && !ctx->ev0) {
+        B2N_CUDA(ctx, cudaEventCreate(&ctx->ev0));
+        B2N_CUDA(ctx, cudaEventCreate(&ctx->ev1));
+    }
+    ctx->timing = enabled ? 1 : 0;
+    ctx->ev_valid = false;
+    return B2N_OK;
+}
+
+double b2n_last_kernel_ms(b2n_ctx* ctx) {
+    if (!ctx || !ctx->ev_valid) return -1.0;
+    if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
 
 static int upload(b2n_ctx* ctx, const double* h, size_t count, const double** d) {
     *d = nullptr;

@@ -227,7 +227,9 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     else if (ax_s) LAUNCH(L, true, false);                             \
     else if (pr_s) LAUNCH(L, false, true);                             \
     else LAUNCH(L, false, false);
+    B2N_TIME_BEGIN(ctx);
     B2N_DISPATCH_LIKE(m.like_kind, CALL)
+    B2N_TIME_END(ctx);
 #undef CALL
 #undef LAUNCH
     B2N_LAUNCH_CHECK(ctx);

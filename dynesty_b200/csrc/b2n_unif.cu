@@ -15,7 +15,7 @@
 
 struct UnifParams {
     B2nModel m;
-    int n, nc, K;
+    int n, nc, K, draw_only;
     const double* ctrs;     // K x nc
     const double* ams;      // K x nc x nc
     const double* axesT;    // K x nc x nc (transposed)
@@ -100,6 +100,10 @@ __global__ void __launch_bounds__(256) unif_kernel(const UnifParams p) {
             }
             if (done) break;
             nprop++;
+            if (p.draw_only) {           // Bound.samples(): no cube test, no likelihood (bounding.py:592-606)
+                for (int i = lane; i < n; i += 32) vv[i] = uu[i];
+                break;
+            }
             // ---- unit-cube check on the clustered dims (internal_samplers.py:314)
             bool ok = true;
             for (int i = lane; i < nc; i += 32) ok = ok && in_cube(uu[i], p.dimflags ? p.dimflags[i] : 0u);
@@ -143,11 +147,18 @@ __global__ void unif_error_kernel(const uint32_t* flags, int64_t Q, int* out) {
 extern "C" int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, double* v, double* logl,
                               int32_t* ncall, int32_t* nprop, uint32_t* flags) {
     if (!ctx || !a || !u || !v || !logl || !ncall || !nprop || !flags) return B2N_ERR_ARG;
-    if (a->model_id < 0 || a->model_id >= (int)ctx->models.size()) return B2N_ERR_ARG;
-    const B2nModel m = ctx->models[a->model_id];
+    const int draw_only = (a->reserved & B2N_OPT_DRAW_ONLY) ? 1 : 0;
+    B2nModel m;
+    memset(&m, 0, sizeof(m));
+    m.ndim = a->ndim;
+    m.like_kind = B2N_LIKE_EGGBOX;
+    if (!draw_only) {
+        if (a->model_id < 0 || a->model_id >= (int)ctx->models.size()) return B2N_ERR_ARG;
+        m = ctx->models[a->model_id];
+    }
     const int n = a->ndim, nc = a->ncdim;
     const int64_t Q = a->nchain;
-    if (n != m.ndim || nc < 1 || nc > n || Q < 0) return B2N_ERR_ARG;
+    if (n != m.ndim || nc < 1 || nc > n || Q < 0 || (draw_only && n != nc)) return B2N_ERR_ARG;
     if (ctx->bK < 1 || ctx->bn != nc || ctx->h_logvols.empty())
         return b2n_fail(ctx, B2N_ERR_ARG, "resident bound (with ctrs/ams/logvols) missing or of wrong dimension");
     if (Q == 0) return B2N_OK;
@@ -170,7 +181,7 @@ extern "C" int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, 
         B2N_TRY(b2n_in_host(ctx, ctx->in3, fl.data(), fl.size() * sizeof(uint32_t), &dfl_in));
     }
     UnifParams p;
-    p.m = m; p.n = n; p.nc = nc; p.K = K; p.Q = Q;
+    p.m = m; p.n = n; p.nc = nc; p.K = K; p.Q = Q; p.draw_only = draw_only;
     p.ctrs = ctx->b_ctrs.as<double>(); p.ams = ctx->b_ams.as<double>(); p.axesT = ctx->b_axesT.as<double>();
     p.cum = (const double*)dcum; p.dimflags = (const uint32_t*)dfl_in;
     p.loglstar = a->loglstar; p.seed = a->seed; p.chain0 = a->chain0;
@@ -191,7 +202,9 @@ extern "C" int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, 
     if (smem > 48 * 1024)                                                                               \
         B2N_CUDA(ctx, cudaFuncSetAttribute(unif_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     unif_kernel<L><<<(unsigned)blocks, threads, smem, ctx->stream>>>(p);
+    B2N_TIME_BEGIN(ctx);
     B2N_DISPATCH_LIKE(m.like_kind, CALL)
+    B2N_TIME_END(ctx);
 #undef CALL
     B2N_LAUNCH_CHECK(ctx);
     int* herr = reinterpret_cast<int*>(ctx->pinned);

@@ -1,0 +1,356 @@
+"""Host mirror of the reference ``Sampler``'s proposal dispatch, batched for the GPU.
+
+What is mirrored (reference py/dynesty/sampler.py, same names / meaning):
+  propose_live            :469-491   start point + axes (+ contains check, forced update)
+  update_bound            :493-510   bound.update(...) + enlarge via scale_to_logvol
+  update_bound_if_needed  :625-674   first-update / interval / forced logic
+  _fill_queue             :676-717   queue_size proposals per fill, ONE kernel launch
+  _new_point              :732-778   pop until logl > loglstar; tune when the queue drains;
+                                     bound update check when the queue is empty
+and the factory defaults of dynesty.py (:126-135 walks/slices, :169-211 enlarge/bootstrap,
+:213-230 update interval, sampler.py:407-409 first update).
+
+The surrounding nested-sampling bookkeeping (dead-point record, evidence integral) is the
+reference's L2/L4 layer and out of scope as a subsystem; the minimum needed to turn the
+hot path into a logZ (the BASELINE metric's second half) is restated compactly in
+``_integrate`` (utils.py:1411-1467) and ``run_nested`` (sampler.py:1040-1212, 780-914).
+On a machine that has dynesty installed the same bounds/samplers plug into
+``dynesty.NestedSampler`` directly; this driver exists because the GPU
+box has no dynesty, and because it proposes/contains-checks a whole queue per call.
+"""
+import heapq
+import math
+
+import numpy as np
+
+from . import bounding as B
+from . import samplers as S
+
+LOWL = -1e300
+
+
+def _logaddexp(a, b):
+    if a < b:
+        a, b = b, a
+    if b == -math.inf:
+        return a
+    return a + math.log1p(math.exp(b - a))
+
+
+class Results(dict):
+    __getattr__ = dict.__getitem__
+
+    def summary(self):
+        return ("niter: %d\nncall: %d\neff(%%): %6.3f\nlogz: %6.3f +/- %6.3f" %
+                (self['niter'], self['ncall'], self['eff'], self['logz'][-1], self['logzerr'][-1]))
+
+    def posterior_moments(self):
+        w = np.exp(self['logwt'] - self['logz'][-1])
+        w /= w.sum()
+        mean = w @ self['samples']
+        d = self['samples'] - mean
+        return mean, (d * w[:, None]).T @ d
+
+
+def _integrate(logl, logvol):
+    """Trapezoid evidence / information integrals over the dead-point sequence
+    (utils.py:1411-1467 compute_integrals, same quadrature)."""
+    lpad = np.concatenate([[LOWL], logl])
+    dlv = np.diff(logvol, prepend=0)
+    logdvol = logvol - dlv + np.log1p(-np.exp(dlv))
+    logdvol2 = logdvol + math.log(0.5)
+    logwt = np.logaddexp(lpad[1:], lpad[:-1]) + logdvol2
+    logz = np.logaddexp.accumulate(logwt)
+    zmax = logz[-1]
+    h1 = np.cumsum(np.exp(lpad[1:] - zmax + logdvol2) * lpad[1:] +
+                   np.exp(lpad[:-1] - zmax + logdvol2) * lpad[:-1])
+    h = h1 - zmax * np.exp(logz - zmax)
+    dh = np.diff(h, prepend=0)
+    logzvar = np.abs(np.cumsum(dh * (-dlv)))
+    return logwt, logz, logzvar, h
+
+
+class NestedSampler:
+    """Static nested sampler whose bound construction and proposal chains run on the GPU.
+
+    Parameters follow dynesty.NestedSampler (dynesty.py:584-614); `model` is a
+    ``DeviceModel`` instead of the (loglikelihood, prior_transform) callables.
+    `comm`: optional ``dynesty_b200.dist.Comm`` -- chains of a queue fill are sharded over
+    the ranks and all-gathered (NCCL), every rank keeps the identical host state.
+    """
+
+    def __init__(self, model, nlive=500, bound='multi', sample='auto', ncdim=None, walks=None, slices=None,
+                 facc=0.5, enlarge=None, bootstrap=None, update_interval=None, first_update=None,
+                 queue_size=None, periodic=None, reflective=None, seed=56432, ctx=None, comm=None):
+        self.model = model
+        self.ndim = n = model.ndim
+        self.ncdim = ncdim or n
+        self.nlive = int(nlive)
+        self.rstate = np.random.default_rng(seed)
+        self.seed = int(seed)
+        self.ctx = ctx
+        self.comm = comm
+        # -- inner sampler (dynesty.py:126-166)
+        if sample == 'auto':
+            sample = 'unif' if n < 10 else ('rwalk' if n <= 20 else 'rslice')
+        kw = dict(model=model, ndim=n, ncdim=self.ncdim, periodic=periodic, reflective=reflective, facc=facc,
+                  ctx=ctx)
+        if isinstance(sample, str):
+            self.sample_name = sample
+            if sample == 'rwalk':
+                sample = S.B200RWalkSampler(walks=walks or n + 20, **kw)
+            elif sample == 'rslice':
+                sample = S.B200RSliceSampler(slices=slices or 3 + n, **kw)
+            elif sample == 'slice':
+                sample = S.B200SliceSampler(slices=slices or 3, **kw)
+            elif sample == 'unif':
+                sample = S.B200UniformSampler(**kw)
+            else:
+                raise ValueError("Unknown sampling method: '%s'" % sample)
+        else:
+            self.sample_name = type(sample).__name__
+        if self.ncdim != n and isinstance(sample, S._B200SliceBase):
+            raise ValueError('ncdim unsupported for slice sampling')          # dynesty.py:505-507
+        self.internal_sampler_next = sample
+        # -- bound (sampler.py:28-53)
+        if bound == 'multi':
+            bound = B.B200MultiEllipsoid(self.ncdim, ctx=ctx)
+        elif bound == 'single':
+            bound = B.B200Ellipsoid(self.ncdim, ctx=ctx)
+        elif bound == 'none':
+            bound = None
+        elif isinstance(bound, str):
+            raise ValueError("Unknown bounding method: %s (B200 path: none/single/multi)" % bound)
+        self.bound_next = bound
+        self.bound = None
+        self.unit_cube_sampling = True
+        # -- enlarge / bootstrap defaults (dynesty.py:169-211)
+        is_unif = isinstance(sample, S.B200UniformSampler)
+        if enlarge is not None and bootstrap is None:
+            bootstrap = 0
+        elif enlarge is None and bootstrap is not None:
+            enlarge = 1
+        elif enlarge is None and bootstrap is None:
+            enlarge, bootstrap = (1, 5) if is_unif else (1.25, 0)
+        elif not (bootstrap == 0 or enlarge == 1):
+            raise ValueError('Enlarge and bootstrap together do not make sense unless '
+                             'bootstrap=0 or enlarge = 1')
+        self.bound_enlarge, self.bound_bootstrap = float(enlarge), int(bootstrap)
+        # -- update interval in calls (dynesty.py:213-240, 646-649)
+        if update_interval is None:
+            ratio = sample.update_bound_interval_ratio
+        elif isinstance(update_interval, float):
+            ratio = update_interval
+        else:
+            ratio = int(update_interval) / self.nlive
+        self.bound_update_interval = int(max(round(ratio * self.nlive), 1))
+        fu = first_update or {}
+        self.first_bound_update_ncall = fu.get('min_ncall', 2 * self.nlive)    # sampler.py:407-409
+        self.first_bound_update_eff = fu.get('min_eff', 10.)
+        self.logl_first_update = None
+        self.ncall_at_last_update = 0
+        self.queue_size = int(queue_size or self.nlive)
+        if comm is not None and self.queue_size % comm.world:
+            self.queue_size += comm.world - self.queue_size % comm.world
+        # -- live points (sampler.py:56-262, evaluated in one launch)
+        self.live_u = self.rstate.random((self.nlive, n))
+        self.live_v, self.live_logl = model.evaluate(self.live_u, ctx=ctx)
+        self.it = 1
+        self.ncall = self.nlive
+        self.eff = 0.
+        self.nbound = 1
+        self.chain_counter = 0
+        self.scale_history = []
+        self.nbatches = 0
+        self.n_proposals = 0
+        self.bound_history = []           # (ncall, nells, logvol) per update
+        self._q = None
+        self._qpos = 0
+
+    # ------------------------------------------------------------------ bounds
+    def update_bound(self, subset=slice(None)):
+        """sampler.py:493-510."""
+        self.bound.update(self.live_u[subset, :self.ncdim], rstate=self.rstate, bootstrap=self.bound_bootstrap)
+        if self.bound_enlarge != 1.:
+            self.bound.scale_to_logvol(self.bound.logvol + math.log(self.bound_enlarge))
+
+    def update_bound_if_needed(self, loglstar, ncall=None, force=False):
+        """sampler.py:625-674."""
+        if self.bound_next is None:
+            return
+        ncall = self.ncall if ncall is None else ncall
+        call_check_first = ncall >= self.first_bound_update_ncall
+        call_check = ncall >= self.bound_update_interval + self.ncall_at_last_update
+        eff_check = self.eff < self.first_bound_update_eff
+        ucs = self.unit_cube_sampling
+        if ((ucs and eff_check and call_check_first) or (not ucs and call_check) or
+                (ucs and self.logl_first_update is not None and loglstar > self.logl_first_update) or force):
+            subset = (self.live_logl > loglstar) if loglstar == LOWL else slice(None)
+            if ucs:
+                self.unit_cube_sampling = False
+                self.logl_first_update = loglstar
+                self.bound = self.bound_next
+                self.internal_sampler = self.internal_sampler_next
+            self.update_bound(subset)
+            self.nbound += 1
+            self.ncall_at_last_update = ncall
+            self.bound_history.append((ncall, getattr(self.bound, 'nells', 1), float(self.bound.logvol)))
+
+    # ------------------------------------------------------------------ proposals
+    def propose_live(self, loglstar, size):
+        """sampler.py:469-491 for a whole queue: start rows + ellipsoid indices."""
+        idx = np.nonzero(self.live_logl > loglstar)[0]
+        if len(idx) == 0:
+            raise RuntimeError('No live points are above loglstar. Do you have a likelihood plateau ?')
+        starts = idx[self.rstate.integers(len(idx), size=size)]
+        uniq = np.unique(starts)
+        if not self.bound.contains_many(self.live_u[uniq, :self.ncdim]).all():
+            self.update_bound_if_needed(-np.inf, force=True)
+            if not self.bound.contains_many(self.live_u[uniq, :self.ncdim]).all():
+                raise RuntimeError('Update of the ellipsoid failed')
+        ell = self.bound.random_ells(self.rstate, size)
+        return starts, ell
+
+    def _run_sharded(self, fn, Q):
+        """Run chains [lo, hi) of a Q-chain fill on this rank and all-gather."""
+        if self.comm is None:
+            return fn(0, Q)
+        lo, hi = self.comm.shard(Q)
+        return self.comm.allgather(fn(lo, hi), Q)
+
+    def _fill_queue(self, loglstar):
+        """sampler.py:676-717: one launch for `queue_size` proposals."""
+        Q = self.queue_size
+        c0 = self.chain_counter
+        self.chain_counter += Q
+        if self.unit_cube_sampling:
+            # UnitCubeSampler (internal_samplers.py:343-441): u ~ U(0,1)^n, one call each
+            u = self.rstate.random((Q, self.ndim))
+
+            def fn(lo, hi):
+                v, l = self.model.evaluate(u[lo:hi], ctx=self.ctx)
+                return dict(u=u[lo:hi], v=v, logl=l, ncall=np.ones(hi - lo, dtype=np.int32))
+            q = self._run_sharded(fn, Q)
+        else:
+            smp = self.internal_sampler
+            if isinstance(smp, S.B200UniformSampler):
+                def fn(lo, hi):
+                    return smp.run_batch(loglstar, hi - lo, self.bound, self.seed, chain0=c0 + lo, ncdim=self.ncdim)
+            else:
+                starts, ell = self.propose_live(loglstar, Q)
+                pts = self.live_u[starts]
+
+                def fn(lo, hi):
+                    return smp.run_batch(loglstar, pts[lo:hi], ell[lo:hi], self.seed, chain0=c0 + lo)
+            q = self._run_sharded(fn, Q)
+        self.nbatches += 1
+        self.n_proposals += int(q['ncall'].sum())
+        self._q = q
+        self._ql = q['logl'].tolist()
+        self._qn = q['ncall'].tolist()
+        self._qpos = 0
+
+    def _queue_drained(self, loglstar):
+        """The part of _new_point that runs when the last queue item has been popped
+        (sampler.py:757-772): tune with update=True, then the bound-update check."""
+        q = self._q
+        if not self.unit_cube_sampling:
+            smp = self.internal_sampler
+            if 'n_accept' in q:
+                smp.tune({'accept': int(q['n_accept'].sum()), 'reject': int(q['n_reject'].sum()),
+                          'scale': smp.scale}, update=True)
+            elif 'n_expand' in q:
+                warned = bool((q['flags'] & 2).any())
+                smp.tune({'n_expand': int(q['n_expand'].sum()), 'n_contract': int(q['n_contract'].sum()),
+                          'expansion_warning_set': warned}, update=True)
+            self.scale_history.append((self.ncall, smp.scale))
+        self.update_bound_if_needed(loglstar, ncall=self.ncall)
+
+    # ------------------------------------------------------------------ main loop
+    def run_nested(self, dlogz=None, maxiter=None, maxcall=None, add_live=True):
+        """sampler.py:1214-1356 / 1040-1212 (no plateau mode: continuous likelihoods)."""
+        nlive = self.nlive
+        if dlogz is None:
+            dlogz = 1e-3 * (nlive - 1.) + 0.01 if add_live else 0.01
+        maxiter = maxiter if maxiter is not None else 1 << 62
+        maxcall = maxcall if maxcall is not None else 1 << 62
+        dlv = math.log((nlive + 1.) / nlive)
+        half_term = math.log(0.5 * (math.exp(dlv) - 1.0))       # logsumexp([lv+dlv, lv], b=[.5,-.5]) - lv
+        heap = [(float(l), i) for i, l in enumerate(self.live_logl)]
+        heapq.heapify(heap)
+        lmax = float(self.live_logl.max())
+        logz, logvol, loglstar = LOWL, 0.0, LOWL
+        cap = 4 * nlive
+        dead_u = np.empty((cap, self.ndim))
+        dead_v = np.empty((cap, self.ndim))
+        dead_l = np.empty(cap)
+        dead_nc = np.empty(cap, dtype=np.int64)
+        ndead = 0
+        ncall0 = self.ncall
+        for it in range(1 << 62):
+            delta_logz = _logaddexp(0.0, lmax + logvol - logz)
+            if it > maxiter or self.ncall - ncall0 > maxcall:
+                break
+            if dlogz is not None and delta_logz < dlogz:
+                break
+            lnew, worst = heap[0]
+            if lnew == lmax:
+                break                                              # all live points equal: plateau
+            logvol -= dlv
+            # ---- _new_point (sampler.py:732-778)
+            nc = 0
+            while True:
+                if self._q is None or self._qpos >= len(self._ql):
+                    self._fill_queue(lnew)
+                j = self._qpos
+                self._qpos += 1
+                l = self._ql[j]
+                nc += self._qn[j]
+                self.ncall += self._qn[j]
+                if self._qpos >= len(self._ql):
+                    self._queue_drained(lnew)
+                if l > lnew:
+                    break
+            # ---- evidence increment (utils.py:1470-1492, logz part only; h/var post-hoc)
+            logwt = _logaddexp(lnew, loglstar) + logvol + half_term
+            logz = _logaddexp(logz, logwt)
+            loglstar = lnew
+            if ndead == cap:
+                cap *= 2
+                dead_u = np.resize(dead_u, (cap, self.ndim))
+                dead_v = np.resize(dead_v, (cap, self.ndim))
+                dead_l = np.resize(dead_l, cap)
+                dead_nc = np.resize(dead_nc, cap)
+            dead_u[ndead] = self.live_u[worst]
+            dead_v[ndead] = self.live_v[worst]
+            dead_l[ndead] = lnew
+            dead_nc[ndead] = nc
+            ndead += 1
+            q = self._q
+            self.live_u[worst] = q['u'][j]
+            self.live_v[worst] = q['v'][j]
+            self.live_logl[worst] = l
+            heapq.heapreplace(heap, (l, worst))
+            if l > lmax:
+                lmax = l
+            self.eff = 100. * self.it / self.ncall
+            self.it += 1
+        # ---- results (+ remaining live points, sampler.py:780-914)
+        logl = dead_l[:ndead]
+        logvols = -dlv * np.arange(1, ndead + 1)
+        su, sv, nc_all = dead_u[:ndead], dead_v[:ndead], dead_nc[:ndead]
+        if add_live:
+            order = np.argsort(self.live_logl)
+            lv_live = np.log(1. - (np.arange(nlive) + 1.) / (nlive + 1.)) + (logvols[-1] if ndead else 0.0)
+            logl = np.concatenate([logl, self.live_logl[order]])
+            logvols = np.concatenate([logvols, lv_live])
+            su = np.concatenate([su, self.live_u[order]])
+            sv = np.concatenate([sv, self.live_v[order]])
+            nc_all = np.concatenate([nc_all, np.ones(nlive, dtype=np.int64)])
+        logwt, logzs, logzvar, h = _integrate(logl, logvols)
+        self.results = Results(niter=ndead, ncall=int(self.ncall), eff=100. * ndead / max(self.ncall, 1),
+                               samples_u=su, samples=sv, logl=logl, logvol=logvols, logwt=logwt, logz=logzs,
+                               logzerr=np.sqrt(logzvar), information=h, ncall_per_it=nc_all,
+                               nbound=self.nbound, nbatches=self.nbatches, n_proposals=self.n_proposals,
+                               bound_history=list(self.bound_history), scale_history=list(self.scale_history))
+        return self.results

@@ -119,8 +119,9 @@ def _chain_args(model, u0, ncdim, loglstar, scale, seed, chain0, ell, dimflags, 
     a = ChainArgs()
     keep = []
     if u0 is not None:
-        u0 = f64(np.atleast_2d(u0))
-        Q, ndim = u0.shape
+        if not hasattr(u0, 'data_ptr'):          # numpy (host mode); torch tensors pass through
+            u0 = f64(np.atleast_2d(u0))
+        Q, ndim = int(u0.shape[0]), int(u0.shape[1])
         keep.append(u0)
     a.nchain, a.ndim, a.ncdim, a.model_id = Q, ndim, (ncdim or ndim), model
     a.u0 = ptr(u0)
@@ -149,13 +150,16 @@ def dimflags_from(ndim, periodic=None, reflective=None):
 
 
 def rwalk_batch(model, u0, loglstar, scale, walks, seed, chain0=0, ncdim=None, ell=None,
-                dimflags=None, ctx=None):
-    """RWalkSampler.sample for every row of u0 (internal_samplers.py:505-561)."""
+                dimflags=None, ctx=None, out=None):
+    """RWalkSampler.sample for every row of u0 (internal_samplers.py:505-561).
+    `out`: optional dict of preallocated buffers (numpy, or torch tensors on the ctx device
+    when the ctx is in device-pointer mode) with keys u, v, logl, n_accept, n_reject, ncall."""
     ctx = _ctx(ctx)
     a, keep, Q, n = _chain_args(model, u0, ncdim, loglstar, scale, seed, chain0, ell, dimflags)
-    o = dict(u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q),
-             n_accept=np.empty(Q, dtype=np.int32), n_reject=np.empty(Q, dtype=np.int32),
-             ncall=np.empty(Q, dtype=np.int32))
+    o = out if out is not None else dict(
+        u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q),
+        n_accept=np.empty(Q, dtype=np.int32), n_reject=np.empty(Q, dtype=np.int32),
+        ncall=np.empty(Q, dtype=np.int32))
     ctx.check(ctx.lib.b2n_rwalk_batch(ctx.h, C.byref(a), int(walks), ptr(o['u']), ptr(o['v']),
                                       ptr(o['logl']), ptr(o['n_accept']), ptr(o['n_reject']),
                                       ptr(o['ncall'])))
@@ -184,11 +188,15 @@ def slice_batch(model, u0, loglstar, scale, slices, seed, chain0=0, doubling=Fal
     return _slice_batch('b2n_slice_batch', model, u0, loglstar, scale, slices, seed, chain0, doubling, ell, ctx)
 
 
-def unif_batch(model, nchain, ndim, loglstar, seed, chain0=0, ncdim=None, dimflags=None, ctx=None):
-    """UniformBoundSampler.sample x nchain on the resident bound (internal_samplers.py:243-340)."""
+def unif_batch(model, nchain, ndim, loglstar, seed, chain0=0, ncdim=None, dimflags=None, ctx=None,
+               draw_only=False):
+    """UniformBoundSampler.sample x nchain on the resident bound (internal_samplers.py:243-340).
+    draw_only=True: just Bound.samples(nchain) (no cube test / likelihood)."""
     ctx = _ctx(ctx)
     a, keep, Q, n = _chain_args(model, None, ncdim, loglstar, 1.0, seed, chain0, None, dimflags,
                                 Q=int(nchain), ndim=int(ndim))
+    if draw_only:
+        a.reserved = 1
     o = dict(u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q), ncall=np.empty(Q, dtype=np.int32),
              nprop=np.empty(Q, dtype=np.int32), flags=np.empty(Q, dtype=np.uint32))
     ctx.check(ctx.lib.b2n_unif_batch(ctx.h, C.byref(a), ptr(o['u']), ptr(o['v']), ptr(o['logl']),

@@ -1,0 +1,248 @@
+"""B200 inner samplers: drop-in mirrors of dynesty's ``RWalkSampler`` / ``RSliceSampler`` /
+``SliceSampler`` / ``UniformBoundSampler`` (internal_samplers.py:206-863).
+
+The reference maps a *static* ``sample(args)`` over the queue, one task per chain
+(sampler.py:708-717).  Here ``prepare_sampler`` -- which the reference calls once with ALL
+queue slots -- launches ONE kernel for the whole queue and returns the finished
+``SamplerReturn`` tuples as the "arguments"; the static ``sample`` is then the identity,
+so ``mapper(self.internal_sampler.sample, args)`` (sampler.py:717) works unchanged with
+any mapper (``map``, ``B200Pool.map``, a real pool).
+
+The likelihood is evaluated in-kernel, so each sampler is constructed with a
+``DeviceModel`` (``model=``); dynesty's ``_new_from_template`` re-instantiates with the
+same kwargs (internal_samplers.py:96-109), so the model travels with it.
+"""
+import math
+import warnings
+
+import numpy as np
+
+from . import ops, _lib
+from ._compat import InternalSamplerBase, SamplerReturn
+from .bounding import TaggedAxes
+
+__all__ = ['B200RWalkSampler', 'B200RSliceSampler', 'B200SliceSampler', 'B200UniformSampler']
+
+
+def _seed_of(seeds, fallback_rstate=None):
+    """One 64-bit Philox seed per queue fill from what Sampler passes as `seeds`
+    (SeedSequence children when queue_size > 1, else the master Generator itself,
+    sampler.py:695-699)."""
+    s = seeds[0]
+    if isinstance(s, np.random.Generator):
+        return int(s.integers(0, 2**63 - 1))
+    if isinstance(s, np.random.SeedSequence):
+        w = s.generate_state(2, dtype=np.uint32)
+        return (int(w[0]) | (int(w[1]) << 32)) & (2**63 - 1)
+    return int(s) & (2**63 - 1)
+
+
+class _Resident:
+    """Keeps the device copy of the current bound's ellipsoids in sync."""
+
+    def __init__(self):
+        self.key = None
+
+    def ensure(self, axes_list, ctx):
+        """Returns the int32 ellipsoid index of every chain."""
+        a0 = axes_list[0]
+        if isinstance(a0, TaggedAxes) and a0.bound is not None and hasattr(a0.bound, 'make_resident'):
+            b = a0.bound
+            key = (id(b), getattr(b, 'version', None))
+            if key != self.key:
+                b.make_resident()
+                self.key = key
+            return np.fromiter((a.ell for a in axes_list), dtype=np.int32, count=len(axes_list))
+        # foreign Bound (e.g. the reference's own classes or a user Box bound,
+        # tests/test_bound_interface.py:20-49): upload the distinct matrices of this fill
+        uniq, ell = {}, np.empty(len(axes_list), dtype=np.int32)
+        mats = []
+        for i, a in enumerate(axes_list):
+            k = id(a)
+            if k not in uniq:
+                uniq[k] = len(mats)
+                mats.append(np.asarray(a, dtype=float))
+            ell[i] = uniq[k]
+        ops.bound_set(np.array(mats), ctx=ctx)
+        self.key = None
+        return ell
+
+
+class _B200Sampler(InternalSamplerBase):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.model = kwargs.get('model')
+        if self.model is None:
+            raise ValueError("B200 samplers evaluate the likelihood in-kernel: pass model=<DeviceModel>")
+        self._ctx = kwargs.get('ctx')
+        self.ncdim = kwargs.get('ncdim')
+        self._res = _Resident()
+        self.chain_counter = 0
+        self.last_batch = None
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d['_ctx'] = None
+        d['_res'] = _Resident()
+        d['last_batch'] = None
+        if 'input_kwargs' in d:
+            d['input_kwargs'] = {k: v for k, v in d['input_kwargs'].items() if k != 'ctx'}
+        return d
+
+    def _flags(self):
+        per, ref = self.sampler_kwargs.get('periodic'), self.sampler_kwargs.get('reflective')
+        return ops.dimflags_from(self.ndim or self.model.ndim, per, ref)
+
+    @staticmethod
+    def sample(args):
+        """The chain already ran inside ``prepare_sampler``'s launch."""
+        return args
+
+
+class B200RWalkSampler(_B200Sampler):
+    """internal_samplers.py:444-565."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        walks = max(2, kwargs.get('walks', 25) or 25)
+        self.facc = min(1., max(1. / walks, kwargs.get('facc', 0.5) or 0.5))
+        self.rwalk_history = {'n_accept': 0, 'n_reject': 0}
+        self.sampler_kwargs['walks'] = walks
+        self.sampler_kwargs['ncdim'] = self.ncdim
+
+    @property
+    def update_bound_interval_ratio(self):
+        return self.sampler_kwargs['walks']
+
+    def run_batch(self, loglstar, points, ell, seed, chain0=0):
+        walks = self.sampler_kwargs['walks']
+        return ops.rwalk_batch(self.model.model_id(self._ctx), points, loglstar, self.scale, walks, seed,
+                               chain0=chain0, ncdim=self.ncdim or self.model.ndim, ell=ell,
+                               dimflags=self._flags(), ctx=self._ctx)
+
+    def prepare_sampler(self, loglstar=None, points=None, axes=None, seeds=None, prior_transform=None,
+                        loglikelihood=None, nested_sampler=None):
+        ell = self._res.ensure(axes, self._ctx)
+        o = self.run_batch(loglstar, np.asarray(points), ell, _seed_of(seeds))
+        self.last_batch = o
+        sc = self.scale
+        return [SamplerReturn(u=o['u'][i], v=o['v'][i], logl=float(o['logl'][i]), ncalls=int(o['ncall'][i]),
+                              evaluation_history=[],
+                              tuning_info={'accept': int(o['n_accept'][i]), 'reject': int(o['n_reject'][i]),
+                                           'scale': sc},
+                              proposal_stats={'n_accept': int(o['n_accept'][i]),
+                                              'n_reject': int(o['n_reject'][i])})
+                for i in range(len(o['logl']))]
+
+    def tune(self, tuning_info, update=True):
+        """internal_samplers.py:460-493."""
+        self.scale = tuning_info['scale']
+        h = self.rwalk_history
+        h['n_accept'] += tuning_info['accept']
+        h['n_reject'] += tuning_info['reject']
+        if not update:
+            return
+        facc = h['n_accept'] / (h['n_accept'] + h['n_reject'])
+        self.scale *= math.exp((facc - self.facc) / self.ncdim / self.facc)
+        h['n_accept'] = h['n_reject'] = 0
+
+    @property
+    def citations(self):
+        return [("Skilling (2006)", "projecteuclid.org/euclid.ba/1340370944")]
+
+
+class _B200SliceBase(_B200Sampler):
+    _fn = None
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.sampler_kwargs['slices'] = kwargs.get('slices', 5) or 5
+        self.slice_history = {'n_contract': 0, 'n_expand': 0}
+
+    def run_batch(self, loglstar, points, ell, seed, chain0=0):
+        fn = getattr(ops, self._fn)
+        return fn(self.model.model_id(self._ctx), points, loglstar, self.scale, self.sampler_kwargs['slices'],
+                  seed, chain0=chain0, doubling=bool(self.sampler_kwargs.get('slice_doubling', False)),
+                  ell=ell, ctx=self._ctx)
+
+    def prepare_sampler(self, loglstar=None, points=None, axes=None, seeds=None, prior_transform=None,
+                        loglikelihood=None, nested_sampler=None):
+        ell = self._res.ensure(axes, self._ctx)
+        o = self.run_batch(loglstar, np.asarray(points), ell, _seed_of(seeds))
+        self.last_batch = o
+        out = []
+        for i in range(len(o['logl'])):
+            warned = bool(o['flags'][i] & _lib.WARN_DOUBLING)
+            ne, nc = int(o['n_expand'][i]), int(o['n_contract'][i])
+            out.append(SamplerReturn(u=o['u'][i], v=o['v'][i], logl=float(o['logl'][i]),
+                                     ncalls=int(o['ncall'][i]), evaluation_history=[],
+                                     tuning_info={'n_expand': ne, 'n_contract': nc,
+                                                  'expansion_warning_set': warned},
+                                     proposal_stats={'n_expand': ne, 'n_contract': nc}))
+        return out
+
+    def tune(self, tuning_info, update=True):
+        """tune_slice (internal_samplers.py:1209-1239)."""
+        h = self.slice_history
+        h['n_expand'] += tuning_info['n_expand']
+        h['n_contract'] += tuning_info['n_contract']
+        if tuning_info['expansion_warning_set']:
+            if not self.sampler_kwargs.get('slice_doubling'):
+                warnings.warn('Enabling doubling strategy of slice sampling from Neal(2003)')
+            self.sampler_kwargs['slice_doubling'] = True
+        if not update:
+            return
+        ne, nc = max(h['n_expand'], 1), h['n_contract']
+        self.scale = self.scale * min(max(ne * 2. / (ne + nc), 0.5), 2.)
+        h['n_expand'] = h['n_contract'] = 0
+
+    @property
+    def citations(self):
+        return [("Neal (2003)", "projecteuclid.org/euclid.aos/1056562461"),
+                ("Handley, Hobson & Lasenby (2015a)", "ui.adsabs.harvard.edu/abs/2015MNRAS.450L..61H"),
+                ("Handley, Hobson & Lasenby (2015b)", "ui.adsabs.harvard.edu/abs/2015MNRAS.453.4384H")]
+
+
+class B200RSliceSampler(_B200SliceBase):
+    """internal_samplers.py:720-863."""
+    _fn = 'rslice_batch'
+
+    @property
+    def update_bound_interval_ratio(self):
+        return self.sampler_kwargs['slices']
+
+
+class B200SliceSampler(_B200SliceBase):
+    """internal_samplers.py:568-717."""
+    _fn = 'slice_batch'
+
+    @property
+    def update_bound_interval_ratio(self):
+        return self.sampler_kwargs['slices'] * (self.ndim or self.model.ndim)
+
+
+class B200UniformSampler(_B200Sampler):
+    """internal_samplers.py:206-340; needs a B200 bound (the kernel draws from the
+    device-resident ellipsoids)."""
+
+    def run_batch(self, loglstar, nchain, bound, seed, chain0=0, ncdim=None):
+        key = (id(bound), getattr(bound, 'version', None))
+        if key != self._res.key:
+            bound.make_resident()
+            self._res.key = key
+        n = self.ndim or self.model.ndim
+        flags = self._flags()
+        return ops.unif_batch(self.model.model_id(self._ctx), nchain, n, loglstar, seed, chain0=chain0,
+                              ncdim=ncdim or self.ncdim or n, dimflags=flags, ctx=self._ctx)
+
+    def prepare_sampler(self, loglstar=None, points=None, axes=None, seeds=None, prior_transform=None,
+                        loglikelihood=None, nested_sampler=None):
+        bound = nested_sampler.bound
+        if not hasattr(bound, 'make_resident'):
+            raise TypeError("B200UniformSampler needs bound=B200Ellipsoid/B200MultiEllipsoid")
+        o = self.run_batch(loglstar, len(points), bound, _seed_of(seeds), ncdim=nested_sampler.ncdim)
+        self.last_batch = o
+        return [SamplerReturn(u=o['u'][i], v=o['v'][i], logl=float(o['logl'][i]), ncalls=int(o['ncall'][i]),
+                              evaluation_history=[], tuning_info=None,
+                              proposal_stats={'n_proposals': int(o['nprop'][i])})
+                for i in range(len(o['logl']))]

@@ -74,6 +74,11 @@ const char* b2n_last_error(b2n_ctx* ctx);
 const char* b2n_version(void);
 /* number of kernel launches issued through this ctx since b2n_init (bench.py gpu_launches) */
 int64_t b2n_launch_count(b2n_ctx* ctx);
+/* kernel timing for the roofline: when enabled, the chain entry points bracket their main
+ * kernel with CUDA events on the ctx stream; b2n_last_kernel_ms waits for it and returns the
+ * duration of the most recent one (ms, <0 if none). */
+int  b2n_set_timing(b2n_ctx* ctx, int enabled);
+double b2n_last_kernel_ms(b2n_ctx* ctx);
 
 /* ---- device models: the "device-side likelihood callback" -----------------
  * The reference evaluates user Python callables prior_transform(u) and
@@ -159,6 +164,11 @@ int b2n_bootstrap_expand(b2n_ctx* ctx, const double* points, int64_t N, int32_t 
 int b2n_bound_set(b2n_ctx* ctx, int32_t K, int32_t ncdim, const double* ctrs,
                   const double* ams, const double* axes, const double* logvols);
 
+/* b2n_unif_batch only: draw from the bound without the unit-cube test and without
+ * evaluating a model (Bound.samples, bounding.py:321-334, 592-606); needs ndim == ncdim,
+ * model_id ignored. */
+#define B2N_OPT_DRAW_ONLY 1
+
 /* ---- proposal chains ----------------------------------------------------------
  * One chain per queue slot (sampler.py:690-717).  Chain q consumes the B2N
  * Philox stream (seed, chain0 + q) -- see oracle/philox.py for the layout. */
@@ -167,7 +177,7 @@ typedef struct {
     int32_t ndim;            /* n                                                   */
     int32_t ncdim;           /* clustered dims (axes are ncdim x ncdim)              */
     int32_t model_id;
-    int32_t reserved;
+    int32_t reserved;        /* option bits: B2N_OPT_*                               */
     const double* u0;        /* Q x ndim start points (live points with logl > loglstar) */
     const int32_t* ell;      /* HOST, Q: index into the resident bound of the axes of
                                 each chain (get_random_axes, bounding.py:726-731); NULL = 0 */

@@ -185,3 +185,40 @@ class ScriptedGenerator(np.random.Generator):
 
     def choice(self, *a, **k):  # pragma: no cover
         raise NotImplementedError("not scripted")
+
+
+class NumpyStream:
+    """Same interface as ChainStream but backed by numpy's native PCG64 Generator, i.e.
+    exactly what the reference uses (utils.py:993-999).  Used by bench.py's cpu_baseline /
+    --impl reference legs so that the timed CPU path has the reference's RNG cost, not
+    the cost of emulating Philox in numpy."""
+
+    def __init__(self, seed, chain):
+        self.g = np.random.Generator(np.random.PCG64([int(seed), int(chain)]))
+        self.tick = 0
+
+    def uniform(self):
+        self.tick += 1
+        return self.g.random()
+
+    def uniforms(self, m):
+        if m == 0:
+            return np.empty(0)
+        self.tick += 1
+        return self.g.random(m)
+
+    def normals(self, m):
+        if m == 0:
+            return np.empty(0)
+        self.tick += 1
+        return self.g.standard_normal(m)
+
+    def integers(self, n, m):
+        self.tick += 1
+        return self.g.integers(n, size=m)
+
+    def permutation(self, m):
+        if m <= 1:
+            return np.arange(m)
+        self.tick += 1
+        return self.g.permutation(m)

@@ -20,3 +20,11 @@ def golden():
     import numpy as np
     return {k: np.load(os.path.join(GOLDEN, k + '.npz'))
             for k in ('bounding', 'multi', 'chains')}
+
+
+@pytest.fixture
+def fake_ops(monkeypatch):
+    """CPU stand-in for dynesty_b200.ops built from the oracle (tests only)."""
+    import fake_backend
+    fake_backend.install(monkeypatch)
+    return fake_backend

@@ -1,0 +1,230 @@
+"""TEST-ONLY stand-in for ``dynesty_b200.ops`` built from the oracle.
+
+The product has no CPU path.  To exercise the HOST logic (``dynesty_b200.nested``, the
+Bound / InternalSampler mirrors, the dynesty drop-in seams, the multi-rank sharding) in
+the CPU-only test tier, the fixture ``fake_ops`` monkeypatches the array-level functions
+of ``dynesty_b200.ops`` with oracle-backed equivalents that honour the same contract
+(same arguments, same outputs, same Philox streams).  Nothing outside tests/ imports this.
+"""
+import numpy as np
+
+from oracle import bounding as OB, samplers as OS, philox, likelihoods as OL
+
+_state = {}
+_models = []
+
+
+def _to_oracle_model(dm, prior_kind):
+    p = {}
+    if prior_kind == OL.PRIOR_UNIFORM:
+        p.update(lo=dm.prior_p0, width=dm.prior_p1)
+    elif prior_kind == OL.PRIOR_NORMAL_PPF:
+        p.update(mu=dm.prior_p0, sigma=dm.prior_p1)
+    k = dm.like_kind
+    if k == OL.LIKE_GAUSS_PREC:
+        p.update(mean=dm.like_vec0, prec=dm.like_mat, lnorm=dm.s[0])
+    elif k == OL.LIKE_GAUSS_DIAG:
+        p.update(mean=dm.like_vec0, ivar=dm.like_vec1, lnorm=dm.s[0])
+    elif k == OL.LIKE_EGGBOX:
+        p.update(tmax=dm.s[0], power=dm.s[1])
+    else:
+        p.update(c1=dm.like_vec0, c2=dm.like_vec1, r=dm.s[0], w=dm.s[1])
+    return OL.Model(dm.ndim, prior_kind, k, **p)
+
+
+def model_ids(self, ctx=None):
+    if not hasattr(self, '_fake_ids'):
+        _models.append(_to_oracle_model(self, self.prior_kind))
+        _models.append(_to_oracle_model(self, OL.PRIOR_IDENTITY))
+        self._fake_ids = (len(_models) - 2, len(_models) - 1)
+    return self._fake_ids
+
+
+def model_eval(model, u, want_v=True, ctx=None):
+    m = _models[model]
+    u = np.atleast_2d(np.asarray(u, dtype=float))
+    v = m.prior_transform(u)
+    return (v if want_v else None), np.asarray(m.loglike(v), dtype=float).reshape(len(u))
+
+
+def membership(x, ctrs, ams, strict=True, want_d2=False, ctx=None):
+    x = np.atleast_2d(np.asarray(x, dtype=float))
+    ctrs = np.atleast_2d(ctrs)
+    ams = np.asarray(ams).reshape(len(ctrs), ctrs.shape[1], ctrs.shape[1])
+    d = x[:, None, :] - ctrs[None]
+    d2 = np.einsum('mki,kij,mkj->mk', d, ams, d)
+    mask = d2 < 1 if strict else d2 <= 1
+    out = (mask, mask.sum(1).astype(np.int32))
+    return out + (d2,) if want_d2 else out
+
+
+def _ell_out(e):
+    lam, vec = np.linalg.eigh(e.cov)
+    return dict(ctr=e.ctr, cov=e.cov, am=e.am, axes=vec * np.sqrt(lam), axlens=np.sqrt(lam),
+                logvol=float(e.logvol), warn=0)
+
+
+def bounding_ellipsoid(points, ctx=None):
+    return _ell_out(OB.bounding_ellipsoid(points))
+
+
+def multi_decompose(points, max_ells=None, ctx=None):
+    me, members = OB.multi_update(points)
+    outs = [_ell_out(e) for e in me.ells]
+    labels = np.empty(len(points), dtype=np.int32)
+    for k, m in enumerate(members):
+        labels[m] = k
+    return dict(nells=me.nells, labels=labels, warn=0,
+                ctrs=np.array([o['ctr'] for o in outs]), covs=np.array([o['cov'] for o in outs]),
+                ams=np.array([o['am'] for o in outs]), axes=np.array([o['axes'] for o in outs]),
+                axlens=np.array([o['axlens'] for o in outs]), logvols=np.array([o['logvol'] for o in outs]))
+
+
+def scale_to_logvol(covs, ams, axes, axlens, logvols, targets, ctx=None):
+    for k in range(len(logvols)):
+        e = OB.Ell.__new__(OB.Ell)
+        e.ndim = covs.shape[1]
+        e.ctr, e.cov, e.am, e.axes, e.axlens, e.logvol = None, covs[k], ams[k], axes[k], axlens[k], logvols[k]
+        e.scale_to_logvol(float(np.asarray(targets)[k]))
+        covs[k], ams[k], axes[k], axlens[k], logvols[k] = e.cov, e.am, e.axes, e.axlens, e.logvol
+
+
+def bootstrap_expand(points, multi, nboot, seed, chain0, ctx=None):
+    out = np.empty(nboot)
+    for r in range(nboot):
+        s = philox.ChainStream(seed, chain0 + r)
+        sel = OB.bootstrap_split(len(points), s.integers(len(points), len(points)))
+        out[r] = OB.bootstrap_expand(np.asarray(points), sel, bool(multi))
+    return out
+
+
+def bound_set(axes, ctrs=None, ams=None, logvols=None, ctx=None):
+    axes = np.asarray(axes, dtype=float)
+    if axes.ndim == 2:
+        axes = axes[None]
+    _state['axes'] = axes.copy()
+    _state['ctrs'] = None if ctrs is None else np.array(ctrs, dtype=float).reshape(len(axes), -1)
+    _state['ams'] = None if ams is None else np.array(ams, dtype=float).reshape(axes.shape)
+    _state['logvols'] = None if logvols is None else np.array(logvols, dtype=float).reshape(-1)
+
+
+def dimflags_from(ndim, periodic=None, reflective=None):
+    if periodic is None and reflective is None:
+        return None
+    f = np.zeros(ndim, dtype=np.uint8)
+    if periodic is not None:
+        f[np.asarray(periodic, dtype=int)] |= 1
+    if reflective is not None:
+        f[np.asarray(reflective, dtype=int)] |= 2
+    return f
+
+
+def rwalk_batch(model, u0, loglstar, scale, walks, seed, chain0=0, ncdim=None, ell=None, dimflags=None,
+                ctx=None):
+    m = _models[model]
+    u0 = np.atleast_2d(u0)
+    Q, n = u0.shape
+    per = ref = nb = None
+    if dimflags is not None:
+        f = np.asarray(dimflags)
+        per = np.nonzero(f & 1)[0] if (f & 1).any() else None
+        ref = np.nonzero(f & 2)[0] if (f & 2).any() else None
+        nb = f == 0
+    o = dict(u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q), n_accept=np.empty(Q, dtype=np.int32),
+             n_reject=np.empty(Q, dtype=np.int32), ncall=np.empty(Q, dtype=np.int32))
+    for i in range(Q):
+        ax = _state['axes'][0 if ell is None else ell[i]]
+        r = OS.rwalk_chain(u0[i], loglstar, ax, scale, m, philox.ChainStream(seed, chain0 + i), walks,
+                           periodic=per, reflective=ref, nonbounded=nb)
+        o['u'][i], o['v'][i], o['logl'][i] = r['u'], r['v'], r['logl']
+        o['n_accept'][i], o['n_reject'][i], o['ncall'][i] = r['n_accept'], r['n_reject'], r['ncall']
+    return o
+
+
+def _slice(fn, model, u0, loglstar, scale, slices, seed, chain0, doubling, ell):
+    m = _models[model]
+    u0 = np.atleast_2d(u0)
+    Q, n = u0.shape
+    o = dict(u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q), n_expand=np.empty(Q, dtype=np.int32),
+             n_contract=np.empty(Q, dtype=np.int32), ncall=np.empty(Q, dtype=np.int32),
+             flags=np.zeros(Q, dtype=np.uint32))
+    for i in range(Q):
+        ax = _state['axes'][0 if ell is None else ell[i]]
+        r = fn(u0[i], loglstar, ax, scale, m, philox.ChainStream(seed, chain0 + i), slices, doubling=doubling)
+        o['u'][i], o['v'][i], o['logl'][i] = r['u'], r['v'], r['logl']
+        o['n_expand'][i], o['n_contract'][i], o['ncall'][i] = r['n_expand'], r['n_contract'], r['ncall']
+        o['flags'][i] = 2 if r['expansion_warning_set'] else 0
+    return o
+
+
+def rslice_batch(model, u0, loglstar, scale, slices, seed, chain0=0, doubling=False, ell=None, ctx=None):
+    return _slice(OS.rslice_chain, model, u0, loglstar, scale, slices, seed, chain0, doubling, ell)
+
+
+def slice_batch(model, u0, loglstar, scale, slices, seed, chain0=0, doubling=False, ell=None, ctx=None):
+    return _slice(OS.slice_chain, model, u0, loglstar, scale, slices, seed, chain0, doubling, ell)
+
+
+def unif_batch(model, nchain, ndim, loglstar, seed, chain0=0, ncdim=None, dimflags=None, ctx=None,
+               draw_only=False):
+    from scipy.special import logsumexp
+    K = len(_state['axes'])
+    me = OB.MultiEll.__new__(OB.MultiEll)
+    me.ells = []
+    for k in range(K):
+        e = OB.Ell.__new__(OB.Ell)
+        e.ctr, e.am, e.axes = _state['ctrs'][k], _state['ams'][k], _state['axes'][k]
+        e.ndim = len(e.ctr)
+        me.ells.append(e)
+    me.nells, me.ctrs, me.ams, me.logvol_ells = K, _state['ctrs'], _state['ams'], _state['logvols']
+    me.logvol = logsumexp(me.logvol_ells)
+    Q, n = int(nchain), int(ndim)
+    o = dict(u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q), ncall=np.empty(Q, dtype=np.int32),
+             nprop=np.empty(Q, dtype=np.int32), flags=np.zeros(Q, dtype=np.uint32))
+    if draw_only:
+        class _Flat:
+            ndim = n
+
+            @staticmethod
+            def prior_transform(u):
+                return np.full_like(u, 0.5)
+
+            @staticmethod
+            def loglike(v):
+                return 0.0
+        # draw-only: accept the first bound draw irrespective of the cube
+        for i in range(Q):
+            s = philox.ChainStream(seed, chain0 + i)
+            if K == 1:
+                x = me.ells[0].ctr + me.ells[0].axes @ OS.randsphere(n, s)
+            else:
+                cum = np.cumsum(np.exp(me.logvol_ells - me.logvol))
+                while True:
+                    idx = min(int(np.searchsorted(cum, s.uniform())), K - 1)
+                    x = me.ells[idx].ctr + me.ells[idx].axes @ OS.randsphere(n, s)
+                    q = int((me.mahal2(x)[0] < 1).sum())
+                    if q <= 1 or s.uniform() < 1. / q:
+                        break
+            o['u'][i] = o['v'][i] = x
+            o['logl'][i], o['ncall'][i], o['nprop'][i] = 0.0, 0, 1
+        return o
+    m = _models[model]
+    nb = None if dimflags is None else (np.asarray(dimflags) == 0)
+    for i in range(Q):
+        r = OS.unif_chain(loglstar, me, m, philox.ChainStream(seed, chain0 + i), n, nonbounded=nb)
+        o['u'][i], o['v'][i], o['logl'][i], o['ncall'][i] = r['u'], r['v'], r['logl'], r['ncall']
+        o['nprop'][i] = r['ncall']
+    return o
+
+
+FUNCS = ['model_eval', 'membership', 'bounding_ellipsoid', 'multi_decompose', 'scale_to_logvol',
+         'bootstrap_expand', 'bound_set', 'dimflags_from', 'rwalk_batch', 'rslice_batch', 'slice_batch',
+         'unif_batch']
+
+
+def install(monkeypatch):
+    from dynesty_b200 import ops, likelihoods
+    g = globals()
+    for name in FUNCS:
+        monkeypatch.setattr(ops, name, g[name])
+    monkeypatch.setattr(likelihoods.DeviceModel, 'ids', model_ids)

@@ -1,0 +1,79 @@
+"""CPU tier: the B200 bounds / samplers / pool plugged into the UNMODIFIED reference
+``dynesty.NestedSampler`` through its official seams (bound= / sample= / pool=), the same
+way the reference's tests/test_bound_interface.py and tests/test_sampler_interface.py
+plug in user classes.  Numerics come from the oracle-backed stand-in (tests/fake_backend.py);
+what is pinned is the interface contract.  Skipped where the reference is absent (GPU box).
+"""
+import numpy as np
+import pytest
+
+from oracle import refshim
+
+pytestmark = pytest.mark.skipif(not refshim.available(), reason="reference not present")
+
+
+@pytest.fixture(scope='module')
+def dynesty():
+    return refshim.import_reference()
+
+
+def _classes():
+    # import AFTER the reference so that the mirrors subclass dynesty's own base classes
+    import importlib
+    import dynesty_b200._compat as c
+    importlib.reload(c)
+    import dynesty_b200.bounding as b
+    import dynesty_b200.samplers as s
+    importlib.reload(b)
+    importlib.reload(s)
+    return c, b, s
+
+
+@pytest.mark.parametrize('bound,sample', [('multi', 'rwalk'), ('single', 'rslice'), ('multi', 'slice'),
+                                          ('multi', 'unif')])
+def test_dropin_run(dynesty, fake_ops, bound, sample):
+    c, b, s = _classes()
+    assert c.HAVE_DYNESTY
+    from dynesty_b200 import likelihoods as DL
+    from dynesty_b200.pool import B200Pool
+    from dynesty import bounding as RB, internal_samplers as RIS
+    m = DL.gauss_test3d()
+    bnd = {'multi': b.B200MultiEllipsoid, 'single': b.B200Ellipsoid}[bound](3)
+    smp = {'rwalk': lambda: s.B200RWalkSampler(model=m, walks=10),
+           'rslice': lambda: s.B200RSliceSampler(model=m, slices=3),
+           'slice': lambda: s.B200SliceSampler(model=m, slices=2),
+           'unif': lambda: s.B200UniformSampler(model=m)}[sample]()
+    assert isinstance(bnd, RB.Bound) and isinstance(smp, RIS.InternalSampler)
+    rstate = np.random.default_rng(56432)
+    ns = dynesty.NestedSampler(m.loglikelihood, m.prior_transform, 3, nlive=100, bound=bnd, sample=smp,
+                               pool=B200Pool(32), queue_size=32, rstate=rstate, bootstrap=0,
+                               use_pool={'prior_transform': False, 'loglikelihood': False})
+    ns.run_nested(dlogz=0.5, print_progress=False)
+    res = ns.results
+    truth = 3 * (-np.log(20.))
+    assert abs(res['logz'][-1] - truth) < 5 * res['logzerr'][-1] + 0.1
+    assert ns.nbound > 1                                   # the B200 bound was updated by Sampler
+    assert isinstance(ns.bound, type(bnd))
+    assert isinstance(ns.internal_sampler, type(smp))
+    assert ns.internal_sampler.model is m                  # survives _new_from_template
+
+
+def test_reference_bound_with_b200_sampler(dynesty, fake_ops):
+    """A foreign Bound (the reference's own MultiEllipsoid, bound='multi') feeding the B200
+    rwalk sampler: axes arrive as plain ndarrays and are uploaded per fill."""
+    c, b, s = _classes()
+    from dynesty_b200 import likelihoods as DL
+    from dynesty_b200.pool import B200Pool
+    m = DL.gauss_test3d()
+    ns = dynesty.NestedSampler(m.loglikelihood, m.prior_transform, 3, nlive=100, bound='multi',
+                               sample=s.B200RWalkSampler(model=m, walks=10), pool=B200Pool(16),
+                               queue_size=16, rstate=np.random.default_rng(1),
+                               use_pool={'prior_transform': False, 'loglikelihood': False})
+    ns.run_nested(dlogz=0.5, print_progress=False)
+    assert abs(ns.results['logz'][-1] - 3 * (-np.log(20.))) < 5 * ns.results['logzerr'][-1] + 0.1
+
+
+def test_sampler_requires_model(dynesty):
+    c, b, s = _classes()
+    with pytest.raises(ValueError):
+        s.B200RWalkSampler(walks=5)
