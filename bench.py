@@ -96,10 +96,13 @@ def cpu_sample(cfg, target_seconds, pool, cores, state=None):
     ell.scale_to_logvol(ell.logvol + math.log(1.25))
     rng = np.random.default_rng(1)
     scale, walks, n = 0.15, cfg['walks'], cfg['ndim']
+    # pilot on every process at once (import + contention included) to size the bounded sample
+    pilot = [(u[:4], loglstar, ell.axes, scale, walks, c * 4, n) for c in range(cores)]
     t0 = time.perf_counter()
-    _cpu_worker((u[:2], loglstar, ell.axes, scale, walks, 0, n))
-    per_chain = (time.perf_counter() - t0) / 2
-    per_core = max(2, int(target_seconds / per_chain))
+    _ = pool.map(_cpu_worker, pilot) if pool is not None else [_cpu_worker(t) for t in pilot]
+    _ = pool.map(_cpu_worker, pilot) if pool is not None else None
+    per_chain = (time.perf_counter() - t0) / (8 if pool is not None else 4)
+    per_core = max(4, min(int(target_seconds / per_chain), 20000))
     tasks = []
     for c in range(cores):
         starts = u[rng.integers(len(u), size=per_core)]
@@ -236,7 +239,11 @@ def run_b200(args, cfg):
         g_u = torch.empty(world * Q, n, dtype=torch.float64, device=dev)
         g_l = torch.empty(world * Q, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream shared by torch and the library, so that torch's CUDA
+    # events bracket the library's launches (a NULL handle would mean "library-owned stream")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     ctx.set_timing(True)
 

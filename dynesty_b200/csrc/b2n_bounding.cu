@@ -152,7 +152,7 @@ __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* cc, doub
     const int T = blockDim.x, tid = threadIdx.x;
     const int m = (n + 1) & ~1, half = m >> 1;
     int sweep = 0;
-    for (; sweep < 60; sweep++) {
+    for (; sweep < 40; sweep++) {
         double off = 0.0, dg = 0.0;
         for (int e = tid; e < n * n; e += T) {
             const int i = e / n, j = e - i * n;
@@ -163,7 +163,9 @@ __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* cc, doub
         dg = block_sum(dg, red);
         const double tot = off + dg;
         if (!(tot < INFINITY) || tot == 0.0) break;      // NaN/Inf or all-zero matrix
-        if (off <= 1e-31 * tot) break;
+        // converged at the round-off floor of the off-diagonal mass (n^2 entries of size
+        // ~eps*||A||): the same absolute accuracy LAPACK's eigh delivers
+        if (off <= (double)n * (double)n * 2.5e-32 * tot) break;
         for (int r = 0; r < m - 1; r++) {
             for (int k = tid; k < half; k += T) {
                 int p, q;
@@ -171,7 +173,7 @@ __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* cc, doub
                 double c = 1.0, s = 0.0;
                 if (q < n) {
                     const double app = A[(size_t)p * ld + p], aqq = A[(size_t)q * ld + q], apq = A[(size_t)p * ld + q];
-                    if (apq != 0.0 && fabs(apq) > 1e-20 * sqrt(fabs(app * aqq))) {
+                    if (apq != 0.0 && fabs(apq) > 1e-17 * sqrt(fabs(app * aqq))) {
                         const double tau = (aqq - app) / (2.0 * apq);
                         const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
                         c = 1.0 / sqrt(fma(t, t, 1.0));

@@ -9,7 +9,7 @@
 #pragma once
 #include "b2n_device.cuh"
 
-#define B2N_ROWS_PER_JOB 512     // rows of a node handled by one moment / fmax job
+#define B2N_ROWS_PER_JOB 128     // rows of a node handled by one moment / fmax job
 #define B2N_TILE 64              // covariance output tile edge
 #define B2N_TK 16                // rows per shared-memory stage of the covariance kernel
 

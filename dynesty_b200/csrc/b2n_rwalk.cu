@@ -11,17 +11,22 @@
 //   5. v = prior_transform(u'), logl = loglikelihood(v), accept iff logl > loglstar
 // exactly `walks` steps; with zero accepts v/logl are recomputed at the start (:970-975).
 //
-// Mapping: a CTA handles chains that share one ellipsoid; its axes^T (and the
-// precision matrix of a GAUSS_PREC model) are staged ONCE into shared memory and
-// every warp then streams them from there `walks` times -- HBM sees each matrix
-// once per CTA.  Lane i owns rows i, i+32, ... of each mat-vec; the proposal
-// vector is a warp-private shared vector read as a broadcast.
+// Mapping.  The grid is persistent-sized: ~one CTA per SM, each CTA owns an equal share of
+// the queue (<= 16 chains in flight, one warp per chain) and only chains of ONE ellipsoid,
+// whose axes^T and the precision matrix of a GAUSS_PREC model are staged ONCE into shared
+// memory (column stride padded to 128 B so every column read is bank-conflict free) and
+// then streamed `walks` times by every warp: HBM sees each matrix once per CTA.  Lane i
+// owns rows i, i+32 of each mat-vec, the proposal vector is a warp-private shared vector
+// read as 16-byte broadcasts; the quadratic form uses the symmetry of the precision matrix
+// (strict upper triangle only) which halves its shared-memory traffic.  ncu (profiles/)
+// shows this kernel is shared-memory-pipe bound, not HBM bound.
 #include "b2n_device.cuh"
 #include <algorithm>
 
 struct RwalkParams {
     B2nModel m;
     int n, nc, walks;
+    int ldA, ldP;          // leading dims of axes^T / precision as seen by the kernel
     const double* u0;
     const int* order;      // chains grouped by ellipsoid
     const int3* cta;       // (first, count, ell) per CTA
@@ -33,35 +38,100 @@ struct RwalkParams {
     int *nacc, *nrej, *ncall;
 };
 
+// y_i = sum_j M[j*ld + i] x_j for rows i0 = base+lane and i0+32; x is 16-byte aligned and is
+// read two entries per broadcast.
+__device__ __forceinline__ void warp_matvec2v(const double* __restrict__ M, int ld, int ncols,
+                                              const double* __restrict__ x, int i0, int nrows, double& y0,
+                                              double& y1) {
+    const int i1 = i0 + 32;
+    const bool r0 = i0 < nrows, r1 = i1 < nrows;
+    const int a0 = r0 ? i0 : 0, a1 = r1 ? i1 : 0;
+    double p0 = 0, p1 = 0, q0 = 0, q1 = 0;
+    const double2* x2 = reinterpret_cast<const double2*>(x);
+    int j = 0;
+    for (; j + 1 < ncols; j += 2) {
+        const double2 xx = x2[j >> 1];
+        p0 = fma(M[(size_t)j * ld + a0], xx.x, p0);
+        p1 = fma(M[(size_t)j * ld + a1], xx.x, p1);
+        q0 = fma(M[(size_t)(j + 1) * ld + a0], xx.y, q0);
+        q1 = fma(M[(size_t)(j + 1) * ld + a1], xx.y, q1);
+    }
+    if (j < ncols) {
+        const double xa = x[j];
+        p0 = fma(M[(size_t)j * ld + a0], xa, p0);
+        p1 = fma(M[(size_t)j * ld + a1], xa, p1);
+    }
+    y0 = r0 ? p0 + q0 : 0.0;
+    y1 = r1 ? p1 + q1 : 0.0;
+}
+
+// d^T P d for symmetric P using only the strict upper triangle (+ diagonal):
+//   sum_i d_i ( P_ii d_i + 2 sum_{j>i} P[j*ld + i] d_j )
+// Lane i owns row i; for column j only lanes with i < j load, so the shared-memory
+// wavefronts are those of the triangle.
+__device__ __forceinline__ double warp_quadform_sym(const double* __restrict__ P, int ld, int n,
+                                                    const double* __restrict__ d, int lane) {
+    double s = 0.0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const bool act = i < n;
+        const int ii = act ? i : 0;
+        const double di = act ? d[ii] : 0.0;
+        double a0 = 0.0, a1 = 0.0;
+        int j = base + 1;
+        for (; j + 1 < n; j += 2) {
+            const double dj0 = d[j], dj1 = d[j + 1];
+            if (i < j) a0 = fma(P[(size_t)j * ld + ii], dj0, a0);
+            if (i < j + 1) a1 = fma(P[(size_t)(j + 1) * ld + ii], dj1, a1);
+        }
+        if (j < n) {
+            if (i < j) a0 = fma(P[(size_t)j * ld + ii], d[j], a0);
+        }
+        if (act) s = fma(di, fma(P[(size_t)ii * ld + ii], di, 2.0 * (a0 + a1)), s);
+    }
+    return warp_sum(s);
+}
+
 template <int LIKE, bool AX_SMEM, bool PREC_SMEM>
-__global__ void __launch_bounds__(256) rwalk_kernel(const RwalkParams p) {
-    extern __shared__ double sm[];
+__global__ void __launch_bounds__(512) rwalk_kernel(const RwalkParams p) {
+    extern __shared__ __align__(16) double sm[];
     const int n = p.n, nc = p.nc;
+    const int npad = (n + 1) & ~1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int3 cd = p.cta[blockIdx.x];
     double* s = sm;
     const double* A = p.axesT + (size_t)cd.z * nc * nc;
+    int ldA = nc;
     if (AX_SMEM) {
-        for (int i = threadIdx.x; i < nc * nc; i += blockDim.x) s[i] = A[i];
+        ldA = p.ldA;
+        for (int e = threadIdx.x; e < nc * nc; e += blockDim.x) {
+            const int j = e / nc, i = e - j * nc;
+            s[(size_t)j * ldA + i] = A[e];
+        }
         A = s;
-        s += nc * nc;
+        s += (size_t)nc * ldA;
     }
     const double* P = p.m.lmat;
+    int ldP = n;
     if (LIKE == B2N_LIKE_GAUSS_PREC && PREC_SMEM) {
-        for (int i = threadIdx.x; i < n * n; i += blockDim.x) s[i] = P[i];
+        ldP = p.ldP;
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+            const int j = e / n, i = e - j * n;
+            s[(size_t)j * ldP + i] = P[e];
+        }
         P = s;
-        s += n * n;
+        s += (size_t)n * ldP;
     }
     uint32_t* fl = reinterpret_cast<uint32_t*>(s);
     for (int i = threadIdx.x; i < n; i += blockDim.x) fl[i] = p.dimflags ? p.dimflags[i] : 0u;
-    s += (n + 1) / 2;
+    s += ((n + 3) >> 2) << 1;
     __syncthreads();
 
-    double* ucur = s + (size_t)warp * 5 * n;
-    double* uprop = ucur + n;
-    double* vcur = uprop + n;
-    double* vprop = vcur + n;
-    double* x = vprop + n;    // direction vector, later likelihood scratch
+    double* ucur = s + (size_t)warp * 5 * npad;
+    double* uprop = ucur + npad;
+    double* vcur = uprop + npad;
+    double* vprop = vcur + npad;
+    double* x = vprop + npad;    // direction vector, later likelihood scratch
     const double inv_nc = 1.0 / (double)nc;
 
     for (int c = warp; c < cd.y; c += nwarps) {
@@ -87,7 +157,7 @@ __global__ void __launch_bounds__(256) rwalk_kernel(const RwalkParams p) {
             bool ok = true;
             for (int base = 0; base < nc; base += 64) {
                 double y0, y1;
-                warp_matvec2(A, nc, nc, x, base + lane, nc, y0, y1);
+                warp_matvec2v(A, ldA, nc, x, base + lane, nc, y0, y1);
                 const int i0 = base + lane, i1 = i0 + 32;
                 if (i0 < nc) uprop[i0] = fma(fac, y0, ucur[i0]);
                 if (i1 < nc) uprop[i1] = fma(fac, y1, ucur[i1]);
@@ -104,9 +174,21 @@ __global__ void __launch_bounds__(256) rwalk_kernel(const RwalkParams p) {
             ok = __all_sync(B2N_FULL, ok);
             if (!ok) { nrej++; continue; }
             // (5) prior transform + likelihood
-            for (int i = lane; i < n; i += 32) vprop[i] = prior_1d(p.m, i, uprop[i]);
-            __syncwarp();
-            const double l = warp_loglike<LIKE>(p.m, P, vprop, x, lane);
+            double l;
+            if (LIKE == B2N_LIKE_GAUSS_PREC) {
+                for (int i = lane; i < n; i += 32) {
+                    const double vi = prior_1d(p.m, i, uprop[i]);
+                    vprop[i] = vi;
+                    x[i] = vi - p.m.lv0[i];
+                }
+                __syncwarp();
+                l = fma(-0.5, warp_quadform_sym(P, ldP, n, x, lane), p.m.s0);
+                __syncwarp();
+            } else {
+                for (int i = lane; i < n; i += 32) vprop[i] = prior_1d(p.m, i, uprop[i]);
+                __syncwarp();
+                l = warp_loglike<LIKE>(p.m, P, vprop, x, lane);
+            }
             if (l > p.loglstar) {
                 double* t = ucur; ucur = uprop; uprop = t;
                 t = vcur; vcur = vprop; vprop = t;
@@ -119,7 +201,13 @@ __global__ void __launch_bounds__(256) rwalk_kernel(const RwalkParams p) {
         if (nacc == 0) {
             for (int i = lane; i < n; i += 32) vcur[i] = prior_1d(p.m, i, ucur[i]);
             __syncwarp();
-            lcur = warp_loglike<LIKE>(p.m, P, vcur, x, lane);
+            if (LIKE == B2N_LIKE_GAUSS_PREC) {
+                for (int i = lane; i < n; i += 32) x[i] = vcur[i] - p.m.lv0[i];
+                __syncwarp();
+                lcur = fma(-0.5, warp_quadform_sym(P, ldP, n, x, lane), p.m.s0);
+            } else {
+                lcur = warp_loglike<LIKE>(p.m, P, vcur, x, lane);
+            }
         }
         __syncwarp();
         for (int i = lane; i < n; i += 32) {
@@ -154,10 +242,26 @@ int b2n_build_worklist(b2n_ctx* ctx, int64_t Q, const int32_t* ell, int K, int c
     for (int k = 0; k < K; k++) count[k + 1] += count[k];
     std::vector<int64_t> pos(count.begin(), count.end() - 1);
     for (int64_t q = 0; q < Q; q++) order[pos[ell ? ell[q] : 0]++] = (int)q;
-    for (int k = 0; k < K; k++)
-        for (int64_t f = count[k]; f < count[k + 1]; f += chains_per_cta)
-            cta.push_back(make_int3((int)f, (int)std::min<int64_t>(chains_per_cta, count[k + 1] - f), k));
+    for (int k = 0; k < K; k++) {
+        // split the group into equal CTAs (no short tail CTA)
+        const int64_t c = count[k + 1] - count[k];
+        if (c == 0) continue;
+        const int64_t parts = (c + chains_per_cta - 1) / chains_per_cta;
+        for (int64_t i = 0; i < parts; i++) {
+            const int64_t lo = count[k] + c * i / parts, hi = count[k] + c * (i + 1) / parts;
+            cta.push_back(make_int3((int)lo, (int)(hi - lo), k));
+        }
+    }
     return B2N_OK;
+}
+
+// Persistent-sized grid: one CTA per SM when every chain can have its own warp
+// (Q <= 16 x SMs), two per SM beyond that; warps loop over their CTA's chains.
+void b2n_chain_grid(const b2n_ctx* ctx, int64_t Q, int max_warps, int& chains_per_cta, int& warps) {
+    const int64_t sms = ctx->sm_count;
+    const int64_t ctas = (Q <= 16 * sms) ? sms : 2 * sms;
+    chains_per_cta = (int)std::max<int64_t>(1, (Q + ctas - 1) / ctas);
+    warps = std::max(1, std::min(max_warps, std::min(16, chains_per_cta)));
 }
 
 extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t walks, double* u,
@@ -173,25 +277,29 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     if (Q == 0) return B2N_OK;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
 
-    // shared-memory plan: per-warp state always; matrices when they fit
-    const int warps = 8;
-    const size_t per_warp = (size_t)5 * n * sizeof(double);
-    const size_t fixed = per_warp * warps + (size_t)((n + 1) / 2) * sizeof(double);
-    const size_t ax_b = (size_t)nc * nc * sizeof(double);
-    const size_t pr_b = (m.like_kind == B2N_LIKE_GAUSS_PREC) ? (size_t)n * n * sizeof(double) : 0;
+    // shared-memory plan: per-warp state always; matrices (128-byte padded columns) when they fit
+    const int npad = (n + 1) & ~1;
+    const size_t per_warp = (size_t)5 * npad * sizeof(double);
+    const size_t flags_b = (size_t)(((n + 3) >> 2) << 1) * sizeof(double);
     const size_t limit = (size_t)ctx->max_smem_optin;
-    if (fixed > limit) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for the rwalk kernel");
-    // prefer CTAs that leave room for >= 2 resident CTAs per SM
-    bool ax_s = fixed + ax_b <= limit;
-    bool pr_s = pr_b > 0 && fixed + (ax_s ? ax_b : 0) + pr_b <= limit;
+    const int max_warps = (int)std::min<size_t>(16, (limit - flags_b) / per_warp);
+    if (max_warps < 1) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for the rwalk kernel");
+    int chains_per_cta, warps;
+    b2n_chain_grid(ctx, Q, max_warps, chains_per_cta, warps);
+    const size_t fixed = per_warp * warps + flags_b;
+    const int ldA = (nc + 15) & ~15, ldP = (n + 15) & ~15;
+    const size_t ax_b = (size_t)nc * ldA * sizeof(double);
+    const size_t pr_b = (m.like_kind == B2N_LIKE_GAUSS_PREC) ? (size_t)n * ldP * sizeof(double) : 0;
+    const bool ax_s = fixed + ax_b <= limit;
+    const bool pr_s = pr_b > 0 && fixed + (ax_s ? ax_b : 0) + pr_b <= limit;
     const size_t smem = fixed + (ax_s ? ax_b : 0) + (pr_s ? pr_b : 0);
 
     std::vector<int> order;
     std::vector<int3> cta;
-    B2N_TRY(b2n_build_worklist(ctx, Q, a->ell, ctx->bK, warps, order, cta));
+    B2N_TRY(b2n_build_worklist(ctx, Q, a->ell, ctx->bK, chains_per_cta, order, cta));
 
     RwalkParams p;
-    p.m = m; p.n = n; p.nc = nc; p.walks = walks;
+    p.m = m; p.n = n; p.nc = nc; p.walks = walks; p.ldA = ldA; p.ldP = ldP;
     p.loglstar = a->loglstar; p.scale = a->scale; p.seed = a->seed; p.chain0 = a->chain0;
     p.axesT = ctx->b_axesT.as<double>();
     const void *du0, *dorder, *dcta, *dfl = nullptr;

@@ -1,0 +1,47 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink on the
+GPU box, gloo in the CPU tests).
+
+The hot path shards naturally: the chains of one queue fill are
+independent (the reference maps them over a pool, sampler.py:717), so rank r runs chains
+[r*Q/W, (r+1)*Q/W) of every fill -- chain ids, and therefore Philox streams, are GLOBAL, so
+the gathered queue is bit-identical to a single-GPU fill.  The one exchange step is an
+all-gather of the finished chains (u, v, logl, counters) -- Q*(2n+1)*8 + O(Q) bytes -- after
+which every rank holds the full queue and advances the identical host state; the live points
+are therefore replicated and the bound update needs no further communication.
+"""
+import numpy as np
+
+
+class Comm:
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.backend = dist.get_backend()
+        self.device = device if device is not None else (
+            torch.device('cuda', torch.cuda.current_device()) if self.backend == 'nccl' else torch.device('cpu'))
+
+    def shard(self, Q):
+        """Rows [lo, hi) of a Q-row fill owned by this rank (Q is a multiple of world)."""
+        assert Q % self.world == 0
+        per = Q // self.world
+        return self.rank * per, (self.rank + 1) * per
+
+    def allgather(self, local, Q):
+        """dict of per-rank arrays (first axis = local rows) -> dict of full arrays."""
+        torch, dist = self.torch, self.dist
+        out = {}
+        for k in sorted(local):
+            a = np.ascontiguousarray(local[k])
+            t = torch.from_numpy(a).to(self.device)
+            full = torch.empty((Q,) + tuple(a.shape[1:]), dtype=t.dtype, device=self.device)
+            dist.all_gather_into_tensor(full, t)
+            out[k] = full.cpu().numpy()
+        return out
+
+    def max(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0])

@@ -239,6 +239,11 @@ class NestedSampler:
             else:
                 starts, ell = self.propose_live(loglstar, Q)
                 pts = self.live_u[starts]
+                # device copy of the bound follows the host object (cf. samplers._Resident)
+                key = (id(self.bound), getattr(self.bound, 'version', None))
+                if key != getattr(self, '_resident_key', None):
+                    self.bound.make_resident()
+                    self._resident_key = key
 
                 def fn(lo, hi):
                     return smp.run_batch(loglstar, pts[lo:hi], ell[lo:hi], self.seed, chain0=c0 + lo)

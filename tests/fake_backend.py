@@ -224,6 +224,7 @@ FUNCS = ['model_eval', 'membership', 'bounding_ellipsoid', 'multi_decompose', 's
 
 def install(monkeypatch):
     from dynesty_b200 import ops, likelihoods
+    _state.clear()          # no resident bound until the code under test uploads one
     g = globals()
     for name in FUNCS:
         monkeypatch.setattr(ops, name, g[name])
