@@ -23,6 +23,14 @@ __global__ void root_scale_kernel(NodeArrays na, int node, int count, double* __
     }
 }
 
+// obs = points / scale (bounding.py:1510), computed ONCE per update: IEEE division like numpy,
+// and the ten Lloyd iterations of every level then read the scaled copy.
+__global__ void scale_points_kernel(const double* __restrict__ P, int64_t total, int n,
+                                    const double* __restrict__ scale, double* __restrict__ out) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = P[e] / scale[e % n];
+}
+
 // ---- 2-means, scipy.cluster.vq.kmeans2(minit='matrix', iter=10) semantics (:1510-1514):
 // one CTA per node; centres start at the major-axis end points (:1500-1501, 278-284) in the
 // std-scaled space; 10 x { assign to the nearest centre (ties -> cluster 0), centroid =
@@ -55,7 +63,7 @@ __global__ void __launch_bounds__(512) kmeans2_kernel(const double* __restrict__
             const size_t row = (size_t)perm[r] * n;
             double d0 = 0.0, d1 = 0.0;
             for (int i = lane; i < n; i += 32) {
-                const double o = P[row + i] / scale[i];
+                const double o = P[row + i];          // P = points / scale (scaled once per update)
                 const double a = o - c[i], b = o - c[n + i];
                 d0 = fma(a, a, d0);
                 d1 = fma(b, b, d1);
@@ -64,7 +72,7 @@ __global__ void __launch_bounds__(512) kmeans2_kernel(const double* __restrict__
             d1 = warp_sum(d1);
             const int lab = (d1 < d0) ? 1 : 0;
             double* dst = acc + (size_t)warp * 2 * n + (size_t)lab * n;
-            for (int i = lane; i < n; i += 32) dst[i] += P[row + i] / scale[i];
+            for (int i = lane; i < n; i += 32) dst[i] += P[row + i];
             if (lane == 0) { cnt[warp * 2 + lab]++; labels[r] = (unsigned char)lab; }
         }
         __syncthreads();
@@ -195,6 +203,15 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
     double* scale = ctx->work1.as<double>();
     root_scale_kernel<<<1, 128, 0, st>>>(w.na, 0, count, scale);
     B2N_LAUNCH_CHECK(ctx);
+    const double* Pscaled = w.P;
+    if (count >= 4 * n) {      // something will be split: scaled copy of the point block
+        B2N_CUDA(ctx, ctx->in2.ensure((size_t)w.N * n * sizeof(double)));
+        const int64_t total = w.N * (int64_t)n;
+        scale_points_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(
+            w.P, total, n, scale, ctx->in2.as<double>());
+        B2N_LAUNCH_CHECK(ctx);
+        Pscaled = ctx->in2.as<double>();
+    }
 
     DevBuf& labbuf = ctx->out7;          // per-position labels (N bytes) + counts
     B2N_CUDA(ctx, labbuf.ensure((size_t)w.N + (size_t)w.cap * 2 * sizeof(int) + 64));
@@ -226,7 +243,7 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
         B2N_TRY(b2n_in_host(ctx, ctx->scratch5, srefs.data(), srefs.size() * sizeof(NodeRef), &drefs));
         const int* pin = w.perm + (size_t)cur * w.N;
         int* pout = w.perm + (size_t)(1 - cur) * w.N;
-        kmeans2_kernel<<<(unsigned)split.size(), nwarps * 32, km_smem, st>>>(w.P, pin, w.na, (const NodeRef*)drefs, scale,
+        kmeans2_kernel<<<(unsigned)split.size(), nwarps * 32, km_smem, st>>>(Pscaled, pin, w.na, (const NodeRef*)drefs, scale,
                                                                            dlab, dcounts);
         B2N_LAUNCH_CHECK(ctx);
         // carry every segment forward, then overwrite the split ones with their partition

@@ -38,181 +38,237 @@ struct RwalkParams {
     int *nacc, *nrej, *ncall;
 };
 
-// y_i = sum_j M[j*ld + i] x_j for rows i0 = base+lane and i0+32; x is 16-byte aligned and is
-// read two entries per broadcast.
-__device__ __forceinline__ void warp_matvec2v(const double* __restrict__ M, int ld, int ncols,
-                                              const double* __restrict__ x, int i0, int nrows, double& y0,
-                                              double& y1) {
-    const int i1 = i0 + 32;
-    const bool r0 = i0 < nrows, r1 = i1 < nrows;
-    const int a0 = r0 ? i0 : 0, a1 = r1 ? i1 : 0;
-    double p0 = 0, p1 = 0, q0 = 0, q1 = 0;
-    const double2* x2 = reinterpret_cast<const double2*>(x);
-    int j = 0;
-    for (; j + 1 < ncols; j += 2) {
-        const double2 xx = x2[j >> 1];
-        p0 = fma(M[(size_t)j * ld + a0], xx.x, p0);
-        p1 = fma(M[(size_t)j * ld + a1], xx.x, p1);
-        q0 = fma(M[(size_t)(j + 1) * ld + a0], xx.y, q0);
-        q1 = fma(M[(size_t)(j + 1) * ld + a1], xx.y, q1);
-    }
-    if (j < ncols) {
-        const double xa = x[j];
-        p0 = fma(M[(size_t)j * ld + a0], xa, p0);
-        p1 = fma(M[(size_t)j * ld + a1], xa, p1);
-    }
-    y0 = r0 ? p0 + q0 : 0.0;
-    y1 = r1 ? p1 + q1 : 0.0;
+extern __shared__ __align__(16) double b2n_sm[];
+
+// Element `idx` of a column-major matrix that lives either in dynamic shared memory (index
+// into b2n_sm: the compiler sees a plain shared-space access, no generic-address fix-ups) or
+// in global memory (read-only path).
+template <bool SMEM>
+__device__ __forceinline__ double mat_ld(const double* __restrict__ g, int idx) {
+    return SMEM ? b2n_sm[idx] : __ldg(g + idx);
 }
 
-// d^T P d for symmetric P using only the strict upper triangle (+ diagonal):
-//   sum_i d_i ( P_ii d_i + 2 sum_{j>i} P[j*ld + i] d_j )
-// Lane i owns row i; for column j only lanes with i < j load, so the shared-memory
-// wavefronts are those of the triangle.
-__device__ __forceinline__ double warp_quadform_sym(const double* __restrict__ P, int ld, int n,
-                                                    const double* __restrict__ d, int lane) {
-    double s = 0.0;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        const bool act = i < n;
-        const int ii = act ? i : 0;
-        const double di = act ? d[ii] : 0.0;
-        double a0 = 0.0, a1 = 0.0;
-        int j = base + 1;
-        for (; j + 1 < n; j += 2) {
-            const double dj0 = d[j], dj1 = d[j + 1];
-            if (i < j) a0 = fma(P[(size_t)j * ld + ii], dj0, a0);
-            if (i < j + 1) a1 = fma(P[(size_t)(j + 1) * ld + ii], dj1, a1);
-        }
-        if (j < n) {
-            if (i < j) a0 = fma(P[(size_t)j * ld + ii], d[j], a0);
-        }
-        if (act) s = fma(di, fma(P[(size_t)ii * ld + ii], di, 2.0 * (a0 + a1)), s);
+// y_i = sum_j M[j*ld + i] x_j for rows i0 and i0+32.  x = b2n_sm[offx..] (16-byte aligned,
+// read as one 16-byte broadcast per two columns); four columns per trip with eight
+// independent accumulators so that consecutive DFMAs never wait on each other.
+template <bool SMEM>
+__device__ __forceinline__ void matvec2o(const double* __restrict__ g, int offM, int ld, int ncols, int offx,
+                                         int i0, int nrows, double& y0, double& y1) {
+    const bool r0 = i0 < nrows, r1 = i0 + 32 < nrows;
+    const int c0 = offM + (r0 ? i0 : 0), c1 = offM + (r1 ? i0 + 32 : 0);
+    double a0 = 0, a1 = 0, b0 = 0, b1 = 0, e0 = 0, e1 = 0, f0 = 0, f1 = 0;
+    int j = 0, o = 0;
+    for (; j + 3 < ncols; j += 4, o += 4 * ld) {
+        const double2 xa = *reinterpret_cast<const double2*>(&b2n_sm[offx + j]);
+        const double2 xb = *reinterpret_cast<const double2*>(&b2n_sm[offx + j + 2]);
+        a0 = fma(mat_ld<SMEM>(g, c0 + o), xa.x, a0);
+        a1 = fma(mat_ld<SMEM>(g, c1 + o), xa.x, a1);
+        b0 = fma(mat_ld<SMEM>(g, c0 + o + ld), xa.y, b0);
+        b1 = fma(mat_ld<SMEM>(g, c1 + o + ld), xa.y, b1);
+        e0 = fma(mat_ld<SMEM>(g, c0 + o + 2 * ld), xb.x, e0);
+        e1 = fma(mat_ld<SMEM>(g, c1 + o + 2 * ld), xb.x, e1);
+        f0 = fma(mat_ld<SMEM>(g, c0 + o + 3 * ld), xb.y, f0);
+        f1 = fma(mat_ld<SMEM>(g, c1 + o + 3 * ld), xb.y, f1);
     }
-    return warp_sum(s);
+    for (; j < ncols; j++, o += ld) {
+        const double xj = b2n_sm[offx + j];
+        a0 = fma(mat_ld<SMEM>(g, c0 + o), xj, a0);
+        a1 = fma(mat_ld<SMEM>(g, c1 + o), xj, a1);
+    }
+    y0 = r0 ? (a0 + b0) + (e0 + f0) : 0.0;
+    y1 = r1 ? (a1 + b1) + (e1 + f1) : 0.0;
+}
+
+// Uniform direction in the unit nc-ball (bounding.py:1288-1297): writes z to b2n_sm[offx..]
+// and returns U^(1/nc) / |z|.  Two draw events (normal vector, then the radius uniform).
+// When the normal vector needs < 32 Philox blocks the otherwise idle lane 31 generates the
+// radius block in the same instruction stream (different counter), so one Philox + one log
+// serve both events.
+__device__ __forceinline__ double ball_direction(ChainRng& g, int offx, int nc, int lane, double inv_nc) {
+    const int nb = (nc + 1) >> 1;
+    if (nb <= 31) {
+        const bool isr = lane == 31;
+        const uint4 r = curand_Philox4x32_10(
+            make_uint4(isr ? 0u : (uint32_t)lane, g.tick + (isr ? 1u : 0u), g.c2, g.c3), g.key);
+        g.tick += 2;
+        const double u0 = b2n_u52(r.x, r.y), u1 = b2n_u52(r.z, r.w);
+        const double lg = log(u0);
+        const double rad = sqrt(-2.0 * lg);
+        double sn, cs;
+        sincospi(2.0 * u1, &sn, &cs);
+        const double z0 = rad * cs, z1 = rad * sn;
+        double ss = 0.0;
+        if (lane < nb) {
+            ss = z0 * z0;
+            if (2 * lane + 1 < nc) {
+                *reinterpret_cast<double2*>(&b2n_sm[offx + 2 * lane]) = make_double2(z0, z1);
+                ss = fma(z1, z1, ss);
+            } else {
+                b2n_sm[offx + 2 * lane] = z0;
+            }
+        }
+        ss = warp_sum(ss);
+        const double lgU = __shfl_sync(B2N_FULL, lg, 31);
+        return exp(lgU * inv_nc) / sqrt(ss);
+    }
+    const double ss = rng_normals_to(g, &b2n_sm[offx], nc, lane);
+    const double U = rng_uniform(g);
+    return pow(U, inv_nc) / sqrt(ss);
+}
+
+__device__ __forceinline__ double prior_sm(int kind, int op0, int op1, int i, double u) {
+    switch (kind) {
+        case B2N_PRIOR_UNIFORM: return fma(b2n_sm[op1 + i], u, b2n_sm[op0 + i]);
+        case B2N_PRIOR_NORMAL_PPF: return fma(b2n_sm[op1 + i], normcdfinv(u), b2n_sm[op0 + i]);
+        default: return u;
+    }
 }
 
 template <int LIKE, bool AX_SMEM, bool PREC_SMEM>
-__global__ void __launch_bounds__(512) rwalk_kernel(const RwalkParams p) {
-    extern __shared__ __align__(16) double sm[];
+__global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
     const int n = p.n, nc = p.nc;
     const int npad = (n + 1) & ~1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int3 cd = p.cta[blockIdx.x];
-    double* s = sm;
-    const double* A = p.axesT + (size_t)cd.z * nc * nc;
-    int ldA = nc;
+    // ---- shared-memory plan (all offsets in doubles, all even)
+    int off = 0;
+    const double* Ag = p.axesT + (size_t)cd.z * nc * nc;
+    int offA = 0, ldA = nc;
     if (AX_SMEM) {
-        ldA = p.ldA;
+        offA = off; ldA = p.ldA;
         for (int e = threadIdx.x; e < nc * nc; e += blockDim.x) {
             const int j = e / nc, i = e - j * nc;
-            s[(size_t)j * ldA + i] = A[e];
+            b2n_sm[offA + j * ldA + i] = Ag[e];
         }
-        A = s;
-        s += (size_t)nc * ldA;
+        off += nc * ldA;
     }
-    const double* P = p.m.lmat;
-    int ldP = n;
+    const double* Pg = p.m.lmat;
+    int offP = 0, ldP = n;
     if (LIKE == B2N_LIKE_GAUSS_PREC && PREC_SMEM) {
-        ldP = p.ldP;
+        offP = off; ldP = p.ldP;
         for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
             const int j = e / n, i = e - j * n;
-            s[(size_t)j * ldP + i] = P[e];
+            b2n_sm[offP + j * ldP + i] = Pg[e];
         }
-        P = s;
-        s += (size_t)n * ldP;
+        off += n * ldP;
     }
-    uint32_t* fl = reinterpret_cast<uint32_t*>(s);
+    const int op0 = off, op1 = off + npad, omu = off + 2 * npad;       // prior p0, p1, likelihood vec0
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        b2n_sm[op0 + i] = p.m.pp0 ? p.m.pp0[i] : 0.0;
+        b2n_sm[op1 + i] = p.m.pp1 ? p.m.pp1[i] : 1.0;
+        b2n_sm[omu + i] = p.m.lv0 ? p.m.lv0[i] : 0.0;
+    }
+    off += 3 * npad;
+    uint32_t* fl = reinterpret_cast<uint32_t*>(&b2n_sm[off]);
     for (int i = threadIdx.x; i < n; i += blockDim.x) fl[i] = p.dimflags ? p.dimflags[i] : 0u;
-    s += ((n + 3) >> 2) << 1;
+    off += ((n + 3) >> 2) << 1;
     __syncthreads();
 
-    double* ucur = s + (size_t)warp * 5 * npad;
-    double* uprop = ucur + npad;
-    double* vcur = uprop + npad;
-    double* vprop = vcur + npad;
-    double* x = vprop + npad;    // direction vector, later likelihood scratch
+    int oucur = off + warp * 6 * npad;
+    int ouprop = oucur + npad;
+    int ovcur = ouprop + npad;
+    int ovprop = ovcur + npad;
+    const int ox = ovprop + npad;       // direction vector
+    const int od = ox + npad;           // v - mean (GAUSS_PREC) / likelihood scratch
     const double inv_nc = 1.0 / (double)nc;
+    const int pk = p.m.prior_kind;
 
     for (int c = warp; c < cd.y; c += nwarps) {
         const int q = p.order[cd.x + c];
         ChainRng g;
         g.init(p.seed, p.chain0 + (uint64_t)q);
-        for (int i = lane; i < n; i += 32) ucur[i] = p.u0[(size_t)q * n + i];
+        for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)q * n + i];
         __syncwarp();
         int nacc = 0, nrej = 0;
         double lcur = 0.0;
         for (int step = 0; step < p.walks; step++) {
             // (1) non-clustered dims: one vector uniform event (only if there are any)
             if (n > nc) {
-                for (int e = lane; e < n - nc; e += 32) uprop[nc + e] = rng_uniform_elem(g, e);
+                for (int e = lane; e < n - nc; e += 32) {
+                    const double t = rng_uniform_elem(g, e);
+                    const double vi = prior_sm(pk, op0, op1, nc + e, t);
+                    b2n_sm[ouprop + nc + e] = t;
+                    b2n_sm[ovprop + nc + e] = vi;
+                    b2n_sm[od + nc + e] = vi - b2n_sm[omu + nc + e];
+                }
                 g.tick++;
             }
             // (2) uniform point in the unit nc-ball
-            const double ss = rng_normals_to(g, x, nc, lane);
-            const double U = rng_uniform(g);
-            const double fac = p.scale * (pow(U, inv_nc) / sqrt(ss));
+            const double fac = p.scale * ball_direction(g, ox, nc, lane, inv_nc);
             __syncwarp();
-            // (3) clustered dims: u' = u + fac * axes @ z ; (4) boundaries
+            // (3) u' = u + fac * axes @ z on the clustered dims, (4) wrap / reflect / cube test,
+            //     and (speculatively) the prior transform of the rows this lane owns
             bool ok = true;
             for (int base = 0; base < nc; base += 64) {
                 double y0, y1;
-                warp_matvec2v(A, ldA, nc, x, base + lane, nc, y0, y1);
-                const int i0 = base + lane, i1 = i0 + 32;
-                if (i0 < nc) uprop[i0] = fma(fac, y0, ucur[i0]);
-                if (i1 < nc) uprop[i1] = fma(fac, y1, ucur[i1]);
+                matvec2o<AX_SMEM>(Ag, offA, ldA, nc, ox, base + lane, nc, y0, y1);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int i = base + lane + 32 * h;
+                    if (i < nc) {
+                        double t = fma(fac, h ? y1 : y0, b2n_sm[oucur + i]);
+                        const uint32_t f = fl[i];
+                        if (f & B2N_DIM_PERIODIC) t = mod1(t);
+                        if (f & B2N_DIM_REFLECTIVE) t = reflect1(t);
+                        ok = ok && in_cube(t, f);
+                        const double vi = prior_sm(pk, op0, op1, i, t);
+                        b2n_sm[ouprop + i] = t;
+                        b2n_sm[ovprop + i] = vi;
+                        b2n_sm[od + i] = vi - b2n_sm[omu + i];
+                    }
+                }
             }
-            __syncwarp();
-            for (int i = lane; i < n; i += 32) {
-                double t = uprop[i];
-                const uint32_t f = fl[i];
-                if (f & B2N_DIM_PERIODIC) t = mod1(t);
-                if (f & B2N_DIM_REFLECTIVE) t = reflect1(t);
-                ok = ok && in_cube(t, f);
-                uprop[i] = t;
-            }
-            ok = __all_sync(B2N_FULL, ok);
+            ok = __all_sync(B2N_FULL, ok);       // also orders the shared-memory writes above
             if (!ok) { nrej++; continue; }
-            // (5) prior transform + likelihood
+            // (5) likelihood
             double l;
             if (LIKE == B2N_LIKE_GAUSS_PREC) {
-                for (int i = lane; i < n; i += 32) {
-                    const double vi = prior_1d(p.m, i, uprop[i]);
-                    vprop[i] = vi;
-                    x[i] = vi - p.m.lv0[i];
+                double sacc = 0.0;
+                for (int base = 0; base < n; base += 64) {
+                    double y0, y1;
+                    matvec2o<PREC_SMEM>(Pg, offP, ldP, n, od, base + lane, n, y0, y1);
+                    const int i0 = base + lane, i1 = i0 + 32;
+                    if (i0 < n) sacc = fma(b2n_sm[od + i0], y0, sacc);
+                    if (i1 < n) sacc = fma(b2n_sm[od + i1], y1, sacc);
                 }
-                __syncwarp();
-                l = fma(-0.5, warp_quadform_sym(P, ldP, n, x, lane), p.m.s0);
-                __syncwarp();
+                l = fma(-0.5, warp_sum(sacc), p.m.s0);
             } else {
-                for (int i = lane; i < n; i += 32) vprop[i] = prior_1d(p.m, i, uprop[i]);
-                __syncwarp();
-                l = warp_loglike<LIKE>(p.m, P, vprop, x, lane);
+                l = warp_loglike<LIKE>(p.m, Pg, &b2n_sm[ovprop], &b2n_sm[od], lane);
             }
             if (l > p.loglstar) {
-                double* t = ucur; ucur = uprop; uprop = t;
-                t = vcur; vcur = vprop; vprop = t;
+                int t = oucur; oucur = ouprop; ouprop = t;
+                t = ovcur; ovcur = ovprop; ovprop = t;
                 lcur = l;
                 nacc++;
             } else {
                 nrej++;
             }
         }
-        if (nacc == 0) {
-            for (int i = lane; i < n; i += 32) vcur[i] = prior_1d(p.m, i, ucur[i]);
+        if (nacc == 0) {       // recompute (v, logl) of the start point (:970-975)
+            for (int i = lane; i < n; i += 32) {
+                const double vi = prior_sm(pk, op0, op1, i, b2n_sm[oucur + i]);
+                b2n_sm[ovcur + i] = vi;
+                b2n_sm[od + i] = vi - b2n_sm[omu + i];
+            }
             __syncwarp();
             if (LIKE == B2N_LIKE_GAUSS_PREC) {
-                for (int i = lane; i < n; i += 32) x[i] = vcur[i] - p.m.lv0[i];
-                __syncwarp();
-                lcur = fma(-0.5, warp_quadform_sym(P, ldP, n, x, lane), p.m.s0);
+                double sacc = 0.0;
+                for (int base = 0; base < n; base += 64) {
+                    double y0, y1;
+                    matvec2o<PREC_SMEM>(Pg, offP, ldP, n, od, base + lane, n, y0, y1);
+                    const int i0 = base + lane, i1 = i0 + 32;
+                    if (i0 < n) sacc = fma(b2n_sm[od + i0], y0, sacc);
+                    if (i1 < n) sacc = fma(b2n_sm[od + i1], y1, sacc);
+                }
+                lcur = fma(-0.5, warp_sum(sacc), p.m.s0);
             } else {
-                lcur = warp_loglike<LIKE>(p.m, P, vcur, x, lane);
+                lcur = warp_loglike<LIKE>(p.m, Pg, &b2n_sm[ovcur], &b2n_sm[od], lane);
             }
         }
         __syncwarp();
         for (int i = lane; i < n; i += 32) {
-            p.u[(size_t)q * n + i] = ucur[i];
-            p.v[(size_t)q * n + i] = vcur[i];
+            p.u[(size_t)q * n + i] = b2n_sm[oucur + i];
+            p.v[(size_t)q * n + i] = b2n_sm[ovcur + i];
         }
         if (lane == 0) {
             p.logl[q] = lcur;
@@ -279,8 +335,8 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
 
     // shared-memory plan: per-warp state always; matrices (128-byte padded columns) when they fit
     const int npad = (n + 1) & ~1;
-    const size_t per_warp = (size_t)5 * npad * sizeof(double);
-    const size_t flags_b = (size_t)(((n + 3) >> 2) << 1) * sizeof(double);
+    const size_t per_warp = (size_t)6 * npad * sizeof(double);
+    const size_t flags_b = (size_t)((((n + 3) >> 2) << 1) + 3 * npad) * sizeof(double);
     const size_t limit = (size_t)ctx->max_smem_optin;
     const int max_warps = (int)std::min<size_t>(16, (limit - flags_b) / per_warp);
     if (max_warps < 1) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for the rwalk kernel");

@@ -77,3 +77,20 @@ def test_sampler_requires_model(dynesty):
     c, b, s = _classes()
     with pytest.raises(ValueError):
         s.B200RWalkSampler(walks=5)
+
+
+def test_dropin_dynamic_sampler(dynesty, fake_ops):
+    """BASELINE C5 shape: DynamicNestedSampler(bound='multi', sample='rslice') re-enters the
+    same plug-in path for every batch (dynamicsampler.py:373-390, 1094-1110)."""
+    c, b, s = _classes()
+    from dynesty_b200 import likelihoods as DL
+    from dynesty_b200.pool import B200Pool
+    m = DL.shells(2)
+    ds = dynesty.DynamicNestedSampler(m.loglikelihood, m.prior_transform, 2, bound=b.B200MultiEllipsoid(2),
+                                      sample=s.B200RSliceSampler(model=m, slices=3), pool=B200Pool(16),
+                                      queue_size=16, rstate=np.random.default_rng(4),
+                                      use_pool={'prior_transform': False, 'loglikelihood': False})
+    ds.run_nested(nlive_init=100, nlive_batch=50, maxbatch=2, dlogz_init=0.5, print_progress=False)
+    res = ds.results
+    assert abs(res['logz'][-1] - (-1.75)) < 5 * res['logzerr'][-1] + 0.15
+    assert len(res['batch_nlive']) >= 2

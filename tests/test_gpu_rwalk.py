@@ -123,3 +123,51 @@ def test_rwalk_edge_cases():
     ops.bound_set(np.eye(4))
     with pytest.raises(ValueError):
         ops.rwalk_batch(dm.model_id(), u0, 0.0, 1.0, 5, 1)
+
+
+def test_rwalk_c4_properties():
+    """BASELINE C4 shape (200-D iid normal, normal-ppf prior, single ellipsoid, walks=220):
+    the axes matrix (320 KB) does not fit in shared memory -> global/L2 path."""
+    m = MODELS['n200']
+    dm = device_model(m)
+    rng = np.random.default_rng(8)
+    pts = 0.5 + 0.04 * rng.standard_normal((4000, 200))
+    e = OB.bounding_ellipsoid(pts)
+    logl = m.loglike(m.prior_transform(pts))
+    loglstar = float(np.quantile(logl, 0.3))
+    u0 = pts[logl > loglstar][:600]
+    ops.bound_set(e.axes)
+    o = ops.rwalk_batch(dm.model_id(), u0, loglstar, 0.12, 220, SEED, chain0=77)
+    assert np.all(o['ncall'] == 220) and np.all(o['n_accept'] + o['n_reject'] == 220)
+    assert np.all(o['logl'] > loglstar)
+    v0 = m.prior_transform(o['u'])
+    close(o['v'], v0, rtol=1e-12)
+    np.testing.assert_allclose(o['logl'], m.loglike(v0), rtol=1e-10)
+    assert 0.05 < o['n_accept'].mean() / 220 < 0.95
+    for i in (0, 599):
+        r = OS.rwalk_chain(u0[i], loglstar, e.axes, 0.12, m, philox.ChainStream(SEED, 77 + i), 220)
+        assert r['n_accept'] == o['n_accept'][i]
+        close(o['u'][i], r['u'], rtol=1e-9)
+
+
+def test_rwalk_large_queue_many_ellipsoids():
+    """Queue much larger than 16 x SMs (warps loop over chains) spread over K=5 ellipsoids."""
+    m = MODELS['g6']
+    dm = device_model(m)
+    rng = np.random.default_rng(21)
+    pts = _cloud(rng, 600, 6, 0.06)
+    ells = [OB.bounding_ellipsoid(pts[i::5]) for i in range(5)]
+    axes = np.array([e.axes for e in ells])
+    logl = m.loglike(m.prior_transform(pts))
+    loglstar = float(np.quantile(logl, 0.4))
+    good = pts[logl > loglstar]
+    Q = 20000
+    u0 = good[rng.integers(len(good), size=Q)]
+    ell = rng.integers(5, size=Q).astype(np.int32)
+    ops.bound_set(axes)
+    o = ops.rwalk_batch(dm.model_id(), u0, loglstar, 0.9, 10, 99, chain0=0, ell=ell)
+    assert np.all(o['logl'] > loglstar) and np.all(o['ncall'] == 10)
+    for i in (0, 1, 7777, 19999):
+        r = OS.rwalk_chain(u0[i], loglstar, axes[ell[i]], 0.9, m, philox.ChainStream(99, i), 10)
+        assert r['n_accept'] == o['n_accept'][i]
+        close(o['u'][i], r['u'], rtol=1e-9)
