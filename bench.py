@@ -157,7 +157,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(device), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                       '--format=csv,noheader,nounits', '-lms', '20'],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
@@ -279,6 +279,7 @@ def run_b200(args, cfg):
             dist.all_gather_into_tensor(g_l, d_out['logl'])
 
     # ---- warm-up: also tunes the proposal scale with the reference's rule (internal_samplers.py:491)
+    clocks = ClockSampler(local)         # samples every 20 ms from here to the end of the timed regions
     for _ in range(max(args.warmup, 3)):
         o = step_host()
         acc, rej = int(o['n_accept'].sum()), int(o['n_reject'].sum())
@@ -286,7 +287,8 @@ def run_b200(args, cfg):
     for _ in range(3):
         o = step_host()
     accept_frac = float(o['n_accept'].sum() / (o['n_accept'].sum() + o['n_reject'].sum()))
-    step_dev()
+    for _ in range(100):                 # clock ramp: ~50 ms of the same kernel before timing
+        step_dev()
     torch.cuda.synchronize()
 
     def barrier():
@@ -295,7 +297,6 @@ def run_b200(args, cfg):
         torch.cuda.synchronize()
 
     # ---- timed: device-resident (value + roofline)
-    clocks = ClockSampler(local)
     launches0 = ctx.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kern_ms = []

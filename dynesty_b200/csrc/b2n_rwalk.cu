@@ -55,7 +55,9 @@ template <bool SMEM>
 __device__ __forceinline__ void matvec2o(const double* __restrict__ g, int offM, int ld, int ncols, int offx,
                                          int i0, int nrows, double& y0, double& y1) {
     const bool r0 = i0 < nrows, r1 = i0 + 32 < nrows;
-    const int c0 = offM + (r0 ? i0 : 0), c1 = offM + (r1 ? i0 + 32 : 0);
+    // idle lanes re-read the LAST row (same 128-byte segment as their active neighbours: a
+    // broadcast), not row 0 -- row 0 sits in the same banks as row 32 and cost an extra wavefront
+    const int c0 = offM + (r0 ? i0 : nrows - 1), c1 = offM + (r1 ? i0 + 32 : nrows - 1);
     double a0 = 0, a1 = 0, b0 = 0, b1 = 0, e0 = 0, e1 = 0, f0 = 0, f1 = 0;
     int j = 0, o = 0;
     for (; j + 3 < ncols; j += 4, o += 4 * ld) {
