@@ -230,14 +230,14 @@ def run_b200(args, cfg):
     h_np = {k: t.numpy() for k, t in h_out.items()}
     d_live = torch.from_numpy(u_live).to(dev)
     d_u0 = torch.empty(Q, n, dtype=torch.float64, device=dev)
-    d_out = dict(u=torch.empty(Q, n, dtype=torch.float64, device=dev), v=torch.empty(Q, n, dtype=torch.float64, device=dev),
-                 logl=torch.empty(Q, dtype=torch.float64, device=dev),
+    d_pack = torch.empty(Q * n + Q, dtype=torch.float64, device=dev)     # (u | logl): ONE all-gather per fill
+    d_out = dict(u=d_pack[:Q * n].view(Q, n), v=torch.empty(Q, n, dtype=torch.float64, device=dev),
+                 logl=d_pack[Q * n:],
                  n_accept=torch.empty(Q, dtype=torch.int32, device=dev),
                  n_reject=torch.empty(Q, dtype=torch.int32, device=dev),
                  ncall=torch.empty(Q, dtype=torch.int32, device=dev))
     if world > 1:
-        g_u = torch.empty(world * Q, n, dtype=torch.float64, device=dev)
-        g_l = torch.empty(world * Q, dtype=torch.float64, device=dev)
+        g_pack = torch.empty(world * (Q * n + Q), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     # one explicit (non-default) stream shared by torch and the library, so that torch's CUDA
     # events bracket the library's launches (a NULL handle would mean "library-owned stream")
@@ -275,8 +275,7 @@ def run_b200(args, cfg):
         ops.rwalk_batch(mid, d_u0, loglstar, state['scale'], walks, SEED, chain0=c0 + rank * Q, ell=ell,
                         ctx=ctx, out=d_out)
         if world > 1:       # the exchange step of the sharded path: every rank gets the whole queue
-            dist.all_gather_into_tensor(g_u, d_out['u'])
-            dist.all_gather_into_tensor(g_l, d_out['logl'])
+            dist.all_gather_into_tensor(g_pack, d_pack)
 
     # ---- warm-up: also tunes the proposal scale with the reference's rule (internal_samplers.py:491)
     clocks = ClockSampler(local)         # samples every 20 ms from here to the end of the timed regions
@@ -287,7 +286,8 @@ def run_b200(args, cfg):
     for _ in range(3):
         o = step_host()
     accept_frac = float(o['n_accept'].sum() / (o['n_accept'].sum() + o['n_reject'].sum()))
-    for _ in range(100):                 # clock ramp: ~50 ms of the same kernel before timing
+    t_ramp = time.perf_counter() + 0.7   # clock ramp: 0.7 s of the same kernel before timing, so that
+    while time.perf_counter() < t_ramp:  # the nvidia-smi sampler has samples under load
         step_dev()
     torch.cuda.synchronize()
 
@@ -340,6 +340,12 @@ def run_b200(args, cfg):
             peak = 6650.0
         kms = float(np.mean(kern_ms))
         achieved = algorithmic_bytes(n) * Q * walks / (kms * 1e-3) / 1e9
+        traffic = None          # measured DRAM bytes per launch of this kernel (ncu --set full)
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+                traffic = json.load(f)['rwalk_kernel']['dram_bytes_per_launch'] if Q == 2000 else None
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -353,7 +359,8 @@ def run_b200(args, cfg):
                     "d2h_bytes_per_step": 2 * Q * n * 8 + Q * 8 + 3 * Q * 4},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "rwalk_kernel",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch",
+                         "algorithmic_bytes_per_launch": algorithmic_bytes(n) * Q * walks, "kernel": "rwalk_kernel",
                          "kernel_ms": kms, "algorithmic_bytes_per_proposal": algorithmic_bytes(n),
                          "peak_source": peak_src},
             "clocks": clk,

@@ -133,6 +133,25 @@ class B200MultiEllipsoid(BoundBase):
             return x, idx, self.overlap(x)
         return x, idx
 
+    def monte_carlo_logvol(self, ndraws=10000, rstate=None, return_overlap=True):
+        """bounding.py:608-630: MC estimate of the log-volume of the UNION (and of its
+        fractional overlap with the unit cube) from volume-weighted draws and their q."""
+        self.make_resident()
+        o = ops.unif_batch(-1, ndraws, self.ndim, -np.inf, _seed_from(rstate), draw_only=True, mixture=True,
+                           ncdim=self.ndim, ctx=self._ctx)
+        w = 1. / o['ncall']                                   # 1 / q
+        logvol = math.log(w.sum() / ndraws) + self.logvol
+        if not return_overlap:
+            return logvol
+        x = o['u']
+        inside = np.all((x > 0) & (x < 1), axis=1)
+        return logvol, float((w * inside).sum() / w.sum())
+
+    def unitcube_overlap(self, ndraws=10000, rstate=None):
+        """bounding.py:336-343 (single ellipsoid) / the overlap half of monte_carlo_logvol."""
+        x = self.samples(ndraws, rstate=rstate)
+        return float(np.all((x > 0) & (x < 1), axis=1).mean())
+
     def get_random_axes(self, rstate):
         """bounding.py:726-731: axes of an ellipsoid picked with probability ~ volume."""
         if self.nells == 1:
@@ -183,8 +202,8 @@ class B200MultiEllipsoid(BoundBase):
                               'from bootstrapping is very large.')
             if expand > 1.:
                 self.scale_to_logvol(self.logvol_ells + ndim * math.log(expand))
-        if mc_integrate:
-            raise NotImplementedError("mc_integrate is never requested by Sampler (sampler.py:502-505)")
+        if mc_integrate:                                                       # :720-724
+            self.logvol, self.funit = self.monte_carlo_logvol(rstate=rstate, return_overlap=True)
 
 
 class B200Ellipsoid(BoundBase):
@@ -261,5 +280,9 @@ class B200Ellipsoid(BoundBase):
             expand = float(expands.max())
             if expand > 1.:
                 self.scale_to_logvol(self.logvol + self.ndim * math.log(expand))
-        if mc_integrate:
-            raise NotImplementedError("mc_integrate is never requested by Sampler")
+        if mc_integrate:                                                       # :411-414
+            self.funit = self.unitcube_overlap(rstate=rstate)
+
+    def unitcube_overlap(self, ndraws=10000, rstate=None):
+        """bounding.py:336-343."""
+        return self._m.unitcube_overlap(ndraws, rstate=rstate)

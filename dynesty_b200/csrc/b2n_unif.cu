@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) unif_kernel(const UnifParams p) {
                     if (i1 < nc) uu[i1] = fma(fac, y1, p.ctrs[(size_t)idx * nc + i1]);
                 }
                 __syncwarp();
-                if (K == 1) break;                                       // bounding.py:543-550
+                if (K == 1) { if (p.draw_only & 2) ncall = 1; break; }   // bounding.py:543-550
                 int qn = 0, qslack = 0;
                 for (int k = 0; k < K; k++) {
                     for (int i = lane; i < nc; i += 32) dl[i] = uu[i] - p.ctrs[(size_t)k * nc + i];
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(256) unif_kernel(const UnifParams p) {
                     if (qn == 0) { fl |= 0x40000000u; done = true; break; }
                     fl |= B2N_WARN_Q0_SLACK;
                 }
+                if (p.draw_only & 2) { ncall = qn; break; }                // sample(return_q=True): no 1/q test
                 if (qn == 1) break;
                 if (rng_uniform(g) < 1.0 / (double)qn) break;            // :589
             }
@@ -147,7 +148,7 @@ __global__ void unif_error_kernel(const uint32_t* flags, int64_t Q, int* out) {
 extern "C" int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, double* v, double* logl,
                               int32_t* ncall, int32_t* nprop, uint32_t* flags) {
     if (!ctx || !a || !u || !v || !logl || !ncall || !nprop || !flags) return B2N_ERR_ARG;
-    const int draw_only = (a->reserved & B2N_OPT_DRAW_ONLY) ? 1 : 0;
+    const int draw_only = (a->reserved & B2N_OPT_DRAW_ONLY) ? ((a->reserved & B2N_OPT_DRAW_MIXTURE) ? 3 : 1) : 0;
     B2nModel m;
     memset(&m, 0, sizeof(m));
     m.ndim = a->ndim;

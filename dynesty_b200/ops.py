@@ -189,14 +189,14 @@ def slice_batch(model, u0, loglstar, scale, slices, seed, chain0=0, doubling=Fal
 
 
 def unif_batch(model, nchain, ndim, loglstar, seed, chain0=0, ncdim=None, dimflags=None, ctx=None,
-               draw_only=False):
+               draw_only=False, mixture=False):
     """UniformBoundSampler.sample x nchain on the resident bound (internal_samplers.py:243-340).
     draw_only=True: just Bound.samples(nchain) (no cube test / likelihood)."""
     ctx = _ctx(ctx)
     a, keep, Q, n = _chain_args(model, None, ncdim, loglstar, 1.0, seed, chain0, None, dimflags,
                                 Q=int(nchain), ndim=int(ndim))
     if draw_only:
-        a.reserved = 1
+        a.reserved = 3 if mixture else 1      # mixture: no 1/q test, q returned in 'ncall'
     o = dict(u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q), ncall=np.empty(Q, dtype=np.int32),
              nprop=np.empty(Q, dtype=np.int32), flags=np.empty(Q, dtype=np.uint32))
     ctx.check(ctx.lib.b2n_unif_batch(ctx.h, C.byref(a), ptr(o['u']), ptr(o['v']), ptr(o['logl']),

@@ -168,6 +168,10 @@ int b2n_bound_set(b2n_ctx* ctx, int32_t K, int32_t ncdim, const double* ctrs,
  * evaluating a model (Bound.samples, bounding.py:321-334, 592-606); needs ndim == ncdim,
  * model_id ignored. */
 #define B2N_OPT_DRAW_ONLY 1
+/* with DRAW_ONLY: MultiEllipsoid.sample(return_q=True) semantics (bounding.py:580-584): the
+ * draw is returned WITHOUT the 1/q acceptance test and ncall[q] receives q (the number of
+ * ellipsoids containing it) -- the input of monte_carlo_logvol (:608-630). */
+#define B2N_OPT_DRAW_MIXTURE 2
 
 /* ---- proposal chains ----------------------------------------------------------
  * One chain per queue slot (sampler.py:690-717).  Chain q consumes the B2N

@@ -109,3 +109,55 @@ def test_unif_uniformity_two_ellipsoids():
     frac = (in0 & in1).mean()
     assert abs(frac - lens / union) < 4 * np.sqrt(frac * (1 - frac) / len(x))
     assert np.all(o['ncall'] == 1)
+
+
+def _two_sphere_vol(d, r1, r2, ndim):
+    """Volume of the union of two n-balls (numerical 1-D integral over the axis joining them)."""
+    from scipy.special import gammaln
+    def ball(n, r):
+        return np.exp(n / 2. * np.log(np.pi) - gammaln(n / 2. + 1) + n * np.log(r))
+    xs = np.linspace(-r1, d + r2, 400001)
+    a = np.clip(r1**2 - xs**2, 0, None)
+    b = np.clip(r2**2 - (xs - d)**2, 0, None)
+    rad = np.sqrt(np.maximum(a, b))
+    return np.trapezoid(ball(ndim - 1, 1.0) * rad**(ndim - 1), xs)
+
+
+def test_mc_logvol_two_spheres():
+    """tests/test_ellipsoid.py:174-194: MC volume of a two-ball union within 1e-2 (n=10, 1e4 draws
+    in the reference; 2e5 here since the draws are one launch)."""
+    from dynesty_b200.bounding import B200MultiEllipsoid
+    import math
+    from scipy.special import gammaln
+    ndim, r1, r2 = 10, 1.0, 0.5
+    pref = ndim / 2. * math.log(math.pi) - gammaln(ndim / 2. + 1)
+    for D in (0.0, 0.6, 1.2, 2.0):
+        b = B200MultiEllipsoid(ndim)
+        c2 = np.zeros(ndim)
+        c2[0] = D
+        b.nells = 2
+        b.ctrs = np.array([np.zeros(ndim), c2])
+        b.covs = np.array([np.eye(ndim) * r1**2, np.eye(ndim) * r2**2])
+        b.ams = np.array([np.eye(ndim) / r1**2, np.eye(ndim) / r2**2])
+        b.axes_all = np.array([np.eye(ndim) * r1, np.eye(ndim) * r2])
+        b.axlens_all = np.array([np.full(ndim, r1), np.full(ndim, r2)])
+        b.logvol_ells = np.array([pref + ndim * math.log(r1), pref + ndim * math.log(r2)])
+        b._refresh_logvol()
+        lv, overlap = b.monte_carlo_logvol(200000, rstate=np.random.default_rng(int(D * 10)))
+        assert abs(lv - math.log(_two_sphere_vol(D, r1, r2, ndim))) < 1e-2
+        assert 0 <= overlap <= 1
+
+
+def test_cube_overlap_half():
+    """tests/test_ellipsoid.py:92-103: a ball centred on a cube face overlaps it by one half."""
+    from dynesty_b200.bounding import B200Ellipsoid
+    ndim = 10
+    b = B200Ellipsoid(ndim)
+    cen = np.full(ndim, 0.5)
+    cen[0] = 0
+    m = b._m
+    m.ctrs, m.covs, m.ams = cen[None], (np.eye(ndim) * 0.25)[None], (np.eye(ndim) * 4.)[None]
+    m.axes_all, m.axlens_all = (np.eye(ndim) * 0.5)[None], np.full((1, ndim), 0.5)
+    m._refresh_logvol()
+    frac = b.unitcube_overlap(100000, rstate=np.random.default_rng(3))
+    assert abs(frac - 0.5) < 5 * np.sqrt(0.25 / 100000)
