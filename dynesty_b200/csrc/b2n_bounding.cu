@@ -166,8 +166,13 @@ __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* cc, doub
         // converged at the round-off floor of the off-diagonal mass (n^2 entries of size
         // ~eps*||A||): the same absolute accuracy LAPACK's eigh delivers
         if (off <= (double)n * (double)n * 2.5e-32 * tot) break;
+        // One round = m/2 disjoint rotations.  WARP k owns pair k: it derives the rotation from
+        // its own three matrix entries (warp-uniform, no staging / no barrier), rotates rows p,q of
+        // A and of V^T with its lanes across the columns; after one barrier the same warp rotates
+        // columns p,q of A with its lanes down the rows.  Two barriers per round.
+        const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
         for (int r = 0; r < m - 1; r++) {
-            for (int k = tid; k < half; k += T) {
+            for (int k = warp; k < half; k += nw) {
                 int p, q;
                 rr_pair(m, r, k, p, q);
                 double c = 1.0, s = 0.0;
@@ -180,37 +185,36 @@ __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* cc, doub
                         s = t * c;
                     }
                 }
-                cc[k] = c;
-                ss[k] = s;
-            }
-            __syncthreads();
-            for (int e = tid; e < half * n; e += T) {        // rows p,q of A and of VT
-                const int k = e / n, j = e - k * n;
-                const double s = ss[k];
+                __syncwarp();                      // every lane has read app/aqq/apq before rows change
+                if (lane == 0) { cc[k] = c; ss[k] = s; }
                 if (s != 0.0) {
-                    int p, q;
-                    rr_pair(m, r, k, p, q);
-                    const double c = cc[k];
-                    double a = A[(size_t)p * ld + j], b = A[(size_t)q * ld + j];
-                    A[(size_t)p * ld + j] = c * a - s * b;
-                    A[(size_t)q * ld + j] = s * a + c * b;
-                    a = VT[(size_t)p * ld + j];
-                    b = VT[(size_t)q * ld + j];
-                    VT[(size_t)p * ld + j] = c * a - s * b;
-                    VT[(size_t)q * ld + j] = s * a + c * b;
+                    double* Ap = A + (size_t)p * ld;
+                    double* Aq = A + (size_t)q * ld;
+                    double* Vp = VT + (size_t)p * ld;
+                    double* Vq = VT + (size_t)q * ld;
+                    for (int j = lane; j < n; j += 32) {
+                        double a = Ap[j], b = Aq[j];
+                        Ap[j] = c * a - s * b;
+                        Aq[j] = s * a + c * b;
+                        a = Vp[j];
+                        b = Vq[j];
+                        Vp[j] = c * a - s * b;
+                        Vq[j] = s * a + c * b;
+                    }
                 }
             }
             __syncthreads();
-            for (int e = tid; e < half * n; e += T) {        // columns p,q of A
-                const int k = e / n, i = e - k * n;
+            for (int k = warp; k < half; k += nw) {
                 const double s = ss[k];
                 if (s != 0.0) {
                     int p, q;
                     rr_pair(m, r, k, p, q);
                     const double c = cc[k];
-                    const double a = A[(size_t)i * ld + p], b = A[(size_t)i * ld + q];
-                    A[(size_t)i * ld + p] = c * a - s * b;
-                    A[(size_t)i * ld + q] = s * a + c * b;
+                    for (int i = lane; i < n; i += 32) {
+                        const double a = A[(size_t)i * ld + p], b = A[(size_t)i * ld + q];
+                        A[(size_t)i * ld + p] = c * a - s * b;
+                        A[(size_t)i * ld + q] = s * a + c * b;
+                    }
                 }
             }
             __syncthreads();
@@ -221,7 +225,7 @@ __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* cc, doub
 
 // improve_covar_mat (bounding.py:1311-1384) for one node per CTA.
 // pass 0: input = covraw ; pass 1: input = current cov (after the pass-0 rescale).
-__global__ void __launch_bounds__(512) eig_ladder_kernel(NodeArrays na, const int* __restrict__ nodelist, int pass,
+__global__ void __launch_bounds__(1024) eig_ladder_kernel(NodeArrays na, const int* __restrict__ nodelist, int pass,
                                                          double* __restrict__ gwork, int use_smem) {
     extern __shared__ double sm[];
     const int n = na.n, ld = na.ld, tid = threadIdx.x, T = blockDim.x;
@@ -514,7 +518,8 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
         gwork = ctx->scratch2.as<double>();
     }
     B2N_CUDA(ctx, cudaFuncSetAttribute(eig_ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem));
-    const int eig_threads = n <= 16 ? 64 : (n <= 48 ? 256 : 512);
+    // one warp per rotation pair of a Jacobi round (n/2 pairs), at least 4 warps for the O(n^2) loops
+    const int eig_threads = 32 * std::max(4, std::min(32, half));
     const size_t fm_smem = (size_t)8 * n * sizeof(double);
 
     std::vector<NodeStat> hs(nnodes);

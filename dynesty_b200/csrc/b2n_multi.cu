@@ -36,7 +36,7 @@ __global__ void scale_points_kernel(const double* __restrict__ P, int64_t total,
 // std-scaled space; 10 x { assign to the nearest centre (ties -> cluster 0), centroid =
 // member mean, an empty cluster keeps its centre }; the labels returned are those of the
 // last assignment (before the last centroid update).
-__global__ void __launch_bounds__(512) kmeans2_kernel(const double* __restrict__ P, const int* __restrict__ perm,
+__global__ void __launch_bounds__(1024) kmeans2_kernel(const double* __restrict__ P, const int* __restrict__ perm,
                                                       NodeArrays na, const NodeRef* __restrict__ refs,
                                                       const double* __restrict__ scale,
                                                       unsigned char* __restrict__ labels, int* __restrict__ counts) {
@@ -59,21 +59,38 @@ __global__ void __launch_bounds__(512) kmeans2_kernel(const double* __restrict__
         for (int i = lane; i < 2 * n; i += 32) acc[(size_t)warp * 2 * n + i] = 0.0;
         if (lane < 2) cnt[warp * 2 + lane] = 0;
         __syncwarp();
-        for (int r = nr.start + warp; r < nr.start + nr.count; r += nw) {
+        // two points per trip: their row loads and shuffle reductions overlap (the loop is
+        // latency-bound: one CTA walks the whole node out of L2)
+        for (int r = nr.start + warp; r < nr.start + nr.count; r += 2 * nw) {
+            const int r2 = r + nw;
+            const bool two = r2 < nr.start + nr.count;
             const size_t row = (size_t)perm[r] * n;
-            double d0 = 0.0, d1 = 0.0;
+            const size_t row2 = two ? (size_t)perm[r2] * n : row;
+            double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
             for (int i = lane; i < n; i += 32) {
                 const double o = P[row + i];          // P = points / scale (scaled once per update)
+                const double o2 = P[row2 + i];
                 const double a = o - c[i], b = o - c[n + i];
+                const double a2 = o2 - c[i], b2 = o2 - c[n + i];
                 d0 = fma(a, a, d0);
                 d1 = fma(b, b, d1);
+                e0 = fma(a2, a2, e0);
+                e1 = fma(b2, b2, e1);
             }
             d0 = warp_sum(d0);
             d1 = warp_sum(d1);
+            e0 = warp_sum(e0);
+            e1 = warp_sum(e1);
             const int lab = (d1 < d0) ? 1 : 0;
+            const int lab2 = (e1 < e0) ? 1 : 0;
             double* dst = acc + (size_t)warp * 2 * n + (size_t)lab * n;
             for (int i = lane; i < n; i += 32) dst[i] += P[row + i];
             if (lane == 0) { cnt[warp * 2 + lab]++; labels[r] = (unsigned char)lab; }
+            if (two) {            // same order as the one-point-per-trip loop: r, then r + nw
+                double* dst2 = acc + (size_t)warp * 2 * n + (size_t)lab2 * n;
+                for (int i = lane; i < n; i += 32) dst2[i] += P[row2 + i];
+                if (lane == 0) { cnt[warp * 2 + lab2]++; labels[r2] = (unsigned char)lab2; }
+            }
         }
         __syncthreads();
         if (threadIdx.x < 2) {
@@ -221,7 +238,7 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
     std::vector<int> frontier(1, 0);
     int cur = 0;
     const int min_size = 2 * n;
-    int nwarps = 16;
+    int nwarps = 32;
     while ((size_t)(2 * n + (size_t)nwarps * 2 * n) * sizeof(double) + nwarps * 2 * sizeof(int) > (size_t)ctx->max_smem_optin && nwarps > 1)
         nwarps >>= 1;
     const size_t km_smem = (size_t)(2 * n + (size_t)nwarps * 2 * n) * sizeof(double) + nwarps * 2 * sizeof(int);

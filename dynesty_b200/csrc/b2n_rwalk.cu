@@ -118,51 +118,22 @@ __device__ __forceinline__ double ball_direction(ChainRng& g, int offx, int nc, 
     return pow(U, inv_nc) / sqrt(ss);
 }
 
-// d^T P d for a SYMMETRIC P (the precision matrix), reading only its strict upper triangle:
-//   sum_i d_i ( P_ii d_i + 2 sum_{j>i} P[j*ld + i] d_j ),   d = b2n_sm[od..].
-// Row block b (rows 32b..32b+31, one per lane) walks the columns j > 32b: inside the
-// diagonal block only lanes with i < j load (predicated LDS -> fewer wavefronts), beyond it
-// all lanes do.  Half the shared-memory traffic AND fewer instructions than the full
-// mat-vec (for n = 50: 66 column visits instead of 100).
+// d^T P d = sum_i d_i (P d)_i with the full mat-vec.  (A strict-upper-triangle variant that
+// halves the shared-memory wavefronts through predicated loads was measured SLOWER on B200 --
+// 0.415 ms vs 0.350 ms per C2 launch, profiles/r1e -- the predicated diagonal block costs more
+// issue slots than the saved wavefronts buy at 14 warps/SM, so the plain form is kept.)
 template <bool SMEM>
-__device__ __forceinline__ double quadform_sym(const double* __restrict__ g, int offP, int ld, int n, int od,
-                                               int lane) {
-    double s = 0.0;
-    for (int b0 = 0; b0 < n; b0 += 32) {
-        const int i = b0 + lane;
-        const bool act = i < n;
-        const int ii = act ? i : n - 1;
-        const int col = offP + ii;
-        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        int j = b0 + 1;
-        const int jfull = min(n, b0 + 32);
-        for (; j + 1 < jfull; j += 2) {               // diagonal block: lanes i < j only
-            double pv = 0.0, pw = 0.0;
-            if (i < j) pv = mat_ld<SMEM>(g, col + j * ld);
-            if (i < j + 1) pw = mat_ld<SMEM>(g, col + (j + 1) * ld);
-            a0 = fma(pv, b2n_sm[od + j], a0);
-            a1 = fma(pw, b2n_sm[od + j + 1], a1);
-        }
-        for (; j < jfull; j++) {
-            double pv = 0.0;
-            if (i < j) pv = mat_ld<SMEM>(g, col + j * ld);
-            a2 = fma(pv, b2n_sm[od + j], a2);
-        }
-        for (; j + 3 < n; j += 4) {                   // off-diagonal blocks: every lane
-            const double d0 = b2n_sm[od + j], d1 = b2n_sm[od + j + 1];
-            const double d2 = b2n_sm[od + j + 2], d3 = b2n_sm[od + j + 3];
-            a0 = fma(mat_ld<SMEM>(g, col + j * ld), d0, a0);
-            a1 = fma(mat_ld<SMEM>(g, col + (j + 1) * ld), d1, a1);
-            a2 = fma(mat_ld<SMEM>(g, col + (j + 2) * ld), d2, a2);
-            a3 = fma(mat_ld<SMEM>(g, col + (j + 3) * ld), d3, a3);
-        }
-        for (; j < n; j++) a1 = fma(mat_ld<SMEM>(g, col + j * ld), b2n_sm[od + j], a1);
-        if (act) {
-            const double di = b2n_sm[od + i];
-            s = fma(di, fma(mat_ld<SMEM>(g, col + i * ld), di, 2.0 * ((a0 + a1) + (a2 + a3))), s);
-        }
+__device__ __forceinline__ double quadform_full(const double* __restrict__ g, int offP, int ld, int n, int od,
+                                                int lane) {
+    double sacc = 0.0;
+    for (int base = 0; base < n; base += 64) {
+        double y0, y1;
+        matvec2o<SMEM>(g, offP, ld, n, od, base + lane, n, y0, y1);
+        const int i0 = base + lane, i1 = i0 + 32;
+        if (i0 < n) sacc = fma(b2n_sm[od + i0], y0, sacc);
+        if (i1 < n) sacc = fma(b2n_sm[od + i1], y1, sacc);
     }
-    return warp_sum(s);
+    return warp_sum(sacc);
 }
 
 __device__ __forceinline__ double prior_sm(int kind, int op0, int op1, int i, double u) {
@@ -272,7 +243,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
             // (5) likelihood
             double l;
             if (LIKE == B2N_LIKE_GAUSS_PREC) {
-                l = fma(-0.5, quadform_sym<PREC_SMEM>(Pg, offP, ldP, n, od, lane), p.m.s0);
+                l = fma(-0.5, quadform_full<PREC_SMEM>(Pg, offP, ldP, n, od, lane), p.m.s0);
             } else {
                 l = warp_loglike<LIKE>(p.m, Pg, &b2n_sm[ovprop], &b2n_sm[od], lane);
             }
@@ -293,7 +264,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
             }
             __syncwarp();
             if (LIKE == B2N_LIKE_GAUSS_PREC) {
-                lcur = fma(-0.5, quadform_sym<PREC_SMEM>(Pg, offP, ldP, n, od, lane), p.m.s0);
+                lcur = fma(-0.5, quadform_full<PREC_SMEM>(Pg, offP, ldP, n, od, lane), p.m.s0);
             } else {
                 lcur = warp_loglike<LIKE>(p.m, Pg, &b2n_sm[ovcur], &b2n_sm[od], lane);
             }

@@ -116,7 +116,7 @@ def _two_sphere_vol(d, r1, r2, ndim):
     from scipy.special import gammaln
     def ball(n, r):
         return np.exp(n / 2. * np.log(np.pi) - gammaln(n / 2. + 1) + n * np.log(r))
-    xs = np.linspace(-r1, d + r2, 400001)
+    xs = np.linspace(-r1, max(r1, d + r2), 400001)
     a = np.clip(r1**2 - xs**2, 0, None)
     b = np.clip(r2**2 - (xs - d)**2, 0, None)
     rad = np.sqrt(np.maximum(a, b))
