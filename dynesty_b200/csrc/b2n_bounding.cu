@@ -131,7 +131,12 @@ __global__ void cov_finalize_kernel(const NodeRef* __restrict__ refs, int n, con
 __device__ __forceinline__ void rr_pair(int m, int r, int k, int& p, int& q) {
     int a, b;
     if (k == 0) { a = m - 1; b = r; }
-    else { a = (r + k) % (m - 1); b = (r - k + (m - 1)) % (m - 1); }
+    else {          // (r + k) mod (m-1), (r - k) mod (m-1) without integer division: r < m-1, k < m/2
+        a = r + k;
+        if (a >= m - 1) a -= m - 1;
+        b = r - k;
+        if (b < 0) b += m - 1;
+    }
     p = min(a, b);
     q = max(a, b);
 }
@@ -178,11 +183,25 @@ __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* cc, doub
                 double c = 1.0, s = 0.0;
                 if (q < n) {
                     const double app = A[(size_t)p * ld + p], aqq = A[(size_t)q * ld + q], apq = A[(size_t)p * ld + q];
-                    if (apq != 0.0 && fabs(apq) > 1e-17 * sqrt(fabs(app * aqq))) {
-                        const double tau = (aqq - app) / (2.0 * apq);
-                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
-                        c = 1.0 / sqrt(fma(t, t, 1.0));
-                        s = t * c;
+                    // skip test |apq| <= 1e-17 sqrt(|app aqq|) without a square root
+                    if (apq != 0.0 && apq * apq > 1e-34 * fabs(app * aqq)) {
+                        // t = tan(theta) = sgn(tau) / (|tau| + sqrt(tau^2 + 1)), tau = (aqq-app)/(2 apq),
+                        // rewritten as t = 2 apq / (d + sgn(d) h), h = hypot(d, 2 apq): one division and
+                        // two reciprocal square roots instead of three divisions and two square roots
+                        // (FP64 div/sqrt are ~350-cycle software sequences and sit on the critical path)
+                        const double d = aqq - app, b2 = 2.0 * apq;
+                        const double x = fma(d, d, b2 * b2);
+                        if (x > 1e-250 && x < 1e250) {
+                            const double h = x * rsqrt(x);
+                            const double t = b2 / (d + (d >= 0.0 ? h : -h));
+                            c = rsqrt(fma(t, t, 1.0));
+                            s = t * c;
+                        } else {        // out of the safe range of d^2: robust (slow) form
+                            const double tau = d / b2;
+                            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
+                            c = 1.0 / sqrt(fma(t, t, 1.0));
+                            s = t * c;
+                        }
                     }
                 }
                 __syncwarp();                      // every lane has read app/aqq/apq before rows change
@@ -320,12 +339,14 @@ __global__ void __launch_bounds__(1024) eig_ladder_kernel(NodeArrays na, const i
         for (int j = 0; j < n; j++) rk += (lamv[j] < l || (lamv[j] == l && j < k)) ? 1 : 0;
         tmpv[k] = (double)rk;
         LM[rk] = l;
+        cc[k] = 1.0 / l;          // cc|ss (2*half >= n doubles) are free after the decomposition
     }
     __syncthreads();
     for (size_t e = tid; e < nn; e += T) {
         const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
         double s = 0.0;
-        for (int k = 0; k < n; k++) s = fma(VT[(size_t)k * ld + i] / lamv[k], VT[(size_t)k * ld + j], s);
+        // am = (V * (1/l)) @ V^T, the reciprocal taken once per eigenvalue as in bounding.py:1381
+        for (int k = 0; k < n; k++) s = fma(VT[(size_t)k * ld + i] * cc[k], VT[(size_t)k * ld + j], s);
         AM[e] = s;
         // here j plays the role of the eigen index: axes[i][rank_j] = V[i][j] sqrt(l_j)
         AX[(size_t)i * n + (int)tmpv[j]] = VT[(size_t)j * ld + i] * sqrt(lamv[j]);

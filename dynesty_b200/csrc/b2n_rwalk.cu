@@ -17,10 +17,12 @@
 // memory (column stride padded to 128 B so every column read is bank-conflict free) and
 // then streamed `walks` times by every warp: HBM sees each matrix once per CTA.  Lane i
 // owns rows i, i+32 of each mat-vec, the proposal vector is a warp-private shared vector
-// read as 16-byte broadcasts; the quadratic form uses the symmetry of the precision matrix
-// (strict upper triangle only) which halves its shared-memory traffic.  ncu (profiles/)
-// shows this kernel is shared-memory-pipe bound, not HBM bound.
-#include "b2n_device.cuh"
+// read as 16-byte broadcasts; all shared-memory traffic is explicit b2n_sm[] indexing (no
+// generic-pointer fix-ups), the wrap/reflect/cube test and the prior transform are fused
+// into the mat-vec epilogue, and the two draw events of a step share one Philox + one log.
+// ncu (profiles/) shows this kernel is shared-memory-pipe bound (84 % of peak wavefronts),
+// not HBM bound: DRAM traffic is ~0.9 MB per launch against 5.8 GB of algorithmic bytes.
+#include "b2n_chain.cuh"
 #include <algorithm>
 
 struct RwalkParams {
@@ -37,112 +39,6 @@ struct RwalkParams {
     double *u, *v, *logl;
     int *nacc, *nrej, *ncall;
 };
-
-extern __shared__ __align__(16) double b2n_sm[];
-
-// Element `idx` of a column-major matrix that lives either in dynamic shared memory (index
-// into b2n_sm: the compiler sees a plain shared-space access, no generic-address fix-ups) or
-// in global memory (read-only path).
-template <bool SMEM>
-__device__ __forceinline__ double mat_ld(const double* __restrict__ g, int idx) {
-    return SMEM ? b2n_sm[idx] : __ldg(g + idx);
-}
-
-// y_i = sum_j M[j*ld + i] x_j for rows i0 and i0+32.  x = b2n_sm[offx..] (16-byte aligned,
-// read as one 16-byte broadcast per two columns); four columns per trip with eight
-// independent accumulators so that consecutive DFMAs never wait on each other.
-template <bool SMEM>
-__device__ __forceinline__ void matvec2o(const double* __restrict__ g, int offM, int ld, int ncols, int offx,
-                                         int i0, int nrows, double& y0, double& y1) {
-    const bool r0 = i0 < nrows, r1 = i0 + 32 < nrows;
-    // idle lanes re-read the LAST row (same 128-byte segment as their active neighbours: a
-    // broadcast), not row 0 -- row 0 sits in the same banks as row 32 and cost an extra wavefront
-    const int c0 = offM + (r0 ? i0 : nrows - 1), c1 = offM + (r1 ? i0 + 32 : nrows - 1);
-    double a0 = 0, a1 = 0, b0 = 0, b1 = 0, e0 = 0, e1 = 0, f0 = 0, f1 = 0;
-    int j = 0, o = 0;
-    for (; j + 3 < ncols; j += 4, o += 4 * ld) {
-        const double2 xa = *reinterpret_cast<const double2*>(&b2n_sm[offx + j]);
-        const double2 xb = *reinterpret_cast<const double2*>(&b2n_sm[offx + j + 2]);
-        a0 = fma(mat_ld<SMEM>(g, c0 + o), xa.x, a0);
-        a1 = fma(mat_ld<SMEM>(g, c1 + o), xa.x, a1);
-        b0 = fma(mat_ld<SMEM>(g, c0 + o + ld), xa.y, b0);
-        b1 = fma(mat_ld<SMEM>(g, c1 + o + ld), xa.y, b1);
-        e0 = fma(mat_ld<SMEM>(g, c0 + o + 2 * ld), xb.x, e0);
-        e1 = fma(mat_ld<SMEM>(g, c1 + o + 2 * ld), xb.x, e1);
-        f0 = fma(mat_ld<SMEM>(g, c0 + o + 3 * ld), xb.y, f0);
-        f1 = fma(mat_ld<SMEM>(g, c1 + o + 3 * ld), xb.y, f1);
-    }
-    for (; j < ncols; j++, o += ld) {
-        const double xj = b2n_sm[offx + j];
-        a0 = fma(mat_ld<SMEM>(g, c0 + o), xj, a0);
-        a1 = fma(mat_ld<SMEM>(g, c1 + o), xj, a1);
-    }
-    y0 = r0 ? (a0 + b0) + (e0 + f0) : 0.0;
-    y1 = r1 ? (a1 + b1) + (e1 + f1) : 0.0;
-}
-
-// Uniform direction in the unit nc-ball (bounding.py:1288-1297): writes z to b2n_sm[offx..]
-// and returns U^(1/nc) / |z|.  Two draw events (normal vector, then the radius uniform).
-// When the normal vector needs < 32 Philox blocks the otherwise idle lane 31 generates the
-// radius block in the same instruction stream (different counter), so one Philox + one log
-// serve both events.
-__device__ __forceinline__ double ball_direction(ChainRng& g, int offx, int nc, int lane, double inv_nc) {
-    const int nb = (nc + 1) >> 1;
-    if (nb <= 31) {
-        const bool isr = lane == 31;
-        const uint4 r = curand_Philox4x32_10(
-            make_uint4(isr ? 0u : (uint32_t)lane, g.tick + (isr ? 1u : 0u), g.c2, g.c3), g.key);
-        g.tick += 2;
-        const double u0 = b2n_u52(r.x, r.y), u1 = b2n_u52(r.z, r.w);
-        const double lg = log(u0);
-        const double rad = sqrt(-2.0 * lg);
-        double sn, cs;
-        sincospi(2.0 * u1, &sn, &cs);
-        const double z0 = rad * cs, z1 = rad * sn;
-        double ss = 0.0;
-        if (lane < nb) {
-            ss = z0 * z0;
-            if (2 * lane + 1 < nc) {
-                *reinterpret_cast<double2*>(&b2n_sm[offx + 2 * lane]) = make_double2(z0, z1);
-                ss = fma(z1, z1, ss);
-            } else {
-                b2n_sm[offx + 2 * lane] = z0;
-            }
-        }
-        ss = warp_sum(ss);
-        const double lgU = __shfl_sync(B2N_FULL, lg, 31);
-        return exp(lgU * inv_nc) / sqrt(ss);
-    }
-    const double ss = rng_normals_to(g, &b2n_sm[offx], nc, lane);
-    const double U = rng_uniform(g);
-    return pow(U, inv_nc) / sqrt(ss);
-}
-
-// d^T P d = sum_i d_i (P d)_i with the full mat-vec.  (A strict-upper-triangle variant that
-// halves the shared-memory wavefronts through predicated loads was measured SLOWER on B200 --
-// 0.415 ms vs 0.350 ms per C2 launch, profiles/r1e -- the predicated diagonal block costs more
-// issue slots than the saved wavefronts buy at 14 warps/SM, so the plain form is kept.)
-template <bool SMEM>
-__device__ __forceinline__ double quadform_full(const double* __restrict__ g, int offP, int ld, int n, int od,
-                                                int lane) {
-    double sacc = 0.0;
-    for (int base = 0; base < n; base += 64) {
-        double y0, y1;
-        matvec2o<SMEM>(g, offP, ld, n, od, base + lane, n, y0, y1);
-        const int i0 = base + lane, i1 = i0 + 32;
-        if (i0 < n) sacc = fma(b2n_sm[od + i0], y0, sacc);
-        if (i1 < n) sacc = fma(b2n_sm[od + i1], y1, sacc);
-    }
-    return warp_sum(sacc);
-}
-
-__device__ __forceinline__ double prior_sm(int kind, int op0, int op1, int i, double u) {
-    switch (kind) {
-        case B2N_PRIOR_UNIFORM: return fma(b2n_sm[op1 + i], u, b2n_sm[op0 + i]);
-        case B2N_PRIOR_NORMAL_PPF: return fma(b2n_sm[op1 + i], normcdfinv(u), b2n_sm[op0 + i]);
-        default: return u;
-    }
-}
 
 template <int LIKE, bool AX_SMEM, bool PREC_SMEM>
 __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
@@ -172,13 +68,9 @@ __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
         }
         off += n * ldP;
     }
-    const int op0 = off, op1 = off + npad, omu = off + 2 * npad;       // prior p0, p1, likelihood vec0
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        b2n_sm[op0 + i] = p.m.pp0 ? p.m.pp0[i] : 0.0;
-        b2n_sm[op1 + i] = p.m.pp1 ? p.m.pp1[i] : 1.0;
-        b2n_sm[omu + i] = p.m.lv0 ? p.m.lv0[i] : 0.0;
-    }
-    off += 3 * npad;
+    const ModelSm ms = stage_model(p.m, off, n, npad);     // prior p0/p1, likelihood vec0/vec1
+    const int op0 = ms.op0, op1 = ms.op1, omu = ms.olv0;
+    off += 4 * npad;
     uint32_t* fl = reinterpret_cast<uint32_t*>(&b2n_sm[off]);
     for (int i = threadIdx.x; i < n; i += blockDim.x) fl[i] = p.dimflags ? p.dimflags[i] : 0u;
     off += ((n + 3) >> 2) << 1;
@@ -245,7 +137,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
             if (LIKE == B2N_LIKE_GAUSS_PREC) {
                 l = fma(-0.5, quadform_full<PREC_SMEM>(Pg, offP, ldP, n, od, lane), p.m.s0);
             } else {
-                l = warp_loglike<LIKE>(p.m, Pg, &b2n_sm[ovprop], &b2n_sm[od], lane);
+                l = loglike_sm<LIKE, PREC_SMEM>(p.m, ms, Pg, offP, ldP, n, ovprop, od, lane);
             }
             if (l > p.loglstar) {
                 int t = oucur; oucur = ouprop; ouprop = t;
@@ -266,7 +158,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
             if (LIKE == B2N_LIKE_GAUSS_PREC) {
                 lcur = fma(-0.5, quadform_full<PREC_SMEM>(Pg, offP, ldP, n, od, lane), p.m.s0);
             } else {
-                lcur = warp_loglike<LIKE>(p.m, Pg, &b2n_sm[ovcur], &b2n_sm[od], lane);
+                lcur = loglike_sm<LIKE, PREC_SMEM>(p.m, ms, Pg, offP, ldP, n, ovcur, od, lane);
             }
         }
         __syncwarp();
@@ -340,7 +232,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     // shared-memory plan: per-warp state always; matrices (128-byte padded columns) when they fit
     const int npad = (n + 1) & ~1;
     const size_t per_warp = (size_t)6 * npad * sizeof(double);
-    const size_t flags_b = (size_t)((((n + 3) >> 2) << 1) + 3 * npad) * sizeof(double);
+    const size_t flags_b = (size_t)((((n + 3) >> 2) << 1) + 4 * npad) * sizeof(double);
     const size_t limit = (size_t)ctx->max_smem_optin;
     const int max_warps = (int)std::min<size_t>(16, (limit - flags_b) / per_warp);
     if (max_warps < 1) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for the rwalk kernel");

@@ -8,20 +8,21 @@
 // warp-uniform scalars (log-likelihood values, uniforms that every lane derives from the
 // same Philox counter), so the 32 lanes of a chain stay converged while they cooperate on
 // the vector work: u + x*d, the unit-cube test, the prior transform and the likelihood.
+// Same layout as the rwalk kernel (b2n_chain.cuh): persistent-sized grid, one ellipsoid per
+// CTA, axes^T / precision matrix staged once in shared memory with 128-byte padded columns,
+// all per-chain vectors addressed as b2n_sm[offset].
 // NOTE (reference behaviour kept): the slice samplers read kwargs['nonperiodic'], which
 // the 3.0 sampler never sets (:654, 804), so every dimension is hard-bounded to (0, 1).
-#include "b2n_device.cuh"
+#include "b2n_chain.cuh"
 #include <algorithm>
 #include <vector>
-
-int b2n_build_worklist(b2n_ctx* ctx, int64_t Q, const int32_t* ell, int K, int chains_per_cta,
-                       std::vector<int>& order, std::vector<int3>& cta);
 
 #define B2N_MAX_EXPAND 4000000      // hard stop against a runaway stepping-out loop
 
 struct SliceParams {
     B2nModel m;
     int n, slices, doubling;
+    int ldA, ldP;
     const double* u0;
     const int* order;
     const int3* cta;
@@ -33,37 +34,33 @@ struct SliceParams {
     uint32_t* flags;
 };
 
-template <int LIKE>
-struct SliceEval {        // F(x) of generic_slice_step (:1112-1123)
+// F(x) of generic_slice_step (:1112-1123): logl(u + x d) or -inf outside the unit cube.
+template <int LIKE, bool PREC_SMEM>
+struct SliceEval {
     const B2nModel& m;
-    const double* P;
-    const double* u;
-    const double* d;
-    double* un;
-    double* vn;
-    double* work;
-    int lane, n;
+    const ModelSm& ms;
+    const double* Pg;
+    int offP, ldP;
+    int ou, odir, oun, ovn, owork;
+    int lane, n, pk;
     int nc;
     __device__ __forceinline__ double operator()(double x) {
         bool ok = true;
         for (int i = lane; i < n; i += 32) {
-            const double t = fma(x, d[i], u[i]);
-            un[i] = t;
+            const double t = fma(x, b2n_sm[odir + i], b2n_sm[ou + i]);
+            b2n_sm[oun + i] = t;
+            b2n_sm[ovn + i] = prior_sm(pk, ms.op0, ms.op1, i, t);
             ok = ok && (t > 0.0 && t < 1.0);
         }
         nc++;
-        ok = __all_sync(B2N_FULL, ok);
+        ok = __all_sync(B2N_FULL, ok);          // also orders the writes above
         if (!ok) return -INFINITY;
-        for (int i = lane; i < n; i += 32) vn[i] = prior_1d(m, i, un[i]);
-        __syncwarp();
-        const double l = warp_loglike<LIKE>(m, P, vn, work, lane);
-        return l;
+        return loglike_sm<LIKE, PREC_SMEM>(m, ms, Pg, offP, ldP, n, ovn, owork, lane);
     }
 };
 
-template <int LIKE>
-__device__ bool doubling_accept(SliceEval<LIKE>& F, double x1, double loglstar, double L, double R, double fL,
-                                double fR) {
+template <class EVAL>
+__device__ bool doubling_accept(EVAL& F, double x1, double loglstar, double L, double R, double fL, double fR) {
     double lhat = L, rhat = R, fl = fL, fr = fR;
     bool D = false;
     while (rhat - lhat > 1.1) {
@@ -76,20 +73,20 @@ __device__ bool doubling_accept(SliceEval<LIKE>& F, double x1, double loglstar, 
     return true;
 }
 
-// one generic_slice_step along d (already scaled, not yet length-capped).  On success the
-// new point is left in F.un / its logl returned; `status` gets error / warning bits.
-template <int LIKE>
-__device__ double slice_step(SliceEval<LIKE>& F, ChainRng& g, double* d, double loglstar, bool doubling,
-                             int& n_expand, int& n_contract, bool& expansion_warning, int& err) {
-    const int n = F.n, lane = F.lane;
+// one generic_slice_step along b2n_sm[odir..] (already scaled, not yet length-capped).  On
+// success the new point is left in b2n_sm[F.oun..] and its logl returned.
+template <class EVAL>
+__device__ double slice_step(EVAL& F, ChainRng& g, double loglstar, bool doubling, int& n_expand, int& n_contract,
+                             bool& expansion_warning, int& err) {
+    const int n = F.n, lane = F.lane, odir = F.odir;
     const double rand0 = rng_uniform(g);                        // :1099
     double ss = 0.0;
-    for (int i = lane; i < n; i += 32) ss = fma(d[i], d[i], ss);
+    for (int i = lane; i < n; i += 32) ss = fma(b2n_sm[odir + i], b2n_sm[odir + i], ss);
     const double dirlen = sqrt(warp_sum(ss));
     const double maxlen = sqrt((double)n) / 2.0;
     if (dirlen > maxlen) {                                      // :1103-1108
         const double dn = dirlen / maxlen;
-        for (int i = lane; i < n; i += 32) d[i] = d[i] / dn;
+        for (int i = lane; i < n; i += 32) b2n_sm[odir + i] = b2n_sm[odir + i] / dn;
     }
     __syncwarp();
     double xl = -rand0, xr = 1.0 - rand0;                       // :1126-1127
@@ -124,8 +121,8 @@ __device__ double slice_step(SliceEval<LIKE>& F, ChainRng& g, double* d, double 
         const double xp = xl + rng_uniform(g) * (xr - xl);
         lp = F(xp);
         n_contract++;
-        if (lp > loglstar && (!doubling || doubling_accept<LIKE>(F, xp, loglstar, L, R, fL, fR))) {
-            if (doubling) {   // the acceptance test moved F.un: restore the accepted point
+        if (lp > loglstar && (!doubling || doubling_accept(F, xp, loglstar, L, R, fL, fR))) {
+            if (doubling) {   // the acceptance test moved F's scratch point: restore the accepted one
                 lp = F(xp);
                 F.nc--;
             }
@@ -140,39 +137,41 @@ __device__ double slice_step(SliceEval<LIKE>& F, ChainRng& g, double* d, double 
 }
 
 template <int LIKE, bool RANDOM_DIR, bool AX_SMEM, bool PREC_SMEM>
-__global__ void __launch_bounds__(256) slice_kernel(const SliceParams p) {
-    extern __shared__ double sm[];
+__global__ void __launch_bounds__(512, 1) slice_kernel(const SliceParams p) {
     const int n = p.n;
+    const int npad = (n + 1) & ~1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int3 cd = p.cta[blockIdx.x];
-    double* s = sm;
-    const double* A = p.axesT + (size_t)cd.z * n * n;
+    int off = 0;
+    const double* Ag = p.axesT + (size_t)cd.z * n * n;
+    int offA = 0, ldA = n;
     if (AX_SMEM) {
-        for (int i = threadIdx.x; i < n * n; i += blockDim.x) s[i] = A[i];
-        A = s;
-        s += n * n;
+        offA = off; ldA = p.ldA;
+        stage_matrix(Ag, offA, n, ldA);
+        off += n * ldA;
     }
-    const double* P = p.m.lmat;
+    const double* Pg = p.m.lmat;
+    int offP = 0, ldP = n;
     if (LIKE == B2N_LIKE_GAUSS_PREC && PREC_SMEM) {
-        for (int i = threadIdx.x; i < n * n; i += blockDim.x) s[i] = P[i];
-        P = s;
-        s += n * n;
+        offP = off; ldP = p.ldP;
+        stage_matrix(Pg, offP, n, ldP);
+        off += n * ldP;
     }
+    const ModelSm ms = stage_model(p.m, off, n, npad);
+    off += 4 * npad;
     __syncthreads();
-    double* ucur = s + (size_t)warp * 6 * n;
-    double* d = ucur + n;
-    double* un = d + n;
-    double* vn = un + n;
-    double* work = vn + n;       // likelihood scratch; also z / uniform vector
-    int* idxs = reinterpret_cast<int*>(work + n);   // n ints (permutation)
+    const int ou = off + warp * 6 * npad;
+    const int odir = ou + npad, oun = odir + npad, ovn = oun + npad, owork = ovn + npad;
+    int* idxs = reinterpret_cast<int*>(&b2n_sm[owork + npad]);   // permutation (n ints)
+    const int pk = p.m.prior_kind;
 
     for (int c = warp; c < cd.y; c += nwarps) {
         const int q = p.order[cd.x + c];
         ChainRng g;
         g.init(p.seed, p.chain0 + (uint64_t)q);
-        for (int i = lane; i < n; i += 32) ucur[i] = p.u0[(size_t)q * n + i];
+        for (int i = lane; i < n; i += 32) b2n_sm[ou + i] = p.u0[(size_t)q * n + i];
         __syncwarp();
-        SliceEval<LIKE> F{p.m, P, ucur, d, un, vn, work, lane, n, 0};
+        SliceEval<LIKE, PREC_SMEM> F{p.m, ms, Pg, offP, ldP, ou, odir, oun, ovn, owork, lane, n, pk, 0};
         int nexp = 0, ncon = 0, err = 0;
         bool doubling = p.doubling != 0, warned = false;
         double lcur = 0.0;
@@ -180,13 +179,16 @@ __global__ void __launch_bounds__(256) slice_kernel(const SliceParams p) {
             const int nsub = RANDOM_DIR ? 1 : n;
             if (!RANDOM_DIR && n > 1) {
                 // rstate.shuffle(idxs) (:673-674): argsort (stable) of one uniform vector event
-                for (int e = lane; e < n; e += 32) work[e] = rng_uniform_elem(g, e);
+                for (int e = lane; e < n; e += 32) b2n_sm[owork + e] = rng_uniform_elem(g, e);
                 g.tick++;
                 __syncwarp();
                 for (int e = lane; e < n; e += 32) {
-                    const double ve = work[e];
+                    const double ve = b2n_sm[owork + e];
                     int rk = 0;
-                    for (int f = 0; f < n; f++) rk += (work[f] < ve || (work[f] == ve && f < e)) ? 1 : 0;
+                    for (int f = 0; f < n; f++) {
+                        const double vf = b2n_sm[owork + f];
+                        rk += (vf < ve || (vf == ve && f < e)) ? 1 : 0;
+                    }
                     idxs[rk] = e;
                 }
                 __syncwarp();
@@ -197,36 +199,35 @@ __global__ void __launch_bounds__(256) slice_kernel(const SliceParams p) {
             for (int sub = 0; sub < nsub && !err; sub++) {
                 if (RANDOM_DIR) {
                     // drhat = z / |z| ; direction = axes @ drhat * scale (:820-824)
-                    const double ss = rng_normals_to(g, work, n, lane);
-                    const double inv = 1.0 / sqrt(ss);
-                    __syncwarp();
-                    for (int i = lane; i < n; i += 32) work[i] *= inv;
+                    const double ssq = normals_sm(g, owork, n, lane);
+                    const double fac = p.scale / sqrt(ssq);
                     __syncwarp();
                     for (int base = 0; base < n; base += 64) {
                         double y0, y1;
-                        warp_matvec2(A, n, n, work, base + lane, n, y0, y1);
-                        if (base + lane < n) d[base + lane] = y0 * p.scale;
-                        if (base + lane + 32 < n) d[base + lane + 32] = y1 * p.scale;
+                        matvec2o<AX_SMEM>(Ag, offA, ldA, n, owork, base + lane, n, y0, y1);
+                        if (base + lane < n) b2n_sm[odir + base + lane] = y0 * fac;
+                        if (base + lane + 32 < n) b2n_sm[odir + base + lane + 32] = y1 * fac;
                     }
                 } else {
                     // axes = scale * axes.T ; axis = axes[idx] (:665, 680) = column idx of the axes matrix
                     const int idx = idxs[sub];
-                    for (int i = lane; i < n; i += 32) d[i] = p.scale * A[(size_t)idx * n + i];
+                    for (int i = lane; i < n; i += 32) b2n_sm[odir + i] = p.scale * mat_ld<AX_SMEM>(Ag, offA + idx * ldA + i);
                 }
                 __syncwarp();
                 bool ew = false;
-                const double l = slice_step<LIKE>(F, g, d, p.loglstar, doubling, nexp, ncon, ew, err);
+                const double l = slice_step(F, g, p.loglstar, doubling, nexp, ncon, ew, err);
                 if (err) break;
                 lcur = l;
-                for (int i = lane; i < n; i += 32) ucur[i] = un[i];     // u = u_prop
+                for (int i = lane; i < n; i += 32) b2n_sm[ou + i] = b2n_sm[oun + i];     // u = u_prop
                 __syncwarp();
                 if (ew && !doubling) { doubling = true; warned = true; }   // :689-693, 836-838
             }
         }
         // v_prop = prior_transform(u_prop) (:1204)
         for (int i = lane; i < n; i += 32) {
-            p.u[(size_t)q * n + i] = ucur[i];
-            p.v[(size_t)q * n + i] = prior_1d(p.m, i, ucur[i]);
+            const double ui = b2n_sm[ou + i];
+            p.u[(size_t)q * n + i] = ui;
+            p.v[(size_t)q * n + i] = prior_sm(pk, ms.op0, ms.op1, i, ui);
         }
         if (lane == 0) {
             p.logl[q] = lcur;
@@ -260,21 +261,26 @@ static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slice
     if (ctx->bK < 1 || ctx->bn != n) return b2n_fail(ctx, B2N_ERR_ARG, "resident bound missing or of wrong dimension");
     if (Q == 0) return B2N_OK;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int warps = 8;
-    const size_t per_warp = (size_t)6 * n * sizeof(double);
-    const size_t fixed = per_warp * warps;
-    const size_t ax_b = (size_t)n * n * sizeof(double);
-    const size_t pr_b = (m.like_kind == B2N_LIKE_GAUSS_PREC) ? ax_b : 0;
+    const int npad = (n + 1) & ~1;
+    const size_t per_warp = (size_t)6 * npad * sizeof(double);           // u, d, un, vn, work, idxs
+    const size_t model_b = (size_t)4 * npad * sizeof(double);
     const size_t limit = (size_t)ctx->max_smem_optin;
-    if (fixed > limit) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for the slice kernel");
+    const int max_warps = (int)std::min<size_t>(16, (limit - model_b) / per_warp);
+    if (max_warps < 1) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for the slice kernel");
+    int chains_per_cta, warps;
+    b2n_chain_grid(ctx, Q, max_warps, chains_per_cta, warps);
+    const size_t fixed = per_warp * warps + model_b;
+    const int ldA = (n + 15) & ~15, ldP = ldA;
+    const size_t ax_b = (size_t)n * ldA * sizeof(double);
+    const size_t pr_b = (m.like_kind == B2N_LIKE_GAUSS_PREC) ? ax_b : 0;
     const bool ax_s = fixed + ax_b <= limit;
     const bool pr_s = pr_b > 0 && fixed + (ax_s ? ax_b : 0) + pr_b <= limit;
     const size_t smem = fixed + (ax_s ? ax_b : 0) + (pr_s ? pr_b : 0);
     std::vector<int> order;
     std::vector<int3> cta;
-    B2N_TRY(b2n_build_worklist(ctx, Q, a->ell, ctx->bK, warps, order, cta));
+    B2N_TRY(b2n_build_worklist(ctx, Q, a->ell, ctx->bK, chains_per_cta, order, cta));
     SliceParams p;
-    p.m = m; p.n = n; p.slices = slices; p.doubling = doubling;
+    p.m = m; p.n = n; p.slices = slices; p.doubling = doubling; p.ldA = ldA; p.ldP = ldP;
     p.loglstar = a->loglstar; p.scale = a->scale; p.seed = a->seed; p.chain0 = a->chain0;
     p.axesT = ctx->b_axesT.as<double>();
     const void *du0, *dorder, *dcta;
