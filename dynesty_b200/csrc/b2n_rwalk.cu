@@ -176,6 +176,189 @@ __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
     }
 }
 
+// =====================================================================================
+// rwalk_mma_kernel -- the same chains, 16 at a time per CTA in LOCK-STEP, with both mat-vecs
+// done as FP64 tensor-core MMAs (mma.sync m8n8k4 f64 = DMMA) whose A operands -- 8-row slabs
+// of axes and of the precision matrix -- live in REGISTERS for the whole kernel.
+//
+// Why: the warp-per-chain kernel above streams 40 KB of matrix per proposal out of shared
+// memory and is bound by the shared-memory pipe (84 % of peak, profiles/r1c).  All chains of
+// a CTA use the same matrices and take the same number of steps, so the per-step work of a
+// CTA is Y[n x 16] = A[n x n] X[n x 16]: a small dense contraction.  Distributing A over the
+// lanes as DMMA fragments (1 double per lane per 8x4 tile; 13 k-tiles for n = 50 -> 26
+// registers per matrix per warp) removes the matrix traffic from shared memory entirely and
+// replaces ~500 LDS/DFMA per proposal by ~4 DMMA.  Only the 16 direction vectors go through
+// shared memory.  Warp w is (i) the owner of chain w (RNG, wrap/reflect/cube test, prior,
+// accept/reject: phases 1,3,5) and (ii) the owner of work item (slab w % S, chain-tile w / S)
+// of the two contractions (phases 2,4); 4 CTA barriers per step.
+// Used when ncdim == ndim, 16 <= n <= 64 (fragments fit in registers); otherwise the
+// warp-per-chain kernel runs.  Results agree with it to round-off (different summation order).
+// =====================================================================================
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+#define B2N_MMA_CH 16          // chains in lock-step per CTA
+
+template <int LIKE, int KT>    // KT = k-tiles of 4 columns (n <= 4*KT)
+__global__ void __launch_bounds__(512, 1) rwalk_mma_kernel(const RwalkParams p) {
+    constexpr int RS = 8 * ((4 * KT + 7) / 8);                    // rows padded to whole 8-row slabs
+    constexpr int XS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16));   // chain stride == 4 (mod 16):
+                                                                  // the B-fragment loads are conflict free
+    constexpr int YS = RS + 2;
+    const int n = p.n;
+    const int npad = (n + 1) & ~1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int3 cd = p.cta[blockIdx.x];
+    const int S = (n + 7) >> 3;                     // 8-row slabs
+    // ---- shared-memory plan
+    int off = 0;
+    const ModelSm ms = stage_model(p.m, off, n, npad);
+    const int op0 = ms.op0, op1 = ms.op1, omu = ms.olv0;
+    off += 4 * npad;
+    uint32_t* fl = reinterpret_cast<uint32_t*>(&b2n_sm[off]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) fl[i] = p.dimflags ? p.dimflags[i] : 0u;
+    off += ((n + 3) >> 2) << 1;
+    const int oX = off;  off += B2N_MMA_CH * XS;    // direction z, later delta = v - mean (chain-major)
+    const int oY = off;  off += B2N_MMA_CH * YS;    // axes @ z (chain-major)
+    const int oQ = off;  off += 8 * B2N_MMA_CH;     // per-slab partial quadratic forms
+    const int ost = off;                            // per-chain state: ucur, uprop, vcur, vprop
+    for (int e = threadIdx.x; e < B2N_MMA_CH * XS; e += blockDim.x) b2n_sm[oX + e] = 0.0;
+    // ---- matrix fragments -> registers.  item (s, t): slab s of rows, chain tile t
+    const int s_it = warp % S, t_it = warp / S;
+    const bool has_item = warp < 2 * S && t_it < 2;
+    double fragA[KT], fragP[KT];
+    {
+        const double* Ag = p.axesT + (size_t)cd.z * n * n;      // axesT[j*n + i] = axes[i][j]
+        const double* Pg = p.m.lmat;
+        const int row = 8 * s_it + (lane >> 2);
+#pragma unroll
+        for (int kt = 0; kt < KT; kt++) {
+            const int col = 4 * kt + (lane & 3);
+            const bool in = has_item && row < n && col < n;
+            fragA[kt] = in ? Ag[(size_t)col * n + row] : 0.0;
+            fragP[kt] = (LIKE == B2N_LIKE_GAUSS_PREC && in) ? Pg[(size_t)row * n + col] : 0.0;
+        }
+    }
+    __syncthreads();
+    const double inv_n = 1.0 / (double)n;
+    const int pk = p.m.prior_kind;
+
+    for (int g0 = 0; g0 < cd.y; g0 += B2N_MMA_CH) {             // groups of 16 chains
+        const int c = warp;                                     // chain slot owned by this warp
+        const bool live = g0 + c < cd.y;
+        const int q = live ? p.order[cd.x + g0 + c] : 0;
+        int oucur = ost + c * 4 * npad, ouprop = oucur + npad, ovcur = ouprop + npad, ovprop = ovcur + npad;
+        const int ox = oX + c * XS, oy = oY + c * YS;
+        ChainRng g;
+        g.init(p.seed, p.chain0 + (uint64_t)q);
+        if (live)
+            for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)q * n + i];
+        int nacc = 0, nrej = 0;
+        double lcur = 0.0;
+        __syncthreads();
+        for (int step = 0; step < p.walks; step++) {
+            // ---- phase 1 (chain warp): direction in the unit ball -> X[c]
+            double fac = 0.0;
+            if (live) fac = p.scale * ball_direction(g, ox, n, lane, inv_n);
+            __syncthreads();
+            // ---- phase 2 (item warp): Y[rows of slab][chains of tile] = A_slab @ X
+            if (has_item) {
+                double d0 = 0.0, d1 = 0.0;
+                const int xb = oX + (8 * t_it + (lane >> 2)) * XS + (lane & 3);
+#pragma unroll
+                for (int kt = 0; kt < KT; kt++) dmma884(d0, d1, fragA[kt], b2n_sm[xb + 4 * kt]);
+                const int row = 8 * s_it + (lane >> 2), c0 = 8 * t_it + 2 * (lane & 3);
+                b2n_sm[oY + c0 * YS + row] = d0;
+                b2n_sm[oY + (c0 + 1) * YS + row] = d1;
+            }
+            __syncthreads();
+            // ---- phase 3 (chain warp): u' = u + fac*y, wrap / reflect / cube test, prior, delta -> X[c]
+            bool ok = true;
+            if (live) {
+                for (int i = lane; i < n; i += 32) {
+                    double t = fma(fac, b2n_sm[oy + i], b2n_sm[oucur + i]);
+                    const uint32_t f = fl[i];
+                    if (f & B2N_DIM_PERIODIC) t = mod1(t);
+                    if (f & B2N_DIM_REFLECTIVE) t = reflect1(t);
+                    ok = ok && in_cube(t, f);
+                    const double vi = prior_sm(pk, op0, op1, i, t);
+                    b2n_sm[ouprop + i] = t;
+                    b2n_sm[ovprop + i] = vi;
+                    b2n_sm[ox + i] = vi - b2n_sm[omu + i];
+                }
+                ok = __all_sync(B2N_FULL, ok);
+            }
+            double l = 0.0;
+            if (LIKE == B2N_LIKE_GAUSS_PREC) {
+                __syncthreads();
+                // ---- phase 4 (item warp): partial delta^T P delta over the rows of the slab
+                if (has_item) {
+                    double d0 = 0.0, d1 = 0.0;
+                    const int xb = oX + (8 * t_it + (lane >> 2)) * XS + (lane & 3);
+#pragma unroll
+                    for (int kt = 0; kt < KT; kt++) dmma884(d0, d1, fragP[kt], b2n_sm[xb + 4 * kt]);
+                    const int row = 8 * s_it + (lane >> 2), c0 = 8 * t_it + 2 * (lane & 3);
+                    double q0 = d0 * b2n_sm[oX + c0 * XS + row], q1 = d1 * b2n_sm[oX + (c0 + 1) * XS + row];
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) {
+                        q0 += __shfl_xor_sync(B2N_FULL, q0, o);
+                        q1 += __shfl_xor_sync(B2N_FULL, q1, o);
+                    }
+                    if (lane < 4) {
+                        b2n_sm[oQ + s_it * B2N_MMA_CH + c0] = q0;
+                        b2n_sm[oQ + s_it * B2N_MMA_CH + c0 + 1] = q1;
+                    }
+                }
+                __syncthreads();
+                // ---- phase 5 (chain warp): logl
+                double qf = 0.0;
+                for (int s = 0; s < S; s++) qf += b2n_sm[oQ + s * B2N_MMA_CH + c];
+                l = fma(-0.5, qf, p.m.s0);
+            } else if (live && ok) {
+                __syncwarp();
+                l = loglike_sm<LIKE, false>(p.m, ms, nullptr, 0, n, n, ovprop, oy, lane);
+            }
+            if (live) {
+                if (!ok) {
+                    nrej++;
+                } else if (l > p.loglstar) {
+                    int t = oucur; oucur = ouprop; ouprop = t;
+                    t = ovcur; ovcur = ovprop; ovprop = t;
+                    lcur = l;
+                    nacc++;
+                } else {
+                    nrej++;
+                }
+            }
+        }
+        if (live) {
+            if (nacc == 0) {   // recompute (v, logl) of the start point (:970-975), warp-local
+                for (int i = lane; i < n; i += 32) b2n_sm[ovcur + i] = prior_sm(pk, op0, op1, i, b2n_sm[oucur + i]);
+                __syncwarp();
+                lcur = loglike_sm<LIKE, false>(p.m, ms, p.m.lmat, 0, n, n, ovcur, oy, lane);
+            }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                p.u[(size_t)q * n + i] = b2n_sm[oucur + i];
+                p.v[(size_t)q * n + i] = b2n_sm[ovcur + i];
+            }
+            if (lane == 0) {
+                p.logl[q] = lcur;
+                p.nacc[q] = nacc;
+                p.nrej[q] = nrej;
+                p.ncall[q] = p.walks;
+            }
+        }
+        __syncthreads();
+        // X rows of chains that are not live in the next group must read as zero
+        for (int e = threadIdx.x; e < B2N_MMA_CH * XS; e += blockDim.x) b2n_sm[oX + e] = 0.0;
+        __syncthreads();
+    }
+}
+
 // Host-side grouping of chains by ellipsoid -> per-CTA work descriptors.
 // (shared with the slice kernels)
 int b2n_build_worklist(b2n_ctx* ctx, int64_t Q, const int32_t* ell, int K, int chains_per_cta,
@@ -238,13 +421,32 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     if (max_warps < 1) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for the rwalk kernel");
     int chains_per_cta, warps;
     b2n_chain_grid(ctx, Q, max_warps, chains_per_cta, warps);
+    // lock-step DMMA kernel: matrices as register fragments (needs ncdim == ndim, 16 <= n <= 64
+    // and enough chains to fill CTAs).  B2N_RWALK_IMPL=warp|mma forces one of the two.
+    const char* impl = getenv("B2N_RWALK_IMPL");
+    bool use_mma = nc == n && n >= 16 && n <= 64 && Q >= 8 * (int64_t)ctx->sm_count;
+    if (impl && !strcmp(impl, "warp")) use_mma = false;
+    if (impl && !strcmp(impl, "mma")) {
+        if (!(nc == n && n >= 4 && n <= 64)) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "B2N_RWALK_IMPL=mma needs ncdim == ndim <= 64");
+        use_mma = true;
+    }
+    const int KT = n <= 32 ? 8 : (n <= 52 ? 13 : 16);
+    size_t mma_smem = 0;
+    if (use_mma) {
+        const int sms = ctx->sm_count;
+        chains_per_cta = (int)std::max<int64_t>(1, (Q + sms - 1) / sms);
+        warps = 16;
+        const int RS = 8 * ((4 * KT + 7) / 8);
+        const int XS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16)), YS = RS + 2;
+        mma_smem = (size_t)(4 * npad + (((n + 3) >> 2) << 1) + 16 * XS + 16 * YS + 8 * 16 + 16 * 4 * npad) * sizeof(double);
+    }
     const size_t fixed = per_warp * warps + flags_b;
     const int ldA = (nc + 15) & ~15, ldP = (n + 15) & ~15;
     const size_t ax_b = (size_t)nc * ldA * sizeof(double);
     const size_t pr_b = (m.like_kind == B2N_LIKE_GAUSS_PREC) ? (size_t)n * ldP * sizeof(double) : 0;
     const bool ax_s = fixed + ax_b <= limit;
     const bool pr_s = pr_b > 0 && fixed + (ax_s ? ax_b : 0) + pr_b <= limit;
-    const size_t smem = fixed + (ax_s ? ax_b : 0) + (pr_s ? pr_b : 0);
+    const size_t smem = use_mma ? mma_smem : fixed + (ax_s ? ax_b : 0) + (pr_s ? pr_b : 0);
 
     std::vector<int> order;
     std::vector<int3> cta;
@@ -287,9 +489,25 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     else if (ax_s) LAUNCH(L, true, false);                             \
     else if (pr_s) LAUNCH(L, false, true);                             \
     else LAUNCH(L, false, false);
+#define LAUNCH_MMA(L, K)                                                                            \
+    do {                                                                                            \
+        B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_mma_kernel<L, K>,                                   \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        rwalk_mma_kernel<L, K><<<grid, 512, smem, ctx->stream>>>(p);                                 \
+    } while (0)
+#define CALL_MMA(L)                      \
+    if (KT == 8) LAUNCH_MMA(L, 8);       \
+    else if (KT == 13) LAUNCH_MMA(L, 13); \
+    else LAUNCH_MMA(L, 16);
     B2N_TIME_BEGIN(ctx);
-    B2N_DISPATCH_LIKE(m.like_kind, CALL)
+    if (use_mma) {
+        B2N_DISPATCH_LIKE(m.like_kind, CALL_MMA)
+    } else {
+        B2N_DISPATCH_LIKE(m.like_kind, CALL)
+    }
     B2N_TIME_END(ctx);
+#undef CALL_MMA
+#undef LAUNCH_MMA
 #undef CALL
 #undef LAUNCH
     B2N_LAUNCH_CHECK(ctx);

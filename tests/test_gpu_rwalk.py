@@ -171,3 +171,75 @@ def test_rwalk_large_queue_many_ellipsoids():
         r = OS.rwalk_chain(u0[i], loglstar, axes[ell[i]], 0.9, m, philox.ChainStream(99, i), 10)
         assert r['n_accept'] == o['n_accept'][i]
         close(o['u'][i], r['u'], rtol=1e-9)
+
+
+class _Impl:
+    """Force one of the two rwalk kernels (b2n_rwalk.cu reads B2N_RWALK_IMPL per call)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        import os
+        self.old = os.environ.get('B2N_RWALK_IMPL')
+        os.environ['B2N_RWALK_IMPL'] = self.name
+
+    def __exit__(self, *a):
+        import os
+        if self.old is None:
+            os.environ.pop('B2N_RWALK_IMPL', None)
+        else:
+            os.environ['B2N_RWALK_IMPL'] = self.old
+
+
+@pytest.mark.parametrize('name', ['g6', 'wall', 'g50'])
+def test_rwalk_mma_kernel_golden(golden, name):
+    """The lock-step DMMA kernel against the reference-generated fixtures (ncdim == ndim cases)."""
+    g = golden['chains']
+    p = 'rwalk_%s_' % name
+    m = MODELS[name]
+    dm = device_model(m)
+    per, ref = g[p + 'periodic'], g[p + 'reflective']
+    flags = ops.dimflags_from(m.ndim, per if len(per) else None, ref if len(ref) else None)
+    ops.bound_set(g[p + 'axes'])
+    with _Impl('mma'):
+        o = ops.rwalk_batch(dm.model_id(), g[p + 'u0'], float(g[p + 'loglstar']), float(g[p + 'scale']),
+                            int(g[p + 'walks']), SEED, chain0=int(g[p + 'chain0']), dimflags=flags)
+    assert np.array_equal(o['n_accept'], g[p + 'accept'])
+    assert np.array_equal(o['n_reject'], g[p + 'reject'])
+    close(o['u'], g[p + 'u'], rtol=1e-9)
+    close(o['v'], g[p + 'v'], rtol=1e-9)
+    np.testing.assert_allclose(o['logl'], g[p + 'logl'], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize('like', ['g50', 'n40diag', 'egg32', 'shell20'])
+def test_rwalk_mma_matches_warp_kernel(like):
+    """Both kernels on the same queue (K = 3 ellipsoids, 5000 chains > 16 per CTA): identical
+    accept counts, end points equal to round-off, for every likelihood kind."""
+    from oracle import likelihoods as OL
+    m = {'g50': MODELS['g50'], 'n40diag': OL.iid_normal_ppf(40), 'egg32': OL.eggbox(32),
+         'shell20': OL.shells(20)}[like]
+    n = m.ndim
+    dm = device_model(m)
+    rng = np.random.default_rng(n)
+    pts = (0.5 + 0.03 * rng.standard_normal((3000, n))) if like != 'egg32' else rng.random((3000, n))
+    logl = m.loglike(m.prior_transform(pts))
+    loglstar = float(np.quantile(logl, 0.3))
+    good = pts[logl > loglstar]
+    ells = [OB.bounding_ellipsoid(good[i::3]) for i in range(3)]
+    axes = np.array([e.axes for e in ells])
+    Q = 5000
+    u0 = good[rng.integers(len(good), size=Q)]
+    ell = rng.integers(3, size=Q).astype(np.int32)
+    ops.bound_set(axes)
+    out = {}
+    for impl in ('warp', 'mma'):
+        with _Impl(impl):
+            out[impl] = ops.rwalk_batch(dm.model_id(), u0, loglstar, 0.4, 30, 4242, chain0=9, ell=ell)
+    a, b = out['warp'], out['mma']
+    same = a['n_accept'] == b['n_accept']
+    assert same.mean() > 0.999            # a proposal within round-off of loglstar may flip
+    close(b['u'][same], a['u'][same], rtol=1e-9)
+    np.testing.assert_allclose(b['logl'][same], a['logl'][same], rtol=1e-9, atol=1e-9)
+    assert np.all(b['logl'] > loglstar) and np.all(b['n_accept'] + b['n_reject'] == 30)
+    assert 0.02 < b['n_accept'].mean() / 30 < 0.98
