@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(1024) eig_ladder_kernel(NodeArrays na, const i
             Cm[e] = v; AM[e] = v; AX[e] = v;
         }
         for (int k = tid; k < n; k += T) LM[k] = 1.0;
-        if (tid == 0) { st->good = 0; st->fallback = 1; st->sweeps = s_sweeps; }
+        if (tid == 0) { st->good = 0; st->fallback = 1; st->sweeps = s_sweeps; st->retry = 0; }
         return;
     }
     // rank-sort eigenvalues ascending (LAPACK order); tmpv[k] = rank of eigenpair k
@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(1024) eig_ladder_kernel(NodeArrays na, const i
         if (pass == 0) st->good = (trial == 0) ? 1 : 0;
         st->fallback = 0;
         st->sweeps = s_sweeps;
+        st->retry = 0;
     }
 }
 
@@ -405,6 +406,7 @@ __global__ void __launch_bounds__(256) scale_finish_kernel(NodeArrays na, const 
     const NodeRef nr = refs[blockIdx.x];
     const size_t nn = (size_t)n * n;
     NodeStat* st = na.stat + nr.node;
+    if (st->retry) return;          // covariance still being repaired: decomposed again first
     if (tid == 0) {
         double fm = -INFINITY;
         for (int k = 0; k < nr.nslots; k++) fm = fmax(fm, partial[nr.slot0 + k]);
@@ -534,7 +536,7 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
     const int use_smem = small_b + mats_b <= (size_t)ctx->max_smem_optin ? 1 : 0;
     const size_t eig_smem = small_b + (use_smem ? mats_b : 0);
     double* gwork = nullptr;
-    if (!use_smem) {
+    if (!use_smem) {       // only used if the sliced path cannot take the matrix either
         B2N_CUDA(ctx, ctx->scratch2.ensure((size_t)nnodes * mats_b));
         gwork = ctx->scratch2.as<double>();
     }
@@ -577,8 +579,13 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
             pn = (int)refs2.size();
             pj = (int)jobs2.size();
         }
-        eig_ladder_kernel<<<pn, eig_threads, eig_smem, st>>>(w.na, (const int*)plist, pass, gwork, use_smem);
-        B2N_LAUNCH_CHECK(ctx);
+        // large n: packed-triangle / column-sliced Jacobi (b2n_eig_sliced.cu); else the single-CTA kernel
+        int sliced = 0;
+        if (!use_smem) B2N_TRY(b2n_eig_sliced(w, (const int*)plist, pn, pass, 0, &sliced));
+        if (!sliced) {
+            eig_ladder_kernel<<<pn, eig_threads, eig_smem, st>>>(w.na, (const int*)plist, pass, gwork, use_smem);
+            B2N_LAUNCH_CHECK(ctx);
+        }
         fmax_partial_kernel<<<pj, 256, fm_smem, st>>>(w.P, w.perm, w.N, w.na, (const JobL*)pjobs, partial);
         B2N_LAUNCH_CHECK(ctx);
         scale_finish_kernel<<<pn, 256, 0, st>>>(w.na, (const NodeRef*)prefs, partial, pass, w.logvol_pref);
@@ -590,6 +597,44 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
         for (int i = 0; i < nnodes; i++) {
             if (pass == 1 && (hs[i].good || hs[i].error)) continue;
             hs[i] = all[refs[i].node];
+        }
+        // sliced path: the repair ladder is one decomposition per launch -> re-run the nodes whose
+        // covariance was modified (rare: rank-deficient / ill-conditioned clouds), up to 100 trials
+        for (int attempt = 1; sliced && attempt < 100; attempt++) {
+            std::vector<NodeRef> refs3;
+            std::vector<JobL> jobs3;
+            std::vector<int> list3, which;
+            int s3 = 0;
+            for (int i = 0; i < nnodes; i++) {
+                if (!hs[i].retry) continue;
+                NodeRef r = refs[i];
+                r.slot0 = s3;
+                for (int a = r.start; a < r.start + r.count; a += B2N_ROWS_PER_JOB) {
+                    JobL j;
+                    memset(&j, 0, sizeof(j));
+                    j.node = r.node; j.r0 = a; j.r1 = std::min(a + B2N_ROWS_PER_JOB, r.start + r.count);
+                    j.slot = s3++; j.level = r.level;
+                    jobs3.push_back(j);
+                }
+                r.nslots = s3 - r.slot0;
+                refs3.push_back(r);
+                list3.push_back(r.node);
+                which.push_back(i);
+            }
+            if (refs3.empty()) break;
+            const void *j3, *r3, *l3;
+            B2N_TRY(b2n_in_host(ctx, ctx->scratch4, jobs3.data(), jobs3.size() * sizeof(JobL), &j3));
+            B2N_TRY(b2n_in_host(ctx, ctx->scratch5, refs3.data(), refs3.size() * sizeof(NodeRef), &r3));
+            B2N_TRY(b2n_in_host(ctx, ctx->work0, list3.data(), list3.size() * sizeof(int), &l3));
+            int used = 0;
+            B2N_TRY(b2n_eig_sliced(w, (const int*)l3, (int)refs3.size(), pass, 1, &used));
+            fmax_partial_kernel<<<(unsigned)jobs3.size(), 256, fm_smem, st>>>(w.P, w.perm, w.N, w.na, (const JobL*)j3, partial);
+            B2N_LAUNCH_CHECK(ctx);
+            scale_finish_kernel<<<(unsigned)refs3.size(), 256, 0, st>>>(w.na, (const NodeRef*)r3, partial, pass, w.logvol_pref);
+            B2N_LAUNCH_CHECK(ctx);
+            B2N_CUDA(ctx, cudaStreamSynchronize(st));
+            B2N_CUDA(ctx, cudaMemcpy(all.data(), w.na.stat, (size_t)w.cap * sizeof(NodeStat), cudaMemcpyDeviceToHost));
+            for (int i : which) hs[i] = all[refs[i].node];
         }
     }
     stats = hs;

@@ -18,6 +18,8 @@ struct NodeStat {
     int fallback;    // identity fallback taken                              bounding.py:1373-1378
     int error;       // b2n_status for this node (0 ok)
     int sweeps;      // Jacobi sweeps of the last decomposition (diagnostic)
+    int trial;       // repair-ladder trial counter (sliced path: one decomposition per launch)
+    int retry;       // 1 = covariance was modified, decompose again (bounding.py:1362-1371)
     double fmax;     // max_i delta_i^T am delta_i                           bounding.py:1438
     double mult;     // covariance scaling applied after pass 0              bounding.py:1444-1450
     double logvol;
@@ -64,6 +66,7 @@ int b2n_boundwork_init(b2n_ctx* ctx, BoundWork& w, const double* dP, int64_t N, 
 int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs, std::vector<NodeStat>& stats);
 int b2n_emit_node(BoundWork& w, int node, int k, double* ctr, double* cov, double* am, double* axes, double* axlens);
 int b2n_init_identity_perm(BoundWork& w);
+int b2n_eig_sliced(BoundWork& w, const int* dlist, int pn, int pass, int retry_only, int* used);
 #endif
 
 int b2n_membership_dev(b2n_ctx* ctx, const double* x, int64_t M, int n, const double* ctrs,

@@ -424,7 +424,9 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     // lock-step DMMA kernel: matrices as register fragments (needs ncdim == ndim, 16 <= n <= 64
     // and enough chains to fill CTAs).  B2N_RWALK_IMPL=warp|mma forces one of the two.
     const char* impl = getenv("B2N_RWALK_IMPL");
-    bool use_mma = nc == n && n >= 16 && n <= 64 && Q >= 8 * (int64_t)ctx->sm_count;
+    // (the choice depends on the problem shape only, never on the queue size: a chain's result
+    // must not depend on which batch it is part of -- sharded multi-GPU runs rely on that)
+    bool use_mma = nc == n && n >= 16 && n <= 64;
     if (impl && !strcmp(impl, "warp")) use_mma = false;
     if (impl && !strcmp(impl, "mma")) {
         if (!(nc == n && n >= 4 && n <= 64)) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "B2N_RWALK_IMPL=mma needs ncdim == ndim <= 64");
