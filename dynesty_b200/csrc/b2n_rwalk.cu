@@ -200,10 +200,11 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                  : "d"(a), "d"(b));
 }
 
-#define B2N_MMA_CH 16          // chains in lock-step per CTA
-
-template <int LIKE, int KT>    // KT = k-tiles of 4 columns (n <= 4*KT)
-__global__ void __launch_bounds__(512, 1) rwalk_mma_kernel(const RwalkParams p) {
+// KT = k-tiles of 4 columns (n <= 4*KT); CH = chains in lock-step per CTA (8 -> 256 threads, two
+// CTAs per SM overlap each other's barriers: measured 1.3x faster than one 16-chain CTA per SM)
+template <int LIKE, int KT, int CH>
+__global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(const RwalkParams p) {
+    constexpr int B2N_MMA_CH = CH;
     constexpr int RS = 8 * ((4 * KT + 7) / 8);                    // rows padded to whole 8-row slabs
     constexpr int XS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16));   // chain stride == 4 (mod 16):
                                                                   // the B-fragment loads are conflict free
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_mma_kernel(const RwalkParams p) 
     for (int e = threadIdx.x; e < B2N_MMA_CH * XS; e += blockDim.x) b2n_sm[oX + e] = 0.0;
     // ---- matrix fragments -> registers.  item (s, t): slab s of rows, chain tile t
     const int s_it = warp % S, t_it = warp / S;
-    const bool has_item = warp < 2 * S && t_it < 2;
+    const bool has_item = warp < (CH / 8) * S && t_it < CH / 8;
     double fragA[KT], fragP[KT];
     {
         const double* Ag = p.axesT + (size_t)cd.z * n * n;      // axesT[j*n + i] = axes[i][j]
@@ -435,12 +436,12 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     const int KT = n <= 32 ? 8 : (n <= 52 ? 13 : 16);
     size_t mma_smem = 0;
     if (use_mma) {
-        const int sms = ctx->sm_count;
-        chains_per_cta = (int)std::max<int64_t>(1, (Q + sms - 1) / sms);
-        warps = 16;
+        const int ctas = 2 * ctx->sm_count;                 // 8-chain CTAs, two resident per SM
+        chains_per_cta = (int)std::max<int64_t>(1, (Q + ctas - 1) / ctas);
+        warps = 8;
         const int RS = 8 * ((4 * KT + 7) / 8);
         const int XS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16)), YS = RS + 2;
-        mma_smem = (size_t)(4 * npad + (((n + 3) >> 2) << 1) + 16 * XS + 16 * YS + 8 * 16 + 16 * 4 * npad) * sizeof(double);
+        mma_smem = (size_t)(4 * npad + (((n + 3) >> 2) << 1) + 8 * XS + 8 * YS + 8 * 8 + 8 * 4 * npad) * sizeof(double);
     }
     const size_t fixed = per_warp * warps + flags_b;
     const int ldA = (nc + 15) & ~15, ldP = (n + 15) & ~15;
@@ -493,9 +494,9 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     else LAUNCH(L, false, false);
 #define LAUNCH_MMA(L, K)                                                                            \
     do {                                                                                            \
-        B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_mma_kernel<L, K>,                                   \
+        B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_mma_kernel<L, K, 8>,                                \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        rwalk_mma_kernel<L, K><<<grid, 512, smem, ctx->stream>>>(p);                                 \
+        rwalk_mma_kernel<L, K, 8><<<grid, 256, smem, ctx->stream>>>(p);                              \
     } while (0)
 #define CALL_MMA(L)                      \
     if (KT == 8) LAUNCH_MMA(L, 8);       \

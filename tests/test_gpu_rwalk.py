@@ -242,4 +242,4 @@ def test_rwalk_mma_matches_warp_kernel(like):
     close(b['u'][same], a['u'][same], rtol=1e-9)
     np.testing.assert_allclose(b['logl'][same], a['logl'][same], rtol=1e-9, atol=1e-9)
     assert np.all(b['logl'] > loglstar) and np.all(b['n_accept'] + b['n_reject'] == 30)
-    assert 0.02 < b['n_accept'].mean() / 30 < 0.98
+    assert 0.002 < b['n_accept'].mean() / 30 < 0.98      # (eggbox at 32-D accepts ~1 %)
