@@ -360,6 +360,173 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
     }
 }
 
+// =====================================================================================
+// rwalk_mmas_kernel -- lock-step DMMA kernel for LARGE n (64 < n: the matrix fragments do not
+// fit in registers, and at n = 200 the 320 KB axes matrix does not even fit in shared memory).
+// Same phases as rwalk_mma_kernel with 16 chains per CTA, but the A-operand fragments are
+// STREAMED from global memory (L2-resident) every step: each 8x4 fragment is loaded once per
+// CTA-step and feeds two DMMAs (the two 8-chain tiles), so the L2 traffic per proposal is
+// n^2*8/16 bytes instead of the n^2*8 of the warp-per-chain kernel (20 KB vs 320 KB at n=200).
+// Warp w owns slabs w, w+16, ...  BASELINE config C4 (200-D, single ellipsoid, rwalk).
+// =====================================================================================
+template <int LIKE>
+__global__ void __launch_bounds__(512, 1) rwalk_mmas_kernel(const RwalkParams p, int XS, int YS) {
+    constexpr int CH = 16;
+    const int n = p.n;
+    const int npad = (n + 1) & ~1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int3 cd = p.cta[blockIdx.x];
+    const int S = (n + 7) >> 3, KT = (n + 3) >> 2;
+    int off = 0;
+    const ModelSm ms = stage_model(p.m, off, n, npad);
+    const int op0 = ms.op0, op1 = ms.op1, omu = ms.olv0;
+    off += 4 * npad;
+    uint32_t* fl = reinterpret_cast<uint32_t*>(&b2n_sm[off]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) fl[i] = p.dimflags ? p.dimflags[i] : 0u;
+    off += ((n + 3) >> 2) << 1;
+    const int oX = off;  off += CH * XS;
+    const int oY = off;  off += CH * YS;
+    const int oQ = off;  off += S * CH;
+    const int ost = off;
+    for (int e = threadIdx.x; e < CH * XS; e += blockDim.x) b2n_sm[oX + e] = 0.0;
+    const double* __restrict__ Ag = p.axesT + (size_t)cd.z * n * n;     // axesT[col*n + row] = axes[row][col]
+    const double* __restrict__ Pg = p.m.lmat;                             // symmetric
+    __syncthreads();
+    const double inv_n = 1.0 / (double)n;
+    const int pk = p.m.prior_kind;
+    const int lr = lane >> 2, lc = lane & 3;
+
+    for (int g0 = 0; g0 < cd.y; g0 += CH) {
+        const int c = warp;
+        const bool live = g0 + c < cd.y;
+        const int q = live ? p.order[cd.x + g0 + c] : 0;
+        int oucur = ost + c * 4 * npad, ouprop = oucur + npad, ovcur = ouprop + npad, ovprop = ovcur + npad;
+        const int ox = oX + c * XS, oy = oY + c * YS;
+        ChainRng g;
+        g.init(p.seed, p.chain0 + (uint64_t)q);
+        if (live)
+            for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)q * n + i];
+        int nacc = 0, nrej = 0;
+        double lcur = 0.0;
+        __syncthreads();
+        for (int step = 0; step < p.walks; step++) {
+            double fac = 0.0;
+            if (live) fac = p.scale * ball_direction(g, ox, n, lane, inv_n);
+            __syncthreads();
+            // ---- Y = A X, fragments of A streamed from L2
+            for (int s = warp; s < S; s += CH) {
+                const int row = 8 * s + lr;
+                const bool rv = row < n;
+                const double* ap = Ag + (rv ? row : 0) + (size_t)lc * n;
+                const int xb0 = oX + lr * XS + lc, xb1 = xb0 + 8 * XS;
+                double d00 = 0, d01 = 0, d10 = 0, d11 = 0;
+#pragma unroll 8
+                for (int kt = 0; kt < KT; kt++) {
+                    const bool in = rv && (4 * kt + lc) < n;
+                    const double a = in ? __ldg(ap + (size_t)(4 * kt) * n) : 0.0;
+                    dmma884(d00, d01, a, b2n_sm[xb0 + 4 * kt]);
+                    dmma884(d10, d11, a, b2n_sm[xb1 + 4 * kt]);
+                }
+                const int c0 = 2 * lc;
+                b2n_sm[oY + c0 * YS + row] = d00;
+                b2n_sm[oY + (c0 + 1) * YS + row] = d01;
+                b2n_sm[oY + (8 + c0) * YS + row] = d10;
+                b2n_sm[oY + (9 + c0) * YS + row] = d11;
+            }
+            __syncthreads();
+            bool ok = true;
+            if (live) {
+                for (int i = lane; i < n; i += 32) {
+                    double t = fma(fac, b2n_sm[oy + i], b2n_sm[oucur + i]);
+                    const uint32_t f = fl[i];
+                    if (f & B2N_DIM_PERIODIC) t = mod1(t);
+                    if (f & B2N_DIM_REFLECTIVE) t = reflect1(t);
+                    ok = ok && in_cube(t, f);
+                    const double vi = prior_sm(pk, op0, op1, i, t);
+                    b2n_sm[ouprop + i] = t;
+                    b2n_sm[ovprop + i] = vi;
+                    b2n_sm[ox + i] = vi - b2n_sm[omu + i];
+                }
+                ok = __all_sync(B2N_FULL, ok);
+            }
+            double l = 0.0;
+            if (LIKE == B2N_LIKE_GAUSS_PREC) {
+                __syncthreads();
+                for (int s = warp; s < S; s += CH) {
+                    const int row = 8 * s + lr;
+                    const bool rv = row < n;
+                    const double* pp = Pg + (rv ? row : 0) + (size_t)lc * n;
+                    const int xb0 = oX + lr * XS + lc, xb1 = xb0 + 8 * XS;
+                    double d00 = 0, d01 = 0, d10 = 0, d11 = 0;
+#pragma unroll 8
+                    for (int kt = 0; kt < KT; kt++) {
+                        const bool in = rv && (4 * kt + lc) < n;
+                        const double a = in ? __ldg(pp + (size_t)(4 * kt) * n) : 0.0;
+                        dmma884(d00, d01, a, b2n_sm[xb0 + 4 * kt]);
+                        dmma884(d10, d11, a, b2n_sm[xb1 + 4 * kt]);
+                    }
+                    const int c0 = 2 * lc;
+                    double q00 = d00 * b2n_sm[oX + c0 * XS + row], q01 = d01 * b2n_sm[oX + (c0 + 1) * XS + row];
+                    double q10 = d10 * b2n_sm[oX + (8 + c0) * XS + row], q11 = d11 * b2n_sm[oX + (9 + c0) * XS + row];
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) {
+                        q00 += __shfl_xor_sync(B2N_FULL, q00, o);
+                        q01 += __shfl_xor_sync(B2N_FULL, q01, o);
+                        q10 += __shfl_xor_sync(B2N_FULL, q10, o);
+                        q11 += __shfl_xor_sync(B2N_FULL, q11, o);
+                    }
+                    if (lane < 4) {
+                        b2n_sm[oQ + s * CH + c0] = q00;
+                        b2n_sm[oQ + s * CH + c0 + 1] = q01;
+                        b2n_sm[oQ + s * CH + 8 + c0] = q10;
+                        b2n_sm[oQ + s * CH + 9 + c0] = q11;
+                    }
+                }
+                __syncthreads();
+                double qf = 0.0;
+                for (int s = 0; s < S; s++) qf += b2n_sm[oQ + s * CH + c];
+                l = fma(-0.5, qf, p.m.s0);
+            } else if (live && ok) {
+                __syncwarp();
+                l = loglike_sm<LIKE, false>(p.m, ms, nullptr, 0, n, n, ovprop, oy, lane);
+            }
+            if (live) {
+                if (!ok) {
+                    nrej++;
+                } else if (l > p.loglstar) {
+                    int t = oucur; oucur = ouprop; ouprop = t;
+                    t = ovcur; ovcur = ovprop; ovprop = t;
+                    lcur = l;
+                    nacc++;
+                } else {
+                    nrej++;
+                }
+            }
+        }
+        if (live) {
+            if (nacc == 0) {
+                for (int i = lane; i < n; i += 32) b2n_sm[ovcur + i] = prior_sm(pk, op0, op1, i, b2n_sm[oucur + i]);
+                __syncwarp();
+                lcur = loglike_sm<LIKE, false>(p.m, ms, p.m.lmat, 0, n, n, ovcur, oy, lane);
+            }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                p.u[(size_t)q * n + i] = b2n_sm[oucur + i];
+                p.v[(size_t)q * n + i] = b2n_sm[ovcur + i];
+            }
+            if (lane == 0) {
+                p.logl[q] = lcur;
+                p.nacc[q] = nacc;
+                p.nrej[q] = nrej;
+                p.ncall[q] = p.walks;
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < CH * XS; e += blockDim.x) b2n_sm[oX + e] = 0.0;
+        __syncthreads();
+    }
+}
+
 // Host-side grouping of chains by ellipsoid -> per-CTA work descriptors.
 // (shared with the slice kernels)
 int b2n_build_worklist(b2n_ctx* ctx, int64_t Q, const int32_t* ell, int K, int chains_per_cta,
@@ -443,13 +610,30 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         const int XS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16)), YS = RS + 2;
         mma_smem = (size_t)(4 * npad + (((n + 3) >> 2) << 1) + 8 * XS + 8 * YS + 8 * 8 + 8 * 4 * npad) * sizeof(double);
     }
+    // large n: lock-step kernel with matrix fragments streamed from L2 (16 chains share each load)
+    bool use_mmas = false;
+    int sXS = 0, sYS = 0;
+    if (!use_mma && nc == n && n > 64 && !(impl && !strcmp(impl, "warp"))) {
+        const int RS = 8 * ((n + 7) / 8);
+        sXS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16));
+        sYS = RS + 2;
+        const size_t need = (size_t)(4 * npad + (((n + 3) >> 2) << 1) + 16 * sXS + 16 * sYS + (RS / 8) * 16 +
+                                     16 * 4 * npad) * sizeof(double);
+        if (need <= limit) {
+            use_mmas = true;
+            mma_smem = need;
+            const int ctas = ctx->sm_count;
+            chains_per_cta = (int)std::max<int64_t>(1, (Q + ctas - 1) / ctas);
+            warps = 16;
+        }
+    }
     const size_t fixed = per_warp * warps + flags_b;
     const int ldA = (nc + 15) & ~15, ldP = (n + 15) & ~15;
     const size_t ax_b = (size_t)nc * ldA * sizeof(double);
     const size_t pr_b = (m.like_kind == B2N_LIKE_GAUSS_PREC) ? (size_t)n * ldP * sizeof(double) : 0;
     const bool ax_s = fixed + ax_b <= limit;
     const bool pr_s = pr_b > 0 && fixed + (ax_s ? ax_b : 0) + pr_b <= limit;
-    const size_t smem = use_mma ? mma_smem : fixed + (ax_s ? ax_b : 0) + (pr_s ? pr_b : 0);
+    const size_t smem = (use_mma || use_mmas) ? mma_smem : fixed + (ax_s ? ax_b : 0) + (pr_s ? pr_b : 0);
 
     std::vector<int> order;
     std::vector<int3> cta;
@@ -502,13 +686,20 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     if (KT == 8) LAUNCH_MMA(L, 8);       \
     else if (KT == 13) LAUNCH_MMA(L, 13); \
     else LAUNCH_MMA(L, 16);
+#define CALL_MMAS(L)                                                                                  \
+    B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_mmas_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem));                                                  \
+    rwalk_mmas_kernel<L><<<grid, 512, smem, ctx->stream>>>(p, sXS, sYS);
     B2N_TIME_BEGIN(ctx);
     if (use_mma) {
         B2N_DISPATCH_LIKE(m.like_kind, CALL_MMA)
+    } else if (use_mmas) {
+        B2N_DISPATCH_LIKE(m.like_kind, CALL_MMAS)
     } else {
         B2N_DISPATCH_LIKE(m.like_kind, CALL)
     }
     B2N_TIME_END(ctx);
+#undef CALL_MMAS
 #undef CALL_MMA
 #undef LAUNCH_MMA
 #undef CALL

@@ -212,13 +212,13 @@ def test_rwalk_mma_kernel_golden(golden, name):
     np.testing.assert_allclose(o['logl'], g[p + 'logl'], rtol=1e-9, atol=1e-9)
 
 
-@pytest.mark.parametrize('like', ['g50', 'n40diag', 'egg32', 'shell20'])
+@pytest.mark.parametrize('like', ['g50', 'n40diag', 'egg32', 'shell20', 'g100', 'n130diag'])
 def test_rwalk_mma_matches_warp_kernel(like):
     """Both kernels on the same queue (K = 3 ellipsoids, 5000 chains > 16 per CTA): identical
     accept counts, end points equal to round-off, for every likelihood kind."""
     from oracle import likelihoods as OL
     m = {'g50': MODELS['g50'], 'n40diag': OL.iid_normal_ppf(40), 'egg32': OL.eggbox(32),
-         'shell20': OL.shells(20)}[like]
+         'shell20': OL.shells(20), 'g100': OL.gauss_corr(100, 0.4, 5.), 'n130diag': OL.iid_normal_ppf(130)}[like]
     n = m.ndim
     dm = device_model(m)
     rng = np.random.default_rng(n)
@@ -233,8 +233,9 @@ def test_rwalk_mma_matches_warp_kernel(like):
     ell = rng.integers(3, size=Q).astype(np.int32)
     ops.bound_set(axes)
     out = {}
+    # n <= 64: register-fragment DMMA kernel (forced); n > 64: 'auto' picks the streamed-fragment one
     for impl in ('warp', 'mma'):
-        with _Impl(impl):
+        with _Impl(impl if (impl == 'warp' or n <= 64) else 'auto'):
             out[impl] = ops.rwalk_batch(dm.model_id(), u0, loglstar, 0.4, 30, 4242, chain0=9, ell=ell)
     a, b = out['warp'], out['mma']
     same = a['n_accept'] == b['n_accept']
