@@ -9,6 +9,7 @@
 // partition launch and one batch of bounding-ellipsoid launches -- and then evaluate the
 // accept/reject logic bottom-up on the host from the per-node log-volumes.
 #include "b2n_bounding.cuh"
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -36,18 +37,32 @@ __global__ void scale_points_kernel(const double* __restrict__ P, int64_t total,
 // std-scaled space; 10 x { assign to the nearest centre (ties -> cluster 0), centroid =
 // member mean, an empty cluster keeps its centre }; the labels returned are those of the
 // last assignment (before the last centroid update).
-__global__ void __launch_bounds__(1024) kmeans2_kernel(const double* __restrict__ P, const int* __restrict__ perm,
-                                                      NodeArrays na, const NodeRef* __restrict__ refs,
-                                                      const double* __restrict__ scale,
-                                                      unsigned char* __restrict__ labels, int* __restrict__ counts) {
+//
+// Blackwell mapping: each node is handled by a THREAD-BLOCK CLUSTER of 8 CTAs (8 SMs): CTA r
+// walks the r-th eighth of the node's points, reduces its per-warp partial sums in its own
+// shared memory, and after a cluster barrier every CTA reads the 8 partials through
+// distributed shared memory (fixed rank order -> every CTA derives bit-identical centroids,
+// run-to-run reproducible, no atomics).  Two cluster barriers per Lloyd iteration.
+#define KM_CLUSTER 8
+__global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
+    kmeans2_kernel(const double* __restrict__ P, const int* __restrict__ perm, NodeArrays na,
+                   const NodeRef* __restrict__ refs, const double* __restrict__ scale,
+                   unsigned char* __restrict__ labels, int* __restrict__ counts) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ double sm[];
     const int n = na.n;
-    const NodeRef nr = refs[blockIdx.x];
+    const int nodei = blockIdx.x / KM_CLUSTER, rank = (int)cluster.block_rank();
+    const NodeRef nr = refs[nodei];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     double* c = sm;                        // 2 x n centres (scaled space)
-    double* acc = c + 2 * n;               // nw x 2 x n
+    double* part = c + 2 * n;              // 2 x n partial sums of this CTA (read by the peers)
+    double* acc = part + 2 * n;            // nw x 2 x n
     int* cnt = reinterpret_cast<int*>(acc + (size_t)nw * 2 * n);   // nw x 2
+    __shared__ int pcnt[2];                // this CTA's member counts (read by the peers)
     __shared__ int tot[2];
+    const int lo = nr.start + (int)((long long)nr.count * rank / KM_CLUSTER);
+    const int hi = nr.start + (int)((long long)nr.count * (rank + 1) / KM_CLUSTER);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const double ctr = na.mean[(size_t)nr.node * n + i];
         const double v = na.axes[(size_t)nr.node * n * n + (size_t)i * n + (n - 1)];   // largest eigenvalue = last column
@@ -59,11 +74,10 @@ __global__ void __launch_bounds__(1024) kmeans2_kernel(const double* __restrict_
         for (int i = lane; i < 2 * n; i += 32) acc[(size_t)warp * 2 * n + i] = 0.0;
         if (lane < 2) cnt[warp * 2 + lane] = 0;
         __syncwarp();
-        // two points per trip: their row loads and shuffle reductions overlap (the loop is
-        // latency-bound: one CTA walks the whole node out of L2)
-        for (int r = nr.start + warp; r < nr.start + nr.count; r += 2 * nw) {
+        // two points per trip: their row loads and shuffle reductions overlap
+        for (int r = lo + warp; r < hi; r += 2 * nw) {
             const int r2 = r + nw;
-            const bool two = r2 < nr.start + nr.count;
+            const bool two = r2 < hi;
             const size_t row = (size_t)perm[r] * n;
             const size_t row2 = two ? (size_t)perm[r2] * n : row;
             double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
@@ -86,16 +100,29 @@ __global__ void __launch_bounds__(1024) kmeans2_kernel(const double* __restrict_
             double* dst = acc + (size_t)warp * 2 * n + (size_t)lab * n;
             for (int i = lane; i < n; i += 32) dst[i] += P[row + i];
             if (lane == 0) { cnt[warp * 2 + lab]++; labels[r] = (unsigned char)lab; }
-            if (two) {            // same order as the one-point-per-trip loop: r, then r + nw
+            if (two) {
                 double* dst2 = acc + (size_t)warp * 2 * n + (size_t)lab2 * n;
                 for (int i = lane; i < n; i += 32) dst2[i] += P[row2 + i];
                 if (lane == 0) { cnt[warp * 2 + lab2]++; labels[r2] = (unsigned char)lab2; }
             }
         }
         __syncthreads();
+        // CTA partials (fixed warp order)
+        for (int e = threadIdx.x; e < 2 * n; e += blockDim.x) {
+            double s = 0.0;
+            for (int w = 0; w < nw; w++) s += acc[(size_t)w * 2 * n + e];
+            part[e] = s;
+        }
         if (threadIdx.x < 2) {
             int t = 0;
             for (int w = 0; w < nw; w++) t += cnt[w * 2 + threadIdx.x];
+            pcnt[threadIdx.x] = t;
+        }
+        cluster.sync();
+        // cluster totals through distributed shared memory (fixed rank order)
+        if (threadIdx.x < 2) {
+            int t = 0;
+            for (int rk = 0; rk < KM_CLUSTER; rk++) t += *cluster.map_shared_rank(&pcnt[threadIdx.x], rk);
             tot[threadIdx.x] = t;
         }
         __syncthreads();
@@ -103,13 +130,13 @@ __global__ void __launch_bounds__(1024) kmeans2_kernel(const double* __restrict_
             const int cl = e / n;
             if (tot[cl] > 0) {
                 double s = 0.0;
-                for (int w = 0; w < nw; w++) s += acc[(size_t)w * 2 * n + e];
+                for (int rk = 0; rk < KM_CLUSTER; rk++) s += cluster.map_shared_rank(part, rk)[e];
                 c[e] = s / (double)tot[cl];
             }
         }
-        __syncthreads();
+        cluster.sync();      // peers have read this CTA's partials before they are overwritten
     }
-    if (threadIdx.x < 2) counts[blockIdx.x * 2 + threadIdx.x] = tot[threadIdx.x];
+    if (rank == 0 && threadIdx.x < 2) counts[nodei * 2 + threadIdx.x] = tot[threadIdx.x];
 }
 
 // ---- stable partition of a node's segment by label: [label 0 ..., label 1 ...]
@@ -238,10 +265,10 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
     std::vector<int> frontier(1, 0);
     int cur = 0;
     const int min_size = 2 * n;
-    int nwarps = 32;
-    while ((size_t)(2 * n + (size_t)nwarps * 2 * n) * sizeof(double) + nwarps * 2 * sizeof(int) > (size_t)ctx->max_smem_optin && nwarps > 1)
+    int nwarps = 16;
+    while ((size_t)(4 * n + (size_t)nwarps * 2 * n) * sizeof(double) + nwarps * 2 * sizeof(int) > (size_t)ctx->max_smem_optin && nwarps > 1)
         nwarps >>= 1;
-    const size_t km_smem = (size_t)(2 * n + (size_t)nwarps * 2 * n) * sizeof(double) + nwarps * 2 * sizeof(int);
+    const size_t km_smem = (size_t)(4 * n + (size_t)nwarps * 2 * n) * sizeof(double) + nwarps * 2 * sizeof(int);
     if (km_smem > (size_t)ctx->max_smem_optin) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for k-means kernel");
     B2N_CUDA(ctx, cudaFuncSetAttribute(kmeans2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km_smem));
 
@@ -260,7 +287,7 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
         B2N_TRY(b2n_in_host(ctx, ctx->scratch5, srefs.data(), srefs.size() * sizeof(NodeRef), &drefs));
         const int* pin = w.perm + (size_t)cur * w.N;
         int* pout = w.perm + (size_t)(1 - cur) * w.N;
-        kmeans2_kernel<<<(unsigned)split.size(), nwarps * 32, km_smem, st>>>(Pscaled, pin, w.na, (const NodeRef*)drefs, scale,
+        kmeans2_kernel<<<(unsigned)split.size() * KM_CLUSTER, nwarps * 32, km_smem, st>>>(Pscaled, pin, w.na, (const NodeRef*)drefs, scale,
                                                                            dlab, dcounts);
         B2N_LAUNCH_CHECK(ctx);
         // carry every segment forward, then overwrite the split ones with their partition
