@@ -236,8 +236,18 @@ def run_b200(args, cfg):
                  n_accept=torch.empty(Q, dtype=torch.int32, device=dev),
                  n_reject=torch.empty(Q, dtype=torch.int32, device=dev),
                  ncall=torch.empty(Q, dtype=torch.int32, device=dev))
+    fused = world > 1 and args.exchange == 'fused'
     if world > 1:
         g_pack = torch.empty(world * (Q * n + Q), dtype=torch.float64, device=dev)
+    if fused:
+        # the exchange step fused into the kernel: finished chains are stored into every rank's
+        # window over NVLink and the kernel ends with a cross-GPU arrive/wait (csrc/b2n_peer.cu)
+        from dynesty_b200.dist import Comm
+        Comm(dev).attach_peer(ctx, world * Q, n)
+        hg_out = dict(u=pin(world * Q, n), v=pin(world * Q, n), logl=pin(world * Q),
+                      n_accept=pin(world * Q, dt=torch.int32), n_reject=pin(world * Q, dt=torch.int32),
+                      ncall=pin(world * Q, dt=torch.int32))
+        hg_np = {k: t.numpy() for k, t in hg_out.items()}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     # one explicit (non-default) stream shared by torch and the library, so that torch's CUDA
     # events bracket the library's launches (a NULL handle would mean "library-owned stream")
@@ -261,6 +271,10 @@ def run_b200(args, cfg):
         ctx.set_pointer_mode(_lib.PTR_HOST)
         c0 = state['chain']
         state['chain'] += Q * world
+        if fused:         # every rank's host receives the whole queue (replicated sampler state)
+            o = ops.rwalk_batch(mid, h_u0.numpy(), loglstar, state['scale'], walks, SEED, chain0=c0 + rank * Q,
+                                ell=ell, ctx=ctx, out=hg_np, peer=(rank * Q, world * Q))
+            return {k: v[rank * Q:(rank + 1) * Q] for k, v in o.items()}
         o = ops.rwalk_batch(mid, h_u0.numpy(), loglstar, state['scale'], walks, SEED, chain0=c0 + rank * Q,
                             ell=ell, ctx=ctx, out=h_np)
         return o
@@ -272,9 +286,13 @@ def run_b200(args, cfg):
         ctx.set_pointer_mode(_lib.PTR_DEVICE)
         c0 = state['chain']
         state['chain'] += Q * world
+        if fused:           # the exchange step of the sharded path, inside the kernel
+            ops.rwalk_batch(mid, d_u0, loglstar, state['scale'], walks, SEED, chain0=c0 + rank * Q, ell=ell,
+                            ctx=ctx, out=ops.NO_OUT, peer=(rank * Q, world * Q))
+            return
         ops.rwalk_batch(mid, d_u0, loglstar, state['scale'], walks, SEED, chain0=c0 + rank * Q, ell=ell,
                         ctx=ctx, out=d_out)
-        if world > 1:       # the exchange step of the sharded path: every rank gets the whole queue
+        if world > 1:       # --exchange nccl: one packed all-gather of (u | logl) after the kernel
             dist.all_gather_into_tensor(g_pack, d_pack)
 
     # ---- warm-up: also tunes the proposal scale with the reference's rule (internal_samplers.py:491)
@@ -286,9 +304,15 @@ def run_b200(args, cfg):
     for _ in range(3):
         o = step_host()
     accept_frac = float(o['n_accept'].sum() / (o['n_accept'].sum() + o['n_reject'].sum()))
-    t_ramp = time.perf_counter() + 0.7   # clock ramp: 0.7 s of the same kernel before timing, so that
-    while time.perf_counter() < t_ramp:  # the nvidia-smi sampler has samples under load
-        step_dev()
+    # clock ramp: ~0.7 s of the same kernel before timing, so that the nvidia-smi sampler has
+    # samples under load.  N>1: a FIXED step count (every rank must issue the same exchanges).
+    if world > 1:
+        for _ in range(2500):
+            step_dev()
+    else:
+        t_ramp = time.perf_counter() + 0.7
+        while time.perf_counter() < t_ramp:
+            step_dev()
     torch.cuda.synchronize()
 
     def barrier():
@@ -320,6 +344,8 @@ def run_b200(args, cfg):
     barrier()
     launches = ctx.launch_count() - launches0
     clk = clocks.stop()
+    if fused:
+        ctx.peer_check()                     # raises if any in-kernel exchange ever timed out
 
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -353,10 +379,13 @@ def run_b200(args, cfg):
             "config": {"workload": cfg['desc'], "queue_chains_per_gpu": Q, "walks": walks, "nells": int(bound.nells),
                        "accept_fraction": round(accept_frac, 3), "scale": round(state['scale'], 4),
                        "l2": "flushed (256 MB memset) between timed iterations",
+                       "exchange": ("fused into the kernel: NVLink peer stores + in-kernel arrive/wait" if fused else
+                                    ("NCCL all-gather after the kernel" if world > 1 else "none (1 GPU)")),
                        "bound_update_ms": round(bound_ms, 3), "bound_update_first_ms": round(bound_ms_first, 2)},
             "e2e": {"value": e2e, "unit": "proposals/s",
                     "h2d_bytes_per_step": Q * n * 8 + Q * 4 + 16 * (Q // 8 + 1),
-                    "d2h_bytes_per_step": 2 * Q * n * 8 + Q * 8 + 3 * Q * 4},
+                    "d2h_bytes_per_step": (world if fused else 1) * (2 * Q * n * 8 + Q * 8 + 3 * Q * 4),
+                    "bytes_are": "per rank"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch",
@@ -416,6 +445,8 @@ def main():
     ap.add_argument('--logz', type=int, default=1, help='also run the full C2 nested-sampling run for logZ')
     ap.add_argument('--logz-queue', type=int, default=200, help='queue_size of the full logZ run')
     ap.add_argument('--cpu-baseline', type=int, default=1)
+    ap.add_argument('--exchange', default='fused', choices=['fused', 'nccl'],
+                    help='N>1: how the finished chains reach every rank')
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     if args.impl == 'reference':

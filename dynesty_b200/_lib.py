@@ -18,7 +18,8 @@ LIKE_GAUSS_PREC, LIKE_GAUSS_DIAG, LIKE_EGGBOX, LIKE_SHELLS = 0, 1, 2, 3
 WARN_IDENTITY_FALLBACK, WARN_DOUBLING, WARN_Q0_SLACK, WARN_UNIF_INEFFICIENT = 1, 2, 4, 8
 
 (OK, ERR_CUDA, ERR_ARG, ERR_SINGLE_POINT, ERR_SINGULAR, ERR_ELL_INIT, ERR_INVALID_REGION,
- ERR_Q0, ERR_SLICE_FAIL, ERR_NOMEM, ERR_UNSUPPORTED, ERR_TOO_MANY_ELLS) = range(12)
+ ERR_Q0, ERR_SLICE_FAIL, ERR_NOMEM, ERR_UNSUPPORTED, ERR_TOO_MANY_ELLS, ERR_PEER) = range(13)
+PEER_HANDLE_BYTES, MAX_PEERS = 64, 8
 
 
 class B200Unavailable(RuntimeError):
@@ -65,6 +66,14 @@ SYMBOLS = {
     'b2n_rslice_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     'b2n_slice_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     'b2n_unif_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _P, _P, _P, _P, _P, _P]),
+    'b2n_peer_export': (C.c_int, [_P, _U64, _P]),
+    'b2n_peer_import': (C.c_int, [_P, _I, _I, _P]),
+    'b2n_peer_import_raw': (C.c_int, [_P, _I, _I, C.POINTER(_P)]),
+    'b2n_peer_rows': (C.c_int, [_P, _L, _L]),
+    'b2n_peer_result': (C.c_int, [_P, C.POINTER(_P), C.POINTER(_U64)]),
+    'b2n_peer_read': (C.c_int, [_P, _U64, _P, _U64]),
+    'b2n_peer_check': (C.c_int, [_P]),
+    'b2n_peer_window_bytes': (_U64, [_L, _I]),
 }
 
 _lib = None
@@ -92,7 +101,7 @@ _EXC = {
     ERR_ARG: ValueError, ERR_SINGLE_POINT: ValueError, ERR_SINGULAR: ValueError,
     ERR_ELL_INIT: RuntimeError, ERR_INVALID_REGION: RuntimeError, ERR_Q0: RuntimeError,
     ERR_SLICE_FAIL: RuntimeError, ERR_NOMEM: MemoryError, ERR_UNSUPPORTED: NotImplementedError,
-    ERR_TOO_MANY_ELLS: RuntimeError,
+    ERR_TOO_MANY_ELLS: RuntimeError, ERR_PEER: RuntimeError,
 }
 
 
@@ -165,6 +174,59 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.b2n_launch_count(self.h))
+
+    # ---- multi-GPU exchange windows (include/b200nest.h, "peer" section) ------------------
+    def peer_window_bytes(self, total_rows, ndim):
+        return int(self.lib.b2n_peer_window_bytes(int(total_rows), int(ndim)))
+
+    def peer_export(self, nbytes):
+        """Allocate this rank's exchange window; returns its 64-byte CUDA IPC handle."""
+        buf = (C.c_ubyte * PEER_HANDLE_BYTES)()
+        self.check(self.lib.b2n_peer_export(self.h, int(nbytes), C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def peer_import(self, rank, world, handles):
+        """Map the windows of all ranks (handles: world x 64 bytes, rank order)."""
+        blob = b''.join(handles) if not isinstance(handles, (bytes, bytearray)) else bytes(handles)
+        assert len(blob) == world * PEER_HANDLE_BYTES
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self.check(self.lib.b2n_peer_import(self.h, int(rank), int(world), C.cast(buf, C.c_void_p)))
+
+    def peer_import_raw(self, rank, world, windows):
+        """Same for ranks that live in this process: device addresses of their windows."""
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(w)) for w in windows])
+        self.check(self.lib.b2n_peer_import_raw(self.h, int(rank), int(world), arr))
+
+    def peer_rows(self, row0, total_rows):
+        self.check(self.lib.b2n_peer_rows(self.h, int(row0), int(total_rows)))
+
+    def peer_result(self):
+        """(window device address, byte offsets of u, v, logl, int0..int3) of the last gather-mode call."""
+        w = C.c_void_p()
+        off = (C.c_uint64 * 7)()
+        self.check(self.lib.b2n_peer_result(self.h, C.byref(w), off))
+        return int(w.value), [int(x) for x in off]
+
+    def peer_read(self, offset, shape, dtype):
+        """Synchronise and fetch an array that starts at byte `offset` of the own window."""
+        a = np.empty(shape, dtype=dtype)
+        self.check(self.lib.b2n_peer_read(self.h, int(offset), a.ctypes.data, a.nbytes))
+        return a
+
+    def peer_gathered(self, total_rows, ndim, names):
+        """The complete outputs of the last gather-mode call, read from the own window:
+        u, v, logl and the call's int32 outputs under `names` (argument order, None = skip)."""
+        _, off = self.peer_result()
+        o = dict(u=self.peer_read(off[0], (total_rows, ndim), np.float64),
+                 v=self.peer_read(off[1], (total_rows, ndim), np.float64),
+                 logl=self.peer_read(off[2], (total_rows,), np.float64))
+        for k, nm in enumerate(names):
+            if nm is not None:
+                o[nm] = self.peer_read(off[3 + k], (total_rows,), np.uint32 if nm == 'flags' else np.int32)
+        return o
+
+    def peer_check(self):
+        self.check(self.lib.b2n_peer_check(self.h))
 
 
 _default_ctx = {}

@@ -39,6 +39,28 @@ struct DevBuf {
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// ---- peer exchange (multi-GPU gather fused into the chain kernels, b2n_peer.cu) ----------
+// Window layout: 256-byte header { u64 arrive @0 | u32 err @8 | u32 done @64 } then two slots
+// (call parity) of { u (R x n f64) | v (R x n f64) | logl (R f64) | 4 x (R i32) }, R = total rows,
+// every array 256-byte aligned.  The same (R, n) gives the same layout on every rank.
+#define B2N_PEER_HDR 256
+struct PeerSet {               // passed by value to the chain kernels; world == 0: exchange off
+    int world = 0, rank = 0;
+    char* base[B2N_MAX_PEERS] = {nullptr};
+    unsigned long long target = 0;     // own arrive counter once every rank has arrived
+};
+struct PeerState {
+    int world = 0, rank = 0;
+    char* win = nullptr;               // own window
+    size_t win_bytes = 0;
+    char* base[B2N_MAX_PEERS] = {nullptr};
+    bool opened[B2N_MAX_PEERS] = {false};      // mapped through cudaIpcOpenMemHandle
+    int64_t row0 = 0, total = 0;       // gather mode when total > 0
+    uint64_t epoch = 0;                // gather-mode calls so far (same on all ranks)
+    uint64_t off[7] = {0};             // byte offsets of the arrays of the last call
+    unsigned int* err_host = nullptr;  // pinned mailbox for the window's err word
+};
+
 struct b2n_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -63,7 +85,17 @@ struct b2n_ctx {
     DevBuf work0, work1;
     void* pinned = nullptr;     // small pinned host mailbox
     size_t pinned_cap = 0;
+    PeerState peer;
 };
+
+// gather-mode plumbing shared by the chain entry points (b2n_peer.cu).  b2n_peer_begin: when
+// gather mode is on, point the 7 output arrays at this rank's rows of its own window and fill
+// `ps`; returns through *on whether it did.  b2n_peer_end: copy the gathered arrays (total rows)
+// to the caller's pointers and fetch the error word; b2n_peer_finish replaces b2n_finish.
+int b2n_peer_begin(b2n_ctx* ctx, int n, PeerSet* ps, void** dev7, bool* on);
+int b2n_peer_end(b2n_ctx* ctx, int n, void* const* user7);
+int b2n_peer_finish(b2n_ctx* ctx, bool on);
+void b2n_peer_release(b2n_ctx* ctx);
 
 #define B2N_CUDA(ctx, call)                                                        \
     do {                                                                           \

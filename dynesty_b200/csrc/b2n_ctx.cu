@@ -20,6 +20,7 @@ const char* b2n_strerror(int s) {
         case B2N_ERR_NOMEM: return "out of memory";
         case B2N_ERR_UNSUPPORTED: return "unsupported configuration";
         case B2N_ERR_TOO_MANY_ELLS: return "max_ells too small";
+        case B2N_ERR_PEER: return "peer exchange failed";
         default: return "unknown status";
     }
 }
@@ -64,6 +65,7 @@ void b2n_free(b2n_ctx* ctx) {
                       &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->scratch4,
                       &ctx->scratch5, &ctx->work0, &ctx->work1};
     for (DevBuf* b : bufs) b->release();
+    b2n_peer_release(ctx);
     for (void* p : ctx->model_allocs) cudaFree(p);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -145,3 +145,53 @@ __device__ __forceinline__ double warp_loglike(const B2nModel& m, const double* 
         case B2N_LIKE_EGGBOX: { CALL(B2N_LIKE_EGGBOX); } break;         \
         default: { CALL(B2N_LIKE_SHELLS); } break;                      \
     }
+
+// ---- fused exchange of finished chains (b2n_peer.cu) ---------------------------------------
+// peer_put: store an output element into the own array AND at the same window offset of every
+// peer (NVLink peer stores).  With the exchange off (world <= 1) it is a plain store.
+template <class T>
+__device__ __forceinline__ void peer_put(const PeerSet& ps, T* local, T val) {
+    *local = val;
+    if (ps.world > 1) {
+        const ptrdiff_t off = reinterpret_cast<char*>(local) - ps.base[ps.rank];
+        for (int w = 0; w < ps.world; w++)
+            if (w != ps.rank) *reinterpret_cast<T*>(ps.base[w] + off) = val;
+    }
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// peer_finish: called by EVERY thread at the end of a chain kernel.  The last CTA of the grid
+// (threadFenceReduction pattern on the window's `done` word) bumps the arrive counter of every
+// rank with system-scope atomics and then waits until all `world` ranks have bumped its own:
+// when the kernel completes, every rank's rows are in this rank's window.  The wait is bounded
+// (~10 s of SM clocks): a missing peer sets the window's err word instead of hanging the GPU.
+__device__ __forceinline__ void peer_finish(const PeerSet& ps) {
+    if (ps.world == 0) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        char* own = ps.base[ps.rank];
+        unsigned int* done = reinterpret_cast<unsigned int*>(own + 64);
+        __threadfence_system();
+        const unsigned int prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x * gridDim.y - 1) {
+            atomicExch(done, 0u);
+            __threadfence_system();
+            for (int w = 0; w < ps.world; w++)
+                atomicAdd_system(reinterpret_cast<unsigned long long*>(ps.base[w]), 1ULL);
+            const long long t0 = clock64();
+            while (ld_acquire_sys_u64(reinterpret_cast<unsigned long long*>(own)) < ps.target) {
+                if (clock64() - t0 > 20000000000LL) {
+                    *reinterpret_cast<volatile unsigned int*>(own + 8) = 1u;
+                    break;
+                }
+                __nanosleep(200);
+            }
+        }
+    }
+}

@@ -38,6 +38,7 @@ struct RwalkParams {
     uint64_t seed, chain0;
     double *u, *v, *logl;
     int *nacc, *nrej, *ncall;
+    PeerSet peer;          // fused multi-GPU gather of the outputs (b2n_peer.cu); world == 0: off
 };
 
 template <int LIKE, bool AX_SMEM, bool PREC_SMEM>
@@ -163,17 +164,18 @@ __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
         }
         __syncwarp();
         for (int i = lane; i < n; i += 32) {
-            p.u[(size_t)q * n + i] = b2n_sm[oucur + i];
-            p.v[(size_t)q * n + i] = b2n_sm[ovcur + i];
+            peer_put(p.peer, &p.u[(size_t)q * n + i], b2n_sm[oucur + i]);
+            peer_put(p.peer, &p.v[(size_t)q * n + i], b2n_sm[ovcur + i]);
         }
         if (lane == 0) {
-            p.logl[q] = lcur;
-            p.nacc[q] = nacc;
-            p.nrej[q] = nrej;
-            p.ncall[q] = p.walks;
+            peer_put(p.peer, &p.logl[q], lcur);
+            peer_put(p.peer, &p.nacc[q], nacc);
+            peer_put(p.peer, &p.nrej[q], nrej);
+            peer_put(p.peer, &p.ncall[q], (int)p.walks);
         }
         __syncwarp();
     }
+    peer_finish(p.peer);
 }
 
 // =====================================================================================
@@ -343,14 +345,14 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
             }
             __syncwarp();
             for (int i = lane; i < n; i += 32) {
-                p.u[(size_t)q * n + i] = b2n_sm[oucur + i];
-                p.v[(size_t)q * n + i] = b2n_sm[ovcur + i];
+                peer_put(p.peer, &p.u[(size_t)q * n + i], b2n_sm[oucur + i]);
+                peer_put(p.peer, &p.v[(size_t)q * n + i], b2n_sm[ovcur + i]);
             }
             if (lane == 0) {
-                p.logl[q] = lcur;
-                p.nacc[q] = nacc;
-                p.nrej[q] = nrej;
-                p.ncall[q] = p.walks;
+                peer_put(p.peer, &p.logl[q], lcur);
+                peer_put(p.peer, &p.nacc[q], nacc);
+                peer_put(p.peer, &p.nrej[q], nrej);
+                peer_put(p.peer, &p.ncall[q], (int)p.walks);
             }
         }
         __syncthreads();
@@ -358,6 +360,7 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
         for (int e = threadIdx.x; e < B2N_MMA_CH * XS; e += blockDim.x) b2n_sm[oX + e] = 0.0;
         __syncthreads();
     }
+    peer_finish(p.peer);
 }
 
 // =====================================================================================
@@ -511,20 +514,21 @@ __global__ void __launch_bounds__(512, 1) rwalk_mmas_kernel(const RwalkParams p,
             }
             __syncwarp();
             for (int i = lane; i < n; i += 32) {
-                p.u[(size_t)q * n + i] = b2n_sm[oucur + i];
-                p.v[(size_t)q * n + i] = b2n_sm[ovcur + i];
+                peer_put(p.peer, &p.u[(size_t)q * n + i], b2n_sm[oucur + i]);
+                peer_put(p.peer, &p.v[(size_t)q * n + i], b2n_sm[ovcur + i]);
             }
             if (lane == 0) {
-                p.logl[q] = lcur;
-                p.nacc[q] = nacc;
-                p.nrej[q] = nrej;
-                p.ncall[q] = p.walks;
+                peer_put(p.peer, &p.logl[q], lcur);
+                peer_put(p.peer, &p.nacc[q], nacc);
+                peer_put(p.peer, &p.nrej[q], nrej);
+                peer_put(p.peer, &p.ncall[q], (int)p.walks);
             }
         }
         __syncthreads();
         for (int e = threadIdx.x; e < CH * XS; e += blockDim.x) b2n_sm[oX + e] = 0.0;
         __syncthreads();
     }
+    peer_finish(p.peer);
 }
 
 // Host-side grouping of chains by ellipsoid -> per-CTA work descriptors.
@@ -570,14 +574,16 @@ void b2n_chain_grid(const b2n_ctx* ctx, int64_t Q, int max_warps, int& chains_pe
 extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t walks, double* u,
                                double* v, double* logl, int32_t* n_accept, int32_t* n_reject,
                                int32_t* ncall) {
-    if (!ctx || !a || !u || !v || !logl || !n_accept || !n_reject || !ncall) return B2N_ERR_ARG;
+    if (!ctx || !a) return B2N_ERR_ARG;
+    const bool gather = ctx->peer.total > 0;      // outputs may be NULL in gather mode (b2n_peer_result)
+    if (!gather && (!u || !v || !logl || !n_accept || !n_reject || !ncall)) return B2N_ERR_ARG;
     if (a->model_id < 0 || a->model_id >= (int)ctx->models.size()) return B2N_ERR_ARG;
     const B2nModel m = ctx->models[a->model_id];
     const int n = a->ndim, nc = a->ncdim;
     const int64_t Q = a->nchain;
     if (n != m.ndim || nc < 1 || nc > n || walks < 1 || Q < 0 || !a->u0) return B2N_ERR_ARG;
     if (ctx->bK < 1 || ctx->bn != nc) return b2n_fail(ctx, B2N_ERR_ARG, "resident bound missing or of wrong dimension (b2n_bound_set)");
-    if (Q == 0) return B2N_OK;
+    if (Q == 0) return gather ? b2n_fail(ctx, B2N_ERR_ARG, "gather mode: every rank must run at least one chain") : B2N_OK;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
 
     // shared-memory plan: per-warp state always; matrices (128-byte padded columns) when they fit
@@ -653,12 +659,20 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         B2N_TRY(b2n_in_host(ctx, ctx->in3, fl.data(), fl.size() * sizeof(uint32_t), &dfl));
     }
     void *du, *dv, *dl, *dna, *dnr, *dncl;
-    B2N_TRY(b2n_out(ctx, ctx->out0, u, (size_t)Q * n * sizeof(double), &du));
-    B2N_TRY(b2n_out(ctx, ctx->out1, v, (size_t)Q * n * sizeof(double), &dv));
-    B2N_TRY(b2n_out(ctx, ctx->out2, logl, (size_t)Q * sizeof(double), &dl));
-    B2N_TRY(b2n_out(ctx, ctx->out3, n_accept, (size_t)Q * sizeof(int), &dna));
-    B2N_TRY(b2n_out(ctx, ctx->out4, n_reject, (size_t)Q * sizeof(int), &dnr));
-    B2N_TRY(b2n_out(ctx, ctx->out5, ncall, (size_t)Q * sizeof(int), &dncl));
+    void* gdev[7];
+    bool peer_on = false;
+    B2N_TRY(b2n_peer_begin(ctx, n, &p.peer, gdev, &peer_on));
+    if (peer_on) {
+        if (ctx->peer.row0 + Q > ctx->peer.total) return b2n_fail(ctx, B2N_ERR_ARG, "gather rows out of range (b2n_peer_rows)");
+        du = gdev[0]; dv = gdev[1]; dl = gdev[2]; dna = gdev[3]; dnr = gdev[4]; dncl = gdev[5];
+    } else {
+        B2N_TRY(b2n_out(ctx, ctx->out0, u, (size_t)Q * n * sizeof(double), &du));
+        B2N_TRY(b2n_out(ctx, ctx->out1, v, (size_t)Q * n * sizeof(double), &dv));
+        B2N_TRY(b2n_out(ctx, ctx->out2, logl, (size_t)Q * sizeof(double), &dl));
+        B2N_TRY(b2n_out(ctx, ctx->out3, n_accept, (size_t)Q * sizeof(int), &dna));
+        B2N_TRY(b2n_out(ctx, ctx->out4, n_reject, (size_t)Q * sizeof(int), &dnr));
+        B2N_TRY(b2n_out(ctx, ctx->out5, ncall, (size_t)Q * sizeof(int), &dncl));
+    }
     p.u0 = (const double*)du0; p.order = (const int*)dorder; p.cta = (const int3*)dcta;
     p.dimflags = (const uint32_t*)dfl;
     p.u = (double*)du; p.v = (double*)dv; p.logl = (double*)dl;
@@ -705,6 +719,11 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
 #undef CALL
 #undef LAUNCH
     B2N_LAUNCH_CHECK(ctx);
+    if (peer_on) {
+        void* const user7[7] = {u, v, logl, n_accept, n_reject, ncall, nullptr};
+        B2N_TRY(b2n_peer_end(ctx, n, user7));
+        return b2n_peer_finish(ctx, true);
+    }
     B2N_TRY(b2n_out_done(ctx, u, du, (size_t)Q * n * sizeof(double)));
     B2N_TRY(b2n_out_done(ctx, v, dv, (size_t)Q * n * sizeof(double)));
     B2N_TRY(b2n_out_done(ctx, logl, dl, (size_t)Q * sizeof(double)));

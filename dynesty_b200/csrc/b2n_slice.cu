@@ -32,6 +32,7 @@ struct SliceParams {
     double *u, *v, *logl;
     int *nexp, *ncon, *ncall;
     uint32_t* flags;
+    PeerSet peer;          // fused multi-GPU gather of the outputs (b2n_peer.cu)
 };
 
 // F(x) of generic_slice_step (:1112-1123): logl(u + x d) or -inf outside the unit cube.
@@ -226,18 +227,19 @@ __global__ void __launch_bounds__(512, 1) slice_kernel(const SliceParams p) {
         // v_prop = prior_transform(u_prop) (:1204)
         for (int i = lane; i < n; i += 32) {
             const double ui = b2n_sm[ou + i];
-            p.u[(size_t)q * n + i] = ui;
-            p.v[(size_t)q * n + i] = prior_sm(pk, ms.op0, ms.op1, i, ui);
+            peer_put(p.peer, &p.u[(size_t)q * n + i], ui);
+            peer_put(p.peer, &p.v[(size_t)q * n + i], prior_sm(pk, ms.op0, ms.op1, i, ui));
         }
         if (lane == 0) {
-            p.logl[q] = lcur;
-            p.nexp[q] = nexp;
-            p.ncon[q] = ncon;
-            p.ncall[q] = F.nc;
-            p.flags[q] = (warned ? B2N_WARN_DOUBLING : 0u) | (err ? 0x80000000u : 0u);
+            peer_put(p.peer, &p.logl[q], lcur);
+            peer_put(p.peer, &p.nexp[q], nexp);
+            peer_put(p.peer, &p.ncon[q], ncon);
+            peer_put(p.peer, &p.ncall[q], (int)F.nc);
+            peer_put(p.peer, &p.flags[q], (warned ? B2N_WARN_DOUBLING : 0u) | (err ? 0x80000000u : 0u));
         }
         __syncwarp();
     }
+    peer_finish(p.peer);
 }
 
 __global__ void any_error_kernel(const uint32_t* flags, int64_t Q, int* out) {
@@ -251,7 +253,9 @@ template <bool RANDOM_DIR>
 static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slices, int32_t doubling, double* u,
                             double* v, double* logl, int32_t* n_expand, int32_t* n_contract, int32_t* ncall,
                             uint32_t* flags) {
-    if (!ctx || !a || !u || !v || !logl || !n_expand || !n_contract || !ncall || !flags) return B2N_ERR_ARG;
+    if (!ctx || !a) return B2N_ERR_ARG;
+    const bool gather = ctx->peer.total > 0;      // outputs may be NULL in gather mode (b2n_peer_result)
+    if (!gather && (!u || !v || !logl || !n_expand || !n_contract || !ncall || !flags)) return B2N_ERR_ARG;
     if (a->model_id < 0 || a->model_id >= (int)ctx->models.size()) return B2N_ERR_ARG;
     const B2nModel m = ctx->models[a->model_id];
     const int n = a->ndim;
@@ -259,7 +263,7 @@ static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slice
     if (n != m.ndim || a->ncdim != n || slices < 1 || Q < 0 || !a->u0)
         return b2n_fail(ctx, B2N_ERR_ARG, "slice samplers need ncdim == ndim (internal_samplers.py:658, 809)");
     if (ctx->bK < 1 || ctx->bn != n) return b2n_fail(ctx, B2N_ERR_ARG, "resident bound missing or of wrong dimension");
-    if (Q == 0) return B2N_OK;
+    if (Q == 0) return gather ? b2n_fail(ctx, B2N_ERR_ARG, "gather mode: every rank must run at least one chain") : B2N_OK;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
     const int npad = (n + 1) & ~1;
     const size_t per_warp = (size_t)6 * npad * sizeof(double);           // u, d, un, vn, work, idxs
@@ -288,13 +292,21 @@ static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slice
     B2N_TRY(b2n_in_host(ctx, ctx->work0, order.data(), order.size() * sizeof(int), &dorder));
     B2N_TRY(b2n_in_host(ctx, ctx->work1, cta.data(), cta.size() * sizeof(int3), &dcta));
     void *du, *dv, *dl, *dne, *dnc, *dncl, *dfl;
-    B2N_TRY(b2n_out(ctx, ctx->out0, u, (size_t)Q * n * sizeof(double), &du));
-    B2N_TRY(b2n_out(ctx, ctx->out1, v, (size_t)Q * n * sizeof(double), &dv));
-    B2N_TRY(b2n_out(ctx, ctx->out2, logl, (size_t)Q * sizeof(double), &dl));
-    B2N_TRY(b2n_out(ctx, ctx->out3, n_expand, (size_t)Q * sizeof(int), &dne));
-    B2N_TRY(b2n_out(ctx, ctx->out4, n_contract, (size_t)Q * sizeof(int), &dnc));
-    B2N_TRY(b2n_out(ctx, ctx->out5, ncall, (size_t)Q * sizeof(int), &dncl));
-    B2N_TRY(b2n_out(ctx, ctx->out6, flags, (size_t)Q * sizeof(uint32_t), &dfl));
+    void* gdev[7];
+    bool peer_on = false;
+    B2N_TRY(b2n_peer_begin(ctx, n, &p.peer, gdev, &peer_on));
+    if (peer_on) {
+        if (ctx->peer.row0 + Q > ctx->peer.total) return b2n_fail(ctx, B2N_ERR_ARG, "gather rows out of range (b2n_peer_rows)");
+        du = gdev[0]; dv = gdev[1]; dl = gdev[2]; dne = gdev[3]; dnc = gdev[4]; dncl = gdev[5]; dfl = gdev[6];
+    } else {
+        B2N_TRY(b2n_out(ctx, ctx->out0, u, (size_t)Q * n * sizeof(double), &du));
+        B2N_TRY(b2n_out(ctx, ctx->out1, v, (size_t)Q * n * sizeof(double), &dv));
+        B2N_TRY(b2n_out(ctx, ctx->out2, logl, (size_t)Q * sizeof(double), &dl));
+        B2N_TRY(b2n_out(ctx, ctx->out3, n_expand, (size_t)Q * sizeof(int), &dne));
+        B2N_TRY(b2n_out(ctx, ctx->out4, n_contract, (size_t)Q * sizeof(int), &dnc));
+        B2N_TRY(b2n_out(ctx, ctx->out5, ncall, (size_t)Q * sizeof(int), &dncl));
+        B2N_TRY(b2n_out(ctx, ctx->out6, flags, (size_t)Q * sizeof(uint32_t), &dfl));
+    }
     p.u0 = (const double*)du0; p.order = (const int*)dorder; p.cta = (const int3*)dcta;
     p.u = (double*)du; p.v = (double*)dv; p.logl = (double*)dl;
     p.nexp = (int*)dne; p.ncon = (int*)dnc; p.ncall = (int*)dncl; p.flags = (uint32_t*)dfl;
@@ -321,9 +333,20 @@ static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slice
     *derr = 0;
     B2N_CUDA(ctx, ctx->out7.ensure(64));
     B2N_CUDA(ctx, cudaMemsetAsync(ctx->out7.p, 0, sizeof(int), ctx->stream));
-    any_error_kernel<<<64, 256, 0, ctx->stream>>>((const uint32_t*)dfl, Q, ctx->out7.as<int>());
+    // (gather mode: over the rows of ALL ranks, so that every rank raises the same error)
+    const uint32_t* eflags = peer_on ? (const uint32_t*)(ctx->peer.win + ctx->peer.off[6]) : (const uint32_t*)dfl;
+    any_error_kernel<<<64, 256, 0, ctx->stream>>>(eflags, peer_on ? ctx->peer.total : Q, ctx->out7.as<int>());
     B2N_LAUNCH_CHECK(ctx);
     B2N_CUDA(ctx, cudaMemcpyAsync(derr, ctx->out7.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (peer_on) {
+        void* const user7[7] = {u, v, logl, n_expand, n_contract, ncall, flags};
+        B2N_TRY(b2n_peer_end(ctx, n, user7));
+        B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->ptr_mode == B2N_PTR_HOST && *ctx->peer.err_host)
+            return b2n_fail(ctx, B2N_ERR_PEER, "a peer never arrived at the exchange (timeout in the kernel)");
+        if (*derr) return B2N_ERR_SLICE_FAIL;
+        return B2N_OK;
+    }
     B2N_TRY(b2n_out_done(ctx, u, du, (size_t)Q * n * sizeof(double)));
     B2N_TRY(b2n_out_done(ctx, v, dv, (size_t)Q * n * sizeof(double)));
     B2N_TRY(b2n_out_done(ctx, logl, dl, (size_t)Q * sizeof(double)));

@@ -27,6 +27,7 @@ struct UnifParams {
     double *u, *v, *logl;
     int *ncall, *nprop;
     uint32_t* flags;
+    PeerSet peer;          // fused multi-GPU gather of the outputs (b2n_peer.cu)
 };
 
 template <int LIKE>
@@ -123,17 +124,18 @@ __global__ void __launch_bounds__(256) unif_kernel(const UnifParams p) {
         }
         __syncwarp();
         for (int i = lane; i < n; i += 32) {
-            p.u[q * n + i] = uu[i];
-            p.v[q * n + i] = vv[i];
+            peer_put(p.peer, &p.u[q * n + i], uu[i]);
+            peer_put(p.peer, &p.v[q * n + i], vv[i]);
         }
         if (lane == 0) {
-            p.logl[q] = lcur;
-            p.ncall[q] = ncall;
-            p.nprop[q] = nprop;
-            p.flags[q] = fl;
+            peer_put(p.peer, &p.logl[q], lcur);
+            peer_put(p.peer, &p.ncall[q], ncall);
+            peer_put(p.peer, &p.nprop[q], nprop);
+            peer_put(p.peer, &p.flags[q], fl);
         }
         __syncwarp();
     }
+    peer_finish(p.peer);
 }
 
 __global__ void unif_error_kernel(const uint32_t* flags, int64_t Q, int* out) {
@@ -147,7 +149,9 @@ __global__ void unif_error_kernel(const uint32_t* flags, int64_t Q, int* out) {
 
 extern "C" int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, double* v, double* logl,
                               int32_t* ncall, int32_t* nprop, uint32_t* flags) {
-    if (!ctx || !a || !u || !v || !logl || !ncall || !nprop || !flags) return B2N_ERR_ARG;
+    if (!ctx || !a) return B2N_ERR_ARG;
+    const bool gather = ctx->peer.total > 0;      // outputs may be NULL in gather mode (b2n_peer_result)
+    if (!gather && (!u || !v || !logl || !ncall || !nprop || !flags)) return B2N_ERR_ARG;
     const int draw_only = (a->reserved & B2N_OPT_DRAW_ONLY) ? ((a->reserved & B2N_OPT_DRAW_MIXTURE) ? 3 : 1) : 0;
     B2nModel m;
     memset(&m, 0, sizeof(m));
@@ -162,7 +166,7 @@ extern "C" int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, 
     if (n != m.ndim || nc < 1 || nc > n || Q < 0 || (draw_only && n != nc)) return B2N_ERR_ARG;
     if (ctx->bK < 1 || ctx->bn != nc || ctx->h_logvols.empty())
         return b2n_fail(ctx, B2N_ERR_ARG, "resident bound (with ctrs/ams/logvols) missing or of wrong dimension");
-    if (Q == 0) return B2N_OK;
+    if (Q == 0) return gather ? b2n_fail(ctx, B2N_ERR_ARG, "gather mode: every rank must run at least one chain") : B2N_OK;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
     const int K = ctx->bK;
     // probs = exp(logvol_ells - logsumexp(logvol_ells)) ; cumsum (bounding.py:552, 1305)
@@ -187,12 +191,20 @@ extern "C" int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, 
     p.cum = (const double*)dcum; p.dimflags = (const uint32_t*)dfl_in;
     p.loglstar = a->loglstar; p.seed = a->seed; p.chain0 = a->chain0;
     void *du, *dv, *dl, *dnc, *dnp, *dfl;
-    B2N_TRY(b2n_out(ctx, ctx->out0, u, (size_t)Q * n * sizeof(double), &du));
-    B2N_TRY(b2n_out(ctx, ctx->out1, v, (size_t)Q * n * sizeof(double), &dv));
-    B2N_TRY(b2n_out(ctx, ctx->out2, logl, (size_t)Q * sizeof(double), &dl));
-    B2N_TRY(b2n_out(ctx, ctx->out3, ncall, (size_t)Q * sizeof(int), &dnc));
-    B2N_TRY(b2n_out(ctx, ctx->out4, nprop, (size_t)Q * sizeof(int), &dnp));
-    B2N_TRY(b2n_out(ctx, ctx->out6, flags, (size_t)Q * sizeof(uint32_t), &dfl));
+    void* gdev[7];
+    bool peer_on = false;
+    B2N_TRY(b2n_peer_begin(ctx, n, &p.peer, gdev, &peer_on));
+    if (peer_on) {
+        if (ctx->peer.row0 + Q > ctx->peer.total) return b2n_fail(ctx, B2N_ERR_ARG, "gather rows out of range (b2n_peer_rows)");
+        du = gdev[0]; dv = gdev[1]; dl = gdev[2]; dnc = gdev[3]; dnp = gdev[4]; dfl = gdev[6];
+    } else {
+        B2N_TRY(b2n_out(ctx, ctx->out0, u, (size_t)Q * n * sizeof(double), &du));
+        B2N_TRY(b2n_out(ctx, ctx->out1, v, (size_t)Q * n * sizeof(double), &dv));
+        B2N_TRY(b2n_out(ctx, ctx->out2, logl, (size_t)Q * sizeof(double), &dl));
+        B2N_TRY(b2n_out(ctx, ctx->out3, ncall, (size_t)Q * sizeof(int), &dnc));
+        B2N_TRY(b2n_out(ctx, ctx->out4, nprop, (size_t)Q * sizeof(int), &dnp));
+        B2N_TRY(b2n_out(ctx, ctx->out6, flags, (size_t)Q * sizeof(uint32_t), &dfl));
+    }
     p.u = (double*)du; p.v = (double*)dv; p.logl = (double*)dl;
     p.ncall = (int*)dnc; p.nprop = (int*)dnp; p.flags = (uint32_t*)dfl;
     const int threads = 128, wpb = threads / 32;
@@ -212,9 +224,20 @@ extern "C" int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, 
     *herr = 0;
     B2N_CUDA(ctx, ctx->out7.ensure(64));
     B2N_CUDA(ctx, cudaMemsetAsync(ctx->out7.p, 0, sizeof(int), ctx->stream));
-    unif_error_kernel<<<64, 256, 0, ctx->stream>>>((const uint32_t*)dfl, Q, ctx->out7.as<int>());
+    const uint32_t* eflags = peer_on ? (const uint32_t*)(ctx->peer.win + ctx->peer.off[6]) : (const uint32_t*)dfl;
+    unif_error_kernel<<<64, 256, 0, ctx->stream>>>(eflags, peer_on ? ctx->peer.total : Q, ctx->out7.as<int>());
     B2N_LAUNCH_CHECK(ctx);
     B2N_CUDA(ctx, cudaMemcpyAsync(herr, ctx->out7.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (peer_on) {
+        void* const user7[7] = {u, v, logl, ncall, nprop, nullptr, flags};
+        B2N_TRY(b2n_peer_end(ctx, n, user7));
+        B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->ptr_mode == B2N_PTR_HOST && *ctx->peer.err_host)
+            return b2n_fail(ctx, B2N_ERR_PEER, "a peer never arrived at the exchange (timeout in the kernel)");
+        if (*herr & 1) return B2N_ERR_Q0;
+        if (*herr & 2) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "uniform sampling did not find a point (bound draw limit)");
+        return B2N_OK;
+    }
     B2N_TRY(b2n_out_done(ctx, u, du, (size_t)Q * n * sizeof(double)));
     B2N_TRY(b2n_out_done(ctx, v, dv, (size_t)Q * n * sizeof(double)));
     B2N_TRY(b2n_out_done(ctx, logl, dl, (size_t)Q * sizeof(double)));

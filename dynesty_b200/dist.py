@@ -8,11 +8,19 @@ the gathered queue is bit-identical to a single-GPU fill.  The one exchange step
 all-gather of the finished chains (u, v, logl, counters) -- Q*(2n+1)*8 + O(Q) bytes -- after
 which every rank holds the full queue and advances the identical host state; the live points
 are therefore replicated and the bound update needs no further communication.
+
+On GPUs the all-gather is FUSED into the chain kernels (``attach_peer``): every rank maps the
+exchange windows of all peers (CUDA IPC over NVLink/NVSwitch) and the kernels store finished
+chains into every window, with an in-kernel arrive/wait at the end (csrc/b2n_peer.cu).
+torch.distributed then only carries the 64-byte IPC handles at start-up; ``allgather`` below
+(one collective per output array) remains as the transport for the gloo/CPU tests.
 """
 import numpy as np
 
 
 class Comm:
+    peer_ctx = None      # _lib.Context whose exchange windows are mapped (attach_peer)
+
     def __init__(self, device=None):
         import torch
         import torch.distributed as dist
@@ -22,6 +30,16 @@ class Comm:
         self.backend = dist.get_backend()
         self.device = device if device is not None else (
             torch.device('cuda', torch.cuda.current_device()) if self.backend == 'nccl' else torch.device('cpu'))
+
+    def attach_peer(self, ctx, max_rows, ndim):
+        """Set up the fused exchange for fills of up to `max_rows` chains of dimension `ndim`:
+        allocate this rank's window, swap IPC handles, map the peers' windows."""
+        handle = ctx.peer_export(ctx.peer_window_bytes(max_rows, ndim))
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, handle)
+        ctx.peer_import(self.rank, self.world, handles)
+        self.dist.barrier()
+        self.peer_ctx = ctx
 
     def shard(self, Q):
         """Rows [lo, hi) of a Q-row fill owned by this rank (Q is a multiple of world)."""

@@ -211,12 +211,16 @@ class NestedSampler:
         ell = self.bound.random_ells(self.rstate, size)
         return starts, ell
 
-    def _run_sharded(self, fn, Q):
-        """Run chains [lo, hi) of a Q-chain fill on this rank and all-gather."""
+    def _run_sharded(self, fn, Q, fused=True):
+        """Run chains [lo, hi) of a Q-chain fill on this rank and gather all ranks' chains:
+        inside the kernel over NVLink peer windows when the Comm has them (dist.attach_peer),
+        else with one all-gather per output array."""
         if self.comm is None:
-            return fn(0, Q)
+            return fn(0, Q, None)
         lo, hi = self.comm.shard(Q)
-        return self.comm.allgather(fn(lo, hi), Q)
+        if fused and self.comm.peer_ctx is not None:
+            return fn(lo, hi, (lo, Q))
+        return self.comm.allgather(fn(lo, hi, None), Q)
 
     def _fill_queue(self, loglstar):
         """sampler.py:676-717: one launch for `queue_size` proposals."""
@@ -227,15 +231,16 @@ class NestedSampler:
             # UnitCubeSampler (internal_samplers.py:343-441): u ~ U(0,1)^n, one call each
             u = self.rstate.random((Q, self.ndim))
 
-            def fn(lo, hi):
+            def fn(lo, hi, peer):
                 v, l = self.model.evaluate(u[lo:hi], ctx=self.ctx)
                 return dict(u=u[lo:hi], v=v, logl=l, ncall=np.ones(hi - lo, dtype=np.int32))
-            q = self._run_sharded(fn, Q)
+            q = self._run_sharded(fn, Q, fused=False)
         else:
             smp = self.internal_sampler
             if isinstance(smp, S.B200UniformSampler):
-                def fn(lo, hi):
-                    return smp.run_batch(loglstar, hi - lo, self.bound, self.seed, chain0=c0 + lo, ncdim=self.ncdim)
+                def fn(lo, hi, peer):
+                    return smp.run_batch(loglstar, hi - lo, self.bound, self.seed, chain0=c0 + lo, ncdim=self.ncdim,
+                                         peer=peer)
             else:
                 starts, ell = self.propose_live(loglstar, Q)
                 pts = self.live_u[starts]
@@ -245,8 +250,8 @@ class NestedSampler:
                     self.bound.make_resident()
                     self._resident_key = key
 
-                def fn(lo, hi):
-                    return smp.run_batch(loglstar, pts[lo:hi], ell[lo:hi], self.seed, chain0=c0 + lo)
+                def fn(lo, hi, peer):
+                    return smp.run_batch(loglstar, pts[lo:hi], ell[lo:hi], self.seed, chain0=c0 + lo, peer=peer)
             q = self._run_sharded(fn, Q)
         self.nbatches += 1
         self.n_proposals += int(q['ncall'].sum())

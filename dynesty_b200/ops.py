@@ -149,47 +149,79 @@ def dimflags_from(ndim, periodic=None, reflective=None):
     return f
 
 
+class _gather:
+    """Context manager for the fused multi-GPU gather (include/b200nest.h, peer section):
+    `peer = (row0, total_rows)` makes the chains of the call rows [row0, row0 + Q) of a
+    total_rows-chain fill whose outputs come back COMPLETE (all ranks' rows)."""
+
+    def __init__(self, ctx, peer):
+        self.ctx, self.peer = ctx, peer
+
+    def __enter__(self):
+        if self.peer is not None:
+            self.ctx.peer_rows(self.peer[0], self.peer[1])
+
+    def __exit__(self, *exc):
+        if self.peer is not None:
+            self.ctx.peer_rows(0, 0)
+        return False
+
+
+_NO_OUT = {}          # out=ops.NO_OUT: gather mode, device-pointer callers that read the window
+NO_OUT = _NO_OUT
+
+
 def rwalk_batch(model, u0, loglstar, scale, walks, seed, chain0=0, ncdim=None, ell=None,
-                dimflags=None, ctx=None, out=None):
+                dimflags=None, ctx=None, out=None, peer=None):
     """RWalkSampler.sample for every row of u0 (internal_samplers.py:505-561).
     `out`: optional dict of preallocated buffers (numpy, or torch tensors on the ctx device
-    when the ctx is in device-pointer mode) with keys u, v, logl, n_accept, n_reject, ncall."""
+    when the ctx is in device-pointer mode) with keys u, v, logl, n_accept, n_reject, ncall.
+    `peer=(row0, total)`: fused multi-GPU gather, outputs have `total` rows."""
     ctx = _ctx(ctx)
     a, keep, Q, n = _chain_args(model, u0, ncdim, loglstar, scale, seed, chain0, ell, dimflags)
+    R = Q if peer is None else int(peer[1])
     o = out if out is not None else dict(
-        u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q),
-        n_accept=np.empty(Q, dtype=np.int32), n_reject=np.empty(Q, dtype=np.int32),
-        ncall=np.empty(Q, dtype=np.int32))
-    ctx.check(ctx.lib.b2n_rwalk_batch(ctx.h, C.byref(a), int(walks), ptr(o['u']), ptr(o['v']),
-                                      ptr(o['logl']), ptr(o['n_accept']), ptr(o['n_reject']),
-                                      ptr(o['ncall'])))
+        u=np.empty((R, n)), v=np.empty((R, n)), logl=np.empty(R),
+        n_accept=np.empty(R, dtype=np.int32), n_reject=np.empty(R, dtype=np.int32),
+        ncall=np.empty(R, dtype=np.int32))
+    g = o.get
+    with _gather(ctx, peer):
+        ctx.check(ctx.lib.b2n_rwalk_batch(ctx.h, C.byref(a), int(walks), ptr(g('u')), ptr(g('v')),
+                                          ptr(g('logl')), ptr(g('n_accept')), ptr(g('n_reject')),
+                                          ptr(g('ncall'))))
     return o
 
 
-def _slice_batch(fn, model, u0, loglstar, scale, slices, seed, chain0, doubling, ell, ctx):
+def _slice_batch(fn, model, u0, loglstar, scale, slices, seed, chain0, doubling, ell, ctx, peer=None):
     ctx = _ctx(ctx)
     a, keep, Q, n = _chain_args(model, u0, None, loglstar, scale, seed, chain0, ell, None)
-    o = dict(u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q),
-             n_expand=np.empty(Q, dtype=np.int32), n_contract=np.empty(Q, dtype=np.int32),
-             ncall=np.empty(Q, dtype=np.int32), flags=np.empty(Q, dtype=np.uint32))
-    ctx.check(getattr(ctx.lib, fn)(ctx.h, C.byref(a), int(slices), int(bool(doubling)), ptr(o['u']),
-                                   ptr(o['v']), ptr(o['logl']), ptr(o['n_expand']), ptr(o['n_contract']),
-                                   ptr(o['ncall']), ptr(o['flags'])))
+    R = Q if peer is None else int(peer[1])
+    o = dict(u=np.empty((R, n)), v=np.empty((R, n)), logl=np.empty(R),
+             n_expand=np.empty(R, dtype=np.int32), n_contract=np.empty(R, dtype=np.int32),
+             ncall=np.empty(R, dtype=np.int32), flags=np.empty(R, dtype=np.uint32))
+    with _gather(ctx, peer):
+        ctx.check(getattr(ctx.lib, fn)(ctx.h, C.byref(a), int(slices), int(bool(doubling)), ptr(o['u']),
+                                       ptr(o['v']), ptr(o['logl']), ptr(o['n_expand']), ptr(o['n_contract']),
+                                       ptr(o['ncall']), ptr(o['flags'])))
     return o
 
 
-def rslice_batch(model, u0, loglstar, scale, slices, seed, chain0=0, doubling=False, ell=None, ctx=None):
+def rslice_batch(model, u0, loglstar, scale, slices, seed, chain0=0, doubling=False, ell=None, ctx=None,
+                 peer=None):
     """RSliceSampler.sample per row of u0 (internal_samplers.py:745-855)."""
-    return _slice_batch('b2n_rslice_batch', model, u0, loglstar, scale, slices, seed, chain0, doubling, ell, ctx)
+    return _slice_batch('b2n_rslice_batch', model, u0, loglstar, scale, slices, seed, chain0, doubling, ell, ctx,
+                        peer)
 
 
-def slice_batch(model, u0, loglstar, scale, slices, seed, chain0=0, doubling=False, ell=None, ctx=None):
+def slice_batch(model, u0, loglstar, scale, slices, seed, chain0=0, doubling=False, ell=None, ctx=None,
+                peer=None):
     """SliceSampler.sample per row of u0 (internal_samplers.py:593-709)."""
-    return _slice_batch('b2n_slice_batch', model, u0, loglstar, scale, slices, seed, chain0, doubling, ell, ctx)
+    return _slice_batch('b2n_slice_batch', model, u0, loglstar, scale, slices, seed, chain0, doubling, ell, ctx,
+                        peer)
 
 
 def unif_batch(model, nchain, ndim, loglstar, seed, chain0=0, ncdim=None, dimflags=None, ctx=None,
-               draw_only=False, mixture=False):
+               draw_only=False, mixture=False, peer=None):
     """UniformBoundSampler.sample x nchain on the resident bound (internal_samplers.py:243-340).
     draw_only=True: just Bound.samples(nchain) (no cube test / likelihood)."""
     ctx = _ctx(ctx)
@@ -197,8 +229,10 @@ def unif_batch(model, nchain, ndim, loglstar, seed, chain0=0, ncdim=None, dimfla
                                 Q=int(nchain), ndim=int(ndim))
     if draw_only:
         a.reserved = 3 if mixture else 1      # mixture: no 1/q test, q returned in 'ncall'
-    o = dict(u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q), ncall=np.empty(Q, dtype=np.int32),
-             nprop=np.empty(Q, dtype=np.int32), flags=np.empty(Q, dtype=np.uint32))
-    ctx.check(ctx.lib.b2n_unif_batch(ctx.h, C.byref(a), ptr(o['u']), ptr(o['v']), ptr(o['logl']),
-                                     ptr(o['ncall']), ptr(o['nprop']), ptr(o['flags'])))
+    R = Q if peer is None else int(peer[1])
+    o = dict(u=np.empty((R, n)), v=np.empty((R, n)), logl=np.empty(R), ncall=np.empty(R, dtype=np.int32),
+             nprop=np.empty(R, dtype=np.int32), flags=np.empty(R, dtype=np.uint32))
+    with _gather(ctx, peer):
+        ctx.check(ctx.lib.b2n_unif_batch(ctx.h, C.byref(a), ptr(o['u']), ptr(o['v']), ptr(o['logl']),
+                                         ptr(o['ncall']), ptr(o['nprop']), ptr(o['flags'])))
     return o

@@ -114,11 +114,11 @@ class B200RWalkSampler(_B200Sampler):
     def update_bound_interval_ratio(self):
         return self.sampler_kwargs['walks']
 
-    def run_batch(self, loglstar, points, ell, seed, chain0=0):
+    def run_batch(self, loglstar, points, ell, seed, chain0=0, peer=None):
         walks = self.sampler_kwargs['walks']
         return ops.rwalk_batch(self.model.model_id(self._ctx), points, loglstar, self.scale, walks, seed,
                                chain0=chain0, ncdim=self.ncdim or self.model.ndim, ell=ell,
-                               dimflags=self._flags(), ctx=self._ctx)
+                               dimflags=self._flags(), ctx=self._ctx, peer=peer)
 
     def prepare_sampler(self, loglstar=None, points=None, axes=None, seeds=None, prior_transform=None,
                         loglikelihood=None, nested_sampler=None):
@@ -159,11 +159,11 @@ class _B200SliceBase(_B200Sampler):
         self.sampler_kwargs['slices'] = kwargs.get('slices', 5) or 5
         self.slice_history = {'n_contract': 0, 'n_expand': 0}
 
-    def run_batch(self, loglstar, points, ell, seed, chain0=0):
+    def run_batch(self, loglstar, points, ell, seed, chain0=0, peer=None):
         fn = getattr(ops, self._fn)
         return fn(self.model.model_id(self._ctx), points, loglstar, self.scale, self.sampler_kwargs['slices'],
                   seed, chain0=chain0, doubling=bool(self.sampler_kwargs.get('slice_doubling', False)),
-                  ell=ell, ctx=self._ctx)
+                  ell=ell, ctx=self._ctx, peer=peer)
 
     def prepare_sampler(self, loglstar=None, points=None, axes=None, seeds=None, prior_transform=None,
                         loglikelihood=None, nested_sampler=None):
@@ -225,7 +225,7 @@ class B200UniformSampler(_B200Sampler):
     """internal_samplers.py:206-340; needs a B200 bound (the kernel draws from the
     device-resident ellipsoids)."""
 
-    def run_batch(self, loglstar, nchain, bound, seed, chain0=0, ncdim=None):
+    def run_batch(self, loglstar, nchain, bound, seed, chain0=0, ncdim=None, peer=None):
         key = (id(bound), getattr(bound, 'version', None))
         if key != self._res.key:
             bound.make_resident()
@@ -233,7 +233,7 @@ class B200UniformSampler(_B200Sampler):
         n = self.ndim or self.model.ndim
         flags = self._flags()
         return ops.unif_batch(self.model.model_id(self._ctx), nchain, n, loglstar, seed, chain0=chain0,
-                              ncdim=ncdim or self.ncdim or n, dimflags=flags, ctx=self._ctx)
+                              ncdim=ncdim or self.ncdim or n, dimflags=flags, ctx=self._ctx, peer=peer)
 
     def prepare_sampler(self, loglstar=None, points=None, axes=None, seeds=None, prior_transform=None,
                         loglikelihood=None, nested_sampler=None):

@@ -48,7 +48,8 @@ typedef enum {
     B2N_ERR_SLICE_FAIL = 8,      /* RuntimeError internal_samplers.py:1191-1203     */
     B2N_ERR_NOMEM = 9,
     B2N_ERR_UNSUPPORTED = 10,
-    B2N_ERR_TOO_MANY_ELLS = 11   /* max_ells too small for the decomposition        */
+    B2N_ERR_TOO_MANY_ELLS = 11,  /* max_ells too small for the decomposition        */
+    B2N_ERR_PEER = 12            /* peer exchange not configured / a peer never arrived */
 } b2n_status;
 
 /* warning bits (the reference issues warnings.warn at the cited lines) */
@@ -217,6 +218,44 @@ int b2n_slice_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slices,
  * unused.  nprop[q] = draws from the bound incl. out-of-cube ones. */
 int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, double* v,
                    double* logl, int32_t* ncall, int32_t* nprop, uint32_t* flags);
+
+/* ---- multi-GPU exchange over NVLink peer memory ------------------------------
+ * The path shards by CHAINS: rank r of W runs rows [row0, row0 + nchain) of a `total_rows`-chain
+ * queue fill (the reference's pool.map over queue slots, sampler.py:717, one slot = one chain).
+ * Every rank needs every finished chain (replicated live set), which is an all-gather.  Instead
+ * of a collective after the kernel, the chain kernels themselves store each finished chain into
+ * the exchange WINDOW of every rank (peer stores over NVLink/NVSwitch), and the last CTA of the
+ * grid runs a cross-GPU arrive/wait on counters in the windows: when a b2n_*_batch launch has
+ * completed on a rank, all `total_rows` rows are present in that rank's window.
+ *
+ *   b2n_peer_export   allocate this rank's window, return its 64-byte CUDA IPC handle
+ *   (exchange the handles of all ranks with any host transport, e.g. torch.distributed)
+ *   b2n_peer_import   map the windows of all ranks (one process per GPU)
+ *   b2n_peer_import_raw  same for ranks living in THIS process (device pointers of the windows)
+ *   b2n_peer_rows     switch the following b2n_{rwalk,rslice,slice,unif}_batch calls to gather
+ *                     mode: a->nchain local chains are rows [row0, row0+nchain) of total_rows;
+ *                     output pointers then receive ALL total_rows rows (they may be NULL in
+ *                     device-pointer mode: read the window through b2n_peer_result instead).
+ *                     total_rows = 0 switches gather mode off.  All ranks must issue the same
+ *                     sequence of gather-mode calls.
+ *   b2n_peer_result   window pointer + byte offsets {u, v, logl, int0, int1, int2, int3} of the
+ *                     last gather-mode call (int0..3 = the call's int32 outputs in argument order)
+ *   b2n_peer_read     synchronise and copy `bytes` at byte `offset` of the own window to HOST memory
+ *   b2n_peer_check    synchronise and report B2N_ERR_PEER if a peer never arrived (device mode;
+ *                     host-pointer mode checks on return of every call).
+ * Windows are double-buffered by call parity, so a rank may consume the rows of call k on its
+ * stream while faster peers already store the rows of call k+1. */
+#define B2N_PEER_HANDLE_BYTES 64
+#define B2N_MAX_PEERS 8
+int b2n_peer_export(b2n_ctx* ctx, uint64_t bytes, unsigned char* handle);
+int b2n_peer_import(b2n_ctx* ctx, int32_t rank, int32_t world, const unsigned char* handles);
+int b2n_peer_import_raw(b2n_ctx* ctx, int32_t rank, int32_t world, void* const* windows);
+int b2n_peer_rows(b2n_ctx* ctx, int64_t row0, int64_t total_rows);
+int b2n_peer_result(b2n_ctx* ctx, void** window, uint64_t* offsets7);
+int b2n_peer_read(b2n_ctx* ctx, uint64_t offset, void* host_dst, uint64_t bytes);
+int b2n_peer_check(b2n_ctx* ctx);
+/* bytes a window needs for gather-mode calls of total_rows x ndim */
+uint64_t b2n_peer_window_bytes(int64_t total_rows, int32_t ndim);
 
 #ifdef __cplusplus
 }

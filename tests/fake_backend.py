@@ -120,7 +120,7 @@ def dimflags_from(ndim, periodic=None, reflective=None):
 
 
 def rwalk_batch(model, u0, loglstar, scale, walks, seed, chain0=0, ncdim=None, ell=None, dimflags=None,
-                ctx=None):
+                ctx=None, peer=None):
     m = _models[model]
     u0 = np.atleast_2d(u0)
     Q, n = u0.shape
@@ -157,16 +157,18 @@ def _slice(fn, model, u0, loglstar, scale, slices, seed, chain0, doubling, ell):
     return o
 
 
-def rslice_batch(model, u0, loglstar, scale, slices, seed, chain0=0, doubling=False, ell=None, ctx=None):
+def rslice_batch(model, u0, loglstar, scale, slices, seed, chain0=0, doubling=False, ell=None, ctx=None,
+                 peer=None):
     return _slice(OS.rslice_chain, model, u0, loglstar, scale, slices, seed, chain0, doubling, ell)
 
 
-def slice_batch(model, u0, loglstar, scale, slices, seed, chain0=0, doubling=False, ell=None, ctx=None):
+def slice_batch(model, u0, loglstar, scale, slices, seed, chain0=0, doubling=False, ell=None, ctx=None,
+                peer=None):
     return _slice(OS.slice_chain, model, u0, loglstar, scale, slices, seed, chain0, doubling, ell)
 
 
 def unif_batch(model, nchain, ndim, loglstar, seed, chain0=0, ncdim=None, dimflags=None, ctx=None,
-               draw_only=False):
+               draw_only=False, mixture=False, peer=None):
     from scipy.special import logsumexp
     K = len(_state['axes'])
     me = OB.MultiEll.__new__(OB.MultiEll)
