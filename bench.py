@@ -279,10 +279,17 @@ def run_b200(args, cfg):
                             ell=ell, ctx=ctx, out=h_np)
         return o
 
-    def step_dev():
-        """Same step with the inputs already resident in HBM (device pointers, async)."""
+    def prep_dev():
+        """Inputs of the next device-resident step: start points gathered from the live set in HBM
+        (outside the timed events: `value` starts with its inputs resident)."""
         starts, ell = propose()
         torch.index_select(d_live, 0, torch.from_numpy(starts).to(dev, non_blocking=True), out=d_u0)
+        return ell
+
+    def step_dev(ell=None):
+        """Same step with the inputs already resident in HBM (device pointers, async)."""
+        if ell is None:
+            ell = prep_dev()
         ctx.set_pointer_mode(_lib.PTR_DEVICE)
         c0 = state['chain']
         state['chain'] += Q * world
@@ -326,9 +333,10 @@ def run_b200(args, cfg):
     kern_ms = []
     barrier()
     for a, b in ev:
+        ell = prep_dev()
         flush.zero_()                        # L2 flush between timed iterations (outside the events)
         a.record(stream)
-        step_dev()
+        step_dev(ell)
         b.record(stream)
         b.synchronize()
         kern_ms.append(ctx.last_kernel_ms())
@@ -387,6 +395,7 @@ def run_b200(args, cfg):
                     "d2h_bytes_per_step": (world if fused else 1) * (2 * Q * n * 8 + Q * 8 + 3 * Q * 4),
                     "bytes_are": "per rank"},
             "gpu_launches": int(launches),
+            "accepted_proposals_per_s": value * accept_frac,      # rwalk n_accept / wall
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch",
                          "algorithmic_bytes_per_launch": algorithmic_bytes(n) * Q * walks, "kernel": "rwalk_kernel",
@@ -416,7 +425,8 @@ def run_b200(args, cfg):
         line["logz"] = {"queue_size": args.logz_queue, "logz": float(res.logz[-1]), "logzerr": float(res.logzerr[-1]),
                         "truth": model.logz_truth, "abs_err": abs(float(res.logz[-1]) - model.logz_truth),
                         "niter": int(res.niter), "ncall": int(res.ncall), "nbound": int(res.nbound),
-                        "wall_s": round(wall, 2), "calls_per_s": res.ncall / wall}
+                        "wall_s": round(wall, 2), "calls_per_s": res.ncall / wall,
+                        "iterations_per_s": res.niter / wall}
     # ---- CPU baseline on the host cores (rank 0, N=1 only), bounded sample
     if rank == 0 and world == 1 and args.cpu_baseline:
         import multiprocessing as mp
@@ -426,8 +436,10 @@ def run_b200(args, cfg):
         v, p, tsec, nch = cpu_sample(cfg, 12.0, pool, cores, (u_live, loglstar))
         if pool is not None:
             pool.close()
+        v1, _, t1, nch1 = cpu_sample(cfg, 3.0, None, 1, (u_live, loglstar))      # (i) one core, serial
         line["cpu_baseline"] = {"value": v, "unit": "proposals/s", "cores": cores, "kind": "port",
-                                "sample": "%d oracle rwalk chains x %d walks (%.1f s) on %d processes" % (nch, walks, tsec, cores)}
+                                "sample": "%d oracle rwalk chains x %d walks (%.1f s) on %d processes" % (nch, walks, tsec, cores),
+                                "one_core_value": v1, "one_core_sample": "%d chains (%.1f s), serial" % (nch1, t1)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
