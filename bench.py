@@ -75,6 +75,43 @@ def host_cores():
 
 
 # ----------------------------------------------------------------------------- CPU arm
+_REF = {}
+
+
+def reference_kind():
+    """"reference" when the unmodified dynesty is importable on this box (the git-ignored offline
+    install baseline/_ref, or /root/reference in the build container), else "port" (the oracle)."""
+    from oracle import refshim
+    return 'reference' if refshim.available() else 'port'
+
+
+def _cpu_worker_ref(args):
+    """The UNMODIFIED reference: dynesty.internal_samplers.RWalkSampler.sample(SamplerArgument)
+    per chain -- the static method dynesty's pool maps over the queue (sampler.py:717) -- with
+    utils.LogLikelihood around the notebook's numpy likelihood and numpy's PCG64 generator."""
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    u0s, loglstar, axes, scale, walks, chain0, ndim = args
+    if 'mod' not in _REF:
+        from oracle import refshim
+        dynesty = refshim.import_reference()
+        from dynesty import internal_samplers as RIS, utils as RU
+        Cm = np.full((ndim, ndim), 0.4)
+        np.fill_diagonal(Cm, 1.0)
+        Cinv = np.linalg.inv(Cm)
+        lnorm = -0.5 * (math.log(2 * math.pi) * ndim + np.linalg.slogdet(Cm)[1])
+        _REF.update(mod=RIS, ptform=lambda u: 10. * u - 5.,
+                    logl=RU.LogLikelihood(lambda x: -0.5 * np.dot(x, np.dot(Cinv, x)) + lnorm, ndim))
+    RIS = _REF['mod']
+    kw = {'walks': walks, 'ncdim': ndim, 'nonbounded': None, 'periodic': None, 'reflective': None}
+    nacc = 0
+    for i, u0 in enumerate(u0s):
+        a = RIS.SamplerArgument(u=u0, loglstar=loglstar, axes=axes, scale=scale, prior_transform=_REF['ptform'],
+                                loglikelihood=_REF['logl'], rseed=SEED + chain0 + i, kwargs=kw)
+        r = RIS.RWalkSampler.sample(a)
+        nacc += r.proposal_stats['n_accept']
+    return len(u0s) * walks, nacc
+
+
 def _cpu_worker(args):
     """Oracle port of the reference's per-chain pure-Python loop (what dynesty.pool.Pool maps)."""
     os.environ.setdefault('OMP_NUM_THREADS', '1')
@@ -88,9 +125,11 @@ def _cpu_worker(args):
     return len(u0s) * walks, nacc
 
 
-def cpu_sample(cfg, target_seconds, pool, cores, state=None):
-    """Times the oracle rwalk chains on `cores` processes for ~target_seconds."""
+def cpu_sample(cfg, target_seconds, pool, cores, state=None, kind='port'):
+    """Times the reference's (kind="reference") or the oracle's (kind="port") rwalk chains on
+    `cores` processes for ~target_seconds."""
     from oracle import bounding as OB
+    worker = _cpu_worker_ref if kind == 'reference' else _cpu_worker
     u, loglstar = state if state is not None else make_state(cfg['ndim'], cfg['nlive'])
     ell = OB.bounding_ellipsoid(u)
     ell.scale_to_logvol(ell.logvol + math.log(1.25))
@@ -98,17 +137,17 @@ def cpu_sample(cfg, target_seconds, pool, cores, state=None):
     scale, walks, n = 0.15, cfg['walks'], cfg['ndim']
     # pilot on every process at once (import + contention included) to size the bounded sample
     pilot = [(u[:4], loglstar, ell.axes, scale, walks, c * 4, n) for c in range(cores)]
+    _ = pool.map(worker, pilot) if pool is not None else [worker(t) for t in pilot]    # imports, untimed
     t0 = time.perf_counter()
-    _ = pool.map(_cpu_worker, pilot) if pool is not None else [_cpu_worker(t) for t in pilot]
-    _ = pool.map(_cpu_worker, pilot) if pool is not None else None
-    per_chain = (time.perf_counter() - t0) / (8 if pool is not None else 4)
+    _ = pool.map(worker, pilot) if pool is not None else [worker(t) for t in pilot]
+    per_chain = (time.perf_counter() - t0) / 4
     per_core = max(4, min(int(target_seconds / per_chain), 20000))
     tasks = []
     for c in range(cores):
         starts = u[rng.integers(len(u), size=per_core)]
         tasks.append((starts, loglstar, ell.axes, scale, walks, 10**6 + c * per_core, n))
     t0 = time.perf_counter()
-    res = pool.map(_cpu_worker, tasks) if pool is not None else [_cpu_worker(t) for t in tasks]
+    res = pool.map(worker, tasks) if pool is not None else [worker(t) for t in tasks]
     dt = time.perf_counter() - t0
     nprop = sum(r[0] for r in res)
     return nprop / dt, nprop, dt, per_core * cores
@@ -123,25 +162,28 @@ def run_reference(args, cfg):
     os.environ['OMP_NUM_THREADS'] = '1'
     pool = mp.get_context('fork').Pool(cores) if cores > 1 else None
     state = make_state(cfg['ndim'], cfg['nlive'])
+    kind = reference_kind()
     per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
-        cpu_sample(cfg, per_step, pool, cores, state)
+        cpu_sample(cfg, per_step, pool, cores, state, kind)
     tot_p = tot_t = 0.0
     nchains = 0
     for _ in range(args.steps):
-        _, p, t, nch = cpu_sample(cfg, per_step, pool, cores, state)
+        _, p, t, nch = cpu_sample(cfg, per_step, pool, cores, state, kind)
         tot_p += p
         tot_t += t
         nchains = nch
     if pool is not None:
         pool.close()
     val = tot_p / tot_t
-    sample = "%d oracle rwalk chains x %d walks per step on %d processes" % (nchains, cfg['walks'], cores)
+    who = ("dynesty RWalkSampler.sample (unmodified reference, baseline/_ref)" if kind == 'reference'
+           else "oracle rwalk")
+    sample = "%d %s chains x %d walks per step on %d processes" % (nchains, who, cfg['walks'], cores)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "proposals/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": cfg['desc'], "queue_chains": nchains},
-            "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -433,12 +475,14 @@ def run_b200(args, cfg):
         cores = host_cores()
         os.environ['OMP_NUM_THREADS'] = '1'
         pool = mp.get_context('fork').Pool(cores) if cores > 1 else None
-        v, p, tsec, nch = cpu_sample(cfg, 12.0, pool, cores, (u_live, loglstar))
+        kind = reference_kind()
+        v, p, tsec, nch = cpu_sample(cfg, 12.0, pool, cores, (u_live, loglstar), kind)
         if pool is not None:
             pool.close()
-        v1, _, t1, nch1 = cpu_sample(cfg, 3.0, None, 1, (u_live, loglstar))      # (i) one core, serial
-        line["cpu_baseline"] = {"value": v, "unit": "proposals/s", "cores": cores, "kind": "port",
-                                "sample": "%d oracle rwalk chains x %d walks (%.1f s) on %d processes" % (nch, walks, tsec, cores),
+        v1, _, t1, nch1 = cpu_sample(cfg, 3.0, None, 1, (u_live, loglstar), kind)   # (i) one core, serial
+        who = "dynesty RWalkSampler.sample (unmodified reference)" if kind == 'reference' else "oracle rwalk"
+        line["cpu_baseline"] = {"value": v, "unit": "proposals/s", "cores": cores, "kind": kind,
+                                "sample": "%d %s chains x %d walks (%.1f s) on %d processes" % (nch, who, walks, tsec, cores),
                                 "one_core_value": v1, "one_core_sample": "%d chains (%.1f s), serial" % (nch1, t1)}
     if rank == 0:
         print(json.dumps(line))
