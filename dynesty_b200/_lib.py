@@ -40,6 +40,21 @@ class ChainArgs(C.Structure):
                 ('scale', C.c_double), ('seed', C.c_uint64), ('chain0', C.c_uint64)]
 
 
+class NsConfig(C.Structure):
+    _fields_ = [('nlive', C.c_int32), ('ndim', C.c_int32), ('ncdim', C.c_int32), ('batch', C.c_int32),
+                ('sampler', C.c_int32), ('steps', C.c_int32), ('model_id', C.c_int32),
+                ('strict_contains', C.c_int32), ('facc', C.c_double), ('dlogz', C.c_double),
+                ('maxiter', C.c_int64), ('maxcall', C.c_int64), ('update_interval', C.c_int64),
+                ('seed', C.c_uint64), ('chain0', C.c_uint64), ('dimflags', C.c_void_p)]
+
+
+class NsStatus(C.Structure):
+    _fields_ = [('it', C.c_int64), ('ncall', C.c_int64), ('rounds', C.c_int64), ('logz', C.c_double),
+                ('logvol', C.c_double), ('loglstar', C.c_double), ('lmax', C.c_double),
+                ('delta_logz', C.c_double), ('scale', C.c_double), ('done', C.c_int32),
+                ('need_bound', C.c_int32), ('doubling', C.c_int32), ('error', C.c_int32)]
+
+
 # every symbol include/b200nest.h declares: (restype, argtypes)
 _P, _I, _L, _D, _U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_uint64
 SYMBOLS = {
@@ -74,6 +89,15 @@ SYMBOLS = {
     'b2n_peer_read': (C.c_int, [_P, _U64, _P, _U64]),
     'b2n_peer_check': (C.c_int, [_P]),
     'b2n_peer_window_bytes': (_U64, [_L, _I]),
+    'b2n_ns_create': (C.c_int, [_P, C.POINTER(NsConfig), _L]),
+    'b2n_ns_destroy': (C.c_int, [_P]),
+    'b2n_ns_set_state': (C.c_int, [_P, _P, _P, _P, _D, _D, _D, _L, _L, _D]),
+    'b2n_ns_run': (C.c_int, [_P, _I, _I, C.POINTER(NsStatus)]),
+    'b2n_ns_status_get': (C.c_int, [_P, C.POINTER(NsStatus)]),
+    'b2n_ns_bound_updated': (C.c_int, [_P]),
+    'b2n_ns_reserve_dead': (C.c_int, [_P, _L]),
+    'b2n_ns_get_live': (C.c_int, [_P, _P, _P, _P]),
+    'b2n_ns_get_dead': (C.c_int, [_P, _L, _L, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

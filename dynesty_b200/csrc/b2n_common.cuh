@@ -61,6 +61,27 @@ struct PeerState {
     unsigned int* err_host = nullptr;  // pinned mailbox for the window's err word
 };
 
+// ---- device-paced launches (b2n_ns.cu): the per-round arguments of a chain kernel live in HBM,
+// written by the previous kernel on the stream, so that consecutive nested-sampling rounds need
+// no host round trip.  A chain kernel given a B2nDyn reads its threshold / scale / chain ids /
+// CTA count from it and returns at once when `skip` is set.
+struct B2nDyn {
+    double loglstar, scale;
+    unsigned long long chain0;
+    int skip, ncta, doubling, pad;
+};
+struct DynLaunch {
+    bool active = false;         // the next chain entry call is device-paced
+    bool plan_only = false;      // ... and only reports chains_per_cta (no launch)
+    const B2nDyn* dev = nullptr;
+    const int* order = nullptr;  // device worklist (same layout as b2n_build_worklist's)
+    const int3* cta = nullptr;
+    int max_cta = 0;             // grid size: upper bound of the CTA count
+    int cpc = 0;                 // out: chains per CTA the entry point planned for
+};
+
+struct b2n_ns;                   // device-resident nested-sampling run (b2n_ns.cu)
+
 struct b2n_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -86,7 +107,10 @@ struct b2n_ctx {
     void* pinned = nullptr;     // small pinned host mailbox
     size_t pinned_cap = 0;
     PeerState peer;
+    DynLaunch dyn;
+    b2n_ns* ns = nullptr;
 };
+void b2n_ns_release(b2n_ctx* ctx);
 
 // gather-mode plumbing shared by the chain entry points (b2n_peer.cu).  b2n_peer_begin: when
 // gather mode is on, point the 7 output arrays at this rank's rows of its own window and fill

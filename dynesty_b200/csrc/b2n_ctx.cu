@@ -66,6 +66,7 @@ void b2n_free(b2n_ctx* ctx) {
                       &ctx->scratch5, &ctx->work0, &ctx->work1};
     for (DevBuf* b : bufs) b->release();
     b2n_peer_release(ctx);
+    b2n_ns_release(ctx);
     for (void* p : ctx->model_allocs) cudaFree(p);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -1,0 +1,621 @@
+// b2n_ns.cu -- device-resident nested-sampling rounds ("replace the K worst live points per
+// launch").  Part of libb200nest.so (C ABI: include/b200nest.h, b2n_ns_*).
+//
+// What it replaces.  The reference's master loop (sampler.py:1040-1212) removes ONE worst live
+// point per iteration and obtains its replacement from `_new_point` (:732-778), which pops a
+// queue that `_fill_queue` (:676-717) fills with `queue_size` proposals evolved at the threshold
+// of fill time.  With a queue, an entry is kept only if it still beats the CURRENT threshold: for
+// chains that stay correlated with their start point (rwalk at 50-D) that filter selects the
+// offspring of the best live points and biases logZ -- and every iteration costs
+// a host round trip.  A round here removes the K lowest live points AT ONCE (threshold = the
+// K-th lowest logl), evolves K chains from uniformly chosen survivors at that threshold and puts
+// every chain end point into a freed slot: no filter, hence no selection effect, and every
+// proposal is used.  Between the removals the number of live points falls N, N-1, .. N-K+1,
+// which the evidence quadrature accounts for exactly as the reference does for a shrinking
+// live set (sampler.py:780-914 / utils.py:1411-1467): ln X decreases by ln((m+1)/m) at a dead
+// point that had m live points.
+//
+// One round = three launches on the ctx stream, no host synchronisation in between:
+//   ns_propose_kernel  sort the live log-likelihoods (bitonic, one CTA), termination test
+//                      (sampler.py:1095-1120), pick K start rows among the survivors and their
+//                      ellipsoids (propose_live :469-491, get_random_axes bounding.py:726-731),
+//                      `bound.contains` of every start (:485-489), build the per-CTA worklist of
+//                      the chain kernel, write the round's B2nDyn
+//   chain kernel       rwalk / rslice / slice (b2n_rwalk.cu, b2n_slice.cu), device-paced
+//   ns_commit_kernel   dead-point records, evidence increment (utils.py:1470-1492), scatter of the
+//                      chain end points into the freed slots, tuning of the proposal scale
+//                      (internal_samplers.py:460-493, 1209-1239), bound-update-due test
+//                      (sampler.py:625-674)
+// A stop condition (done / bound update due / start outside the bound / dead buffer full) sets a
+// flag in HBM; the remaining enqueued rounds return at once and the host picks the flag up at its
+// next status read.
+#include "b2n_device.cuh"
+#include <algorithm>
+#include <math_constants.h>
+
+#define B2N_NS_DRIVER_CHAIN 0x4000000000000000ULL   // Philox chain id space of the round driver
+#define B2N_NS_THREADS 1024
+
+struct NsScalars {
+    long long it, ncall, ncall_last_update, round;
+    double logvol, logz, loglstar, lmax, scale, delta_logz;
+    long long hist_a, hist_b;
+    int done, need_bound, doubling, error;
+};
+
+struct NsDev {
+    int N, n, nc, K, Kell, cpc, strict, sampler, Npad;
+    double dlogz, facc;
+    long long maxiter, maxcall, update_interval, dead_cap;
+    unsigned long long seed, chain0;
+    double *live_u, *live_v, *live_logl;
+    double *dead_u, *dead_v, *dead_logl, *dead_logvol;
+    int* dead_ncall;
+    NsScalars* sc;
+    B2nDyn* dyn;
+    int* sidx;          // live rows sorted by (logl, row) ascending
+    double* slogl;      // their logl
+    double* u0;         // K x n start points of the round
+    int* order;         // chain worklist
+    int3* cta;
+    double *o_u, *o_v, *o_logl;
+    int *o_i0, *o_i1, *o_ncall;
+    uint32_t* o_flags;
+    const double *ctrs, *ams, *logvols;      // resident bound
+};
+
+struct b2n_ns {
+    b2n_ns_config cfg;
+    std::vector<uint8_t> dimflags;
+    bool has_flags = false;
+    NsDev d;
+    long long dead_cap = 0;
+    std::vector<void*> allocs;
+    void* dead_alloc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+__device__ __forceinline__ double dev_logaddexp(double a, double b) {
+    const double hi = fmax(a, b), lo = fmin(a, b);
+    if (lo == -CUDART_INF) return hi;
+    return hi + log1p(exp(lo - hi));
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsDev s) {
+    extern __shared__ __align__(16) unsigned char ns_smem[];
+    const int tid = threadIdx.x, nth = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    NsScalars* sc = s.sc;
+    if (sc->done || sc->need_bound) {
+        if (tid == 0) s.dyn->skip = 1;
+        return;
+    }
+    const int N = s.N, K = s.K, n = s.n, nc = s.nc, Npad = s.Npad;
+    double* key = reinterpret_cast<double*>(ns_smem);
+    double* dvec = key + Npad;                               // 32 warps x nc
+    double* cum = dvec + 32 * nc;                            // Kell
+    int* idx = reinterpret_cast<int*>(cum + ((s.Kell + 1) & ~1));
+    int* start = idx + Npad;                                 // K
+    int* ell = start + K;                                    // K
+    int* cnt = ell + K;                                      // Kell + 1
+    __shared__ int s_flag, s_bad;
+    for (int i = tid; i < Npad; i += nth) {
+        key[i] = i < N ? s.live_logl[i] : CUDART_INF;
+        idx[i] = i;
+    }
+    if (tid == 0) { s_flag = 0; s_bad = 0; }
+    __syncthreads();
+    // ---- bitonic sort of (logl, row), ascending; padding (+inf, row >= N) sorts last
+    for (int k = 2; k <= Npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (Npad >> 1); t += nth) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool asc = (i & k) == 0;
+                const double ka = key[i], kb = key[l];
+                const int ia = idx[i], ib = idx[l];
+                const bool gt = ka > kb || (ka == kb && ia > ib);
+                if (gt == asc) { key[i] = kb; key[l] = ka; idx[i] = ib; idx[l] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- termination (sampler.py:1095-1120) and capacity
+    if (tid == 0) {
+        const double lmax = key[N - 1];
+        const double delta = dev_logaddexp(0.0, lmax + sc->logvol - sc->logz);
+        sc->lmax = lmax;
+        sc->delta_logz = delta;
+        if (delta < s.dlogz || sc->it >= s.maxiter || sc->ncall >= s.maxcall || key[0] == lmax) {
+            sc->done = 1;
+            s_flag = 1;
+        } else if (sc->it + K > s.dead_cap) {
+            sc->need_bound = 3;                             // dead buffer full: the host grows it
+            s_flag = 1;
+        }
+        if (s_flag) s.dyn->skip = 1;
+    }
+    __syncthreads();
+    if (s_flag) return;
+    for (int i = tid; i < N; i += nth) s.sidx[i] = idx[i];
+    for (int i = tid; i < K; i += nth) s.slogl[i] = key[i];
+    // ---- start rows among the survivors, ellipsoid of every chain
+    ChainRng g;
+    g.init(s.seed, B2N_NS_DRIVER_CHAIN + (unsigned long long)sc->round);
+    if (s.Kell > 1 && tid == 0) {                           // volume-weighted pick: cumulative probabilities
+        double m = s.logvols[0];
+        for (int k = 1; k < s.Kell; k++) m = fmax(m, s.logvols[k]);
+        double tot = 0.0;
+        for (int k = 0; k < s.Kell; k++) tot += exp(s.logvols[k] - m);
+        const double lv = m + log(tot);
+        double c = 0.0;
+        for (int k = 0; k < s.Kell; k++) { c += exp(s.logvols[k] - lv); cum[k] = c; }
+    }
+    __syncthreads();
+    const int nsurv = N - K;
+    for (int c = tid; c < K; c += nth) {
+        g.tick = 0;
+        const double U = rng_uniform_elem(g, c);
+        int sidx = (int)(U * (double)nsurv);
+        sidx = sidx < nsurv - 1 ? sidx : nsurv - 1;
+        start[c] = idx[K + sidx];
+        int e = 0;
+        if (s.Kell > 1) {
+            g.tick = 1;
+            const double U2 = rng_uniform_elem(g, c);
+            while (e < s.Kell - 1 && cum[e] < U2) e++;       // np.searchsorted(cumsum, U), clipped
+        }
+        ell[c] = e;
+    }
+    __syncthreads();
+    // ---- bound.contains(start[:nc]) (sampler.py:485-489): a start outside forces a bound update
+    for (int c = warp; c < K; c += (nth >> 5)) {
+        const double* x = s.live_u + (size_t)start[c] * n;
+        double* d = dvec + warp * nc;
+        bool inside = false;
+        for (int k = 0; k < s.Kell && !inside; k++) {
+            const double* ctr = s.ctrs + (size_t)k * nc;
+            const double* A = s.ams + (size_t)k * nc * nc;
+            for (int i = lane; i < nc; i += 32) d[i] = x[i] - ctr[i];
+            __syncwarp();
+            double acc = 0.0;
+            for (int i = lane; i < nc; i += 32) {
+                double y = 0.0;
+                for (int j = 0; j < nc; j++) y = fma(A[(size_t)i * nc + j], d[j], y);
+                acc = fma(d[i], y, acc);
+            }
+            acc = warp_sum(acc);
+            inside = s.strict ? (acc < 1.0) : (acc <= 1.0);
+            __syncwarp();
+        }
+        if (!inside && lane == 0) atomicOr(&s_bad, 1);
+    }
+    // ---- start points of the chains
+    for (int e = tid; e < K * n; e += nth) {
+        const int c = e / n, i = e - c * n;
+        s.u0[e] = s.live_u[(size_t)start[c] * n + i];
+    }
+    __syncthreads();
+    // ---- worklist: chains grouped by ellipsoid, groups split into equal CTAs (b2n_build_worklist)
+    int ncta = 0;
+    if (s.Kell == 1) {
+        const int parts = (K + s.cpc - 1) / s.cpc;
+        for (int c = tid; c < K; c += nth) s.order[c] = c;
+        for (int i = tid; i < parts; i += nth) {
+            const int lo = (int)((long long)K * i / parts), hi = (int)((long long)K * (i + 1) / parts);
+            s.cta[i] = make_int3(lo, hi - lo, 0);
+        }
+        ncta = parts;
+    } else if (tid == 0) {
+        for (int k = 0; k <= s.Kell; k++) cnt[k] = 0;
+        for (int c = 0; c < K; c++) cnt[ell[c] + 1]++;
+        for (int k = 0; k < s.Kell; k++) cnt[k + 1] += cnt[k];
+        for (int k = 0; k < s.Kell; k++) {
+            const int c0 = cnt[k], c = cnt[k + 1] - c0;
+            if (c == 0) continue;
+            const int parts = (c + s.cpc - 1) / s.cpc;
+            for (int i = 0; i < parts; i++) {
+                const int lo = c0 + (int)((long long)c * i / parts), hi = c0 + (int)((long long)c * (i + 1) / parts);
+                s.cta[ncta++] = make_int3(lo, hi - lo, k);
+            }
+        }
+        // stable fill (chains of one ellipsoid keep their order); cnt[k] becomes the write cursor
+        for (int c = 0; c < K; c++) s.order[cnt[ell[c]]++] = c;
+    }
+    if (tid == 0) {
+        B2nDyn* dy = s.dyn;
+        dy->loglstar = key[K - 1];
+        dy->scale = sc->scale;
+        dy->chain0 = s.chain0 + (unsigned long long)sc->round * (unsigned long long)K;
+        dy->ncta = ncta;
+        dy->doubling = sc->doubling;
+        dy->skip = s_bad ? 1 : 0;
+        if (s_bad) sc->need_bound = 2;                       // forced update (sampler.py:486)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_reduce_max(double v, double* buf) {
+    const int tid = threadIdx.x;
+    buf[tid] = v;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (tid < o) buf[tid] = fmax(buf[tid], buf[tid + o]);
+        __syncthreads();
+    }
+    const double r = buf[0];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ double block_reduce_sum(double v, double* buf) {   // fixed tree: reproducible
+    const int tid = threadIdx.x;
+    buf[tid] = v;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (tid < o) buf[tid] += buf[tid + o];
+        __syncthreads();
+    }
+    const double r = buf[0];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ long long block_reduce_sum_ll(long long v, long long* buf) {
+    const int tid = threadIdx.x;
+    buf[tid] = v;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (tid < o) buf[tid] += buf[tid + o];
+        __syncthreads();
+    }
+    const long long r = buf[0];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDev s) {
+    if (s.dyn->skip) return;
+    __shared__ double rbuf[B2N_NS_THREADS];
+    __shared__ unsigned int s_or;
+    long long* lbuf = reinterpret_cast<long long*>(rbuf);
+    const int tid = threadIdx.x, nth = blockDim.x;
+    NsScalars* sc = s.sc;
+    const int N = s.N, K = s.K, n = s.n;
+    const long long it0 = sc->it;
+    const double logvol0 = sc->logvol, lprev0 = sc->loglstar;
+    if (tid == 0) s_or = 0u;
+    __syncthreads();
+    // ---- dead-point rows out, chain end points in (slot of the j-th lowest <- chain j)
+    for (int e = tid; e < K * n; e += nth) {
+        const int j = e / n, i = e - j * n;
+        const size_t src = (size_t)s.sidx[j] * n + i;
+        const size_t dst = (size_t)(it0 + j) * n + i;
+        s.dead_u[dst] = s.live_u[src];
+        s.dead_v[dst] = s.live_v[src];
+        s.live_u[src] = s.o_u[e];
+        s.live_v[src] = s.o_v[e];
+    }
+    // ---- evidence: ln X_j = ln X_0 + ln((N-j)/(N+1)); trapezoid weight with dX_j = X_j / (N-j) * 1/2 ..
+    double wmax = -CUDART_INF, lnew = -CUDART_INF;
+    long long ncall = 0, ha = 0, hb = 0;
+    unsigned int fl = 0;
+    for (int j = tid; j < K; j += nth) {
+        const double L = s.slogl[j], Lp = j ? s.slogl[j - 1] : lprev0;
+        const double lv = logvol0 + log((double)(N - j) / (double)(N + 1));
+        const double w = dev_logaddexp(L, Lp) + lv + log(0.5 / (double)(N - j));
+        wmax = fmax(wmax, w);
+        s.dead_logl[it0 + j] = L;
+        s.dead_logvol[it0 + j] = lv;
+        s.dead_ncall[it0 + j] = s.o_ncall[j];
+        const double lo = s.o_logl[j];
+        s.live_logl[s.sidx[j]] = lo;
+        lnew = fmax(lnew, lo);
+        ncall += s.o_ncall[j];
+        ha += s.o_i0[j];
+        hb += s.o_i1[j];
+        if (s.sampler != 0) fl |= s.o_flags[j];
+    }
+    const double m = block_reduce_max(wmax, rbuf);
+    double se = 0.0;
+    for (int j = tid; j < K; j += nth) {
+        const double L = s.slogl[j], Lp = j ? s.slogl[j - 1] : lprev0;
+        const double lv = logvol0 + log((double)(N - j) / (double)(N + 1));
+        se += exp(dev_logaddexp(L, Lp) + lv + log(0.5 / (double)(N - j)) - m);
+    }
+    se = block_reduce_sum(se, rbuf);
+    lnew = block_reduce_max(lnew, rbuf);
+    ncall = block_reduce_sum_ll(ncall, lbuf);
+    ha = block_reduce_sum_ll(ha, lbuf);
+    hb = block_reduce_sum_ll(hb, lbuf);
+    if (fl) atomicOr(&s_or, fl);
+    __syncthreads();
+    if (tid == 0) {
+        sc->logz = dev_logaddexp(sc->logz, m + log(se));
+        sc->logvol = logvol0 + log((double)(N - K + 1) / (double)(N + 1));
+        sc->loglstar = s.slogl[K - 1];
+        sc->lmax = fmax(sc->lmax, lnew);
+        sc->it = it0 + K;
+        sc->ncall += ncall;
+        sc->round += 1;
+        // ---- tune (update=True every round: the queue of the round has drained, sampler.py:757-768)
+        sc->hist_a = ha;
+        sc->hist_b = hb;
+        if (s.sampler == 0) {                                // internal_samplers.py:460-493
+            const double facc = (double)ha / (double)(ha + hb);
+            sc->scale *= exp((facc - s.facc) / (double)s.nc / s.facc);
+        } else {                                             // tune_slice :1209-1239
+            if (s_or & B2N_WARN_DOUBLING) sc->doubling = 1;
+            const double ne = (double)(ha > 1 ? ha : 1), ncn = (double)hb;
+            sc->scale *= fmin(fmax(ne * 2.0 / (ne + ncn), 0.5), 2.0);
+            if (s_or & 0x80000000u) { sc->error = B2N_ERR_SLICE_FAIL; sc->done = 1; }
+        }
+        // ---- bound update due (sampler.py:648-651)
+        if (sc->ncall >= sc->ncall_last_update + s.update_interval) sc->need_bound = 1;
+    }
+}
+
+__global__ void ns_clear_kernel(NsScalars* sc, B2nDyn* dyn, int bound_updated) {
+    sc->need_bound = 0;
+    if (bound_updated) sc->ncall_last_update = sc->ncall;
+    dyn->skip = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int ns_alloc(b2n_ctx* ctx, b2n_ns* ns, void** p, size_t bytes) {
+    B2N_CUDA(ctx, cudaMalloc(p, bytes ? bytes : 8));
+    ns->allocs.push_back(*p);
+    return B2N_OK;
+}
+
+static int ns_alloc_dead(b2n_ctx* ctx, b2n_ns* ns, long long cap) {
+    // (re)allocate the dead-point arrays with room for `cap` rows, keeping the first `it` rows
+    NsDev& d = ns->d;
+    const size_t n = d.n;
+    void* nu[5];
+    const size_t bytes[5] = {(size_t)cap * n * 8, (size_t)cap * n * 8, (size_t)cap * 8, (size_t)cap * 8, (size_t)cap * 4};
+    for (int i = 0; i < 5; i++) B2N_CUDA(ctx, cudaMalloc(&nu[i], bytes[i] ? bytes[i] : 8));
+    if (ns->dead_alloc[0]) {
+        NsScalars h;
+        B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        B2N_CUDA(ctx, cudaMemcpy(&h, d.sc, sizeof(h), cudaMemcpyDeviceToHost));
+        const size_t rows = (size_t)std::min<long long>(h.it, ns->dead_cap);
+        const size_t keep[5] = {rows * n * 8, rows * n * 8, rows * 8, rows * 8, rows * 4};
+        for (int i = 0; i < 5; i++) {
+            if (keep[i]) B2N_CUDA(ctx, cudaMemcpy(nu[i], ns->dead_alloc[i], keep[i], cudaMemcpyDeviceToDevice));
+            cudaFree(ns->dead_alloc[i]);
+        }
+    }
+    for (int i = 0; i < 5; i++) ns->dead_alloc[i] = nu[i];
+    d.dead_u = (double*)nu[0]; d.dead_v = (double*)nu[1]; d.dead_logl = (double*)nu[2];
+    d.dead_logvol = (double*)nu[3]; d.dead_ncall = (int*)nu[4];
+    ns->dead_cap = cap;
+    d.dead_cap = cap;
+    return B2N_OK;
+}
+
+void b2n_ns_release(b2n_ctx* ctx) {
+    if (!ctx || !ctx->ns) return;
+    for (void* p : ctx->ns->allocs) cudaFree(p);
+    for (void* p : ctx->ns->dead_alloc) if (p) cudaFree(p);
+    delete ctx->ns;
+    ctx->ns = nullptr;
+}
+
+// one chain-entry call in device-paced mode (plan_only: just report chains_per_cta)
+static int ns_chain_call(b2n_ctx* ctx, b2n_ns* ns, bool plan_only) {
+    NsDev& d = ns->d;
+    b2n_chain_args a;
+    memset(&a, 0, sizeof(a));
+    a.nchain = d.K; a.ndim = d.n; a.ncdim = d.nc; a.model_id = ns->cfg.model_id;
+    a.u0 = d.u0; a.ell = nullptr; a.dimflags = ns->has_flags ? ns->dimflags.data() : nullptr;
+    a.seed = d.seed;
+    const int mode = ctx->ptr_mode;
+    ctx->ptr_mode = B2N_PTR_DEVICE;
+    ctx->dyn.active = true;
+    ctx->dyn.plan_only = plan_only;
+    ctx->dyn.dev = d.dyn; ctx->dyn.order = d.order; ctx->dyn.cta = d.cta;
+    ctx->dyn.max_cta = d.cpc > 0 ? d.K / d.cpc + d.Kell : 1;
+    int st;
+    if (d.sampler == 0)
+        st = b2n_rwalk_batch(ctx, &a, ns->cfg.steps, d.o_u, d.o_v, d.o_logl, d.o_i0, d.o_i1, d.o_ncall);
+    else if (d.sampler == 1)
+        st = b2n_rslice_batch(ctx, &a, ns->cfg.steps, 0, d.o_u, d.o_v, d.o_logl, d.o_i0, d.o_i1, d.o_ncall, d.o_flags);
+    else
+        st = b2n_slice_batch(ctx, &a, ns->cfg.steps, 0, d.o_u, d.o_v, d.o_logl, d.o_i0, d.o_i1, d.o_ncall, d.o_flags);
+    ctx->dyn.active = false;
+    ctx->dyn.plan_only = false;
+    ctx->ptr_mode = mode;
+    return st;
+}
+
+static size_t ns_propose_smem(const NsDev& d) {
+    return (size_t)d.Npad * 8 + (size_t)32 * d.nc * 8 + (size_t)((d.Kell + 1) & ~1) * 8 + (size_t)d.Npad * 4 +
+           (size_t)d.K * 8 + (size_t)(d.Kell + 2) * 4 + 64;
+}
+
+extern "C" {
+
+int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* c, int64_t dead_capacity) {
+    if (!ctx || !c) return B2N_ERR_ARG;
+    if (c->model_id < 0 || c->model_id >= (int)ctx->models.size()) return B2N_ERR_ARG;
+    const int n = ctx->models[c->model_id].ndim;
+    if (c->ndim != n || c->nlive < 2 || c->batch < 1 || c->batch >= c->nlive || c->steps < 1 || c->sampler < 0 ||
+        c->sampler > 2 || c->ncdim < 1 || c->ncdim > n)
+        return b2n_fail(ctx, B2N_ERR_ARG, "b2n_ns_create: need 1 <= batch < nlive, steps >= 1, sampler in {0,1,2}, ndim == model ndim");
+    if (c->sampler != 0 && c->ncdim != n) return b2n_fail(ctx, B2N_ERR_ARG, "slice samplers need ncdim == ndim");
+    int Npad = 2;
+    while (Npad < c->nlive) Npad <<= 1;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    b2n_ns_release(ctx);
+    b2n_ns* ns = new b2n_ns();
+    ctx->ns = ns;
+    ns->cfg = *c;
+    if (c->dimflags) { ns->dimflags.assign(c->dimflags, c->dimflags + n); ns->has_flags = true; }
+    ns->cfg.dimflags = nullptr;
+    NsDev& d = ns->d;
+    memset(&d, 0, sizeof(d));
+    d.N = c->nlive; d.n = n; d.nc = c->ncdim; d.K = c->batch; d.Kell = 1; d.strict = 1; d.sampler = c->sampler;
+    d.Npad = Npad;
+    d.dlogz = c->dlogz; d.facc = c->facc; d.maxiter = c->maxiter; d.maxcall = c->maxcall;
+    d.update_interval = c->update_interval; d.seed = c->seed; d.chain0 = c->chain0;
+    const size_t N = d.N, K = d.K;
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.live_u, N * n * 8));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.live_v, N * n * 8));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.live_logl, N * 8));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.sc, sizeof(NsScalars)));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.dyn, sizeof(B2nDyn)));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.sidx, N * 4));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.slogl, K * 8));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.u0, K * n * 8));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.order, K * 4));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.cta, (K + N + 8) * sizeof(int3)));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_u, K * n * 8));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_v, K * n * 8));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_logl, K * 8));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_i0, K * 4));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_i1, K * 4));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_ncall, K * 4));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_flags, K * 4));
+    B2N_CUDA(ctx, cudaMemset(d.sc, 0, sizeof(NsScalars)));
+    B2N_CUDA(ctx, cudaMemset(d.dyn, 0, sizeof(B2nDyn)));
+    B2N_TRY(ns_alloc_dead(ctx, ns, std::max<int64_t>(dead_capacity, (int64_t)K)));
+    return B2N_OK;
+}
+
+int b2n_ns_destroy(b2n_ctx* ctx) {
+    if (!ctx) return B2N_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    b2n_ns_release(ctx);
+    return B2N_OK;
+}
+
+int b2n_ns_set_state(b2n_ctx* ctx, const double* live_u, const double* live_v, const double* live_logl,
+                     double logvol, double logz, double loglstar, int64_t it, int64_t ncall, double scale) {
+    if (!ctx || !ctx->ns || !live_u || !live_v || !live_logl) return B2N_ERR_ARG;
+    b2n_ns* ns = ctx->ns;
+    NsDev& d = ns->d;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t N = d.N, n = d.n;
+    B2N_CUDA(ctx, cudaMemcpy(d.live_u, live_u, N * n * 8, cudaMemcpyHostToDevice));
+    B2N_CUDA(ctx, cudaMemcpy(d.live_v, live_v, N * n * 8, cudaMemcpyHostToDevice));
+    B2N_CUDA(ctx, cudaMemcpy(d.live_logl, live_logl, N * 8, cudaMemcpyHostToDevice));
+    NsScalars h;
+    memset(&h, 0, sizeof(h));
+    h.it = 0;                       // rows of the device dead buffer; the caller keeps its own offset
+    (void)it;
+    h.ncall = ncall; h.ncall_last_update = ncall;
+    h.logvol = logvol; h.logz = logz; h.loglstar = loglstar; h.scale = scale;
+    h.lmax = -1e300; h.delta_logz = 1e300;
+    B2N_CUDA(ctx, cudaMemcpy(d.sc, &h, sizeof(h), cudaMemcpyHostToDevice));
+    B2N_CUDA(ctx, cudaMemset(d.dyn, 0, sizeof(B2nDyn)));
+    return B2N_OK;
+}
+
+static int ns_status(b2n_ctx* ctx, b2n_ns_status* out) {
+    NsScalars* h = reinterpret_cast<NsScalars*>(ctx->pinned);
+    B2N_CUDA(ctx, cudaMemcpyAsync(h, ctx->ns->d.sc, sizeof(NsScalars), cudaMemcpyDeviceToHost, ctx->stream));
+    B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out) {
+        out->it = h->it; out->ncall = h->ncall; out->rounds = h->round;
+        out->logz = h->logz; out->logvol = h->logvol; out->loglstar = h->loglstar; out->lmax = h->lmax;
+        out->delta_logz = h->delta_logz; out->scale = h->scale;
+        out->done = h->done; out->need_bound = h->need_bound; out->doubling = h->doubling; out->error = h->error;
+    }
+    return B2N_OK;
+}
+
+int b2n_ns_status_get(b2n_ctx* ctx, b2n_ns_status* out) {
+    if (!ctx || !ctx->ns || !out) return B2N_ERR_ARG;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ns_status(ctx, out);
+}
+
+int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_status* out) {
+    if (!ctx || !ctx->ns || max_rounds < 0) return B2N_ERR_ARG;
+    b2n_ns* ns = ctx->ns;
+    NsDev& d = ns->d;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->bK < 1 || ctx->bn != d.nc) return b2n_fail(ctx, B2N_ERR_ARG, "resident bound missing or of wrong dimension (b2n_bound_set)");
+    if (!ctx->b_ctrs.p || !ctx->b_ams.p || !ctx->b_logvols.p || ctx->h_logvols.empty())
+        return b2n_fail(ctx, B2N_ERR_ARG, "b2n_ns_run needs the full resident bound (ctrs, ams, logvols)");
+    if (ctx->peer.total > 0) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "b2n_ns_run: gather mode must be off");
+    d.Kell = ctx->bK;
+    d.strict = ns->cfg.strict_contains;
+    d.ctrs = ctx->b_ctrs.as<double>(); d.ams = ctx->b_ams.as<double>(); d.logvols = ctx->b_logvols.as<double>();
+    if ((size_t)d.K / 1 + (size_t)d.Kell + 8 > (size_t)d.K + (size_t)d.N + 8)
+        return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "too many ellipsoids for the round worklist");
+    B2N_TRY(ns_chain_call(ctx, ns, true));               // chains per CTA the chain kernel plans for
+    d.cpc = ctx->dyn.cpc;
+    const size_t smem = ns_propose_smem(d);
+    if (smem > (size_t)ctx->max_smem_optin) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "nlive too large for the one-CTA sort of b2n_ns_run");
+    B2N_CUDA(ctx, cudaFuncSetAttribute(ns_propose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (check_every < 1) check_every = max_rounds > 0 ? max_rounds : 1;
+    int left = max_rounds;
+    b2n_ns_status st;
+    memset(&st, 0, sizeof(st));
+    while (left > 0) {
+        const int chunk = std::min(left, (int)check_every);
+        for (int r = 0; r < chunk; r++) {
+            ns_propose_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d);
+            B2N_LAUNCH_CHECK(ctx);
+            B2N_TRY(ns_chain_call(ctx, ns, false));
+            ns_commit_kernel<<<1, B2N_NS_THREADS, 0, ctx->stream>>>(d);
+            B2N_LAUNCH_CHECK(ctx);
+        }
+        left -= chunk;
+        B2N_TRY(ns_status(ctx, &st));
+        if (st.done || st.need_bound) break;
+    }
+    if (max_rounds == 0) B2N_TRY(ns_status(ctx, &st));
+    if (out) *out = st;
+    if (st.error) return st.error;
+    return B2N_OK;
+}
+
+int b2n_ns_bound_updated(b2n_ctx* ctx) {
+    if (!ctx || !ctx->ns) return B2N_ERR_ARG;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    ns_clear_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ns->d.sc, ctx->ns->d.dyn, 1);
+    B2N_LAUNCH_CHECK(ctx);
+    return B2N_OK;
+}
+
+int b2n_ns_reserve_dead(b2n_ctx* ctx, int64_t capacity) {
+    if (!ctx || !ctx->ns) return B2N_ERR_ARG;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (capacity > ctx->ns->dead_cap) B2N_TRY(ns_alloc_dead(ctx, ctx->ns, capacity));
+    ns_clear_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ns->d.sc, ctx->ns->d.dyn, 0);   // clears need_bound == 3
+    B2N_LAUNCH_CHECK(ctx);
+    return B2N_OK;
+}
+
+int b2n_ns_get_live(b2n_ctx* ctx, double* live_u, double* live_v, double* live_logl) {
+    if (!ctx || !ctx->ns) return B2N_ERR_ARG;
+    NsDev& d = ctx->ns->d;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t N = d.N, n = d.n;
+    if (live_u) B2N_CUDA(ctx, cudaMemcpy(live_u, d.live_u, N * n * 8, cudaMemcpyDeviceToHost));
+    if (live_v) B2N_CUDA(ctx, cudaMemcpy(live_v, d.live_v, N * n * 8, cudaMemcpyDeviceToHost));
+    if (live_logl) B2N_CUDA(ctx, cudaMemcpy(live_logl, d.live_logl, N * 8, cudaMemcpyDeviceToHost));
+    return B2N_OK;
+}
+
+int b2n_ns_get_dead(b2n_ctx* ctx, int64_t first, int64_t count, double* u, double* v, double* logl,
+                    double* logvol, int32_t* ncall) {
+    if (!ctx || !ctx->ns || first < 0 || count < 0) return B2N_ERR_ARG;
+    NsDev& d = ctx->ns->d;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (first + count > ctx->ns->dead_cap) return B2N_ERR_ARG;
+    const size_t n = d.n, f = (size_t)first, c = (size_t)count;
+    if (c == 0) return B2N_OK;
+    if (u) B2N_CUDA(ctx, cudaMemcpy(u, d.dead_u + f * n, c * n * 8, cudaMemcpyDeviceToHost));
+    if (v) B2N_CUDA(ctx, cudaMemcpy(v, d.dead_v + f * n, c * n * 8, cudaMemcpyDeviceToHost));
+    if (logl) B2N_CUDA(ctx, cudaMemcpy(logl, d.dead_logl + f, c * 8, cudaMemcpyDeviceToHost));
+    if (logvol) B2N_CUDA(ctx, cudaMemcpy(logvol, d.dead_logvol + f, c * 8, cudaMemcpyDeviceToHost));
+    if (ncall) B2N_CUDA(ctx, cudaMemcpy(ncall, d.dead_ncall + f, c * 4, cudaMemcpyDeviceToHost));
+    return B2N_OK;
+}
+
+}  // extern "C"

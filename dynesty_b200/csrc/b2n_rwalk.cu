@@ -39,13 +39,25 @@ struct RwalkParams {
     double *u, *v, *logl;
     int *nacc, *nrej, *ncall;
     PeerSet peer;          // fused multi-GPU gather of the outputs (b2n_peer.cu); world == 0: off
+    const B2nDyn* dyn;     // device-paced launch (b2n_ns.cu): threshold / scale / chain ids / CTA count in HBM
 };
+
+// Per-launch scalars: kernel arguments, or -- device-paced -- the B2nDyn the previous kernel on
+// the stream wrote (a skipped round or a CTA beyond the round's worklist returns at once).
+#define B2N_DYN_PROLOGUE(p)                                                                  \
+    double loglstar_ = (p).loglstar, scale_ = (p).scale;                                     \
+    unsigned long long chain0_ = (p).chain0;                                                 \
+    if ((p).dyn) {                                                                           \
+        if ((p).dyn->skip || (int)blockIdx.x >= (p).dyn->ncta) return;                       \
+        loglstar_ = (p).dyn->loglstar; scale_ = (p).dyn->scale; chain0_ = (p).dyn->chain0;   \
+    }
 
 template <int LIKE, bool AX_SMEM, bool PREC_SMEM>
 __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
     const int n = p.n, nc = p.nc;
     const int npad = (n + 1) & ~1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    B2N_DYN_PROLOGUE(p)
     const int3 cd = p.cta[blockIdx.x];
     // ---- shared-memory plan (all offsets in doubles, all even)
     int off = 0;
@@ -89,7 +101,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
     for (int c = warp; c < cd.y; c += nwarps) {
         const int q = p.order[cd.x + c];
         ChainRng g;
-        g.init(p.seed, p.chain0 + (uint64_t)q);
+        g.init(p.seed, chain0_ + (uint64_t)q);
         for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)q * n + i];
         __syncwarp();
         int nacc = 0, nrej = 0;
@@ -107,7 +119,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
                 g.tick++;
             }
             // (2) uniform point in the unit nc-ball
-            const double fac = p.scale * ball_direction(g, ox, nc, lane, inv_nc);
+            const double fac = scale_ * ball_direction(g, ox, nc, lane, inv_nc);
             __syncwarp();
             // (3) u' = u + fac * axes @ z on the clustered dims, (4) wrap / reflect / cube test,
             //     and (speculatively) the prior transform of the rows this lane owns
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
             } else {
                 l = loglike_sm<LIKE, PREC_SMEM>(p.m, ms, Pg, offP, ldP, n, ovprop, od, lane);
             }
-            if (l > p.loglstar) {
+            if (l > loglstar_) {
                 int t = oucur; oucur = ouprop; ouprop = t;
                 t = ovcur; ovcur = ovprop; ovprop = t;
                 lcur = l;
@@ -204,7 +216,11 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 
 // KT = k-tiles of 4 columns (n <= 4*KT); CH = chains in lock-step per CTA (8 -> 256 threads, two
 // CTAs per SM overlap each other's barriers: measured 1.3x faster than one 16-chain CTA per SM)
-template <int LIKE, int KT, int CH>
+// DU = direction look-ahead: the draws of a step do not depend on the chain state (the Philox
+// counter is a function of (chain, tick) only), so a chain warp generates the directions of DU
+// consecutive steps in ONE straight-line block -- DU independent Philox / log / sincospi
+// dependency chains interleaved by the compiler -- instead of one latency-bound chain per step.
+template <int LIKE, int KT, int CH, int DU>
 __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(const RwalkParams p) {
     constexpr int B2N_MMA_CH = CH;
     constexpr int RS = 8 * ((4 * KT + 7) / 8);                    // rows padded to whole 8-row slabs
@@ -214,6 +230,7 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
     const int n = p.n;
     const int npad = (n + 1) & ~1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    B2N_DYN_PROLOGUE(p)
     const int3 cd = p.cta[blockIdx.x];
     const int S = (n + 7) >> 3;                     // 8-row slabs
     // ---- shared-memory plan
@@ -224,11 +241,12 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
     uint32_t* fl = reinterpret_cast<uint32_t*>(&b2n_sm[off]);
     for (int i = threadIdx.x; i < n; i += blockDim.x) fl[i] = p.dimflags ? p.dimflags[i] : 0u;
     off += ((n + 3) >> 2) << 1;
-    const int oX = off;  off += B2N_MMA_CH * XS;    // direction z, later delta = v - mean (chain-major)
+    constexpr int XB = B2N_MMA_CH * XS;             // one direction buffer (all chains of the CTA)
+    const int oX = off;  off += DU * XB;            // DU x: direction z, later delta = v - mean (chain-major)
     const int oY = off;  off += B2N_MMA_CH * YS;    // axes @ z (chain-major)
     const int oQ = off;  off += 8 * B2N_MMA_CH;     // per-slab partial quadratic forms
     const int ost = off;                            // per-chain state: ucur, uprop, vcur, vprop
-    for (int e = threadIdx.x; e < B2N_MMA_CH * XS; e += blockDim.x) b2n_sm[oX + e] = 0.0;
+    for (int e = threadIdx.x; e < DU * XB; e += blockDim.x) b2n_sm[oX + e] = 0.0;
     // ---- matrix fragments -> registers.  item (s, t): slab s of rows, chain tile t
     const int s_it = warp % S, t_it = warp / S;
     const bool has_item = warp < (CH / 8) * S && t_it < CH / 8;
@@ -254,23 +272,44 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
         const bool live = g0 + c < cd.y;
         const int q = live ? p.order[cd.x + g0 + c] : 0;
         int oucur = ost + c * 4 * npad, ouprop = oucur + npad, ovcur = ouprop + npad, ovprop = ovcur + npad;
-        const int ox = oX + c * XS, oy = oY + c * YS;
+        const int oy = oY + c * YS;
         ChainRng g;
-        g.init(p.seed, p.chain0 + (uint64_t)q);
+        g.init(p.seed, chain0_ + (uint64_t)q);
         if (live)
             for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)q * n + i];
         int nacc = 0, nrej = 0;
         double lcur = 0.0;
         __syncthreads();
-        for (int step = 0; step < p.walks; step++) {
-            // ---- phase 1 (chain warp): direction in the unit ball -> X[c]
-            double fac = 0.0;
-            if (live) fac = p.scale * ball_direction(g, ox, n, lane, inv_n);
+        for (int step0 = 0; step0 < p.walks; step0 += DU) {
+            // ---- phase 1 (chain warp): directions in the unit ball of the next DU steps -> X[s][c]
+            double facs[DU];
+            if (live) {
+                int offx[DU];
+#pragma unroll
+                for (int s = 0; s < DU; s++) offx[s] = oX + s * XB + c * XS;
+                const int left = p.walks - step0;
+                if (n <= 62) {
+                    ball_directions<DU>(g, offx, left < DU ? left : DU, n, lane, inv_n, facs);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < DU; s++) facs[s] = s < left ? ball_direction(g, offx[s], n, lane, inv_n) : 0.0;
+                }
+#pragma unroll
+                for (int s = 0; s < DU; s++) facs[s] *= scale_;
+            } else {
+#pragma unroll
+                for (int s = 0; s < DU; s++) facs[s] = 0.0;
+            }
+#pragma unroll
+            for (int s = 0; s < DU; s++) {
+            if (step0 + s >= p.walks) break;                 // CTA-uniform
+            const int oXs = oX + s * XB, ox = oXs + c * XS;
+            const double fac = facs[s];
             __syncthreads();
             // ---- phase 2 (item warp): Y[rows of slab][chains of tile] = A_slab @ X
             if (has_item) {
                 double d0 = 0.0, d1 = 0.0;
-                const int xb = oX + (8 * t_it + (lane >> 2)) * XS + (lane & 3);
+                const int xb = oXs + (8 * t_it + (lane >> 2)) * XS + (lane & 3);
 #pragma unroll
                 for (int kt = 0; kt < KT; kt++) dmma884(d0, d1, fragA[kt], b2n_sm[xb + 4 * kt]);
                 const int row = 8 * s_it + (lane >> 2), c0 = 8 * t_it + 2 * (lane & 3);
@@ -300,11 +339,11 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
                 // ---- phase 4 (item warp): partial delta^T P delta over the rows of the slab
                 if (has_item) {
                     double d0 = 0.0, d1 = 0.0;
-                    const int xb = oX + (8 * t_it + (lane >> 2)) * XS + (lane & 3);
+                    const int xb = oXs + (8 * t_it + (lane >> 2)) * XS + (lane & 3);
 #pragma unroll
                     for (int kt = 0; kt < KT; kt++) dmma884(d0, d1, fragP[kt], b2n_sm[xb + 4 * kt]);
                     const int row = 8 * s_it + (lane >> 2), c0 = 8 * t_it + 2 * (lane & 3);
-                    double q0 = d0 * b2n_sm[oX + c0 * XS + row], q1 = d1 * b2n_sm[oX + (c0 + 1) * XS + row];
+                    double q0 = d0 * b2n_sm[oXs + c0 * XS + row], q1 = d1 * b2n_sm[oXs + (c0 + 1) * XS + row];
 #pragma unroll
                     for (int o = 4; o < 32; o <<= 1) {
                         q0 += __shfl_xor_sync(B2N_FULL, q0, o);
@@ -327,7 +366,7 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
             if (live) {
                 if (!ok) {
                     nrej++;
-                } else if (l > p.loglstar) {
+                } else if (l > loglstar_) {
                     int t = oucur; oucur = ouprop; ouprop = t;
                     t = ovcur; ovcur = ovprop; ovprop = t;
                     lcur = l;
@@ -336,6 +375,7 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
                     nrej++;
                 }
             }
+            }   // s
         }
         if (live) {
             if (nacc == 0) {   // recompute (v, logl) of the start point (:970-975), warp-local
@@ -357,7 +397,7 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
         }
         __syncthreads();
         // X rows of chains that are not live in the next group must read as zero
-        for (int e = threadIdx.x; e < B2N_MMA_CH * XS; e += blockDim.x) b2n_sm[oX + e] = 0.0;
+        for (int e = threadIdx.x; e < DU * XB; e += blockDim.x) b2n_sm[oX + e] = 0.0;
         __syncthreads();
     }
     peer_finish(p.peer);
@@ -378,6 +418,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_mmas_kernel(const RwalkParams p,
     const int n = p.n;
     const int npad = (n + 1) & ~1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    B2N_DYN_PROLOGUE(p)
     const int3 cd = p.cta[blockIdx.x];
     const int S = (n + 7) >> 3, KT = (n + 3) >> 2;
     int off = 0;
@@ -406,7 +447,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_mmas_kernel(const RwalkParams p,
         int oucur = ost + c * 4 * npad, ouprop = oucur + npad, ovcur = ouprop + npad, ovprop = ovcur + npad;
         const int ox = oX + c * XS, oy = oY + c * YS;
         ChainRng g;
-        g.init(p.seed, p.chain0 + (uint64_t)q);
+        g.init(p.seed, chain0_ + (uint64_t)q);
         if (live)
             for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)q * n + i];
         int nacc = 0, nrej = 0;
@@ -414,7 +455,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_mmas_kernel(const RwalkParams p,
         __syncthreads();
         for (int step = 0; step < p.walks; step++) {
             double fac = 0.0;
-            if (live) fac = p.scale * ball_direction(g, ox, n, lane, inv_n);
+            if (live) fac = scale_ * ball_direction(g, ox, n, lane, inv_n);
             __syncthreads();
             // ---- Y = A X, fragments of A streamed from L2
             for (int s = warp; s < S; s += CH) {
@@ -496,7 +537,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_mmas_kernel(const RwalkParams p,
             if (live) {
                 if (!ok) {
                     nrej++;
-                } else if (l > p.loglstar) {
+                } else if (l > loglstar_) {
                     int t = oucur; oucur = ouprop; ouprop = t;
                     t = ovcur; ovcur = ovprop; ovprop = t;
                     lcur = l;
@@ -607,6 +648,9 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         use_mma = true;
     }
     const int KT = n <= 32 ? 8 : (n <= 52 ? 13 : 16);
+    // direction look-ahead of the lock-step kernel (B2N_RWALK_DU=1|2|4: experiments; results identical)
+    int DU = 1;
+    if (const char* e = getenv("B2N_RWALK_DU")) DU = (atoi(e) == 2) ? 2 : (atoi(e) == 4 ? 4 : 1);
     size_t mma_smem = 0;
     if (use_mma) {
         const int ctas = 2 * ctx->sm_count;                 // 8-chain CTAs, two resident per SM
@@ -614,7 +658,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         warps = 8;
         const int RS = 8 * ((4 * KT + 7) / 8);
         const int XS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16)), YS = RS + 2;
-        mma_smem = (size_t)(4 * npad + (((n + 3) >> 2) << 1) + 8 * XS + 8 * YS + 8 * 8 + 8 * 4 * npad) * sizeof(double);
+        mma_smem = (size_t)(4 * npad + (((n + 3) >> 2) << 1) + DU * 8 * XS + 8 * YS + 8 * 8 + 8 * 4 * npad) * sizeof(double);
     }
     // large n: lock-step kernel with matrix fragments streamed from L2 (16 chains share each load)
     bool use_mmas = false;
@@ -641,18 +685,29 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     const bool pr_s = pr_b > 0 && fixed + (ax_s ? ax_b : 0) + pr_b <= limit;
     const size_t smem = (use_mma || use_mmas) ? mma_smem : fixed + (ax_s ? ax_b : 0) + (pr_s ? pr_b : 0);
 
+    const bool dyn = ctx->dyn.active;        // device-paced launch (b2n_ns.cu): worklist + scalars in HBM
+    if (dyn) {
+        ctx->dyn.cpc = chains_per_cta;
+        if (ctx->dyn.plan_only) return B2N_OK;
+        if (gather || ctx->ptr_mode != B2N_PTR_DEVICE) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "device-paced launch needs device pointers and no gather mode");
+    }
     std::vector<int> order;
     std::vector<int3> cta;
-    B2N_TRY(b2n_build_worklist(ctx, Q, a->ell, ctx->bK, chains_per_cta, order, cta));
+    if (!dyn) B2N_TRY(b2n_build_worklist(ctx, Q, a->ell, ctx->bK, chains_per_cta, order, cta));
 
     RwalkParams p;
+    p.dyn = dyn ? ctx->dyn.dev : nullptr;
     p.m = m; p.n = n; p.nc = nc; p.walks = walks; p.ldA = ldA; p.ldP = ldP;
     p.loglstar = a->loglstar; p.scale = a->scale; p.seed = a->seed; p.chain0 = a->chain0;
     p.axesT = ctx->b_axesT.as<double>();
     const void *du0, *dorder, *dcta, *dfl = nullptr;
     B2N_TRY(b2n_in(ctx, ctx->in0, a->u0, (size_t)Q * n * sizeof(double), &du0));
-    B2N_TRY(b2n_in_host(ctx, ctx->work0, order.data(), order.size() * sizeof(int), &dorder));
-    B2N_TRY(b2n_in_host(ctx, ctx->work1, cta.data(), cta.size() * sizeof(int3), &dcta));
+    if (dyn) {
+        dorder = ctx->dyn.order; dcta = ctx->dyn.cta;
+    } else {
+        B2N_TRY(b2n_in_host(ctx, ctx->work0, order.data(), order.size() * sizeof(int), &dorder));
+        B2N_TRY(b2n_in_host(ctx, ctx->work1, cta.data(), cta.size() * sizeof(int3), &dcta));
+    }
     std::vector<uint32_t> fl;
     if (a->dimflags) {
         fl.assign(a->dimflags, a->dimflags + n);
@@ -678,7 +733,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     p.u = (double*)du; p.v = (double*)dv; p.logl = (double*)dl;
     p.nacc = (int*)dna; p.nrej = (int*)dnr; p.ncall = (int*)dncl;
 
-    const unsigned grid = (unsigned)cta.size();
+    const unsigned grid = dyn ? (unsigned)ctx->dyn.max_cta : (unsigned)cta.size();
 #define LAUNCH(L, AXS, PRS)                                                                       \
     do {                                                                                          \
         B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_kernel<L, AXS, PRS>,                             \
@@ -690,16 +745,20 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     else if (ax_s) LAUNCH(L, true, false);                             \
     else if (pr_s) LAUNCH(L, false, true);                             \
     else LAUNCH(L, false, false);
-#define LAUNCH_MMA(L, K)                                                                            \
+#define LAUNCH_MMA2(L, K, D)                                                                         \
     do {                                                                                            \
-        B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_mma_kernel<L, K, 8>,                                \
+        B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_mma_kernel<L, K, 8, D>,                             \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        rwalk_mma_kernel<L, K, 8><<<grid, 256, smem, ctx->stream>>>(p);                              \
+        rwalk_mma_kernel<L, K, 8, D><<<grid, 256, smem, ctx->stream>>>(p);                           \
     } while (0)
+#define LAUNCH_MMA(L, K)                 \
+    if (DU == 2) LAUNCH_MMA2(L, K, 2);   \
+    else if (DU == 4) LAUNCH_MMA2(L, K, 4); \
+    else LAUNCH_MMA2(L, K, 1);
 #define CALL_MMA(L)                      \
-    if (KT == 8) LAUNCH_MMA(L, 8);       \
-    else if (KT == 13) LAUNCH_MMA(L, 13); \
-    else LAUNCH_MMA(L, 16);
+    if (KT == 8) { LAUNCH_MMA(L, 8) }    \
+    else if (KT == 13) { LAUNCH_MMA(L, 13) } \
+    else { LAUNCH_MMA(L, 16) }
 #define CALL_MMAS(L)                                                                                  \
     B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_mmas_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        (int)smem));                                                  \
@@ -716,6 +775,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
 #undef CALL_MMAS
 #undef CALL_MMA
 #undef LAUNCH_MMA
+#undef LAUNCH_MMA2
 #undef CALL
 #undef LAUNCH
     B2N_LAUNCH_CHECK(ctx);

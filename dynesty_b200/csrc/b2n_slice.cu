@@ -33,6 +33,7 @@ struct SliceParams {
     int *nexp, *ncon, *ncall;
     uint32_t* flags;
     PeerSet peer;          // fused multi-GPU gather of the outputs (b2n_peer.cu)
+    const B2nDyn* dyn;     // device-paced launch (b2n_ns.cu)
 };
 
 // F(x) of generic_slice_step (:1112-1123): logl(u + x d) or -inf outside the unit cube.
@@ -142,6 +143,13 @@ __global__ void __launch_bounds__(512, 1) slice_kernel(const SliceParams p) {
     const int n = p.n;
     const int npad = (n + 1) & ~1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    double loglstar_ = p.loglstar, scale_ = p.scale;
+    unsigned long long chain0_ = p.chain0;
+    int doubling_ = p.doubling;
+    if (p.dyn) {      // device-paced: scalars written by the previous kernel on the stream
+        if (p.dyn->skip || (int)blockIdx.x >= p.dyn->ncta) return;
+        loglstar_ = p.dyn->loglstar; scale_ = p.dyn->scale; chain0_ = p.dyn->chain0; doubling_ = p.dyn->doubling;
+    }
     const int3 cd = p.cta[blockIdx.x];
     int off = 0;
     const double* Ag = p.axesT + (size_t)cd.z * n * n;
@@ -169,12 +177,12 @@ __global__ void __launch_bounds__(512, 1) slice_kernel(const SliceParams p) {
     for (int c = warp; c < cd.y; c += nwarps) {
         const int q = p.order[cd.x + c];
         ChainRng g;
-        g.init(p.seed, p.chain0 + (uint64_t)q);
+        g.init(p.seed, chain0_ + (uint64_t)q);
         for (int i = lane; i < n; i += 32) b2n_sm[ou + i] = p.u0[(size_t)q * n + i];
         __syncwarp();
         SliceEval<LIKE, PREC_SMEM> F{p.m, ms, Pg, offP, ldP, ou, odir, oun, ovn, owork, lane, n, pk, 0};
         int nexp = 0, ncon = 0, err = 0;
-        bool doubling = p.doubling != 0, warned = false;
+        bool doubling = doubling_ != 0, warned = false;
         double lcur = 0.0;
         for (int sl = 0; sl < p.slices && !err; sl++) {
             const int nsub = RANDOM_DIR ? 1 : n;
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__(512, 1) slice_kernel(const SliceParams p) {
                 if (RANDOM_DIR) {
                     // drhat = z / |z| ; direction = axes @ drhat * scale (:820-824)
                     const double ssq = normals_sm(g, owork, n, lane);
-                    const double fac = p.scale / sqrt(ssq);
+                    const double fac = scale_ / sqrt(ssq);
                     __syncwarp();
                     for (int base = 0; base < n; base += 64) {
                         double y0, y1;
@@ -212,11 +220,11 @@ __global__ void __launch_bounds__(512, 1) slice_kernel(const SliceParams p) {
                 } else {
                     // axes = scale * axes.T ; axis = axes[idx] (:665, 680) = column idx of the axes matrix
                     const int idx = idxs[sub];
-                    for (int i = lane; i < n; i += 32) b2n_sm[odir + i] = p.scale * mat_ld<AX_SMEM>(Ag, offA + idx * ldA + i);
+                    for (int i = lane; i < n; i += 32) b2n_sm[odir + i] = scale_ * mat_ld<AX_SMEM>(Ag, offA + idx * ldA + i);
                 }
                 __syncwarp();
                 bool ew = false;
-                const double l = slice_step(F, g, p.loglstar, doubling, nexp, ncon, ew, err);
+                const double l = slice_step(F, g, loglstar_, doubling, nexp, ncon, ew, err);
                 if (err) break;
                 lcur = l;
                 for (int i = lane; i < n; i += 32) b2n_sm[ou + i] = b2n_sm[oun + i];     // u = u_prop
@@ -280,17 +288,28 @@ static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slice
     const bool ax_s = fixed + ax_b <= limit;
     const bool pr_s = pr_b > 0 && fixed + (ax_s ? ax_b : 0) + pr_b <= limit;
     const size_t smem = fixed + (ax_s ? ax_b : 0) + (pr_s ? pr_b : 0);
+    const bool dyn = ctx->dyn.active;        // device-paced launch (b2n_ns.cu)
+    if (dyn) {
+        ctx->dyn.cpc = chains_per_cta;
+        if (ctx->dyn.plan_only) return B2N_OK;
+        if (gather || ctx->ptr_mode != B2N_PTR_DEVICE) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "device-paced launch needs device pointers and no gather mode");
+    }
     std::vector<int> order;
     std::vector<int3> cta;
-    B2N_TRY(b2n_build_worklist(ctx, Q, a->ell, ctx->bK, chains_per_cta, order, cta));
+    if (!dyn) B2N_TRY(b2n_build_worklist(ctx, Q, a->ell, ctx->bK, chains_per_cta, order, cta));
     SliceParams p;
+    p.dyn = dyn ? ctx->dyn.dev : nullptr;
     p.m = m; p.n = n; p.slices = slices; p.doubling = doubling; p.ldA = ldA; p.ldP = ldP;
     p.loglstar = a->loglstar; p.scale = a->scale; p.seed = a->seed; p.chain0 = a->chain0;
     p.axesT = ctx->b_axesT.as<double>();
     const void *du0, *dorder, *dcta;
     B2N_TRY(b2n_in(ctx, ctx->in0, a->u0, (size_t)Q * n * sizeof(double), &du0));
-    B2N_TRY(b2n_in_host(ctx, ctx->work0, order.data(), order.size() * sizeof(int), &dorder));
-    B2N_TRY(b2n_in_host(ctx, ctx->work1, cta.data(), cta.size() * sizeof(int3), &dcta));
+    if (dyn) {
+        dorder = ctx->dyn.order; dcta = ctx->dyn.cta;
+    } else {
+        B2N_TRY(b2n_in_host(ctx, ctx->work0, order.data(), order.size() * sizeof(int), &dorder));
+        B2N_TRY(b2n_in_host(ctx, ctx->work1, cta.data(), cta.size() * sizeof(int3), &dcta));
+    }
     void *du, *dv, *dl, *dne, *dnc, *dncl, *dfl;
     void* gdev[7];
     bool peer_on = false;
@@ -310,7 +329,7 @@ static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slice
     p.u0 = (const double*)du0; p.order = (const int*)dorder; p.cta = (const int3*)dcta;
     p.u = (double*)du; p.v = (double*)dv; p.logl = (double*)dl;
     p.nexp = (int*)dne; p.ncon = (int*)dnc; p.ncall = (int*)dncl; p.flags = (uint32_t*)dfl;
-    const unsigned grid = (unsigned)cta.size();
+    const unsigned grid = dyn ? (unsigned)ctx->dyn.max_cta : (unsigned)cta.size();
 #define LAUNCH(L, AXS, PRS)                                                                          \
     do {                                                                                             \
         B2N_CUDA(ctx, cudaFuncSetAttribute(slice_kernel<L, RANDOM_DIR, AXS, PRS>,                     \
@@ -328,6 +347,7 @@ static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slice
 #undef CALL
 #undef LAUNCH
     B2N_LAUNCH_CHECK(ctx);
+    if (dyn) return B2N_OK;      // device-paced: the commit kernel of the round folds the flags
     // error summary (a collapsed interval anywhere = RuntimeError in the reference)
     int* derr = reinterpret_cast<int*>(ctx->pinned);
     *derr = 0;

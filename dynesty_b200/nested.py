@@ -276,9 +276,83 @@ class NestedSampler:
             self.scale_history.append((self.ncall, smp.scale))
         self.update_bound_if_needed(loglstar, ncall=self.ncall)
 
+    # ------------------------------------------------------------------ device-resident rounds
+    def _device_rounds(self, logz, logvol, loglstar, dlogz, maxiter, maxcall, batch):
+        """Continue the run with ``b2n_ns_run`` (include/b200nest.h): K-worst replacement rounds
+        paced on the device; the host only rebuilds the bound when the device asks for it
+        (update_bound, sampler.py:493-510) and collects the dead points at the end."""
+        from . import ops
+        smp, n, N = self.internal_sampler, self.ndim, self.nlive
+        kind = 0 if isinstance(smp, S.B200RWalkSampler) else (1 if isinstance(smp, S.B200RSliceSampler) else 2)
+        steps = smp.sampler_kwargs['walks' if kind == 0 else 'slices']
+        K = int(batch or max(1, N // 10))
+        self.batch = K
+        ops.ns_create(self.model.model_id(self.ctx), N, n, K, kind, steps, self.seed, chain0=self.chain_counter,
+                      ncdim=self.ncdim, strict_contains=not isinstance(self.bound, B.B200Ellipsoid),
+                      facc=getattr(smp, 'facc', 0.5), dlogz=dlogz if dlogz is not None else 0.0,
+                      maxiter=maxiter if maxiter < (1 << 61) else None, maxcall=maxcall,
+                      update_interval=self.bound_update_interval, dimflags=smp._flags(), ctx=self.ctx)
+        ops.ns_set_state(self.live_u, self.live_v, self.live_logl, logvol, logz, loglstar, self.ncall, smp.scale,
+                         ctx=self.ctx)
+        self.bound.make_resident()
+        self._resident_key = (id(self.bound), getattr(self.bound, 'version', None))
+        cap, last_forced = 64 * N, -1
+        ncall_start, rounds = self.ncall, 0
+        while True:
+            per_round = max(1.0, (self.ncall - ncall_start) / rounds) if rounds else K * steps * (1 if kind == 0 else 6)
+            due = self.ncall_at_last_update + self.bound_update_interval - self.ncall
+            want = int(min(256, max(1, math.ceil(due / per_round))))
+            st = ops.ns_run(want, 0, ctx=self.ctx)
+            rounds, self.ncall = st['rounds'], st['ncall']
+            self.scale_history.append((self.ncall, st['scale']))
+            if st['done']:
+                break
+            if st['need_bound'] == 3:                               # dead-point buffer full
+                cap *= 2
+                ops.ns_reserve_dead(cap, ctx=self.ctx)
+            elif st['need_bound']:
+                if st['need_bound'] == 2:                           # a start point outside the bound
+                    if last_forced == rounds:
+                        raise RuntimeError('Update of the ellipsoid failed')     # sampler.py:489
+                    last_forced = rounds
+                self.live_u, self.live_v, self.live_logl = ops.ns_get_live(N, n, ctx=self.ctx)
+                self.update_bound()
+                self.nbound += 1
+                self.ncall_at_last_update = self.ncall
+                self.bound_history.append((self.ncall, getattr(self.bound, 'nells', 1), float(self.bound.logvol)))
+                self.bound.make_resident()
+                self._resident_key = (id(self.bound), getattr(self.bound, 'version', None))
+                ops.ns_bound_updated(ctx=self.ctx)
+        smp.scale = st['scale']
+        if st['doubling']:
+            smp.sampler_kwargs['slice_doubling'] = True
+        self.live_u, self.live_v, self.live_logl = ops.ns_get_live(N, n, ctx=self.ctx)
+        out = ops.ns_get_dead(0, st['it'], n, ctx=self.ctx)
+        self.chain_counter += rounds * K
+        self.nbatches += rounds
+        self.n_proposals += self.ncall - ncall_start
+        self.it += st['it']
+        self.device_rounds = rounds
+        ops.ns_destroy(ctx=self.ctx)
+        return out
+
     # ------------------------------------------------------------------ main loop
-    def run_nested(self, dlogz=None, maxiter=None, maxcall=None, add_live=True):
-        """sampler.py:1214-1356 / 1040-1212 (no plateau mode: continuous likelihoods)."""
+    def run_nested(self, dlogz=None, maxiter=None, maxcall=None, add_live=True, loop='host', batch=None):
+        """sampler.py:1214-1356 / 1040-1212 (no plateau mode: continuous likelihoods).
+
+        loop='host'   : the reference's semantics -- one worst point per iteration, replacements
+                        popped from a queue of `queue_size` proposals (sampler.py:732-778).
+        loop='device' : once the first bound exists, the run continues in ROUNDS on the device
+                        (csrc/b2n_ns.cu, ``b2n_ns_run``): each round removes the `batch` lowest
+                        live points at once and replaces them with `batch` chains evolved at the
+                        threshold of the batch-th lowest -- no stale-threshold filter, hence no
+                        selection bias for correlated chains, no host round trip
+                        per iteration.  batch defaults to nlive // 10."""
+        if loop not in ('host', 'device'):
+            raise ValueError("loop must be 'host' or 'device'")
+        if loop == 'device' and (self.comm is not None or self.bound_next is None or
+                                 isinstance(self.internal_sampler_next, S.B200UniformSampler)):
+            raise ValueError("loop='device' needs a bound and a chain sampler (rwalk/rslice/slice) on one GPU")
         nlive = self.nlive
         if dlogz is None:
             dlogz = 1e-3 * (nlive - 1.) + 0.01 if add_live else 0.01
@@ -297,9 +371,13 @@ class NestedSampler:
         dead_nc = np.empty(cap, dtype=np.int64)
         ndead = 0
         ncall0 = self.ncall
+        hand_over = False
         for it in range(1 << 62):
             delta_logz = _logaddexp(0.0, lmax + logvol - logz)
             if it > maxiter or self.ncall - ncall0 > maxcall:
+                break
+            if loop == 'device' and not self.unit_cube_sampling and self._qpos >= len(self._ql):
+                hand_over = True                                    # bound exists, queue drained
                 break
             if dlogz is not None and delta_logz < dlogz:
                 break
@@ -349,6 +427,13 @@ class NestedSampler:
         logl = dead_l[:ndead]
         logvols = -dlv * np.arange(1, ndead + 1)
         su, sv, nc_all = dead_u[:ndead], dead_v[:ndead], dead_nc[:ndead]
+        if hand_over:
+            du, dv, dl, dlvol, dnc = self._device_rounds(logz, logvol, loglstar, dlogz, maxiter - ndead,
+                                                         ncall0 + maxcall if maxcall < (1 << 61) else None, batch)
+            logl, logvols = np.concatenate([logl, dl]), np.concatenate([logvols, dlvol])
+            su, sv = np.concatenate([su, du]), np.concatenate([sv, dv])
+            nc_all = np.concatenate([nc_all, dnc.astype(np.int64)])
+            ndead = len(logl)
         if add_live:
             order = np.argsort(self.live_logl)
             lv_live = np.log(1. - (np.arange(nlive) + 1.) / (nlive + 1.)) + (logvols[-1] if ndead else 0.0)

@@ -236,3 +236,81 @@ def unif_batch(model, nchain, ndim, loglstar, seed, chain0=0, ncdim=None, dimfla
         ctx.check(ctx.lib.b2n_unif_batch(ctx.h, C.byref(a), ptr(o['u']), ptr(o['v']), ptr(o['logl']),
                                          ptr(o['ncall']), ptr(o['nprop']), ptr(o['flags'])))
     return o
+
+
+# ---- device-resident nested-sampling rounds (include/b200nest.h, b2n_ns_*) ----------------------
+def ns_create(model, nlive, ndim, batch, sampler, steps, seed, chain0=0, ncdim=None, strict_contains=True,
+              facc=0.5, dlogz=0.01, maxiter=None, maxcall=None, update_interval=1 << 62, dimflags=None,
+              dead_capacity=None, ctx=None):
+    """Allocate the device state of a batched-replacement run (sampler: 0 rwalk, 1 rslice, 2 slice)."""
+    ctx = _ctx(ctx)
+    c = _lib.NsConfig()
+    c.nlive, c.ndim, c.ncdim, c.batch = int(nlive), int(ndim), int(ncdim or ndim), int(batch)
+    c.sampler, c.steps, c.model_id, c.strict_contains = int(sampler), int(steps), int(model), int(bool(strict_contains))
+    c.facc, c.dlogz = float(facc), float(dlogz)
+    big = (1 << 62)
+    c.maxiter = int(maxiter) if maxiter is not None else big
+    c.maxcall = int(maxcall) if maxcall is not None else big
+    c.update_interval, c.seed, c.chain0 = int(update_interval), int(seed), int(chain0)
+    if dimflags is not None:
+        dimflags = np.ascontiguousarray(dimflags, dtype=np.uint8)
+    c.dimflags = ptr(dimflags)
+    cap = int(dead_capacity) if dead_capacity is not None else 64 * int(nlive)
+    ctx.check(ctx.lib.b2n_ns_create(ctx.h, C.byref(c), cap))
+
+
+def ns_set_state(live_u, live_v, live_logl, logvol, logz, loglstar, ncall, scale, ctx=None):
+    ctx = _ctx(ctx)
+    live_u, live_v, live_logl = f64(live_u), f64(live_v), f64(live_logl)
+    ctx.check(ctx.lib.b2n_ns_set_state(ctx.h, ptr(live_u), ptr(live_v), ptr(live_logl), float(logvol), float(logz),
+                                       float(loglstar), 0, int(ncall), float(scale)))
+
+
+def _ns_status(st):
+    return {k: getattr(st, k) for k, _ in st._fields_}
+
+
+def ns_run(max_rounds, check_every=0, ctx=None):
+    """Enqueue up to max_rounds rounds; returns the status dict (it, ncall, rounds, logz, logvol, loglstar,
+    lmax, delta_logz, scale, done, need_bound, doubling, error)."""
+    ctx = _ctx(ctx)
+    st = _lib.NsStatus()
+    ctx.check(ctx.lib.b2n_ns_run(ctx.h, int(max_rounds), int(check_every), C.byref(st)))
+    return _ns_status(st)
+
+
+def ns_status(ctx=None):
+    ctx = _ctx(ctx)
+    st = _lib.NsStatus()
+    ctx.check(ctx.lib.b2n_ns_status_get(ctx.h, C.byref(st)))
+    return _ns_status(st)
+
+
+def ns_bound_updated(ctx=None):
+    ctx = _ctx(ctx)
+    ctx.check(ctx.lib.b2n_ns_bound_updated(ctx.h))
+
+
+def ns_reserve_dead(capacity, ctx=None):
+    ctx = _ctx(ctx)
+    ctx.check(ctx.lib.b2n_ns_reserve_dead(ctx.h, int(capacity)))
+
+
+def ns_get_live(nlive, ndim, ctx=None):
+    ctx = _ctx(ctx)
+    u, v, l = np.empty((nlive, ndim)), np.empty((nlive, ndim)), np.empty(nlive)
+    ctx.check(ctx.lib.b2n_ns_get_live(ctx.h, ptr(u), ptr(v), ptr(l)))
+    return u, v, l
+
+
+def ns_get_dead(first, count, ndim, ctx=None):
+    ctx = _ctx(ctx)
+    u, v = np.empty((count, ndim)), np.empty((count, ndim))
+    l, lv, nc = np.empty(count), np.empty(count), np.empty(count, dtype=np.int32)
+    ctx.check(ctx.lib.b2n_ns_get_dead(ctx.h, int(first), int(count), ptr(u), ptr(v), ptr(l), ptr(lv), ptr(nc)))
+    return u, v, l, lv, nc
+
+
+def ns_destroy(ctx=None):
+    ctx = _ctx(ctx)
+    ctx.check(ctx.lib.b2n_ns_destroy(ctx.h))

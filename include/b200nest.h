@@ -257,6 +257,68 @@ int b2n_peer_check(b2n_ctx* ctx);
 /* bytes a window needs for gather-mode calls of total_rows x ndim */
 uint64_t b2n_peer_window_bytes(int64_t total_rows, int32_t ndim);
 
+/* ---- device-resident nested-sampling rounds ("replace K worst points per launch") ----
+ * Replaces the reference's per-iteration master loop for the bounded phase of a run: the
+ * worst-point search and evidence update of Sampler.sample (sampler.py:1040-1212,
+ * utils.py:1470-1492 progress_integration), propose_live (:469-491), _fill_queue / _new_point
+ * (:676-778) and the samplers' tune() (internal_samplers.py:460-493, 1209-1239).
+ *
+ * One ROUND removes the `batch` lowest live points at once (threshold L* = the batch-th lowest
+ * logl), evolves `batch` chains from uniformly chosen survivors at L* against the resident bound
+ * and writes every chain end point into a freed slot.  Unlike the reference's queue (an entry
+ * evolved at an older threshold is kept only if it beats the current one -- a filter that
+ * selects the offspring of the best live points when chains stay correlated with their starts,
+ * DESIGN.md 9.4) no chain is ever discarded, so there is no selection effect; the live-point
+ * count N, N-1, .., N-batch+1 seen by the removed points enters the quadrature the way the
+ * reference treats a shrinking live set (ln X -= ln((m+1)/m) at a point with m live points).
+ * A round is three launches (sort/propose, chains, commit) with no host synchronisation;
+ * b2n_ns_run enqueues rounds until a stop flag is raised on the device:
+ *   done        dlogz / maxiter / maxcall / plateau reached (sampler.py:1095-1120)
+ *   need_bound  1 = update interval reached (sampler.py:648-651), 2 = a start point is outside
+ *               the bound (forced update, :485-489), 3 = dead-point buffer full
+ * The caller then updates the bound from b2n_ns_get_live (b2n_multi_decompose / b2n_bound_set as
+ * usual), calls b2n_ns_bound_updated and runs on.  Random streams: chain c of round r is the
+ * B2N chain (seed, chain0 + r*batch + c); the round driver (start rows, ellipsoid picks) is the
+ * chain (seed, 2^62 + r), tick 0 / 1 = one uniform vector event each (oracle/nsloop.py).      */
+typedef struct {
+    int32_t nlive, ndim, ncdim, batch;
+    int32_t sampler;          /* 0 rwalk, 1 rslice, 2 slice                                     */
+    int32_t steps;            /* walks / slices                                                  */
+    int32_t model_id;
+    int32_t strict_contains;  /* 1: MultiEllipsoid.contains (d2 < 1), 0: Ellipsoid.contains (<= 1) */
+    double  facc;             /* rwalk target acceptance (internal_samplers.py:449-451)          */
+    double  dlogz;
+    int64_t maxiter, maxcall; /* in device-buffer iterations / total calls                       */
+    int64_t update_interval;  /* bound update every this many calls (dynesty.py:213-240)         */
+    uint64_t seed, chain0;
+    const uint8_t* dimflags;  /* HOST, ndim B2N_DIM_* flags or NULL (copied)                      */
+} b2n_ns_config;
+
+typedef struct {
+    int64_t it, ncall, rounds;       /* dead points in the device buffer, total calls, rounds done */
+    double logz, logvol, loglstar, lmax, delta_logz, scale;
+    int32_t done, need_bound, doubling, error;
+} b2n_ns_status;
+
+int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* cfg, int64_t dead_capacity);
+int b2n_ns_destroy(b2n_ctx* ctx);
+/* host arrays: the live set (nlive x ndim, nlive) and the scalars of the run so far */
+int b2n_ns_set_state(b2n_ctx* ctx, const double* live_u, const double* live_v, const double* live_logl,
+                     double logvol, double logz, double loglstar, int64_t it, int64_t ncall, double scale);
+/* enqueue up to max_rounds rounds, reading the stop flags every check_every rounds (<= 0: once at
+ * the end); synchronises; returns the status (and the sampler error status, e.g.
+ * B2N_ERR_SLICE_FAIL, if a chain failed). */
+int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_status* status);
+int b2n_ns_status_get(b2n_ctx* ctx, b2n_ns_status* status);
+/* after the caller replaced the resident bound: clears need_bound, restarts the update interval */
+int b2n_ns_bound_updated(b2n_ctx* ctx);
+/* grow the dead-point buffer to `capacity` rows (keeps the rows written so far); clears need_bound == 3 */
+int b2n_ns_reserve_dead(b2n_ctx* ctx, int64_t capacity);
+/* host outputs (each may be NULL) */
+int b2n_ns_get_live(b2n_ctx* ctx, double* live_u, double* live_v, double* live_logl);
+int b2n_ns_get_dead(b2n_ctx* ctx, int64_t first, int64_t count, double* u, double* v, double* logl,
+                    double* logvol, int32_t* ncall);
+
 #ifdef __cplusplus
 }
 #endif

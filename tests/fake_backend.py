@@ -219,7 +219,73 @@ def unif_batch(model, nchain, ndim, loglstar, seed, chain0=0, ncdim=None, dimfla
     return o
 
 
-FUNCS = ['model_eval', 'membership', 'bounding_ellipsoid', 'multi_decompose', 'scale_to_logvol',
+# ---- device-resident rounds (ops.ns_*) backed by oracle.nsloop.BatchNS ---------------------------
+def _ns_bound():
+    return dict(ctrs=_state['ctrs'], ams=_state['ams'], axes=_state['axes'], logvols=_state['logvols'],
+                strict=_state['ns_cfg']['strict'])
+
+
+def ns_create(model, nlive, ndim, batch, sampler, steps, seed, chain0=0, ncdim=None, strict_contains=True,
+              facc=0.5, dlogz=0.01, maxiter=None, maxcall=None, update_interval=1 << 62, dimflags=None,
+              dead_capacity=None, ctx=None):
+    assert dimflags is None, "fake backend: periodic/reflective not wired for ns rounds"
+    _state['ns_cfg'] = dict(model=_models[model], batch=batch, sampler=('rwalk', 'rslice', 'slice')[sampler],
+                            steps=steps, seed=seed, chain0=chain0, facc=facc, dlogz=dlogz,
+                            maxiter=maxiter if maxiter is not None else 1 << 62,
+                            maxcall=maxcall if maxcall is not None else 1 << 62,
+                            update_interval=update_interval, strict=bool(strict_contains))
+
+
+def ns_set_state(live_u, live_v, live_logl, logvol, logz, loglstar, ncall, scale, ctx=None):
+    from oracle import nsloop
+    c = _state['ns_cfg']
+    _state['ns'] = nsloop.BatchNS(c['model'], live_u, live_v, live_logl, c['batch'], c['sampler'], c['steps'],
+                                  c['seed'], chain0=c['chain0'], facc=c['facc'], scale=scale, logvol=logvol,
+                                  logz=logz, loglstar=loglstar, ncall=ncall, update_interval=c['update_interval'],
+                                  dlogz=c['dlogz'], maxiter=c['maxiter'], maxcall=c['maxcall'], bound=None)
+
+
+def ns_status(ctx=None):
+    b = _state['ns']
+    return dict(it=b.it, ncall=b.ncall, rounds=b.round, logz=b.logz, logvol=b.logvol, loglstar=b.loglstar,
+                lmax=float(b.live_logl.max()), delta_logz=b.delta_logz, scale=b.scale, done=b.done,
+                need_bound=b.need_bound, doubling=int(b.doubling), error=0)
+
+
+def ns_run(max_rounds, check_every=0, ctx=None):
+    b = _state['ns']
+    b.bound = _ns_bound()
+    for _ in range(max_rounds):
+        if not b.step():
+            break
+    return ns_status()
+
+
+def ns_bound_updated(ctx=None):
+    _state['ns'].bound_updated(_ns_bound())
+
+
+def ns_reserve_dead(capacity, ctx=None):
+    pass
+
+
+def ns_get_live(nlive, ndim, ctx=None):
+    b = _state['ns']
+    return b.live_u.copy(), b.live_v.copy(), b.live_logl.copy()
+
+
+def ns_get_dead(first, count, ndim, ctx=None):
+    u, v, l, lv, nc = _state['ns'].dead_arrays()
+    sl = slice(first, first + count)
+    return u[sl], v[sl], l[sl], lv[sl], nc[sl].astype(np.int32)
+
+
+def ns_destroy(ctx=None):
+    _state.pop('ns', None)
+
+
+FUNCS = ['ns_create', 'ns_set_state', 'ns_status', 'ns_run', 'ns_bound_updated', 'ns_reserve_dead',
+         'ns_get_live', 'ns_get_dead', 'ns_destroy', 'model_eval', 'membership', 'bounding_ellipsoid', 'multi_decompose', 'scale_to_logvol',
          'bootstrap_expand', 'bound_set', 'dimflags_from', 'rwalk_batch', 'rslice_batch', 'slice_batch',
          'unif_batch']
 

@@ -1,0 +1,162 @@
+"""GPU tier: the device-resident nested-sampling rounds (csrc/b2n_ns.cu, C ABI b2n_ns_*) against
+their oracle (oracle/nsloop.py) on the same seeded inputs, their stop flags, and whole runs
+(``run_nested(loop='device')``) against analytic evidences.
+
+Tolerances: dead-point order / counts / call totals exact; dead logl exact (they are copies of the
+inputs' values); ln X per dead point 1e-14; running logZ 1e-10; live set after the rounds rtol 1e-8
+(chains replay the oracle's to ~1e-9, tests/test_gpu_rwalk.py); tuned scale 1e-10."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import nsloop, likelihoods as OL, bounding as OB
+from dynesty_b200 import ops, likelihoods as DL, nested
+
+pytestmark = pytest.mark.gpu
+
+
+def _bound(points_list, strict=True, enlarge=1.25):
+    ells = []
+    for p in points_list:
+        e = OB.bounding_ellipsoid(p)
+        e.scale_to_logvol(e.logvol + math.log(enlarge))
+        ells.append(e)
+    return dict(ctrs=np.array([e.ctr for e in ells]), ams=np.array([e.am for e in ells]),
+                axes=np.array([e.axes for e in ells]), logvols=np.array([e.logvol for e in ells]), strict=strict)
+
+
+def _models(kind, n):
+    if kind == 'gauss':
+        return DL.gauss_corr(n, 0.4, 5.0), OL.gauss_corr(n, 0.4, 5.0)
+    return DL.shells(n), OL.shells(n)
+
+
+def _live(om, n, N, rng, two=False):
+    if two:        # two clusters around the two shell centres
+        half = N // 2
+        c1, c2 = 0.5 + np.zeros(n), 0.5 + np.zeros(n)
+        c1[0], c2[0] = 0.5 - 3.5 / 12, 0.5 + 3.5 / 12
+        u = np.concatenate([c1 + 0.03 * rng.standard_normal((half, n)), c2 + 0.03 * rng.standard_normal((N - half, n))])
+        groups = [u[:half], u[half:]]
+    else:
+        u = 0.5 + 0.05 * rng.standard_normal((N, n))
+        groups = [u]
+    v = om.prior_transform(u)
+    l = np.array([float(om.loglike(x)) for x in v])
+    return u, v, l, groups
+
+
+CASES = [
+    # kind, n, N, K, sampler, steps, two-ellipsoid bound, rounds
+    ('gauss', 6, 64, 16, 'rwalk', 10, False, 3),       # warp-per-chain rwalk kernel
+    ('gauss', 20, 96, 24, 'rwalk', 12, False, 3),      # lock-step DMMA rwalk kernel
+    ('gauss', 5, 64, 8, 'rslice', 4, False, 3),
+    ('gauss', 4, 48, 12, 'slice', 1, False, 2),
+    ('shells', 4, 80, 20, 'rwalk', 8, True, 3),        # 2 ellipsoids: volume-weighted picks + grouped worklist
+    ('shells', 4, 80, 10, 'rslice', 3, True, 2),
+]
+
+
+@pytest.mark.parametrize('kind,n,N,K,sampler,steps,two,rounds', CASES)
+def test_rounds_match_oracle(kind, n, N, K, sampler, steps, two, rounds):
+    dm, om = _models(kind, n)
+    rng = np.random.default_rng(100 + n + K)
+    u, v, l, groups = _live(om, n, N, rng, two)
+    b = _bound(groups)
+    seed, chain0, scale0 = 56432, 1000, 0.7
+    o = nsloop.BatchNS(om, u, v, l, K, sampler, steps, seed, chain0=chain0, scale=scale0, logvol=-2.5, logz=-40.0,
+                       loglstar=float(l.min()) - 0.5, ncall=500, bound=b, dlogz=1e-6)
+    for _ in range(rounds):
+        assert o.step(), (o.done, o.need_bound)
+    ops.bound_set(b['axes'], b['ctrs'], b['ams'], b['logvols'])
+    ops.ns_create(dm.model_id(), N, n, K, ('rwalk', 'rslice', 'slice').index(sampler), steps, seed, chain0=chain0,
+                  dlogz=1e-6, dead_capacity=rounds * K + 5)
+    try:
+        ops.ns_set_state(u, v, l, -2.5, -40.0, float(l.min()) - 0.5, 500, scale0)
+        st = ops.ns_run(rounds, 0)
+        assert (st['done'], st['need_bound'], st['error']) == (0, 0, 0)
+        assert st['rounds'] == rounds and st['it'] == rounds * K
+        assert st['ncall'] == o.ncall
+        du, dv, dl, dlv, dnc = ops.ns_get_dead(0, st['it'], n)
+        ou, ov, ol, olv, onc = o.dead_arrays()
+        assert np.array_equal(dl[:K], ol[:K])                       # first round: copies of the inputs, same order
+        assert np.allclose(dl, ol, rtol=1e-9, atol=0) and np.allclose(du, ou, rtol=1e-8, atol=1e-12)
+        assert np.allclose(dlv, olv, rtol=0, atol=1e-13)
+        assert np.array_equal(dnc, onc)
+        lu, lv_, ll = ops.ns_get_live(N, n)
+        assert np.allclose(lu, o.live_u, rtol=1e-8, atol=1e-12) and np.allclose(ll, o.live_logl, rtol=1e-8, atol=1e-10)
+        assert np.allclose(lv_, o.live_v, rtol=1e-8, atol=1e-11)
+        assert st['logz'] == pytest.approx(o.logz, rel=1e-10)
+        assert st['logvol'] == pytest.approx(o.logvol, abs=1e-13)
+        assert st['scale'] == pytest.approx(o.scale, rel=1e-10)
+        assert st['loglstar'] == pytest.approx(o.loglstar, rel=1e-9)
+    finally:
+        ops.ns_destroy()
+
+
+def test_stop_flags_and_dead_capacity():
+    dm, om = _models('gauss', 6)
+    rng = np.random.default_rng(3)
+    N, K, n = 64, 16, 6
+    u, v, l, groups = _live(om, n, N, rng)
+    b = _bound(groups)
+    ops.bound_set(b['axes'], b['ctrs'], b['ams'], b['logvols'])
+    ops.ns_create(dm.model_id(), N, n, K, 0, 5, 1, update_interval=100, dlogz=1e-9, dead_capacity=2 * K)
+    try:
+        ops.ns_set_state(u, v, l, 0.0, -1e300, -1e300, 0, 0.5)
+        st = ops.ns_run(8, 0)                                    # 16 x 5 = 80 calls per round, interval 100
+        assert st['rounds'] == 2 and st['need_bound'] == 1 and st['ncall'] == 160
+        st = ops.ns_run(4, 0)                                    # flag still up: nothing runs
+        assert st['rounds'] == 2
+        lu, _, _ = ops.ns_get_live(N, n)
+        b2 = _bound([lu])
+        ops.bound_set(b2['axes'], b2['ctrs'], b2['ams'], b2['logvols'])
+        ops.ns_bound_updated()
+        st = ops.ns_run(1, 0)                                    # dead buffer (2K rows) is full
+        assert st['need_bound'] == 3 and st['rounds'] == 2
+        ops.ns_reserve_dead(10 * K)
+        st = ops.ns_run(1, 0)
+        assert st['rounds'] == 3 and st['it'] == 3 * K
+        _, _, dl, _, _ = ops.ns_get_dead(0, 3 * K, n)
+        assert np.all(np.diff(dl) >= 0)                          # rows survived the reallocation, still ascending
+        # a bound that does not contain the live points -> forced update request
+        ops.bound_set(b2['axes'], b2['ctrs'] + 5.0, b2['ams'], b2['logvols'])
+        ops.ns_bound_updated()
+        st = ops.ns_run(2, 0)
+        assert st['need_bound'] == 2 and st['rounds'] == 3
+    finally:
+        ops.ns_destroy()
+    # termination: dlogz huge -> done at the first propose
+    ops.bound_set(b['axes'], b['ctrs'], b['ams'], b['logvols'])
+    ops.ns_create(dm.model_id(), N, n, K, 0, 5, 1, dlogz=1e9)
+    try:
+        ops.ns_set_state(u, v, l, 0.0, -10.0, -1e300, 0, 0.5)
+        st = ops.ns_run(3, 0)
+        assert st['done'] == 1 and st['rounds'] == 0 and st['it'] == 0
+    finally:
+        ops.ns_destroy()
+
+
+@pytest.mark.parametrize('ndim,nlive,sample,batch', [(20, 1000, 'rwalk', 100), (20, 600, 'rslice', 120),
+                                                     (6, 400, 'slice', 40)])
+def test_device_loop_logz(ndim, nlive, sample, batch):
+    """Whole runs with the rounds on the device: logZ against the analytic evidence of the C2 family."""
+    m = DL.gauss_corr(ndim, 0.4, 5.0)
+    s = nested.NestedSampler(m, nlive=nlive, bound='multi', sample=sample, seed=5, queue_size=max(32, nlive // 10))
+    res = s.run_nested(loop='device', batch=batch)
+    assert abs(res.logz[-1] - m.logz_truth) < 3.5 * res.logzerr[-1] + 0.1, (res.logz[-1], res.logzerr[-1], m.logz_truth)
+    assert s.device_rounds > 20 and s.nbound > 3
+    assert np.all(np.diff(res.logl) >= 0) and np.all(np.diff(res.logvol) < 0)
+    mean, cov = res.posterior_moments()
+    assert np.all(np.abs(mean) < 0.5)
+    assert np.all(np.abs(np.diag(cov) - 1.0) < 0.5)
+
+
+def test_device_loop_shells_two_ellipsoids():
+    """C5 likelihood (Gaussian shells, two modes): multi-ellipsoid bound with K > 1 inside the device loop."""
+    m = DL.shells(2)
+    s = nested.NestedSampler(m, nlive=600, bound='multi', sample='rslice', seed=9, queue_size=60)
+    res = s.run_nested(loop='device', batch=60)
+    assert abs(res.logz[-1] - m.logz_truth) < 3.5 * res.logzerr[-1] + 0.1
+    assert max(h[1] for h in res.bound_history) >= 2
