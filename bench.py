@@ -448,27 +448,49 @@ def run_b200(args, cfg):
     if world > 1:
         dist.barrier()
 
-    # ---- the second half of the metric: logZ error of a full run (not in the timed region)
+    # ---- the second half of the metric: logZ error of full runs (not in the timed region)
     if rank == 0 and world == 1 and args.logz:
         from dynesty_b200 import nested
         ctx.set_timing(False)
         ctx.set_stream(None)
         ctx.set_pointer_mode(_lib.PTR_HOST)
-        t0 = time.perf_counter()
-        # queue_size: chains proposed per fill at a FIXED threshold.  rwalk chains at 50-D barely
-        # decorrelate from their start points (true of the reference too), and the bias this
-        # causes grows with the fraction of the live set replaced per fill; nlive/10 reproduces
-        # the reference's own logZ.  The throughput steps above use
+        # Full C2 runs with the rounds paced on the device (b2n_ns_run): each round replaces the
+        # `batch` lowest live points.  rwalk chains at 50-D use proposal shapes estimated from the live
+        # points themselves and mix slowly along under-estimated directions (true of the reference too:
+        # its own logZ is +0.4 off the analytic value at nlive = 2000); the resulting bias grows with the
+        # fraction of the live set replaced per round, and batch = nlive/40 reproduces the reference's
+        # serial (queue_size = 1) result -- see DESIGN.md section 9.4.  The throughput steps above use
         # Q = nlive chains per launch.
-        ns = nested.NestedSampler(model, nlive=nlive, bound=cfg['bound'], sample=cfg['sample'], walks=walks,
-                                  seed=SEED, ctx=ctx, queue_size=args.logz_queue)
-        res = ns.run_nested()
-        wall = time.perf_counter() - t0
-        line["logz"] = {"queue_size": args.logz_queue, "logz": float(res.logz[-1]), "logzerr": float(res.logzerr[-1]),
-                        "truth": model.logz_truth, "abs_err": abs(float(res.logz[-1]) - model.logz_truth),
-                        "niter": int(res.niter), "ncall": int(res.ncall), "nbound": int(res.nbound),
-                        "wall_s": round(wall, 2), "calls_per_s": res.ncall / wall,
-                        "iterations_per_s": res.niter / wall}
+        batch = args.logz_batch or max(1, nlive // 40)
+        runs = []
+        for k in range(args.logz):
+            t0 = time.perf_counter()
+            ns = nested.NestedSampler(model, nlive=nlive, bound=cfg['bound'], sample=cfg['sample'], walks=walks,
+                                      seed=SEED + k, ctx=ctx, queue_size=args.logz_queue)
+            res = ns.run_nested(loop='device', batch=batch)
+            wall = time.perf_counter() - t0
+            runs.append({"seed": SEED + k, "logz": float(res.logz[-1]), "logzerr": float(res.logzerr[-1]),
+                         "niter": int(res.niter), "ncall": int(res.ncall), "nbound": int(res.nbound),
+                         "rounds": int(ns.device_rounds), "wall_s": round(wall, 3),
+                         "rounds_s": round(ns.device_timing['rounds_s'], 3),
+                         "bound_s": round(ns.device_timing['bound_s'], 3)})
+        lz = np.array([r["logz"] for r in runs])
+        best = min(r["wall_s"] for r in runs)
+        line["logz"] = {"loop": "device rounds (b2n_ns_run), K-worst replacement", "batch": batch, "runs": runs,
+                        "logz_mean": float(lz.mean()), "logz_std": float(lz.std(ddof=1)) if len(lz) > 1 else None,
+                        "truth": model.logz_truth, "abs_err_mean": abs(float(lz.mean()) - model.logz_truth),
+                        "wall_s_best": best, "calls_per_s": runs[-1]["ncall"] / runs[-1]["wall_s"],
+                        "iterations_per_s": runs[-1]["niter"] / runs[-1]["wall_s"]}
+        try:        # the UNMODIFIED reference on this config (CPU, serial), recorded by scripts/ref_c2_run.py
+            with open(os.path.join(ROOT, 'profiles', 'ref_c2_rwalk_nlive2000.jsonl')) as f:
+                ref = [json.loads(x) for x in f if x.strip()]
+            rz = np.array([r["logz"] for r in ref])
+            line["logz"]["reference"] = {"logz_mean": float(rz.mean()), "logz_std": float(rz.std(ddof=1)), "runs": len(rz),
+                                         "wall_s_mean": float(np.mean([r["wall"] for r in ref])),
+                                         "source": "profiles/ref_c2_rwalk_nlive2000.jsonl (dynesty, 1 CPU core, build container)"}
+            line["logz"]["mean_minus_reference_mean"] = float(lz.mean() - rz.mean())
+        except Exception:
+            pass
     # ---- CPU baseline on the host cores (rank 0, N=1 only), bounded sample
     if rank == 0 and world == 1 and args.cpu_baseline:
         import multiprocessing as mp
@@ -498,8 +520,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--chains', type=int, default=0, help='chains per step per GPU (default nlive)')
-    ap.add_argument('--logz', type=int, default=1, help='also run the full C2 nested-sampling run for logZ')
-    ap.add_argument('--logz-queue', type=int, default=200, help='queue_size of the full logZ run')
+    ap.add_argument('--logz', type=int, default=4, help='number of full C2 nested-sampling runs (seeds) for logZ; 0 = none')
+    ap.add_argument('--logz-queue', type=int, default=200, help='queue_size of the host (unit-cube) phase of the logZ runs')
+    ap.add_argument('--logz-batch', type=int, default=0, help='points replaced per device round (default nlive/40)')
     ap.add_argument('--cpu-baseline', type=int, default=1)
     ap.add_argument('--exchange', default='fused', choices=['fused', 'nccl'],
                     help='N>1: how the finished chains reach every rank')

@@ -16,8 +16,9 @@
 // point that had m live points.
 //
 // One round = three launches on the ctx stream, no host synchronisation in between:
-//   ns_propose_kernel  sort the live log-likelihoods (bitonic, one CTA), termination test
-//                      (sampler.py:1095-1120), pick K start rows among the survivors and their
+//   ns_propose_kernel  termination test (sampler.py:1095-1120) on the sorted live log-likelihoods (kept
+//                      sorted across rounds: one bitonic sort at start-up, then a K-into-(N-K) merge
+//                      per round in the commit kernel), pick K start rows among the survivors and their
 //                      ellipsoids (propose_live :469-491, get_random_axes bounding.py:726-731),
 //                      `bound.contains` of every start (:485-489), build the per-CTA worklist of
 //                      the chain kernel, write the round's B2nDyn
@@ -44,7 +45,7 @@ struct NsScalars {
 };
 
 struct NsDev {
-    int N, n, nc, K, Kell, cpc, strict, sampler, Npad;
+    int N, n, nc, K, Kell, cpc, strict, sampler, Npad, Kpad, threads;
     double dlogz, facc;
     long long maxiter, maxcall, update_interval, dead_cap;
     unsigned long long seed, chain0;
@@ -53,8 +54,10 @@ struct NsDev {
     int* dead_ncall;
     NsScalars* sc;
     B2nDyn* dyn;
-    int* sidx;          // live rows sorted by (logl, row) ascending
-    double* slogl;      // their logl
+    int* sidx;          // live rows sorted by (logl, row) ascending -- maintained across rounds
+    double* skey;       // their logl
+    int* tidx;          // merge scratch
+    double* tkey;
     double* u0;         // K x n start points of the round
     int* order;         // chain worklist
     int3* cta;
@@ -81,30 +84,18 @@ __device__ __forceinline__ double dev_logaddexp(double a, double b) {
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsDev s) {
+// full sort of the live log-likelihoods (start-up only): bitonic over (logl, row), one CTA
+__global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_sort_kernel(const NsDev s) {
     extern __shared__ __align__(16) unsigned char ns_smem[];
-    const int tid = threadIdx.x, nth = blockDim.x, warp = tid >> 5, lane = tid & 31;
-    NsScalars* sc = s.sc;
-    if (sc->done || sc->need_bound) {
-        if (tid == 0) s.dyn->skip = 1;
-        return;
-    }
-    const int N = s.N, K = s.K, n = s.n, nc = s.nc, Npad = s.Npad;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int N = s.N, Npad = s.Npad;
     double* key = reinterpret_cast<double*>(ns_smem);
-    double* dvec = key + Npad;                               // 32 warps x nc
-    double* cum = dvec + 32 * nc;                            // Kell
-    int* idx = reinterpret_cast<int*>(cum + ((s.Kell + 1) & ~1));
-    int* start = idx + Npad;                                 // K
-    int* ell = start + K;                                    // K
-    int* cnt = ell + K;                                      // Kell + 1
-    __shared__ int s_flag, s_bad;
+    int* idx = reinterpret_cast<int*>(key + Npad);
     for (int i = tid; i < Npad; i += nth) {
-        key[i] = i < N ? s.live_logl[i] : CUDART_INF;
+        key[i] = i < N ? s.live_logl[i] : CUDART_INF;     // padding (+inf, row >= N) sorts last
         idx[i] = i;
     }
-    if (tid == 0) { s_flag = 0; s_bad = 0; }
     __syncthreads();
-    // ---- bitonic sort of (logl, row), ascending; padding (+inf, row >= N) sorts last
     for (int k = 2; k <= Npad; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < (Npad >> 1); t += nth) {
@@ -119,6 +110,28 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsD
             __syncthreads();
         }
     }
+    for (int i = tid; i < N; i += nth) { s.sidx[i] = idx[i]; s.skey[i] = key[i]; }
+}
+
+__global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsDev s) {
+    extern __shared__ __align__(16) unsigned char ns_smem[];
+    const int tid = threadIdx.x, nth = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    NsScalars* sc = s.sc;
+    if (sc->done || sc->need_bound) {
+        if (tid == 0) s.dyn->skip = 1;
+        return;
+    }
+    const int N = s.N, K = s.K, n = s.n, nc = s.nc;
+    double* dvec = reinterpret_cast<double*>(ns_smem);       // (warps) x nc
+    double* cum = dvec + (nth >> 5) * nc;                    // Kell
+    int* start = reinterpret_cast<int*>(cum + ((s.Kell + 1) & ~1));   // K
+    int* ell = start + K;                                    // K
+    int* cnt = ell + K;                                      // Kell + 1
+    const double* key = s.skey;                              // sorted ascending by (logl, row)
+    const int* idx = s.sidx;
+    __shared__ int s_flag, s_bad;
+    if (tid == 0) { s_flag = 0; s_bad = 0; }
+    __syncthreads();
     // ---- termination (sampler.py:1095-1120) and capacity
     if (tid == 0) {
         const double lmax = key[N - 1];
@@ -136,8 +149,6 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsD
     }
     __syncthreads();
     if (s_flag) return;
-    for (int i = tid; i < N; i += nth) s.sidx[i] = idx[i];
-    for (int i = tid; i < K; i += nth) s.slogl[i] = key[i];
     // ---- start rows among the survivors, ellipsoid of every chain
     ChainRng g;
     g.init(s.seed, B2N_NS_DRIVER_CHAIN + (unsigned long long)sc->round);
@@ -294,11 +305,11 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
         s.live_v[src] = s.o_v[e];
     }
     // ---- evidence: ln X_j = ln X_0 + ln((N-j)/(N+1)); trapezoid weight with dX_j = X_j / (N-j) * 1/2 ..
-    double wmax = -CUDART_INF, lnew = -CUDART_INF;
+    double wmax = -CUDART_INF;
     long long ncall = 0, ha = 0, hb = 0;
     unsigned int fl = 0;
     for (int j = tid; j < K; j += nth) {
-        const double L = s.slogl[j], Lp = j ? s.slogl[j - 1] : lprev0;
+        const double L = s.skey[j], Lp = j ? s.skey[j - 1] : lprev0;
         const double lv = logvol0 + log((double)(N - j) / (double)(N + 1));
         const double w = dev_logaddexp(L, Lp) + lv + log(0.5 / (double)(N - j));
         wmax = fmax(wmax, w);
@@ -307,7 +318,6 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
         s.dead_ncall[it0 + j] = s.o_ncall[j];
         const double lo = s.o_logl[j];
         s.live_logl[s.sidx[j]] = lo;
-        lnew = fmax(lnew, lo);
         ncall += s.o_ncall[j];
         ha += s.o_i0[j];
         hb += s.o_i1[j];
@@ -316,22 +326,80 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
     const double m = block_reduce_max(wmax, rbuf);
     double se = 0.0;
     for (int j = tid; j < K; j += nth) {
-        const double L = s.slogl[j], Lp = j ? s.slogl[j - 1] : lprev0;
+        const double L = s.skey[j], Lp = j ? s.skey[j - 1] : lprev0;
         const double lv = logvol0 + log((double)(N - j) / (double)(N + 1));
         se += exp(dev_logaddexp(L, Lp) + lv + log(0.5 / (double)(N - j)) - m);
     }
     se = block_reduce_sum(se, rbuf);
-    lnew = block_reduce_max(lnew, rbuf);
     ncall = block_reduce_sum_ll(ncall, lbuf);
     ha = block_reduce_sum_ll(ha, lbuf);
     hb = block_reduce_sum_ll(hb, lbuf);
     if (fl) atomicOr(&s_or, fl);
     __syncthreads();
+    // ---- keep (skey, sidx) sorted: the K lowest were replaced, so merge the K new (logl, row) pairs
+    //      into the N-K survivors (already sorted).  Comparator = (logl, row) lexicographic, a strict
+    //      total order, hence position = own rank + number of elements of the OTHER list below.
+    {
+        extern __shared__ __align__(16) unsigned char ns_smem[];
+        const int NA = N - K, Kpad = s.Kpad;
+        double* akey = reinterpret_cast<double*>(ns_smem);       // NA survivors
+        double* bkey = akey + NA + (NA & 1);                      // Kpad new
+        int* aidx = reinterpret_cast<int*>(bkey + Kpad);
+        int* bidx = aidx + NA;
+        const double thr_keep = s.skey[K - 1];
+        for (int i = tid; i < NA; i += nth) { akey[i] = s.skey[K + i]; aidx[i] = s.sidx[K + i]; }
+        for (int j = tid; j < Kpad; j += nth) {
+            bkey[j] = j < K ? s.o_logl[j] : CUDART_INF;
+            bidx[j] = j < K ? s.sidx[j] : 0x7fffffff;
+        }
+        __syncthreads();
+        for (int k = 2; k <= Kpad; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (Kpad >> 1); t += nth) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int l = i | j;
+                    const bool asc = (i & k) == 0;
+                    const double ka = bkey[i], kb = bkey[l];
+                    const int ia = bidx[i], ib = bidx[l];
+                    const bool gt = ka > kb || (ka == kb && ia > ib);
+                    if (gt == asc) { bkey[i] = kb; bkey[l] = ka; bidx[i] = ib; bidx[l] = ia; }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = tid; i < NA; i += nth) {                     // survivors: count new pairs below
+            const double ka = akey[i];
+            const int ia = aidx[i];
+            int lo = 0, hi = K;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const bool less = bkey[mid] < ka || (bkey[mid] == ka && bidx[mid] < ia);
+                if (less) lo = mid + 1; else hi = mid;
+            }
+            s.tkey[i + lo] = ka;
+            s.tidx[i + lo] = ia;
+        }
+        for (int j = tid; j < K; j += nth) {                      // new pairs: count survivors below
+            const double kb = bkey[j];
+            const int ib = bidx[j];
+            int lo = 0, hi = NA;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const bool less = akey[mid] < kb || (akey[mid] == kb && aidx[mid] < ib);
+                if (less) lo = mid + 1; else hi = mid;
+            }
+            s.tkey[j + lo] = kb;
+            s.tidx[j + lo] = ib;
+        }
+        __syncthreads();
+        if (tid == 0) sc->loglstar = thr_keep;
+        for (int i = tid; i < N; i += nth) { s.skey[i] = s.tkey[i]; s.sidx[i] = s.tidx[i]; }
+        __syncthreads();
+    }
     if (tid == 0) {
         sc->logz = dev_logaddexp(sc->logz, m + log(se));
         sc->logvol = logvol0 + log((double)(N - K + 1) / (double)(N + 1));
-        sc->loglstar = s.slogl[K - 1];
-        sc->lmax = fmax(sc->lmax, lnew);
+        sc->lmax = s.skey[N - 1];
         sc->it = it0 + K;
         sc->ncall += ncall;
         sc->round += 1;
@@ -427,9 +495,14 @@ static int ns_chain_call(b2n_ctx* ctx, b2n_ns* ns, bool plan_only) {
 }
 
 static size_t ns_propose_smem(const NsDev& d) {
-    return (size_t)d.Npad * 8 + (size_t)32 * d.nc * 8 + (size_t)((d.Kell + 1) & ~1) * 8 + (size_t)d.Npad * 4 +
-           (size_t)d.K * 8 + (size_t)(d.Kell + 2) * 4 + 64;
+    return (size_t)(d.threads / 32) * d.nc * 8 + (size_t)((d.Kell + 1) & ~1) * 8 + (size_t)d.K * 8 +
+           (size_t)(d.Kell + 2) * 4 + 64;
 }
+static size_t ns_commit_smem(const NsDev& d) {
+    const size_t NA = (size_t)(d.N - d.K);
+    return (NA + (NA & 1)) * 8 + (size_t)d.Kpad * 8 + NA * 4 + (size_t)d.Kpad * 4 + 64;
+}
+static size_t ns_sort_smem(const NsDev& d) { return (size_t)d.Npad * 12 + 64; }
 
 extern "C" {
 
@@ -454,6 +527,9 @@ int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* c, int64_t dead_capacity) {
     memset(&d, 0, sizeof(d));
     d.N = c->nlive; d.n = n; d.nc = c->ncdim; d.K = c->batch; d.Kell = 1; d.strict = 1; d.sampler = c->sampler;
     d.Npad = Npad;
+    d.Kpad = 2;
+    while (d.Kpad < c->batch) d.Kpad <<= 1;
+    d.threads = c->batch <= 128 ? 256 : B2N_NS_THREADS;     // small rounds: cheaper CTA barriers
     d.dlogz = c->dlogz; d.facc = c->facc; d.maxiter = c->maxiter; d.maxcall = c->maxcall;
     d.update_interval = c->update_interval; d.seed = c->seed; d.chain0 = c->chain0;
     const size_t N = d.N, K = d.K;
@@ -463,7 +539,9 @@ int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* c, int64_t dead_capacity) {
     B2N_TRY(ns_alloc(ctx, ns, (void**)&d.sc, sizeof(NsScalars)));
     B2N_TRY(ns_alloc(ctx, ns, (void**)&d.dyn, sizeof(B2nDyn)));
     B2N_TRY(ns_alloc(ctx, ns, (void**)&d.sidx, N * 4));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.slogl, K * 8));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.skey, N * 8));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.tidx, N * 4));
+    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.tkey, N * 8));
     B2N_TRY(ns_alloc(ctx, ns, (void**)&d.u0, K * n * 8));
     B2N_TRY(ns_alloc(ctx, ns, (void**)&d.order, K * 4));
     B2N_TRY(ns_alloc(ctx, ns, (void**)&d.cta, (K + N + 8) * sizeof(int3)));
@@ -508,6 +586,11 @@ int b2n_ns_set_state(b2n_ctx* ctx, const double* live_u, const double* live_v, c
     h.lmax = -1e300; h.delta_logz = 1e300;
     B2N_CUDA(ctx, cudaMemcpy(d.sc, &h, sizeof(h), cudaMemcpyHostToDevice));
     B2N_CUDA(ctx, cudaMemset(d.dyn, 0, sizeof(B2nDyn)));
+    const size_t smem = ns_sort_smem(d);
+    if (smem > (size_t)ctx->max_smem_optin) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "nlive too large for the one-CTA sort of b2n_ns");
+    B2N_CUDA(ctx, cudaFuncSetAttribute(ns_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ns_sort_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d);
+    B2N_LAUNCH_CHECK(ctx);
     return B2N_OK;
 }
 
@@ -546,9 +629,11 @@ int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_sta
         return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "too many ellipsoids for the round worklist");
     B2N_TRY(ns_chain_call(ctx, ns, true));               // chains per CTA the chain kernel plans for
     d.cpc = ctx->dyn.cpc;
-    const size_t smem = ns_propose_smem(d);
-    if (smem > (size_t)ctx->max_smem_optin) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "nlive too large for the one-CTA sort of b2n_ns_run");
+    const size_t smem = ns_propose_smem(d), csmem = ns_commit_smem(d);
+    if (smem > (size_t)ctx->max_smem_optin || csmem + 8192 + 64 > (size_t)ctx->max_smem_optin)
+        return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "nlive / batch too large for the one-CTA kernels of b2n_ns_run");
     B2N_CUDA(ctx, cudaFuncSetAttribute(ns_propose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2N_CUDA(ctx, cudaFuncSetAttribute(ns_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
     if (check_every < 1) check_every = max_rounds > 0 ? max_rounds : 1;
     int left = max_rounds;
     b2n_ns_status st;
@@ -556,10 +641,10 @@ int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_sta
     while (left > 0) {
         const int chunk = std::min(left, (int)check_every);
         for (int r = 0; r < chunk; r++) {
-            ns_propose_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d);
+            ns_propose_kernel<<<1, d.threads, smem, ctx->stream>>>(d);
             B2N_LAUNCH_CHECK(ctx);
             B2N_TRY(ns_chain_call(ctx, ns, false));
-            ns_commit_kernel<<<1, B2N_NS_THREADS, 0, ctx->stream>>>(d);
+            ns_commit_kernel<<<1, d.threads, csmem, ctx->stream>>>(d);
             B2N_LAUNCH_CHECK(ctx);
         }
         left -= chunk;

@@ -215,12 +215,14 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 }
 
 // KT = k-tiles of 4 columns (n <= 4*KT); CH = chains in lock-step per CTA (8 -> 256 threads, two
-// CTAs per SM overlap each other's barriers: measured 1.3x faster than one 16-chain CTA per SM)
-// DU = direction look-ahead: the draws of a step do not depend on the chain state (the Philox
-// counter is a function of (chain, tick) only), so a chain warp generates the directions of DU
-// consecutive steps in ONE straight-line block -- DU independent Philox / log / sincospi
-// dependency chains interleaved by the compiler -- instead of one latency-bound chain per step.
-template <int LIKE, int KT, int CH, int DU>
+// CTAs per SM overlap each other's barriers: measured 1.3x faster than one 16-chain CTA per SM).
+// DEPTH = direction ring: the draws of a step do not depend on the chain state (the Philox counter
+// is a function of (chain, tick = 2 * step) only), so the directions of the next DEPTH steps of all
+// live chains of the CTA are generated up front and dealt over ALL warps of the CTA.  A full CTA
+// (8 chains) gains a barrier per step; a CTA with few chains -- the small rounds of b2n_ns_run run
+// one chain per CTA -- generates its directions on 8 warps in parallel instead of serially on one,
+// which is the longest dependency chain of a step (Philox -> log -> sqrt -> sincospi).
+template <int LIKE, int KT, int CH, int DEPTH>
 __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(const RwalkParams p) {
     constexpr int B2N_MMA_CH = CH;
     constexpr int RS = 8 * ((4 * KT + 7) / 8);                    // rows padded to whole 8-row slabs
@@ -242,11 +244,12 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
     for (int i = threadIdx.x; i < n; i += blockDim.x) fl[i] = p.dimflags ? p.dimflags[i] : 0u;
     off += ((n + 3) >> 2) << 1;
     constexpr int XB = B2N_MMA_CH * XS;             // one direction buffer (all chains of the CTA)
-    const int oX = off;  off += DU * XB;            // DU x: direction z, later delta = v - mean (chain-major)
+    const int oX = off;  off += DEPTH * XB;         // ring: direction z of step s, later delta = v - mean
     const int oY = off;  off += B2N_MMA_CH * YS;    // axes @ z (chain-major)
     const int oQ = off;  off += 8 * B2N_MMA_CH;     // per-slab partial quadratic forms
+    const int oF = off;  off += DEPTH * B2N_MMA_CH; // step factors scale * U^(1/n) / |z|
     const int ost = off;                            // per-chain state: ucur, uprop, vcur, vprop
-    for (int e = threadIdx.x; e < DU * XB; e += blockDim.x) b2n_sm[oX + e] = 0.0;
+    for (int e = threadIdx.x; e < DEPTH * XB; e += blockDim.x) b2n_sm[oX + e] = 0.0;
     // ---- matrix fragments -> registers.  item (s, t): slab s of rows, chain tile t
     const int s_it = warp % S, t_it = warp / S;
     const bool has_item = warp < (CH / 8) * S && t_it < CH / 8;
@@ -267,45 +270,33 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
     const double inv_n = 1.0 / (double)n;
     const int pk = p.m.prior_kind;
 
-    for (int g0 = 0; g0 < cd.y; g0 += B2N_MMA_CH) {             // groups of 16 chains
+    for (int g0 = 0; g0 < cd.y; g0 += B2N_MMA_CH) {             // groups of CH chains
         const int c = warp;                                     // chain slot owned by this warp
-        const bool live = g0 + c < cd.y;
+        const int nlc = (cd.y - g0) < B2N_MMA_CH ? (cd.y - g0) : B2N_MMA_CH;   // live chains of the group
+        const bool live = c < nlc;
         const int q = live ? p.order[cd.x + g0 + c] : 0;
         int oucur = ost + c * 4 * npad, ouprop = oucur + npad, ovcur = ouprop + npad, ovprop = ovcur + npad;
         const int oy = oY + c * YS;
-        ChainRng g;
-        g.init(p.seed, chain0_ + (uint64_t)q);
         if (live)
             for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)q * n + i];
         int nacc = 0, nrej = 0;
         double lcur = 0.0;
-        __syncthreads();
-        for (int step0 = 0; step0 < p.walks; step0 += DU) {
-            // ---- phase 1 (chain warp): directions in the unit ball of the next DU steps -> X[s][c]
-            double facs[DU];
-            if (live) {
-                int offx[DU];
-#pragma unroll
-                for (int s = 0; s < DU; s++) offx[s] = oX + s * XB + c * XS;
-                const int left = p.walks - step0;
-                if (n <= 62) {
-                    ball_directions<DU>(g, offx, left < DU ? left : DU, n, lane, inv_n, facs);
-                } else {
-#pragma unroll
-                    for (int s = 0; s < DU; s++) facs[s] = s < left ? ball_direction(g, offx[s], n, lane, inv_n) : 0.0;
-                }
-#pragma unroll
-                for (int s = 0; s < DU; s++) facs[s] *= scale_;
-            } else {
-#pragma unroll
-                for (int s = 0; s < DU; s++) facs[s] = 0.0;
+        for (int step0 = 0; step0 < p.walks; step0 += DEPTH) {
+            // ---- phase 1 (all warps): directions in the unit ball of the next DEPTH steps of every
+            //      live chain -> X[s][chain], factors -> F[s][chain].  Item w = (step s, chain c2).
+            const int nd = (p.walks - step0) < DEPTH ? (p.walks - step0) : DEPTH;
+            for (int w = warp; w < nd * nlc; w += B2N_MMA_CH) {
+                const int s = w / nlc, c2 = w - s * nlc;
+                ChainRng g;
+                g.init(p.seed, chain0_ + (uint64_t)p.order[cd.x + g0 + c2]);
+                g.tick = 2u * (uint32_t)(step0 + s);             // two draw events per step (:1011-1016)
+                const double f = scale_ * ball_direction(g, oX + s * XB + c2 * XS, n, lane, inv_n);
+                if (lane == 0) b2n_sm[oF + s * B2N_MMA_CH + c2] = f;
             }
-#pragma unroll
-            for (int s = 0; s < DU; s++) {
-            if (step0 + s >= p.walks) break;                 // CTA-uniform
-            const int oXs = oX + s * XB, ox = oXs + c * XS;
-            const double fac = facs[s];
             __syncthreads();
+            for (int s = 0; s < nd; s++) {
+            const int oXs = oX + s * XB, ox = oXs + c * XS;
+            const double fac = live ? b2n_sm[oF + s * B2N_MMA_CH + c] : 0.0;
             // ---- phase 2 (item warp): Y[rows of slab][chains of tile] = A_slab @ X
             if (has_item) {
                 double d0 = 0.0, d1 = 0.0;
@@ -317,7 +308,7 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
                 b2n_sm[oY + (c0 + 1) * YS + row] = d1;
             }
             __syncthreads();
-            // ---- phase 3 (chain warp): u' = u + fac*y, wrap / reflect / cube test, prior, delta -> X[c]
+            // ---- phase 3 (chain warp): u' = u + fac*y, wrap / reflect / cube test, prior, delta -> X[s][c]
             bool ok = true;
             if (live) {
                 for (int i = lane; i < n; i += 32) {
@@ -357,11 +348,14 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
                 __syncthreads();
                 // ---- phase 5 (chain warp): logl
                 double qf = 0.0;
-                for (int s = 0; s < S; s++) qf += b2n_sm[oQ + s * B2N_MMA_CH + c];
+                for (int s2 = 0; s2 < S; s2++) qf += b2n_sm[oQ + s2 * B2N_MMA_CH + c];
                 l = fma(-0.5, qf, p.m.s0);
-            } else if (live && ok) {
-                __syncwarp();
-                l = loglike_sm<LIKE, false>(p.m, ms, nullptr, 0, n, n, ovprop, oy, lane);
+            } else {
+                if (live && ok) {
+                    __syncwarp();
+                    l = loglike_sm<LIKE, false>(p.m, ms, nullptr, 0, n, n, ovprop, oy, lane);
+                }
+                __syncthreads();      // Y (scratch of the likelihood) is rewritten by the next step's phase 2
             }
             if (live) {
                 if (!ok) {
@@ -376,6 +370,8 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
                 }
             }
             }   // s
+            // the ring is regenerated only after every warp has finished reading it (phase 4 of the
+            // last step sits before a barrier; phase 3 of non-GAUSS_PREC likelihoods does too)
         }
         if (live) {
             if (nacc == 0) {   // recompute (v, logl) of the start point (:970-975), warp-local
@@ -397,7 +393,7 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
         }
         __syncthreads();
         // X rows of chains that are not live in the next group must read as zero
-        for (int e = threadIdx.x; e < DU * XB; e += blockDim.x) b2n_sm[oX + e] = 0.0;
+        for (int e = threadIdx.x; e < DEPTH * XB; e += blockDim.x) b2n_sm[oX + e] = 0.0;
         __syncthreads();
     }
     peer_finish(p.peer);
@@ -648,9 +644,10 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         use_mma = true;
     }
     const int KT = n <= 32 ? 8 : (n <= 52 ? 13 : 16);
-    // direction look-ahead of the lock-step kernel (B2N_RWALK_DU=1|2|4: experiments; results identical)
-    int DU = 1;
-    if (const char* e = getenv("B2N_RWALK_DU")) DU = (atoi(e) == 2) ? 2 : (atoi(e) == 4 ? 4 : 1);
+    // direction ring depth of the lock-step kernel (B2N_RWALK_DEPTH=1: one step at a time, as before the
+    // ring; results identical)
+    int DU = 8;
+    if (const char* e = getenv("B2N_RWALK_DEPTH")) DU = (atoi(e) == 1) ? 1 : 8;
     size_t mma_smem = 0;
     if (use_mma) {
         const int ctas = 2 * ctx->sm_count;                 // 8-chain CTAs, two resident per SM
@@ -658,7 +655,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         warps = 8;
         const int RS = 8 * ((4 * KT + 7) / 8);
         const int XS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16)), YS = RS + 2;
-        mma_smem = (size_t)(4 * npad + (((n + 3) >> 2) << 1) + DU * 8 * XS + 8 * YS + 8 * 8 + 8 * 4 * npad) * sizeof(double);
+        mma_smem = (size_t)(4 * npad + (((n + 3) >> 2) << 1) + DU * 8 * XS + 8 * YS + 8 * 8 + DU * 8 + 8 * 4 * npad) * sizeof(double);
     }
     // large n: lock-step kernel with matrix fragments streamed from L2 (16 chains share each load)
     bool use_mmas = false;
@@ -752,9 +749,8 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         rwalk_mma_kernel<L, K, 8, D><<<grid, 256, smem, ctx->stream>>>(p);                           \
     } while (0)
 #define LAUNCH_MMA(L, K)                 \
-    if (DU == 2) LAUNCH_MMA2(L, K, 2);   \
-    else if (DU == 4) LAUNCH_MMA2(L, K, 4); \
-    else LAUNCH_MMA2(L, K, 1);
+    if (DU == 1) LAUNCH_MMA2(L, K, 1);   \
+    else LAUNCH_MMA2(L, K, 8);
 #define CALL_MMA(L)                      \
     if (KT == 8) { LAUNCH_MMA(L, 8) }    \
     else if (KT == 13) { LAUNCH_MMA(L, 13) } \

@@ -298,11 +298,16 @@ class NestedSampler:
         self._resident_key = (id(self.bound), getattr(self.bound, 'version', None))
         cap, last_forced = 64 * N, -1
         ncall_start, rounds = self.ncall, 0
+        import time
+        tm = dict(rounds_s=0.0, bound_s=0.0)
+        self.device_timing = tm
         while True:
             per_round = max(1.0, (self.ncall - ncall_start) / rounds) if rounds else K * steps * (1 if kind == 0 else 6)
             due = self.ncall_at_last_update + self.bound_update_interval - self.ncall
-            want = int(min(256, max(1, math.ceil(due / per_round))))
+            want = int(min(4096, max(1, math.ceil(due / per_round))))
+            t0 = time.perf_counter()
             st = ops.ns_run(want, 0, ctx=self.ctx)
+            tm['rounds_s'] += time.perf_counter() - t0
             rounds, self.ncall = st['rounds'], st['ncall']
             self.scale_history.append((self.ncall, st['scale']))
             if st['done']:
@@ -315,7 +320,8 @@ class NestedSampler:
                     if last_forced == rounds:
                         raise RuntimeError('Update of the ellipsoid failed')     # sampler.py:489
                     last_forced = rounds
-                self.live_u, self.live_v, self.live_logl = ops.ns_get_live(N, n, ctx=self.ctx)
+                t0 = time.perf_counter()
+                self.live_u = ops.ns_get_live(N, n, ctx=self.ctx, only_u=True)
                 self.update_bound()
                 self.nbound += 1
                 self.ncall_at_last_update = self.ncall
@@ -323,6 +329,7 @@ class NestedSampler:
                 self.bound.make_resident()
                 self._resident_key = (id(self.bound), getattr(self.bound, 'version', None))
                 ops.ns_bound_updated(ctx=self.ctx)
+                tm['bound_s'] += time.perf_counter() - t0
         smp.scale = st['scale']
         if st['doubling']:
             smp.sampler_kwargs['slice_doubling'] = True

@@ -296,9 +296,13 @@ def ns_reserve_dead(capacity, ctx=None):
     ctx.check(ctx.lib.b2n_ns_reserve_dead(ctx.h, int(capacity)))
 
 
-def ns_get_live(nlive, ndim, ctx=None):
+def ns_get_live(nlive, ndim, ctx=None, only_u=False):
     ctx = _ctx(ctx)
-    u, v, l = np.empty((nlive, ndim)), np.empty((nlive, ndim)), np.empty(nlive)
+    u = np.empty((nlive, ndim))
+    if only_u:          # what a bound update needs
+        ctx.check(ctx.lib.b2n_ns_get_live(ctx.h, ptr(u), None, None))
+        return u
+    v, l = np.empty((nlive, ndim)), np.empty(nlive)
     ctx.check(ctx.lib.b2n_ns_get_live(ctx.h, ptr(u), ptr(v), ptr(l)))
     return u, v, l
 

@@ -269,8 +269,10 @@ def ns_reserve_dead(capacity, ctx=None):
     pass
 
 
-def ns_get_live(nlive, ndim, ctx=None):
+def ns_get_live(nlive, ndim, ctx=None, only_u=False):
     b = _state['ns']
+    if only_u:
+        return b.live_u.copy()
     return b.live_u.copy(), b.live_v.copy(), b.live_logl.copy()
 
 
