@@ -242,6 +242,9 @@ def run_b200(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # stdout carries exactly ONE line (the JSON): NCCL's own banner / debug lines go to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')
         dist.init_process_group('nccl', device_id=dev)
     ctx = _lib.Context(local)
     n, nlive, walks = cfg['ndim'], cfg['nlive'], cfg['walks']
@@ -419,7 +422,7 @@ def run_b200(args, cfg):
         traffic = None          # measured DRAM bytes per launch of this kernel (ncu --set full)
         try:
             with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
-                traffic = json.load(f)['rwalk_kernel']['dram_bytes_per_launch'] if Q == 2000 else None
+                traffic = json.load(f)['rwalk_mma_kernel']['dram_bytes_per_launch'] if Q == 2000 else None
         except Exception:
             pass
         line = {
@@ -440,7 +443,11 @@ def run_b200(args, cfg):
             "accepted_proposals_per_s": value * accept_frac,      # rwalk n_accept / wall
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch",
-                         "algorithmic_bytes_per_launch": algorithmic_bytes(n) * Q * walks, "kernel": "rwalk_kernel",
+                         "algorithmic_bytes_per_launch": algorithmic_bytes(n) * Q * walks,
+                         "kernel": "rwalk_mma_kernel<GAUSS_PREC, KT=13, 8 chains/CTA, ring 8>",
+                         "note": ("frac > 1: SURVEY 8(d)'s byte model counts both 20 KB matrices per proposal (no reuse); the "
+                                  "kernel keeps them in registers, so HBM is idle (traffic) and the kernel is latency-bound "
+                                  "at the problem's parallelism (DESIGN.md 9.1)"),
                          "kernel_ms": kms, "algorithmic_bytes_per_proposal": algorithmic_bytes(n),
                          "peak_source": peak_src},
             "clocks": clk,

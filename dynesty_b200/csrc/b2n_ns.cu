@@ -189,10 +189,15 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsD
             for (int i = lane; i < nc; i += 32) d[i] = x[i] - ctr[i];
             __syncwarp();
             double acc = 0.0;
-            for (int i = lane; i < nc; i += 32) {
-                double y = 0.0;
-                for (int j = 0; j < nc; j++) y = fma(A[(size_t)i * nc + j], d[j], y);
-                acc = fma(d[i], y, acc);
+            for (int i = lane; i < nc; i += 32) {        // A is symmetric: read it column-wise (coalesced)
+                double y0 = 0.0, y1 = 0.0;
+                int j = 0;
+                for (; j + 1 < nc; j += 2) {
+                    y0 = fma(__ldg(A + (size_t)j * nc + i), d[j], y0);
+                    y1 = fma(__ldg(A + (size_t)(j + 1) * nc + i), d[j + 1], y1);
+                }
+                if (j < nc) y0 = fma(__ldg(A + (size_t)j * nc + i), d[j], y0);
+                acc = fma(d[i], y0 + y1, acc);
             }
             acc = warp_sum(acc);
             inside = s.strict ? (acc < 1.0) : (acc <= 1.0);
@@ -245,46 +250,44 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsD
 }
 
 // ---------------------------------------------------------------------------------------------
+// Block reductions: warp shuffles, one partial per warp in shared memory, first warp finishes.
+// Fixed order (lane tree, then warp 0 over the partials): bit-reproducible for a given blockDim.
 __device__ __forceinline__ double block_reduce_max(double v, double* buf) {
-    const int tid = threadIdx.x;
-    buf[tid] = v;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+    v = warp_max(v);
+    if (lane == 0) buf[w] = v;
     __syncthreads();
-    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-        if (tid < o) buf[tid] = fmax(buf[tid], buf[tid + o]);
-        __syncthreads();
-    }
-    const double r = buf[0];
+    double r = lane < nw ? buf[lane] : -CUDART_INF;
+    r = warp_max(r);
     __syncthreads();
     return r;
 }
-__device__ __forceinline__ double block_reduce_sum(double v, double* buf) {   // fixed tree: reproducible
-    const int tid = threadIdx.x;
-    buf[tid] = v;
+__device__ __forceinline__ double block_reduce_sum(double v, double* buf) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) buf[w] = v;
     __syncthreads();
-    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-        if (tid < o) buf[tid] += buf[tid + o];
-        __syncthreads();
-    }
-    const double r = buf[0];
+    double r = lane < nw ? buf[lane] : 0.0;
+    r = warp_sum(r);
     __syncthreads();
     return r;
 }
 __device__ __forceinline__ long long block_reduce_sum_ll(long long v, long long* buf) {
-    const int tid = threadIdx.x;
-    buf[tid] = v;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(B2N_FULL, v, o);
+    if (lane == 0) buf[w] = v;
     __syncthreads();
-    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-        if (tid < o) buf[tid] += buf[tid + o];
-        __syncthreads();
-    }
-    const long long r = buf[0];
+    long long r = lane < nw ? buf[lane] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(B2N_FULL, r, o);
     __syncthreads();
     return r;
 }
 
 __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDev s) {
     if (s.dyn->skip) return;
-    __shared__ double rbuf[B2N_NS_THREADS];
+    __shared__ double rbuf[64];
     __shared__ unsigned int s_or;
     long long* lbuf = reinterpret_cast<long long*>(rbuf);
     const int tid = threadIdx.x, nth = blockDim.x;
@@ -495,7 +498,7 @@ static int ns_chain_call(b2n_ctx* ctx, b2n_ns* ns, bool plan_only) {
 }
 
 static size_t ns_propose_smem(const NsDev& d) {
-    return (size_t)(d.threads / 32) * d.nc * 8 + (size_t)((d.Kell + 1) & ~1) * 8 + (size_t)d.K * 8 +
+    return (size_t)(B2N_NS_THREADS / 32) * d.nc * 8 + (size_t)((d.Kell + 1) & ~1) * 8 + (size_t)d.K * 8 +
            (size_t)(d.Kell + 2) * 4 + 64;
 }
 static size_t ns_commit_smem(const NsDev& d) {
@@ -630,7 +633,7 @@ int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_sta
     B2N_TRY(ns_chain_call(ctx, ns, true));               // chains per CTA the chain kernel plans for
     d.cpc = ctx->dyn.cpc;
     const size_t smem = ns_propose_smem(d), csmem = ns_commit_smem(d);
-    if (smem > (size_t)ctx->max_smem_optin || csmem + 8192 + 64 > (size_t)ctx->max_smem_optin)
+    if (smem > (size_t)ctx->max_smem_optin || csmem + 1024 > (size_t)ctx->max_smem_optin)
         return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "nlive / batch too large for the one-CTA kernels of b2n_ns_run");
     B2N_CUDA(ctx, cudaFuncSetAttribute(ns_propose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B2N_CUDA(ctx, cudaFuncSetAttribute(ns_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
@@ -641,7 +644,7 @@ int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_sta
     while (left > 0) {
         const int chunk = std::min(left, (int)check_every);
         for (int r = 0; r < chunk; r++) {
-            ns_propose_kernel<<<1, d.threads, smem, ctx->stream>>>(d);
+            ns_propose_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d);
             B2N_LAUNCH_CHECK(ctx);
             B2N_TRY(ns_chain_call(ctx, ns, false));
             ns_commit_kernel<<<1, d.threads, csmem, ctx->stream>>>(d);
