@@ -163,7 +163,7 @@ def run_reference(args, cfg):
     pool = mp.get_context('fork').Pool(cores) if cores > 1 else None
     state = make_state(cfg['ndim'], cfg['nlive'])
     kind = reference_kind()
-    per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    per_step = float(os.environ.get('B2N_BENCH_CPU_SECONDS', max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))))
     for _ in range(args.warmup):
         cpu_sample(cfg, per_step, pool, cores, state, kind)
     tot_p = tot_t = 0.0

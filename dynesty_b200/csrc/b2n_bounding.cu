@@ -359,6 +359,241 @@ __global__ void __launch_bounds__(1024) eig_ladder_kernel(NodeArrays na, const i
     }
 }
 
+// ------------------------------------------------------------------ candidate nodes: Cholesky path
+// _bounding_ellipsoids (bounding.py:1464-1563) fits an ellipsoid to EVERY node of the candidate tree --
+// it always recurses into both children before its two volume tests -- but returns only the accepted
+// leaves (one, for a unimodal live set).  What the recursion needs from a candidate is (i) its
+// log-volume, (ii) its precision matrix (for the fmax rescale, :1438-1450) and (iii) its major axis
+// (k-means start centres, :278-284, 1500-1501); none of that needs the full eigen-decomposition, which
+// is the latency-bound part of a bound update (0.66 ms per tree level at n = 50).  For a candidate:
+//   Cholesky cov = L L^T  ->  ln det = 2 sum ln L_ii, am = L^-T L^-1;
+//   improve_covar_mat's test (all eigenvalues finite, max > 0, min >= max/1e12, :1343-1352) is certified
+//   by cond_2 <= |cov|_inf |am|_inf < 1e10 (a sufficient condition: then the ladder is a no-op);
+//   major axis by power iteration to 1e-13, written as the LAST column of `axes` (largest eigenvalue).
+// The pivots L_ii^2 are stored where the eigenvalues go (`lam`): scale_finish_kernel's sum of logs is then
+// ln det, and its rescale / singularity test apply unchanged.  A node that cannot be certified (Cholesky
+// break-down, condition bound, slow power iteration: near-degenerate leading eigenvalues) is flagged
+// `suspect` and the caller redoes the whole update with the eigen path.  Accepted leaves are always
+// re-fitted with the eigen path (they need axes / axlens), so outputs never come from this kernel.
+__global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int* __restrict__ nodelist) {
+    extern __shared__ double sm[];
+    const int n = na.n, ld = na.ld, tid = threadIdx.x, T = blockDim.x;
+    const int node = nodelist[blockIdx.x];
+    const size_t nn = (size_t)n * n;
+    double* L = sm;                          // n x ld: lower triangle = Cholesky factor (diag kept apart)
+    double* Li = L + (size_t)n * ld;         // n x ld: L^-1 (lower)
+    double* dg = Li + (size_t)n * ld;        // n: pivots L_ii
+    double* v = dg + n;                      // n: power-iteration vector
+    double* y = v + n;                       // n
+    double* red = y + n;                     // 32
+    __shared__ int s_bad, s_it;
+    __shared__ double s_lam, s_diff;
+    const double* src = na.covraw + (size_t)node * nn;
+    double* Cm = na.cov + (size_t)node * nn;
+    NodeStat* st = na.stat + node;
+    for (size_t e = tid; e < nn; e += T) {
+        const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+        const double c = src[e];
+        Cm[e] = c;
+        L[(size_t)i * ld + j] = c;
+    }
+    if (tid == 0) { s_bad = 0; s_it = 0; }
+    __syncthreads();
+    // ---- |cov|_inf
+    double rs = 0.0;
+    for (int i = tid; i < n; i += T) {
+        double a = 0.0;
+        for (int j = 0; j < n; j++) a += fabs(L[(size_t)i * ld + j]);
+        rs = fmax(rs, a);
+    }
+    rs = warp_max(rs);
+    if ((tid & 31) == 0) red[tid >> 5] = rs;
+    __syncthreads();
+    double cnorm = 0.0;
+    for (int w = 0; w < ((T + 31) >> 5); w++) cnorm = fmax(cnorm, red[w]);
+    __syncthreads();
+    // ---- right-looking Cholesky, two barriers per column
+    for (int k = 0; k < n; k++) {
+        const double d = L[(size_t)k * ld + k];
+        if (!(d > 0.0) || !(d < INFINITY)) {       // same value for every thread: uniform exit
+            if (tid == 0) s_bad = 1;
+            break;
+        }
+        const double r = rsqrt(d);
+        if (tid == 0) dg[k] = d * r;               // sqrt(d)
+        for (int i = k + 1 + tid; i < n; i += T) L[(size_t)i * ld + k] *= r;
+        __syncthreads();
+        const int m = n - k - 1;                   // trailing (lower incl. diagonal) update
+        for (int e = tid; e < m * m; e += T) {
+            const int a = e / m, b = e - a * m;
+            if (b <= a) {
+                const int i = k + 1 + a, j = k + 1 + b;
+                L[(size_t)i * ld + j] = fma(-L[(size_t)i * ld + k], L[(size_t)j * ld + k], L[(size_t)i * ld + j]);
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (s_bad) {
+        if (tid == 0) { st->suspect = 1; st->good = 1; st->fallback = 0; st->retry = 0; st->sweeps = 0; }
+        for (int k = tid; k < n; k += T) na.lam[(size_t)node * n + k] = 1.0;
+        return;
+    }
+    // ---- L^-1 by forward substitution, one column per thread
+    for (int j = tid; j < n; j += T) {
+        for (int i = 0; i < j; i++) Li[(size_t)i * ld + j] = 0.0;
+        Li[(size_t)j * ld + j] = 1.0 / dg[j];
+        for (int i = j + 1; i < n; i++) {
+            double a0 = 0.0, a1 = 0.0;
+            int m = j;
+            for (; m + 1 < i; m += 2) {
+                a0 = fma(L[(size_t)i * ld + m], Li[(size_t)m * ld + j], a0);
+                a1 = fma(L[(size_t)i * ld + m + 1], Li[(size_t)(m + 1) * ld + j], a1);
+            }
+            if (m < i) a0 = fma(L[(size_t)i * ld + m], Li[(size_t)m * ld + j], a0);
+            Li[(size_t)i * ld + j] = -(a0 + a1) / dg[i];
+        }
+    }
+    __syncthreads();
+    // ---- am = L^-T L^-1 (symmetric), |am|_inf
+    double* AM = na.am + (size_t)node * nn;
+    for (size_t e = tid; e < nn; e += T) {
+        const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+        const int m0 = i > j ? i : j;
+        double a = 0.0;
+        for (int m = m0; m < n; m++) a = fma(Li[(size_t)m * ld + i], Li[(size_t)m * ld + j], a);
+        AM[e] = a;
+    }
+    __syncthreads();
+    rs = 0.0;
+    for (int i = tid; i < n; i += T) {
+        double a = 0.0;
+        for (int j = 0; j < n; j++) a += fabs(AM[(size_t)i * n + j]);
+        rs = fmax(rs, a);
+    }
+    rs = warp_max(rs);
+    if ((tid & 31) == 0) red[tid >> 5] = rs;
+    __syncthreads();
+    double anorm = 0.0;
+    for (int w = 0; w < ((T + 31) >> 5); w++) anorm = fmax(anorm, red[w]);
+    __syncthreads();
+    // ---- major axis.  Plain power iteration stalls on the deep nodes of the tree (a half of a half of a
+    //      Gaussian cloud has a leading eigenvalue within a few % of the next ones), so the dominant
+    //      eigenvector is extracted by REPEATED SQUARING: M <- M^2 / |M^2|_F, 18 times = the 2^18-th power of
+    //      cov in 18 small matrix products (the two Cholesky work matrices are free now).  M converges to
+    //      v1 v1^T (|.|_F = 1, trace 1); a gap below ~1e-4 leaves trace(M) != 1 and is flagged suspect.
+    double* A = L;
+    double* B = Li;
+    {
+        double ss = 0.0;
+        for (size_t e = tid; e < nn; e += T) { const double c = src[e]; ss = fma(c, c, ss); }
+        const double inv = rsqrt(block_sum(ss, red));
+        for (size_t e = tid; e < nn; e += T) {
+            const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+            A[(size_t)i * ld + j] = src[e] * inv;
+        }
+        __syncthreads();
+    }
+    for (int sq = 0; sq < 18; sq++) {
+        double ss = 0.0;
+        for (size_t e = tid; e < nn; e += T) {
+            const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+            if (j > i) continue;                       // symmetric: lower triangle, mirrored below
+            double a0 = 0.0, a1 = 0.0;
+            const double* ri = A + (size_t)i * ld;
+            const double* rj = A + (size_t)j * ld;
+            int m = 0;
+            for (; m + 1 < n; m += 2) { a0 = fma(ri[m], rj[m], a0); a1 = fma(ri[m + 1], rj[m + 1], a1); }
+            if (m < n) a0 = fma(ri[m], rj[m], a0);
+            const double bij = a0 + a1;
+            B[(size_t)i * ld + j] = bij;
+            B[(size_t)j * ld + i] = bij;
+            ss = fma(bij, bij, (i == j) ? ss : fma(bij, bij, ss));
+        }
+        const double inv = rsqrt(block_sum(ss, red));
+        for (size_t e = tid; e < nn; e += T) {
+            const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+            B[(size_t)i * ld + j] *= inv;
+        }
+        __syncthreads();
+        double* t = A; A = B; B = t;
+    }
+    // trace test + the column of the largest diagonal entry as the start of two clean-up power steps on cov
+    if (tid == 0) {
+        double tr = 0.0;
+        int jm = 0;
+        for (int i = 0; i < n; i++) {
+            tr += A[(size_t)i * ld + i];
+            if (A[(size_t)i * ld + i] > A[(size_t)jm * ld + jm]) jm = i;
+        }
+        s_diff = fabs(tr - 1.0);
+        s_it = jm;
+    }
+    __syncthreads();
+    const double trdev = s_diff;
+    {
+        const int jm = s_it;
+        double ss = 0.0;
+        for (int i = tid; i < n; i += T) { const double c = A[(size_t)i * ld + jm]; ss = fma(c, c, ss); }
+        const double inv = rsqrt(block_sum(ss, red));
+        for (int i = tid; i < n; i += T) v[i] = A[(size_t)i * ld + jm] * inv;
+        __syncthreads();
+    }
+    double lam = 0.0;
+    bool conv = false;
+    int it = 0;
+    for (; it < 3; it++) {
+        for (int i = tid; i < n; i += T) {
+            double a0 = 0.0, a1 = 0.0;
+            const double* row = src + (size_t)i * n;
+            int j = 0;
+            for (; j + 1 < n; j += 2) { a0 = fma(row[j], v[j], a0); a1 = fma(row[j + 1], v[j + 1], a1); }
+            if (j < n) a0 = fma(row[j], v[j], a0);
+            y[i] = a0 + a1;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            double ss = 0.0;
+            for (int i = tid; i < n; i += 32) ss = fma(y[i], y[i], ss);
+            ss = warp_sum(ss);
+            const double nrm = sqrt(ss), inv = 1.0 / nrm;
+            double df = 0.0;
+            for (int i = tid; i < n; i += 32) {
+                const double nv = y[i] * inv;
+                df = fmax(df, fabs(nv - v[i]));
+                v[i] = nv;
+            }
+            df = warp_max(df);
+            if (tid == 0) { s_lam = nrm; s_diff = df; }
+        }
+        __syncthreads();
+        lam = s_lam;
+        conv = s_diff < 1e-11 && trdev < 1e-6;
+    }
+    // sign convention: the component of largest magnitude is positive
+    if (tid == 0) {
+        int im = 0;
+        for (int i = 1; i < n; i++) if (fabs(v[i]) > fabs(v[im])) im = i;
+        s_lam = v[im] < 0.0 ? -1.0 : 1.0;
+    }
+    __syncthreads();
+    const double sgn = s_lam, ax = sqrt(lam);
+    double* AX = na.axes + (size_t)node * nn;
+    for (size_t e = tid; e < nn; e += T) {
+        const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+        AX[e] = (j == n - 1) ? sgn * v[i] * ax : 0.0;
+    }
+    for (int k = tid; k < n; k += T) na.lam[(size_t)node * n + k] = dg[k] * dg[k];
+    if (tid == 0) {
+        const bool ok = conv && (cnorm * anorm < 1e10) && (lam > 0.0);
+        st->suspect = ok ? 0 : 1;
+        st->good = 1;
+        st->fallback = 0;
+        st->sweeps = it;
+        st->retry = 0;
+    }
+}
+
 // ------------------------------------------------------------------ fmax + rescale + finish
 __global__ void __launch_bounds__(256) fmax_partial_kernel(const double* __restrict__ P, const int* __restrict__ perm,
                                                            int64_t N, NodeArrays na, const JobL* __restrict__ jobs,
@@ -485,7 +720,8 @@ int b2n_boundwork_init(b2n_ctx* ctx, BoundWork& w, const double* dP, int64_t N, 
 
 // Full bounding_ellipsoid (bounding.py:1387-1461) for every node in `refs`.
 // On return `stats` holds the per-node NodeStat (host copy); the stream is synchronised.
-int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::vector<NodeStat>& stats) {
+int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::vector<NodeStat>& stats,
+                      bool candidate) {
     b2n_ctx* ctx = w.ctx;
     const int n = w.n;
     const size_t nn = (size_t)n * n;
@@ -581,8 +817,13 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
         }
         // large n: packed-triangle / column-sliced Jacobi (b2n_eig_sliced.cu); else the single-CTA kernel
         int sliced = 0;
-        if (!use_smem) B2N_TRY(b2n_eig_sliced(w, (const int*)plist, pn, pass, 0, &sliced));
-        if (!sliced) {
+        if (candidate) {            // Cholesky path (pass 0 only: certified nodes never need the second pass)
+            const size_t csm = (size_t)(2 * n * ld + 3 * n + 32) * sizeof(double);
+            B2N_CUDA(ctx, cudaFuncSetAttribute(chol_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+            chol_node_kernel<<<pn, 512, csm, st>>>(w.na, (const int*)plist);
+            B2N_LAUNCH_CHECK(ctx);
+        } else if (!use_smem) B2N_TRY(b2n_eig_sliced(w, (const int*)plist, pn, pass, 0, &sliced));
+        if (!candidate && !sliced) {
             eig_ladder_kernel<<<pn, eig_threads, eig_smem, st>>>(w.na, (const int*)plist, pass, gwork, use_smem);
             B2N_LAUNCH_CHECK(ctx);
         }

@@ -20,6 +20,9 @@ struct NodeStat {
     int sweeps;      // Jacobi sweeps of the last decomposition (diagnostic)
     int trial;       // repair-ladder trial counter (sliced path: one decomposition per launch)
     int retry;       // 1 = covariance was modified, decompose again (bounding.py:1362-1371)
+    int suspect;     // candidate (Cholesky) path only: conditioning / convergence not certified -> the caller
+                     // redoes the whole update with the full eigen path
+    int pad;
     double fmax;     // max_i delta_i^T am delta_i                           bounding.py:1438
     double mult;     // covariance scaling applied after pass 0              bounding.py:1444-1450
     double logvol;
@@ -63,7 +66,11 @@ struct BoundWork {
 #ifdef __cplusplus
 #include <vector>
 int b2n_boundwork_init(b2n_ctx* ctx, BoundWork& w, const double* dP, int64_t N, int n, int cap);
-int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs, std::vector<NodeStat>& stats);
+// candidate = false: the full path (eigen-decomposition + repair ladder).  candidate = true: nodes that
+// are only CANDIDATES of the multi-ellipsoid tree (bounding.py:1464-1563 evaluates every candidate but
+// returns few): Cholesky-based precision / log-volume + power-iteration major axis, see chol_node_kernel.
+int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs, std::vector<NodeStat>& stats,
+                      bool candidate = false);
 int b2n_emit_node(BoundWork& w, int node, int k, double* ctr, double* cov, double* am, double* axes, double* axlens);
 int b2n_init_identity_perm(BoundWork& w);
 int b2n_eig_sliced(BoundWork& w, const int* dlist, int pn, int pass, int retry_only, int* used);

@@ -189,59 +189,6 @@ __device__ __forceinline__ double ball_direction(ChainRng& g, int offx, int nc, 
     return pow(U, inv_nc) / sqrt(ss);
 }
 
-// DU directions of DU consecutive steps of one chain at once (same draw events, same ticks as DU
-// calls of ball_direction): the DU Philox / log / sqrt / sincospi dependency chains are written
-// stage by stage so that they sit between the SAME warp-synchronous points -- ptxas does not
-// move arithmetic across the shuffles of separate calls (checked in SASS), so only this form
-// overlaps the latencies.  offx[s] = destination of direction s; fac[s] = U^(1/nc) / |z|.
-// Needs nc <= 62 (the radius block rides on lane 31); `count` <= DU directions are produced.
-template <int DU>
-__device__ __forceinline__ void ball_directions(ChainRng& g, const int (&offx)[DU], int count, int nc, int lane,
-                                                double inv_nc, double (&fac)[DU]) {
-    const int nb = (nc + 1) >> 1;
-    const bool isr = lane == 31;
-    uint4 r[DU];
-#pragma unroll
-    for (int s = 0; s < DU; s++)
-        r[s] = curand_Philox4x32_10(
-            make_uint4(isr ? 0u : (uint32_t)lane, g.tick + 2u * s + (isr ? 1u : 0u), g.c2, g.c3), g.key);
-    double lg[DU], z0[DU], z1[DU], ss[DU];
-#pragma unroll
-    for (int s = 0; s < DU; s++) {
-        const double u0 = b2n_u52(r[s].x, r[s].y), u1 = b2n_u52(r[s].z, r[s].w);
-        lg[s] = log(u0);
-        const double rad = sqrt(-2.0 * lg[s]);
-        double sn, cs;
-        sincospi(2.0 * u1, &sn, &cs);
-        z0[s] = rad * cs;
-        z1[s] = rad * sn;
-    }
-#pragma unroll
-    for (int s = 0; s < DU; s++) {
-        ss[s] = 0.0;
-        if (lane < nb && s < count) {
-            ss[s] = z0[s] * z0[s];
-            if (2 * lane + 1 < nc) {
-                *reinterpret_cast<double2*>(&b2n_sm[offx[s] + 2 * lane]) = make_double2(z0[s], z1[s]);
-                ss[s] = fma(z1[s], z1[s], ss[s]);
-            } else {
-                b2n_sm[offx[s] + 2 * lane] = z0[s];
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int s = 0; s < DU; s++) ss[s] += __shfl_xor_sync(B2N_FULL, ss[s], o);
-    }
-#pragma unroll
-    for (int s = 0; s < DU; s++) {
-        const double lgU = __shfl_sync(B2N_FULL, lg[s], 31);
-        fac[s] = exp(lgU * inv_nc) / sqrt(ss[s]);
-    }
-    g.tick += 2u * (uint32_t)count;
-}
-
 // Stage a column-major matrix (n x n, ld = n in global) into b2n_sm with padded leading dim.
 __device__ __forceinline__ void stage_matrix(const double* __restrict__ g, int off, int n, int ldp) {
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {

@@ -109,6 +109,7 @@ struct b2n_ctx {
     PeerState peer;
     DynLaunch dyn;
     b2n_ns* ns = nullptr;
+    int bound_fast_skip = 0;    // b2n_multi_decompose: updates left to skip the Cholesky candidate path
 };
 void b2n_ns_release(b2n_ctx* ctx);
 

@@ -224,8 +224,12 @@ static void resolve(const std::vector<HNode>& t, int id, int n, std::vector<int>
 
 // Decompose the node (level 0 of w.perm, segment [0, count)) -> final leaves.
 // Leaves' arrays stay in w.na; returns node ids + final perm buffer index.
+#define B2N_RETRY_FULL (-1000)    // internal: a candidate node could not be certified, redo with the eigen path
+
+// fast = true: candidates of the tree go through the Cholesky path (chol_node_kernel), only the accepted
+// leaves are fitted with the eigen path; returns B2N_RETRY_FULL if a candidate cannot be certified.
 static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vector<int>& leaves, int& final_level,
-                     uint32_t* warn) {
+                     uint32_t* warn, bool fast = false) {
     b2n_ctx* ctx = w.ctx;
     const int n = w.n;
     cudaStream_t st = ctx->stream;
@@ -237,9 +241,10 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
     memset(&refs[0], 0, sizeof(NodeRef));
     refs[0].node = 0; refs[0].start = 0; refs[0].count = count; refs[0].level = 0;
     std::vector<NodeStat> hs;
-    B2N_TRY(b2n_process_nodes(w, refs, hs));
+    B2N_TRY(b2n_process_nodes(w, refs, hs, fast));
+    if (fast && hs[0].suspect) return B2N_RETRY_FULL;
     if (hs[0].fallback && warn) *warn |= B2N_WARN_IDENTITY_FALLBACK;
-    if (hs[0].error) return hs[0].error;
+    if (hs[0].error) return fast ? B2N_RETRY_FULL : hs[0].error;
     tree[0].logvol = hs[0].logvol;
 
     // scale = std of the ROOT points, reused at every depth (:1503-1504, 1548-1549)
@@ -320,8 +325,9 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
             }
         }
         if (!crefs.empty()) {
-            B2N_TRY(b2n_process_nodes(w, crefs, hs));
+            B2N_TRY(b2n_process_nodes(w, crefs, hs, fast));
             for (size_t i = 0; i < crefs.size(); i++) {
+                if (fast && (hs[i].suspect || hs[i].error)) return B2N_RETRY_FULL;
                 if (hs[i].fallback && warn) *warn |= B2N_WARN_IDENTITY_FALLBACK;
                 if (hs[i].error) return hs[i].error;
                 tree[crefs[i].node].logvol = hs[i].logvol;
@@ -332,6 +338,23 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
     leaves.clear();
     resolve(tree, 0, n, leaves);
     final_level = cur;
+    if (fast) {
+        // the accepted leaves get the full fit (eigen-decomposition: axes, axlens, and the reference's exact
+        // ladder / rescale); a leaf's points are the segment [start, start+count) of EITHER index buffer as a
+        // set (partitions only permute inside segments), so the last buffer serves all of them
+        std::vector<NodeRef> lrefs(leaves.size());
+        for (size_t k = 0; k < leaves.size(); k++) {
+            memset(&lrefs[k], 0, sizeof(NodeRef));
+            lrefs[k].node = leaves[k]; lrefs[k].start = tree[leaves[k]].start; lrefs[k].count = tree[leaves[k]].count;
+            lrefs[k].level = cur;
+        }
+        B2N_TRY(b2n_process_nodes(w, lrefs, hs, false));
+        for (size_t k = 0; k < leaves.size(); k++) {
+            if (hs[k].fallback && warn) *warn |= B2N_WARN_IDENTITY_FALLBACK;
+            if (hs[k].error) return hs[k].error;
+            tree[leaves[k]].logvol = hs[k].logvol;
+        }
+    }
     return B2N_OK;
 }
 
@@ -367,7 +390,21 @@ extern "C" int b2n_multi_decompose(b2n_ctx* ctx, const double* points, int64_t N
     std::vector<HNode> tree;
     std::vector<int> leaves;
     int level = 0;
-    B2N_TRY(decompose(w, (int)N, tree, leaves, level, warn));
+    // candidates through the Cholesky path when the two work matrices fit in shared memory (n <= ~117)
+    // and the path has not just failed to certify a node of this problem (ctx->bound_fast_skip)
+    const char* fenv = getenv("B2N_BOUND_FAST");
+    const int ldw = n | 1;
+    bool fast = !(fenv && !strcmp(fenv, "0")) && N >= 4 * (int64_t)n &&
+                (size_t)(2 * n * ldw + 3 * n + 32) * sizeof(double) <= (size_t)ctx->max_smem_optin;
+    if (fast && ctx->bound_fast_skip > 0) { ctx->bound_fast_skip--; fast = false; }
+    int dst = decompose(w, (int)N, tree, leaves, level, warn, fast);
+    if (dst == B2N_RETRY_FULL) {
+        ctx->bound_fast_skip = 16;
+        if (warn) *warn = 0;
+        B2N_TRY(b2n_init_identity_perm(w));
+        dst = decompose(w, (int)N, tree, leaves, level, warn, false);
+    }
+    if (dst != B2N_OK) return dst;
     const int K = (int)leaves.size();
     *nells = K;
     if (K > max_ells) return B2N_ERR_TOO_MANY_ELLS;

@@ -285,7 +285,11 @@ class NestedSampler:
         smp, n, N = self.internal_sampler, self.ndim, self.nlive
         kind = 0 if isinstance(smp, S.B200RWalkSampler) else (1 if isinstance(smp, S.B200RSliceSampler) else 2)
         steps = smp.sampler_kwargs['walks' if kind == 0 else 'slices']
-        K = int(batch or max(1, N // 10))
+        # default batch: rwalk chains use a proposal shape estimated from the live points and mix slowly along
+        # under-estimated directions; the resulting logZ bias grows with the fraction of the live set replaced
+        # per round: nlive/40 reproduces the reference's serial result.  Slice chains
+        # decorrelate: nlive/10.
+        K = int(batch or max(1, N // (40 if kind == 0 else 10)))
         self.batch = K
         ops.ns_create(self.model.model_id(self.ctx), N, n, K, kind, steps, self.seed, chain0=self.chain_counter,
                       ncdim=self.ncdim, strict_contains=not isinstance(self.bound, B.B200Ellipsoid),
@@ -354,7 +358,7 @@ class NestedSampler:
                         live points at once and replaces them with `batch` chains evolved at the
                         threshold of the batch-th lowest -- no stale-threshold filter, hence no
                         selection bias for correlated chains, no host round trip
-                        per iteration.  batch defaults to nlive // 10."""
+                        per iteration.  batch defaults to nlive // 40 (rwalk) or nlive // 10 (slices)."""
         if loop not in ('host', 'device'):
             raise ValueError("loop must be 'host' or 'device'")
         if loop == 'device' and (self.comm is not None or self.bound_next is None or
