@@ -18,6 +18,8 @@
 #include <vector>
 
 // ------------------------------------------------------------------ moments
+#define B2N_FMAX_SUB 4     // CTAs per 128-row job in the fmax scan
+
 struct JobL {   // MomentJob + perm level
     int node, r0, r1, slot, level, pad0, pad1, pad2;
 };
@@ -608,7 +610,10 @@ __global__ void __launch_bounds__(256) fmax_partial_kernel(const double* __restr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* d = sm + (size_t)warp * n;
     double best = -INFINITY;
-    for (int r = jb.r0 + warp; r < jb.r1; r += 8) {
+    // a job's rows are dealt over gridDim.y CTAs (a 2000-point node is only 16 jobs: too few CTAs otherwise)
+    const int chunk = (jb.r1 - jb.r0 + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int rb = jb.r0 + (int)blockIdx.y * chunk, re = min(rb + chunk, jb.r1);
+    for (int r = rb + warp; r < re; r += 8) {
         const size_t row = (size_t)pm[r] * n;
         __syncwarp();
         for (int i = lane; i < n; i += 32) d[i] = P[row + i] - mu[i];
@@ -628,13 +633,13 @@ __global__ void __launch_bounds__(256) fmax_partial_kernel(const double* __restr
     if (threadIdx.x == 0) {
         double b = wmax[0];
         for (int w = 1; w < 8; w++) b = fmax(b, wmax[w]);
-        partial[jb.slot] = b;
+        partial[(size_t)jb.slot * gridDim.y + blockIdx.y] = b;
     }
 }
 
 __global__ void __launch_bounds__(256) scale_finish_kernel(NodeArrays na, const NodeRef* __restrict__ refs,
                                                            const double* __restrict__ partial, int pass,
-                                                           double logvol_pref) {
+                                                           double logvol_pref, int nsub) {
     __shared__ double s_mult;
     __shared__ double red[32];
     const int n = na.n, tid = threadIdx.x, T = blockDim.x;
@@ -644,7 +649,7 @@ __global__ void __launch_bounds__(256) scale_finish_kernel(NodeArrays na, const 
     if (st->retry) return;          // covariance still being repaired: decomposed again first
     if (tid == 0) {
         double fm = -INFINITY;
-        for (int k = 0; k < nr.nslots; k++) fm = fmax(fm, partial[nr.slot0 + k]);
+        for (int k = 0; k < nr.nslots * nsub; k++) fm = fmax(fm, partial[(size_t)nr.slot0 * nsub + k]);
         st->fmax = fm;
         double mult = 1.0;
         if (pass == 0) {
@@ -827,9 +832,9 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
             eig_ladder_kernel<<<pn, eig_threads, eig_smem, st>>>(w.na, (const int*)plist, pass, gwork, use_smem);
             B2N_LAUNCH_CHECK(ctx);
         }
-        fmax_partial_kernel<<<pj, 256, fm_smem, st>>>(w.P, w.perm, w.N, w.na, (const JobL*)pjobs, partial);
+        fmax_partial_kernel<<<dim3(pj, B2N_FMAX_SUB), 256, fm_smem, st>>>(w.P, w.perm, w.N, w.na, (const JobL*)pjobs, partial);
         B2N_LAUNCH_CHECK(ctx);
-        scale_finish_kernel<<<pn, 256, 0, st>>>(w.na, (const NodeRef*)prefs, partial, pass, w.logvol_pref);
+        scale_finish_kernel<<<pn, 256, 0, st>>>(w.na, (const NodeRef*)prefs, partial, pass, w.logvol_pref, B2N_FMAX_SUB);
         B2N_LAUNCH_CHECK(ctx);
         // read back the node stats (one copy of the whole small array)
         B2N_CUDA(ctx, cudaStreamSynchronize(st));
@@ -869,9 +874,9 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
             B2N_TRY(b2n_in_host(ctx, ctx->work0, list3.data(), list3.size() * sizeof(int), &l3));
             int used = 0;
             B2N_TRY(b2n_eig_sliced(w, (const int*)l3, (int)refs3.size(), pass, 1, &used));
-            fmax_partial_kernel<<<(unsigned)jobs3.size(), 256, fm_smem, st>>>(w.P, w.perm, w.N, w.na, (const JobL*)j3, partial);
+            fmax_partial_kernel<<<dim3((unsigned)jobs3.size(), B2N_FMAX_SUB), 256, fm_smem, st>>>(w.P, w.perm, w.N, w.na, (const JobL*)j3, partial);
             B2N_LAUNCH_CHECK(ctx);
-            scale_finish_kernel<<<(unsigned)refs3.size(), 256, 0, st>>>(w.na, (const NodeRef*)r3, partial, pass, w.logvol_pref);
+            scale_finish_kernel<<<(unsigned)refs3.size(), 256, 0, st>>>(w.na, (const NodeRef*)r3, partial, pass, w.logvol_pref, B2N_FMAX_SUB);
             B2N_LAUNCH_CHECK(ctx);
             B2N_CUDA(ctx, cudaStreamSynchronize(st));
             B2N_CUDA(ctx, cudaMemcpy(all.data(), w.na.stat, (size_t)w.cap * sizeof(NodeStat), cudaMemcpyDeviceToHost));

@@ -201,3 +201,6 @@ __device__ __forceinline__ void stage_matrix(const double* __restrict__ g, int o
 int b2n_build_worklist(b2n_ctx* ctx, int64_t Q, const int32_t* ell, int K, int chains_per_cta,
                        std::vector<int>& order, std::vector<int3>& cta);
 void b2n_chain_grid(const b2n_ctx* ctx, int64_t Q, int max_warps, int& chains_per_cta, int& warps);
+// worklist on the device: cached for the single-ellipsoid case, else built on the host and uploaded
+int b2n_worklist_dev(b2n_ctx* ctx, int64_t Q, const int32_t* ell, int K, int chains_per_cta, const void** dorder,
+                     const void** dcta, unsigned* ncta);

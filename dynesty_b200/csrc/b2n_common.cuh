@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "../../include/b200nest.h"
@@ -110,6 +111,12 @@ struct b2n_ctx {
     DynLaunch dyn;
     b2n_ns* ns = nullptr;
     int bound_fast_skip = 0;    // b2n_multi_decompose: updates left to skip the Cholesky candidate path
+    bool zc_enabled = false;    // chain entry points, host-pointer mode: pinned caller buffers are used in place
+    // cached chain worklist of the single-ellipsoid case (identity order, equal CTAs): rebuilt only when
+    // (Q, chains per CTA) change -- saves two small pageable H2D copies per queue fill
+    DevBuf wl_order, wl_cta;
+    int64_t wl_Q = -1;
+    int wl_cpc = 0, wl_ncta = 0;
 };
 void b2n_ns_release(b2n_ctx* ctx);
 
@@ -152,10 +159,30 @@ static inline int b2n_fail(b2n_ctx* ctx, int status, const char* msg) {
     return status;
 }
 
+// Zero-copy for PINNED caller buffers (host-pointer mode, chain entry points only: their inputs are read
+// once and their outputs written once).  Under UVA a cudaHostAlloc'ed buffer is addressable from the device
+// by its host address: the kernel then reads the start points / writes the finished chains straight over
+// PCIe -- the transfer overlaps the kernel instead of following it as a DMA copy.  Pageable memory (plain
+// numpy arrays) keeps the staged path.
+static inline bool b2n_zc_ok(b2n_ctx* ctx, const void* p) {
+    if (!ctx->zc_enabled || p == nullptr) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost && a.devicePointer == p;
+}
+struct ZcScope {          // enables zero-copy for the lifetime of a chain entry call
+    b2n_ctx* c;
+    explicit ZcScope(b2n_ctx* ctx) : c(ctx) {
+        const char* e = getenv("B2N_ZERO_COPY");
+        c->zc_enabled = c->ptr_mode == B2N_PTR_HOST && !(e && e[0] == '0');
+    }
+    ~ZcScope() { c->zc_enabled = false; }
+};
+
 // Input staging: returns a device pointer for `src` (copying when in host mode).
 static inline int b2n_in(b2n_ctx* ctx, DevBuf& buf, const void* src, size_t bytes,
                          const void** dev) {
-    if (ctx->ptr_mode == B2N_PTR_DEVICE || src == nullptr || bytes == 0) {
+    if (ctx->ptr_mode == B2N_PTR_DEVICE || src == nullptr || bytes == 0 || b2n_zc_ok(ctx, src)) {
         *dev = src;
         return B2N_OK;
     }
@@ -176,13 +203,13 @@ static inline int b2n_in_host(b2n_ctx* ctx, DevBuf& buf, const void* src, size_t
 // Output staging: device pointer to write into.
 static inline int b2n_out(b2n_ctx* ctx, DevBuf& buf, void* dst, size_t bytes, void** dev) {
     if (dst == nullptr) { *dev = nullptr; return B2N_OK; }
-    if (ctx->ptr_mode == B2N_PTR_DEVICE) { *dev = dst; return B2N_OK; }
+    if (ctx->ptr_mode == B2N_PTR_DEVICE || b2n_zc_ok(ctx, dst)) { *dev = dst; return B2N_OK; }
     B2N_CUDA(ctx, buf.ensure(bytes));
     *dev = buf.p;
     return B2N_OK;
 }
 static inline int b2n_out_done(b2n_ctx* ctx, void* dst, const void* dev, size_t bytes) {
-    if (dst == nullptr || ctx->ptr_mode == B2N_PTR_DEVICE) return B2N_OK;
+    if (dst == nullptr || ctx->ptr_mode == B2N_PTR_DEVICE || dev == dst) return B2N_OK;   // dev == dst: written in place
     B2N_CUDA(ctx, cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return B2N_OK;
 }

@@ -63,7 +63,7 @@ void b2n_free(b2n_ctx* ctx) {
                       &ctx->in2, &ctx->in3, &ctx->out0, &ctx->out1, &ctx->out2, &ctx->out3,
                       &ctx->out4, &ctx->out5, &ctx->out6, &ctx->out7, &ctx->scratch0,
                       &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->scratch4,
-                      &ctx->scratch5, &ctx->work0, &ctx->work1};
+                      &ctx->scratch5, &ctx->work0, &ctx->work1, &ctx->wl_order, &ctx->wl_cta};
     for (DevBuf* b : bufs) b->release();
     b2n_peer_release(ctx);
     b2n_ns_release(ctx);

@@ -599,6 +599,36 @@ int b2n_build_worklist(b2n_ctx* ctx, int64_t Q, const int32_t* ell, int K, int c
     return B2N_OK;
 }
 
+int b2n_worklist_dev(b2n_ctx* ctx, int64_t Q, const int32_t* ell, int K, int chains_per_cta, const void** dorder,
+                     const void** dcta, unsigned* ncta) {
+    const bool trivial = (ell == nullptr || K == 1);
+    if (trivial && ell)
+        for (int64_t q = 0; q < Q; q++)
+            if (ell[q] != 0) return b2n_fail(ctx, B2N_ERR_ARG, "chain ellipsoid index out of range");
+    if (trivial && ctx->wl_Q == Q && ctx->wl_cpc == chains_per_cta && ctx->wl_order.p && ctx->wl_cta.p) {
+        *dorder = ctx->wl_order.p; *dcta = ctx->wl_cta.p; *ncta = (unsigned)ctx->wl_ncta;
+        return B2N_OK;
+    }
+    std::vector<int> order;
+    std::vector<int3> cta;
+    B2N_TRY(b2n_build_worklist(ctx, Q, trivial ? nullptr : ell, K, chains_per_cta, order, cta));
+    *ncta = (unsigned)cta.size();
+    if (trivial) {
+        // (the buffers may still be read by an enqueued kernel of a device-pointer caller)
+        B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        B2N_CUDA(ctx, ctx->wl_order.ensure(order.size() * sizeof(int)));
+        B2N_CUDA(ctx, ctx->wl_cta.ensure(cta.size() * sizeof(int3)));
+        B2N_CUDA(ctx, cudaMemcpy(ctx->wl_order.p, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+        B2N_CUDA(ctx, cudaMemcpy(ctx->wl_cta.p, cta.data(), cta.size() * sizeof(int3), cudaMemcpyHostToDevice));
+        ctx->wl_Q = Q; ctx->wl_cpc = chains_per_cta; ctx->wl_ncta = (int)cta.size();
+        *dorder = ctx->wl_order.p; *dcta = ctx->wl_cta.p;
+        return B2N_OK;
+    }
+    B2N_TRY(b2n_in_host(ctx, ctx->work0, order.data(), order.size() * sizeof(int), dorder));
+    B2N_TRY(b2n_in_host(ctx, ctx->work1, cta.data(), cta.size() * sizeof(int3), dcta));
+    return B2N_OK;
+}
+
 // Persistent-sized grid: one CTA per SM when every chain can have its own warp
 // (Q <= 16 x SMs), two per SM beyond that; warps loop over their CTA's chains.
 void b2n_chain_grid(const b2n_ctx* ctx, int64_t Q, int max_warps, int& chains_per_cta, int& warps) {
@@ -622,6 +652,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     if (ctx->bK < 1 || ctx->bn != nc) return b2n_fail(ctx, B2N_ERR_ARG, "resident bound missing or of wrong dimension (b2n_bound_set)");
     if (Q == 0) return gather ? b2n_fail(ctx, B2N_ERR_ARG, "gather mode: every rank must run at least one chain") : B2N_OK;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZcScope zc(ctx);          // pinned caller buffers are read / written in place (host-pointer mode)
 
     // shared-memory plan: per-warp state always; matrices (128-byte padded columns) when they fit
     const int npad = (n + 1) & ~1;
@@ -688,10 +719,6 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         if (ctx->dyn.plan_only) return B2N_OK;
         if (gather || ctx->ptr_mode != B2N_PTR_DEVICE) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "device-paced launch needs device pointers and no gather mode");
     }
-    std::vector<int> order;
-    std::vector<int3> cta;
-    if (!dyn) B2N_TRY(b2n_build_worklist(ctx, Q, a->ell, ctx->bK, chains_per_cta, order, cta));
-
     RwalkParams p;
     p.dyn = dyn ? ctx->dyn.dev : nullptr;
     p.m = m; p.n = n; p.nc = nc; p.walks = walks; p.ldA = ldA; p.ldP = ldP;
@@ -699,11 +726,11 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     p.axesT = ctx->b_axesT.as<double>();
     const void *du0, *dorder, *dcta, *dfl = nullptr;
     B2N_TRY(b2n_in(ctx, ctx->in0, a->u0, (size_t)Q * n * sizeof(double), &du0));
+    unsigned ncta = 0;
     if (dyn) {
         dorder = ctx->dyn.order; dcta = ctx->dyn.cta;
     } else {
-        B2N_TRY(b2n_in_host(ctx, ctx->work0, order.data(), order.size() * sizeof(int), &dorder));
-        B2N_TRY(b2n_in_host(ctx, ctx->work1, cta.data(), cta.size() * sizeof(int3), &dcta));
+        B2N_TRY(b2n_worklist_dev(ctx, Q, a->ell, ctx->bK, chains_per_cta, &dorder, &dcta, &ncta));
     }
     std::vector<uint32_t> fl;
     if (a->dimflags) {
@@ -730,7 +757,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     p.u = (double*)du; p.v = (double*)dv; p.logl = (double*)dl;
     p.nacc = (int*)dna; p.nrej = (int*)dnr; p.ncall = (int*)dncl;
 
-    const unsigned grid = dyn ? (unsigned)ctx->dyn.max_cta : (unsigned)cta.size();
+    const unsigned grid = dyn ? (unsigned)ctx->dyn.max_cta : ncta;
 #define LAUNCH(L, AXS, PRS)                                                                       \
     do {                                                                                          \
         B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_kernel<L, AXS, PRS>,                             \

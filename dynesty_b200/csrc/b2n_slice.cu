@@ -273,6 +273,7 @@ static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slice
     if (ctx->bK < 1 || ctx->bn != n) return b2n_fail(ctx, B2N_ERR_ARG, "resident bound missing or of wrong dimension");
     if (Q == 0) return gather ? b2n_fail(ctx, B2N_ERR_ARG, "gather mode: every rank must run at least one chain") : B2N_OK;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZcScope zc(ctx);          // pinned caller buffers are read / written in place (host-pointer mode)
     const int npad = (n + 1) & ~1;
     const size_t per_warp = (size_t)6 * npad * sizeof(double);           // u, d, un, vn, work, idxs
     const size_t model_b = (size_t)4 * npad * sizeof(double);
@@ -294,9 +295,6 @@ static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slice
         if (ctx->dyn.plan_only) return B2N_OK;
         if (gather || ctx->ptr_mode != B2N_PTR_DEVICE) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "device-paced launch needs device pointers and no gather mode");
     }
-    std::vector<int> order;
-    std::vector<int3> cta;
-    if (!dyn) B2N_TRY(b2n_build_worklist(ctx, Q, a->ell, ctx->bK, chains_per_cta, order, cta));
     SliceParams p;
     p.dyn = dyn ? ctx->dyn.dev : nullptr;
     p.m = m; p.n = n; p.slices = slices; p.doubling = doubling; p.ldA = ldA; p.ldP = ldP;
@@ -304,11 +302,11 @@ static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slice
     p.axesT = ctx->b_axesT.as<double>();
     const void *du0, *dorder, *dcta;
     B2N_TRY(b2n_in(ctx, ctx->in0, a->u0, (size_t)Q * n * sizeof(double), &du0));
+    unsigned ncta = 0;
     if (dyn) {
         dorder = ctx->dyn.order; dcta = ctx->dyn.cta;
     } else {
-        B2N_TRY(b2n_in_host(ctx, ctx->work0, order.data(), order.size() * sizeof(int), &dorder));
-        B2N_TRY(b2n_in_host(ctx, ctx->work1, cta.data(), cta.size() * sizeof(int3), &dcta));
+        B2N_TRY(b2n_worklist_dev(ctx, Q, a->ell, ctx->bK, chains_per_cta, &dorder, &dcta, &ncta));
     }
     void *du, *dv, *dl, *dne, *dnc, *dncl, *dfl;
     void* gdev[7];
@@ -329,7 +327,7 @@ static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slice
     p.u0 = (const double*)du0; p.order = (const int*)dorder; p.cta = (const int3*)dcta;
     p.u = (double*)du; p.v = (double*)dv; p.logl = (double*)dl;
     p.nexp = (int*)dne; p.ncon = (int*)dnc; p.ncall = (int*)dncl; p.flags = (uint32_t*)dfl;
-    const unsigned grid = dyn ? (unsigned)ctx->dyn.max_cta : (unsigned)cta.size();
+    const unsigned grid = dyn ? (unsigned)ctx->dyn.max_cta : ncta;
 #define LAUNCH(L, AXS, PRS)                                                                          \
     do {                                                                                             \
         B2N_CUDA(ctx, cudaFuncSetAttribute(slice_kernel<L, RANDOM_DIR, AXS, PRS>,                     \

@@ -244,3 +244,37 @@ def test_rwalk_mma_matches_warp_kernel(like):
     np.testing.assert_allclose(b['logl'][same], a['logl'][same], rtol=1e-9, atol=1e-9)
     assert np.all(b['logl'] > loglstar) and np.all(b['n_accept'] + b['n_reject'] == 30)
     assert 0.002 < b['n_accept'].mean() / 30 < 0.98      # (eggbox at 32-D accepts ~1 %)
+
+
+@pytest.mark.parametrize('sampler', ['rwalk', 'rslice'])
+def test_pinned_buffers_are_used_in_place(sampler):
+    """Host-pointer mode with PINNED caller buffers: the chain kernels read the start points and write the
+    finished chains straight through the buffers' device alias (no staging copy, csrc/b2n_common.cuh
+    b2n_zc_ok); results must be identical to the staged path used for pageable numpy arrays."""
+    import torch
+    m = MODELS['g50']
+    dm = device_model(m)
+    rng = np.random.default_rng(11)
+    pts = _cloud(rng, 600, 50, 0.02)
+    e = OB.bounding_ellipsoid(pts)
+    logl = m.loglike(m.prior_transform(pts))
+    loglstar = float(np.quantile(logl, 0.2))
+    u0 = pts[logl > loglstar][:256]
+    Q, n = u0.shape
+    ops.bound_set(e.axes)
+    pin = lambda *s, dt=torch.float64: torch.empty(*s, dtype=dt).pin_memory()
+    h_u0 = pin(Q, n)
+    h_u0.numpy()[:] = u0
+    if sampler == 'rwalk':
+        ref = ops.rwalk_batch(dm.model_id(), u0, loglstar, 0.3, 30, SEED, chain0=7)
+        out = dict(u=pin(Q, n), v=pin(Q, n), logl=pin(Q), n_accept=pin(Q, dt=torch.int32),
+                   n_reject=pin(Q, dt=torch.int32), ncall=pin(Q, dt=torch.int32))
+        for t in out.values():
+            t.zero_()
+        o = ops.rwalk_batch(dm.model_id(), h_u0.numpy(), loglstar, 0.3, 30, SEED, chain0=7,
+                            out={k: t.numpy() for k, t in out.items()})
+    else:
+        ref = ops.rslice_batch(dm.model_id(), u0, loglstar, 0.3, 4, SEED, chain0=7)
+        o = ops.rslice_batch(dm.model_id(), h_u0.numpy(), loglstar, 0.3, 4, SEED, chain0=7)   # pinned input only
+    for k in ref:
+        assert np.array_equal(np.asarray(o[k]), ref[k]), k
