@@ -450,6 +450,12 @@ def run_b200(args, cfg):
                                   "at the problem's parallelism (DESIGN.md 9.1)"),
                          "kernel_ms": kms, "algorithmic_bytes_per_proposal": algorithmic_bytes(n),
                          "peak_source": peak_src},
+            # the byte model above assumes no reuse; the honest ceiling of this kernel is FP64 issue: SURVEY 8(d)'s
+            # 4n^2 + 7n flop per proposal against the chip's nominal FP64 tensor (DMMA) rate
+            "roofline_fp64": {"achieved_tflops": (4 * n * n + 7 * n) * Q * walks / (kms * 1e-3) / 1e12,
+                              "peak_tflops": 45.0, "peak_source": "nominal B200 FP64 tensor rate (blackwell_cuda_programming.md:52)",
+                              "frac": (4 * n * n + 7 * n) * Q * walks / (kms * 1e-3) / 45e12,
+                              "flops_per_proposal": 4 * n * n + 7 * n},
             "clocks": clk,
         }
     if world > 1:

@@ -396,7 +396,7 @@ extern "C" int b2n_multi_decompose(b2n_ctx* ctx, const double* points, int64_t N
     const int ldw = n | 1;
     bool fast = !(fenv && !strcmp(fenv, "0")) && N >= 4 * (int64_t)n &&
                 (size_t)(2 * n * ldw + 3 * n + 32) * sizeof(double) <= (size_t)ctx->max_smem_optin;
-    if (fast && ctx->bound_fast_skip > 0) { ctx->bound_fast_skip--; fast = false; }
+    if (fast && ctx->bound_fast_skip > 0 && !(fenv && fenv[0] == '1')) { ctx->bound_fast_skip--; fast = false; }   // "1" forces the attempt
     int dst = decompose(w, (int)N, tree, leaves, level, warn, fast);
     if (dst == B2N_RETRY_FULL) {
         ctx->bound_fast_skip = 16;

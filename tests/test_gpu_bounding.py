@@ -142,3 +142,38 @@ def test_bootstrap_expand_golden(golden, multi):
     g = golden['multi']
     got = ops.bootstrap_expand(g['me_c2_points'], multi, 4, SEED, 1000)
     np.testing.assert_allclose(got, g['boot_%d_expand' % multi], rtol=1e-8)
+
+
+@pytest.mark.parametrize('case', ['gauss2000x50', 'clusters4000x25', 'grid'])
+def test_candidate_path_equals_eigen_path(case, monkeypatch):
+    """The candidates of the multi-ellipsoid tree go through the Cholesky / matrix-squaring kernel
+    (chol_node_kernel), only the accepted leaves through the eigen path; B2N_BOUND_FAST=0 forces the eigen
+    path for every node.  Same tree, same leaves: nells equal, centres / covariances / log-volumes to
+    round-off (the leaf fits see the points in a different order), every point inside its ellipsoid.
+    'grid' has exactly degenerate spectra: the candidate path cannot certify its nodes and must fall back."""
+    rng = np.random.default_rng(SEED)
+    if case == 'gauss2000x50':
+        Cm = np.full((50, 50), 0.4)
+        np.fill_diagonal(Cm, 1.0)
+        pts = 0.5 + 0.02 * rng.standard_normal((2000, 50)) @ np.linalg.cholesky(Cm).T
+    elif case == 'clusters4000x25':
+        ctrs = 0.2 + 0.6 * rng.random((8, 25))
+        pts = np.concatenate([c + 0.01 * rng.standard_normal((500, 25)) for c in ctrs])
+    else:
+        g1 = np.linspace(0.2, 0.8, 5)
+        pts = np.array(np.meshgrid(g1, g1, g1)).reshape(3, -1).T
+        pts = np.concatenate([pts, pts + 1e-3, pts - 1e-3, pts + 2e-3])
+    monkeypatch.setenv('B2N_BOUND_FAST', '0')
+    slow = ops.multi_decompose(pts)
+    monkeypatch.setenv('B2N_BOUND_FAST', '1')
+    fast = ops.multi_decompose(pts)
+    assert fast['nells'] == slow['nells']
+    a, b = np.lexsort(fast['ctrs'].T[::-1]), np.lexsort(slow['ctrs'].T[::-1])
+    close(fast['ctrs'][a], slow['ctrs'][b], rtol=1e-12)
+    close(fast['covs'][a], slow['covs'][b], rtol=1e-9)
+    close(fast['logvols'][a], slow['logvols'][b], rtol=1e-11)
+    close(fast['ams'][a], slow['ams'][b], rtol=1e-7)
+    mask = ops.membership(pts, fast['ctrs'], fast['ams'])[0]
+    assert mask[np.arange(len(pts)), fast['labels']].all()
+    if case == 'clusters4000x25':
+        assert fast['nells'] == 8
