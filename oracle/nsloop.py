@@ -56,7 +56,7 @@ class BatchNS:
 
     def __init__(self, model, live_u, live_v, live_logl, batch, sampler, steps, seed, chain0=0, facc=0.5,
                  scale=1.0, logvol=0.0, logz=LOWL, loglstar=LOWL, ncall=0, update_interval=1 << 62,
-                 dlogz=0.01, maxiter=1 << 62, maxcall=1 << 62, bound=None):
+                 dlogz=0.01, maxiter=1 << 62, maxcall=1 << 62, bound=None, dimflags=None):
         self.model = model
         self.live_u = np.array(live_u, dtype=float)
         self.live_v = np.array(live_v, dtype=float)
@@ -71,6 +71,13 @@ class BatchNS:
         self.ncall = self.ncall_last_update = int(ncall)
         self.update_interval, self.dlogz, self.maxiter, self.maxcall = update_interval, dlogz, maxiter, maxcall
         self.bound = bound
+        # per-dimension boundary flags (1 periodic, 2 reflective; utils.py:950-976) -> rwalk_chain arguments
+        self.per = self.ref = self.nb = None
+        if dimflags is not None:
+            f = np.asarray(dimflags)
+            self.per = np.nonzero(f & 1)[0] if (f & 1).any() else None
+            self.ref = np.nonzero(f & 2)[0] if (f & 2).any() else None
+            self.nb = f == 0
         self.it = self.round = 0
         self.done = self.need_bound = 0
         self.doubling = False
@@ -136,7 +143,8 @@ class BatchNS:
             st = philox.ChainStream(self.seed, self.chain0 + self.round * K + c)
             u0, ax = self.live_u[starts[c]], b['axes'][ell[c]]
             if self.sampler == 'rwalk':
-                r = OS.rwalk_chain(u0, thr, ax, self.scale, self.model, st, self.steps)
+                r = OS.rwalk_chain(u0, thr, ax, self.scale, self.model, st, self.steps, periodic=self.per,
+                                   reflective=self.ref, nonbounded=self.nb)
             elif self.sampler == 'rslice':
                 r = OS.rslice_chain(u0, thr, ax, self.scale, self.model, st, self.steps, doubling=self.doubling)
             else:

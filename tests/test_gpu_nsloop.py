@@ -55,26 +55,32 @@ CASES = [
     ('gauss', 4, 48, 12, 'slice', 1, False, 2),
     ('shells', 4, 80, 20, 'rwalk', 8, True, 3),        # 2 ellipsoids: volume-weighted picks + grouped worklist
     ('shells', 4, 80, 10, 'rslice', 3, True, 2),
+    ('gauss', 6, 64, 16, 'rwalk', 10, False, 3, dict(ncdim=4)),                  # bound on the first 4 dims only
+    ('gauss', 6, 64, 16, 'rwalk', 10, False, 3, dict(dimflags=[1, 2, 0, 0, 1, 0])),   # periodic / reflective dims
 ]
+CASES = [c if len(c) == 9 else c + ({},) for c in CASES]
 
 
-@pytest.mark.parametrize('kind,n,N,K,sampler,steps,two,rounds', CASES)
-def test_rounds_match_oracle(kind, n, N, K, sampler, steps, two, rounds):
+@pytest.mark.parametrize('kind,n,N,K,sampler,steps,two,rounds,extra', CASES)
+def test_rounds_match_oracle(kind, n, N, K, sampler, steps, two, rounds, extra):
     dm, om = _models(kind, n)
     rng = np.random.default_rng(100 + n + K)
     u, v, l, groups = _live(om, n, N, rng, two)
-    b = _bound(groups)
+    nc = extra.get('ncdim', n)
+    flags = extra.get('dimflags')
+    b = _bound([g[:, :nc] for g in groups])
     seed, chain0, scale0 = 56432, 1000, 0.7
     o = nsloop.BatchNS(om, u, v, l, K, sampler, steps, seed, chain0=chain0, scale=scale0, logvol=-2.5, logz=-40.0,
-                       loglstar=float(l.min()) - 0.5, ncall=500, bound=b, dlogz=1e-6)
+                       loglstar=float(l.min()) - 0.5, ncall=500, bound=b, dlogz=1e-6, dimflags=flags)
     ops.ns_create(dm.model_id(), N, n, K, ('rwalk', 'rslice', 'slice').index(sampler), steps, seed, chain0=chain0,
-                  dlogz=1e-6, dead_capacity=rounds * K + 5)
+                  ncdim=nc, dlogz=1e-6, dead_capacity=rounds * K + 5,
+                  dimflags=None if flags is None else np.array(flags, dtype=np.uint8))
     try:
         ops.ns_set_state(u, v, l, -2.5, -40.0, float(l.min()) - 0.5, 500, scale0)
         for r in range(rounds):
             # the same bound on both sides, rebuilt from the oracle's live set before every round
             # (chains leave a static bound; a start outside it raises need_bound = 2 on both sides)
-            lu = o.live_u
+            lu = o.live_u[:, :nc]
             b = _bound([lu[lu[:, 0] < 0.5], lu[lu[:, 0] >= 0.5]] if two else [lu])
             o.bound = b
             ops.bound_set(b['axes'], b['ctrs'], b['ams'], b['logvols'])
