@@ -362,7 +362,7 @@ def run_b200(args, cfg):
         for _ in range(2500):
             step_dev()
     else:
-        t_ramp = time.perf_counter() + 0.7
+        t_ramp = time.perf_counter() + args.ramp
         while time.perf_counter() < t_ramp:
             step_dev()
     torch.cuda.synchronize()
@@ -537,6 +537,7 @@ def main():
     ap.add_argument('--logz-queue', type=int, default=200, help='queue_size of the host (unit-cube) phase of the logZ runs')
     ap.add_argument('--logz-batch', type=int, default=0, help='points replaced per device round (default nlive/40)')
     ap.add_argument('--cpu-baseline', type=int, default=1)
+    ap.add_argument('--ramp', type=float, default=0.7, help='seconds of untimed steps before timing (clock ramp; 0 under ncu)')
     ap.add_argument('--exchange', default='fused', choices=['fused', 'nccl'],
                     help='N>1: how the finished chains reach every rank')
     args = ap.parse_args()

@@ -496,29 +496,49 @@ __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int
         }
         __syncthreads();
     }
+    // One squaring = n^2/2 dot products of length n out of shared memory on ONE SM: bandwidth bound, so each
+    // thread owns a 2 x 2 tile {ti, ti+nt} x {tj, tj+nt} (rows a tile-stride apart: consecutive threads read
+    // consecutive rows, conflict free with the odd leading dimension) -- one load per FMA instead of two --
+    // and the loop stops as soon as M is a projector to round-off (trace(M) = |M|_F = 1).
+    const int nt = (n + 1) >> 1;
     for (int sq = 0; sq < 18; sq++) {
         double ss = 0.0;
-        for (size_t e = tid; e < nn; e += T) {
-            const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
-            if (j > i) continue;                       // symmetric: lower triangle, mirrored below
-            double a0 = 0.0, a1 = 0.0;
-            const double* ri = A + (size_t)i * ld;
-            const double* rj = A + (size_t)j * ld;
-            int m = 0;
-            for (; m + 1 < n; m += 2) { a0 = fma(ri[m], rj[m], a0); a1 = fma(ri[m + 1], rj[m + 1], a1); }
-            if (m < n) a0 = fma(ri[m], rj[m], a0);
-            const double bij = a0 + a1;
-            B[(size_t)i * ld + j] = bij;
-            B[(size_t)j * ld + i] = bij;
-            ss = fma(bij, bij, (i == j) ? ss : fma(bij, bij, ss));
+        for (int e = tid; e < nt * nt; e += T) {
+            const int ti = e / nt, tj = e - ti * nt;
+            if (tj > ti) continue;
+            const int i0 = ti, i1 = ti + nt, j0 = tj, j1 = tj + nt;
+            const bool vi = i1 < n, vj = j1 < n;
+            const double* r0 = A + (size_t)i0 * ld;
+            const double* r1 = A + (size_t)(vi ? i1 : i0) * ld;
+            const double* c0 = A + (size_t)j0 * ld;
+            const double* c1 = A + (size_t)(vj ? j1 : j0) * ld;
+            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+            for (int m = 0; m < n; m++) {
+                const double x0 = r0[m], x1 = r1[m], y0 = c0[m], y1 = c1[m];
+                a00 = fma(x0, y0, a00);
+                a01 = fma(x0, y1, a01);
+                a10 = fma(x1, y0, a10);
+                a11 = fma(x1, y1, a11);
+            }
+            const double wgt = (ti == tj) ? 1.0 : 2.0;           // off-diagonal tiles are mirrored
+            B[(size_t)i0 * ld + j0] = a00; B[(size_t)j0 * ld + i0] = a00;
+            ss = fma(wgt * a00, a00, ss);
+            if (vj) { B[(size_t)i0 * ld + j1] = a01; B[(size_t)j1 * ld + i0] = a01; ss = fma(wgt * a01, a01, ss); }
+            if (vi) { B[(size_t)i1 * ld + j0] = a10; B[(size_t)j0 * ld + i1] = a10; ss = fma(wgt * a10, a10, ss); }
+            if (vi && vj) { B[(size_t)i1 * ld + j1] = a11; B[(size_t)j1 * ld + i1] = a11; ss = fma(wgt * a11, a11, ss); }
         }
         const double inv = rsqrt(block_sum(ss, red));
+        double tr = 0.0;
         for (size_t e = tid; e < nn; e += T) {
             const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
-            B[(size_t)i * ld + j] *= inv;
+            const double bv = B[(size_t)i * ld + j] * inv;
+            B[(size_t)i * ld + j] = bv;
+            if (i == j) tr += bv;
         }
+        tr = block_sum(tr, red);
         __syncthreads();
         double* t = A; A = B; B = t;
+        if (fabs(tr - 1.0) < 1e-13) break;                       // uniform: every thread holds the same sum
     }
     // trace test + the column of the largest diagonal entry as the start of two clean-up power steps on cov
     if (tid == 0) {
@@ -637,7 +657,7 @@ __global__ void __launch_bounds__(256) fmax_partial_kernel(const double* __restr
     }
 }
 
-__global__ void __launch_bounds__(256) scale_finish_kernel(NodeArrays na, const NodeRef* __restrict__ refs,
+__global__ void __launch_bounds__(1024) scale_finish_kernel(NodeArrays na, const NodeRef* __restrict__ refs,
                                                            const double* __restrict__ partial, int pass,
                                                            double logvol_pref, int nsub) {
     __shared__ double s_mult;
@@ -834,7 +854,7 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
         }
         fmax_partial_kernel<<<dim3(pj, B2N_FMAX_SUB), 256, fm_smem, st>>>(w.P, w.perm, w.N, w.na, (const JobL*)pjobs, partial);
         B2N_LAUNCH_CHECK(ctx);
-        scale_finish_kernel<<<pn, 256, 0, st>>>(w.na, (const NodeRef*)prefs, partial, pass, w.logvol_pref, B2N_FMAX_SUB);
+        scale_finish_kernel<<<pn, 1024, 0, st>>>(w.na, (const NodeRef*)prefs, partial, pass, w.logvol_pref, B2N_FMAX_SUB);
         B2N_LAUNCH_CHECK(ctx);
         // read back the node stats (one copy of the whole small array)
         B2N_CUDA(ctx, cudaStreamSynchronize(st));
@@ -876,7 +896,7 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
             B2N_TRY(b2n_eig_sliced(w, (const int*)l3, (int)refs3.size(), pass, 1, &used));
             fmax_partial_kernel<<<dim3((unsigned)jobs3.size(), B2N_FMAX_SUB), 256, fm_smem, st>>>(w.P, w.perm, w.N, w.na, (const JobL*)j3, partial);
             B2N_LAUNCH_CHECK(ctx);
-            scale_finish_kernel<<<(unsigned)refs3.size(), 256, 0, st>>>(w.na, (const NodeRef*)r3, partial, pass, w.logvol_pref, B2N_FMAX_SUB);
+            scale_finish_kernel<<<(unsigned)refs3.size(), 1024, 0, st>>>(w.na, (const NodeRef*)r3, partial, pass, w.logvol_pref, B2N_FMAX_SUB);
             B2N_LAUNCH_CHECK(ctx);
             B2N_CUDA(ctx, cudaStreamSynchronize(st));
             B2N_CUDA(ctx, cudaMemcpy(all.data(), w.na.stat, (size_t)w.cap * sizeof(NodeStat), cudaMemcpyDeviceToHost));
@@ -944,14 +964,16 @@ extern "C" int b2n_bounding_ellipsoid(b2n_ctx* ctx, const double* points, int64_
 
 // ------------------------------------------------------------------ scale_to_logvol
 // Ellipsoid.scale_to_logvol (bounding.py:242-276); one CTA per ellipsoid.
-__global__ void __launch_bounds__(256) scale_to_logvol_kernel(int n, double* __restrict__ covs, double* __restrict__ ams,
+__global__ void __launch_bounds__(1024) scale_to_logvol_kernel(int n, double* __restrict__ covs, double* __restrict__ ams,
                                                               double* __restrict__ axes, double* __restrict__ axlens,
                                                               double* __restrict__ logvols,
                                                               const double* __restrict__ targets) {
-    extern __shared__ double sm[];     // fax[n], lam[n], order[n]
+    extern __shared__ double sm[];     // fax[n], lam[n], wc[n], wa[n], order[n]
     double* fax = sm;
     double* lam = fax + n;
-    int* order = reinterpret_cast<int*>(lam + n);
+    double* wc = lam + n;              // per-axis weights of the rebuilt cov / am (hoisted out of the n^3 loop)
+    double* wa = wc + n;
+    int* order = reinterpret_cast<int*>(wa + n);
     __shared__ int s_iso;
     __shared__ double s_f;
     const int k = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
@@ -994,15 +1016,20 @@ __global__ void __launch_bounds__(256) scale_to_logvol_kernel(int n, double* __r
             }
         }
         __syncthreads();
+        for (int q = tid; q < n; q += T) {
+            const double f2 = fax[q] * fax[q];
+            wc[q] = f2;
+            wa[q] = 1.0 / (lam[q] * lam[q] * f2);
+        }
+        __syncthreads();
         // cov = sum_k a_k a_k^T fax_k^2 ; am = sum_k a_k a_k^T / (lam_k^2 fax_k^2),  a_k = axes[:,k]
         for (size_t e = tid; e < nn; e += T) {
             const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
             double c = 0.0, a = 0.0;
             for (int q = 0; q < n; q++) {
                 const double pr = AX[(size_t)i * n + q] * AX[(size_t)j * n + q];
-                const double f2 = fax[q] * fax[q];
-                c = fma(pr, f2, c);
-                a = fma(pr, 1.0 / (lam[q] * lam[q] * f2), a);
+                c = fma(pr, wc[q], c);
+                a = fma(pr, wa[q], a);
             }
             Cm[e] = c;
             AM[e] = a;
@@ -1026,8 +1053,8 @@ extern "C" int b2n_scale_to_logvol(b2n_ctx* ctx, int32_t K, int32_t n, double* c
     B2N_TRY(b2n_in(ctx, ctx->out3, axlens, (size_t)K * n * sizeof(double), &li));
     B2N_TRY(b2n_in(ctx, ctx->out4, logvols, (size_t)K * sizeof(double), &vi));
     B2N_TRY(b2n_in_host(ctx, ctx->in3, targets, (size_t)K * sizeof(double), &ti));
-    const size_t smem = (size_t)(3 * n + 2) * sizeof(double);
-    scale_to_logvol_kernel<<<K, 256, smem, ctx->stream>>>(n, (double*)ci, (double*)ai, (double*)xi, (double*)li,
+    const size_t smem = (size_t)(5 * n + 2) * sizeof(double);
+    scale_to_logvol_kernel<<<K, 1024, smem, ctx->stream>>>(n, (double*)ci, (double*)ai, (double*)xi, (double*)li,
                                                           (double*)vi, (const double*)ti);
     B2N_LAUNCH_CHECK(ctx);
     B2N_TRY(b2n_out_done(ctx, covs, ci, K * nn * sizeof(double)));

@@ -299,10 +299,18 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
             const double fac = live ? b2n_sm[oF + s * B2N_MMA_CH + c] : 0.0;
             // ---- phase 2 (item warp): Y[rows of slab][chains of tile] = A_slab @ X
             if (has_item) {
-                double d0 = 0.0, d1 = 0.0;
+                // NACC independent accumulator pairs: the k-tiles form NACC short DMMA dependency chains instead
+                // of one long one (a CTA with one chain -- b2n_ns_run's small rounds -- is bound by that latency)
+                double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
                 const int xb = oXs + (8 * t_it + (lane >> 2)) * XS + (lane & 3);
 #pragma unroll
-                for (int kt = 0; kt < KT; kt++) dmma884(d0, d1, fragA[kt], b2n_sm[xb + 4 * kt]);
+                for (int kt = 0; kt + 1 < KT; kt += 2) {
+                    dmma884(d0, d1, fragA[kt], b2n_sm[xb + 4 * kt]);
+                    dmma884(e0, e1, fragA[kt + 1], b2n_sm[xb + 4 * kt + 4]);
+                }
+                if (KT & 1) dmma884(d0, d1, fragA[KT - 1], b2n_sm[xb + 4 * (KT - 1)]);
+                d0 += e0;
+                d1 += e1;
                 const int row = 8 * s_it + (lane >> 2), c0 = 8 * t_it + 2 * (lane & 3);
                 b2n_sm[oY + c0 * YS + row] = d0;
                 b2n_sm[oY + (c0 + 1) * YS + row] = d1;
@@ -329,10 +337,16 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
                 __syncthreads();
                 // ---- phase 4 (item warp): partial delta^T P delta over the rows of the slab
                 if (has_item) {
-                    double d0 = 0.0, d1 = 0.0;
+                    double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
                     const int xb = oXs + (8 * t_it + (lane >> 2)) * XS + (lane & 3);
 #pragma unroll
-                    for (int kt = 0; kt < KT; kt++) dmma884(d0, d1, fragP[kt], b2n_sm[xb + 4 * kt]);
+                    for (int kt = 0; kt + 1 < KT; kt += 2) {
+                        dmma884(d0, d1, fragP[kt], b2n_sm[xb + 4 * kt]);
+                        dmma884(e0, e1, fragP[kt + 1], b2n_sm[xb + 4 * kt + 4]);
+                    }
+                    if (KT & 1) dmma884(d0, d1, fragP[KT - 1], b2n_sm[xb + 4 * (KT - 1)]);
+                    d0 += e0;
+                    d1 += e1;
                     const int row = 8 * s_it + (lane >> 2), c0 = 8 * t_it + 2 * (lane & 3);
                     double q0 = d0 * b2n_sm[oXs + c0 * XS + row], q1 = d1 * b2n_sm[oXs + (c0 + 1) * XS + row];
 #pragma unroll
