@@ -176,3 +176,43 @@ def test_device_loop_shells_two_ellipsoids():
     res = s.run_nested(loop='device', batch=60)
     assert abs(res.logz[-1] - m.logz_truth) < 3.5 * res.logzerr[-1] + 0.1
     assert max(h[1] for h in res.bound_history) >= 2
+
+
+def test_rounds_c2_size_properties():
+    """BASELINE C2 size (50-D, nlive 2000, batch 50, walks 70) -- too big for the per-chain Python oracle, so
+    size-independent properties of the rounds: the batch lowest points die in ascending order, every live
+    point beats the last threshold, (u, v, logl) stay consistent with the model, ln X telescopes, the call
+    count is rounds x batch x walks, the sorted order the device maintains by merging equals a full sort."""
+    m = DL.gauss_corr(50, 0.4, 5.0)
+    om = OL.gauss_corr(50, 0.4, 5.0)
+    rng = np.random.default_rng(8)
+    N, n, K, walks, R = 2000, 50, 50, 70, 12
+    Cm = np.full((n, n), 0.4)
+    np.fill_diagonal(Cm, 1.0)
+    u = 0.5 + 0.03 * rng.standard_normal((N, n)) @ np.linalg.cholesky(Cm).T
+    v, l = m.evaluate(u)
+    b = _bound([u], enlarge=3.0**n)
+    ops.bound_set(b['axes'], b['ctrs'], b['ams'], b['logvols'])
+    ops.ns_create(m.model_id(), N, n, K, 0, walks, 3, dlogz=1e-9, dead_capacity=R * K)
+    try:
+        ops.ns_set_state(u, v, l, 0.0, -1e300, -1e300, 0, 0.05)
+        st = ops.ns_run(R, 0)
+        assert (st['done'], st['need_bound'], st['rounds'], st['it']) == (0, 0, R, R * K)
+        assert st['ncall'] == R * K * walks
+        du, dv, dl, dlv, dnc = ops.ns_get_dead(0, R * K, n)
+        assert np.all(np.diff(dl) >= 0) and np.all(dnc == walks)
+        assert np.array_equal(dl[:K], np.sort(l)[:K])
+        lu, lv_, ll = ops.ns_get_live(N, n)
+        assert ll.min() > dl[-1] and st['loglstar'] == dl[-1] and st['lmax'] == ll.max()
+        np.testing.assert_allclose(lv_, om.prior_transform(lu), rtol=1e-13)
+        np.testing.assert_allclose(ll, om.loglike(lv_), rtol=1e-10)
+        # ln X: after r full rounds ln X = r ln((N-K+1)/(N+1)); inside a round ln((N-j)/(N+1)) on top
+        j = np.arange(R * K)
+        expect = (j // K) * math.log((N - K + 1) / (N + 1.0)) + np.log((N - j % K) / (N + 1.0))
+        np.testing.assert_allclose(dlv, expect, rtol=0, atol=1e-12)
+        assert st['logvol'] == pytest.approx(R * math.log((N - K + 1) / (N + 1.0)), abs=1e-12)
+        # running logZ == post-hoc trapezoid integral of the dead points
+        _, logz, _, _ = nested._integrate(dl, dlv)
+        assert st['logz'] == pytest.approx(logz[-1], rel=1e-11)
+    finally:
+        ops.ns_destroy()
