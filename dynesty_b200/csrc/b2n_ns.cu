@@ -22,7 +22,7 @@
 //                      ellipsoids (propose_live :469-491, get_random_axes bounding.py:726-731),
 //                      `bound.contains` of every start (:485-489), build the per-CTA worklist of
 //                      the chain kernel, write the round's B2nDyn
-//   chain kernel       rwalk / rslice / slice (b2n_rwalk.cu, b2n_slice.cu), device-paced
+//   chain kernel       rwalk / rslice / slice / unif (b2n_rwalk.cu, b2n_slice.cu, b2n_unif.cu), device-paced
 //   ns_commit_kernel   dead-point records, evidence increment (utils.py:1470-1492), scatter of the
 //                      chain end points into the freed slots, tuning of the proposal scale
 //                      (internal_samplers.py:460-493, 1209-1239), bound-update-due test
@@ -149,6 +149,18 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsD
     }
     __syncthreads();
     if (s_flag) return;
+    if (s.sampler == 3) {        // uniform sampler: the chains draw from the bound themselves -- no start rows
+        if (tid == 0) {
+            B2nDyn* dy = s.dyn;
+            dy->loglstar = key[K - 1];
+            dy->scale = sc->scale;
+            dy->chain0 = s.chain0 + (unsigned long long)sc->round * (unsigned long long)K;
+            dy->ncta = 0;
+            dy->doubling = 0;
+            dy->skip = 0;
+        }
+        return;
+    }
     // ---- start rows among the survivors, ellipsoid of every chain
     ChainRng g;
     g.init(s.seed, B2N_NS_DRIVER_CHAIN + (unsigned long long)sc->round);
@@ -324,7 +336,7 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
         ncall += s.o_ncall[j];
         ha += s.o_i0[j];
         hb += s.o_i1[j];
-        if (s.sampler != 0) fl |= s.o_flags[j];
+        if (s.sampler != 0) fl |= s.o_flags[j];           // rwalk writes no flags
     }
     const double m = block_reduce_max(wmax, rbuf);
     double se = 0.0;
@@ -409,7 +421,10 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
         // ---- tune (update=True every round: the queue of the round has drained, sampler.py:757-768)
         sc->hist_a = ha;
         sc->hist_b = hb;
-        if (s.sampler == 0) {                                // internal_samplers.py:460-493
+        if (s.sampler == 3) {                                // UniformBoundSampler: nothing to tune
+            if (s_or & 0x40000000u) { sc->error = B2N_ERR_Q0; sc->done = 1; }            // bounding.py:570-574
+            if (s_or & 0x80000000u) { sc->error = B2N_ERR_UNSUPPORTED; sc->done = 1; }   // draw limit
+        } else if (s.sampler == 0) {                         // internal_samplers.py:460-493
             const double facc = (double)ha / (double)(ha + hb);
             sc->scale *= exp((facc - s.facc) / (double)s.nc / s.facc);
         } else {                                             // tune_slice :1209-1239
@@ -485,7 +500,10 @@ static int ns_chain_call(b2n_ctx* ctx, b2n_ns* ns, bool plan_only) {
     ctx->dyn.dev = d.dyn; ctx->dyn.order = d.order; ctx->dyn.cta = d.cta;
     ctx->dyn.max_cta = d.cpc > 0 ? d.K / d.cpc + d.Kell : 1;
     int st;
-    if (d.sampler == 0)
+    if (d.sampler == 3) {
+        if (plan_only) { ctx->dyn.cpc = 1; st = B2N_OK; }
+        else st = b2n_unif_batch(ctx, &a, d.o_u, d.o_v, d.o_logl, d.o_ncall, d.o_i0, d.o_flags);
+    } else if (d.sampler == 0)
         st = b2n_rwalk_batch(ctx, &a, ns->cfg.steps, d.o_u, d.o_v, d.o_logl, d.o_i0, d.o_i1, d.o_ncall);
     else if (d.sampler == 1)
         st = b2n_rslice_batch(ctx, &a, ns->cfg.steps, 0, d.o_u, d.o_v, d.o_logl, d.o_i0, d.o_i1, d.o_ncall, d.o_flags);
@@ -514,9 +532,9 @@ int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* c, int64_t dead_capacity) {
     if (c->model_id < 0 || c->model_id >= (int)ctx->models.size()) return B2N_ERR_ARG;
     const int n = ctx->models[c->model_id].ndim;
     if (c->ndim != n || c->nlive < 2 || c->batch < 1 || c->batch >= c->nlive || c->steps < 1 || c->sampler < 0 ||
-        c->sampler > 2 || c->ncdim < 1 || c->ncdim > n)
-        return b2n_fail(ctx, B2N_ERR_ARG, "b2n_ns_create: need 1 <= batch < nlive, steps >= 1, sampler in {0,1,2}, ndim == model ndim");
-    if (c->sampler != 0 && c->ncdim != n) return b2n_fail(ctx, B2N_ERR_ARG, "slice samplers need ncdim == ndim");
+        c->sampler > 3 || c->ncdim < 1 || c->ncdim > n)
+        return b2n_fail(ctx, B2N_ERR_ARG, "b2n_ns_create: need 1 <= batch < nlive, steps >= 1, sampler in {0,1,2,3}, ndim == model ndim");
+    if ((c->sampler == 1 || c->sampler == 2) && c->ncdim != n) return b2n_fail(ctx, B2N_ERR_ARG, "slice samplers need ncdim == ndim");
     int Npad = 2;
     while (Npad < c->nlive) Npad <<= 1;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -555,6 +573,7 @@ int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* c, int64_t dead_capacity) {
     B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_i1, K * 4));
     B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_ncall, K * 4));
     B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_flags, K * 4));
+    B2N_CUDA(ctx, cudaMemset(d.o_i1, 0, K * 4));          // (the uniform sampler writes no second counter)
     B2N_CUDA(ctx, cudaMemset(d.sc, 0, sizeof(NsScalars)));
     B2N_CUDA(ctx, cudaMemset(d.dyn, 0, sizeof(B2nDyn)));
     B2N_TRY(ns_alloc_dead(ctx, ns, std::max<int64_t>(dead_capacity, (int64_t)K)));

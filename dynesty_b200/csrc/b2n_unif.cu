@@ -28,12 +28,19 @@ struct UnifParams {
     int *ncall, *nprop;
     uint32_t* flags;
     PeerSet peer;          // fused multi-GPU gather of the outputs (b2n_peer.cu)
+    const B2nDyn* dyn;     // device-paced launch (b2n_ns.cu): threshold / chain ids in HBM
 };
 
 template <int LIKE>
 __global__ void __launch_bounds__(256) unif_kernel(const UnifParams p) {
     extern __shared__ double sm[];
     const int n = p.n, nc = p.nc, K = p.K;
+    double loglstar_ = p.loglstar;
+    unsigned long long chain0_ = p.chain0;
+    if (p.dyn) {
+        if (p.dyn->skip) return;
+        loglstar_ = p.dyn->loglstar; chain0_ = p.dyn->chain0;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     double* uu = sm + (size_t)warp * 5 * n;   // candidate point (n)
     double* z = uu + n;                        // unit-ball draw (nc)
@@ -43,7 +50,7 @@ __global__ void __launch_bounds__(256) unif_kernel(const UnifParams p) {
     const double inv_nc = 1.0 / (double)nc;
     for (int64_t q = (int64_t)blockIdx.x * wpb + warp; q < p.Q; q += (int64_t)gridDim.x * wpb) {
         ChainRng g;
-        g.init(p.seed, p.chain0 + (uint64_t)q);
+        g.init(p.seed, chain0_ + (uint64_t)q);
         int ncall = 0, nprop = 0;
         uint32_t fl = 0;
         double lcur = 0.0;
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(256) unif_kernel(const UnifParams p) {
             __syncwarp();
             lcur = warp_loglike<LIKE>(p.m, p.m.lmat, vv, work, lane);
             ncall++;
-            if (lcur > p.loglstar) done = true;
+            if (lcur > loglstar_) done = true;
         }
         __syncwarp();
         for (int i = lane; i < n; i += 32) {
@@ -186,7 +193,11 @@ extern "C" int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, 
         fl.assign(a->dimflags, a->dimflags + n);
         B2N_TRY(b2n_in_host(ctx, ctx->in3, fl.data(), fl.size() * sizeof(uint32_t), &dfl_in));
     }
+    const bool dyn = ctx->dyn.active;        // device-paced launch (b2n_ns.cu)
+    if (dyn && (gather || ctx->ptr_mode != B2N_PTR_DEVICE || draw_only))
+        return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "device-paced launch needs device pointers and no gather mode");
     UnifParams p;
+    p.dyn = dyn ? ctx->dyn.dev : nullptr;
     p.m = m; p.n = n; p.nc = nc; p.K = K; p.Q = Q; p.draw_only = draw_only;
     p.ctrs = ctx->b_ctrs.as<double>(); p.ams = ctx->b_ams.as<double>(); p.axesT = ctx->b_axesT.as<double>();
     p.cum = (const double*)dcum; p.dimflags = (const uint32_t*)dfl_in;
@@ -221,6 +232,7 @@ extern "C" int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, 
     B2N_TIME_END(ctx);
 #undef CALL
     B2N_LAUNCH_CHECK(ctx);
+    if (dyn) return B2N_OK;      // device-paced: the commit kernel of the round folds the flags
     int* herr = reinterpret_cast<int*>(ctx->pinned);
     *herr = 0;
     B2N_CUDA(ctx, ctx->out7.ensure(64));

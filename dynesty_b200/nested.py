@@ -283,8 +283,9 @@ class NestedSampler:
         (update_bound, sampler.py:493-510) and collects the dead points at the end."""
         from . import ops
         smp, n, N = self.internal_sampler, self.ndim, self.nlive
-        kind = 0 if isinstance(smp, S.B200RWalkSampler) else (1 if isinstance(smp, S.B200RSliceSampler) else 2)
-        steps = smp.sampler_kwargs['walks' if kind == 0 else 'slices']
+        kind = (0 if isinstance(smp, S.B200RWalkSampler) else 1 if isinstance(smp, S.B200RSliceSampler) else
+                2 if isinstance(smp, S.B200SliceSampler) else 3)             # 3: uniform sampler (no chains to tune)
+        steps = 1 if kind == 3 else smp.sampler_kwargs['walks' if kind == 0 else 'slices']
         # default batch: rwalk chains use a proposal shape estimated from the live points and mix slowly along
         # under-estimated directions; the resulting logZ bias grows with the fraction of the live set replaced
         # per round (DESIGN.md 9.4): nlive/40 reproduces the reference's serial result.  Slice chains
@@ -307,6 +308,8 @@ class NestedSampler:
         self.device_timing = tm
         while True:
             per_round = max(1.0, (self.ncall - ncall_start) / rounds) if rounds else K * steps * (1 if kind == 0 else 6)
+            if kind == 3 and not rounds:
+                per_round = K * max(1.0, 100. / max(self.eff, 1.))        # uniform draws: ~1/eff calls each
             due = self.ncall_at_last_update + self.bound_update_interval - self.ncall
             want = int(min(4096, max(1, math.ceil(due / per_round))))
             t0 = time.perf_counter()
@@ -361,9 +364,8 @@ class NestedSampler:
                         per iteration.  batch defaults to nlive // 40 (rwalk) or nlive // 10 (slices)."""
         if loop not in ('host', 'device'):
             raise ValueError("loop must be 'host' or 'device'")
-        if loop == 'device' and (self.comm is not None or self.bound_next is None or
-                                 isinstance(self.internal_sampler_next, S.B200UniformSampler)):
-            raise ValueError("loop='device' needs a bound and a chain sampler (rwalk/rslice/slice) on one GPU")
+        if loop == 'device' and (self.comm is not None or self.bound_next is None):
+            raise ValueError("loop='device' needs a bound (single/multi) and runs on one GPU")
         nlive = self.nlive
         if dlogz is None:
             dlogz = 1e-3 * (nlive - 1.) + 0.01 if add_live else 0.01

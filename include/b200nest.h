@@ -282,7 +282,7 @@ uint64_t b2n_peer_window_bytes(int64_t total_rows, int32_t ndim);
  * chain (seed, 2^62 + r), tick 0 / 1 = one uniform vector event each (oracle/nsloop.py).      */
 typedef struct {
     int32_t nlive, ndim, ncdim, batch;
-    int32_t sampler;          /* 0 rwalk, 1 rslice, 2 slice                                     */
+    int32_t sampler;          /* 0 rwalk, 1 rslice, 2 slice, 3 unif (steps ignored)             */
     int32_t steps;            /* walks / slices                                                  */
     int32_t model_id;
     int32_t strict_contains;  /* 1: MultiEllipsoid.contains (d2 < 1), 0: Ellipsoid.contains (<= 1) */

@@ -116,6 +116,8 @@ class BatchNS:
             self.done = 1
             return False
         thr = float(sl[K - 1])
+        if self.sampler == 'unif':
+            return self._step_unif(order, sl, thr)
         drv = philox.ChainStream(self.seed, DRIVER_CHAIN + self.round)
         U = philox.event_uniforms(self.seed, drv.chain, 0, K)
         nsurv = N - K
@@ -151,7 +153,53 @@ class BatchNS:
                 r = OS.slice_chain(u0, thr, ax, self.scale, self.model, st, self.steps, doubling=self.doubling)
             out.append(r)
             warned = warned or bool(r.get('expansion_warning_set', False))
-        # ---- commit: dead records + evidence (live count N - j at the j-th removal)
+        self._commit(order, sl, thr, out)
+        # ---- tune (update=True)
+        b = self.bound
+        if self.sampler == 'rwalk':
+            a, r_ = sum(o['n_accept'] for o in out), sum(o['n_reject'] for o in out)
+            nc = b['ctrs'].shape[1]
+            self.scale *= math.exp((a / (a + r_) - self.facc) / nc / self.facc)
+            self.last = dict(starts=starts, ell=ell, thr=thr, n_accept=a, n_reject=r_)
+        else:
+            ne, ncn = sum(o['n_expand'] for o in out), sum(o['n_contract'] for o in out)
+            if warned:
+                self.doubling = True
+            ne = max(ne, 1)
+            self.scale *= min(max(ne * 2. / (ne + ncn), 0.5), 2.)
+            self.last = dict(starts=starts, ell=ell, thr=thr, n_expand=ne, n_contract=ncn)
+        if self.ncall >= self.ncall_last_update + self.update_interval:
+            self.need_bound = 1
+        return True
+
+    def _step_unif(self, order, sl, thr):
+        """Round of the uniform sampler (UniformBoundSampler.sample, internal_samplers.py:243-340): every chain
+        draws from the bound until logl > thr; no start rows, nothing to tune."""
+        from . import bounding as OB
+        b = self.bound
+        Ke = b['ctrs'].shape[0]
+        me = OB.MultiEll.__new__(OB.MultiEll)
+        me.ells = []
+        for k in range(Ke):
+            e = OB.Ell.__new__(OB.Ell)
+            e.ctr, e.am, e.axes = b['ctrs'][k], b['ams'][k], b['axes'][k]
+            e.ndim = len(e.ctr)
+            me.ells.append(e)
+        me.nells, me.ctrs, me.ams, me.logvol_ells = Ke, b['ctrs'], b['ams'], b['logvols']
+        lv = b['logvols']
+        m = float(lv.max())
+        me.logvol = m + math.log(float(np.exp(lv - m).sum()))
+        out = [OS.unif_chain(thr, me, self.model, philox.ChainStream(self.seed, self.chain0 + self.round * self.K + c),
+                             self.n, nonbounded=self.nb) for c in range(self.K)]
+        self._commit(order, sl, thr, out)
+        self.last = dict(thr=thr)
+        if self.ncall >= self.ncall_last_update + self.update_interval:
+            self.need_bound = 1
+        return True
+
+    def _commit(self, order, sl, thr, out):
+        """dead records + evidence (live count N - j at the j-th removal), chain end points into the freed slots"""
+        N, K = self.N, self.K
         ws = np.empty(K)
         for j in range(K):
             L, Lp = float(sl[j]), (float(sl[j - 1]) if j else self.loglstar)
@@ -171,22 +219,6 @@ class BatchNS:
         self.it += K
         self.ncall += sum(o['ncall'] for o in out)
         self.round += 1
-        # ---- tune (update=True)
-        if self.sampler == 'rwalk':
-            a, r_ = sum(o['n_accept'] for o in out), sum(o['n_reject'] for o in out)
-            nc = b['ctrs'].shape[1]
-            self.scale *= math.exp((a / (a + r_) - self.facc) / nc / self.facc)
-            self.last = dict(starts=starts, ell=ell, thr=thr, n_accept=a, n_reject=r_)
-        else:
-            ne, ncn = sum(o['n_expand'] for o in out), sum(o['n_contract'] for o in out)
-            if warned:
-                self.doubling = True
-            ne = max(ne, 1)
-            self.scale *= min(max(ne * 2. / (ne + ncn), 0.5), 2.)
-            self.last = dict(starts=starts, ell=ell, thr=thr, n_expand=ne, n_contract=ncn)
-        if self.ncall >= self.ncall_last_update + self.update_interval:
-            self.need_bound = 1
-        return True
 
     def dead_arrays(self):
         d = self.dead

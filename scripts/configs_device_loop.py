@@ -27,9 +27,11 @@ def run(tag, model, loop='device', batch=None, seed=56432, **kw):
 
 
 which = sys.argv[1:] or ['c1', 'c2', 'c2r', 'c3', 'c4', 'c5']
-if 'c1' in which:     # 3-D Gaussian, single/unif: the uniform sampler has no chains -> host loop
-    run('C1 3-D gauss single/unif nlive=500', DL.gauss_test3d(), loop='host', nlive=500, bound='single', sample='unif',
+if 'c1' in which:     # 3-D Gaussian, single/unif (bootstrap 5, the reference's default for unif)
+    run('C1 3-D gauss single/unif nlive=500', DL.gauss_test3d(), batch=50, nlive=500, bound='single', sample='unif',
         queue_size=64)
+    run('C1 3-D gauss single/unif nlive=500 (host loop)', DL.gauss_test3d(), loop='host', nlive=500, bound='single',
+        sample='unif', queue_size=64)
 if 'c2' in which:
     run('C2 50-D gauss multi/rwalk nlive=2000', DL.gauss_corr(50, 0.4, 5.0), batch=50, nlive=2000, bound='multi',
         sample='rwalk', queue_size=200)

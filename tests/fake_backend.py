@@ -229,7 +229,7 @@ def ns_create(model, nlive, ndim, batch, sampler, steps, seed, chain0=0, ncdim=N
               facc=0.5, dlogz=0.01, maxiter=None, maxcall=None, update_interval=1 << 62, dimflags=None,
               dead_capacity=None, ctx=None):
     assert dimflags is None, "fake backend: periodic/reflective not wired for ns rounds"
-    _state['ns_cfg'] = dict(model=_models[model], batch=batch, sampler=('rwalk', 'rslice', 'slice')[sampler],
+    _state['ns_cfg'] = dict(model=_models[model], batch=batch, sampler=('rwalk', 'rslice', 'slice', 'unif')[sampler],
                             steps=steps, seed=seed, chain0=chain0, facc=facc, dlogz=dlogz,
                             maxiter=maxiter if maxiter is not None else 1 << 62,
                             maxcall=maxcall if maxcall is not None else 1 << 62,
