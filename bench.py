@@ -241,10 +241,12 @@ def run_b200(args, cfg):
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    # stdout carries exactly ONE line (the JSON): while the benchmark runs, file descriptor 1 points at stderr,
+    # so that banners printed by native libraries (NCCL's "NCCL version ..." goes to stdout) cannot precede it
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly ONE line (the JSON): NCCL's own banner / debug lines go to stderr
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        os.environ.setdefault('NCCL_DEBUG', 'WARN')
         dist.init_process_group('nccl', device_id=dev)
     ctx = _lib.Context(local)
     n, nlive, walks = cfg['ndim'], cfg['nlive'], cfg['walks']
@@ -519,9 +521,13 @@ def run_b200(args, cfg):
         line["cpu_baseline"] = {"value": v, "unit": "proposals/s", "cores": cores, "kind": kind,
                                 "sample": "%d %s chains x %d walks (%.1f s) on %d processes" % (nch, who, walks, tsec, cores),
                                 "one_core_value": v1, "one_core_sample": "%d chains (%.1f s), serial" % (nch1, t1)}
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)               # (teardown messages of native libraries: not on stdout either)
         dist.destroy_process_group()
 
 

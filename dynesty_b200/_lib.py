@@ -52,7 +52,8 @@ class NsStatus(C.Structure):
     _fields_ = [('it', C.c_int64), ('ncall', C.c_int64), ('rounds', C.c_int64), ('logz', C.c_double),
                 ('logvol', C.c_double), ('loglstar', C.c_double), ('lmax', C.c_double),
                 ('delta_logz', C.c_double), ('scale', C.c_double), ('done', C.c_int32),
-                ('need_bound', C.c_int32), ('doubling', C.c_int32), ('error', C.c_int32)]
+                ('need_bound', C.c_int32), ('doubling', C.c_int32), ('error', C.c_int32),
+                ('ncall_last_update', C.c_int64)]
 
 
 # every symbol include/b200nest.h declares: (restype, argtypes)
@@ -94,6 +95,7 @@ SYMBOLS = {
     'b2n_ns_set_state': (C.c_int, [_P, _P, _P, _P, _D, _D, _D, _L, _L, _D]),
     'b2n_ns_run': (C.c_int, [_P, _I, _I, C.POINTER(NsStatus)]),
     'b2n_ns_status_get': (C.c_int, [_P, C.POINTER(NsStatus)]),
+    'b2n_ns_set_counters': (C.c_int, [_P, _L, _L, _I]),
     'b2n_ns_bound_updated': (C.c_int, [_P]),
     'b2n_ns_reserve_dead': (C.c_int, [_P, _L]),
     'b2n_ns_get_live': (C.c_int, [_P, _P, _P, _P]),

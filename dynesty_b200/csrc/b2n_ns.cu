@@ -625,6 +625,7 @@ static int ns_status(b2n_ctx* ctx, b2n_ns_status* out) {
         out->logz = h->logz; out->logvol = h->logvol; out->loglstar = h->loglstar; out->lmax = h->lmax;
         out->delta_logz = h->delta_logz; out->scale = h->scale;
         out->done = h->done; out->need_bound = h->need_bound; out->doubling = h->doubling; out->error = h->error;
+        out->ncall_last_update = h->ncall_last_update;
     }
     return B2N_OK;
 }
@@ -676,6 +677,20 @@ int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_sta
     if (max_rounds == 0) B2N_TRY(ns_status(ctx, &st));
     if (out) *out = st;
     if (st.error) return st.error;
+    return B2N_OK;
+}
+
+__global__ void ns_set_counters_kernel(NsScalars* sc, long long rounds, long long ncall_last_update, int doubling) {
+    sc->round = rounds;
+    sc->ncall_last_update = ncall_last_update;
+    sc->doubling = doubling;
+}
+
+int b2n_ns_set_counters(b2n_ctx* ctx, int64_t rounds, int64_t ncall_last_update, int32_t doubling) {
+    if (!ctx || !ctx->ns || rounds < 0) return B2N_ERR_ARG;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    ns_set_counters_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ns->d.sc, rounds, ncall_last_update, doubling);
+    B2N_LAUNCH_CHECK(ctx);
     return B2N_OK;
 }
 

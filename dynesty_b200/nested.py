@@ -167,6 +167,37 @@ class NestedSampler:
         self._q = None
         self._qpos = 0
 
+    # ------------------------------------------------------------------ save / restore (utils.py:2321-2355)
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d['ctx'] = d['comm'] = None                  # device handles are per process
+        d.pop('_resident_key', None)
+        return d
+
+    def save(self, fname):
+        """Pickle the sampler (the reference's ``save_sampler``): with loop='device' the pickle carries the
+        snapshot of the device-resident run taken at the last consistent point (``_dev_snap``)."""
+        import os
+        import pickle
+        tmp = fname + '.tmp'
+        with open(tmp, 'wb') as f:
+            pickle.dump(self, f, protocol=pickle.HIGHEST_PROTOCOL)
+        os.replace(tmp, fname)                        # atomic, like utils.py:2343-2352
+
+    @classmethod
+    def restore(cls, fname, ctx=None):
+        """``restore_sampler``: continue with ``run_nested(resume=True)``."""
+        import pickle
+        with open(fname, 'rb') as f:
+            ns = pickle.load(f)
+        ns.ctx = ctx
+        for o in (ns.bound, ns.bound_next, getattr(ns, 'internal_sampler', None), ns.internal_sampler_next):
+            if o is not None and hasattr(o, '_ctx'):
+                o._ctx = ctx
+            if o is not None and hasattr(o, '_m'):
+                o._m._ctx = ctx
+        return ns
+
     # ------------------------------------------------------------------ bounds
     def update_bound(self, subset=slice(None)):
         """sampler.py:493-510."""
@@ -277,7 +308,8 @@ class NestedSampler:
         self.update_bound_if_needed(loglstar, ncall=self.ncall)
 
     # ------------------------------------------------------------------ device-resident rounds
-    def _device_rounds(self, logz, logvol, loglstar, dlogz, maxiter, maxcall, batch):
+    def _device_rounds(self, logz, logvol, loglstar, dlogz, maxiter, maxcall, batch, checkpoint_file=None,
+                       checkpoint_every=0.0, snap=None, _abort_after=None):
         """Continue the run with ``b2n_ns_run`` (include/b200nest.h): K-worst replacement rounds
         paced on the device; the host only rebuilds the bound when the device asks for it
         (update_bound, sampler.py:493-510) and collects the dead points at the end."""
@@ -292,23 +324,52 @@ class NestedSampler:
         # decorrelate: nlive/10.
         K = int(batch or max(1, N // (40 if kind == 0 else 10)))
         self.batch = K
-        ops.ns_create(self.model.model_id(self.ctx), N, n, K, kind, steps, self.seed, chain0=self.chain_counter,
+        prev = [np.empty((0, n)), np.empty((0, n)), np.empty(0), np.empty(0), np.empty(0, dtype=np.int32)]
+        chain_base = self.chain_counter
+        if snap is not None:             # resume: rows that died before the snapshot, scalars of the run
+            prev = [snap['dead'][k] for k in range(5)]
+            self.live_u, self.live_v, self.live_logl = snap['live']
+            logvol, logz, loglstar = snap['logvol'], snap['logz'], snap['loglstar']
+            self.ncall, smp.scale, chain_base = snap['ncall'], snap['scale'], snap['chain_base']
+            maxiter = maxiter - len(prev[2]) if maxiter < (1 << 61) else maxiter
+        nprev = len(prev[2])
+        ops.ns_create(self.model.model_id(self.ctx), N, n, K, kind, steps, self.seed, chain0=chain_base,
                       ncdim=self.ncdim, strict_contains=not isinstance(self.bound, B.B200Ellipsoid),
                       facc=getattr(smp, 'facc', 0.5), dlogz=dlogz if dlogz is not None else 0.0,
                       maxiter=maxiter if maxiter < (1 << 61) else None, maxcall=maxcall,
                       update_interval=self.bound_update_interval, dimflags=smp._flags(), ctx=self.ctx)
         ops.ns_set_state(self.live_u, self.live_v, self.live_logl, logvol, logz, loglstar, self.ncall, smp.scale,
                          ctx=self.ctx)
+        rounds0 = 0
+        if snap is not None:
+            rounds0 = snap['rounds']
+            ops.ns_set_counters(snap['rounds'], snap['ncall_last_update'], snap['doubling'], ctx=self.ctx)
         self.bound.make_resident()
         self._resident_key = (id(self.bound), getattr(self.bound, 'version', None))
         cap, last_forced = 64 * N, -1
-        ncall_start, rounds = self.ncall, 0
+        ncall_start, rounds = self.ncall, rounds0
         import time
         tm = dict(rounds_s=0.0, bound_s=0.0)
         self.device_timing = tm
+        t_ckpt, n_ckpt, saved_it = time.perf_counter(), 0, 0
+
+        def checkpoint(st):
+            """Snapshot at a consistent point (flags clear, bound current): live set, scalars, the rows that
+            died since the last snapshot; then pickle the whole sampler (host phase results included)."""
+            nonlocal saved_it, prev
+            new = ops.ns_get_dead(saved_it, st['it'] - saved_it, n, ctx=self.ctx)
+            prev = [np.concatenate([a, b]) for a, b in zip(prev, new)]
+            saved_it = st['it']
+            self._dev_snap = dict(dead=prev, live=ops.ns_get_live(N, n, ctx=self.ctx), logvol=st['logvol'],
+                                  logz=st['logz'], loglstar=st['loglstar'], ncall=st['ncall'], scale=st['scale'],
+                                  rounds=st['rounds'], ncall_last_update=st['ncall_last_update'],
+                                  doubling=st['doubling'], chain_base=chain_base, batch=K)
+            self.save(checkpoint_file)
+
         while True:
-            per_round = max(1.0, (self.ncall - ncall_start) / rounds) if rounds else K * steps * (1 if kind == 0 else 6)
-            if kind == 3 and not rounds:
+            done_r = rounds - rounds0
+            per_round = max(1.0, (self.ncall - ncall_start) / done_r) if done_r else K * steps * (1 if kind == 0 else 6)
+            if kind == 3 and not done_r:
                 per_round = K * max(1.0, 100. / max(self.eff, 1.))        # uniform draws: ~1/eff calls each
             due = self.ncall_at_last_update + self.bound_update_interval - self.ncall
             want = int(min(4096, max(1, math.ceil(due / per_round))))
@@ -337,21 +398,31 @@ class NestedSampler:
                 self._resident_key = (id(self.bound), getattr(self.bound, 'version', None))
                 ops.ns_bound_updated(ctx=self.ctx)
                 tm['bound_s'] += time.perf_counter() - t0
+                if checkpoint_file is not None and time.perf_counter() - t_ckpt >= checkpoint_every:
+                    st = ops.ns_status(ctx=self.ctx)              # flags cleared, interval restarted
+                    checkpoint(st)
+                    t_ckpt, n_ckpt = time.perf_counter(), n_ckpt + 1
+                    if _abort_after is not None and n_ckpt >= _abort_after:
+                        ops.ns_destroy(ctx=self.ctx)
+                        raise KeyboardInterrupt('test hook: run aborted after checkpoint %d' % n_ckpt)
         smp.scale = st['scale']
         if st['doubling']:
             smp.sampler_kwargs['slice_doubling'] = True
         self.live_u, self.live_v, self.live_logl = ops.ns_get_live(N, n, ctx=self.ctx)
-        out = ops.ns_get_dead(0, st['it'], n, ctx=self.ctx)
-        self.chain_counter += rounds * K
-        self.nbatches += rounds
+        new = ops.ns_get_dead(saved_it, st['it'] - saved_it, n, ctx=self.ctx)
+        out = tuple(np.concatenate([a, b]) for a, b in zip(prev, new))
+        self.chain_counter = chain_base + rounds * K
+        self.nbatches += rounds - rounds0
         self.n_proposals += self.ncall - ncall_start
         self.it += st['it']
         self.device_rounds = rounds
+        self._dev_snap = None
         ops.ns_destroy(ctx=self.ctx)
         return out
 
     # ------------------------------------------------------------------ main loop
-    def run_nested(self, dlogz=None, maxiter=None, maxcall=None, add_live=True, loop='host', batch=None):
+    def run_nested(self, dlogz=None, maxiter=None, maxcall=None, add_live=True, loop='host', batch=None,
+                   checkpoint_file=None, checkpoint_every=60., resume=False, _abort_after=None):
         """sampler.py:1214-1356 / 1040-1212 (no plateau mode: continuous likelihoods).
 
         loop='host'   : the reference's semantics -- one worst point per iteration, replacements
@@ -362,8 +433,12 @@ class NestedSampler:
                         threshold of the batch-th lowest -- no stale-threshold filter, hence no
                         selection bias for correlated chains, no host round trip
                         per iteration.  batch defaults to nlive // 40 (rwalk) or nlive // 10 (slices)."""
+        if resume:
+            return self._resume(checkpoint_file, checkpoint_every)
         if loop not in ('host', 'device'):
             raise ValueError("loop must be 'host' or 'device'")
+        if checkpoint_file is not None and loop != 'device':
+            raise ValueError("checkpointing is implemented for loop='device'")
         if loop == 'device' and (self.comm is not None or self.bound_next is None):
             raise ValueError("loop='device' needs a bound (single/multi) and runs on one GPU")
         nlive = self.nlive
@@ -441,8 +516,33 @@ class NestedSampler:
         logvols = -dlv * np.arange(1, ndead + 1)
         su, sv, nc_all = dead_u[:ndead], dead_v[:ndead], dead_nc[:ndead]
         if hand_over:
-            du, dv, dl, dlvol, dnc = self._device_rounds(logz, logvol, loglstar, dlogz, maxiter - ndead,
-                                                         ncall0 + maxcall if maxcall < (1 << 61) else None, batch)
+            # (kept on the object so that a checkpoint of the device phase carries the host phase's results)
+            self._host_part = dict(su=su.copy(), sv=sv.copy(), logl=logl.copy(), logvols=logvols, nc_all=nc_all.copy(),
+                                   logz=logz, logvol=logvol, loglstar=loglstar, dlogz=dlogz, add_live=add_live,
+                                   maxiter=maxiter - ndead,
+                                   maxcall=ncall0 + maxcall if maxcall < (1 << 61) else None)
+            dev = self._device_rounds(logz, logvol, loglstar, dlogz, self._host_part['maxiter'],
+                                      self._host_part['maxcall'], batch, checkpoint_file=checkpoint_file,
+                                      checkpoint_every=checkpoint_every, _abort_after=_abort_after)
+            return self._finalize(su, sv, logl, logvols, nc_all, dev, add_live)
+        return self._finalize(su, sv, logl, logvols, nc_all, None, add_live)
+
+    def _resume(self, checkpoint_file, checkpoint_every):
+        """Continue a run restored from a checkpoint of the device phase (``NestedSampler.restore``)."""
+        snap, hp = getattr(self, '_dev_snap', None), getattr(self, '_host_part', None)
+        if snap is None or hp is None:
+            raise ValueError("nothing to resume: the pickle carries no snapshot of a device-resident run")
+        dev = self._device_rounds(hp['logz'], hp['logvol'], hp['loglstar'], hp['dlogz'], hp['maxiter'], hp['maxcall'],
+                                  snap['batch'], checkpoint_file=checkpoint_file, checkpoint_every=checkpoint_every,
+                                  snap=snap)
+        return self._finalize(hp['su'], hp['sv'], hp['logl'], hp['logvols'], hp['nc_all'], dev, hp['add_live'])
+
+    def _finalize(self, su, sv, logl, logvols, nc_all, dev, add_live):
+        """Results (+ remaining live points, sampler.py:780-914) from the host-phase and device-phase dead points."""
+        nlive = self.nlive
+        ndead = len(logl)
+        if dev is not None:
+            du, dv, dl, dlvol, dnc = dev
             logl, logvols = np.concatenate([logl, dl]), np.concatenate([logvols, dlvol])
             su, sv = np.concatenate([su, du]), np.concatenate([sv, dv])
             nc_all = np.concatenate([nc_all, dnc.astype(np.int64)])

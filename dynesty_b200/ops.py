@@ -286,6 +286,12 @@ def ns_status(ctx=None):
     return _ns_status(st)
 
 
+def ns_set_counters(rounds, ncall_last_update, doubling, ctx=None):
+    """Counters of a restored run (round index, calls at the last bound update, slice-doubling switch)."""
+    ctx = _ctx(ctx)
+    ctx.check(ctx.lib.b2n_ns_set_counters(ctx.h, int(rounds), int(ncall_last_update), int(bool(doubling))))
+
+
 def ns_bound_updated(ctx=None):
     ctx = _ctx(ctx)
     ctx.check(ctx.lib.b2n_ns_bound_updated(ctx.h))

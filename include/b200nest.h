@@ -298,6 +298,7 @@ typedef struct {
     int64_t it, ncall, rounds;       /* dead points in the device buffer, total calls, rounds done */
     double logz, logvol, loglstar, lmax, delta_logz, scale;
     int32_t done, need_bound, doubling, error;
+    int64_t ncall_last_update;       /* calls at the last bound update (restorable state)            */
 } b2n_ns_status;
 
 int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* cfg, int64_t dead_capacity);
@@ -310,6 +311,11 @@ int b2n_ns_set_state(b2n_ctx* ctx, const double* live_u, const double* live_v, c
  * B2N_ERR_SLICE_FAIL, if a chain failed). */
 int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_status* status);
 int b2n_ns_status_get(b2n_ctx* ctx, b2n_ns_status* status);
+/* restore the counters a snapshot of a run carries besides b2n_ns_set_state's arguments (utils.py:2321-2355
+ * save / restore of the reference pickles the whole sampler; here: live set + scalars + these): the round
+ * index (chain ids and the round driver's stream depend on it), the calls at the last bound update, the
+ * slice-doubling switch.  A run restored this way continues bit-identically. */
+int b2n_ns_set_counters(b2n_ctx* ctx, int64_t rounds, int64_t ncall_last_update, int32_t doubling);
 /* after the caller replaced the resident bound: clears need_bound, restarts the update interval */
 int b2n_ns_bound_updated(b2n_ctx* ctx);
 /* grow the dead-point buffer to `capacity` rows (keeps the rows written so far); clears need_bound == 3 */

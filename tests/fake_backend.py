@@ -249,7 +249,7 @@ def ns_status(ctx=None):
     b = _state['ns']
     return dict(it=b.it, ncall=b.ncall, rounds=b.round, logz=b.logz, logvol=b.logvol, loglstar=b.loglstar,
                 lmax=float(b.live_logl.max()), delta_logz=b.delta_logz, scale=b.scale, done=b.done,
-                need_bound=b.need_bound, doubling=int(b.doubling), error=0)
+                need_bound=b.need_bound, doubling=int(b.doubling), error=0, ncall_last_update=b.ncall_last_update)
 
 
 def ns_run(max_rounds, check_every=0, ctx=None):
@@ -259,6 +259,11 @@ def ns_run(max_rounds, check_every=0, ctx=None):
         if not b.step():
             break
     return ns_status()
+
+
+def ns_set_counters(rounds, ncall_last_update, doubling, ctx=None):
+    b = _state['ns']
+    b.round, b.ncall_last_update, b.doubling = int(rounds), int(ncall_last_update), bool(doubling)
 
 
 def ns_bound_updated(ctx=None):
@@ -286,7 +291,7 @@ def ns_destroy(ctx=None):
     _state.pop('ns', None)
 
 
-FUNCS = ['ns_create', 'ns_set_state', 'ns_status', 'ns_run', 'ns_bound_updated', 'ns_reserve_dead',
+FUNCS = ['ns_set_counters', 'ns_create', 'ns_set_state', 'ns_status', 'ns_run', 'ns_bound_updated', 'ns_reserve_dead',
          'ns_get_live', 'ns_get_dead', 'ns_destroy', 'model_eval', 'membership', 'bounding_ellipsoid', 'multi_decompose', 'scale_to_logvol',
          'bootstrap_expand', 'bound_set', 'dimflags_from', 'rwalk_batch', 'rslice_batch', 'slice_batch',
          'unif_batch']

@@ -219,3 +219,25 @@ def test_rounds_c2_size_properties():
         assert st['logz'] == pytest.approx(logz[-1], rel=1e-11)
     finally:
         ops.ns_destroy()
+
+
+@pytest.mark.parametrize('sample,kw', [('rwalk', dict(walks=30)), ('rslice', dict(slices=8))])
+def test_checkpoint_resume_is_bit_identical(tmp_path, sample, kw):
+    """tests/test_resume.py of the reference: kill after a checkpoint, restore, resume -> the same results as the
+    uninterrupted run, bit for bit (device state restored through b2n_ns_set_state + b2n_ns_set_counters)."""
+    m = DL.gauss_corr(10, 0.4, 5.0)
+    mk = lambda: nested.NestedSampler(m, nlive=400, bound='multi', sample=sample, queue_size=40, seed=11, **kw)
+    ref = mk().run_nested(loop='device', batch=20)
+    f = str(tmp_path / 'ckpt.pkl')
+    s = mk()
+    with pytest.raises(KeyboardInterrupt):
+        s.run_nested(loop='device', batch=20, checkpoint_file=f, checkpoint_every=0., _abort_after=4)
+    del s
+    r = nested.NestedSampler.restore(f)
+    assert r._dev_snap['rounds'] > 0 and len(r._dev_snap['dead'][2]) > 0
+    res = r.run_nested(resume=True)
+    assert res.niter == ref.niter and res.ncall == ref.ncall
+    assert np.array_equal(res.logl, ref.logl) and np.array_equal(res.logvol, ref.logvol)
+    assert np.array_equal(res.samples_u, ref.samples_u) and np.array_equal(res.samples, ref.samples)
+    assert res.logz[-1] == ref.logz[-1] and res.logzerr[-1] == ref.logzerr[-1]
+    assert abs(res.logz[-1] - m.logz_truth) < 4 * res.logzerr[-1] + 0.1

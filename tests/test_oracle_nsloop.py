@@ -112,3 +112,27 @@ def test_device_loop_rejects_unsupported(fake_ops):
     m = DL.gauss_test3d()
     with pytest.raises(ValueError):
         nested.NestedSampler(m, nlive=50, bound='none', sample='unif').run_nested(loop='device')
+
+
+@pytest.mark.parametrize('sample,kw', [('rwalk', dict(walks=12)), ('rslice', dict(slices=3))])
+def test_checkpoint_resume_is_bit_identical(fake_ops, tmp_path, sample, kw):
+    """The reference's tests/test_resume.py property: a run killed after a checkpoint and resumed from the file
+    ends with the SAME results as the uninterrupted run (utils.py:2321-2355 save / restore).  Here the checkpoint
+    carries the snapshot of the device-resident phase (live set, scalars, round counter, dead rows so far)."""
+    m = DL.gauss_test3d()
+    mk = lambda: nested.NestedSampler(m, nlive=100, bound='multi', sample=sample, queue_size=25, seed=11, **kw)
+    ref = mk().run_nested(dlogz=0.5, loop='device', batch=20)
+    f = str(tmp_path / 'ckpt.pkl')
+    s = mk()
+    with pytest.raises(KeyboardInterrupt):
+        s.run_nested(dlogz=0.5, loop='device', batch=20, checkpoint_file=f, checkpoint_every=0., _abort_after=3)
+    del s
+    r = nested.NestedSampler.restore(f)
+    assert r._dev_snap is not None and r._dev_snap['rounds'] > 0 and len(r._dev_snap['dead'][2]) > 0
+    res = r.run_nested(resume=True)
+    assert res.niter == ref.niter and res.ncall == ref.ncall and r.nbound == 1 + len(ref.bound_history)
+    assert np.array_equal(res.logl, ref.logl) and np.array_equal(res.logvol, ref.logvol)
+    assert np.array_equal(res.samples_u, ref.samples_u)
+    assert res.logz[-1] == ref.logz[-1]
+    with pytest.raises(ValueError):
+        mk().run_nested(resume=True)
