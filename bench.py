@@ -539,7 +539,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--chains', type=int, default=0, help='chains per step per GPU (default nlive)')
-    ap.add_argument('--logz', type=int, default=4, help='number of full C2 nested-sampling runs (seeds) for logZ; 0 = none')
+    ap.add_argument('--logz', type=int, default=8, help='number of full C2 nested-sampling runs (seeds) for logZ; 0 = none')
     ap.add_argument('--logz-queue', type=int, default=200, help='queue_size of the host (unit-cube) phase of the logZ runs')
     ap.add_argument('--logz-batch', type=int, default=0, help='points replaced per device round (default nlive/40)')
     ap.add_argument('--cpu-baseline', type=int, default=1)
