@@ -42,6 +42,7 @@ struct NsScalars {
     double logvol, logz, loglstar, lmax, scale, delta_logz;
     long long hist_a, hist_b;
     int done, need_bound, doubling, error;
+    int parity, pad0;          // which of the two (key, row) buffer pairs holds the current sorted order
 };
 
 struct NsDev {
@@ -127,8 +128,9 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsD
     int* start = reinterpret_cast<int*>(cum + ((s.Kell + 1) & ~1));   // K
     int* ell = start + K;                                    // K
     int* cnt = ell + K;                                      // Kell + 1
-    const double* key = s.skey;                              // sorted ascending by (logl, row)
-    const int* idx = s.sidx;
+    const int par = sc->parity;                              // current sorted order: ascending by (logl, row)
+    const double* key = par ? s.tkey : s.skey;
+    const int* idx = par ? s.tidx : s.sidx;
     __shared__ int s_flag, s_bad;
     if (tid == 0) { s_flag = 0; s_bad = 0; }
     __syncthreads();
@@ -307,12 +309,17 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
     const int N = s.N, K = s.K, n = s.n;
     const long long it0 = sc->it;
     const double logvol0 = sc->logvol, lprev0 = sc->loglstar;
+    const int par = sc->parity;
+    const double* ckey = par ? s.tkey : s.skey;      // current sorted order (read) ...
+    const int* cidx = par ? s.tidx : s.sidx;
+    double* nkey = par ? s.skey : s.tkey;            // ... the merged order of the next round (written)
+    int* nidx = par ? s.sidx : s.tidx;
     if (tid == 0) s_or = 0u;
     __syncthreads();
     // ---- dead-point rows out, chain end points in (slot of the j-th lowest <- chain j)
     for (int e = tid; e < K * n; e += nth) {
         const int j = e / n, i = e - j * n;
-        const size_t src = (size_t)s.sidx[j] * n + i;
+        const size_t src = (size_t)cidx[j] * n + i;
         const size_t dst = (size_t)(it0 + j) * n + i;
         s.dead_u[dst] = s.live_u[src];
         s.dead_v[dst] = s.live_v[src];
@@ -324,7 +331,7 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
     long long ncall = 0, ha = 0, hb = 0;
     unsigned int fl = 0;
     for (int j = tid; j < K; j += nth) {
-        const double L = s.skey[j], Lp = j ? s.skey[j - 1] : lprev0;
+        const double L = ckey[j], Lp = j ? ckey[j - 1] : lprev0;
         const double lv = logvol0 + log((double)(N - j) / (double)(N + 1));
         const double w = dev_logaddexp(L, Lp) + lv + log(0.5 / (double)(N - j));
         wmax = fmax(wmax, w);
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
         s.dead_logvol[it0 + j] = lv;
         s.dead_ncall[it0 + j] = s.o_ncall[j];
         const double lo = s.o_logl[j];
-        s.live_logl[s.sidx[j]] = lo;
+        s.live_logl[cidx[j]] = lo;
         ncall += s.o_ncall[j];
         ha += s.o_i0[j];
         hb += s.o_i1[j];
@@ -341,7 +348,7 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
     const double m = block_reduce_max(wmax, rbuf);
     double se = 0.0;
     for (int j = tid; j < K; j += nth) {
-        const double L = s.skey[j], Lp = j ? s.skey[j - 1] : lprev0;
+        const double L = ckey[j], Lp = j ? ckey[j - 1] : lprev0;
         const double lv = logvol0 + log((double)(N - j) / (double)(N + 1));
         se += exp(dev_logaddexp(L, Lp) + lv + log(0.5 / (double)(N - j)) - m);
     }
@@ -361,11 +368,11 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
         double* bkey = akey + NA + (NA & 1);                      // Kpad new
         int* aidx = reinterpret_cast<int*>(bkey + Kpad);
         int* bidx = aidx + NA;
-        const double thr_keep = s.skey[K - 1];
-        for (int i = tid; i < NA; i += nth) { akey[i] = s.skey[K + i]; aidx[i] = s.sidx[K + i]; }
+        const double thr_keep = ckey[K - 1];
+        for (int i = tid; i < NA; i += nth) { akey[i] = ckey[K + i]; aidx[i] = cidx[K + i]; }
         for (int j = tid; j < Kpad; j += nth) {
             bkey[j] = j < K ? s.o_logl[j] : CUDART_INF;
-            bidx[j] = j < K ? s.sidx[j] : 0x7fffffff;
+            bidx[j] = j < K ? cidx[j] : 0x7fffffff;
         }
         __syncthreads();
         for (int k = 2; k <= Kpad; k <<= 1) {
@@ -391,8 +398,8 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
                 const bool less = bkey[mid] < ka || (bkey[mid] == ka && bidx[mid] < ia);
                 if (less) lo = mid + 1; else hi = mid;
             }
-            s.tkey[i + lo] = ka;
-            s.tidx[i + lo] = ia;
+            nkey[i + lo] = ka;
+            nidx[i + lo] = ia;
         }
         for (int j = tid; j < K; j += nth) {                      // new pairs: count survivors below
             const double kb = bkey[j];
@@ -403,18 +410,17 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
                 const bool less = akey[mid] < kb || (akey[mid] == kb && aidx[mid] < ib);
                 if (less) lo = mid + 1; else hi = mid;
             }
-            s.tkey[j + lo] = kb;
-            s.tidx[j + lo] = ib;
+            nkey[j + lo] = kb;
+            nidx[j + lo] = ib;
         }
         __syncthreads();
         if (tid == 0) sc->loglstar = thr_keep;
-        for (int i = tid; i < N; i += nth) { s.skey[i] = s.tkey[i]; s.sidx[i] = s.tidx[i]; }
-        __syncthreads();
     }
     if (tid == 0) {
         sc->logz = dev_logaddexp(sc->logz, m + log(se));
         sc->logvol = logvol0 + log((double)(N - K + 1) / (double)(N + 1));
-        sc->lmax = s.skey[N - 1];
+        sc->lmax = nkey[N - 1];
+        sc->parity = par ^ 1;
         sc->it = it0 + K;
         sc->ncall += ncall;
         sc->round += 1;
@@ -550,7 +556,8 @@ int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* c, int64_t dead_capacity) {
     d.Npad = Npad;
     d.Kpad = 2;
     while (d.Kpad < c->batch) d.Kpad <<= 1;
-    d.threads = c->batch <= 128 ? 256 : B2N_NS_THREADS;     // small rounds: cheaper CTA barriers
+    d.threads = B2N_NS_THREADS;     // (256 threads for small rounds measured 4 % slower: the loops are latency bound)
+    if (const char* e = getenv("B2N_NS_THREADS")) d.threads = atoi(e) >= 1024 ? 1024 : (atoi(e) >= 512 ? 512 : 256);
     d.dlogz = c->dlogz; d.facc = c->facc; d.maxiter = c->maxiter; d.maxcall = c->maxcall;
     d.update_interval = c->update_interval; d.seed = c->seed; d.chain0 = c->chain0;
     const size_t N = d.N, K = d.K;
