@@ -274,7 +274,7 @@ class NestedSampler:
                                          peer=peer)
             else:
                 starts, ell = self.propose_live(loglstar, Q)
-                pts = self.live_u[starts]
+                pts = np.take(self.live_u, starts, axis=0, mode='clip')       # (valid rows by construction)
                 # device copy of the bound follows the host object (cf. samplers._Resident)
                 key = (id(self.bound), getattr(self.bound, 'version', None))
                 if key != getattr(self, '_resident_key', None):

@@ -46,7 +46,7 @@ def t(fn, k=200):
 def propose():
     starts = rng.integers(len(u_live), size=Q)
     ell = bound.random_ells(rng, Q)
-    np.take(u_live, starts, axis=0, out=h_u0.numpy())
+    np.take(u_live, starts, axis=0, out=h_u0.numpy(), mode='clip')
     return ell
 
 
