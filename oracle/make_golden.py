@@ -312,11 +312,65 @@ def gen_chains(B, IS):
     return out
 
 
+def gen_friends(B):
+    """RadFriends / SupFriends (bounding.py:734-1263): two successive updates (the second clusters with the
+    first one's am), leave-one-out and bootstrap radii, overlap counts, scripted draws."""
+    rng = np.random.default_rng(SEED + 7)
+    out = {}
+    clouds = {'blob': cloud_gauss(rng, 160, 4, spread=0.05),
+              'two': np.concatenate([0.25 + 0.02 * rng.standard_normal((90, 3)),
+                                     0.75 + 0.02 * rng.standard_normal((90, 3))])}
+    for cname, pts in clouds.items():
+        n = pts.shape[1]
+        for kind, cls in (('balls', B.RadFriends), ('cubes', B.SupFriends)):
+            p = 'fr_%s_%s_' % (cname, kind)
+            out[p + 'points'] = pts
+            b = cls(n)
+            for rep in (1, 2):
+                b.update(pts if rep == 1 else pts[::-1][:len(pts) - 10], rstate=np.random.default_rng(1), bootstrap=0)
+                b.ctrs = pts if rep == 1 else pts[::-1][:len(pts) - 10]
+                q = p + 'u%d_' % rep
+                out[q + 'cov'], out[q + 'am'], out[q + 'axes'] = b.cov.copy(), b.am.copy(), np.real(b.axes).copy()
+                out[q + 'axes_inv'], out[q + 'logvol'] = np.real(b.axes_inv).copy(), np.float64(b.logvol)
+                # the Sampler enlarges after every update (sampler.py:506-508).  Without it the pair that
+                # defines the leave-one-out radius sits at Mahalanobis distance exactly 1 -- the clustering
+                # threshold of the NEXT update -- and the partition would hinge on the last bit
+                b.scale_to_logvol(b.logvol + np.log(1.25))
+            xs = np.concatenate([pts[:20] + 0.01 * rng.standard_normal((20, n)), rng.random((20, n))])
+            out[p + 'query'] = xs
+            out[p + 'overlap'] = np.array([b.overlap(x) for x in xs])
+            out[p + 'contains'] = np.array([b.contains(x) for x in xs])
+            # radii helpers on the decorrelated points (bounding.py:1651-1705)
+            pt = np.dot(b.ctrs, np.real(b.axes_inv))
+            out[p + 'loo'] = B._friends_leaveoneout_radius(pt, kind)
+            brad = []
+            for r in range(3):
+                g = philox.ScriptedGenerator(SEED, 400 + r)
+                brad.append(B._friends_bootstrap_radius((pt, kind, g)))
+            out[p + 'boot'] = np.array(brad)
+            # scripted draws: sample() and sample(return_q=True)
+            xs1, qs = [], []
+            for c in range(30):
+                g = philox.ScriptedGenerator(SEED, 500 + c)
+                xs1.append(b.sample(rstate=g))
+                x, qq = b.sample(rstate=philox.ScriptedGenerator(SEED, 600 + c), return_q=True)
+                xs1.append(x)
+                qs.append(qq)
+            out[p + 'draws'] = np.array(xs1)
+            out[p + 'draw_q'] = np.array(qs)
+            lv0 = b.logvol
+            b.scale_to_logvol(lv0 + 0.3)
+            out[p + 'scaled_am'], out[p + 'scaled_axes'] = b.am.copy(), np.real(b.axes).copy()
+    np.savez_compressed(os.path.join(OUT, 'friends.npz'), **out)
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     refshim.import_reference()
     from dynesty import bounding as B, internal_samplers as IS
     gen_bounding(B)
+    gen_friends(B)
     out = gen_chains(B, IS)
     print('wrote', OUT, {k: os.path.getsize(os.path.join(OUT, k))
                          for k in sorted(os.listdir(OUT))})

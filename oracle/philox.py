@@ -165,8 +165,9 @@ class ScriptedGenerator(np.random.Generator):
         return self._s.uniforms(int(np.prod(size))).reshape(size)
 
     def uniform(self, low=0.0, high=1.0, size=None):
-        assert low == 0.0 and high == 1.0
-        return self.random(size)
+        """internal_samplers.py:327 (0, 1); bounding.py:1082 ``uniform(-1, 1, size=ndim)`` (SupFriends)."""
+        r = self.random(size)
+        return r if (low == 0.0 and high == 1.0) else low + (high - low) * r
 
     def standard_normal(self, size=None, *a, **k):
         if size is None:
@@ -180,7 +181,9 @@ class ScriptedGenerator(np.random.Generator):
     def integers(self, low, high=None, size=None, **k):
         """bounding.py:1603 ``rstate.integers(npoints, size=npoints)``:
         element e = floor(U_e * npoints) of one uniform vector event."""
-        assert high is None and size is not None
+        assert high is None
+        if size is None:            # bounding.py:819, 1089 ``rstate.integers(nctrs)``: one uniform event
+            return int(self._s.integers(int(low), 1)[0])
         return self._s.integers(int(low), int(np.prod(size))).reshape(size)
 
     def choice(self, *a, **k):  # pragma: no cover
