@@ -1,4 +1,6 @@
-// b2n_rwalk.cu -- batched random-walk proposal chains (one warp per chain).
+// b2n_rwalk.cu -- batched random-walk proposal chains: a warp-per-chain kernel (this comment), and two
+// lock-step FP64-tensor-core kernels further down (rwalk_mma_kernel: the default for 16 <= n <= 64,
+// rwalk_mmas_kernel: n > 64).
 //
 // Replaces RWalkSampler.sample -> generic_random_walk -> propose_ball_point
 // (reference internal_samplers.py:505-561, 866-986, 989-1035) for a whole queue
@@ -11,7 +13,7 @@
 //   5. v = prior_transform(u'), logl = loglikelihood(v), accept iff logl > loglstar
 // exactly `walks` steps; with zero accepts v/logl are recomputed at the start (:970-975).
 //
-// Mapping.  The grid is persistent-sized: ~one CTA per SM, each CTA owns an equal share of
+// Mapping of rwalk_kernel (ncdim < n, n < 16, or B2N_RWALK_IMPL=warp).  The grid is persistent-sized: ~one CTA per SM, each CTA owns an equal share of
 // the queue (<= 16 chains in flight, one warp per chain) and only chains of ONE ellipsoid,
 // whose axes^T and the precision matrix of a GAUSS_PREC model are staged ONCE into shared
 // memory (column stride padded to 128 B so every column read is bank-conflict free) and
@@ -198,13 +200,14 @@ __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
 // Why: the warp-per-chain kernel above streams 40 KB of matrix per proposal out of shared
 // memory and is bound by the shared-memory pipe (84 % of peak, profiles/r1c).  All chains of
 // a CTA use the same matrices and take the same number of steps, so the per-step work of a
-// CTA is Y[n x 16] = A[n x n] X[n x 16]: a small dense contraction.  Distributing A over the
+// CTA is Y[n x 8] = A[n x n] X[n x 8]: a small dense contraction.  Distributing A over the
 // lanes as DMMA fragments (1 double per lane per 8x4 tile; 13 k-tiles for n = 50 -> 26
 // registers per matrix per warp) removes the matrix traffic from shared memory entirely and
-// replaces ~500 LDS/DFMA per proposal by ~4 DMMA.  Only the 16 direction vectors go through
+// replaces ~500 LDS/DFMA per proposal by ~4 DMMA.  Only the 8 direction vectors go through
 // shared memory.  Warp w is (i) the owner of chain w (RNG, wrap/reflect/cube test, prior,
 // accept/reject: phases 1,3,5) and (ii) the owner of work item (slab w % S, chain-tile w / S)
-// of the two contractions (phases 2,4); 4 CTA barriers per step.
+// of the two contractions (phases 2,4); the directions (phase 1) come from a ring generated 8 steps ahead
+// by all warps (see DEPTH below); 3 CTA barriers per step.
 // Used when ncdim == ndim, 16 <= n <= 64 (fragments fit in registers); otherwise the
 // warp-per-chain kernel runs.  Results agree with it to round-off (different summation order).
 // =====================================================================================
