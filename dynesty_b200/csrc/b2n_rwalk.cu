@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
 }
 
 // =====================================================================================
-// rwalk_mma_kernel -- the same chains, 16 at a time per CTA in LOCK-STEP, with both mat-vecs
+// rwalk_mma_kernel -- the same chains, 8 at a time per CTA in LOCK-STEP, with both mat-vecs
 // done as FP64 tensor-core MMAs (mma.sync m8n8k4 f64 = DMMA) whose A operands -- 8-row slabs
 // of axes and of the precision matrix -- live in REGISTERS for the whole kernel.
 //
