@@ -5,6 +5,7 @@
 // math), which is worth ~40 % of the instruction count of these kernels (profiles/r1a vs r1c).
 #pragma once
 #include "b2n_device.cuh"
+#include "b2n_fastmath.cuh"
 
 extern __shared__ __align__(16) double b2n_sm[];
 
@@ -187,6 +188,48 @@ __device__ __forceinline__ double ball_direction(ChainRng& g, int offx, int nc, 
     const double ss = normals_sm(g, offx, nc, lane);
     const double U = rng_uniform(g);
     return pow(U, inv_nc) / sqrt(ss);
+}
+
+// Two directions at once with the BRANCH-FREE math of b2n_fastmath.cuh (nc <= 62): same draw events and ticks
+// as two calls of ball_direction(), but the two Philox -> log -> sqrt -> sincos dependency chains contain no
+// control flow and are written side by side, so the instruction scheduler overlaps their latencies -- which it
+// cannot do for libdevice's log / sqrt / sincospi (slow-path branches keep the calls in separate basic blocks,
+// DESIGN.md 9.1 r1m).  `two` = false generates only the first (the second result is then meaningless).
+__device__ __forceinline__ void ball_direction_pair_fast(const ChainRng& ga, const ChainRng& gb, int offa, int offb,
+                                                         bool two, int nc, int lane, double inv_nc, double& fa,
+                                                         double& fb) {
+    const int nb = (nc + 1) >> 1;
+    const bool isr = lane == 31;
+    const uint32_t blk = isr ? 0u : (uint32_t)lane, dt = isr ? 1u : 0u;
+    const uint4 ra = curand_Philox4x32_10(make_uint4(blk, ga.tick + dt, ga.c2, ga.c3), ga.key);
+    const uint4 rb = curand_Philox4x32_10(make_uint4(blk, gb.tick + dt, gb.c2, gb.c3), gb.key);
+    const double lga = b2n_log(b2n_u52(ra.x, ra.y)), lgb = b2n_log(b2n_u52(rb.x, rb.y));
+    const double rada = b2n_sqrt(-2.0 * lga), radb = b2n_sqrt(-2.0 * lgb);
+    double sa, ca, sb, cb;
+    b2n_sincos2pi(b2n_u52(ra.z, ra.w), &sa, &ca);
+    b2n_sincos2pi(b2n_u52(rb.z, rb.w), &sb, &cb);
+    const double z0a = rada * ca, z1a = rada * sa, z0b = radb * cb, z1b = radb * sb;
+    double ssa = 0.0, ssb = 0.0;
+    if (lane < nb) {
+        const bool full = 2 * lane + 1 < nc;
+        ssa = full ? fma(z1a, z1a, z0a * z0a) : z0a * z0a;
+        ssb = full ? fma(z1b, z1b, z0b * z0b) : z0b * z0b;
+        if (full) {
+            *reinterpret_cast<double2*>(&b2n_sm[offa + 2 * lane]) = make_double2(z0a, z1a);
+            if (two) *reinterpret_cast<double2*>(&b2n_sm[offb + 2 * lane]) = make_double2(z0b, z1b);
+        } else {
+            b2n_sm[offa + 2 * lane] = z0a;
+            if (two) b2n_sm[offb + 2 * lane] = z0b;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ssa += __shfl_xor_sync(B2N_FULL, ssa, o);
+        ssb += __shfl_xor_sync(B2N_FULL, ssb, o);
+    }
+    const double la = __shfl_sync(B2N_FULL, lga, 31), lb = __shfl_sync(B2N_FULL, lgb, 31);
+    fa = b2n_div(exp(la * inv_nc), b2n_sqrt(ssa));
+    fb = b2n_div(exp(lb * inv_nc), b2n_sqrt(two ? ssb : 1.0));
 }
 
 // Stage a column-major matrix (n x n, ld = n in global) into b2n_sm with padded leading dim.

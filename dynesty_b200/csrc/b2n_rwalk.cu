@@ -225,7 +225,9 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // (8 chains) gains a barrier per step; a CTA with few chains -- the small rounds of b2n_ns_run run
 // one chain per CTA -- generates its directions on 8 warps in parallel instead of serially on one,
 // which is the longest dependency chain of a step (Philox -> log -> sqrt -> sincospi).
-template <int LIKE, int KT, int CH, int DEPTH>
+// FAST = the draws use the branch-free math of b2n_fastmath.cuh, two ring items at a time per warp
+// (the default; B2N_RWALK_DRAWS=libm selects libdevice math, results differ by a few ulp in the directions).
+template <int LIKE, int KT, int CH, int DEPTH, bool FAST>
 __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(const RwalkParams p) {
     constexpr int B2N_MMA_CH = CH;
     constexpr int RS = 8 * ((4 * KT + 7) / 8);                    // rows padded to whole 8-row slabs
@@ -288,6 +290,26 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
             // ---- phase 1 (all warps): directions in the unit ball of the next DEPTH steps of every
             //      live chain -> X[s][chain], factors -> F[s][chain].  Item w = (step s, chain c2).
             const int nd = (p.walks - step0) < DEPTH ? (p.walks - step0) : DEPTH;
+            if (FAST && n <= 62) {
+                for (int w = warp; w < nd * nlc; w += 2 * B2N_MMA_CH) {       // items w and w + CH together
+                    const int w2 = w + B2N_MMA_CH;
+                    const bool two = w2 < nd * nlc;
+                    const int sa = w / nlc, ca = w - sa * nlc;
+                    const int sb = two ? w2 / nlc : sa, cb = two ? w2 - sb * nlc : ca;
+                    ChainRng ga, gb;
+                    ga.init(p.seed, chain0_ + (uint64_t)p.order[cd.x + g0 + ca]);
+                    gb.init(p.seed, chain0_ + (uint64_t)p.order[cd.x + g0 + cb]);
+                    ga.tick = 2u * (uint32_t)(step0 + sa);
+                    gb.tick = 2u * (uint32_t)(step0 + sb);
+                    double fa, fb;
+                    ball_direction_pair_fast(ga, gb, oX + sa * XB + ca * XS, oX + sb * XB + cb * XS, two, n, lane, inv_n,
+                                             fa, fb);
+                    if (lane == 0) {
+                        b2n_sm[oF + sa * B2N_MMA_CH + ca] = scale_ * fa;
+                        if (two) b2n_sm[oF + sb * B2N_MMA_CH + cb] = scale_ * fb;
+                    }
+                }
+            } else
             for (int w = warp; w < nd * nlc; w += B2N_MMA_CH) {
                 const int s = w / nlc, c2 = w - s * nlc;
                 ChainRng g;
@@ -696,6 +718,10 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     // ring; results identical)
     int DU = 8;
     if (const char* e = getenv("B2N_RWALK_DEPTH")) DU = (atoi(e) == 1) ? 1 : 8;
+    // draws: branch-free math, two ring items per warp at a time (default); B2N_RWALK_DRAWS=libm = libdevice
+    // log / sqrt / sincospi, one item at a time (measured 3.6 % slower per C2 launch, results differ by a few ulp)
+    const char* denv = getenv("B2N_RWALK_DRAWS");
+    const bool fast_draws = !(denv && !strcmp(denv, "libm")) && DU == 8;
     size_t mma_smem = 0;
     if (use_mma) {
         const int ctas = 2 * ctx->sm_count;                 // 8-chain CTAs, two resident per SM
@@ -786,15 +812,16 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     else if (ax_s) LAUNCH(L, true, false);                             \
     else if (pr_s) LAUNCH(L, false, true);                             \
     else LAUNCH(L, false, false);
-#define LAUNCH_MMA2(L, K, D)                                                                         \
+#define LAUNCH_MMA2(L, K, D, F)                                                                      \
     do {                                                                                            \
-        B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_mma_kernel<L, K, 8, D>,                             \
+        B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_mma_kernel<L, K, 8, D, F>,                          \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        rwalk_mma_kernel<L, K, 8, D><<<grid, 256, smem, ctx->stream>>>(p);                           \
+        rwalk_mma_kernel<L, K, 8, D, F><<<grid, 256, smem, ctx->stream>>>(p);                        \
     } while (0)
-#define LAUNCH_MMA(L, K)                 \
-    if (DU == 1) LAUNCH_MMA2(L, K, 1);   \
-    else LAUNCH_MMA2(L, K, 8);
+#define LAUNCH_MMA(L, K)                        \
+    if (DU == 1) LAUNCH_MMA2(L, K, 1, false);   \
+    else if (fast_draws) LAUNCH_MMA2(L, K, 8, true); \
+    else LAUNCH_MMA2(L, K, 8, false);
 #define CALL_MMA(L)                      \
     if (KT == 8) { LAUNCH_MMA(L, 8) }    \
     else if (KT == 13) { LAUNCH_MMA(L, 13) } \
