@@ -136,3 +136,18 @@ def test_checkpoint_resume_is_bit_identical(fake_ops, tmp_path, sample, kw):
     assert res.logz[-1] == ref.logz[-1]
     with pytest.raises(ValueError):
         mk().run_nested(resume=True)
+
+
+def test_device_loop_single_bound_and_limits(fake_ops):
+    """bound='single' (non-strict contains) inside the rounds; maxiter / maxcall stop the device phase."""
+    m = DL.gauss_test3d()
+    s = nested.NestedSampler(m, nlive=100, bound='single', sample='rwalk', walks=10, queue_size=25, seed=5)
+    res = s.run_nested(dlogz=0.5, loop='device', batch=10)
+    assert abs(res.logz[-1] - 3 * (-np.log(20.))) < 4 * res.logzerr[-1] + 0.1
+    assert s.device_rounds > 5 and isinstance(s.bound, type(s.bound_next))
+    s2 = nested.NestedSampler(m, nlive=100, bound='single', sample='rwalk', walks=10, queue_size=25, seed=5)
+    r2 = s2.run_nested(dlogz=None, maxiter=400, loop='device', batch=10, add_live=False)
+    assert 400 <= r2.niter <= 400 + 10                  # checked once per round
+    s3 = nested.NestedSampler(m, nlive=100, bound='single', sample='rwalk', walks=10, queue_size=25, seed=5)
+    r3 = s3.run_nested(dlogz=None, maxcall=6000, loop='device', batch=10, add_live=False)
+    assert r3.ncall <= 100 + 6000 + 10 * 10 + 25 * 10
