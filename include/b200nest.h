@@ -20,6 +20,9 @@
  *     the ctx device, work is enqueued on the ctx stream and NOT synchronised
  *     (functions that must return a host scalar synchronise and say so).
  *     Arguments documented "host" are host pointers in both modes.
+ *     In B2N_PTR_HOST mode the chain entry points (b2n_{rwalk,rslice,slice,unif}_batch) use PINNED caller
+ *     buffers in place: the kernel reads the start points and writes the finished chains through the
+ *     buffers' device alias (no staging copy); pageable buffers are staged.  Same results either way.
  *   - one caller thread per ctx (the reference's master is single-threaded,
  *     calls are strictly serialised from Sampler, sampler.py:676-778).
  */
