@@ -126,13 +126,14 @@ class B200RWalkSampler(_B200Sampler):
         o = self.run_batch(loglstar, np.asarray(points), ell, _seed_of(seeds))
         self.last_batch = o
         sc = self.scale
-        return [SamplerReturn(u=o['u'][i], v=o['v'][i], logl=float(o['logl'][i]), ncalls=int(o['ncall'][i]),
-                              evaluation_history=[],
-                              tuning_info={'accept': int(o['n_accept'][i]), 'reject': int(o['n_reject'][i]),
-                                           'scale': sc},
-                              proposal_stats={'n_accept': int(o['n_accept'][i]),
-                                              'n_reject': int(o['n_reject'][i])})
-                for i in range(len(o['logl']))]
+        # (one .tolist() per array instead of a numpy scalar conversion per field: the list is built once per
+        # queue fill and its cost, not the kernel's, is what dynesty sees per fill)
+        ll, nc = o['logl'].tolist(), o['ncall'].tolist()
+        na, nr = o['n_accept'].tolist(), o['n_reject'].tolist()
+        return [SamplerReturn(u=u, v=v, logl=l, ncalls=c, evaluation_history=[],
+                              tuning_info={'accept': a, 'reject': r, 'scale': sc},
+                              proposal_stats={'n_accept': a, 'n_reject': r})
+                for u, v, l, c, a, r in zip(o['u'], o['v'], ll, nc, na, nr)]
 
     def tune(self, tuning_info, update=True):
         """internal_samplers.py:460-493."""
@@ -170,16 +171,13 @@ class _B200SliceBase(_B200Sampler):
         ell = self._res.ensure(axes, self._ctx)
         o = self.run_batch(loglstar, np.asarray(points), ell, _seed_of(seeds))
         self.last_batch = o
-        out = []
-        for i in range(len(o['logl'])):
-            warned = bool(o['flags'][i] & _lib.WARN_DOUBLING)
-            ne, nc = int(o['n_expand'][i]), int(o['n_contract'][i])
-            out.append(SamplerReturn(u=o['u'][i], v=o['v'][i], logl=float(o['logl'][i]),
-                                     ncalls=int(o['ncall'][i]), evaluation_history=[],
-                                     tuning_info={'n_expand': ne, 'n_contract': nc,
-                                                  'expansion_warning_set': warned},
-                                     proposal_stats={'n_expand': ne, 'n_contract': nc}))
-        return out
+        ll, ncl = o['logl'].tolist(), o['ncall'].tolist()
+        nes, ncs = o['n_expand'].tolist(), o['n_contract'].tolist()
+        warns = ((o['flags'] & _lib.WARN_DOUBLING) != 0).tolist()
+        return [SamplerReturn(u=u, v=v, logl=l, ncalls=c, evaluation_history=[],
+                              tuning_info={'n_expand': ne, 'n_contract': nc, 'expansion_warning_set': w},
+                              proposal_stats={'n_expand': ne, 'n_contract': nc})
+                for u, v, l, c, ne, nc, w in zip(o['u'], o['v'], ll, ncl, nes, ncs, warns)]
 
     def tune(self, tuning_info, update=True):
         """tune_slice (internal_samplers.py:1209-1239)."""
@@ -242,7 +240,6 @@ class B200UniformSampler(_B200Sampler):
             raise TypeError("B200UniformSampler needs bound=B200Ellipsoid/B200MultiEllipsoid")
         o = self.run_batch(loglstar, len(points), bound, _seed_of(seeds), ncdim=nested_sampler.ncdim)
         self.last_batch = o
-        return [SamplerReturn(u=o['u'][i], v=o['v'][i], logl=float(o['logl'][i]), ncalls=int(o['ncall'][i]),
-                              evaluation_history=[], tuning_info=None,
-                              proposal_stats={'n_proposals': int(o['nprop'][i])})
-                for i in range(len(o['logl']))]
+        return [SamplerReturn(u=u, v=v, logl=l, ncalls=c, evaluation_history=[], tuning_info=None,
+                              proposal_stats={'n_proposals': npr})
+                for u, v, l, c, npr in zip(o['u'], o['v'], o['logl'].tolist(), o['ncall'].tolist(), o['nprop'].tolist())]
