@@ -94,3 +94,29 @@ def test_dropin_dynamic_sampler(dynesty, fake_ops):
     res = ds.results
     assert abs(res['logz'][-1] - (-1.75)) < 5 * res['logzerr'][-1] + 0.15
     assert len(res['batch_nlive']) >= 2
+
+
+def test_dropin_checkpoint_restore(dynesty, fake_ops, tmp_path):
+    """The reference's own checkpointing (Sampler.save -> utils.save_sampler pickles the whole sampler,
+    utils.py:2321-2355; tests/test_resume.py) with the B200 bound / sampler / pool inside: the plug-in objects
+    must pickle (device handles dropped, re-created lazily) and the restored sampler must keep running."""
+    c, b, s = _classes()
+    from dynesty_b200 import likelihoods as DL
+    from dynesty_b200.pool import B200Pool
+    m = DL.gauss_test3d()
+    mk = lambda: dynesty.NestedSampler(m.loglikelihood, m.prior_transform, 3, nlive=100, bound=b.B200MultiEllipsoid(3),
+                                       sample=s.B200RWalkSampler(model=m, walks=10), pool=B200Pool(16), queue_size=16,
+                                       rstate=np.random.default_rng(9),
+                                       use_pool={'prior_transform': False, 'loglikelihood': False})
+    f = str(tmp_path / 'dyn.save')
+    ns = mk()
+    ns.run_nested(maxiter=700, dlogz=1e-9, print_progress=False, checkpoint_file=f, add_live=False)
+    assert ns.nbound > 1
+    ns.save(f)
+    r = dynesty.NestedSampler.restore(f, pool=B200Pool(16))
+    assert isinstance(r.bound, b.B200MultiEllipsoid) and isinstance(r.internal_sampler, s.B200RWalkSampler)
+    assert r.it == ns.it and np.array_equal(r.live_logl, ns.live_logl)
+    assert np.array_equal(r.bound.ctrs, ns.bound.ctrs) and r.internal_sampler.scale == ns.internal_sampler.scale
+    r.run_nested(dlogz=0.5, print_progress=False, resume=True)
+    assert abs(r.results['logz'][-1] - 3 * (-np.log(20.))) < 5 * r.results['logzerr'][-1] + 0.1
+    assert r.results["niter"] > 700
