@@ -120,3 +120,19 @@ def test_dropin_checkpoint_restore(dynesty, fake_ops, tmp_path):
     r.run_nested(dlogz=0.5, print_progress=False, resume=True)
     assert abs(r.results['logz'][-1] - 3 * (-np.log(20.))) < 5 * r.results['logzerr'][-1] + 0.1
     assert r.results["niter"] > 700
+
+
+def test_pool_size_sets_the_queue(dynesty, fake_ops):
+    """utils.py:2358-2381 _parse_pool_queue: without queue_size the Sampler takes it from ``pool.size`` -- the
+    number of chains the B200 pool advertises = chains per kernel launch."""
+    c, b, s = _classes()
+    from dynesty_b200 import likelihoods as DL
+    from dynesty_b200.pool import B200Pool
+    m = DL.gauss_test3d()
+    ns = dynesty.NestedSampler(m.loglikelihood, m.prior_transform, 3, nlive=60, bound=b.B200Ellipsoid(3),
+                               sample=s.B200RSliceSampler(model=m, slices=2), pool=B200Pool(24),
+                               rstate=np.random.default_rng(3),
+                               use_pool={'prior_transform': False, 'loglikelihood': False})
+    assert ns.queue_size == 24
+    ns.run_nested(maxiter=300, dlogz=1e-9, print_progress=False, add_live=False)
+    assert ns.internal_sampler.last_batch is not None and len(ns.internal_sampler.last_batch['logl']) == 24
