@@ -592,14 +592,18 @@ __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int
         lam = s_lam;
         conv = s_diff < 1e-11 && trdev < 1e-6;
     }
-    // sign convention: the component of largest magnitude is positive
+    // sign convention: the component of largest magnitude is positive.  (Own shared word + a barrier first:
+    // compute-sanitizer racecheck flagged the earlier version, which reused s_lam here while slower threads could
+    // still be reading the eigenvalue from it -- profiles/r1o_sanitizer_racecheck_smoke.log.)
+    __shared__ double s_sgn;
+    __syncthreads();
     if (tid == 0) {
         int im = 0;
         for (int i = 1; i < n; i++) if (fabs(v[i]) > fabs(v[im])) im = i;
-        s_lam = v[im] < 0.0 ? -1.0 : 1.0;
+        s_sgn = v[im] < 0.0 ? -1.0 : 1.0;
     }
     __syncthreads();
-    const double sgn = s_lam, ax = sqrt(lam);
+    const double sgn = s_sgn, ax = sqrt(lam);
     double* AX = na.axes + (size_t)node * nn;
     for (size_t e = tid; e < nn; e += T) {
         const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
