@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(1024) eig_check_kernel(NodeArrays na, const in
     if (retry_only && !st->retry) { if (tid == 0) gMode[b] = -1; return; }
     const double* lam = gLam + (size_t)b * n;
     const size_t nn = (size_t)n * n;
+    const int trial = st->trial;        // read by every thread BEFORE the barrier: thread 0 rewrites it below
     if (tid == 0) {
         bool fin = true;
         double mx = -INFINITY, mn = INFINITY;
@@ -214,7 +215,6 @@ __global__ void __launch_bounds__(1024) eig_check_kernel(NodeArrays na, const in
     }
     __syncthreads();
     const int failed = s_failed;
-    const int trial = st->trial;
     double* Cm = na.cov + (size_t)node * nn;
     if (failed == 0) {
         for (int k = tid; k < n; k += T) {
