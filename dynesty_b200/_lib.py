@@ -4,6 +4,7 @@ There is NO CPU fallback: if the library is missing or no CUDA device is
 available every entry point raises ``B200Unavailable``.
 """
 import ctypes as C
+import itertools
 import os
 
 import numpy as np
@@ -147,11 +148,17 @@ def f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+_ctx_serial = itertools.count(1)
+
+
 class Context:
-    """Owns one b2n_ctx (one per process / GPU)."""
+    """Owns one b2n_ctx.  One per process / GPU is the normal case; several contexts on one GPU
+    (each with its own stream and scratch memory) run concurrently -- ``dynesty_b200.replicas``."""
 
     def __init__(self, device=0):
         self.lib = load()
+        self.serial = next(_ctx_serial)      # never reused, unlike id(): the key of per-context caches
+        self.resident_key = None             # version token of the bound whose ellipsoids are resident (ops.bound_set)
         h = C.c_void_p()
         st = self.lib.b2n_init(int(device), C.byref(h))
         if st != OK:

@@ -6,6 +6,7 @@ logvol_ells/nells``, bounding.py:201-240, 440-476; plotting.py:1710, 2035).  Eve
 numeric method is one call into libb200nest.so; the objects hold plain numpy arrays,
 so ``copy.deepcopy`` (sampler.py:510) and ``pickle`` (utils.py:2343) just work.
 """
+import itertools
 import math
 import warnings
 
@@ -40,6 +41,20 @@ class TaggedAxes(np.ndarray):
         return np.array(self)
 
 
+# Version tokens: process-wide unique and increasing, a fresh one after EVERY change of a bound's arrays and
+# after every unpickle / deepcopy.  `Context.resident_key == bound.version` therefore means "these very
+# ellipsoids are the resident bound of that ctx" no matter which object, sampler or driver uploaded them
+# (one resident bound per ctx; round-1 ADVICE: per-object caches keyed on id() went stale).
+_version = itertools.count(1)
+
+
+def _resolve_ctx(ctx, device):
+    """The Context a bound works on: the one it was given, else the default context of its device."""
+    if ctx is not None:
+        return ctx
+    return _lib.default_context(device)
+
+
 def _seed_from(rstate):
     """64-bit Philox seed drawn from the caller's numpy Generator."""
     if rstate is None:
@@ -64,6 +79,7 @@ class B200MultiEllipsoid(BoundBase):
     def __init__(self, ndim, ctx=None):
         super().__init__(ndim)
         self._ctx = ctx
+        self._device = getattr(ctx, 'device', None)     # survives pickling (the handle does not)
         n = ndim
         # Ellipsoid(ndim) default: centre 0 (sic), cov = I n/4 (bounding.py:203-205)
         cov = np.identity(n) * n / 4
@@ -79,13 +95,34 @@ class B200MultiEllipsoid(BoundBase):
         self.logvol = float(self.logvol_ells[0])
         self.funit = 1
         self.labels = None
-        self.version = 0           # bumped whenever the arrays change (device cache key)
+        self.version = next(_version)      # new token whenever the arrays change (device cache key)
 
-    # -- pickling / deepcopy: drop the (per-process) context handle -----------------
+    # -- pickling: drop the (per-process) context handle, keep the device index ------------
     def __getstate__(self):
         d = self.__dict__.copy()
         d['_ctx'] = None
         return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self.__dict__.setdefault('_device', None)
+        self.version = next(_version)
+
+    # -- deepcopy (sampler.py:510, 589 copy the bound on every update): same process, so the copy stays
+    #    on the SAME context (a copy that silently moved to the default context would run on another
+    #    stream / GPU than the sampler it belongs to)
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = v if k == '_ctx' else copy.deepcopy(v, memo)
+        new.version = next(_version)
+        return new
+
+    @property
+    def ctx(self):
+        return _resolve_ctx(self._ctx, self._device)
 
     @property
     def ells(self):
@@ -94,20 +131,20 @@ class B200MultiEllipsoid(BoundBase):
     def _refresh_logvol(self):
         from scipy.special import logsumexp
         self.logvol = float(logsumexp(self.logvol_ells))     # ignores overlap (:466)
-        self.version += 1
+        self.version = next(_version)
 
     # -- Bound interface -----------------------------------------------------------------
     def contains(self, x):
         """bounding.py:520-523 (strict <)."""
-        _, q = ops.membership(np.asarray(x, dtype=float)[None], self.ctrs, self.ams, strict=True, ctx=self._ctx)
+        _, q = ops.membership(np.asarray(x, dtype=float)[None], self.ctrs, self.ams, strict=True, ctx=self.ctx)
         return bool(q[0] > 0)
 
     def contains_many(self, x):
         """Batched ``contains`` (one launch for a whole queue of start points)."""
-        return ops.membership(x, self.ctrs, self.ams, strict=True, ctx=self._ctx)[1] > 0
+        return ops.membership(x, self.ctrs, self.ams, strict=True, ctx=self.ctx)[1] > 0
 
     def within(self, x, j=None):
-        mask, _ = ops.membership(np.asarray(x, dtype=float)[None], self.ctrs, self.ams, ctx=self._ctx)
+        mask, _ = ops.membership(np.asarray(x, dtype=float)[None], self.ctrs, self.ams, ctx=self.ctx)
         m = mask[0].copy()
         if j is not None:
             m[j] = False
@@ -116,14 +153,16 @@ class B200MultiEllipsoid(BoundBase):
     def overlap(self, x, j=None):
         return len(self.within(x, j=j))
 
-    def make_resident(self):
-        ops.bound_set(self.axes_all, self.ctrs, self.ams, self.logvol_ells, ctx=self._ctx)
+    def make_resident(self, ctx=None):
+        """Upload the ellipsoids as the resident bound of `ctx` (default: the bound's own context)."""
+        ops.bound_set(self.axes_all, self.ctrs, self.ams, self.logvol_ells, ctx=ctx if ctx is not None else self.ctx,
+                      key=self.version)
 
     def samples(self, nsamples, rstate=None):
         """bounding.py:592-606: uniform draws from the union (no cube test)."""
-        self.make_resident()
+        ops.ensure_resident(self, self.ctx)
         o = ops.unif_batch(-1, nsamples, self.ndim, -np.inf, _seed_from(rstate), draw_only=True,
-                           ncdim=self.ndim, ctx=self._ctx)
+                           ncdim=self.ndim, ctx=self.ctx)
         return o['u']
 
     def sample(self, rstate=None, return_q=False):
@@ -136,9 +175,9 @@ class B200MultiEllipsoid(BoundBase):
     def monte_carlo_logvol(self, ndraws=10000, rstate=None, return_overlap=True):
         """bounding.py:608-630: MC estimate of the log-volume of the UNION (and of its
         fractional overlap with the unit cube) from volume-weighted draws and their q."""
-        self.make_resident()
+        ops.ensure_resident(self, self.ctx)
         o = ops.unif_batch(-1, ndraws, self.ndim, -np.inf, _seed_from(rstate), draw_only=True, mixture=True,
-                           ncdim=self.ndim, ctx=self._ctx)
+                           ncdim=self.ndim, ctx=self.ctx)
         w = 1. / o['ncall']                                   # 1 / q
         logvol = math.log(w.sum() / ndraws) + self.logvol
         if not return_overlap:
@@ -176,7 +215,7 @@ class B200MultiEllipsoid(BoundBase):
         else:
             target = self.logvol_ells + (float(logvol) - self.logvol)
         ops.scale_to_logvol(self.covs, self.ams, self.axes_all, self.axlens_all, self.logvol_ells,
-                            target, ctx=self._ctx)
+                            target, ctx=self.ctx)
         self._refresh_logvol()
 
     def update(self, points, rstate=None, bootstrap=0, pool=None, mc_integrate=False):
@@ -185,7 +224,7 @@ class B200MultiEllipsoid(BoundBase):
         npoints, ndim = points.shape
         if npoints == 1:
             raise RuntimeError('Cannot compute the bounding ellipsoid of a single point.')
-        o = ops.multi_decompose(points, ctx=self._ctx)
+        o = ops.multi_decompose(points, ctx=self.ctx)
         if o['warn'] & _lib.WARN_IDENTITY_FALLBACK:
             warnings.warn("Failed to guarantee the ellipsoid axes will be non-singular. "
                           "Defaulting to a sphere.")
@@ -195,7 +234,7 @@ class B200MultiEllipsoid(BoundBase):
         self.labels = o['labels']
         self._refresh_logvol()
         if bootstrap > 0:
-            expands = ops.bootstrap_expand(points, True, int(bootstrap), _seed_from(rstate), 0, ctx=self._ctx)
+            expands = ops.bootstrap_expand(points, True, int(bootstrap), _seed_from(rstate), 0, ctx=self.ctx)
             expand = float(expands.max())
             if math.log10(expand) * ndim > 2:                              # :705-714
                 warnings.warn('The enlargement factor for the ellipsoidal bounds determined '
@@ -236,16 +275,20 @@ class B200Ellipsoid(BoundBase):
     def contains(self, x):
         """bounding.py:302-305 (non-strict: distance <= 1)."""
         return bool(ops.membership(np.asarray(x, dtype=float)[None], self._m.ctrs, self._m.ams,
-                                   strict=False, ctx=self._m._ctx)[1][0] > 0)
+                                   strict=False, ctx=self._m.ctx)[1][0] > 0)
 
     def contains_many(self, x):
-        return ops.membership(x, self._m.ctrs, self._m.ams, strict=False, ctx=self._m._ctx)[1] > 0
+        return ops.membership(x, self._m.ctrs, self._m.ams, strict=False, ctx=self._m.ctx)[1] > 0
 
     def distance_many(self, x):
-        return np.sqrt(ops.membership(x, self._m.ctrs, self._m.ams, want_d2=True, ctx=self._m._ctx)[2][:, 0])
+        return np.sqrt(ops.membership(x, self._m.ctrs, self._m.ams, want_d2=True, ctx=self._m.ctx)[2][:, 0])
 
-    def make_resident(self):
-        self._m.make_resident()
+    def make_resident(self, ctx=None):
+        self._m.make_resident(ctx)
+
+    @property
+    def ctx(self):
+        return self._m.ctx
 
     def samples(self, nsamples, rstate=None):
         return self._m.samples(nsamples, rstate=rstate)
@@ -265,7 +308,7 @@ class B200Ellipsoid(BoundBase):
     def update(self, points, rstate=None, bootstrap=0, pool=None, mc_integrate=False):
         """bounding.py:345-414."""
         points = np.ascontiguousarray(points, dtype=float)
-        o = ops.bounding_ellipsoid(points, ctx=self._m._ctx)
+        o = ops.bounding_ellipsoid(points, ctx=self._m.ctx)
         if o['warn'] & _lib.WARN_IDENTITY_FALLBACK:
             warnings.warn("Failed to guarantee the ellipsoid axes will be non-singular. "
                           "Defaulting to a sphere.")
@@ -276,7 +319,7 @@ class B200Ellipsoid(BoundBase):
         m.logvol_ells = np.array([o['logvol']])
         m._refresh_logvol()
         if bootstrap > 0:
-            expands = ops.bootstrap_expand(points, False, int(bootstrap), _seed_from(rstate), 0, ctx=m._ctx)
+            expands = ops.bootstrap_expand(points, False, int(bootstrap), _seed_from(rstate), 0, ctx=m.ctx)
             expand = float(expands.max())
             if expand > 1.:
                 self.scale_to_logvol(self.logvol + self.ndim * math.log(expand))

@@ -53,11 +53,37 @@ class Comm:
         out = {}
         for k in sorted(local):
             a = np.ascontiguousarray(local[k])
+            # torch.distributed has no unsigned 16/32/64-bit collectives (gloo raises "Invalid scalar type"):
+            # ship the bits as the signed type of the same width and view them back
+            dt = a.dtype
+            if dt.kind == 'u' and dt.itemsize > 1:
+                a = a.view(np.dtype('i%d' % dt.itemsize))
             t = torch.from_numpy(a).to(self.device)
             full = torch.empty((Q,) + tuple(a.shape[1:]), dtype=t.dtype, device=self.device)
             dist.all_gather_into_tensor(full, t)
-            out[k] = full.cpu().numpy()
+            out[k] = full.cpu().numpy().view(dt)
         return out
+
+    def allreduce_sum(self, a):
+        """Element-wise sum over ranks of a float64 array (the moment exchange of a sharded bound update)."""
+        t = self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def gather_rows(self, a, dst=0):
+        """Gather per-rank arrays (same shape on every rank) on rank `dst` only: the other ranks' hosts
+        receive nothing (rank 0 owns the nested-sampling bookkeeping)."""
+        a = np.ascontiguousarray(a)
+        dt = a.dtype
+        if dt.kind == 'u' and dt.itemsize > 1:
+            a = a.view(np.dtype('i%d' % dt.itemsize))
+        t = self.torch.from_numpy(a).to(self.device)
+        if self.rank == dst:
+            parts = [self.torch.empty_like(t) for _ in range(self.world)]
+            self.dist.gather(t, parts, dst=dst)
+            return self.torch.cat(parts).cpu().numpy().view(dt)
+        self.dist.gather(t, None, dst=dst)
+        return None
 
     def max(self, x):
         t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.device)

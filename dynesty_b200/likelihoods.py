@@ -50,7 +50,7 @@ class DeviceModel:
 
     def ids(self, ctx=None):
         ctx = ctx if ctx is not None else _lib.default_context()
-        key = id(ctx)
+        key = ctx.serial           # (not id(ctx): an address can be reused after a Context is freed)
         if key not in self._ids:
             out = []
             for pk in (self.prior_kind, _lib.PRIOR_IDENTITY):

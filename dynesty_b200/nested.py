@@ -171,7 +171,6 @@ class NestedSampler:
     def __getstate__(self):
         d = self.__dict__.copy()
         d['ctx'] = d['comm'] = None                  # device handles are per process
-        d.pop('_resident_key', None)
         return d
 
     def save(self, fname):
@@ -199,6 +198,12 @@ class NestedSampler:
         return ns
 
     # ------------------------------------------------------------------ bounds
+    def _ensure_resident(self):
+        from . import ops, _lib
+        c = self.ctx if self.ctx is not None else _lib.default_context()
+        if c.resident_key is None or c.resident_key != self.bound.version:
+            self.bound.make_resident(c)
+
     def update_bound(self, subset=slice(None)):
         """sampler.py:493-510."""
         self.bound.update(self.live_u[subset, :self.ncdim], rstate=self.rstate, bootstrap=self.bound_bootstrap)
@@ -275,11 +280,9 @@ class NestedSampler:
             else:
                 starts, ell = self.propose_live(loglstar, Q)
                 pts = np.take(self.live_u, starts, axis=0, mode='clip')       # (valid rows by construction)
-                # device copy of the bound follows the host object (cf. samplers._Resident)
-                key = (id(self.bound), getattr(self.bound, 'version', None))
-                if key != getattr(self, '_resident_key', None):
-                    self.bound.make_resident()
-                    self._resident_key = key
+                # device copy of the bound follows the host object (one resident bound per ctx, tracked on the
+                # Context: ops.ensure_resident)
+                self._ensure_resident()
 
                 def fn(lo, hi, peer):
                     return smp.run_batch(loglstar, pts[lo:hi], ell[lo:hi], self.seed, chain0=c0 + lo, peer=peer)
@@ -344,8 +347,7 @@ class NestedSampler:
         if snap is not None:
             rounds0 = snap['rounds']
             ops.ns_set_counters(snap['rounds'], snap['ncall_last_update'], snap['doubling'], ctx=self.ctx)
-        self.bound.make_resident()
-        self._resident_key = (id(self.bound), getattr(self.bound, 'version', None))
+        self._ensure_resident()
         cap, last_forced = 64 * N, -1
         ncall_start, rounds = self.ncall, rounds0
         import time
@@ -394,8 +396,7 @@ class NestedSampler:
                 self.nbound += 1
                 self.ncall_at_last_update = self.ncall
                 self.bound_history.append((self.ncall, getattr(self.bound, 'nells', 1), float(self.bound.logvol)))
-                self.bound.make_resident()
-                self._resident_key = (id(self.bound), getattr(self.bound, 'version', None))
+                self._ensure_resident()
                 ops.ns_bound_updated(ctx=self.ctx)
                 tm['bound_s'] += time.perf_counter() - t0
                 if checkpoint_file is not None and time.perf_counter() - t_ckpt >= checkpoint_every:

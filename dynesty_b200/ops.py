@@ -103,9 +103,13 @@ def bootstrap_expand(points, multi, nboot, seed, chain0, ctx=None):
     return out
 
 
-def bound_set(axes, ctrs=None, ams=None, logvols=None, ctx=None):
-    """Make K ellipsoids resident for the proposal kernels (axes: (K, nc, nc))."""
+def bound_set(axes, ctrs=None, ams=None, logvols=None, ctx=None, key=None):
+    """Make K ellipsoids resident for the proposal kernels (axes: (K, nc, nc)).
+    A ctx holds ONE resident bound; `key` (the uploading bound's version token, None = anonymous) is
+    recorded on the Context so that every user of the ctx can tell whether its bound is still the
+    resident one (``ensure_resident``)."""
     ctx = _ctx(ctx)
+    ctx.resident_key = None
     axes = f64(axes)
     if axes.ndim == 2:
         axes = axes[None]
@@ -113,6 +117,14 @@ def bound_set(axes, ctrs=None, ams=None, logvols=None, ctx=None):
     if ctrs is not None:
         ctrs, ams, logvols = f64(ctrs).reshape(K, nc), f64(ams).reshape(K, nc, nc), f64(logvols).reshape(K)
     ctx.check(ctx.lib.b2n_bound_set(ctx.h, K, nc, ptr(ctrs), ptr(ams), ptr(axes), ptr(logvols)))
+    ctx.resident_key = key
+
+
+def ensure_resident(bound, ctx=None):
+    """Upload `bound` (a B200 bound) unless it already is the resident bound of the ctx."""
+    ctx = _ctx(ctx if ctx is not None else getattr(bound, 'ctx', None))
+    if ctx.resident_key is None or ctx.resident_key != bound.version:
+        bound.make_resident()
 
 
 def _chain_args(model, u0, ncdim, loglstar, scale, seed, chain0, ell, dimflags, Q=None, ndim=None):

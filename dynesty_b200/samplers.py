@@ -38,20 +38,18 @@ def _seed_of(seeds, fallback_rstate=None):
 
 
 class _Resident:
-    """Keeps the device copy of the current bound's ellipsoids in sync."""
-
-    def __init__(self):
-        self.key = None
+    """Keeps the device copy of the current bound's ellipsoids in sync.  Which bound is resident is
+    recorded ONCE per context (``Context.resident_key``, set by ``ops.bound_set``), not per sampler:
+    anything else that uploads a bound to the same ctx invalidates it for everybody."""
 
     def ensure(self, axes_list, ctx):
         """Returns the int32 ellipsoid index of every chain."""
         a0 = axes_list[0]
         if isinstance(a0, TaggedAxes) and a0.bound is not None and hasattr(a0.bound, 'make_resident'):
             b = a0.bound
-            key = (id(b), getattr(b, 'version', None))
-            if key != self.key:
-                b.make_resident()
-                self.key = key
+            c = ctx if ctx is not None else b.ctx
+            if c.resident_key is None or c.resident_key != b.version:
+                b.make_resident(c)
             return np.fromiter((a.ell for a in axes_list), dtype=np.int32, count=len(axes_list))
         # foreign Bound (e.g. the reference's own classes or a user Box bound,
         # tests/test_bound_interface.py:20-49): upload the distinct matrices of this fill
@@ -63,8 +61,7 @@ class _Resident:
                 uniq[k] = len(mats)
                 mats.append(np.asarray(a, dtype=float))
             ell[i] = uniq[k]
-        ops.bound_set(np.array(mats), ctx=ctx)
-        self.key = None
+        ops.bound_set(np.array(mats), ctx=ctx)          # anonymous upload: resident_key = None
         return ell
 
 
@@ -224,10 +221,9 @@ class B200UniformSampler(_B200Sampler):
     device-resident ellipsoids)."""
 
     def run_batch(self, loglstar, nchain, bound, seed, chain0=0, ncdim=None, peer=None):
-        key = (id(bound), getattr(bound, 'version', None))
-        if key != self._res.key:
-            bound.make_resident()
-            self._res.key = key
+        c = self._ctx if self._ctx is not None else bound.ctx
+        if c.resident_key is None or c.resident_key != bound.version:
+            bound.make_resident(c)
         n = self.ndim or self.model.ndim
         flags = self._flags()
         return ops.unif_batch(self.model.model_id(self._ctx), nchain, n, loglstar, seed, chain0=chain0,

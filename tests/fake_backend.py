@@ -98,7 +98,28 @@ def bootstrap_expand(points, multi, nboot, seed, chain0, ctx=None):
     return out
 
 
-def bound_set(axes, ctrs=None, ams=None, logvols=None, ctx=None):
+class FakeContext:
+    """What the host code reads off a ``_lib.Context`` (no device behind it)."""
+    serial = 0
+    device = 0
+    resident_key = None
+
+
+_fake_ctx = FakeContext()
+
+
+def default_context(device=None):
+    return _fake_ctx
+
+
+def ensure_resident(bound, ctx=None):
+    c = ctx if ctx is not None else _fake_ctx
+    if c.resident_key is None or c.resident_key != bound.version:
+        bound.make_resident()
+
+
+def bound_set(axes, ctrs=None, ams=None, logvols=None, ctx=None, key=None):
+    (ctx if ctx is not None else _fake_ctx).resident_key = key
     axes = np.asarray(axes, dtype=float)
     if axes.ndim == 2:
         axes = axes[None]
@@ -293,13 +314,15 @@ def ns_destroy(ctx=None):
 
 FUNCS = ['ns_set_counters', 'ns_create', 'ns_set_state', 'ns_status', 'ns_run', 'ns_bound_updated', 'ns_reserve_dead',
          'ns_get_live', 'ns_get_dead', 'ns_destroy', 'model_eval', 'membership', 'bounding_ellipsoid', 'multi_decompose', 'scale_to_logvol',
-         'bootstrap_expand', 'bound_set', 'dimflags_from', 'rwalk_batch', 'rslice_batch', 'slice_batch',
+         'bootstrap_expand', 'bound_set', 'ensure_resident', 'dimflags_from', 'rwalk_batch', 'rslice_batch', 'slice_batch',
          'unif_batch']
 
 
 def install(monkeypatch):
-    from dynesty_b200 import ops, likelihoods
+    from dynesty_b200 import ops, likelihoods, _lib
     _state.clear()          # no resident bound until the code under test uploads one
+    _fake_ctx.resident_key = None
+    monkeypatch.setattr(_lib, 'default_context', default_context)
     g = globals()
     for name in FUNCS:
         monkeypatch.setattr(ops, name, g[name])

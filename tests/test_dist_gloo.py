@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _run(rank, world, port, outdir):
+def _run(rank, world, port, outdir, sample='rwalk'):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -39,22 +39,25 @@ def _run(rank, world, port, outdir):
         dist.init_process_group('gloo', rank=rank, world_size=world)
         comm = Comm()
     m = DL.gauss_test3d()
-    s = nested.NestedSampler(m, nlive=60, bound='multi', sample='rwalk', walks=8, queue_size=20, seed=5, comm=comm)
+    s = nested.NestedSampler(m, nlive=60, bound='multi', sample=sample, walks=8, slices=3, queue_size=20, seed=5,
+                             comm=comm)
     res = s.run_nested(dlogz=None, maxiter=250)
-    np.savez(os.path.join(outdir, 'r%d_w%d.npz' % (rank, world)), logz=res.logz, logl=res.logl,
+    np.savez(os.path.join(outdir, '%s_r%d_w%d.npz' % (sample, rank, world)), logz=res.logz, logl=res.logl,
              samples=res.samples, ncall=res.ncall)
     if world > 1:
         dist.destroy_process_group()
 
 
-def test_sharded_run_matches_single_rank(tmp_path):
+@pytest.mark.parametrize('sample', ['rwalk', 'rslice', 'unif'])
+def test_sharded_run_matches_single_rank(tmp_path, sample):
+    """rslice / unif fills return an unsigned `flags` array: the all-gather must carry it."""
     import torch.multiprocessing as mp
-    _run(0, 1, 0, str(tmp_path))
+    _run(0, 1, 0, str(tmp_path), sample)
     port = _free_port()
-    mp.spawn(_run, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    a = np.load(tmp_path / 'r0_w1.npz')
-    b0 = np.load(tmp_path / 'r0_w2.npz')
-    b1 = np.load(tmp_path / 'r1_w2.npz')
+    mp.spawn(_run, args=(2, port, str(tmp_path), sample), nprocs=2, join=True)
+    a = np.load(tmp_path / ('%s_r0_w1.npz' % sample))
+    b0 = np.load(tmp_path / ('%s_r0_w2.npz' % sample))
+    b1 = np.load(tmp_path / ('%s_r1_w2.npz' % sample))
     for k in ('logz', 'logl', 'samples', 'ncall'):
         assert np.array_equal(b0[k], b1[k])            # replicated host state
         assert np.array_equal(a[k], b0[k])             # sharding does not change the run

@@ -114,3 +114,29 @@ def test_queue_discard_rule(fake_ops):
     assert res.ncall == 50 + res.ncall_per_it.sum() + (len(s._ql) - s._qpos) * 0 or True
     assert res.ncall_per_it.sum() <= res.ncall - 50
     assert np.all(np.diff(res.logl) > 0)              # dead points strictly increasing
+
+
+def test_resident_bound_is_tracked_per_context(fake_ops):
+    """a ctx holds ONE resident bound.  Two samplers stepped alternately on the same ctx must each
+    find that the other's upload invalidated theirs (the token lives on the Context, not in per-object caches),
+    and a deepcopy / unpickle never aliases the token of the object it came from."""
+    import copy
+    import pickle
+    from dynesty_b200 import nested, likelihoods as DL, _lib
+    import fake_backend
+    m = DL.gauss_test3d()
+    a = nested.NestedSampler(m, nlive=50, bound='multi', sample='rwalk', walks=5, queue_size=10, seed=1)
+    b = nested.NestedSampler(m, nlive=50, bound='multi', sample='rwalk', walks=5, queue_size=10, seed=2)
+    a.run_nested(dlogz=None, maxiter=120)
+    ctx = _lib.default_context()
+    assert ctx.resident_key == a.bound.version
+    axes_a = fake_backend._state['axes'].copy()
+    b.run_nested(dlogz=None, maxiter=120)
+    assert ctx.resident_key == b.bound.version != a.bound.version
+    a._ensure_resident()                                   # A's next fill: must upload again
+    assert ctx.resident_key == a.bound.version
+    assert np.array_equal(fake_backend._state['axes'], axes_a)
+    c = copy.deepcopy(a.bound)
+    d = pickle.loads(pickle.dumps(a.bound))
+    assert len({a.bound.version, c.version, d.version}) == 3
+    assert c._ctx is a.bound._ctx                           # a deepcopy stays on its context
