@@ -125,8 +125,10 @@ def test_resident_bound_is_tracked_per_context(fake_ops):
     from dynesty_b200 import nested, likelihoods as DL, _lib
     import fake_backend
     m = DL.gauss_test3d()
-    a = nested.NestedSampler(m, nlive=50, bound='multi', sample='rwalk', walks=5, queue_size=10, seed=1)
-    b = nested.NestedSampler(m, nlive=50, bound='multi', sample='rwalk', walks=5, queue_size=10, seed=2)
+    a = nested.NestedSampler(m, nlive=50, bound='multi', sample='rwalk', walks=5, queue_size=10, seed=1,
+                             first_update={'min_ncall': 0, 'min_eff': 100.})
+    b = nested.NestedSampler(m, nlive=50, bound='multi', sample='rwalk', walks=5, queue_size=10, seed=2,
+                             first_update={'min_ncall': 0, 'min_eff': 100.})
     a.run_nested(dlogz=None, maxiter=120)
     ctx = _lib.default_context()
     assert ctx.resident_key == a.bound.version
