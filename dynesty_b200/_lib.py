@@ -15,11 +15,11 @@ LIBPATH = os.path.join(HERE, 'libb200nest.so')
 PTR_HOST, PTR_DEVICE = 0, 1
 DIM_PERIODIC, DIM_REFLECTIVE = 1, 2
 PRIOR_IDENTITY, PRIOR_UNIFORM, PRIOR_NORMAL_PPF = 0, 1, 2
-LIKE_GAUSS_PREC, LIKE_GAUSS_DIAG, LIKE_EGGBOX, LIKE_SHELLS = 0, 1, 2, 3
+LIKE_GAUSS_PREC, LIKE_GAUSS_DIAG, LIKE_EGGBOX, LIKE_SHELLS, LIKE_REGION2D = 0, 1, 2, 3, 4
 WARN_IDENTITY_FALLBACK, WARN_DOUBLING, WARN_Q0_SLACK, WARN_UNIF_INEFFICIENT = 1, 2, 4, 8
 
 (OK, ERR_CUDA, ERR_ARG, ERR_SINGLE_POINT, ERR_SINGULAR, ERR_ELL_INIT, ERR_INVALID_REGION,
- ERR_Q0, ERR_SLICE_FAIL, ERR_NOMEM, ERR_UNSUPPORTED, ERR_TOO_MANY_ELLS, ERR_PEER) = range(13)
+ ERR_Q0, ERR_SLICE_FAIL, ERR_NOMEM, ERR_UNSUPPORTED, ERR_TOO_MANY_ELLS, ERR_PEER, ERR_PLATEAU) = range(14)
 PEER_HANDLE_BYTES, MAX_PEERS = 64, 8
 
 
@@ -46,7 +46,9 @@ class NsConfig(C.Structure):
                 ('sampler', C.c_int32), ('steps', C.c_int32), ('model_id', C.c_int32),
                 ('strict_contains', C.c_int32), ('facc', C.c_double), ('dlogz', C.c_double),
                 ('maxiter', C.c_int64), ('maxcall', C.c_int64), ('update_interval', C.c_int64),
-                ('seed', C.c_uint64), ('chain0', C.c_uint64), ('dimflags', C.c_void_p)]
+                ('seed', C.c_uint64), ('chain0', C.c_uint64), ('dimflags', C.c_void_p),
+                ('unit_cube_phase', C.c_int32), ('use_logl_max', C.c_int32), ('first_min_ncall', C.c_int64),
+                ('first_min_eff', C.c_double), ('logl_max', C.c_double), ('it0', C.c_int64)]
 
 
 class NsStatus(C.Structure):
@@ -76,12 +78,15 @@ SYMBOLS = {
     'b2n_membership': (C.c_int, [_P, _P, _L, _I, _P, _P, _I, _I, _P, _P, _P]),
     'b2n_bounding_ellipsoid': (C.c_int, [_P, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
     'b2n_multi_decompose': (C.c_int, [_P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'b2n_improve_covar': (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P]),
+    'b2n_fp64_peak': (C.c_int, [_P, _I, _I, C.POINTER(_D), C.POINTER(_D)]),
     'b2n_scale_to_logvol': (C.c_int, [_P, _I, _I, _P, _P, _P, _P, _P, _P]),
     'b2n_bootstrap_expand': (C.c_int, [_P, _P, _L, _I, _I, _I, _U64, _U64, _P]),
     'b2n_bound_set': (C.c_int, [_P, _I, _I, _P, _P, _P, _P]),
     'b2n_rwalk_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _I, _P, _P, _P, _P, _P, _P]),
     'b2n_rslice_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     'b2n_slice_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    'b2n_unitcube_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _P, _P, _P, _P, _P]),
     'b2n_unif_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _P, _P, _P, _P, _P, _P]),
     'b2n_peer_export': (C.c_int, [_P, _U64, _P]),
     'b2n_peer_import': (C.c_int, [_P, _I, _I, _P]),
@@ -98,6 +103,8 @@ SYMBOLS = {
     'b2n_ns_status_get': (C.c_int, [_P, C.POINTER(NsStatus)]),
     'b2n_ns_set_counters': (C.c_int, [_P, _L, _L, _I]),
     'b2n_ns_bound_updated': (C.c_int, [_P]),
+    'b2n_ns_update_bound': (C.c_int, [_P, _I, _D, _P, _P, _P]),
+    'b2n_ns_get_bound': (C.c_int, [_P, _I, _P, _P, _P, _P, _P, _P]),
     'b2n_ns_reserve_dead': (C.c_int, [_P, _L]),
     'b2n_ns_get_live': (C.c_int, [_P, _P, _P, _P]),
     'b2n_ns_get_dead': (C.c_int, [_P, _L, _L, _P, _P, _P, _P, _P]),
@@ -128,7 +135,7 @@ _EXC = {
     ERR_ARG: ValueError, ERR_SINGLE_POINT: ValueError, ERR_SINGULAR: ValueError,
     ERR_ELL_INIT: RuntimeError, ERR_INVALID_REGION: RuntimeError, ERR_Q0: RuntimeError,
     ERR_SLICE_FAIL: RuntimeError, ERR_NOMEM: MemoryError, ERR_UNSUPPORTED: NotImplementedError,
-    ERR_TOO_MANY_ELLS: RuntimeError, ERR_PEER: RuntimeError,
+    ERR_TOO_MANY_ELLS: RuntimeError, ERR_PEER: RuntimeError, ERR_PLATEAU: RuntimeError,
 }
 
 

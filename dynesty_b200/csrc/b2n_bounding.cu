@@ -966,6 +966,120 @@ extern "C" int b2n_bounding_ellipsoid(b2n_ctx* ctx, const double* points, int64_
     return B2N_OK;
 }
 
+// improve_covar_mat (bounding.py:1311-1384) on a caller-supplied matrix: the repair ladder of the fit
+// kernels exposed on its own (the same eig_ladder_kernel / sliced solver, fed through `covraw`).
+extern "C" int b2n_improve_covar(b2n_ctx* ctx, const double* covar, int32_t n, double* cov_out, double* am,
+                                 double* axes, int32_t* good, uint32_t* warn) {
+    if (!ctx || !covar || n < 1) return B2N_ERR_ARG;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    BoundWork w;
+    B2N_TRY(b2n_boundwork_init(ctx, w, nullptr, 1, n, 1));
+    const size_t nn = (size_t)n * n;
+    cudaStream_t st = ctx->stream;
+    const cudaMemcpyKind in_kind = ctx->ptr_mode == B2N_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    B2N_CUDA(ctx, cudaMemcpyAsync(w.na.covraw, covar, nn * sizeof(double), in_kind, st));
+    B2N_CUDA(ctx, cudaMemsetAsync(w.na.stat, 0, sizeof(NodeStat), st));
+    const int zero = 0;
+    const void* dlist;
+    B2N_TRY(b2n_in_host(ctx, ctx->work0, &zero, sizeof(int), &dlist));
+    const int ld = w.na.ld, half = ((n + 1) & ~1) / 2;
+    const size_t small_b = (size_t)(2 * half + 2 * n + 32) * sizeof(double);
+    const size_t mats_b = (size_t)2 * n * ld * sizeof(double);
+    const int use_smem = small_b + mats_b <= (size_t)ctx->max_smem_optin ? 1 : 0;
+    NodeStat hs;
+    memset(&hs, 0, sizeof(hs));
+    int sliced = 0;
+    if (!use_smem) {
+        B2N_TRY(b2n_eig_sliced(w, (const int*)dlist, 1, 0, 0, &sliced));
+        for (int attempt = 1; sliced && attempt <= 100; attempt++) {        // one decomposition per launch
+            B2N_CUDA(ctx, cudaStreamSynchronize(st));
+            B2N_CUDA(ctx, cudaMemcpy(&hs, w.na.stat, sizeof(NodeStat), cudaMemcpyDeviceToHost));
+            if (!hs.retry) break;
+            int used = 0;
+            B2N_TRY(b2n_eig_sliced(w, (const int*)dlist, 1, 0, 1, &used));
+        }
+    }
+    if (!sliced) {
+        const size_t eig_smem = small_b + (use_smem ? mats_b : 0);
+        double* gwork = nullptr;
+        if (!use_smem) {
+            B2N_CUDA(ctx, ctx->scratch2.ensure(mats_b));
+            gwork = ctx->scratch2.as<double>();
+        }
+        B2N_CUDA(ctx, cudaFuncSetAttribute(eig_ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem));
+        eig_ladder_kernel<<<1, 32 * std::max(4, std::min(32, half)), eig_smem, st>>>(w.na, (const int*)dlist, 0, gwork, use_smem);
+        B2N_LAUNCH_CHECK(ctx);
+    }
+    B2N_CUDA(ctx, cudaStreamSynchronize(st));
+    B2N_CUDA(ctx, cudaMemcpy(&hs, w.na.stat, sizeof(NodeStat), cudaMemcpyDeviceToHost));
+    if (good) *good = hs.good;
+    if (warn) *warn = hs.fallback ? B2N_WARN_IDENTITY_FALLBACK : 0u;
+    B2N_TRY(emit_node(w, 0, 0, nullptr, cov_out, am, axes, nullptr));
+    B2N_CUDA(ctx, cudaStreamSynchronize(st));
+    return B2N_OK;
+}
+
+// ------------------------------------------------------------------ FP64 issue ceilings (bench.py roofline)
+// What the chain kernels are made of is FP64 FMA (vector pipe) and FP64 m8n8k4 MMA (tensor pipe, DMMA).  Both
+// ceilings are MEASURED here instead of quoted: every warp runs `iters` rounds of 16 independent dependency
+// chains (DFMA: 16 accumulators per thread; DMMA: 8 accumulator pairs per warp), 8 warps x 8 CTAs per SM.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int kind, int iters, double seed, double* __restrict__ out) {
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = seed * (double)(threadIdx.x + i + 1);
+    const double a = 1.0 + 1e-9 * seed, b = 1e-9 * (double)(threadIdx.x & 3);
+    if (kind == 0) {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) acc[i] = fma(acc[i], a, b);
+        }
+    } else {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(acc[i]), "+d"(acc[i + 1])
+                             : "d"(a), "d"(b));
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += acc[i];
+    if (s == 123456.789) out[blockIdx.x * blockDim.x + threadIdx.x] = s;     // keeps the chains alive
+}
+
+extern "C" int b2n_fp64_peak(b2n_ctx* ctx, int32_t kind, int32_t iters, double* tflops, double* ms_out) {
+    if (!ctx || (kind != 0 && kind != 1) || iters < 1 || !tflops) return B2N_ERR_ARG;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int ctas = ctx->sm_count * 8, threads = 256;
+    B2N_CUDA(ctx, ctx->scratch1.ensure((size_t)ctas * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    B2N_CUDA(ctx, cudaEventCreate(&e0));
+    B2N_CUDA(ctx, cudaEventCreate(&e1));
+    cudaStream_t st = ctx->stream;
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {          // rep 0 warms up; best of the rest
+        cudaEventRecord(e0, st);
+        fp64_peak_kernel<<<ctas, threads, 0, st>>>(kind, iters, 1.0 + rep, ctx->scratch1.as<double>());
+        cudaEventRecord(e1, st);
+        ctx->launches++;
+        B2N_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        B2N_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    B2N_CUDA(ctx, cudaGetLastError());
+    // flop count: DFMA = 2 flop per lane per instruction; DMMA m8n8k4 = 2*8*8*4 = 512 flop per warp instruction
+    const double per_thread_instr = (double)iters * (kind == 0 ? 16.0 : 8.0);
+    const double flops = kind == 0 ? per_thread_instr * 2.0 * (double)ctas * threads
+                                   : per_thread_instr * 512.0 * (double)ctas * (threads / 32);
+    *tflops = flops / ((double)best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = (double)best;
+    return B2N_OK;
+}
+
 // ------------------------------------------------------------------ scale_to_logvol
 // Ellipsoid.scale_to_logvol (bounding.py:242-276); one CTA per ellipsoid.
 __global__ void __launch_bounds__(1024) scale_to_logvol_kernel(int n, double* __restrict__ covs, double* __restrict__ ams,

@@ -115,6 +115,8 @@ __device__ __forceinline__ double loglike_sm(const B2nModel& m, const ModelSm& m
             pr *= cos(t * 0.5);
         }
         return pow(2.0 + warp_prod(pr), m.s1);
+    } else if (LIKE == B2N_LIKE_REGION2D) {
+        return region2d_logl(m.s0, b2n_sm[ov], b2n_sm[ov + 1]);
     } else {  // SHELLS
         double a = 0.0, b = 0.0;
         for (int i = lane; i < n; i += 32) {

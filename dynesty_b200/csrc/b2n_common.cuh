@@ -119,6 +119,8 @@ struct b2n_ctx {
     int wl_cpc = 0, wl_ncta = 0;
 };
 void b2n_ns_release(b2n_ctx* ctx);
+int b2n_bound_set_dev(b2n_ctx* ctx, int K, int nc, const double* dctrs, const double* dams, const double* daxes,
+                      const double* h_logvols);
 
 // gather-mode plumbing shared by the chain entry points (b2n_peer.cu).  b2n_peer_begin: when
 // gather mode is on, point the 7 output arrays at this rank's rows of its own window and fill

@@ -1,6 +1,7 @@
 // b2n_ctx.cu -- context lifetime, model registry, resident bound, batched model
 // evaluation.  Part of libb200nest.so (C ABI in include/b200nest.h).
 #include "b2n_device.cuh"
+#include <algorithm>
 
 extern "C" {
 
@@ -21,6 +22,7 @@ const char* b2n_strerror(int s) {
         case B2N_ERR_UNSUPPORTED: return "unsupported configuration";
         case B2N_ERR_TOO_MANY_ELLS: return "max_ells too small";
         case B2N_ERR_PEER: return "peer exchange failed";
+        case B2N_ERR_PLATEAU: return "No live points are above loglstar. Do you have a likelihood plateau ?";
         default: return "unknown status";
     }
 }
@@ -145,9 +147,10 @@ int b2n_model_create(b2n_ctx* ctx, const b2n_model_desc* d, int32_t* id) {
     m.like_kind = d->like_kind;
     m.s0 = d->like_s0; m.s1 = d->like_s1; m.s2 = d->like_s2;
     if (d->prior_kind < 0 || d->prior_kind > B2N_PRIOR_NORMAL_PPF) return B2N_ERR_ARG;
-    if (d->like_kind < 0 || d->like_kind > B2N_LIKE_SHELLS) return B2N_ERR_ARG;
+    if (d->like_kind < 0 || d->like_kind > B2N_LIKE_REGION2D) return B2N_ERR_ARG;
+    if (d->like_kind == B2N_LIKE_REGION2D && d->ndim < 2) return B2N_ERR_ARG;
     if (d->prior_kind != B2N_PRIOR_IDENTITY && (!d->prior_p0 || !d->prior_p1)) return B2N_ERR_ARG;
-    if (d->like_kind != B2N_LIKE_EGGBOX && !d->like_vec0) return B2N_ERR_ARG;
+    if (d->like_kind != B2N_LIKE_EGGBOX && d->like_kind != B2N_LIKE_REGION2D && !d->like_vec0) return B2N_ERR_ARG;
     if ((d->like_kind == B2N_LIKE_GAUSS_DIAG || d->like_kind == B2N_LIKE_SHELLS) && !d->like_vec1)
         return B2N_ERR_ARG;
     if (d->like_kind == B2N_LIKE_GAUSS_PREC && !d->like_mat) return B2N_ERR_ARG;
@@ -192,6 +195,42 @@ int b2n_bound_set(b2n_ctx* ctx, int32_t K, int32_t nc, const double* ctrs, const
     ctx->bn = nc;
     return B2N_OK;
 }
+
+}  // extern "C"
+
+// axes (K x nc x nc, row-major) -> axesT[k][j*nc+i] = axes[k][i][j], on the device
+__global__ void transpose_axes_kernel(const double* __restrict__ axes, double* __restrict__ axesT, int K, int nc) {
+    const size_t mat = (size_t)nc * nc, tot = mat * K;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t k = e / mat, r = e - k * mat;
+        const int j = (int)(r / nc), i = (int)(r - (size_t)j * nc);
+        axesT[e] = axes[k * mat + (size_t)i * nc + j];
+    }
+}
+
+// b2n_bound_set for arrays that already live on the device (b2n_ns_update_bound): no host staging.
+// logvols: HOST copy (K), needed for the volume-weighted ellipsoid pick of the uniform sampler.
+int b2n_bound_set_dev(b2n_ctx* ctx, int K, int nc, const double* dctrs, const double* dams, const double* daxes,
+                      const double* h_logvols) {
+    const size_t mat = (size_t)nc * nc;
+    B2N_CUDA(ctx, ctx->b_axesT.ensure(mat * K * sizeof(double)));
+    B2N_CUDA(ctx, ctx->b_ctrs.ensure((size_t)K * nc * sizeof(double)));
+    B2N_CUDA(ctx, ctx->b_ams.ensure(mat * K * sizeof(double)));
+    B2N_CUDA(ctx, ctx->b_logvols.ensure((size_t)K * sizeof(double)));
+    cudaStream_t st = ctx->stream;       // stream order: kernels enqueued before still see the previous bound
+    transpose_axes_kernel<<<(unsigned)std::min<size_t>((mat * K + 255) / 256, 1024), 256, 0, st>>>(daxes, ctx->b_axesT.as<double>(), K, nc);
+    B2N_LAUNCH_CHECK(ctx);
+    B2N_CUDA(ctx, cudaMemcpyAsync(ctx->b_ctrs.p, dctrs, (size_t)K * nc * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    B2N_CUDA(ctx, cudaMemcpyAsync(ctx->b_ams.p, dams, mat * K * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    ctx->h_logvols.assign(h_logvols, h_logvols + K);
+    B2N_CUDA(ctx, cudaMemcpyAsync(ctx->b_logvols.p, ctx->h_logvols.data(), (size_t)K * sizeof(double), cudaMemcpyHostToDevice, st));
+    ctx->bK = K;
+    ctx->bn = nc;
+    return B2N_OK;
+}
+
+extern "C" {
+
 
 }  // extern "C"
 

@@ -83,6 +83,20 @@ __device__ __forceinline__ double prior_1d(const B2nModel& m, int i, double u) {
     }
 }
 
+// the 2-D constraint regions of the reference's uniformity harness (tests/test_sampling.py:8-23)
+__device__ __forceinline__ double region2d_logl(double shape, double x, double y) {
+    const double ninf = __longlong_as_double(0xfff0000000000000LL);
+    if (shape == 0.0) {                                   // diamond_logl
+        const double x1 = fabs(x - 0.5), y1 = fabs(y - 0.5);
+        if (fmin(x, y) < 0.0 || fmax(x, y) > 1.0) return ninf;
+        const double D2 = (x1 - 0.5) * (x1 - 0.5) + (y1 - 0.5) * (y1 - 0.5);
+        return D2 > 0.25 ? D2 - 0.25 : ninf;
+    }
+    const double mult = 16.0 * 2.0 * 3.14159265358979323846;         // checker_logl
+    if (!(x >= 0.0 && x <= 1.0 && y >= 0.0 && y < 1.0)) return ninf;
+    return sin(x * mult) * sin(y * mult);
+}
+
 // ---- log-likelihood, evaluated cooperatively by one warp ---------------------------
 // v: warp-private shared vector (n).  work: warp-private shared scratch (n).
 // lmat: pointer to the n x n matrix for GAUSS_PREC (shared or global).
@@ -119,6 +133,8 @@ __device__ __forceinline__ double warp_loglike(const B2nModel& m, const double* 
         }
         p = warp_prod(p);
         return pow(2.0 + p, m.s1);
+    } else if (LIKE == B2N_LIKE_REGION2D) {
+        return region2d_logl(m.s0, v[0], v[1]);
     } else {  // SHELLS
         double a = 0.0, b = 0.0;
         for (int i = lane; i < n; i += 32) {
@@ -143,6 +159,7 @@ __device__ __forceinline__ double warp_loglike(const B2nModel& m, const double* 
         case B2N_LIKE_GAUSS_PREC: { CALL(B2N_LIKE_GAUSS_PREC); } break; \
         case B2N_LIKE_GAUSS_DIAG: { CALL(B2N_LIKE_GAUSS_DIAG); } break; \
         case B2N_LIKE_EGGBOX: { CALL(B2N_LIKE_EGGBOX); } break;         \
+        case B2N_LIKE_REGION2D: { CALL(B2N_LIKE_REGION2D); } break;     \
         default: { CALL(B2N_LIKE_SHELLS); } break;                      \
     }
 

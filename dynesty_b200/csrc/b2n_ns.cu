@@ -43,12 +43,14 @@ struct NsScalars {
     long long hist_a, hist_b;
     int done, need_bound, doubling, error;
     int parity, pad0;          // which of the two (key, row) buffer pairs holds the current sorted order
+    int phase, pending;        // phase 0: unit-cube rounds (no bound yet), 1: bounded rounds.  pending: a round
+                               // has been proposed (its chains are in flight) and waits for its commit
 };
 
 struct NsDev {
     int N, n, nc, K, Kell, cpc, strict, sampler, Npad, Kpad, threads;
-    double dlogz, facc;
-    long long maxiter, maxcall, update_interval, dead_cap;
+    double dlogz, facc, first_min_eff, logl_max;
+    long long maxiter, maxcall, update_interval, dead_cap, first_min_ncall, it0;
     unsigned long long seed, chain0;
     double *live_u, *live_v, *live_logl;
     double *dead_u, *dead_v, *dead_logl, *dead_logvol;
@@ -76,6 +78,12 @@ struct b2n_ns {
     long long dead_cap = 0;
     std::vector<void*> allocs;
     void* dead_alloc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int phase = 1;                     // host copy of NsScalars::phase (transitions are host-mediated)
+    // device copy of the bound built by b2n_ns_update_bound (Kmax ellipsoids of dimension nc)
+    int Kmax = 0, bK = 0;
+    double *bd_ctrs = nullptr, *bd_covs = nullptr, *bd_ams = nullptr, *bd_axes = nullptr, *bd_axlens = nullptr,
+           *bd_logvols = nullptr, *bd_points = nullptr;
+    std::vector<double> bd_hlogvols;
 };
 
 __device__ __forceinline__ double dev_logaddexp(double a, double b) {
@@ -114,8 +122,9 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_sort_kernel(const NsDev 
     for (int i = tid; i < N; i += nth) { s.sidx[i] = idx[i]; s.skey[i] = key[i]; }
 }
 
-__global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsDev s) {
-    extern __shared__ __align__(16) unsigned char ns_smem[];
+extern __shared__ __align__(16) unsigned char ns_smem[];
+
+__device__ __forceinline__ void ns_propose_body(const NsDev& s) {
     const int tid = threadIdx.x, nth = blockDim.x, warp = tid >> 5, lane = tid & 31;
     NsScalars* sc = s.sc;
     if (sc->done || sc->need_bound) {
@@ -131,8 +140,8 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsD
     const int par = sc->parity;                              // current sorted order: ascending by (logl, row)
     const double* key = par ? s.tkey : s.skey;
     const int* idx = par ? s.tidx : s.sidx;
-    __shared__ int s_flag, s_bad;
-    if (tid == 0) { s_flag = 0; s_bad = 0; }
+    __shared__ int s_flag, s_bad, s_first;
+    if (tid == 0) { s_flag = 0; s_bad = 0; s_first = K; }
     __syncthreads();
     // ---- termination (sampler.py:1095-1120) and capacity
     if (tid == 0) {
@@ -140,18 +149,36 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsD
         const double delta = dev_logaddexp(0.0, lmax + sc->logvol - sc->logz);
         sc->lmax = lmax;
         sc->delta_logz = delta;
-        if (delta < s.dlogz || sc->it >= s.maxiter || sc->ncall >= s.maxcall || key[0] == lmax) {
+        // (maxiter is tested per round: a run may overshoot it by up to batch - 1 iterations.  logl_max: the stop
+        //  of a dynamic-sampler batch, dynamicsampler.py:1338-1345 -- the worst live point has left the range)
+        if (delta < s.dlogz || sc->it >= s.maxiter || sc->ncall >= s.maxcall || key[0] == lmax || key[0] > s.logl_max) {
             sc->done = 1;
             s_flag = 1;
         } else if (sc->it + K > s.dead_cap) {
             sc->need_bound = 3;                             // dead buffer full: the host grows it
             s_flag = 1;
+        } else {
+            // start rows must have logl STRICTLY above the threshold key[K-1] (sampler.py:471: live_logl > loglstar):
+            // with ties at the threshold (plateau likelihoods, a stuck chain duplicating its start) the sorted
+            // suffix begins later than K.  Binary search for the first key > threshold.
+            const double thr = key[K - 1];
+            int lo = K, hi = N;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (key[mid] > thr) hi = mid; else lo = mid + 1;
+            }
+            s_first = lo;
+            if (lo >= N) {                                   // no live point above the threshold: plateau
+                sc->done = 1;
+                sc->error = B2N_ERR_PLATEAU;
+                s_flag = 1;
+            }
         }
         if (s_flag) s.dyn->skip = 1;
     }
     __syncthreads();
     if (s_flag) return;
-    if (s.sampler == 3) {        // uniform sampler: the chains draw from the bound themselves -- no start rows
+    if (s.sampler == 3 || sc->phase == 0) {   // uniform / unit-cube sampler: the chains draw themselves -- no start rows
         if (tid == 0) {
             B2nDyn* dy = s.dyn;
             dy->loglstar = key[K - 1];
@@ -160,6 +187,7 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsD
             dy->ncta = 0;
             dy->doubling = 0;
             dy->skip = 0;
+            sc->pending = 1;
         }
         return;
     }
@@ -176,13 +204,13 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsD
         for (int k = 0; k < s.Kell; k++) { c += exp(s.logvols[k] - lv); cum[k] = c; }
     }
     __syncthreads();
-    const int nsurv = N - K;
+    const int first = s_first, nsurv = N - first;
     for (int c = tid; c < K; c += nth) {
         g.tick = 0;
         const double U = rng_uniform_elem(g, c);
         int sidx = (int)(U * (double)nsurv);
         sidx = sidx < nsurv - 1 ? sidx : nsurv - 1;
-        start[c] = idx[K + sidx];
+        start[c] = idx[first + sidx];
         int e = 0;
         if (s.Kell > 1) {
             g.tick = 1;
@@ -260,6 +288,7 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_propose_kernel(const NsD
         dy->doubling = sc->doubling;
         dy->skip = s_bad ? 1 : 0;
         if (s_bad) sc->need_bound = 2;                       // forced update (sampler.py:486)
+        else sc->pending = 1;
     }
 }
 
@@ -299,8 +328,8 @@ __device__ __forceinline__ long long block_reduce_sum_ll(long long v, long long*
     return r;
 }
 
-__global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDev s) {
-    if (s.dyn->skip) return;
+__device__ __forceinline__ void ns_commit_body(const NsDev& s) {
+    if (!s.sc->pending) return;
     __shared__ double rbuf[64];
     __shared__ unsigned int s_or;
     long long* lbuf = reinterpret_cast<long long*>(rbuf);
@@ -343,7 +372,7 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
         ncall += s.o_ncall[j];
         ha += s.o_i0[j];
         hb += s.o_i1[j];
-        if (s.sampler != 0) fl |= s.o_flags[j];           // rwalk writes no flags
+        if (s.sampler != 0 || s.sc->phase == 0) fl |= s.o_flags[j];   // rwalk writes no flags; unit-cube chains do
     }
     const double m = block_reduce_max(wmax, rbuf);
     double se = 0.0;
@@ -362,7 +391,6 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
     //      into the N-K survivors (already sorted).  Comparator = (logl, row) lexicographic, a strict
     //      total order, hence position = own rank + number of elements of the OTHER list below.
     {
-        extern __shared__ __align__(16) unsigned char ns_smem[];
         const int NA = N - K, Kpad = s.Kpad;
         double* akey = reinterpret_cast<double*>(ns_smem);       // NA survivors
         double* bkey = akey + NA + (NA & 1);                      // Kpad new
@@ -424,10 +452,13 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
         sc->it = it0 + K;
         sc->ncall += ncall;
         sc->round += 1;
+        sc->pending = 0;
         // ---- tune (update=True every round: the queue of the round has drained, sampler.py:757-768)
         sc->hist_a = ha;
         sc->hist_b = hb;
-        if (s.sampler == 3) {                                // UniformBoundSampler: nothing to tune
+        if (sc->phase == 0) {                                // UnitCubeSampler: nothing to tune
+            if (s_or & 0x80000000u) { sc->error = B2N_ERR_UNSUPPORTED; sc->done = 1; }   // draw limit
+        } else if (s.sampler == 3) {                                // UniformBoundSampler: nothing to tune
             if (s_or & 0x40000000u) { sc->error = B2N_ERR_Q0; sc->done = 1; }            // bounding.py:570-574
             if (s_or & 0x80000000u) { sc->error = B2N_ERR_UNSUPPORTED; sc->done = 1; }   // draw limit
         } else if (s.sampler == 0) {                         // internal_samplers.py:460-493
@@ -439,14 +470,35 @@ __global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_commit_kernel(const NsDe
             sc->scale *= fmin(fmax(ne * 2.0 / (ne + ncn), 0.5), 2.0);
             if (s_or & 0x80000000u) { sc->error = B2N_ERR_SLICE_FAIL; sc->done = 1; }
         }
-        // ---- bound update due (sampler.py:648-651)
-        if (sc->ncall >= sc->ncall_last_update + s.update_interval) sc->need_bound = 1;
+        // ---- bound update due (sampler.py:648-651); first bound: enough calls AND efficiency below the
+        //      threshold (sampler.py:407-409, 640-647)
+        if (sc->phase == 0) {
+            const double eff = 100.0 * (double)(s.it0 + sc->it) / (double)sc->ncall;
+            if (sc->ncall >= s.first_min_ncall && eff < s.first_min_eff) sc->need_bound = 4;
+        } else if (sc->ncall >= sc->ncall_last_update + s.update_interval) sc->need_bound = 1;
+    }
+}
+
+// One launch between two chain launches: commit of the round whose chains have just finished, then the proposal
+// of the next round (mode bit 0: commit, bit 1: propose).  R rounds = R + 1 of these instead of 2 R launches.
+__global__ void __launch_bounds__(B2N_NS_THREADS, 1) ns_step_kernel(const NsDev s, int mode) {
+    if (mode & 1) ns_commit_body(s);
+    if (mode == 3) __syncthreads();       // the commit's global writes (live set, sorted order, scalars) are read below
+    if (mode & 2) ns_propose_body(s);
+}
+
+// first nc columns of an (N, n) row-major block -> contiguous (N, nc)
+__global__ void gather_cols_kernel(const double* __restrict__ src, int N, int n, int nc, double* __restrict__ dst) {
+    const size_t tot = (size_t)N * nc;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = e / nc, c = e - r * nc;
+        dst[e] = src[r * n + c];
     }
 }
 
 __global__ void ns_clear_kernel(NsScalars* sc, B2nDyn* dyn, int bound_updated) {
     sc->need_bound = 0;
-    if (bound_updated) sc->ncall_last_update = sc->ncall;
+    if (bound_updated) { sc->ncall_last_update = sc->ncall; sc->phase = 1; }     // a bound exists from now on
     dyn->skip = 0;
 }
 
@@ -506,7 +558,10 @@ static int ns_chain_call(b2n_ctx* ctx, b2n_ns* ns, bool plan_only) {
     ctx->dyn.dev = d.dyn; ctx->dyn.order = d.order; ctx->dyn.cta = d.cta;
     ctx->dyn.max_cta = d.cpc > 0 ? d.K / d.cpc + d.Kell : 1;
     int st;
-    if (d.sampler == 3) {
+    if (ns->phase == 0) {
+        if (plan_only) { ctx->dyn.cpc = 1; st = B2N_OK; }
+        else st = b2n_unitcube_batch(ctx, &a, d.o_u, d.o_v, d.o_logl, d.o_ncall, d.o_flags);
+    } else if (d.sampler == 3) {
         if (plan_only) { ctx->dyn.cpc = 1; st = B2N_OK; }
         else st = b2n_unif_batch(ctx, &a, d.o_u, d.o_v, d.o_logl, d.o_ncall, d.o_i0, d.o_flags);
     } else if (d.sampler == 0)
@@ -560,6 +615,9 @@ int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* c, int64_t dead_capacity) {
     if (const char* e = getenv("B2N_NS_THREADS")) d.threads = atoi(e) >= 1024 ? 1024 : (atoi(e) >= 512 ? 512 : 256);
     d.dlogz = c->dlogz; d.facc = c->facc; d.maxiter = c->maxiter; d.maxcall = c->maxcall;
     d.update_interval = c->update_interval; d.seed = c->seed; d.chain0 = c->chain0;
+    d.first_min_ncall = c->first_min_ncall; d.first_min_eff = c->first_min_eff; d.it0 = c->it0;
+    d.logl_max = c->use_logl_max ? c->logl_max : (double)INFINITY;
+    ns->phase = c->unit_cube_phase ? 0 : 1;
     const size_t N = d.N, K = d.K;
     B2N_TRY(ns_alloc(ctx, ns, (void**)&d.live_u, N * n * 8));
     B2N_TRY(ns_alloc(ctx, ns, (void**)&d.live_v, N * n * 8));
@@ -580,7 +638,21 @@ int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* c, int64_t dead_capacity) {
     B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_i1, K * 4));
     B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_ncall, K * 4));
     B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_flags, K * 4));
+    B2N_CUDA(ctx, cudaMemset(d.o_i0, 0, K * 4));          // (the unit-cube sampler writes no counters)
     B2N_CUDA(ctx, cudaMemset(d.o_i1, 0, K * 4));          // (the uniform sampler writes no second counter)
+    B2N_CUDA(ctx, cudaMemset(d.o_flags, 0, K * 4));
+    {   // device copy of the bound b2n_ns_update_bound builds (bounding.py:1493: a leaf has >= 2 ncdim points)
+        const size_t nc = d.nc, nn = nc * nc;
+        ns->Kmax = (int)std::max<size_t>(1, N / std::max<size_t>(2 * nc, 1));
+        const size_t Km = ns->Kmax;
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&ns->bd_ctrs, Km * nc * 8));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&ns->bd_covs, Km * nn * 8));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&ns->bd_ams, Km * nn * 8));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&ns->bd_axes, Km * nn * 8));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&ns->bd_axlens, Km * nc * 8));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&ns->bd_logvols, Km * 8));
+        if (nc != (size_t)n) B2N_TRY(ns_alloc(ctx, ns, (void**)&ns->bd_points, N * nc * 8));
+    }
     B2N_CUDA(ctx, cudaMemset(d.sc, 0, sizeof(NsScalars)));
     B2N_CUDA(ctx, cudaMemset(d.dyn, 0, sizeof(B2nDyn)));
     B2N_TRY(ns_alloc_dead(ctx, ns, std::max<int64_t>(dead_capacity, (int64_t)K)));
@@ -613,6 +685,7 @@ int b2n_ns_set_state(b2n_ctx* ctx, const double* live_u, const double* live_v, c
     h.ncall = ncall; h.ncall_last_update = ncall;
     h.logvol = logvol; h.logz = logz; h.loglstar = loglstar; h.scale = scale;
     h.lmax = -1e300; h.delta_logz = 1e300;
+    h.phase = ns->phase;
     B2N_CUDA(ctx, cudaMemcpy(d.sc, &h, sizeof(h), cudaMemcpyHostToDevice));
     B2N_CUDA(ctx, cudaMemset(d.dyn, 0, sizeof(B2nDyn)));
     const size_t smem = ns_sort_smem(d);
@@ -648,35 +721,40 @@ int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_sta
     b2n_ns* ns = ctx->ns;
     NsDev& d = ns->d;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (ctx->bK < 1 || ctx->bn != d.nc) return b2n_fail(ctx, B2N_ERR_ARG, "resident bound missing or of wrong dimension (b2n_bound_set)");
-    if (!ctx->b_ctrs.p || !ctx->b_ams.p || !ctx->b_logvols.p || ctx->h_logvols.empty())
-        return b2n_fail(ctx, B2N_ERR_ARG, "b2n_ns_run needs the full resident bound (ctrs, ams, logvols)");
     if (ctx->peer.total > 0) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "b2n_ns_run: gather mode must be off");
-    d.Kell = ctx->bK;
+    if (ns->phase == 0) {            // unit-cube rounds: no bound yet
+        d.Kell = 1;
+        d.ctrs = d.ams = d.logvols = nullptr;
+    } else {
+        if (ctx->bK < 1 || ctx->bn != d.nc) return b2n_fail(ctx, B2N_ERR_ARG, "resident bound missing or of wrong dimension (b2n_bound_set)");
+        if (!ctx->b_ctrs.p || !ctx->b_ams.p || !ctx->b_logvols.p || ctx->h_logvols.empty())
+            return b2n_fail(ctx, B2N_ERR_ARG, "b2n_ns_run needs the full resident bound (ctrs, ams, logvols)");
+        d.Kell = ctx->bK;
+        d.ctrs = ctx->b_ctrs.as<double>(); d.ams = ctx->b_ams.as<double>(); d.logvols = ctx->b_logvols.as<double>();
+    }
     d.strict = ns->cfg.strict_contains;
-    d.ctrs = ctx->b_ctrs.as<double>(); d.ams = ctx->b_ams.as<double>(); d.logvols = ctx->b_logvols.as<double>();
     if ((size_t)d.K / 1 + (size_t)d.Kell + 8 > (size_t)d.K + (size_t)d.N + 8)
         return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "too many ellipsoids for the round worklist");
     B2N_TRY(ns_chain_call(ctx, ns, true));               // chains per CTA the chain kernel plans for
     d.cpc = ctx->dyn.cpc;
-    const size_t smem = ns_propose_smem(d), csmem = ns_commit_smem(d);
-    if (smem > (size_t)ctx->max_smem_optin || csmem + 1024 > (size_t)ctx->max_smem_optin)
+    const size_t smem = std::max(ns_propose_smem(d), ns_commit_smem(d));
+    if (smem + 2048 > (size_t)ctx->max_smem_optin)
         return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "nlive / batch too large for the one-CTA kernels of b2n_ns_run");
-    B2N_CUDA(ctx, cudaFuncSetAttribute(ns_propose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2N_CUDA(ctx, cudaFuncSetAttribute(ns_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+    B2N_CUDA(ctx, cudaFuncSetAttribute(ns_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (check_every < 1) check_every = max_rounds > 0 ? max_rounds : 1;
     int left = max_rounds;
     b2n_ns_status st;
     memset(&st, 0, sizeof(st));
     while (left > 0) {
         const int chunk = std::min(left, (int)check_every);
+        // propose | chains | commit + propose | chains | ... | commit : chunk + 1 single-CTA launches
         for (int r = 0; r < chunk; r++) {
-            ns_propose_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d);
+            ns_step_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d, r == 0 ? 2 : 3);
             B2N_LAUNCH_CHECK(ctx);
             B2N_TRY(ns_chain_call(ctx, ns, false));
-            ns_commit_kernel<<<1, d.threads, csmem, ctx->stream>>>(d);
-            B2N_LAUNCH_CHECK(ctx);
         }
+        ns_step_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d, 1);
+        B2N_LAUNCH_CHECK(ctx);
         left -= chunk;
         B2N_TRY(ns_status(ctx, &st));
         if (st.done || st.need_bound) break;
@@ -706,6 +784,79 @@ int b2n_ns_bound_updated(b2n_ctx* ctx) {
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
     ns_clear_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ns->d.sc, ctx->ns->d.dyn, 1);
     B2N_LAUNCH_CHECK(ctx);
+    ctx->ns->phase = 1;              // the unit-cube phase ends with the first bound (sampler.py:640-647)
+    return B2N_OK;
+}
+
+int b2n_ns_update_bound(b2n_ctx* ctx, int32_t multi, double enlarge, int32_t* nells, double* logvol, uint32_t* warn) {
+    if (!ctx || !ctx->ns || !(enlarge > 0.0)) return B2N_ERR_ARG;
+    b2n_ns* ns = ctx->ns;
+    NsDev& d = ns->d;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n = d.n, nc = d.nc, N = d.N;
+    const double* pts = d.live_u;
+    if (nc != n) {                  // the bound lives in the first ncdim coordinates (sampler.py:497)
+        gather_cols_kernel<<<(unsigned)std::min<size_t>(((size_t)N * nc + 255) / 256, 1024), 256, 0, ctx->stream>>>(
+            d.live_u, N, n, nc, ns->bd_points);
+        B2N_LAUNCH_CHECK(ctx);
+        pts = ns->bd_points;
+    }
+    const int mode = ctx->ptr_mode;
+    ctx->ptr_mode = B2N_PTR_DEVICE;          // points and outputs are device arrays of this run
+    int32_t K = 1;
+    uint32_t w = 0;
+    int st;
+    if (multi)
+        st = b2n_multi_decompose(ctx, pts, N, nc, ns->Kmax, &K, nullptr, ns->bd_ctrs, ns->bd_covs, ns->bd_ams, ns->bd_axes,
+                                 ns->bd_axlens, ns->bd_logvols, &w);
+    else
+        st = b2n_bounding_ellipsoid(ctx, pts, N, nc, ns->bd_ctrs, ns->bd_covs, ns->bd_ams, ns->bd_axes, ns->bd_axlens,
+                                    ns->bd_logvols, &w);
+    ctx->ptr_mode = mode;
+    if (st != B2N_OK) return st;
+    std::vector<double> lv(K);
+    B2N_CUDA(ctx, cudaMemcpyAsync(lv.data(), ns->bd_logvols, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (enlarge != 1.0) {
+        // sampler.py:506-508 -> scalar branch of MultiEllipsoid.scale_to_logvol (bounding.py:487-489): every
+        // ellipsoid is shifted by the same ln(enlarge)
+        std::vector<double> tg(K);
+        for (int k = 0; k < K; k++) tg[k] = lv[k] + log(enlarge);
+        ctx->ptr_mode = B2N_PTR_DEVICE;
+        st = b2n_scale_to_logvol(ctx, K, nc, ns->bd_covs, ns->bd_ams, ns->bd_axes, ns->bd_axlens, ns->bd_logvols, tg.data());
+        ctx->ptr_mode = mode;
+        if (st != B2N_OK) return st;
+        B2N_CUDA(ctx, cudaMemcpyAsync(lv.data(), ns->bd_logvols, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    B2N_TRY(b2n_bound_set_dev(ctx, K, nc, ns->bd_ctrs, ns->bd_ams, ns->bd_axes, lv.data()));
+    ns->bK = K;
+    ns->bd_hlogvols = lv;
+    if (nells) *nells = K;
+    if (logvol) {
+        double hi = -INFINITY, se = 0.0;
+        for (double x : lv) hi = std::max(hi, x);
+        for (double x : lv) se += exp(x - hi);
+        *logvol = hi + log(se);
+    }
+    if (warn) *warn = w;
+    return B2N_OK;
+}
+
+int b2n_ns_get_bound(b2n_ctx* ctx, int32_t max_ells, double* ctrs, double* covs, double* ams, double* axes,
+                     double* axlens, double* logvols) {
+    if (!ctx || !ctx->ns) return B2N_ERR_ARG;
+    b2n_ns* ns = ctx->ns;
+    if (ns->bK < 1 || max_ells < ns->bK) return b2n_fail(ctx, B2N_ERR_ARG, "b2n_ns_get_bound: no device-built bound / max_ells too small");
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t K = ns->bK, nc = ns->d.nc, nn = nc * nc;
+    if (ctrs) B2N_CUDA(ctx, cudaMemcpy(ctrs, ns->bd_ctrs, K * nc * 8, cudaMemcpyDeviceToHost));
+    if (covs) B2N_CUDA(ctx, cudaMemcpy(covs, ns->bd_covs, K * nn * 8, cudaMemcpyDeviceToHost));
+    if (ams) B2N_CUDA(ctx, cudaMemcpy(ams, ns->bd_ams, K * nn * 8, cudaMemcpyDeviceToHost));
+    if (axes) B2N_CUDA(ctx, cudaMemcpy(axes, ns->bd_axes, K * nn * 8, cudaMemcpyDeviceToHost));
+    if (axlens) B2N_CUDA(ctx, cudaMemcpy(axlens, ns->bd_axlens, K * nc * 8, cudaMemcpyDeviceToHost));
+    if (logvols) memcpy(logvols, ns->bd_hlogvols.data(), K * 8);
     return B2N_OK;
 }
 

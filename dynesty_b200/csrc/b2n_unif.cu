@@ -145,6 +145,71 @@ __global__ void __launch_bounds__(256) unif_kernel(const UnifParams p) {
     peer_finish(p.peer);
 }
 
+// ---- UnitCubeSampler.sample (internal_samplers.py:343-441) for a queue of chains: draw u ~ U(0,1)^n (one
+// uniform vector event per draw), v = prior_transform(u), until loglikelihood(v) > loglstar.  This is what the
+// reference runs before the first bound exists (sampler.py:407-409, 625-674).  One warp per chain.
+struct CubeParams {
+    B2nModel m;
+    int n;
+    double loglstar;
+    uint64_t seed, chain0;
+    int64_t Q;
+    double *u, *v, *logl;
+    int* ncall;
+    uint32_t* flags;
+    PeerSet peer;
+    const B2nDyn* dyn;
+};
+
+template <int LIKE>
+__global__ void __launch_bounds__(128) unitcube_kernel(const CubeParams p) {
+    extern __shared__ double sm[];
+    const int n = p.n;
+    double loglstar_ = p.loglstar;
+    unsigned long long chain0_ = p.chain0;
+    if (p.dyn) {
+        if (p.dyn->skip) return;
+        loglstar_ = p.dyn->loglstar; chain0_ = p.dyn->chain0;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    double* uu = sm + (size_t)warp * 3 * n;
+    double* vv = uu + n;
+    double* work = vv + n;
+    for (int64_t q = (int64_t)blockIdx.x * wpb + warp; q < p.Q; q += (int64_t)gridDim.x * wpb) {
+        ChainRng g;
+        g.init(p.seed, chain0_ + (uint64_t)q);
+        int ncall = 0;
+        uint32_t fl = 0;
+        double lcur = 0.0;
+        for (;;) {
+            if (ncall >= B2N_UNIF_MAX_DRAWS) { fl |= 0x80000000u; break; }
+            for (int e = lane; e < n; e += 32) {
+                const double t = rng_uniform_elem(g, e);
+                uu[e] = t;
+                vv[e] = prior_1d(p.m, e, t);
+            }
+            g.tick++;
+            __syncwarp();
+            lcur = warp_loglike<LIKE>(p.m, p.m.lmat, vv, work, lane);
+            ncall++;
+            if (lcur > loglstar_) break;
+            __syncwarp();
+        }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            peer_put(p.peer, &p.u[q * n + i], uu[i]);
+            peer_put(p.peer, &p.v[q * n + i], vv[i]);
+        }
+        if (lane == 0) {
+            peer_put(p.peer, &p.logl[q], lcur);
+            peer_put(p.peer, &p.ncall[q], ncall);
+            if (p.flags) peer_put(p.peer, &p.flags[q], fl);
+        }
+        __syncwarp();
+    }
+    peer_finish(p.peer);
+}
+
 __global__ void unif_error_kernel(const uint32_t* flags, int64_t Q, int* out) {
     int bad = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Q; i += (int64_t)gridDim.x * blockDim.x) {
@@ -260,5 +325,85 @@ extern "C" int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, 
     B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (*herr & 1) return B2N_ERR_Q0;
     if (*herr & 2) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "uniform sampling did not find a point (bound draw limit)");
+    return B2N_OK;
+}
+
+
+extern "C" int b2n_unitcube_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, double* v, double* logl,
+                                  int32_t* ncall, uint32_t* flags) {
+    if (!ctx || !a) return B2N_ERR_ARG;
+    const bool gather = ctx->peer.total > 0;
+    if (!gather && (!u || !v || !logl || !ncall)) return B2N_ERR_ARG;
+    if (a->model_id < 0 || a->model_id >= (int)ctx->models.size()) return B2N_ERR_ARG;
+    const B2nModel m = ctx->models[a->model_id];
+    const int n = a->ndim;
+    const int64_t Q = a->nchain;
+    if (n != m.ndim || Q < 0) return B2N_ERR_ARG;
+    if (Q == 0) return gather ? b2n_fail(ctx, B2N_ERR_ARG, "gather mode: every rank must run at least one chain") : B2N_OK;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZcScope zc(ctx);
+    const bool dyn = ctx->dyn.active;
+    if (dyn) {
+        ctx->dyn.cpc = 1;
+        if (ctx->dyn.plan_only) return B2N_OK;
+        if (gather || ctx->ptr_mode != B2N_PTR_DEVICE) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "device-paced launch needs device pointers and no gather mode");
+    }
+    CubeParams p;
+    p.dyn = dyn ? ctx->dyn.dev : nullptr;
+    p.m = m; p.n = n; p.Q = Q; p.loglstar = a->loglstar; p.seed = a->seed; p.chain0 = a->chain0;
+    void *du, *dv, *dl, *dnc, *dfl = nullptr;
+    void* gdev[7];
+    bool peer_on = false;
+    B2N_TRY(b2n_peer_begin(ctx, n, &p.peer, gdev, &peer_on));
+    if (peer_on) {
+        if (ctx->peer.row0 + Q > ctx->peer.total) return b2n_fail(ctx, B2N_ERR_ARG, "gather rows out of range (b2n_peer_rows)");
+        du = gdev[0]; dv = gdev[1]; dl = gdev[2]; dnc = gdev[3]; dfl = gdev[6];
+    } else {
+        B2N_TRY(b2n_out(ctx, ctx->out0, u, (size_t)Q * n * sizeof(double), &du));
+        B2N_TRY(b2n_out(ctx, ctx->out1, v, (size_t)Q * n * sizeof(double), &dv));
+        B2N_TRY(b2n_out(ctx, ctx->out2, logl, (size_t)Q * sizeof(double), &dl));
+        B2N_TRY(b2n_out(ctx, ctx->out3, ncall, (size_t)Q * sizeof(int), &dnc));
+        if (dyn) dfl = flags;
+        else { B2N_CUDA(ctx, ctx->out6.ensure((size_t)Q * sizeof(uint32_t))); dfl = ctx->out6.p; }
+    }
+    p.u = (double*)du; p.v = (double*)dv; p.logl = (double*)dl; p.ncall = (int*)dnc; p.flags = (uint32_t*)dfl;
+    const int threads = 128, wpb = threads / 32;
+    const size_t smem = (size_t)wpb * 3 * n * sizeof(double);
+    if (smem > (size_t)ctx->max_smem_optin) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for the unit-cube kernel");
+    const int64_t blocks = (Q + wpb - 1) / wpb;
+#define CALL(L)                                                                                             \
+    if (smem > 48 * 1024)                                                                                   \
+        B2N_CUDA(ctx, cudaFuncSetAttribute(unitcube_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    unitcube_kernel<L><<<(unsigned)blocks, threads, smem, ctx->stream>>>(p);
+    B2N_TIME_BEGIN(ctx);
+    B2N_DISPATCH_LIKE(m.like_kind, CALL)
+    B2N_TIME_END(ctx);
+#undef CALL
+    B2N_LAUNCH_CHECK(ctx);
+    if (dyn) return B2N_OK;
+    int* herr = reinterpret_cast<int*>(ctx->pinned);
+    *herr = 0;
+    B2N_CUDA(ctx, ctx->out7.ensure(64));
+    B2N_CUDA(ctx, cudaMemsetAsync(ctx->out7.p, 0, sizeof(int), ctx->stream));
+    const uint32_t* eflags = peer_on ? (const uint32_t*)(ctx->peer.win + ctx->peer.off[6]) : (const uint32_t*)dfl;
+    unif_error_kernel<<<64, 256, 0, ctx->stream>>>(eflags, peer_on ? ctx->peer.total : Q, ctx->out7.as<int>());
+    B2N_LAUNCH_CHECK(ctx);
+    B2N_CUDA(ctx, cudaMemcpyAsync(herr, ctx->out7.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (peer_on) {
+        void* const user7[7] = {u, v, logl, ncall, nullptr, nullptr, flags};
+        B2N_TRY(b2n_peer_end(ctx, n, user7));
+        B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->ptr_mode == B2N_PTR_HOST && *ctx->peer.err_host)
+            return b2n_fail(ctx, B2N_ERR_PEER, "a peer never arrived at the exchange (timeout in the kernel)");
+    } else {
+        B2N_TRY(b2n_out_done(ctx, u, du, (size_t)Q * n * sizeof(double)));
+        B2N_TRY(b2n_out_done(ctx, v, dv, (size_t)Q * n * sizeof(double)));
+        B2N_TRY(b2n_out_done(ctx, logl, dl, (size_t)Q * sizeof(double)));
+        B2N_TRY(b2n_out_done(ctx, ncall, dnc, (size_t)Q * sizeof(int)));
+        if (flags && ctx->ptr_mode == B2N_PTR_HOST)
+            B2N_CUDA(ctx, cudaMemcpyAsync(flags, dfl, (size_t)Q * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (*herr & 2) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "unit-cube sampling did not find a point above the threshold (draw limit)");
     return B2N_OK;
 }

@@ -138,3 +138,14 @@ def shells(ndim, r=2.0, w=0.1, c=3.5, halfwidth=6.0):
                     name='shells%d' % ndim)
     m.logz_truth = {2: -1.75, 5: -5.67, 10: -14.59}.get(ndim)
     return m
+
+
+def region2d(shape='diamond', ndim=2):
+    """The hard-edged regions of the reference's sampler-uniformity harness (tests/test_sampling.py:8-23):
+    ``diamond_logl`` / ``checker_logl`` on the first two coordinates, identity prior, the remaining
+    dimensions free.  Used with loglstar = 0: the samplers must leave the uniform distribution on
+    {logl > 0} invariant."""
+    m = DeviceModel(ndim, _lib.PRIOR_IDENTITY, _lib.LIKE_REGION2D, s0={'diamond': 0.0, 'checkerboard': 1.0}[shape],
+                    name='region2d_%s%d' % (shape, ndim))
+    m.logz_truth = None
+    return m

@@ -311,13 +311,36 @@ class NestedSampler:
         self.update_bound_if_needed(loglstar, ncall=self.ncall)
 
     # ------------------------------------------------------------------ device-resident rounds
-    def _device_rounds(self, logz, logvol, loglstar, dlogz, maxiter, maxcall, batch, checkpoint_file=None,
-                       checkpoint_every=0.0, snap=None, _abort_after=None):
-        """Continue the run with ``b2n_ns_run`` (include/b200nest.h): K-worst replacement rounds
-        paced on the device; the host only rebuilds the bound when the device asks for it
-        (update_bound, sampler.py:493-510) and collects the dead points at the end."""
+    def _device_bound_ok(self):
+        """The bound can be rebuilt without leaving the device (b2n_ns_update_bound): one of the library's own
+        ellipsoid bounds and no bootstrap expansion."""
+        b = self.bound_next
+        return type(b) in (B.B200MultiEllipsoid, B.B200Ellipsoid) and self.bound_bootstrap == 0 and \
+            getattr(self, 'device_bound', True)
+
+    def _pull_device_bound(self, nells):
+        """Host bound object <- the bound the device built (results, checkpoints, plotting read self.bound)."""
         from . import ops
-        smp, n, N = self.internal_sampler, self.ndim, self.nlive
+        o = ops.ns_get_bound(nells, self.ncdim, ctx=self.ctx)
+        m = self.bound._m if isinstance(self.bound, B.B200Ellipsoid) else self.bound
+        m.nells = nells
+        m.ctrs, m.covs, m.ams = o['ctrs'], o['covs'], o['ams']
+        m.axes_all, m.axlens_all, m.logvol_ells = o['axes'], o['axlens'], o['logvols']
+        m._refresh_logvol()
+        c = self.ctx if self.ctx is not None else m.ctx
+        c.resident_key = m.version                     # these very ellipsoids ARE the resident bound
+
+    def _device_rounds(self, logz, logvol, loglstar, dlogz, maxiter, maxcall, batch, checkpoint_file=None,
+                       checkpoint_every=0.0, snap=None, on_checkpoint=None):
+        """Run (or continue) with ``b2n_ns_run`` (include/b200nest.h): K-worst replacement rounds paced on the
+        device -- first with prior draws (the phase before the first bound, sampler.py:407-409), then with the
+        inner sampler against the resident bound.  The host only reacts to the device's flags: (re)build the bound
+        (update_bound, sampler.py:493-510 -- on the device when ``_device_bound_ok``), grow the dead buffer, and
+        collect the dead points at the end."""
+        from . import ops
+        import time
+        n, N = self.ndim, self.nlive
+        smp = self.internal_sampler_next
         kind = (0 if isinstance(smp, S.B200RWalkSampler) else 1 if isinstance(smp, S.B200RSliceSampler) else
                 2 if isinstance(smp, S.B200SliceSampler) else 3)             # 3: uniform sampler (no chains to tune)
         steps = 1 if kind == 3 else smp.sampler_kwargs['walks' if kind == 0 else 'slices']
@@ -329,119 +352,155 @@ class NestedSampler:
         self.batch = K
         prev = [np.empty((0, n)), np.empty((0, n)), np.empty(0), np.empty(0), np.empty(0, dtype=np.int32)]
         chain_base = self.chain_counter
+        it0_orig = it0 = self.it         # iterations before the device phase (enters the efficiency test)
         if snap is not None:             # resume: rows that died before the snapshot, scalars of the run
             prev = [snap['dead'][k] for k in range(5)]
             self.live_u, self.live_v, self.live_logl = snap['live']
             logvol, logz, loglstar = snap['logvol'], snap['logz'], snap['loglstar']
             self.ncall, smp.scale, chain_base = snap['ncall'], snap['scale'], snap['chain_base']
             maxiter = maxiter - len(prev[2]) if maxiter < (1 << 61) else maxiter
-        nprev = len(prev[2])
+            it0_orig = snap['it0']
+            it0 = it0_orig + len(prev[2])
+        no_bound = self.bound_next is None
+        multi = not isinstance(self.bound_next, B.B200Ellipsoid)
         ops.ns_create(self.model.model_id(self.ctx), N, n, K, kind, steps, self.seed, chain0=chain_base,
-                      ncdim=self.ncdim, strict_contains=not isinstance(self.bound, B.B200Ellipsoid),
+                      ncdim=self.ncdim, strict_contains=multi,
                       facc=getattr(smp, 'facc', 0.5), dlogz=dlogz if dlogz is not None else 0.0,
                       maxiter=maxiter if maxiter < (1 << 61) else None, maxcall=maxcall,
-                      update_interval=self.bound_update_interval, dimflags=smp._flags(), ctx=self.ctx)
-        ops.ns_set_state(self.live_u, self.live_v, self.live_logl, logvol, logz, loglstar, self.ncall, smp.scale,
-                         ctx=self.ctx)
-        rounds0 = 0
-        if snap is not None:
-            rounds0 = snap['rounds']
-            ops.ns_set_counters(snap['rounds'], snap['ncall_last_update'], snap['doubling'], ctx=self.ctx)
-        self._ensure_resident()
-        cap, last_forced = 64 * N, -1
-        ncall_start, rounds = self.ncall, rounds0
-        import time
+                      update_interval=self.bound_update_interval, dimflags=smp._flags(), ctx=self.ctx,
+                      unit_cube_phase=self.unit_cube_sampling,
+                      first_min_ncall=(1 << 62) if no_bound else self.first_bound_update_ncall,
+                      first_min_eff=self.first_bound_update_eff, it0=it0)
         tm = dict(rounds_s=0.0, bound_s=0.0)
         self.device_timing = tm
-        t_ckpt, n_ckpt, saved_it = time.perf_counter(), 0, 0
-
-        def checkpoint(st):
-            """Snapshot at a consistent point (flags clear, bound current): live set, scalars, the rows that
-            died since the last snapshot; then pickle the whole sampler (host phase results included)."""
-            nonlocal saved_it, prev
-            new = ops.ns_get_dead(saved_it, st['it'] - saved_it, n, ctx=self.ctx)
-            prev = [np.concatenate([a, b]) for a, b in zip(prev, new)]
-            saved_it = st['it']
-            self._dev_snap = dict(dead=prev, live=ops.ns_get_live(N, n, ctx=self.ctx), logvol=st['logvol'],
-                                  logz=st['logz'], loglstar=st['loglstar'], ncall=st['ncall'], scale=st['scale'],
-                                  rounds=st['rounds'], ncall_last_update=st['ncall_last_update'],
-                                  doubling=st['doubling'], chain_base=chain_base, batch=K)
-            self.save(checkpoint_file)
-
-        while True:
-            done_r = rounds - rounds0
-            per_round = max(1.0, (self.ncall - ncall_start) / done_r) if done_r else K * steps * (1 if kind == 0 else 6)
-            if kind == 3 and not done_r:
-                per_round = K * max(1.0, 100. / max(self.eff, 1.))        # uniform draws: ~1/eff calls each
-            due = self.ncall_at_last_update + self.bound_update_interval - self.ncall
-            want = int(min(4096, max(1, math.ceil(due / per_round))))
-            t0 = time.perf_counter()
-            st = ops.ns_run(want, 0, ctx=self.ctx)
-            tm['rounds_s'] += time.perf_counter() - t0
-            rounds, self.ncall = st['rounds'], st['ncall']
-            self.scale_history.append((self.ncall, st['scale']))
-            if st['done']:
-                break
-            if st['need_bound'] == 3:                               # dead-point buffer full
-                cap *= 2
-                ops.ns_reserve_dead(cap, ctx=self.ctx)
-            elif st['need_bound']:
-                if st['need_bound'] == 2:                           # a start point outside the bound
-                    if last_forced == rounds:
-                        raise RuntimeError('Update of the ellipsoid failed')     # sampler.py:489
-                    last_forced = rounds
-                t0 = time.perf_counter()
-                self.live_u = ops.ns_get_live(N, n, ctx=self.ctx, only_u=True)
-                self.update_bound()
-                self.nbound += 1
-                self.ncall_at_last_update = self.ncall
-                self.bound_history.append((self.ncall, getattr(self.bound, 'nells', 1), float(self.bound.logvol)))
+        st = None
+        try:
+            ops.ns_set_state(self.live_u, self.live_v, self.live_logl, logvol, logz, loglstar, self.ncall, smp.scale,
+                             ctx=self.ctx)
+            rounds0 = 0
+            if snap is not None:
+                rounds0 = snap['rounds']
+                ops.ns_set_counters(snap['rounds'], snap['ncall_last_update'], snap['doubling'], ctx=self.ctx)
+            if not self.unit_cube_sampling:
                 self._ensure_resident()
-                ops.ns_bound_updated(ctx=self.ctx)
-                tm['bound_s'] += time.perf_counter() - t0
-                if checkpoint_file is not None and time.perf_counter() - t_ckpt >= checkpoint_every:
-                    st = ops.ns_status(ctx=self.ctx)              # flags cleared, interval restarted
-                    checkpoint(st)
-                    t_ckpt, n_ckpt = time.perf_counter(), n_ckpt + 1
-                    if _abort_after is not None and n_ckpt >= _abort_after:
-                        ops.ns_destroy(ctx=self.ctx)
-                        raise KeyboardInterrupt('test hook: run aborted after checkpoint %d' % n_ckpt)
-        smp.scale = st['scale']
-        if st['doubling']:
-            smp.sampler_kwargs['slice_doubling'] = True
-        self.live_u, self.live_v, self.live_logl = ops.ns_get_live(N, n, ctx=self.ctx)
-        new = ops.ns_get_dead(saved_it, st['it'] - saved_it, n, ctx=self.ctx)
-        out = tuple(np.concatenate([a, b]) for a, b in zip(prev, new))
-        self.chain_counter = chain_base + rounds * K
-        self.nbatches += rounds - rounds0
-        self.n_proposals += self.ncall - ncall_start
-        self.it += st['it']
-        self.device_rounds = rounds
-        self._dev_snap = None
-        ops.ns_destroy(ctx=self.ctx)
-        return out
+            cap, last_forced = 64 * N, -1
+            ncall_start, rounds = self.ncall, rounds0
+            t_ckpt, n_ckpt, saved_it = time.perf_counter(), 0, 0
+            dev_nells = 0
+
+            def checkpoint(st):
+                """Snapshot at a consistent point (flags clear, bound current): live set, scalars, the rows that
+                died since the last snapshot; then pickle the whole sampler (host phase results included)."""
+                nonlocal saved_it, prev
+                new = ops.ns_get_dead(saved_it, st['it'] - saved_it, n, ctx=self.ctx)
+                prev = [np.concatenate([a, b]) for a, b in zip(prev, new)]
+                saved_it = st['it']
+                if dev_nells:
+                    self._pull_device_bound(dev_nells)
+                self._dev_snap = dict(dead=prev, live=ops.ns_get_live(N, n, ctx=self.ctx), logvol=st['logvol'],
+                                      logz=st['logz'], loglstar=st['loglstar'], ncall=st['ncall'], scale=st['scale'],
+                                      rounds=st['rounds'], ncall_last_update=st['ncall_last_update'],
+                                      doubling=st['doubling'], chain_base=chain_base, batch=K, it0=it0_orig)
+                self.save(checkpoint_file)
+
+            while True:
+                done_r = rounds - rounds0
+                if self.unit_cube_sampling:           # prior draws: ~100/eff calls per accepted point
+                    per_round = max(1.0, (self.ncall - ncall_start) / done_r) if done_r else 2.0 * K
+                    due = self.first_bound_update_ncall - self.ncall
+                    want = int(min(64, max(1, math.ceil(due / per_round)))) if not no_bound else 256
+                else:
+                    per_round = max(1.0, (self.ncall - ncall_start) / done_r) if done_r else K * steps * (1 if kind == 0 else 6)
+                    if kind == 3 and not done_r:
+                        per_round = K * max(1.0, 100. / max(self.eff, 1.))        # uniform draws: ~1/eff calls each
+                    due = self.ncall_at_last_update + self.bound_update_interval - self.ncall
+                    want = int(min(4096, max(1, math.ceil(due / per_round))))
+                t0 = time.perf_counter()
+                st = ops.ns_run(want, 0, ctx=self.ctx)
+                tm['rounds_s'] += time.perf_counter() - t0
+                rounds, self.ncall = st['rounds'], st['ncall']
+                self.eff = 100. * (it0 + st['it']) / max(self.ncall, 1)
+                self.scale_history.append((self.ncall, st['scale']))
+                if st['done']:
+                    break
+                if st['need_bound'] == 3:                               # dead-point buffer full
+                    cap *= 2
+                    ops.ns_reserve_dead(cap, ctx=self.ctx)
+                elif st['need_bound']:
+                    if st['need_bound'] == 2:                           # a start point outside the bound
+                        if last_forced == rounds:
+                            raise RuntimeError('Update of the ellipsoid failed')     # sampler.py:489
+                        last_forced = rounds
+                    t0 = time.perf_counter()
+                    if st['need_bound'] == 4:                           # first bound (sampler.py:640-647)
+                        self.unit_cube_sampling = False
+                        self.logl_first_update = st['loglstar']
+                        self.bound = self.bound_next
+                        self.internal_sampler = self.internal_sampler_next
+                        ncall_start, rounds0 = self.ncall, rounds      # calls per round change with the sampler
+                    if self._device_bound_ok():
+                        dev_nells, lv, warn = ops.ns_update_bound(multi, self.bound_enlarge, ctx=self.ctx)
+                        nells = dev_nells
+                    else:
+                        self.live_u = ops.ns_get_live(N, n, ctx=self.ctx, only_u=True)
+                        self.update_bound()
+                        self._ensure_resident()
+                        dev_nells, nells, lv = 0, getattr(self.bound, 'nells', 1), float(self.bound.logvol)
+                    self.nbound += 1
+                    self.ncall_at_last_update = self.ncall
+                    self.bound_history.append((self.ncall, nells, lv))
+                    ops.ns_bound_updated(ctx=self.ctx)
+                    tm['bound_s'] += time.perf_counter() - t0
+                    if checkpoint_file is not None and time.perf_counter() - t_ckpt >= checkpoint_every:
+                        st = ops.ns_status(ctx=self.ctx)              # flags cleared, interval restarted
+                        checkpoint(st)
+                        t_ckpt, n_ckpt = time.perf_counter(), n_ckpt + 1
+                        if on_checkpoint is not None:
+                            on_checkpoint(n_ckpt)
+            if not self.unit_cube_sampling:
+                smp.scale = st['scale']
+                if st['doubling']:
+                    smp.sampler_kwargs['slice_doubling'] = True
+                if dev_nells:
+                    self._pull_device_bound(dev_nells)
+            self.live_u, self.live_v, self.live_logl = ops.ns_get_live(N, n, ctx=self.ctx)
+            new = ops.ns_get_dead(saved_it, st['it'] - saved_it, n, ctx=self.ctx)
+            out = tuple(np.concatenate([a, b]) for a, b in zip(prev, new))
+            self.chain_counter = chain_base + rounds * K
+            self.nbatches += rounds - (snap['rounds'] if snap is not None else 0)
+            self.n_proposals += self.ncall - ncall_start
+            self.it = it0 + st['it']
+            self.device_rounds = rounds
+            self._dev_snap = None
+            return out
+        finally:
+            ops.ns_destroy(ctx=self.ctx)            # also on errors: the device state never outlives the call
 
     # ------------------------------------------------------------------ main loop
     def run_nested(self, dlogz=None, maxiter=None, maxcall=None, add_live=True, loop='host', batch=None,
-                   checkpoint_file=None, checkpoint_every=60., resume=False, _abort_after=None):
+                   checkpoint_file=None, checkpoint_every=60., resume=False, on_checkpoint=None):
         """sampler.py:1214-1356 / 1040-1212 (no plateau mode: continuous likelihoods).
 
         loop='host'   : the reference's semantics -- one worst point per iteration, replacements
                         popped from a queue of `queue_size` proposals (sampler.py:732-778).
-        loop='device' : once the first bound exists, the run continues in ROUNDS on the device
-                        (csrc/b2n_ns.cu, ``b2n_ns_run``): each round removes the `batch` lowest
-                        live points at once and replaces them with `batch` chains evolved at the
-                        threshold of the batch-th lowest -- no stale-threshold filter, hence no
-                        selection bias for correlated chains, no host round trip
-                        per iteration.  batch defaults to nlive // 40 (rwalk) or nlive // 10 (slices)."""
+        loop='device' : the WHOLE run is rounds on the device (csrc/b2n_ns.cu, ``b2n_ns_run``): each round
+                        removes the `batch` lowest live points at once and replaces them with `batch`
+                        chains evolved at the threshold of the batch-th lowest -- prior draws until the
+                        first bound is due (UnitCubeSampler, sampler.py:407-409), then the inner sampler.
+                        No stale-threshold filter, hence no selection bias for correlated chains
+                        (DESIGN.md 9.4), no host round trip per iteration.  batch defaults to
+                        nlive // 40 (rwalk) or nlive // 10 (slices).
+        on_checkpoint : callable(k) invoked after the k-th checkpoint has been written."""
         if resume:
             return self._resume(checkpoint_file, checkpoint_every)
         if loop not in ('host', 'device'):
             raise ValueError("loop must be 'host' or 'device'")
         if checkpoint_file is not None and loop != 'device':
             raise ValueError("checkpointing is implemented for loop='device'")
-        if loop == 'device' and (self.comm is not None or self.bound_next is None):
-            raise ValueError("loop='device' needs a bound (single/multi) and runs on one GPU")
+        if loop == 'device' and self.comm is not None:
+            raise ValueError("loop='device' runs on one GPU (replicas: dynesty_b200.replicas)")
+        if loop == 'device' and self.internal_sampler_next is None:
+            raise ValueError("loop='device' needs one of the B200 samplers")
         nlive = self.nlive
         if dlogz is None:
             dlogz = 1e-3 * (nlive - 1.) + 0.01 if add_live else 0.01
@@ -465,8 +524,8 @@ class NestedSampler:
             delta_logz = _logaddexp(0.0, lmax + logvol - logz)
             if it > maxiter or self.ncall - ncall0 > maxcall:
                 break
-            if loop == 'device' and not self.unit_cube_sampling and self._qpos >= len(self._ql):
-                hand_over = True                                    # bound exists, queue drained
+            if loop == 'device' and (self._q is None or self._qpos >= len(self._ql)):
+                hand_over = True                                    # (queue drained): the device takes over
                 break
             if dlogz is not None and delta_logz < dlogz:
                 break
@@ -524,7 +583,7 @@ class NestedSampler:
                                    maxcall=ncall0 + maxcall if maxcall < (1 << 61) else None)
             dev = self._device_rounds(logz, logvol, loglstar, dlogz, self._host_part['maxiter'],
                                       self._host_part['maxcall'], batch, checkpoint_file=checkpoint_file,
-                                      checkpoint_every=checkpoint_every, _abort_after=_abort_after)
+                                      checkpoint_every=checkpoint_every, on_checkpoint=on_checkpoint)
             return self._finalize(su, sv, logl, logvols, nc_all, dev, add_live)
         return self._finalize(su, sv, logl, logvols, nc_all, None, add_live)
 

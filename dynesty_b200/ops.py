@@ -82,6 +82,26 @@ def multi_decompose(points, max_ells=None, ctx=None):
     return o
 
 
+def improve_covar(covar, ctx=None):
+    """(good, cov, am, axes, warn) = improve_covar_mat(covar)  (bounding.py:1311-1384)."""
+    ctx = _ctx(ctx)
+    covar = f64(covar)
+    n = covar.shape[0]
+    cov, am, axes = np.empty((n, n)), np.empty((n, n)), np.empty((n, n))
+    good, warn = C.c_int32(0), C.c_uint32(0)
+    ctx.check(ctx.lib.b2n_improve_covar(ctx.h, ptr(covar), n, ptr(cov), ptr(am), ptr(axes), C.addressof(good),
+                                        C.addressof(warn)))
+    return bool(good.value), cov, am, axes, warn.value
+
+
+def fp64_peak(kind, iters=20000, ctx=None):
+    """Measured FP64 ceiling in TFLOP/s: kind 'fma' (vector pipe) or 'mma' (m8n8k4 tensor pipe)."""
+    ctx = _ctx(ctx)
+    t, ms = C.c_double(0.0), C.c_double(0.0)
+    ctx.check(ctx.lib.b2n_fp64_peak(ctx.h, {'fma': 0, 'mma': 1}[kind], int(iters), C.byref(t), C.byref(ms)))
+    return t.value, ms.value
+
+
 def scale_to_logvol(covs, ams, axes, axlens, logvols, targets, ctx=None):
     """In-place Ellipsoid.scale_to_logvol on K stacked ellipsoids (bounding.py:242-276)."""
     ctx = _ctx(ctx)
@@ -250,11 +270,26 @@ def unif_batch(model, nchain, ndim, loglstar, seed, chain0=0, ncdim=None, dimfla
     return o
 
 
+def unitcube_batch(model, nchain, ndim, loglstar, seed, chain0=0, ctx=None, peer=None):
+    """UnitCubeSampler.sample x nchain (internal_samplers.py:343-441): prior draws until logl > loglstar."""
+    ctx = _ctx(ctx)
+    a, keep, Q, n = _chain_args(model, None, None, loglstar, 1.0, seed, chain0, None, None, Q=int(nchain), ndim=int(ndim))
+    R = Q if peer is None else int(peer[1])
+    o = dict(u=np.empty((R, n)), v=np.empty((R, n)), logl=np.empty(R), ncall=np.empty(R, dtype=np.int32))
+    with _gather(ctx, peer):
+        ctx.check(ctx.lib.b2n_unitcube_batch(ctx.h, C.byref(a), ptr(o['u']), ptr(o['v']), ptr(o['logl']),
+                                             ptr(o['ncall']), None))
+    return o
+
+
 # ---- device-resident nested-sampling rounds (include/b200nest.h, b2n_ns_*) ----------------------
 def ns_create(model, nlive, ndim, batch, sampler, steps, seed, chain0=0, ncdim=None, strict_contains=True,
               facc=0.5, dlogz=0.01, maxiter=None, maxcall=None, update_interval=1 << 62, dimflags=None,
-              dead_capacity=None, ctx=None):
-    """Allocate the device state of a batched-replacement run (sampler: 0 rwalk, 1 rslice, 2 slice)."""
+              dead_capacity=None, ctx=None, unit_cube_phase=False, first_min_ncall=0, first_min_eff=100., it0=0,
+              logl_max=None):
+    """Allocate the device state of a batched-replacement run (sampler: 0 rwalk, 1 rslice, 2 slice, 3 unif).
+    unit_cube_phase: start with rounds that draw from the prior until the first bound is due
+    (need_bound = 4 once ncall >= first_min_ncall and 100 (it0 + it) / ncall < first_min_eff)."""
     ctx = _ctx(ctx)
     c = _lib.NsConfig()
     c.nlive, c.ndim, c.ncdim, c.batch = int(nlive), int(ndim), int(ncdim or ndim), int(batch)
@@ -267,6 +302,9 @@ def ns_create(model, nlive, ndim, batch, sampler, steps, seed, chain0=0, ncdim=N
     if dimflags is not None:
         dimflags = np.ascontiguousarray(dimflags, dtype=np.uint8)
     c.dimflags = ptr(dimflags)
+    c.unit_cube_phase, c.first_min_ncall, c.first_min_eff, c.it0 = int(bool(unit_cube_phase)), int(first_min_ncall), \
+        float(first_min_eff), int(it0)
+    c.use_logl_max, c.logl_max = (0, 0.0) if logl_max is None else (1, float(logl_max))
     cap = int(dead_capacity) if dead_capacity is not None else 64 * int(nlive)
     ctx.check(ctx.lib.b2n_ns_create(ctx.h, C.byref(c), cap))
 
@@ -307,6 +345,33 @@ def ns_set_counters(rounds, ncall_last_update, doubling, ctx=None):
 def ns_bound_updated(ctx=None):
     ctx = _ctx(ctx)
     ctx.check(ctx.lib.b2n_ns_bound_updated(ctx.h))
+
+
+_ns_bound_serial = [0]
+
+
+def ns_update_bound(multi, enlarge=1.0, ctx=None):
+    """Sampler.update_bound on the device (b2n_ns_update_bound): fit the bound to the run's live points in HBM,
+    enlarge, make resident.  Returns (nells, logvol, warn)."""
+    ctx = _ctx(ctx)
+    nells, warn, lv = C.c_int32(0), C.c_uint32(0), C.c_double(0.0)
+    ctx.resident_key = None
+    ctx.check(ctx.lib.b2n_ns_update_bound(ctx.h, int(bool(multi)), float(enlarge), C.addressof(nells), C.addressof(lv),
+                                          C.addressof(warn)))
+    _ns_bound_serial[0] += 1
+    ctx.resident_key = ('ns', ctx.serial, _ns_bound_serial[0])     # no host bound object owns these ellipsoids
+    return nells.value, lv.value, warn.value
+
+
+def ns_get_bound(nells, ncdim, ctx=None):
+    """The bound the last ns_update_bound built: dict(ctrs, covs, ams, axes, axlens, logvols)."""
+    ctx = _ctx(ctx)
+    K, n = int(nells), int(ncdim)
+    o = dict(ctrs=np.empty((K, n)), covs=np.empty((K, n, n)), ams=np.empty((K, n, n)), axes=np.empty((K, n, n)),
+             axlens=np.empty((K, n)), logvols=np.empty(K))
+    ctx.check(ctx.lib.b2n_ns_get_bound(ctx.h, K, ptr(o['ctrs']), ptr(o['covs']), ptr(o['ams']), ptr(o['axes']),
+                                       ptr(o['axlens']), ptr(o['logvols'])))
+    return o
 
 
 def ns_reserve_dead(capacity, ctx=None):

@@ -52,7 +52,8 @@ typedef enum {
     B2N_ERR_NOMEM = 9,
     B2N_ERR_UNSUPPORTED = 10,
     B2N_ERR_TOO_MANY_ELLS = 11,  /* max_ells too small for the decomposition        */
-    B2N_ERR_PEER = 12            /* peer exchange not configured / a peer never arrived */
+    B2N_ERR_PEER = 12,           /* peer exchange not configured / a peer never arrived */
+    B2N_ERR_PLATEAU = 13         /* RuntimeError sampler.py:473-475: no live point above loglstar   */
 } b2n_status;
 
 /* warning bits (the reference issues warnings.warn at the cited lines) */
@@ -95,6 +96,9 @@ double b2n_last_kernel_ms(b2n_ctx* ctx);
 #define B2N_LIKE_GAUSS_DIAG  1  /* -0.5 sum vec1[i] (v-vec0)[i]^2 + s0            */
 #define B2N_LIKE_EGGBOX      2  /* (2 + prod cos((2 s0 v - s0)/2))^s1  (tmax, power) */
 #define B2N_LIKE_SHELLS      3  /* logaddexp of two shells: centres vec0, vec1, radius s0, width s1 */
+#define B2N_LIKE_REGION2D    4  /* the hard-edged 2-D regions of the reference's sampler-uniformity harness
+                                   (tests/test_sampling.py:8-23) on (v[0], v[1]), other dims free:
+                                   s0 = 0: diamond_logl, s0 = 1: checker_logl; -inf outside           */
 
 typedef struct {
     int32_t ndim;
@@ -145,6 +149,18 @@ int b2n_multi_decompose(b2n_ctx* ctx, const double* points, int64_t N, int32_t n
                         int32_t max_ells, int32_t* nells, int32_t* labels,
                         double* ctrs, double* covs, double* ams, double* axes,
                         double* axlens, double* logvols, uint32_t* warn);
+
+/* improve_covar_mat (bounding.py:1311-1384) on its own: the <= 100-trial repair ladder (eigenvalue clamp at
+ * 10 max/1e12, then the identity blend, then the identity fallback) applied to `covar` (n x n).  Outputs:
+ * the repaired covariance, its inverse `am`, `axes` = V sqrt(lambda) (columns, ascending eigenvalue);
+ * *good = 1 iff the input passed untouched (host int), *warn = B2N_WARN_IDENTITY_FALLBACK bit.  Synchronises. */
+int b2n_improve_covar(b2n_ctx* ctx, const double* covar, int32_t n, double* cov_out, double* am,
+                      double* axes, int32_t* good, uint32_t* warn);
+
+/* Measured FP64 issue ceilings of this GPU for bench.py's roofline: kind 0 = FP64 FMA (vector pipe),
+ * kind 1 = FP64 m8n8k4 MMA (tensor pipe); `iters` rounds of 16 independent chains per thread, all SMs.
+ * *tflops, *ms (best of 4 timed launches, CUDA events): host outputs.  Synchronises. */
+int b2n_fp64_peak(b2n_ctx* ctx, int32_t kind, int32_t iters, double* tflops, double* ms);
 
 /* Ellipsoid.scale_to_logvol for K ellipsoids (bounding.py:242-276, 478-495).
  * target_logvols: host, K.  covs/ams/axes/axlens/logvols updated in place. */
@@ -216,6 +232,12 @@ int b2n_slice_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slices,
                     int32_t* n_expand, int32_t* n_contract, int32_t* ncall,
                     uint32_t* flags);
 
+/* UnitCubeSampler.sample (internal_samplers.py:343-441) for a queue: every chain draws u ~ U(0,1)^ndim (one
+ * uniform vector event per draw of its B2N stream) until loglikelihood(prior_transform(u)) > loglstar; ncall[q] =
+ * number of draws.  u0 / ell / scale / ncdim unused, no resident bound needed.  flags may be NULL. */
+int b2n_unitcube_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, double* v, double* logl,
+                       int32_t* ncall, uint32_t* flags);
+
 /* UniformBoundSampler.sample (internal_samplers.py:243-340) with
  * MultiEllipsoid.sample (bounding.py:525-590) as the bound draw; u0/ell/scale
  * unused.  nprop[q] = draws from the bound incl. out-of-cube ones. */
@@ -274,11 +296,13 @@ uint64_t b2n_peer_window_bytes(int64_t total_rows, int32_t ndim);
  * DESIGN.md 9.4) no chain is ever discarded, so there is no selection effect; the live-point
  * count N, N-1, .., N-batch+1 seen by the removed points enters the quadrature the way the
  * reference treats a shrinking live set (ln X -= ln((m+1)/m) at a point with m live points).
- * A round is three launches (sort/propose, chains, commit) with no host synchronisation;
+ * Launches of R rounds: propose | chains | commit+propose | chains | ... | commit (R chain launches and R + 1
+ * single-CTA step launches), no host synchronisation in between;
  * b2n_ns_run enqueues rounds until a stop flag is raised on the device:
  *   done        dlogz / maxiter / maxcall / plateau reached (sampler.py:1095-1120)
  *   need_bound  1 = update interval reached (sampler.py:648-651), 2 = a start point is outside
- *               the bound (forced update, :485-489), 3 = dead-point buffer full
+ *               the bound (forced update, :485-489), 3 = dead-point buffer full, 4 = the FIRST bound is
+ *               due (unit-cube phase: enough calls and low efficiency, sampler.py:640-647)
  * The caller then updates the bound from b2n_ns_get_live (b2n_multi_decompose / b2n_bound_set as
  * usual), calls b2n_ns_bound_updated and runs on.  Random streams: chain c of round r is the
  * B2N chain (seed, chain0 + r*batch + c); the round driver (start rows, ellipsoid picks) is the
@@ -295,6 +319,17 @@ typedef struct {
     int64_t update_interval;  /* bound update every this many calls (dynesty.py:213-240)         */
     uint64_t seed, chain0;
     const uint8_t* dimflags;  /* HOST, ndim B2N_DIM_* flags or NULL (copied)                      */
+    /* -- the phase before the first bound (sampler.py:407-409, 625-674; _initialize_live_points + UnitCubeSampler,
+     *    sampler.py:56-262, internal_samplers.py:343-441): with unit_cube_phase = 1 the run STARTS with rounds whose
+     *    chains draw from the prior (b2n_unitcube_batch) and raises need_bound = 4 once ncall >= first_min_ncall and
+     *    the efficiency 100 (it0 + it) / ncall has fallen below first_min_eff; b2n_ns_bound_updated ends the phase. */
+    int32_t unit_cube_phase;
+    int32_t use_logl_max;     /* 1: stop (done) once the lowest live logl exceeds logl_max (the end of a
+                                 dynamic-sampler batch, dynamicsampler.py:1338-1345)                */
+    int64_t first_min_ncall;
+    double  first_min_eff;
+    double  logl_max;
+    int64_t it0;              /* iterations of the run before this device phase (enters the efficiency) */
 } b2n_ns_config;
 
 typedef struct {
@@ -319,8 +354,20 @@ int b2n_ns_status_get(b2n_ctx* ctx, b2n_ns_status* status);
  * index (chain ids and the round driver's stream depend on it), the calls at the last bound update, the
  * slice-doubling switch.  A run restored this way continues bit-identically. */
 int b2n_ns_set_counters(b2n_ctx* ctx, int64_t rounds, int64_t ncall_last_update, int32_t doubling);
-/* after the caller replaced the resident bound: clears need_bound, restarts the update interval */
+/* after the caller replaced the resident bound: clears need_bound, restarts the update interval, ends the
+ * unit-cube phase */
 int b2n_ns_bound_updated(b2n_ctx* ctx);
+/* Sampler.update_bound (sampler.py:493-510) WITHOUT leaving the device: fits the bound to the run's live points
+ * where they lie in HBM (multi = 1: MultiEllipsoid.update, bounding.py:632-686 -- b2n_multi_decompose; 0:
+ * Ellipsoid.update, :345-414 -- b2n_bounding_ellipsoid; first ncdim coordinates), enlarges it
+ * (scale_to_logvol(logvol + ln enlarge), sampler.py:506-508) and makes it the resident bound of the ctx -- no
+ * live-set download, no bound upload.  Bootstrap expansion is not part of this entry (callers that need it take
+ * the host route: b2n_ns_get_live + b2n_bootstrap_expand + b2n_bound_set).  nells / logvol (ln of the summed
+ * volumes) / warn: host outputs, may be NULL.  Follow with b2n_ns_bound_updated.  Synchronises. */
+int b2n_ns_update_bound(b2n_ctx* ctx, int32_t multi, double enlarge, int32_t* nells, double* logvol, uint32_t* warn);
+/* the bound b2n_ns_update_bound built last (host outputs sized for max_ells >= nells; each may be NULL) */
+int b2n_ns_get_bound(b2n_ctx* ctx, int32_t max_ells, double* ctrs, double* covs, double* ams, double* axes,
+                     double* axlens, double* logvols);
 /* grow the dead-point buffer to `capacity` rows (keeps the rows written so far); clears need_bound == 3 */
 int b2n_ns_reserve_dead(b2n_ctx* ctx, int64_t capacity);
 /* host outputs (each may be NULL) */

@@ -18,7 +18,7 @@ import numpy as np
 from scipy.special import ndtri
 
 PRIOR_IDENTITY, PRIOR_UNIFORM, PRIOR_NORMAL_PPF = 0, 1, 2
-LIKE_GAUSS_PREC, LIKE_GAUSS_DIAG, LIKE_EGGBOX, LIKE_SHELLS = 0, 1, 2, 3
+LIKE_GAUSS_PREC, LIKE_GAUSS_DIAG, LIKE_EGGBOX, LIKE_SHELLS, LIKE_REGION2D = 0, 1, 2, 3, 4
 
 
 class Model:
@@ -62,7 +62,22 @@ class Model:
             d2 = np.sqrt(np.sum((v - self.p['c2'])**2, axis=-1))
             return np.logaddexp(const - (d1 - r)**2 / (2. * w**2),
                                 const - (d2 - r)**2 / (2. * w**2))
+        if k == LIKE_REGION2D:
+            # tests/test_sampling.py:8-23 (diamond_logl / checker_logl) on the first two coordinates
+            x, y = v[..., 0], v[..., 1]
+            if self.p['shape'] == 0:
+                x1, y1 = np.abs(x - 0.5), np.abs(y - 0.5)
+                D2 = (x1 - 0.5)**2 + (y1 - 0.5)**2
+                out = (np.minimum(x, y) < 0) | (np.maximum(x, y) > 1)
+                return np.where((D2 > 0.25) & ~out, D2 - 0.25, -np.inf)
+            mult = 16 * 2 * np.pi
+            return np.where((x >= 0) & (x <= 1) & (y >= 0) & (y < 1), np.sin(x * mult) * np.sin(y * mult), -np.inf)
         raise ValueError(k)
+
+
+def region2d(shape='diamond', ndim=2):
+    """tests/test_sampling.py:8-23."""
+    return Model(ndim, PRIOR_IDENTITY, LIKE_REGION2D, shape={'diamond': 0, 'checkerboard': 1}[shape])
 
 
 def gauss_corr(ndim, rho, halfwidth):

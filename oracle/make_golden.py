@@ -308,6 +308,12 @@ def gen_chains(B, IS):
     pp = rng.random((20000, 2))
     pp = pp[np.argsort(sh2.loglike(sh2.prior_transform(pp)))[-600:]]
     add_unif('shell2', sh2, pp, 2, 24, 1400, frac=0.2)
+    # the sampler of the phase before the first bound: UnitCubeSampler.sample (internal_samplers.py:343-441),
+    # replayed on the Philox stream like the others (added in round 2, after every earlier fixture)
+    uc_thr = -20.0
+    res = run_ref_chains(IS, IS.UnitCubeSampler, g3, [p3[0]] * 32, uc_thr, np.eye(3), 1.0, dict(ndim=3), 1500)
+    out.update(pack_chain('uc_', res, []))
+    out['uc_loglstar'], out['uc_seed'], out['uc_chain0'] = np.float64(uc_thr), np.int64(SEED), np.int64(1500)
     np.savez_compressed(os.path.join(OUT, 'chains.npz'), **out)
     return out
 

@@ -56,7 +56,8 @@ class BatchNS:
 
     def __init__(self, model, live_u, live_v, live_logl, batch, sampler, steps, seed, chain0=0, facc=0.5,
                  scale=1.0, logvol=0.0, logz=LOWL, loglstar=LOWL, ncall=0, update_interval=1 << 62,
-                 dlogz=0.01, maxiter=1 << 62, maxcall=1 << 62, bound=None, dimflags=None):
+                 dlogz=0.01, maxiter=1 << 62, maxcall=1 << 62, bound=None, dimflags=None, unit_cube_phase=False,
+                 first_min_ncall=0, first_min_eff=100., it0=0, logl_max=math.inf):
         self.model = model
         self.live_u = np.array(live_u, dtype=float)
         self.live_v = np.array(live_v, dtype=float)
@@ -78,6 +79,11 @@ class BatchNS:
             self.per = np.nonzero(f & 1)[0] if (f & 1).any() else None
             self.ref = np.nonzero(f & 2)[0] if (f & 2).any() else None
             self.nb = f == 0
+        # phase 0: the rounds before the first bound draw from the prior (UnitCubeSampler,
+        # internal_samplers.py:343-441) until ncall >= first_min_ncall and eff < first_min_eff (sampler.py:640-647)
+        self.phase = 0 if unit_cube_phase else 1
+        self.first_min_ncall, self.first_min_eff, self.it0, self.logl_max = first_min_ncall, first_min_eff, it0, logl_max
+        self.error = 0
         self.it = self.round = 0
         self.done = self.need_bound = 0
         self.doubling = False
@@ -101,6 +107,7 @@ class BatchNS:
             self.bound = bound
         self.need_bound = 0
         self.ncall_last_update = self.ncall
+        self.phase = 1
 
     # ------------------------------------------------------------------ one round
     def step(self):
@@ -112,16 +119,24 @@ class BatchNS:
         sl = self.live_logl[order]
         lmax = float(sl[-1])
         self.delta_logz = logaddexp(0.0, lmax + self.logvol - self.logz)
-        if self.delta_logz < self.dlogz or self.it >= self.maxiter or self.ncall >= self.maxcall or sl[0] == lmax:
+        if (self.delta_logz < self.dlogz or self.it >= self.maxiter or self.ncall >= self.maxcall or sl[0] == lmax
+                or sl[0] > self.logl_max):
             self.done = 1
             return False
         thr = float(sl[K - 1])
+        # start rows need logl STRICTLY above the threshold (sampler.py:471): first sorted position above it
+        first = int(np.searchsorted(sl, thr, side='right'))
+        if first >= N:
+            self.done, self.error = 1, 13           # B2N_ERR_PLATEAU: no live point above the threshold
+            return False
+        if self.phase == 0:
+            return self._step_unitcube(order, sl, thr)
         if self.sampler == 'unif':
             return self._step_unif(order, sl, thr)
         drv = philox.ChainStream(self.seed, DRIVER_CHAIN + self.round)
         U = philox.event_uniforms(self.seed, drv.chain, 0, K)
-        nsurv = N - K
-        starts = order[K + np.minimum((U * nsurv).astype(np.int64), nsurv - 1)]
+        nsurv = N - first
+        starts = order[first + np.minimum((U * nsurv).astype(np.int64), nsurv - 1)]
         b = self.bound
         Ke = b['ctrs'].shape[0]
         ell = np.zeros(K, dtype=np.int64)
@@ -170,6 +185,17 @@ class BatchNS:
             self.last = dict(starts=starts, ell=ell, thr=thr, n_expand=ne, n_contract=ncn)
         if self.ncall >= self.ncall_last_update + self.update_interval:
             self.need_bound = 1
+        return True
+
+    def _step_unitcube(self, order, sl, thr):
+        """Round of the phase before the first bound: every chain draws from the prior until logl > thr."""
+        out = [OS.unitcube_chain(thr, self.model, philox.ChainStream(self.seed, self.chain0 + self.round * self.K + c),
+                                 self.n) for c in range(self.K)]
+        self._commit(order, sl, thr, out)
+        self.last = dict(thr=thr)
+        eff = 100.0 * (self.it0 + self.it) / self.ncall
+        if self.ncall >= self.first_min_ncall and eff < self.first_min_eff:
+            self.need_bound = 4
         return True
 
     def _step_unif(self, order, sl, thr):

@@ -206,6 +206,18 @@ def slice_chain(u0, loglstar, axes, scale, model, stream, slices,
                 ticks=stream.tick)
 
 
+def unitcube_chain(loglstar, model, stream, ndim, max_tries=10**7):
+    """UnitCubeSampler.sample (internal_samplers.py:420-441): u = rstate.uniform(size=ndim) until
+    loglikelihood(prior_transform(u)) > loglstar; one uniform vector event per draw."""
+    for nc in range(1, max_tries + 1):
+        u = stream.uniforms(ndim)
+        v = model.prior_transform(u)
+        logl = float(model.loglike(v))
+        if logl > loglstar:
+            return dict(u=u, v=v, logl=logl, ncall=nc, ticks=stream.tick)
+    raise RuntimeError("unitcube_chain: no point found")
+
+
 def unif_chain(loglstar, multi, model, stream, ndim, nonbounded=None,
                max_tries=10**7):
     """UniformBoundSampler.sample (:243-340) with a MultiEll/Ell-like bound

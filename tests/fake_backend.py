@@ -27,6 +27,8 @@ def _to_oracle_model(dm, prior_kind):
         p.update(mean=dm.like_vec0, ivar=dm.like_vec1, lnorm=dm.s[0])
     elif k == OL.LIKE_EGGBOX:
         p.update(tmax=dm.s[0], power=dm.s[1])
+    elif k == OL.LIKE_REGION2D:
+        p.update(shape=int(dm.s[0]))
     else:
         p.update(c1=dm.like_vec0, c2=dm.like_vec1, r=dm.s[0], w=dm.s[1])
     return OL.Model(dm.ndim, prior_kind, k, **p)
@@ -248,13 +250,17 @@ def _ns_bound():
 
 def ns_create(model, nlive, ndim, batch, sampler, steps, seed, chain0=0, ncdim=None, strict_contains=True,
               facc=0.5, dlogz=0.01, maxiter=None, maxcall=None, update_interval=1 << 62, dimflags=None,
-              dead_capacity=None, ctx=None):
+              dead_capacity=None, ctx=None, unit_cube_phase=False, first_min_ncall=0, first_min_eff=100., it0=0,
+              logl_max=None):
     assert dimflags is None, "fake backend: periodic/reflective not wired for ns rounds"
     _state['ns_cfg'] = dict(model=_models[model], batch=batch, sampler=('rwalk', 'rslice', 'slice', 'unif')[sampler],
                             steps=steps, seed=seed, chain0=chain0, facc=facc, dlogz=dlogz,
                             maxiter=maxiter if maxiter is not None else 1 << 62,
                             maxcall=maxcall if maxcall is not None else 1 << 62,
-                            update_interval=update_interval, strict=bool(strict_contains))
+                            update_interval=update_interval, strict=bool(strict_contains),
+                            unit_cube_phase=bool(unit_cube_phase), first_min_ncall=first_min_ncall,
+                            first_min_eff=first_min_eff, it0=it0,
+                            logl_max=np.inf if logl_max is None else logl_max, ncdim=int(ncdim or ndim))
 
 
 def ns_set_state(live_u, live_v, live_logl, logvol, logz, loglstar, ncall, scale, ctx=None):
@@ -263,19 +269,23 @@ def ns_set_state(live_u, live_v, live_logl, logvol, logz, loglstar, ncall, scale
     _state['ns'] = nsloop.BatchNS(c['model'], live_u, live_v, live_logl, c['batch'], c['sampler'], c['steps'],
                                   c['seed'], chain0=c['chain0'], facc=c['facc'], scale=scale, logvol=logvol,
                                   logz=logz, loglstar=loglstar, ncall=ncall, update_interval=c['update_interval'],
-                                  dlogz=c['dlogz'], maxiter=c['maxiter'], maxcall=c['maxcall'], bound=None)
+                                  dlogz=c['dlogz'], maxiter=c['maxiter'], maxcall=c['maxcall'], bound=None,
+                                  unit_cube_phase=c['unit_cube_phase'], first_min_ncall=c['first_min_ncall'],
+                                  first_min_eff=c['first_min_eff'], it0=c['it0'], logl_max=c['logl_max'])
 
 
 def ns_status(ctx=None):
     b = _state['ns']
     return dict(it=b.it, ncall=b.ncall, rounds=b.round, logz=b.logz, logvol=b.logvol, loglstar=b.loglstar,
                 lmax=float(b.live_logl.max()), delta_logz=b.delta_logz, scale=b.scale, done=b.done,
-                need_bound=b.need_bound, doubling=int(b.doubling), error=0, ncall_last_update=b.ncall_last_update)
+                need_bound=b.need_bound, doubling=int(b.doubling), error=b.error,
+                ncall_last_update=b.ncall_last_update)
 
 
 def ns_run(max_rounds, check_every=0, ctx=None):
     b = _state['ns']
-    b.bound = _ns_bound()
+    if b.phase == 1:
+        b.bound = _ns_bound()
     for _ in range(max_rounds):
         if not b.step():
             break
@@ -293,6 +303,44 @@ def ns_bound_updated(ctx=None):
 
 def ns_reserve_dead(capacity, ctx=None):
     pass
+
+
+def ns_update_bound(multi, enlarge=1.0, ctx=None):
+    """b2n_ns_update_bound: fit to the run's live points, enlarge (scalar branch: every ellipsoid shifted by the
+    same ln enlarge, bounding.py:487-489), make resident."""
+    import math
+    b = _state['ns']
+    pts = b.live_u[:, :_state['ns_cfg']['ncdim']]
+    if multi:
+        o = multi_decompose(pts)
+    else:
+        e = bounding_ellipsoid(pts)
+        o = dict(nells=1, ctrs=e['ctr'][None], covs=e['cov'][None], ams=e['am'][None], axes=e['axes'][None],
+                 axlens=e['axlens'][None], logvols=np.array([e['logvol']]))
+    for k in ('ctrs', 'covs', 'ams', 'axes', 'axlens', 'logvols'):
+        o[k] = np.array(o[k], dtype=float)
+    if enlarge != 1.0:
+        scale_to_logvol(o['covs'], o['ams'], o['axes'], o['axlens'], o['logvols'], o['logvols'] + math.log(enlarge))
+    bound_set(o['axes'], o['ctrs'], o['ams'], o['logvols'], ctx=ctx, key=('ns', len(_state.setdefault('ns_hist', []))))
+    _state['ns_hist'].append(1)
+    _state['ns_bound'] = o
+    from scipy.special import logsumexp
+    return o['nells'], float(logsumexp(o['logvols'])), 0
+
+
+def ns_get_bound(nells, ncdim, ctx=None):
+    o = _state['ns_bound']
+    return {k: o[k].copy() for k in ('ctrs', 'covs', 'ams', 'axes', 'axlens', 'logvols')}
+
+
+def unitcube_batch(model, nchain, ndim, loglstar, seed, chain0=0, ctx=None, peer=None):
+    m = _models[model]
+    Q, n = int(nchain), int(ndim)
+    o = dict(u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q), ncall=np.empty(Q, dtype=np.int32))
+    for i in range(Q):
+        r = OS.unitcube_chain(loglstar, m, philox.ChainStream(seed, chain0 + i), n)
+        o['u'][i], o['v'][i], o['logl'][i], o['ncall'][i] = r['u'], r['v'], r['logl'], r['ncall']
+    return o
 
 
 def ns_get_live(nlive, ndim, ctx=None, only_u=False):
@@ -313,7 +361,7 @@ def ns_destroy(ctx=None):
 
 
 FUNCS = ['ns_set_counters', 'ns_create', 'ns_set_state', 'ns_status', 'ns_run', 'ns_bound_updated', 'ns_reserve_dead',
-         'ns_get_live', 'ns_get_dead', 'ns_destroy', 'model_eval', 'membership', 'bounding_ellipsoid', 'multi_decompose', 'scale_to_logvol',
+         'ns_get_live', 'ns_get_dead', 'ns_destroy', 'ns_update_bound', 'ns_get_bound', 'unitcube_batch', 'model_eval', 'membership', 'bounding_ellipsoid', 'multi_decompose', 'scale_to_logvol',
          'bootstrap_expand', 'bound_set', 'ensure_resident', 'dimflags_from', 'rwalk_batch', 'rslice_batch', 'slice_batch',
          'unif_batch']
 

@@ -177,3 +177,79 @@ def test_candidate_path_equals_eigen_path(case, monkeypatch):
     assert mask[np.arange(len(pts)), fast['labels']].all()
     if case == 'clusters4000x25':
         assert fast['nells'] == 8
+
+
+# ---- improve_covar_mat on its own (b2n_improve_covar): the reference's test matrices (tests/test_ellipsoid.py:242-255)
+@pytest.mark.parametrize('name', ['zero', 'rank1', 'neg', 'good'])
+def test_improve_covar_mat_fixtures(golden, name):
+    """The repair ladder fed a RAW matrix: `zero` / `neg` take the failed == 2 identity blend
+    (bounding.py:1366-1371), `rank1` the eigenvalue clamp (:1362-1365), `good` passes untouched.  The clamp /
+    blend outputs are deterministic functions of the eigen-decomposition, compared with the reference's own
+    outputs (fixtures) at 1e-6 -- the bar of tests/test_oracle_golden.py for the oracle."""
+    g = golden['bounding']
+    good, cov, am, axes, warn = ops.improve_covar(g['icm_%s_in' % name])
+    assert good == bool(g['icm_%s_good' % name])
+    assert warn == 0
+    close(cov, g['icm_%s_cov' % name], rtol=1e-6)
+    assert np.all(np.linalg.eigvalsh(cov) > 0)
+    close(cov @ am, np.eye(cov.shape[0]), rtol=1e-3)
+    close(axes @ axes.T, cov, rtol=1e-6)
+
+
+def test_improve_covar_identity_fallback():
+    """A matrix no blend can repair (NaN: eigh(check_finite=False) returns NaN, every trial fails) ends in the
+    identity fallback with the reference's warning (bounding.py:1373-1378); the oracle agrees."""
+    import warnings
+    bad = np.full((5, 5), np.nan)
+    good, cov, am, axes, warn = ops.improve_covar(bad)
+    assert not good and warn & 1
+    for a in (cov, am, axes):
+        assert np.array_equal(a, np.eye(5))
+    try:                    # (LAPACK may refuse NaN input instead of returning NaN: the reference catches that, :1358)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            og, oc, oa, ox, _ = OB.improve_covar_mat(bad)
+        assert not og and np.array_equal(oc, np.eye(5))
+    except np.linalg.LinAlgError:
+        pass
+
+
+@pytest.mark.parametrize('n', [3, 40, 130])
+def test_improve_covar_vs_oracle_random(n):
+    """Singular, indefinite and ill-conditioned random matrices (n = 130: the sliced eigensolver's ladder)."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n))
+    S = A @ A.T / n
+    lam, V = np.linalg.eigh(S)
+    for kind in ('illcond', 'indefinite', 'singular'):
+        l2 = lam.copy()
+        if kind == 'illcond':
+            l2[0] = l2[-1] * 1e-15
+        elif kind == 'indefinite':
+            l2[:2] = -l2[:2]
+        else:
+            l2[:max(1, n // 4)] = 0.0
+        M = (V * l2) @ V.T
+        M = 0.5 * (M + M.T)
+        good, cov, am, axes, warn = ops.improve_covar(M)
+        og, oc, oa, ox, _ = OB.improve_covar_mat(M)
+        assert good == og and warn == 0
+        close(cov, oc, rtol=1e-6)
+        w = np.linalg.eigvalsh(cov)
+        assert w.min() > 0 and w.max() / w.min() < 1.05e11      # clamped at 10 max / 1e12 (:1362-1365)
+        close(cov @ am, np.eye(n), rtol=1e-3)
+
+
+def test_bounding_identical_and_collinear_points():
+    """Clouds that drive the ladder through `failed == 2` from the POINT side: identical points (zero covariance)
+    and collinear points (rank 1) -- bounding_ellipsoid must still return a bound containing every point."""
+    rng = np.random.default_rng(7)
+    same = np.tile(rng.random(6), (40, 1))
+    line = np.outer(np.linspace(0.2, 0.8, 60), np.ones(6)) + 0.1
+    for pts in (same, line):
+        o = ops.bounding_ellipsoid(pts)
+        d2 = ops.membership(pts, o['ctr'], o['am'], want_d2=True)[2]
+        assert d2.max() < 1 + 1e-9
+        assert np.all(np.linalg.eigvalsh(o['cov']) > 0)
+        e = OB.bounding_ellipsoid(pts)
+        assert abs(o['logvol'] - e.logvol) < 1e-5 * max(1.0, abs(e.logvol))

@@ -64,6 +64,16 @@ CASES = [
 CASES = [c if len(c) == 9 else c + ({},) for c in CASES]
 
 
+
+def _abort_at(k_stop):
+    """on_checkpoint callback that kills the run after its k_stop-th checkpoint (the reference's
+    tests/test_resume.py kills the process instead)."""
+    def cb(k):
+        if k >= k_stop:
+            raise KeyboardInterrupt('test: run aborted after checkpoint %d' % k)
+    return cb
+
+
 @pytest.mark.parametrize('kind,n,N,K,sampler,steps,two,rounds,extra', CASES)
 def test_rounds_match_oracle(kind, n, N, K, sampler, steps, two, rounds, extra):
     dm, om = _models(kind, n)
@@ -231,7 +241,7 @@ def test_checkpoint_resume_is_bit_identical(tmp_path, sample, kw):
     f = str(tmp_path / 'ckpt.pkl')
     s = mk()
     with pytest.raises(KeyboardInterrupt):
-        s.run_nested(loop='device', batch=20, checkpoint_file=f, checkpoint_every=0., _abort_after=4)
+        s.run_nested(loop='device', batch=20, checkpoint_file=f, checkpoint_every=0., on_checkpoint=_abort_at(4))
     del s
     r = nested.NestedSampler.restore(f)
     assert r._dev_snap['rounds'] > 0 and len(r._dev_snap['dead'][2]) > 0
@@ -241,3 +251,138 @@ def test_checkpoint_resume_is_bit_identical(tmp_path, sample, kw):
     assert np.array_equal(res.samples_u, ref.samples_u) and np.array_equal(res.samples, ref.samples)
     assert res.logz[-1] == ref.logz[-1] and res.logzerr[-1] == ref.logzerr[-1]
     assert abs(res.logz[-1] - m.logz_truth) < 4 * res.logzerr[-1] + 0.1
+
+
+# ---- round 2: the phase before the first bound, the device-side bound update, ties at the threshold -----------
+def test_unitcube_batch_matches_oracle():
+    """b2n_unitcube_batch == UnitCubeSampler.sample (internal_samplers.py:420-441) on the B2N stream: same draws,
+    same call counts (the oracle chain is pinned to the reference in tests/golden/chains.npz: uc_*)."""
+    from oracle import samplers as OS, philox
+    dm, om = _models('gauss', 6)
+    thr = -30.0
+    o = ops.unitcube_batch(dm.model_id(), 48, 6, thr, 77, chain0=9)
+    for i in (0, 5, 47):
+        c = OS.unitcube_chain(thr, om, philox.ChainStream(77, 9 + i), 6)
+        assert c['ncall'] == o['ncall'][i]
+        close(o['u'][i], c['u'], rtol=1e-15)
+        close(o['v'][i], c['v'], rtol=1e-12)
+        assert o['logl'][i] == pytest.approx(c['logl'], rel=1e-11)
+    assert np.all(o['logl'] > thr) and o['ncall'].max() > 1
+
+
+def test_unitcube_golden(golden):
+    """The reference's own UnitCubeSampler.sample replayed on the Philox stream (oracle/make_golden.py)."""
+    g = golden['chains']
+    dm = DL.gauss_test3d()
+    thr = float(g['uc_loglstar'])
+    o = ops.unitcube_batch(dm.model_id(), len(g['uc_u']), 3, thr, int(g['uc_seed']), chain0=int(g['uc_chain0']))
+    assert np.array_equal(o['ncall'], g['uc_ncall'])
+    close(o['u'], g['uc_u'], rtol=1e-15)
+    close(o['v'], g['uc_v'], rtol=1e-12)
+    np.testing.assert_allclose(o['logl'], g['uc_logl'], rtol=1e-11)
+
+
+def test_unitcube_phase_rounds_match_oracle():
+    """Rounds before the first bound (unit_cube_phase): prior draws at the round's threshold, dead records and
+    evidence as in the bounded rounds, need_bound = 4 exactly when the reference's first-update test fires
+    (ncall >= min_ncall and eff < min_eff, sampler.py:640-647)."""
+    dm, om = _models('gauss', 4)
+    rng = np.random.default_rng(8)
+    N, K, n = 60, 6, 4
+    u = rng.random((N, n))
+    v = om.prior_transform(u)
+    l = np.array([float(om.loglike(x)) for x in v])
+    kw = dict(unit_cube_phase=True, first_min_ncall=2 * N, first_min_eff=25.0, it0=1)
+    o = nsloop.BatchNS(om, u, v, l, K, 'rwalk', 9, 5, chain0=0, ncall=N, dlogz=1e-6, **kw)
+    ops.ns_create(dm.model_id(), N, n, K, 0, 9, 5, chain0=0, dlogz=1e-6, **kw)
+    try:
+        ops.ns_set_state(u, v, l, 0.0, -1e300, -1e300, N, 1.0)
+        nr = 0
+        while o.step():
+            nr += 1
+        assert o.need_bound == 4 and nr >= 3
+        st = ops.ns_run(nr + 5, 0)                       # the extra rounds must be no-ops
+        assert (st['rounds'], st['need_bound'], st['done'], st['it'], st['ncall']) == (nr, 4, 0, nr * K, o.ncall)
+        assert st['logz'] == pytest.approx(o.logz, rel=1e-11) and st['logvol'] == pytest.approx(o.logvol, abs=1e-13)
+        du, dv, dl, dlv, dnc = ops.ns_get_dead(0, st['it'], n)
+        ou, ov, ol, olv, onc = o.dead_arrays()
+        assert np.array_equal(du, ou) and np.array_equal(dl[:K], ol[:K]) and np.array_equal(dnc, onc)
+        np.testing.assert_allclose(dl, ol, rtol=1e-11)
+        lu, lv_, ll = ops.ns_get_live(N, n)
+        assert np.array_equal(np.sort(lu, axis=0), np.sort(o.live_u, axis=0))
+        # first bound on the device, then bounded rounds continue and still agree with the oracle
+        nells, lv, warn = ops.ns_update_bound(True, 1.25)
+        ops.ns_bound_updated()
+        e = OB.bounding_ellipsoid(o.live_u)
+        e.scale_to_logvol(e.logvol + math.log(1.25))
+        assert nells == 1 and lv == pytest.approx(e.logvol, abs=1e-8)
+        o.bound_updated(dict(ctrs=e.ctr[None], ams=e.am[None], axes=e.axes[None], logvols=np.array([e.logvol]), strict=True))
+        assert o.step()
+        st = ops.ns_run(1, 0)
+        assert (st['rounds'], st['ncall'], st['need_bound']) == (nr + 1, o.ncall, o.need_bound)
+        assert st['logz'] == pytest.approx(o.logz, rel=1e-10) and st['scale'] == pytest.approx(o.scale, rel=1e-10)
+    finally:
+        ops.ns_destroy()
+
+
+def test_start_rows_are_strictly_above_threshold():
+    """Ties at the threshold (sampler.py:471 requires live_logl > loglstar): live points that share the
+    K-th lowest logl are never start rows; when NO point is above the threshold the run ends with the reference's
+    plateau error (sampler.py:473-475)."""
+    dm, om = _models('gauss', 4)
+    rng = np.random.default_rng(2)
+    N, K, n = 40, 8, 4
+    u = 0.5 + 0.04 * rng.standard_normal((N, n))
+    v = om.prior_transform(u)
+    far = np.argsort([float(om.loglike(x)) for x in v])[:14]
+    u[far] = u[far[0]]                               # 14 clones: the 8 lowest and 6 survivors share one logl
+    v = om.prior_transform(u)
+    l = np.array([float(om.loglike(x)) for x in v])
+    order = np.argsort(l, kind='stable')
+    assert l[order[K - 1]] == l[order[K + 3]]        # the tie straddles the removal boundary
+    b = _bound([0.5 + 0.2 * rng.standard_normal((200, n))])
+    o = nsloop.BatchNS(om, u, v, l, K, 'rwalk', 6, 3, scale=0.3, logvol=-1.0, logz=-30.0, loglstar=float(l.min()) - 1, ncall=10,
+                       bound=b, dlogz=1e-9)
+    ops.bound_set(b['axes'], b['ctrs'], b['ams'], b['logvols'])
+    ops.ns_create(dm.model_id(), N, n, K, 0, 6, 3, dlogz=1e-9)
+    try:
+        ops.ns_set_state(u, v, l, -1.0, -30.0, float(l.min()) - 1, 10, 0.3)
+        assert o.step()
+        assert np.all(l[o.last['starts']] > o.last['thr'])
+        st = ops.ns_run(1, 0)
+        assert st['ncall'] == o.ncall and st['logz'] == pytest.approx(o.logz, rel=1e-10)
+        assert st['scale'] == pytest.approx(o.scale, rel=1e-10)          # same chains => same accept counts
+    finally:
+        ops.ns_destroy()
+    # plateau: every live point at the same logl except the K lowest -> nothing above the threshold
+    l2 = np.full(N, 1.0)
+    l2[:3] = 0.0
+    ops.ns_create(dm.model_id(), N, n, K, 0, 6, 3, dlogz=1e-9)
+    try:
+        ops.ns_set_state(u, v, l2, -1.0, -30.0, 0.0, 10, 0.3)
+        with pytest.raises(RuntimeError, match='plateau'):
+            ops.ns_run(1, 0)
+    finally:
+        ops.ns_destroy()
+
+
+@pytest.mark.parametrize('bound,sample,kw', [('multi', 'rwalk', dict(walks=15)), ('single', 'rslice', dict(slices=4)),
+                                              ('multi', 'rwalk', dict(walks=15, ncdim=4))])
+def test_device_bound_update_equals_host_path(bound, sample, kw):
+    """b2n_ns_update_bound (fit + enlarge + make resident without leaving the device) runs the same kernels on the
+    same live points as the host route (b2n_ns_get_live -> b2n_multi_decompose -> b2n_scale_to_logvol ->
+    b2n_bound_set): whole runs are bit-identical."""
+    out = []
+    for dev in (True, False):
+        s = nested.NestedSampler(DL.gauss_corr(6, 0.4, 5.0), nlive=200, bound=bound, sample=sample, seed=12, **kw)
+        s.device_bound = dev
+        r = s.run_nested(loop='device', batch=10, dlogz=0.5)
+        out.append((r, s))
+    (a, sa), (b, sb) = out
+    assert a.niter == b.niter and a.ncall == b.ncall and sa.nbound == sb.nbound > 3
+    assert np.array_equal(a.logl, b.logl) and np.array_equal(a.samples, b.samples)
+    assert a.logz[-1] == b.logz[-1]
+    assert [h[1] for h in sa.bound_history] == [h[1] for h in sb.bound_history]
+    np.testing.assert_allclose([h[2] for h in sa.bound_history], [h[2] for h in sb.bound_history], rtol=0, atol=1e-12)
+    close(sa.bound.ctrs, sb.bound.ctrs, rtol=1e-15)            # the host object is synchronised at the end
+    close(sa.bound.ams, sb.bound.ams, rtol=1e-15)

@@ -31,6 +31,16 @@ def _setup(N=60, K=12, sampler='rwalk', steps=8, seed=11, **kw):
     return m, b
 
 
+
+def _abort_at(k_stop):
+    """on_checkpoint callback that kills the run after its k_stop-th checkpoint (the reference's
+    tests/test_resume.py kills the process instead)."""
+    def cb(k):
+        if k >= k_stop:
+            raise KeyboardInterrupt('test: run aborted after checkpoint %d' % k)
+    return cb
+
+
 @pytest.mark.parametrize('sampler,steps', [('rwalk', 8), ('rslice', 3), ('slice', 1), ('unif', 1)])
 def test_round_invariants(sampler, steps):
     m, b = _setup(sampler=sampler, steps=steps)
@@ -93,8 +103,9 @@ def test_stop_flags():
 
 @pytest.mark.parametrize('sample,kw', [('rwalk', dict(walks=12)), ('rslice', dict(slices=3)), ('unif', dict(bootstrap=0))])
 def test_device_loop_host_logic_logz(fake_ops, sample, kw):
-    """run_nested(loop='device') end to end on the oracle backend: unit-cube phase on the host, hand-over at
-    the first bound, rounds + bound updates, results integration; logZ against the analytic truth."""
+    """run_nested(loop='device') end to end on the oracle backend: prior-draw rounds until the first bound is
+    due, rounds + bound updates (fitted where the live points lie: ns_update_bound), results integration; logZ
+    against the analytic truth."""
     m = DL.gauss_test3d()
     s = nested.NestedSampler(m, nlive=120, bound='multi', sample=sample, queue_size=40, seed=3, **kw)
     res = s.run_nested(dlogz=0.5, loop='device', batch=24)
@@ -108,10 +119,18 @@ def test_device_loop_host_logic_logz(fake_ops, sample, kw):
     assert np.all(np.abs(mean - np.linspace(-1, 1, 3)) < 0.4)
 
 
-def test_device_loop_rejects_unsupported(fake_ops):
+def test_device_loop_without_bound_and_rejections(fake_ops):
+    """bound='none' (the reference then samples the unit cube for the whole run, sampler.py:625-674): the device
+    rounds stay in the prior-draw phase; a multi-rank communicator is refused (replicas shard, rounds do not)."""
     m = DL.gauss_test3d()
+    s = nested.NestedSampler(m, nlive=50, bound='none', sample='unif', seed=4)
+    res = s.run_nested(loop='device', batch=5, dlogz=None, maxiter=60)
+    assert s.unit_cube_sampling and s.nbound == 1 and 60 <= res.niter < 60 + 5
+    assert np.all(np.diff(res.logl[:res.niter]) >= 0)
+    s2 = nested.NestedSampler(m, nlive=50, bound='multi', sample='rwalk', seed=4)
+    s2.comm = object()
     with pytest.raises(ValueError):
-        nested.NestedSampler(m, nlive=50, bound='none', sample='unif').run_nested(loop='device')
+        s2.run_nested(loop='device')
 
 
 @pytest.mark.parametrize('sample,kw', [('rwalk', dict(walks=12)), ('rslice', dict(slices=3))])
@@ -125,7 +144,7 @@ def test_checkpoint_resume_is_bit_identical(fake_ops, tmp_path, sample, kw):
     f = str(tmp_path / 'ckpt.pkl')
     s = mk()
     with pytest.raises(KeyboardInterrupt):
-        s.run_nested(dlogz=0.5, loop='device', batch=20, checkpoint_file=f, checkpoint_every=0., _abort_after=3)
+        s.run_nested(dlogz=0.5, loop='device', batch=20, checkpoint_file=f, checkpoint_every=0., on_checkpoint=_abort_at(3))
     del s
     r = nested.NestedSampler.restore(f)
     assert r._dev_snap is not None and r._dev_snap['rounds'] > 0 and len(r._dev_snap['dead'][2]) > 0
