@@ -29,6 +29,11 @@ import subprocess
 import sys
 import time
 
+# one BLAS / OpenMP thread per process BEFORE numpy loads: the CPU arm runs one process per core, and a 50 x 50
+# mat-vec must not fan out into a thread team in each of them
+for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+    os.environ.setdefault(_v, '1')
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -63,15 +68,59 @@ def make_state(ndim, nlive, seed=SEED):
     return np.ascontiguousarray(u), loglstar
 
 
+def config_block(cfg, Q):
+    """`config` of the JSON line -- the SAME dict in both arms (the driver compares them)."""
+    return {"workload": cfg['desc'], "queue_chains_per_gpu": int(Q), "walks": int(cfg['walks']),
+            "l2": "GPU arm: flushed (256 MB memset) between timed iterations"}
+
+
 def algorithmic_bytes(n):
     return 16 * n * n + 24 * n      # SURVEY.md section 8(d): B_rwalk(n), GAUSS_PREC likelihood
 
 
 def host_cores():
+    """Cores this process may use: the scheduler affinity mask, capped by the cgroup CPU quota (a container
+    lease can expose 128 CPUs in the mask and grant 8 of them in /sys/fs/cgroup/cpu.max)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as f:                       # cgroup v2
+            q, per = f.read().split()
+        if q != 'max':
+            quota = float(q) / float(per)
+    except Exception:
+        try:                                                            # cgroup v1
+            with open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us') as f:
+                q = float(f.read())
+            with open('/sys/fs/cgroup/cpu/cpu.cfs_period_us') as f:
+                per = float(f.read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(math.floor(quota + 0.5))))
+    return n
+
+
+def pick_process_count(cfg, pool_factory, cores, state, kind, seconds=1.5):
+    """The process count that actually maximises the CPU arm's throughput on THIS box.  A quota is not the only
+    way a lease is CPU-starved (round-1 BENCH: 128 CPUs visible, 7x one core delivered): time a short sample at
+    cores, cores/2, cores/4, ... and keep the best, so the reference arm is never handicapped by
+    oversubscription.  Returns (processes, {processes: proposals/s})."""
+    tried = {}
+    for p in sorted({cores, max(1, cores // 2), max(1, cores // 4), max(1, cores // 8)}, reverse=True):
+        pool = pool_factory(p)
+        try:
+            tried[p] = cpu_sample(cfg, seconds, pool, p, state, kind)[0]
+        finally:
+            if pool is not None:
+                pool.close()
+    best = max(tried, key=tried.get)
+    return best, tried
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -158,11 +207,13 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = host_cores()
+    visible = host_cores()
     os.environ['OMP_NUM_THREADS'] = '1'
-    pool = mp.get_context('fork').Pool(cores) if cores > 1 else None
     state = make_state(cfg['ndim'], cfg['nlive'])
     kind = reference_kind()
+    mk = lambda p: mp.get_context('fork').Pool(p) if p > 1 else None
+    cores, tried = pick_process_count(cfg, mk, visible, state, kind)
+    pool = mk(cores)
     per_step = float(os.environ.get('B2N_BENCH_CPU_SECONDS', max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))))
     for _ in range(args.warmup):
         cpu_sample(cfg, per_step, pool, cores, state, kind)
@@ -182,8 +233,11 @@ def run_reference(args, cfg):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "proposals/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": cfg['desc'], "queue_chains": nchains},
-            "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": cores, "kind": kind, "sample": sample},
+            "data": "synthetic", "config": config_block(cfg, args.chains or cfg['nlive']),
+            "run": {"chains_per_step": nchains, "processes": cores},
+            "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": cores, "kind": kind, "sample": sample,
+                             "cores_visible": visible,
+                             "process_count_scan": {str(k): round(v, 1) for k, v in sorted(tried.items())}},
             "e2e": {"value": val, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -229,6 +283,73 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def e2e_plugin(args, cfg, ctx, model, u_live, loglstar, scale, Q, walks):
+    """The plug-in path a dynesty user drives, timed per queue fill on HOST data (every H2D / D2H inside):
+      prepare_sampler : B200RWalkSampler.prepare_sampler(points=<list of Q rows>, axes=<Q axes handles>, seeds) +
+                        map(sample) -- what Sampler._fill_queue hands the sampler and gets back (Q SamplerReturn)
+      dynesty_fill_queue : the UNMODIFIED reference's own Sampler._fill_queue (sampler.py:676-717) with
+                        bound=B200MultiEllipsoid, sample=B200RWalkSampler, pool=B200Pool, queue_size=Q -- Q x
+                        propose_live (start row, get_random_axes, bound.contains) + prepare_sampler + map; only
+                        when the reference install (baseline/_ref) is present on this box."""
+    import importlib
+    from dynesty_b200 import _lib, samplers as S, bounding as B
+    from dynesty_b200.pool import B200Pool
+    n, steps = cfg['ndim'], max(3, args.steps)
+    ctx.set_pointer_mode(_lib.PTR_HOST)
+    out = {"unit": "proposals/s", "queue_size": Q, "walks": walks}
+    rng = np.random.default_rng(SEED)
+    bound = B.B200MultiEllipsoid(n, ctx=ctx)
+    bound.update(u_live, rstate=rng)
+    bound.scale_to_logvol(bound.logvol + math.log(1.25))
+    smp = S.B200RWalkSampler(model=model, ndim=n, ncdim=n, walks=walks, ctx=ctx)
+    smp.scale = scale
+
+    def fill():
+        starts = rng.integers(len(u_live), size=Q)
+        pts = [u_live[i] for i in starts]
+        axes = [bound.get_random_axes(rng) for _ in range(Q)]
+        seeds = np.random.SeedSequence(rng.integers(0, 2**63 - 1, size=4)).spawn(Q)
+        a = smp.prepare_sampler(loglstar=loglstar, points=pts, axes=axes, seeds=seeds, nested_sampler=None)
+        return list(map(smp.sample, a))
+    for _ in range(3):
+        fill()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fill()
+    dt = time.perf_counter() - t0
+    out["prepare_sampler"] = {"value": Q * walks * steps / dt, "ms_per_fill": 1e3 * dt / steps}
+    from oracle import refshim
+    if not refshim.available():
+        out["dynesty_fill_queue"] = None
+        return out
+    dynesty = refshim.import_reference()
+    import dynesty_b200._compat as c
+    importlib.reload(c)                      # the mirrors must subclass dynesty's own Bound / InternalSampler
+    importlib.reload(B)
+    importlib.reload(S)
+    v_live, l_live = model.evaluate(u_live, ctx=ctx)
+    ns = dynesty.NestedSampler(model.loglikelihood, model.prior_transform, n, nlive=len(u_live),
+                               bound=B.B200MultiEllipsoid(n, ctx=ctx),
+                               sample=S.B200RWalkSampler(model=model, walks=walks, ctx=ctx), pool=B200Pool(Q), queue_size=Q,
+                               live_points=[u_live, v_live, l_live], first_update={'min_ncall': 0, 'min_eff': 100.},
+                               rstate=np.random.default_rng(SEED),
+                               use_pool={'prior_transform': False, 'loglikelihood': False})
+    ns.update_bound_if_needed(loglstar, force=True)      # first bound: built on the GPU through the Bound seam
+    ns.internal_sampler.scale = scale
+    for _ in range(3):
+        ns.nqueue = 0
+        ns._fill_queue(loglstar)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ns.nqueue = 0
+        ns._fill_queue(loglstar)
+    dt = time.perf_counter() - t0
+    assert len(ns.queue) == Q and all(r.logl > loglstar for r in ns.queue[:50])
+    out["dynesty_fill_queue"] = {"value": Q * walks * steps / dt, "ms_per_fill": 1e3 * dt / steps,
+                                 "sampler": "unmodified dynesty.NestedSampler (baseline/_ref) with the B200 bound / sampler / pool"}
+    return out
+
+
 def run_b200(args, cfg):
     import torch
     import torch.distributed as dist
@@ -318,9 +439,13 @@ def run_b200(args, cfg):
         ctx.set_pointer_mode(_lib.PTR_HOST)
         c0 = state['chain']
         state['chain'] += Q * world
-        if fused:         # every rank's host receives the whole queue (replicated sampler state)
+        if fused:
+            # every rank's WINDOW (HBM) receives the whole queue inside the kernel; only rank 0 -- the owner of the
+            # nested-sampling bookkeeping -- copies it to its host, the other ranks' hosts receive nothing
             o = ops.rwalk_batch(mid, h_u0.numpy(), loglstar, state['scale'], walks, SEED, chain0=c0 + rank * Q,
-                                ell=ell, ctx=ctx, out=hg_np, peer=(rank * Q, world * Q))
+                                ell=ell, ctx=ctx, out=hg_np if rank == 0 else ops.NO_OUT, peer=(rank * Q, world * Q))
+            if rank != 0:
+                return None
             return {k: v[rank * Q:(rank + 1) * Q] for k, v in o.items()}
         o = ops.rwalk_batch(mid, h_u0.numpy(), loglstar, state['scale'], walks, SEED, chain0=c0 + rank * Q,
                             ell=ell, ctx=ctx, out=h_np)
@@ -351,13 +476,44 @@ def run_b200(args, cfg):
 
     # ---- warm-up: also tunes the proposal scale with the reference's rule (internal_samplers.py:491)
     clocks = ClockSampler(local)         # samples every 20 ms from here to the end of the timed regions
+    def sync_scale(acc_frac):
+        """rank 0 tunes the proposal scale (it alone sees the counters on its host); every rank uses its value"""
+        t = torch.tensor([acc_frac if acc_frac is not None else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.broadcast(t, 0)
+        return float(t[0])
+
     for _ in range(max(args.warmup, 3)):
         o = step_host()
-        acc, rej = int(o['n_accept'].sum()), int(o['n_reject'].sum())
-        state['scale'] *= math.exp((acc / (acc + rej) - 0.5) / n / 0.5)
+        fr = None if o is None else float(o['n_accept'].sum() / (o['n_accept'].sum() + o['n_reject'].sum()))
+        fr = sync_scale(fr)
+        state['scale'] *= math.exp((fr - 0.5) / n / 0.5)
     for _ in range(3):
         o = step_host()
-    accept_frac = float(o['n_accept'].sum() / (o['n_accept'].sum() + o['n_reject'].sum()))
+    accept_frac = sync_scale(None if o is None else float(o['n_accept'].sum() / (o['n_accept'].sum() + o['n_reject'].sum())))
+    # ---- N > 1: the gathered rows must BE what a single GPU computes for the same chain ids (rank 0 recomputes
+    #      the rows of the last rank locally and compares them with what arrived in its window)
+    gather_check = None
+    if fused:
+        starts_c, ell_c = propose()
+        np.take(u_live, starts_c, axis=0, out=h_u0.numpy(), mode='clip')
+        allq = [None] * world
+        dist.all_gather_object(allq, (h_u0.numpy().copy(), ell_c))
+        ctx.set_pointer_mode(_lib.PTR_HOST)
+        c0 = state['chain']
+        state['chain'] += Q * world
+        o = ops.rwalk_batch(mid, h_u0.numpy(), loglstar, state['scale'], walks, SEED, chain0=c0 + rank * Q, ell=ell_c,
+                            ctx=ctx, out=hg_np if rank == 0 else ops.NO_OUT, peer=(rank * Q, world * Q))
+        if rank == 0:
+            r = world - 1
+            got = {k: v[r * Q:(r + 1) * Q].copy() for k, v in o.items()}
+            loc = ops.rwalk_batch(mid, allq[r][0], loglstar, state['scale'], walks, SEED, chain0=c0 + r * Q, ell=allq[r][1],
+                                  ctx=ctx)
+            same = all(np.array_equal(got[k], loc[k]) for k in ('u', 'v', 'logl', 'n_accept', 'n_reject', 'ncall'))
+            gather_check = {"rows_of_rank": r, "bit_identical_to_local_recompute": bool(same)}
+            if not same:
+                raise SystemExit("gathered rows differ from a local recomputation")
+        dist.barrier()
     # clock ramp: ~0.7 s of the same kernel before timing, so that the nvidia-smi sampler has
     # samples under load.  N>1: a FIXED step count (every rank must issue the same exchanges).
     if world > 1:
@@ -402,6 +558,23 @@ def run_b200(args, cfg):
     if fused:
         ctx.peer_check()                     # raises if any in-kernel exchange ever timed out
 
+    # ---- e2e through the reference-facing PLUG-IN objects: what dynesty's Sampler._fill_queue costs per fill
+    plugin = None
+    if rank == 0:
+        try:
+            plugin = e2e_plugin(args, cfg, ctx, model, u_live, loglstar, state['scale'], Q, walks)
+        except Exception as e:                       # never lose the contract line over the extra measurement
+            plugin = {"error": repr(e)[:200]}
+    if world > 1:
+        dist.barrier()
+    # ---- measured FP64 ceilings of this GPU (the kernel's real bound; nothing quoted)
+    ctx.set_pointer_mode(_lib.PTR_HOST)
+    fp64 = None
+    if rank == 0:
+        fma_tf, fma_ms = ops.fp64_peak('fma', 20000, ctx=ctx)
+        mma_tf, mma_ms = ops.fp64_peak('mma', 20000, ctx=ctx)
+        fp64 = {"fma_tflops": fma_tf, "mma_tflops": mma_tf, "fma_ms": fma_ms, "mma_ms": mma_ms}
+
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -421,106 +594,138 @@ def run_b200(args, cfg):
             peak = 6650.0
         kms = float(np.mean(kern_ms))
         achieved = algorithmic_bytes(n) * Q * walks / (kms * 1e-3) / 1e9
-        traffic = None          # measured DRAM bytes per launch of this kernel (ncu --set full)
-        try:
+        traffic = None          # DRAM bytes per launch of this kernel from the committed ncu --set full capture
+        try:                    # (profiles/traffic.json: a constant of the capture, NOT measured in this run)
             with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
                 traffic = json.load(f)['rwalk_mma_kernel']['dram_bytes_per_launch'] if Q == 2000 else None
         except Exception:
             pass
+        flops_pp = 4 * n * n + 7 * n                      # flop per proposal
+        mma_flops_pp, fma_flops_pp = 4 * n * n, 7 * n     # the two contractions (DMMA) / everything else (DFMA)
+        ach_tf = flops_pp * Q * walks / (kms * 1e-3) / 1e12
+        # time the launch would take if both pipes ran at their measured ceilings back to back
+        t_floor_ms = 1e3 * Q * walks * (mma_flops_pp / (fp64["mma_tflops"] * 1e12) + fma_flops_pp / (fp64["fma_tflops"] * 1e12))
         line = {
             "metric": METRIC, "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg['desc'], "queue_chains_per_gpu": Q, "walks": walks, "nells": int(bound.nells),
-                       "accept_fraction": round(accept_frac, 3), "scale": round(state['scale'], 4),
-                       "l2": "flushed (256 MB memset) between timed iterations",
-                       "exchange": ("fused into the kernel: NVLink peer stores + in-kernel arrive/wait" if fused else
-                                    ("NCCL all-gather after the kernel" if world > 1 else "none (1 GPU)")),
-                       "bound_update_ms": round(bound_ms, 3), "bound_update_first_ms": round(bound_ms_first, 2)},
+            "config": config_block(cfg, Q),
+            "run": {"nells": int(bound.nells), "accept_fraction": round(accept_frac, 3), "scale": round(state['scale'], 4),
+                    "exchange": ("fused into the kernel: NVLink peer stores + in-kernel arrive/wait" if fused else
+                                 ("NCCL all-gather after the kernel" if world > 1 else "none (1 GPU)")),
+                    "bound_update_ms": round(bound_ms, 3), "bound_update_first_ms": round(bound_ms_first, 2)},
             "e2e": {"value": e2e, "unit": "proposals/s",
                     "h2d_bytes_per_step": Q * n * 8 + Q * 4 + 16 * (Q // 8 + 1),
                     "d2h_bytes_per_step": (world if fused else 1) * (2 * Q * n * 8 + Q * 8 + 3 * Q * 4),
-                    "bytes_are": "per rank"},
+                    "bytes_are": ("rank 0 (the owner of the sampler state receives the whole queue; the other ranks' hosts "
+                                  "receive nothing)" if fused else "per rank")},
             "gpu_launches": int(launches),
             "accepted_proposals_per_s": value * accept_frac,      # rwalk n_accept / wall
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch",
-                         "algorithmic_bytes_per_launch": algorithmic_bytes(n) * Q * walks,
-                         "kernel": "rwalk_mma_kernel<GAUSS_PREC, KT=13, 8 chains/CTA, ring 8>",
-                         "note": ("frac > 1: SURVEY 8(d)'s byte model counts both 20 KB matrices per proposal (no reuse); the "
-                                  "kernel keeps them in registers, so HBM is idle (traffic) and the kernel is latency-bound "
-                                  "at the problem's parallelism (DESIGN.md 9.1)"),
-                         "kernel_ms": kms, "algorithmic_bytes_per_proposal": algorithmic_bytes(n),
-                         "peak_source": peak_src},
-            # the byte model above assumes no reuse; the honest ceiling of this kernel is FP64 issue: SURVEY 8(d)'s
-            # 4n^2 + 7n flop per proposal against the chip's nominal FP64 tensor (DMMA) rate
-            "roofline_fp64": {"achieved_tflops": (4 * n * n + 7 * n) * Q * walks / (kms * 1e-3) / 1e12,
-                              "peak_tflops": 45.0, "peak_source": "nominal B200 FP64 tensor rate (blackwell_cuda_programming.md:52)",
-                              "frac": (4 * n * n + 7 * n) * Q * walks / (kms * 1e-3) / 45e12,
-                              "flops_per_proposal": 4 * n * n + 7 * n},
+            # The dominant kernel's two mat-vecs per proposal are FP64 tensor-core MMAs (mma.m8n8k4.f64) on
+            # register-resident matrices: its bound is the FP64 pipes, not HBM.  Both ceilings are MEASURED in
+            # this run by the library's own microbenchmark (b2n_fp64_peak: 16 independent chains per thread on
+            # every SM); `peak` is the measured FP64 MMA rate, which carries 97 % of the flops.
+            "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": fp64["mma_tflops"], "unit": "TFLOP/s",
+                         "frac": ach_tf / fp64["mma_tflops"], "traffic": traffic, "traffic_unit": "bytes/launch",
+                         "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel at this size; a "
+                                           "constant, not measured in this run)",
+                         "kernel": "rwalk_mma_kernel<GAUSS_PREC, KT=13, 8 chains/CTA, ring 8>", "kernel_ms": kms,
+                         "flops_per_proposal": flops_pp, "flops_per_launch": flops_pp * Q * walks,
+                         "peak_source": "measured in this run: FP64 mma.m8n8k4 rate of this GPU (b2n_fp64_peak kind 1)",
+                         "fp64_fma_peak_tflops": fp64["fma_tflops"], "fp64_mma_peak_tflops": fp64["mma_tflops"],
+                         "pipes_floor_ms": t_floor_ms, "frac_of_pipes_floor": t_floor_ms / kms,
+                         "note": ("MEASURED_PEAKS.json holds HBM and bf16 numbers only; this kernel computes in FP64, so the "
+                                  "FP64 ceilings are measured here.  pipes_floor_ms = launch time with both FP64 pipes at their "
+                                  "measured ceilings; the rest is the draw latency chain (Philox + Box-Muller) and barriers, "
+                                  "DESIGN.md 9.1")},
+            # SURVEY 8(d)'s no-reuse byte model (both 20 KB matrices charged to every proposal) against the measured
+            # HBM copy peak.  > 1 by construction for a kernel that keeps the matrices in registers: kept as the
+            # figure the survey defines, not as evidence.
+            "roofline_hbm_model": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                   "algorithmic_bytes_per_proposal": algorithmic_bytes(n),
+                                   "algorithmic_bytes_per_launch": algorithmic_bytes(n) * Q * walks, "peak_source": peak_src},
+            "e2e_plugin": plugin,
+            "gather_check": gather_check,
             "clocks": clk,
         }
     if world > 1:
         dist.barrier()
 
-    # ---- the second half of the metric: logZ error of full runs (not in the timed region)
-    if rank == 0 and world == 1 and args.logz:
-        from dynesty_b200 import nested
+    # ---- the second half of the metric, and throughput AT THE SAME OPERATING POINT: an ensemble of full C2 runs
+    #      (one per seed) with the rounds on the device at the batch that reproduces the reference's logZ
+    #      (nlive/40), the replicas running concurrently on every GPU (dynesty_b200/replicas.py).  The ensemble is
+    #      FIXED (args.ensemble runs) whatever --gpus is: its calls/s over N = 1, 2, 4, 8 is the strong-scaling curve.
+    if args.ensemble:
+        from dynesty_b200 import replicas
         ctx.set_timing(False)
-        ctx.set_stream(None)
         ctx.set_pointer_mode(_lib.PTR_HOST)
-        # Full C2 runs with the rounds paced on the device (b2n_ns_run): each round replaces the
-        # `batch` lowest live points.  rwalk chains at 50-D use proposal shapes estimated from the live
-        # points themselves and mix slowly along under-estimated directions (true of the reference too:
-        # its own logZ is +0.4 off the analytic value at nlive = 2000); the resulting bias grows with the
-        # fraction of the live set replaced per round, and batch = nlive/40 reproduces the reference's
-        # serial (queue_size = 1) result -- see DESIGN.md section 9.4.  The throughput steps above use
-        # Q = nlive chains per launch.
+        comm = None
+        if world > 1:
+            from dynesty_b200.dist import Comm
+            comm = Comm(dev)
         batch = args.logz_batch or max(1, nlive // 40)
-        runs = []
-        for k in range(args.logz):
-            t0 = time.perf_counter()
-            ns = nested.NestedSampler(model, nlive=nlive, bound=cfg['bound'], sample=cfg['sample'], walks=walks,
-                                      seed=SEED + k, ctx=ctx, queue_size=args.logz_queue)
-            res = ns.run_nested(loop='device', batch=batch)
-            wall = time.perf_counter() - t0
-            runs.append({"seed": SEED + k, "logz": float(res.logz[-1]), "logzerr": float(res.logzerr[-1]),
-                         "niter": int(res.niter), "ncall": int(res.ncall), "nbound": int(res.nbound),
-                         "rounds": int(ns.device_rounds), "wall_s": round(wall, 3),
-                         "rounds_s": round(ns.device_timing['rounds_s'], 3),
-                         "bound_s": round(ns.device_timing['bound_s'], 3)})
-        lz = np.array([r["logz"] for r in runs])
-        best = min(r["wall_s"] for r in runs)
-        line["logz"] = {"loop": "device rounds (b2n_ns_run), K-worst replacement", "batch": batch, "runs": runs,
-                        "logz_mean": float(lz.mean()), "logz_std": float(lz.std(ddof=1)) if len(lz) > 1 else None,
-                        "truth": model.logz_truth, "abs_err_mean": abs(float(lz.mean()) - model.logz_truth),
-                        "wall_s_best": best, "calls_per_s": runs[-1]["ncall"] / runs[-1]["wall_s"],
-                        "iterations_per_s": runs[-1]["niter"] / runs[-1]["wall_s"]}
-        try:        # the UNMODIFIED reference on this config (CPU, serial), recorded by scripts/ref_c2_run.py
-            with open(os.path.join(ROOT, 'profiles', 'ref_c2_rwalk_nlive2000.jsonl')) as f:
-                ref = [json.loads(x) for x in f if x.strip()]
-            rz = np.array([r["logz"] for r in ref])
-            line["logz"]["reference"] = {"logz_mean": float(rz.mean()), "logz_std": float(rz.std(ddof=1)), "runs": len(rz),
-                                         "wall_s_mean": float(np.mean([r["wall"] for r in ref])),
-                                         "source": "profiles/ref_c2_rwalk_nlive2000.jsonl (dynesty, 1 CPU core, build container)"}
-            line["logz"]["mean_minus_reference_mean"] = float(lz.mean() - rz.mean())
-        except Exception:
-            pass
+        seeds = list(range(SEED, SEED + args.ensemble))
+        rkw = dict(nlive=nlive, bound=cfg['bound'], sample=cfg['sample'], sampler_kwargs=dict(walks=walks), device=local,
+                   max_in_flight=args.in_flight, comm=comm, batch=batch)
+        replicas.run_replicas(model, seeds[:min(len(seeds), 2 * world)], **rkw)          # warm-up (allocations, clocks)
+        barrier()
+        t0 = time.perf_counter()
+        outs, _ = replicas.run_replicas(model, seeds, **rkw)
+        barrier()
+        tens = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tens, op=dist.ReduceOp.MAX)
+        ens_wall = float(tens[0])
+        if rank == 0:
+            summ = replicas.summarize(outs, ens_wall)
+            runs = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in o.items()} for o in outs]
+            line["full_runs"] = {
+                "what": ("%d full C2 nested-sampling runs (seeds %d..%d), device rounds (b2n_ns_run) with batch = %d, %d "
+                         "replicas in flight per GPU; proposals/s and logZ come from THE SAME runs" %
+                         (len(seeds), seeds[0], seeds[-1], batch, args.in_flight)),
+                "scaling": "strong (the ensemble is fixed; ranks take seeds[rank::world])",
+                "batch": batch, "replicas": len(seeds), "in_flight_per_gpu": args.in_flight, "n_gpus": world,
+                "wall_s": ens_wall, "proposals_per_s": summ["calls_per_s"], "calls_per_s": summ["calls_per_s"],
+                "iterations_per_s": summ["niter"] / ens_wall, "run_wall_s_mean": summ["run_wall_s_mean"],
+                "logz_mean": summ["logz_mean"], "logz_std": summ["logz_std"], "truth": model.logz_truth,
+                "abs_err_mean": abs(summ["logz_mean"] - model.logz_truth),
+                "runs": runs[:8], "logz_all": [round(o["logz"], 4) for o in outs]}
+            try:        # the UNMODIFIED reference on this config (CPU, serial), recorded by scripts/ref_c2_run.py
+                with open(os.path.join(ROOT, 'profiles', 'ref_c2_rwalk_nlive2000.jsonl')) as f:
+                    ref = [json.loads(x) for x in f if x.strip()]
+                rz = np.array([r["logz"] for r in ref])
+                line["full_runs"]["reference"] = {
+                    "logz_mean": float(rz.mean()), "logz_std": float(rz.std(ddof=1)), "runs": len(rz),
+                    "wall_s_mean": float(np.mean([r["wall"] for r in ref])),
+                    "calls_per_s_one_core": float(np.mean([r["ncall"] / r["wall"] for r in ref])),
+                    "source": "profiles/ref_c2_rwalk_nlive2000.jsonl (dynesty, 1 CPU core, build container)"}
+                line["full_runs"]["mean_minus_reference_mean"] = float(summ["logz_mean"] - rz.mean())
+            except Exception:
+                pass
+        if world == 1 and args.solo:          # latency of ONE run with nothing else on the GPU
+            o1, w1 = replicas.run_replicas(model, [SEED], **dict(rkw, max_in_flight=1))
+            line["full_runs"]["solo_run"] = {"wall_s": w1, "calls_per_s": o1[0]["ncall"] / w1, "logz": o1[0]["logz"],
+                                             "rounds_s": o1[0]["rounds_s"], "bound_s": o1[0]["bound_s"],
+                                             "nbound": o1[0]["nbound"], "rounds": o1[0]["rounds"]}
     # ---- CPU baseline on the host cores (rank 0, N=1 only), bounded sample
     if rank == 0 and world == 1 and args.cpu_baseline:
         import multiprocessing as mp
-        cores = host_cores()
+        visible = host_cores()
         os.environ['OMP_NUM_THREADS'] = '1'
-        pool = mp.get_context('fork').Pool(cores) if cores > 1 else None
         kind = reference_kind()
-        v, p, tsec, nch = cpu_sample(cfg, 12.0, pool, cores, (u_live, loglstar), kind)
+        mk = lambda p: mp.get_context('fork').Pool(p) if p > 1 else None
+        cores, tried = pick_process_count(cfg, mk, visible, (u_live, loglstar), kind, seconds=1.0)
+        pool = mk(cores)
+        v, p, tsec, nch = cpu_sample(cfg, 10.0, pool, cores, (u_live, loglstar), kind)
         if pool is not None:
             pool.close()
         v1, _, t1, nch1 = cpu_sample(cfg, 3.0, None, 1, (u_live, loglstar), kind)   # (i) one core, serial
         who = "dynesty RWalkSampler.sample (unmodified reference)" if kind == 'reference' else "oracle rwalk"
         line["cpu_baseline"] = {"value": v, "unit": "proposals/s", "cores": cores, "kind": kind,
                                 "sample": "%d %s chains x %d walks (%.1f s) on %d processes" % (nch, who, walks, tsec, cores),
-                                "one_core_value": v1, "one_core_sample": "%d chains (%.1f s), serial" % (nch1, t1)}
+                                "one_core_value": v1, "one_core_sample": "%d chains (%.1f s), serial" % (nch1, t1),
+                                "cores_visible": visible, "effective_cores": v / v1,
+                                "process_count_scan": {str(k): round(x, 1) for k, x in sorted(tried.items())}}
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     os.close(real_stdout)
@@ -539,8 +744,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--chains', type=int, default=0, help='chains per step per GPU (default nlive)')
-    ap.add_argument('--logz', type=int, default=8, help='number of full C2 nested-sampling runs (seeds) for logZ; 0 = none')
-    ap.add_argument('--logz-queue', type=int, default=200, help='queue_size of the host (unit-cube) phase of the logZ runs')
+    ap.add_argument('--ensemble', type=int, default=64, help='full C2 runs (seeds) of the logZ / same-operating-point block; 0 = none')
+    ap.add_argument('--in-flight', type=int, default=8, help='replicas in flight per GPU')
+    ap.add_argument('--solo', type=int, default=1, help='N=1: also time one run alone on the GPU')
     ap.add_argument('--logz-batch', type=int, default=0, help='points replaced per device round (default nlive/40)')
     ap.add_argument('--cpu-baseline', type=int, default=1)
     ap.add_argument('--ramp', type=float, default=0.7, help='seconds of untimed steps before timing (clock ramp; 0 under ncu)')

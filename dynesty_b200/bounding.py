@@ -101,6 +101,7 @@ class B200MultiEllipsoid(BoundBase):
     def __getstate__(self):
         d = self.__dict__.copy()
         d['_ctx'] = None
+        d.pop('_contains_cache', None)
         return d
 
     def __setstate__(self, d):
@@ -116,7 +117,8 @@ class B200MultiEllipsoid(BoundBase):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = v if k == '_ctx' else copy.deepcopy(v, memo)
+            if k != '_contains_cache':
+                new.__dict__[k] = v if k == '_ctx' else copy.deepcopy(v, memo)
         new.version = next(_version)
         return new
 
@@ -134,10 +136,52 @@ class B200MultiEllipsoid(BoundBase):
         self.version = next(_version)
 
     # -- Bound interface -----------------------------------------------------------------
+    # The reference's Sampler.propose_live asks ``bound.contains(u)`` once per queue slot (sampler.py:485), i.e.
+    # `queue_size` single-point queries per fill.  One launch + round trip per point would dominate a fill, so
+    # membership is computed IN BATCHES on the GPU and memoised per bound version: `update` prefetches the points
+    # it was fitted to (the live points -- the only start points there are), the samplers prefetch the end points
+    # of every queue they evolve (the live points of the future); ``contains`` is then a dictionary lookup and
+    # falls back to a one-point launch only for a point nobody announced.
+    def _cache(self, strict):
+        c = self.__dict__.get('_contains_cache')
+        if c is None or c['version'] != self.version or c['strict'] != strict:
+            pts = None if c is None else c.get('points')
+            c = dict(version=self.version, strict=strict, hit={}, points=None)
+            self.__dict__['_contains_cache'] = c
+            if pts is not None and pts.shape[1] == self.ndim:
+                self._prefetch(pts, strict)               # same points, new ellipsoids (e.g. after the enlarge)
+        return c
+
+    def _prefetch(self, x, strict=True):
+        x = np.ascontiguousarray(x, dtype=float)
+        if x.ndim != 2 or x.shape[1] != self.ndim or len(x) == 0:
+            return
+        c = self._cache(strict)
+        q = ops.membership(x, self.ctrs, self.ams, strict=strict, ctx=self.ctx)[1]
+        inside = (q > 0).tolist()
+        hit = c['hit']
+        if len(hit) > 8 * max(len(x), 4096):              # bounded memory: drop what was announced long ago
+            hit.clear()
+        for row, ok in zip(x, inside):
+            hit[row.tobytes()] = ok
+        c['points'] = x if c['points'] is None or len(x) >= len(c['points']) else c['points']
+
+    def prefetch_contains(self, x):
+        """Announce points whose membership will be asked for (batched on the GPU, memoised)."""
+        self._prefetch(np.asarray(x, dtype=float)[:, :self.ndim], self.__dict__.get('_strict', True))
+
+    def _contains_one(self, x, strict):
+        x = np.ascontiguousarray(x, dtype=float)
+        c = self._cache(strict)
+        r = c['hit'].get(x.tobytes())
+        if r is None:
+            r = bool(ops.membership(x[None], self.ctrs, self.ams, strict=strict, ctx=self.ctx)[1][0] > 0)
+            c['hit'][x.tobytes()] = r
+        return r
+
     def contains(self, x):
         """bounding.py:520-523 (strict <)."""
-        _, q = ops.membership(np.asarray(x, dtype=float)[None], self.ctrs, self.ams, strict=True, ctx=self.ctx)
-        return bool(q[0] > 0)
+        return self._contains_one(x, True)
 
     def contains_many(self, x):
         """Batched ``contains`` (one launch for a whole queue of start points)."""
@@ -233,6 +277,7 @@ class B200MultiEllipsoid(BoundBase):
         self.axes_all, self.axlens_all, self.logvol_ells = o['axes'], o['axlens'], o['logvols']
         self.labels = o['labels']
         self._refresh_logvol()
+        self.__dict__['_contains_cache'] = dict(version=-1, strict=True, hit={}, points=points)   # re-evaluated lazily
         if bootstrap > 0:
             expands = ops.bootstrap_expand(points, True, int(bootstrap), _seed_from(rstate), 0, ctx=self.ctx)
             expand = float(expands.max())
@@ -273,9 +318,11 @@ class B200Ellipsoid(BoundBase):
         pass
 
     def contains(self, x):
-        """bounding.py:302-305 (non-strict: distance <= 1)."""
-        return bool(ops.membership(np.asarray(x, dtype=float)[None], self._m.ctrs, self._m.ams,
-                                   strict=False, ctx=self._m.ctx)[1][0] > 0)
+        """bounding.py:302-305 (non-strict: distance <= 1); memoised like MultiEllipsoid.contains."""
+        return self._m._contains_one(x, False)
+
+    def prefetch_contains(self, x):
+        self._m._prefetch(np.asarray(x, dtype=float)[:, :self.ndim], False)
 
     def contains_many(self, x):
         return ops.membership(x, self._m.ctrs, self._m.ams, strict=False, ctx=self._m.ctx)[1] > 0
@@ -318,6 +365,7 @@ class B200Ellipsoid(BoundBase):
         m.axes_all, m.axlens_all = o['axes'][None], o['axlens'][None]
         m.logvol_ells = np.array([o['logvol']])
         m._refresh_logvol()
+        m.__dict__['_contains_cache'] = dict(version=-1, strict=False, hit={}, points=points)
         if bootstrap > 0:
             expands = ops.bootstrap_expand(points, False, int(bootstrap), _seed_from(rstate), 0, ctx=m.ctx)
             expand = float(expands.max())

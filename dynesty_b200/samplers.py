@@ -37,6 +37,16 @@ def _seed_of(seeds, fallback_rstate=None):
     return int(s) & (2**63 - 1)
 
 
+def _announce(axes, nested_sampler, u):
+    """The end points of a queue are the live points -- hence the ``bound.contains`` queries of
+    Sampler.propose_live (sampler.py:485) -- of the near future: evaluate their membership in one launch."""
+    b = getattr(nested_sampler, 'bound', None)
+    if b is None and len(axes) and isinstance(axes[0], TaggedAxes):
+        b = axes[0].bound
+    if b is not None and hasattr(b, 'prefetch_contains'):
+        b.prefetch_contains(u)
+
+
 class _Resident:
     """Keeps the device copy of the current bound's ellipsoids in sync.  Which bound is resident is
     recorded ONCE per context (``Context.resident_key``, set by ``ops.bound_set``), not per sampler:
@@ -122,6 +132,7 @@ class B200RWalkSampler(_B200Sampler):
         ell = self._res.ensure(axes, self._ctx)
         o = self.run_batch(loglstar, np.asarray(points), ell, _seed_of(seeds))
         self.last_batch = o
+        _announce(axes, nested_sampler, o['u'])
         sc = self.scale
         # (one .tolist() per array instead of a numpy scalar conversion per field: the list is built once per
         # queue fill and its cost, not the kernel's, is what dynesty sees per fill)
@@ -168,6 +179,7 @@ class _B200SliceBase(_B200Sampler):
         ell = self._res.ensure(axes, self._ctx)
         o = self.run_batch(loglstar, np.asarray(points), ell, _seed_of(seeds))
         self.last_batch = o
+        _announce(axes, nested_sampler, o['u'])
         ll, ncl = o['logl'].tolist(), o['ncall'].tolist()
         nes, ncs = o['n_expand'].tolist(), o['n_contract'].tolist()
         warns = ((o['flags'] & _lib.WARN_DOUBLING) != 0).tolist()

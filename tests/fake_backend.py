@@ -106,6 +106,12 @@ class FakeContext:
     device = 0
     resident_key = None
 
+    def __init__(self, device=0):
+        self.device = device
+
+    def close(self):
+        pass
+
 
 _fake_ctx = FakeContext()
 
@@ -371,6 +377,7 @@ def install(monkeypatch):
     _state.clear()          # no resident bound until the code under test uploads one
     _fake_ctx.resident_key = None
     monkeypatch.setattr(_lib, 'default_context', default_context)
+    monkeypatch.setattr(_lib, 'Context', lambda device=0: _fake_ctx)
     g = globals()
     for name in FUNCS:
         monkeypatch.setattr(ops, name, g[name])

@@ -170,3 +170,20 @@ def test_device_loop_single_bound_and_limits(fake_ops):
     s3 = nested.NestedSampler(m, nlive=100, bound='single', sample='rwalk', walks=10, queue_size=25, seed=5)
     r3 = s3.run_nested(dlogz=None, maxcall=6000, loop='device', batch=10, add_live=False)
     assert r3.ncall <= 100 + 6000 + 10 * 10 + 25 * 10
+
+
+def test_replicas_plumbing(fake_ops):
+    """dynesty_b200.replicas: one device-resident run per seed; a replica equals the same run done on its own
+    (the oracle backend has ONE device state, so the replicas run one at a time here; on the GPU every replica
+    owns a context and they run concurrently -- tests/test_gpu_replicas.py)."""
+    from dynesty_b200 import replicas
+    m = DL.gauss_test3d()
+    kw = dict(nlive=80, bound='multi', sample='rwalk', sampler_kwargs=dict(walks=10), max_in_flight=1, dlogz=0.5, batch=16)
+    outs, wall = replicas.run_replicas(m, [3, 4, 5], **kw)
+    assert [o['seed'] for o in outs] == [3, 4, 5] and wall > 0
+    s = nested.NestedSampler(m, nlive=80, bound='multi', sample='rwalk', walks=10, seed=4)
+    r = s.run_nested(loop='device', dlogz=0.5, batch=16)
+    assert outs[1]['logz'] == float(r.logz[-1]) and outs[1]['ncall'] == r.ncall
+    summ = replicas.summarize(outs, wall)
+    assert summ['replicas'] == 3 and summ['ncall'] == sum(o['ncall'] for o in outs)
+    assert abs(summ['logz_mean'] - 3 * (-np.log(20.))) < 1.0
