@@ -84,6 +84,9 @@ def test_c3_eggbox_logz_trajectory_vs_reference():
                                     add_live=False)
     lz = np.array([o['logz'] for o in outs])
     rz = np.array([r['logz_dead'] for r in ref])
-    # logZ of the dead points only after `maxiter` iterations: dominated by the volume shrinkage exp(-maxiter/nlive)
-    # common to both, plus the (nearly flat) likelihood values -> agreement to a few 1e-2 is expected
-    assert abs(lz.mean() - rz.mean()) < 0.1, (lz, rz)
+    # logZ of the dead points only after `maxiter` iterations = ln sum L_i w_i ~ 32 + ln(1 - X_end): the reference's
+    # three seeds agree to 4e-5.  A round removes its K points from a shrinking live set (ln X falls by
+    # ln((N-K+1)/(N+1)) per round, not K ln(N/(N+1))), so X_end = e^-10.5 here against e^-10.0 for the reference:
+    # a difference of 2e-5 in logZ.  Stated tolerance 1e-3.
+    assert abs(lz.mean() - rz.mean()) < 1e-3, (lz, rz)
+    assert all(o['niter'] == maxiter for o in outs)
