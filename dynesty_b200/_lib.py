@@ -67,6 +67,7 @@ SYMBOLS = {
     'b2n_set_stream': (C.c_int, [_P, _P]),
     'b2n_set_pointer_mode': (C.c_int, [_P, C.c_int]),
     'b2n_synchronize': (C.c_int, [_P]),
+    'b2n_set_chain_pack': (C.c_int, [_P, _I]),
     'b2n_strerror': (C.c_char_p, [C.c_int]),
     'b2n_last_error': (C.c_char_p, [_P]),
     'b2n_version': (C.c_char_p, []),
@@ -82,6 +83,10 @@ SYMBOLS = {
     'b2n_fp64_peak': (C.c_int, [_P, _I, _I, C.POINTER(_D), C.POINTER(_D)]),
     'b2n_scale_to_logvol': (C.c_int, [_P, _I, _I, _P, _P, _P, _P, _P, _P]),
     'b2n_bootstrap_expand': (C.c_int, [_P, _P, _L, _I, _I, _I, _U64, _U64, _P]),
+    'b2n_friends_update': (C.c_int, [_P, _P, _L, _I, _I, _I, _P, _I, _U64, _U64, _P, _P, _P, _P, _P, _P, _P]),
+    'b2n_friends_set': (C.c_int, [_P, _I, _P, _L, _I, _P, _P]),
+    'b2n_friends_overlap': (C.c_int, [_P, _P, _L, _I, _P]),
+    'b2n_friends_unif_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _P, _P, _P, _P, _P, _P]),
     'b2n_bound_set': (C.c_int, [_P, _I, _I, _P, _P, _P, _P]),
     'b2n_rwalk_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _I, _P, _P, _P, _P, _P, _P]),
     'b2n_rslice_batch': (C.c_int, [_P, C.POINTER(ChainArgs), _I, _I, _P, _P, _P, _P, _P, _P, _P]),
@@ -166,6 +171,7 @@ class Context:
         self.lib = load()
         self.serial = next(_ctx_serial)      # never reused, unlike id(): the key of per-context caches
         self.resident_key = None             # version token of the bound whose ellipsoids are resident (ops.bound_set)
+        self.friends_key = None              # same for the resident RadFriends / SupFriends bound (ops.friends_set)
         h = C.c_void_p()
         st = self.lib.b2n_init(int(device), C.byref(h))
         if st != OK:
@@ -202,6 +208,9 @@ class Context:
     def set_pointer_mode(self, mode):
         self.check(self.lib.b2n_set_pointer_mode(self.h, mode))
         self.mode = mode
+
+    def set_chain_pack(self, chains_per_cta):
+        self.check(self.lib.b2n_set_chain_pack(self.h, int(chains_per_cta)))
 
     def synchronize(self):
         self.check(self.lib.b2n_synchronize(self.h))

@@ -15,7 +15,7 @@ import numpy as np
 from . import ops, _lib
 from ._compat import BoundBase
 
-__all__ = ['B200Ellipsoid', 'B200MultiEllipsoid', 'TaggedAxes']
+__all__ = ['B200Ellipsoid', 'B200MultiEllipsoid', 'B200RadFriends', 'B200SupFriends', 'TaggedAxes']
 
 
 class TaggedAxes(np.ndarray):
@@ -377,3 +377,144 @@ class B200Ellipsoid(BoundBase):
     def unitcube_overlap(self, ndraws=10000, rstate=None):
         """bounding.py:336-343."""
         return self._m.unitcube_overlap(ndraws, rstate=rstate)
+
+
+class _B200Friends(BoundBase):
+    """``RadFriends`` / ``SupFriends`` (bounding.py:734-996 / 999-1263): one ball / cube of common shape around every
+    live point, built and queried on the GPU (csrc/b2n_friends.cu).  Attributes as in the reference: ``ctrs, cov, am,
+    axes, axes_inv, logvol, funit``; ``need_centers`` makes the Sampler hand over the live points before it samples
+    (sampler.py:479-482)."""
+    kind = None
+
+    def __init__(self, ndim, cov=None, ctx=None):
+        super().__init__(ndim)
+        self._ctx = ctx
+        self._device = getattr(ctx, 'device', None)
+        self.need_centers = True
+        self.ctrs = np.empty((0, ndim))
+        from scipy.special import gammaln
+        self._pref = (ndim * math.log(2.) + ndim * gammaln(1.5) - gammaln(ndim / 2. + 1)) if self.kind == 'balls' \
+            else ndim * math.log(2.)                                      # :761 / :1027
+        cov = np.identity(ndim) if cov is None else np.array(cov, dtype=float)
+        lam, vec = np.linalg.eigh(cov)        # (constructor only: the initial metric of a fresh object, :749-762)
+        self.cov = cov
+        self.am = (vec / lam) @ vec.T
+        self.axes = (vec * np.sqrt(lam)) @ vec.T
+        self.axes_inv = (vec / np.sqrt(lam)) @ vec.T
+        self.logvol = float(self._pref + 0.5 * np.log(lam).sum())
+        self.funit = 1
+        self.radius = 1.0
+        self.version = next(_version)
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d['_ctx'] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self.version = next(_version)
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = v if k == '_ctx' else copy.deepcopy(v, memo)
+        new.version = next(_version)
+        return new
+
+    @property
+    def ctx(self):
+        return _resolve_ctx(self._ctx, self._device)
+
+    # -- residency: (ctrs, axes, axes_inv) on the device.  `ctrs` is a plain attribute the reference's Sampler
+    #    re-assigns to its live-point array before every proposal (sampler.py:481) -- the SAME array object, mutated
+    #    in place as live points are replaced -- so it is uploaded afresh for every batched operation (N x n doubles).
+    def _resident(self):
+        c = self.ctx
+        ops.friends_set(self.kind, np.asarray(self.ctrs, dtype=float)[:, :self.ndim], self.axes, self.axes_inv, ctx=c,
+                        key=self.version)
+        return c
+
+    def make_resident(self, ctx=None):
+        """for the chain samplers: the common axes as a one-ellipsoid resident bound (get_random_axes)"""
+        ops.bound_set(self.axes[None], ctx=ctx if ctx is not None else self.ctx, key=self.version)
+
+    def scale_to_logvol(self, logvol):
+        """bounding.py:765-774 / 1031-1040."""
+        f = math.exp((float(logvol) - self.logvol) / self.ndim)
+        self.cov = self.cov * f**2
+        self.am = self.am / f**2
+        self.axes = self.axes * f
+        self.axes_inv = self.axes_inv / f
+        self.logvol = float(logvol)
+        self.version = next(_version)
+
+    def overlap(self, x):
+        return int(ops.friends_overlap(np.asarray(x, dtype=float)[None], ctx=self._resident())[0])
+
+    def overlap_many(self, x):
+        return ops.friends_overlap(x, ctx=self._resident())
+
+    def contains(self, x):
+        """bounding.py:792-795 / 1059-1062.  The Sampler asks this for its START points (sampler.py:485), which are
+        rows of `ctrs` themselves: a centre lies in its own ball / cube (its distance to itself is exactly 0), so a
+        query that IS a row of the centre array is answered without a launch; anything else goes to the GPU."""
+        x = np.asarray(x)
+        c = self.ctrs
+        if isinstance(c, np.ndarray) and len(c) and np.may_share_memory(x, c) and x.shape == (self.ndim,):
+            return True
+        return self.overlap(x) > 0
+
+    def contains_many(self, x):
+        return self.overlap_many(x) > 0
+
+    def samples(self, nsamples, rstate=None):
+        o = ops.friends_unif_batch(-1, nsamples, self.ndim, -np.inf, _seed_from(rstate), draw_only=True, ctx=self._resident())
+        return o['u']
+
+    def sample(self, rstate=None, return_q=False):
+        o = ops.friends_unif_batch(-1, 1, self.ndim, -np.inf, _seed_from(rstate), draw_only=True, mixture=return_q,
+                                   ctx=self._resident())
+        return (o['u'][0], int(o['ncall'][0])) if return_q else o['u'][0]
+
+    def monte_carlo_logvol(self, ndraws=10000, rstate=None, return_overlap=True):
+        """bounding.py:842-869 / 1110-1137."""
+        o = ops.friends_unif_batch(-1, ndraws, self.ndim, -np.inf, _seed_from(rstate), draw_only=True, mixture=True,
+                                   ctx=self._resident())
+        w = 1. / o['ncall']
+        logvol = math.log(w.sum() / ndraws * len(self.ctrs)) + self.logvol
+        if not return_overlap:
+            return logvol
+        x = o['u']
+        inside = np.all((x > 0) & (x < 1), axis=1)
+        return logvol, float((w * inside).sum() / w.sum())
+
+    def get_random_axes(self, rstate):
+        return TaggedAxes(self.axes, self, 0)
+
+    def random_ells(self, rstate, size):
+        return np.zeros(size, dtype=np.int32)
+
+    def update(self, points, rstate=None, bootstrap=0, pool=None, mc_integrate=False, use_clustering=True):
+        """bounding.py:874-958 / 1142-1226.  `pool` is ignored: the bootstrap realisations run on the GPU."""
+        points = np.ascontiguousarray(points, dtype=float)
+        o = ops.friends_update(points, self.kind, am_prev=self.am, use_clustering=use_clustering, nboot=int(bootstrap),
+                               seed=_seed_from(rstate) if bootstrap else 0, ctx=self.ctx)
+        self.cov, self.am, self.axes, self.axes_inv = o['cov'], o['am'], o['axes'], o['axes_inv']
+        self.logvol, self.radius, self.nclusters = o['logvol'], o['radius'], o['nclusters']
+        self.ctrs = points
+        self.version = next(_version)
+        if mc_integrate:
+            self.funit = self.monte_carlo_logvol(rstate=rstate, return_overlap=True)[1]
+
+
+class B200RadFriends(_B200Friends):
+    """``RadFriends`` (bounding.py:734-996): N-balls, Euclidean norm."""
+    kind = 'balls'
+
+
+class B200SupFriends(_B200Friends):
+    """``SupFriends`` (bounding.py:999-1263): N-cubes, Chebyshev norm."""
+    kind = 'cubes'

@@ -128,121 +128,7 @@ __global__ void cov_finalize_kernel(const NodeRef* __restrict__ refs, int n, con
     }
 }
 
-// ------------------------------------------------------------------ Jacobi eigensolver
-// round-robin pairing: m players (m even), round r in [0, m-1), slot k in [0, m/2)
-__device__ __forceinline__ void rr_pair(int m, int r, int k, int& p, int& q) {
-    int a, b;
-    if (k == 0) { a = m - 1; b = r; }
-    else {          // (r + k) mod (m-1), (r - k) mod (m-1) without integer division: r < m-1, k < m/2
-        a = r + k;
-        if (a >= m - 1) a -= m - 1;
-        b = r - k;
-        if (b < 0) b += m - 1;
-    }
-    p = min(a, b);
-    q = max(a, b);
-}
-
-__device__ double block_sum(double v, double* red) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) red[w] = v;
-    __syncthreads();
-    double t = 0.0;
-    for (int i = 0; i < nw; i++) t += red[i];
-    return t;
-}
-
-// In-place: A (n x n, ld) -> diagonal ; VT rows = eigenvectors.  Returns sweeps used.
-__device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* cc, double* ss, double* red) {
-    const int T = blockDim.x, tid = threadIdx.x;
-    const int m = (n + 1) & ~1, half = m >> 1;
-    int sweep = 0;
-    for (; sweep < 40; sweep++) {
-        double off = 0.0, dg = 0.0;
-        for (int e = tid; e < n * n; e += T) {
-            const int i = e / n, j = e - i * n;
-            const double a = A[(size_t)i * ld + j];
-            if (i == j) dg = fma(a, a, dg); else off = fma(a, a, off);
-        }
-        off = block_sum(off, red);
-        dg = block_sum(dg, red);
-        const double tot = off + dg;
-        if (!(tot < INFINITY) || tot == 0.0) break;      // NaN/Inf or all-zero matrix
-        // converged at the round-off floor of the off-diagonal mass (n^2 entries of size
-        // ~eps*||A||): the same absolute accuracy LAPACK's eigh delivers
-        if (off <= (double)n * (double)n * 2.5e-32 * tot) break;
-        // One round = m/2 disjoint rotations.  WARP k owns pair k: it derives the rotation from
-        // its own three matrix entries (warp-uniform, no staging / no barrier), rotates rows p,q of
-        // A and of V^T with its lanes across the columns; after one barrier the same warp rotates
-        // columns p,q of A with its lanes down the rows.  Two barriers per round.
-        const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
-        for (int r = 0; r < m - 1; r++) {
-            for (int k = warp; k < half; k += nw) {
-                int p, q;
-                rr_pair(m, r, k, p, q);
-                double c = 1.0, s = 0.0;
-                if (q < n) {
-                    const double app = A[(size_t)p * ld + p], aqq = A[(size_t)q * ld + q], apq = A[(size_t)p * ld + q];
-                    // skip test |apq| <= 1e-17 sqrt(|app aqq|) without a square root
-                    if (apq != 0.0 && apq * apq > 1e-34 * fabs(app * aqq)) {
-                        // t = tan(theta) = sgn(tau) / (|tau| + sqrt(tau^2 + 1)), tau = (aqq-app)/(2 apq),
-                        // rewritten as t = 2 apq / (d + sgn(d) h), h = hypot(d, 2 apq): one division and
-                        // two reciprocal square roots instead of three divisions and two square roots
-                        // (FP64 div/sqrt are ~350-cycle software sequences and sit on the critical path)
-                        const double d = aqq - app, b2 = 2.0 * apq;
-                        const double x = fma(d, d, b2 * b2);
-                        if (x > 1e-250 && x < 1e250) {
-                            const double h = x * rsqrt(x);
-                            const double t = b2 / (d + (d >= 0.0 ? h : -h));
-                            c = rsqrt(fma(t, t, 1.0));
-                            s = t * c;
-                        } else {        // out of the safe range of d^2: robust (slow) form
-                            const double tau = d / b2;
-                            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
-                            c = 1.0 / sqrt(fma(t, t, 1.0));
-                            s = t * c;
-                        }
-                    }
-                }
-                __syncwarp();                      // every lane has read app/aqq/apq before rows change
-                if (lane == 0) { cc[k] = c; ss[k] = s; }
-                if (s != 0.0) {
-                    double* Ap = A + (size_t)p * ld;
-                    double* Aq = A + (size_t)q * ld;
-                    double* Vp = VT + (size_t)p * ld;
-                    double* Vq = VT + (size_t)q * ld;
-                    for (int j = lane; j < n; j += 32) {
-                        double a = Ap[j], b = Aq[j];
-                        Ap[j] = c * a - s * b;
-                        Aq[j] = s * a + c * b;
-                        a = Vp[j];
-                        b = Vq[j];
-                        Vp[j] = c * a - s * b;
-                        Vq[j] = s * a + c * b;
-                    }
-                }
-            }
-            __syncthreads();
-            for (int k = warp; k < half; k += nw) {
-                const double s = ss[k];
-                if (s != 0.0) {
-                    int p, q;
-                    rr_pair(m, r, k, p, q);
-                    const double c = cc[k];
-                    for (int i = lane; i < n; i += 32) {
-                        const double a = A[(size_t)i * ld + p], b = A[(size_t)i * ld + q];
-                        A[(size_t)i * ld + p] = c * a - s * b;
-                        A[(size_t)i * ld + q] = s * a + c * b;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    return sweep;
-}
+#include "b2n_jacobi.cuh"
 
 // improve_covar_mat (bounding.py:1311-1384) for one node per CTA.
 // pass 0: input = covraw ; pass 1: input = current cov (after the pass-0 rescale).
@@ -908,6 +794,44 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
         }
     }
     stats = hs;
+    return B2N_OK;
+}
+
+// np.mean / np.cov(ddof=1) of one node (rows [0, count) of perm level 0): the moment kernels of b2n_process_nodes
+// without the eigen / fmax stages (used by b2n_friends.cu)
+int b2n_node_moments(BoundWork& w, int count) {
+    b2n_ctx* ctx = w.ctx;
+    const int n = w.n;
+    const size_t nn = (size_t)n * n;
+    NodeRef ref;
+    memset(&ref, 0, sizeof(ref));
+    ref.node = 0; ref.start = 0; ref.count = count; ref.level = 0; ref.slot0 = 0;
+    std::vector<JobL> jobs;
+    for (int a = 0; a < count; a += B2N_ROWS_PER_JOB) {
+        JobL j;
+        memset(&j, 0, sizeof(j));
+        j.node = 0; j.r0 = a; j.r1 = std::min(a + B2N_ROWS_PER_JOB, count); j.slot = (int)jobs.size(); j.level = 0;
+        jobs.push_back(j);
+    }
+    ref.nslots = (int)jobs.size();
+    const int njobs = (int)jobs.size();
+    const void *djobs, *drefs;
+    B2N_TRY(b2n_in_host(ctx, ctx->scratch4, jobs.data(), jobs.size() * sizeof(JobL), &djobs));
+    B2N_TRY(b2n_in_host(ctx, ctx->scratch5, &ref, sizeof(NodeRef), &drefs));
+    B2N_CUDA(ctx, ctx->scratch1.ensure((size_t)njobs * std::max(nn, (size_t)n) * sizeof(double)));
+    double* partial = ctx->scratch1.as<double>();
+    cudaStream_t st = ctx->stream;
+    colsum_partial_kernel<<<njobs, 256, (size_t)8 * n * sizeof(double), st>>>(w.P, w.perm, w.N, n, (const JobL*)djobs, partial);
+    B2N_LAUNCH_CHECK(ctx);
+    mean_finalize_kernel<<<1, 128, 0, st>>>((const NodeRef*)drefs, n, partial, w.na.mean);
+    B2N_LAUNCH_CHECK(ctx);
+    const int ntile = (n + B2N_TILE - 1) / B2N_TILE;
+    cov_partial_kernel<<<dim3(njobs, ntile * (ntile + 1) / 2), 256, 0, st>>>(w.P, w.perm, w.N, n, (const JobL*)djobs,
+                                                                            w.na.mean, partial, ntile);
+    B2N_LAUNCH_CHECK(ctx);
+    cov_finalize_kernel<<<dim3(1, (unsigned)std::min<size_t>((nn + 255) / 256, 64)), 256, 0, st>>>(
+        (const NodeRef*)drefs, n, partial, w.na.covraw);
+    B2N_LAUNCH_CHECK(ctx);
     return B2N_OK;
 }
 

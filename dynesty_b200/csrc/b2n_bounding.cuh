@@ -73,6 +73,8 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs, std::vecto
                       bool candidate = false);
 int b2n_emit_node(BoundWork& w, int node, int k, double* ctr, double* cov, double* am, double* axes, double* axlens);
 int b2n_init_identity_perm(BoundWork& w);
+// mean + sample covariance (ddof = 1) of node 0 = rows [0, count) of perm level 0 -> w.na.mean / w.na.covraw
+int b2n_node_moments(BoundWork& w, int count);
 int b2n_eig_sliced(BoundWork& w, const int* dlist, int pn, int pass, int retry_only, int* used);
 #endif
 

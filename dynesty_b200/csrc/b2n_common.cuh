@@ -110,6 +110,8 @@ struct b2n_ctx {
     PeerState peer;
     DynLaunch dyn;
     b2n_ns* ns = nullptr;
+    void* friends = nullptr;    // resident RadFriends / SupFriends bound (b2n_friends.cu)
+    int min_cpc = 1;            // b2n_set_chain_pack: at least this many chains per CTA (see include/b200nest.h)
     int bound_fast_skip = 0;    // b2n_multi_decompose: updates left to skip the Cholesky candidate path
     bool zc_enabled = false;    // chain entry points, host-pointer mode: pinned caller buffers are used in place
     // cached chain worklist of the single-ellipsoid case (identity order, equal CTAs): rebuilt only when
@@ -119,6 +121,7 @@ struct b2n_ctx {
     int wl_cpc = 0, wl_ncta = 0;
 };
 void b2n_ns_release(b2n_ctx* ctx);
+void b2n_friends_release(b2n_ctx* ctx);
 int b2n_bound_set_dev(b2n_ctx* ctx, int K, int nc, const double* dctrs, const double* dams, const double* daxes,
                       const double* h_logvols);
 

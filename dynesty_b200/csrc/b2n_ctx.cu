@@ -69,6 +69,7 @@ void b2n_free(b2n_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     b2n_peer_release(ctx);
     b2n_ns_release(ctx);
+    b2n_friends_release(ctx);
     for (void* p : ctx->model_allocs) cudaFree(p);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -94,6 +95,12 @@ int b2n_set_stream(b2n_ctx* ctx, void* s) {
 int b2n_set_pointer_mode(b2n_ctx* ctx, int mode) {
     if (!ctx || (mode != B2N_PTR_HOST && mode != B2N_PTR_DEVICE)) return B2N_ERR_ARG;
     ctx->ptr_mode = mode;
+    return B2N_OK;
+}
+
+int b2n_set_chain_pack(b2n_ctx* ctx, int32_t chains_per_cta) {
+    if (!ctx || chains_per_cta < 1) return B2N_ERR_ARG;
+    ctx->min_cpc = chains_per_cta;
     return B2N_OK;
 }
 

@@ -79,6 +79,10 @@ struct b2n_ns {
     std::vector<void*> allocs;
     void* dead_alloc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int phase = 1;                     // host copy of NsScalars::phase (transitions are host-mediated)
+    bool active = false;               // between b2n_ns_create and b2n_ns_destroy.  The device allocations OUTLIVE a run
+                                       // (released by b2n_free, or by a b2n_ns_create of another shape): cudaMalloc /
+                                       // cudaFree synchronise the whole device, which would stall every other replica
+                                       // running on this GPU (dynesty_b200/replicas.py) once per run
     // device copy of the bound built by b2n_ns_update_bound (Kmax ellipsoids of dimension nc)
     int Kmax = 0, bK = 0;
     double *bd_ctrs = nullptr, *bd_covs = nullptr, *bd_ams = nullptr, *bd_axes = nullptr, *bd_axlens = nullptr,
@@ -599,49 +603,51 @@ int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* c, int64_t dead_capacity) {
     int Npad = 2;
     while (Npad < c->nlive) Npad <<= 1;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
-    b2n_ns_release(ctx);
-    b2n_ns* ns = new b2n_ns();
+    const int64_t want_cap = std::max<int64_t>(dead_capacity, (int64_t)c->batch);
+    const bool reuse = ctx->ns && !ctx->ns->active && ctx->ns->d.N == c->nlive && ctx->ns->d.n == n &&
+                       ctx->ns->d.nc == c->ncdim && ctx->ns->d.K == c->batch;
+    if (!reuse) b2n_ns_release(ctx);
+    b2n_ns* ns = reuse ? ctx->ns : new b2n_ns();
     ctx->ns = ns;
     ns->cfg = *c;
+    ns->has_flags = false;
     if (c->dimflags) { ns->dimflags.assign(c->dimflags, c->dimflags + n); ns->has_flags = true; }
     ns->cfg.dimflags = nullptr;
     NsDev& d = ns->d;
-    memset(&d, 0, sizeof(d));
+    if (!reuse) memset(&d, 0, sizeof(d));
     d.N = c->nlive; d.n = n; d.nc = c->ncdim; d.K = c->batch; d.Kell = 1; d.strict = 1; d.sampler = c->sampler;
     d.Npad = Npad;
     d.Kpad = 2;
     while (d.Kpad < c->batch) d.Kpad <<= 1;
-    d.threads = B2N_NS_THREADS;     // (256 threads for small rounds measured 4 % slower: the loops are latency bound)
-    if (const char* e = getenv("B2N_NS_THREADS")) d.threads = atoi(e) >= 1024 ? 1024 : (atoi(e) >= 512 ? 512 : 256);
+    d.threads = B2N_NS_THREADS;
     d.dlogz = c->dlogz; d.facc = c->facc; d.maxiter = c->maxiter; d.maxcall = c->maxcall;
     d.update_interval = c->update_interval; d.seed = c->seed; d.chain0 = c->chain0;
     d.first_min_ncall = c->first_min_ncall; d.first_min_eff = c->first_min_eff; d.it0 = c->it0;
     d.logl_max = c->use_logl_max ? c->logl_max : (double)INFINITY;
     ns->phase = c->unit_cube_phase ? 0 : 1;
+    ns->bK = 0;
     const size_t N = d.N, K = d.K;
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.live_u, N * n * 8));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.live_v, N * n * 8));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.live_logl, N * 8));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.sc, sizeof(NsScalars)));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.dyn, sizeof(B2nDyn)));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.sidx, N * 4));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.skey, N * 8));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.tidx, N * 4));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.tkey, N * 8));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.u0, K * n * 8));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.order, K * 4));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.cta, (K + N + 8) * sizeof(int3)));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_u, K * n * 8));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_v, K * n * 8));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_logl, K * 8));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_i0, K * 4));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_i1, K * 4));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_ncall, K * 4));
-    B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_flags, K * 4));
-    B2N_CUDA(ctx, cudaMemset(d.o_i0, 0, K * 4));          // (the unit-cube sampler writes no counters)
-    B2N_CUDA(ctx, cudaMemset(d.o_i1, 0, K * 4));          // (the uniform sampler writes no second counter)
-    B2N_CUDA(ctx, cudaMemset(d.o_flags, 0, K * 4));
-    {   // device copy of the bound b2n_ns_update_bound builds (bounding.py:1493: a leaf has >= 2 ncdim points)
+    if (!reuse) {
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.live_u, N * n * 8));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.live_v, N * n * 8));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.live_logl, N * 8));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.sc, sizeof(NsScalars)));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.dyn, sizeof(B2nDyn)));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.sidx, N * 4));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.skey, N * 8));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.tidx, N * 4));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.tkey, N * 8));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.u0, K * n * 8));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.order, K * 4));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.cta, (K + N + 8) * sizeof(int3)));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_u, K * n * 8));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_v, K * n * 8));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_logl, K * 8));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_i0, K * 4));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_i1, K * 4));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_ncall, K * 4));
+        B2N_TRY(ns_alloc(ctx, ns, (void**)&d.o_flags, K * 4));
+        // device copy of the bound b2n_ns_update_bound builds (bounding.py:1493: a leaf has >= 2 ncdim points)
         const size_t nc = d.nc, nn = nc * nc;
         ns->Kmax = (int)std::max<size_t>(1, N / std::max<size_t>(2 * nc, 1));
         const size_t Km = ns->Kmax;
@@ -652,10 +658,18 @@ int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* c, int64_t dead_capacity) {
         B2N_TRY(ns_alloc(ctx, ns, (void**)&ns->bd_axlens, Km * nc * 8));
         B2N_TRY(ns_alloc(ctx, ns, (void**)&ns->bd_logvols, Km * 8));
         if (nc != (size_t)n) B2N_TRY(ns_alloc(ctx, ns, (void**)&ns->bd_points, N * nc * 8));
+        B2N_TRY(ns_alloc_dead(ctx, ns, want_cap));
+    } else if (ns->dead_cap < want_cap) {
+        for (void*& pp : ns->dead_alloc) { if (pp) cudaFree(pp); pp = nullptr; }     // (nothing to keep from the last run)
+        B2N_TRY(ns_alloc_dead(ctx, ns, want_cap));
     }
-    B2N_CUDA(ctx, cudaMemset(d.sc, 0, sizeof(NsScalars)));
-    B2N_CUDA(ctx, cudaMemset(d.dyn, 0, sizeof(B2nDyn)));
-    B2N_TRY(ns_alloc_dead(ctx, ns, std::max<int64_t>(dead_capacity, (int64_t)K)));
+    cudaStream_t st = ctx->stream;      // stream-ordered clears (no device-wide synchronisation)
+    B2N_CUDA(ctx, cudaMemsetAsync(d.o_i0, 0, K * 4, st));          // (the unit-cube sampler writes no counters)
+    B2N_CUDA(ctx, cudaMemsetAsync(d.o_i1, 0, K * 4, st));          // (the uniform sampler writes no second counter)
+    B2N_CUDA(ctx, cudaMemsetAsync(d.o_flags, 0, K * 4, st));
+    B2N_CUDA(ctx, cudaMemsetAsync(d.sc, 0, sizeof(NsScalars), st));
+    B2N_CUDA(ctx, cudaMemsetAsync(d.dyn, 0, sizeof(B2nDyn), st));
+    ns->active = true;
     return B2N_OK;
 }
 
@@ -663,13 +677,13 @@ int b2n_ns_destroy(b2n_ctx* ctx) {
     if (!ctx) return B2N_ERR_ARG;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    b2n_ns_release(ctx);
+    if (ctx->ns) ctx->ns->active = false;          // allocations are kept for the next run of the same shape
     return B2N_OK;
 }
 
 int b2n_ns_set_state(b2n_ctx* ctx, const double* live_u, const double* live_v, const double* live_logl,
                      double logvol, double logz, double loglstar, int64_t it, int64_t ncall, double scale) {
-    if (!ctx || !ctx->ns || !live_u || !live_v || !live_logl) return B2N_ERR_ARG;
+    if (!ctx || !ctx->ns || !ctx->ns->active || !live_u || !live_v || !live_logl) return B2N_ERR_ARG;
     b2n_ns* ns = ctx->ns;
     NsDev& d = ns->d;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -711,13 +725,13 @@ static int ns_status(b2n_ctx* ctx, b2n_ns_status* out) {
 }
 
 int b2n_ns_status_get(b2n_ctx* ctx, b2n_ns_status* out) {
-    if (!ctx || !ctx->ns || !out) return B2N_ERR_ARG;
+    if (!ctx || !ctx->ns || !ctx->ns->active || !out) return B2N_ERR_ARG;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
     return ns_status(ctx, out);
 }
 
 int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_status* out) {
-    if (!ctx || !ctx->ns || max_rounds < 0) return B2N_ERR_ARG;
+    if (!ctx || !ctx->ns || !ctx->ns->active || max_rounds < 0) return B2N_ERR_ARG;
     b2n_ns* ns = ctx->ns;
     NsDev& d = ns->d;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -772,7 +786,7 @@ __global__ void ns_set_counters_kernel(NsScalars* sc, long long rounds, long lon
 }
 
 int b2n_ns_set_counters(b2n_ctx* ctx, int64_t rounds, int64_t ncall_last_update, int32_t doubling) {
-    if (!ctx || !ctx->ns || rounds < 0) return B2N_ERR_ARG;
+    if (!ctx || !ctx->ns || !ctx->ns->active || rounds < 0) return B2N_ERR_ARG;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
     ns_set_counters_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ns->d.sc, rounds, ncall_last_update, doubling);
     B2N_LAUNCH_CHECK(ctx);
@@ -780,7 +794,7 @@ int b2n_ns_set_counters(b2n_ctx* ctx, int64_t rounds, int64_t ncall_last_update,
 }
 
 int b2n_ns_bound_updated(b2n_ctx* ctx) {
-    if (!ctx || !ctx->ns) return B2N_ERR_ARG;
+    if (!ctx || !ctx->ns || !ctx->ns->active) return B2N_ERR_ARG;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
     ns_clear_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ns->d.sc, ctx->ns->d.dyn, 1);
     B2N_LAUNCH_CHECK(ctx);
@@ -789,7 +803,7 @@ int b2n_ns_bound_updated(b2n_ctx* ctx) {
 }
 
 int b2n_ns_update_bound(b2n_ctx* ctx, int32_t multi, double enlarge, int32_t* nells, double* logvol, uint32_t* warn) {
-    if (!ctx || !ctx->ns || !(enlarge > 0.0)) return B2N_ERR_ARG;
+    if (!ctx || !ctx->ns || !ctx->ns->active || !(enlarge > 0.0)) return B2N_ERR_ARG;
     b2n_ns* ns = ctx->ns;
     NsDev& d = ns->d;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -820,8 +834,18 @@ int b2n_ns_update_bound(b2n_ctx* ctx, int32_t multi, double enlarge, int32_t* ne
     if (enlarge != 1.0) {
         // sampler.py:506-508 -> scalar branch of MultiEllipsoid.scale_to_logvol (bounding.py:487-489): every
         // ellipsoid is shifted by the same ln(enlarge)
+        // (the targets are formed with the host classes' arithmetic, so that this entry and the host route --
+        //  B200MultiEllipsoid.scale_to_logvol(logvol + ln enlarge) -- are bit-identical: (L + x) - L != x)
         std::vector<double> tg(K);
-        for (int k = 0; k < K; k++) tg[k] = lv[k] + log(enlarge);
+        if (multi) {
+            double hi = -INFINITY, se = 0.0;
+            for (double x : lv) hi = std::max(hi, x);
+            for (double x : lv) se += exp(x - hi);
+            const double L = hi + log(se), T = L + log(enlarge);
+            for (int k = 0; k < K; k++) tg[k] = lv[k] + (T - L);
+        } else {
+            tg[0] = lv[0] + log(enlarge);
+        }
         ctx->ptr_mode = B2N_PTR_DEVICE;
         st = b2n_scale_to_logvol(ctx, K, nc, ns->bd_covs, ns->bd_ams, ns->bd_axes, ns->bd_axlens, ns->bd_logvols, tg.data());
         ctx->ptr_mode = mode;
@@ -845,7 +869,7 @@ int b2n_ns_update_bound(b2n_ctx* ctx, int32_t multi, double enlarge, int32_t* ne
 
 int b2n_ns_get_bound(b2n_ctx* ctx, int32_t max_ells, double* ctrs, double* covs, double* ams, double* axes,
                      double* axlens, double* logvols) {
-    if (!ctx || !ctx->ns) return B2N_ERR_ARG;
+    if (!ctx || !ctx->ns || !ctx->ns->active) return B2N_ERR_ARG;
     b2n_ns* ns = ctx->ns;
     if (ns->bK < 1 || max_ells < ns->bK) return b2n_fail(ctx, B2N_ERR_ARG, "b2n_ns_get_bound: no device-built bound / max_ells too small");
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -861,7 +885,7 @@ int b2n_ns_get_bound(b2n_ctx* ctx, int32_t max_ells, double* ctrs, double* covs,
 }
 
 int b2n_ns_reserve_dead(b2n_ctx* ctx, int64_t capacity) {
-    if (!ctx || !ctx->ns) return B2N_ERR_ARG;
+    if (!ctx || !ctx->ns || !ctx->ns->active) return B2N_ERR_ARG;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
     if (capacity > ctx->ns->dead_cap) B2N_TRY(ns_alloc_dead(ctx, ctx->ns, capacity));
     ns_clear_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ns->d.sc, ctx->ns->d.dyn, 0);   // clears need_bound == 3
@@ -870,7 +894,7 @@ int b2n_ns_reserve_dead(b2n_ctx* ctx, int64_t capacity) {
 }
 
 int b2n_ns_get_live(b2n_ctx* ctx, double* live_u, double* live_v, double* live_logl) {
-    if (!ctx || !ctx->ns) return B2N_ERR_ARG;
+    if (!ctx || !ctx->ns || !ctx->ns->active) return B2N_ERR_ARG;
     NsDev& d = ctx->ns->d;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
     B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -673,7 +673,7 @@ int b2n_worklist_dev(b2n_ctx* ctx, int64_t Q, const int32_t* ell, int K, int cha
 void b2n_chain_grid(const b2n_ctx* ctx, int64_t Q, int max_warps, int& chains_per_cta, int& warps) {
     const int64_t sms = ctx->sm_count;
     const int64_t ctas = (Q <= 16 * sms) ? sms : 2 * sms;
-    chains_per_cta = (int)std::max<int64_t>(1, (Q + ctas - 1) / ctas);
+    chains_per_cta = (int)std::max<int64_t>(std::min(ctx->min_cpc, 16), (Q + ctas - 1) / ctas);
     warps = std::max(1, std::min(max_warps, std::min(16, chains_per_cta)));
 }
 
@@ -725,7 +725,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     size_t mma_smem = 0;
     if (use_mma) {
         const int ctas = 2 * ctx->sm_count;                 // 8-chain CTAs, two resident per SM
-        chains_per_cta = (int)std::max<int64_t>(1, (Q + ctas - 1) / ctas);
+        chains_per_cta = (int)std::max<int64_t>(std::min(ctx->min_cpc, 8), (Q + ctas - 1) / ctas);
         warps = 8;
         const int RS = 8 * ((4 * KT + 7) / 8);
         const int XS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16)), YS = RS + 2;
@@ -744,7 +744,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
             use_mmas = true;
             mma_smem = need;
             const int ctas = ctx->sm_count;
-            chains_per_cta = (int)std::max<int64_t>(1, (Q + ctas - 1) / ctas);
+            chains_per_cta = (int)std::max<int64_t>(std::min(ctx->min_cpc, 16), (Q + ctas - 1) / ctas);
             warps = 16;
         }
     }

@@ -117,10 +117,14 @@ class NestedSampler:
             bound = B.B200MultiEllipsoid(self.ncdim, ctx=ctx)
         elif bound == 'single':
             bound = B.B200Ellipsoid(self.ncdim, ctx=ctx)
+        elif bound in ('balls', 'cubes'):
+            if self.ncdim != n:
+                raise ValueError('ncdim unsupported for the friends bounds')
+            bound = (B.B200RadFriends if bound == 'balls' else B.B200SupFriends)(n, ctx=ctx)
         elif bound == 'none':
             bound = None
         elif isinstance(bound, str):
-            raise ValueError("Unknown bounding method: %s (B200 path: none/single/multi)" % bound)
+            raise ValueError("Unknown bounding method: %s (B200 path: none/single/multi/balls/cubes)" % bound)
         self.bound_next = bound
         self.bound = None
         self.unit_cube_sampling = True
@@ -206,6 +210,8 @@ class NestedSampler:
 
     def update_bound(self, subset=slice(None)):
         """sampler.py:493-510."""
+        if getattr(self.bound, 'need_centers', False):
+            self.bound.ctrs = self.live_u
         self.bound.update(self.live_u[subset, :self.ncdim], rstate=self.rstate, bootstrap=self.bound_bootstrap)
         if self.bound_enlarge != 1.:
             self.bound.scale_to_logvol(self.bound.logvol + math.log(self.bound_enlarge))
@@ -263,6 +269,8 @@ class NestedSampler:
         Q = self.queue_size
         c0 = self.chain_counter
         self.chain_counter += Q
+        if not self.unit_cube_sampling and getattr(self.bound, 'need_centers', False):
+            self.bound.ctrs = self.live_u                                  # sampler.py:479-482
         if self.unit_cube_sampling:
             # UnitCubeSampler (internal_samplers.py:343-441): u ~ U(0,1)^n, one call each
             u = self.rstate.random((Q, self.ndim))
@@ -331,7 +339,7 @@ class NestedSampler:
         c.resident_key = m.version                     # these very ellipsoids ARE the resident bound
 
     def _device_rounds(self, logz, logvol, loglstar, dlogz, maxiter, maxcall, batch, checkpoint_file=None,
-                       checkpoint_every=0.0, snap=None, on_checkpoint=None):
+                       checkpoint_every=0.0, snap=None, on_checkpoint=None, keep_samples=True):
         """Run (or continue) with ``b2n_ns_run`` (include/b200nest.h): K-worst replacement rounds paced on the
         device -- first with prior draws (the phase before the first bound, sampler.py:407-409), then with the
         inner sampler against the resident bound.  The host only reacts to the device's flags: (re)build the bound
@@ -464,7 +472,7 @@ class NestedSampler:
                 if dev_nells:
                     self._pull_device_bound(dev_nells)
             self.live_u, self.live_v, self.live_logl = ops.ns_get_live(N, n, ctx=self.ctx)
-            new = ops.ns_get_dead(saved_it, st['it'] - saved_it, n, ctx=self.ctx)
+            new = ops.ns_get_dead(saved_it, st['it'] - saved_it, n, ctx=self.ctx, positions=keep_samples)
             out = tuple(np.concatenate([a, b]) for a, b in zip(prev, new))
             self.chain_counter = chain_base + rounds * K
             self.nbatches += rounds - (snap['rounds'] if snap is not None else 0)
@@ -478,7 +486,8 @@ class NestedSampler:
 
     # ------------------------------------------------------------------ main loop
     def run_nested(self, dlogz=None, maxiter=None, maxcall=None, add_live=True, loop='host', batch=None,
-                   checkpoint_file=None, checkpoint_every=60., resume=False, on_checkpoint=None):
+                   checkpoint_file=None, checkpoint_every=60., resume=False, on_checkpoint=None, device_init=True,
+                   keep_samples=True):
         """sampler.py:1214-1356 / 1040-1212 (no plateau mode: continuous likelihoods).
 
         loop='host'   : the reference's semantics -- one worst point per iteration, replacements
@@ -490,7 +499,12 @@ class NestedSampler:
                         No stale-threshold filter, hence no selection bias for correlated chains
                         (DESIGN.md 9.4), no host round trip per iteration.  batch defaults to
                         nlive // 40 (rwalk) or nlive // 10 (slices).
-        on_checkpoint : callable(k) invoked after the k-th checkpoint has been written."""
+        on_checkpoint : callable(k) invoked after the k-th checkpoint has been written.
+        keep_samples  : loop='device' only.  False = the positions of the dead points are NOT brought back from the
+                        device (results.samples / samples_u are then empty; logz, logzerr, logl, logvol, logwt and the
+                        call counts are complete): for ensembles that only want evidences.
+        device_init   : False = the phase before the first bound runs in the host loop (queue of prior draws
+                        evaluated on the GPU) and the device takes over when the first bound exists."""
         if resume:
             return self._resume(checkpoint_file, checkpoint_every)
         if loop not in ('host', 'device'):
@@ -524,7 +538,8 @@ class NestedSampler:
             delta_logz = _logaddexp(0.0, lmax + logvol - logz)
             if it > maxiter or self.ncall - ncall0 > maxcall:
                 break
-            if loop == 'device' and (self._q is None or self._qpos >= len(self._ql)):
+            if loop == 'device' and (self._q is None or self._qpos >= len(self._ql)) and \
+                    (device_init or not self.unit_cube_sampling):
                 hand_over = True                                    # (queue drained): the device takes over
                 break
             if dlogz is not None and delta_logz < dlogz:
@@ -583,7 +598,8 @@ class NestedSampler:
                                    maxcall=ncall0 + maxcall if maxcall < (1 << 61) else None)
             dev = self._device_rounds(logz, logvol, loglstar, dlogz, self._host_part['maxiter'],
                                       self._host_part['maxcall'], batch, checkpoint_file=checkpoint_file,
-                                      checkpoint_every=checkpoint_every, on_checkpoint=on_checkpoint)
+                                      checkpoint_every=checkpoint_every, on_checkpoint=on_checkpoint,
+                                      keep_samples=keep_samples or checkpoint_file is not None)
             return self._finalize(su, sv, logl, logvols, nc_all, dev, add_live)
         return self._finalize(su, sv, logl, logvols, nc_all, None, add_live)
 
@@ -601,10 +617,12 @@ class NestedSampler:
         """Results (+ remaining live points, sampler.py:780-914) from the host-phase and device-phase dead points."""
         nlive = self.nlive
         ndead = len(logl)
+        have_pos = True
         if dev is not None:
             du, dv, dl, dlvol, dnc = dev
             logl, logvols = np.concatenate([logl, dl]), np.concatenate([logvols, dlvol])
-            su, sv = np.concatenate([su, du]), np.concatenate([sv, dv])
+            have_pos = len(du) == len(dl)
+            su, sv = (np.concatenate([su, du]), np.concatenate([sv, dv])) if have_pos else (du, dv)
             nc_all = np.concatenate([nc_all, dnc.astype(np.int64)])
             ndead = len(logl)
         if add_live:
@@ -612,8 +630,9 @@ class NestedSampler:
             lv_live = np.log(1. - (np.arange(nlive) + 1.) / (nlive + 1.)) + (logvols[-1] if ndead else 0.0)
             logl = np.concatenate([logl, self.live_logl[order]])
             logvols = np.concatenate([logvols, lv_live])
-            su = np.concatenate([su, self.live_u[order]])
-            sv = np.concatenate([sv, self.live_v[order]])
+            if have_pos:
+                su = np.concatenate([su, self.live_u[order]])
+                sv = np.concatenate([sv, self.live_v[order]])
             nc_all = np.concatenate([nc_all, np.ones(nlive, dtype=np.int64)])
         logwt, logzs, logzvar, h = _integrate(logl, logvols)
         self.results = Results(niter=ndead, ncall=int(self.ncall), eff=100. * ndead / max(self.ncall, 1),

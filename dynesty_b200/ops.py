@@ -123,6 +123,59 @@ def bootstrap_expand(points, multi, nboot, seed, chain0, ctx=None):
     return out
 
 
+# ---- RadFriends / SupFriends (include/b200nest.h, b2n_friends_*) ---------------------------------
+def friends_update(points, kind, am_prev=None, use_clustering=True, nboot=0, seed=0, chain0=0, ctx=None):
+    """RadFriends.update / SupFriends.update (bounding.py:874-958 / 1142-1226).  kind: 'balls' | 'cubes'.
+    Returns dict(cov, am, axes, axes_inv, logvol, radius, nclusters)."""
+    ctx = _ctx(ctx)
+    points = f64(points)
+    N, n = points.shape
+    o = dict(cov=np.empty((n, n)), am=np.empty((n, n)), axes=np.empty((n, n)), axes_inv=np.empty((n, n)))
+    lv, rad, ncl = C.c_double(0.0), C.c_double(0.0), C.c_int32(0)
+    amp = f64(am_prev) if (use_clustering and am_prev is not None) else None
+    ctx.check(ctx.lib.b2n_friends_update(ctx.h, ptr(points), N, n, {'balls': 0, 'cubes': 1}[kind],
+                                         int(bool(use_clustering and amp is not None)), ptr(amp), int(nboot), int(seed),
+                                         int(chain0), ptr(o['cov']), ptr(o['am']), ptr(o['axes']), ptr(o['axes_inv']),
+                                         C.addressof(lv), C.addressof(rad), C.addressof(ncl)))
+    o.update(logvol=lv.value, radius=rad.value, nclusters=ncl.value)
+    return o
+
+
+def friends_set(kind, ctrs, axes, axes_inv, ctx=None, key=None):
+    """Make (ctrs, axes, axes_inv) the resident friends bound of the ctx."""
+    ctx = _ctx(ctx)
+    ctrs, axes, axes_inv = f64(ctrs), f64(axes), f64(axes_inv)
+    N, n = ctrs.shape
+    ctx.friends_key = None
+    ctx.check(ctx.lib.b2n_friends_set(ctx.h, {'balls': 0, 'cubes': 1}[kind], ptr(ctrs), N, n, ptr(axes), ptr(axes_inv)))
+    ctx.friends_key = key
+
+
+def friends_overlap(x, ctx=None):
+    """q (M,) int32: number of balls / cubes of the resident friends bound containing each row of x."""
+    ctx = _ctx(ctx)
+    x = f64(np.atleast_2d(x))
+    q = np.empty(len(x), dtype=np.int32)
+    ctx.check(ctx.lib.b2n_friends_overlap(ctx.h, ptr(x), len(x), x.shape[1], ptr(q)))
+    return q
+
+
+def friends_unif_batch(model, nchain, ndim, loglstar, seed, chain0=0, dimflags=None, ctx=None, draw_only=False,
+                       mixture=False):
+    """UniformBoundSampler.sample x nchain on the resident friends bound; draw_only: Bound.samples(nchain)."""
+    ctx = _ctx(ctx)
+    a, keep, Q, n = _chain_args(model, None, ndim, loglstar, 1.0, seed, chain0, None, dimflags, Q=int(nchain), ndim=int(ndim))
+    if draw_only:
+        a.reserved = 3 if mixture else 1
+    o = dict(u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.empty(Q), ncall=np.empty(Q, dtype=np.int32),
+             nprop=np.empty(Q, dtype=np.int32), flags=np.empty(Q, dtype=np.uint32))
+    ctx.check(ctx.lib.b2n_friends_unif_batch(ctx.h, C.byref(a), ptr(o['u']), ptr(o['v']), ptr(o['logl']), ptr(o['ncall']),
+                                             ptr(o['nprop']), ptr(o['flags'])))
+    if not draw_only and (o['flags'] & 0x80000000).any():
+        raise NotImplementedError("uniform sampling did not find a point (bound draw limit)")
+    return o
+
+
 def bound_set(axes, ctrs=None, ams=None, logvols=None, ctx=None, key=None):
     """Make K ellipsoids resident for the proposal kernels (axes: (K, nc, nc)).
     A ctx holds ONE resident bound; `key` (the uploading bound's version token, None = anonymous) is
@@ -390,11 +443,15 @@ def ns_get_live(nlive, ndim, ctx=None, only_u=False):
     return u, v, l
 
 
-def ns_get_dead(first, count, ndim, ctx=None):
+def ns_get_dead(first, count, ndim, ctx=None, positions=True):
+    """(u, v, logl, logvol, ncall) of dead points [first, first + count); positions=False skips the two
+    (count, ndim) position arrays (zero-row placeholders) -- the evidence needs only the scalars."""
     ctx = _ctx(ctx)
-    u, v = np.empty((count, ndim)), np.empty((count, ndim))
+    u, v = (np.empty((count, ndim)), np.empty((count, ndim))) if positions else (None, None)
     l, lv, nc = np.empty(count), np.empty(count), np.empty(count, dtype=np.int32)
     ctx.check(ctx.lib.b2n_ns_get_dead(ctx.h, int(first), int(count), ptr(u), ptr(v), ptr(l), ptr(lv), ptr(nc)))
+    if not positions:
+        u, v = np.empty((0, ndim)), np.empty((0, ndim))
     return u, v, l, lv, nc
 
 

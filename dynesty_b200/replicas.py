@@ -28,12 +28,12 @@ import numpy as np
 from . import _lib, nested
 
 
-def _one(device, make_sampler, run_kwargs, seed, keep_results):
-    ctx = _lib.Context(device)
-    try:
+def _one(pool, make_sampler, run_kwargs, seed, keep_results):
+    ctx = pool.get()                     # a context is reused by the replicas that follow each other on it: its device
+    try:                                 # allocations (scratch, run state) are made once, not once per run
         t0 = time.perf_counter()
         s = make_sampler(seed, ctx)
-        res = s.run_nested(loop='device', **run_kwargs)
+        res = s.run_nested(loop='device', keep_samples=keep_results, **run_kwargs)
         wall = time.perf_counter() - t0
         out = dict(seed=int(seed), logz=float(res.logz[-1]), logzerr=float(res.logzerr[-1]), niter=int(res.niter),
                    ncall=int(res.ncall), nbound=int(res.nbound), rounds=int(s.device_rounds), wall_s=wall,
@@ -42,15 +42,41 @@ def _one(device, make_sampler, run_kwargs, seed, keep_results):
             out['results'] = res
         return out
     finally:
-        ctx.close()
+        pool.put(ctx)
+
+
+class ContextPool:
+    """`size` contexts on one GPU, handed to the replica threads; ``chain_pack``: chains per CTA of their chain
+    kernels (b2n_set_chain_pack) -- with many runs in flight a few chains per CTA leave room for everybody."""
+
+    def __init__(self, device, size, chain_pack=1):
+        import queue
+        self.q = queue.Queue()
+        self.all = [_lib.Context(device) for _ in range(size)]
+        for c in self.all:
+            if chain_pack > 1:
+                c.set_chain_pack(chain_pack)
+            self.q.put(c)
+
+    def get(self):
+        return self.q.get()
+
+    def put(self, c):
+        self.q.put(c)
+
+    def close(self):
+        for c in self.all:
+            c.close()
 
 
 def run_replicas(model, seeds, nlive=500, bound='multi', sample='rwalk', device=None, max_in_flight=16, comm=None,
-                 keep_results=False, sampler_kwargs=None, **run_kwargs):
+                 keep_results=False, sampler_kwargs=None, chain_pack=1, pool=None, **run_kwargs):
     """Run one device-resident nested-sampling run per seed, `max_in_flight` at a time on this GPU.
 
     model / nlive / bound / sample / sampler_kwargs : as for ``nested.NestedSampler``.
     run_kwargs : passed to ``run_nested`` (dlogz, maxiter, maxcall, batch, ...).
+    chain_pack : chains per CTA of the replicas' chain kernels (see ContextPool); pool: a ContextPool to reuse
+           across calls (its size bounds the number of replicas in flight).
     comm : optional ``dist.Comm`` -- the seeds are dealt over the ranks (rank r: seeds[r::world]); rank 0
            returns the summaries of ALL replicas (in seed order), the other ranks their own.
     Returns (summaries, wall_seconds): one dict per replica (seed, logz, logzerr, niter, ncall, nbound, rounds,
@@ -65,13 +91,21 @@ def run_replicas(model, seeds, nlive=500, bound='multi', sample='rwalk', device=
     def make(seed, ctx):
         return nested.NestedSampler(model, nlive=nlive, bound=bound, sample=sample, seed=seed, ctx=ctx, **kw)
 
+    nthr = max(1, min(int(max_in_flight), len(mine))) if mine else 0
+    own_pool = pool is None and nthr > 0
+    if own_pool:
+        pool = ContextPool(device, nthr, chain_pack)
     t0 = time.perf_counter()
     outs = []
-    if mine:
-        with ThreadPoolExecutor(max_workers=max(1, min(int(max_in_flight), len(mine)))) as ex:
-            futs = [ex.submit(_one, device, make, run_kwargs, s, keep_results) for s in mine]
-            outs = [f.result() for f in futs]
-    wall = time.perf_counter() - t0
+    try:
+        if mine:
+            with ThreadPoolExecutor(max_workers=nthr) as ex:
+                futs = [ex.submit(_one, pool, make, run_kwargs, s, keep_results) for s in mine]
+                outs = [f.result() for f in futs]
+        wall = time.perf_counter() - t0
+    finally:
+        if own_pool:
+            pool.close()
     if comm is not None:
         slim = [{k: v for k, v in o.items() if k != 'results'} for o in outs]
         parts = [None] * comm.world

@@ -233,6 +233,13 @@ class B200UniformSampler(_B200Sampler):
     device-resident ellipsoids)."""
 
     def run_batch(self, loglstar, nchain, bound, seed, chain0=0, ncdim=None, peer=None):
+        if getattr(bound, 'kind', None) in ('balls', 'cubes'):          # RadFriends / SupFriends: their own draw
+            if peer is not None:
+                raise NotImplementedError("fused multi-GPU gather is not wired for the friends bounds")
+            n = self.ndim or self.model.ndim
+            c = bound._resident()
+            return ops.friends_unif_batch(self.model.model_id(c), nchain, n, loglstar, seed, chain0=chain0,
+                                          dimflags=self._flags(), ctx=c)
         c = self._ctx if self._ctx is not None else bound.ctx
         if c.resident_key is None or c.resident_key != bound.version:
             bound.make_resident(c)
@@ -245,7 +252,7 @@ class B200UniformSampler(_B200Sampler):
                         loglikelihood=None, nested_sampler=None):
         bound = nested_sampler.bound
         if not hasattr(bound, 'make_resident'):
-            raise TypeError("B200UniformSampler needs bound=B200Ellipsoid/B200MultiEllipsoid")
+            raise TypeError("B200UniformSampler needs one of the B200 bounds (ellipsoids or friends)")
         o = self.run_batch(loglstar, len(points), bound, _seed_of(seeds), ncdim=nested_sampler.ncdim)
         self.last_batch = o
         return [SamplerReturn(u=u, v=v, logl=l, ncalls=c, evaluation_history=[], tuning_info=None,

@@ -74,6 +74,11 @@ void b2n_free(b2n_ctx* ctx);
 int  b2n_set_stream(b2n_ctx* ctx, void* cuda_stream);   /* cudaStream_t; NULL = own stream */
 int  b2n_set_pointer_mode(b2n_ctx* ctx, int mode);
 int  b2n_synchronize(b2n_ctx* ctx);
+/* Chains per CTA of the chain kernels: by default a launch spreads its chains over as many CTAs as the GPU holds
+ * (small launches: ONE chain per CTA, the shortest latency for a lone run).  When many contexts share the GPU
+ * (replicas), packing k chains into a CTA (lock-step, k <= 8 / 16 depending on the kernel) leaves the SMs to the
+ * other contexts at a small cost in per-launch latency.  Results do not depend on it. */
+int  b2n_set_chain_pack(b2n_ctx* ctx, int32_t chains_per_cta);
 const char* b2n_strerror(int status);
 const char* b2n_last_error(b2n_ctx* ctx);
 const char* b2n_version(void);
@@ -243,6 +248,31 @@ int b2n_unitcube_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, double*
  * unused.  nprop[q] = draws from the bound incl. out-of-cube ones. */
 int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, double* v,
                    double* logl, int32_t* ncall, int32_t* nprop, uint32_t* flags);
+
+/* ---- RadFriends / SupFriends: one ball / cube per live point (bounding.py:734-996, 999-1263) ------------------
+ * kind: 0 = balls (RadFriends, Euclidean norm), 1 = cubes (SupFriends, Chebyshev norm).
+ * b2n_friends_update  = RadFriends.update / SupFriends.update (:874-958 / 1142-1226): covariance from the clusters
+ *     of the single-linkage tree cut at Mahalanobis distance 1 under the CURRENT metric am_prev (use_clustering;
+ *     :966-993), am = pinvh(cov), axes = sqrtm(cov), axes_inv = pinvh(axes), radius = leave-one-out nearest-neighbour
+ *     distance (nboot = 0; :1683-1705) or the bootstrap radius over nboot realisations (:1651-1680; realisation b
+ *     resamples with the B2N stream (seed, chain0 + b), one integers event), everything rescaled by the radius,
+ *     logvol = prefactor - slogdet(am) / 2.  Outputs (n x n each, logvol / radius / nclusters host scalars); the
+ *     caller keeps `ctrs = points` (:950, sampler.py:481).  Synchronises.
+ * b2n_friends_set     makes (ctrs, axes, axes_inv) the resident friends bound of the ctx.
+ * b2n_friends_overlap = overlap(x) (:785-790 / 1052-1057) for M query points: q[m] = number of balls / cubes
+ *     containing x_m (contains = q > 0, within = the indices).
+ * b2n_friends_unif_batch = UniformBoundSampler.sample (internal_samplers.py:243-340) with the bound's own
+ *     sample() (:797-831 / 1065-1100: random centre + random offset, accepted with probability 1/q) as the draw;
+ *     a->reserved = B2N_OPT_DRAW_ONLY: Bound.samples (no cube test / likelihood), | B2N_OPT_DRAW_MIXTURE:
+ *     sample(return_q=True), ncall[q] = q. */
+int b2n_friends_update(b2n_ctx* ctx, const double* points, int64_t N, int32_t n, int32_t kind, int32_t use_clustering,
+                       const double* am_prev, int32_t nboot, uint64_t seed, uint64_t chain0, double* cov, double* am,
+                       double* axes, double* axes_inv, double* logvol, double* radius, int32_t* nclusters);
+int b2n_friends_set(b2n_ctx* ctx, int32_t kind, const double* ctrs, int64_t N, int32_t n, const double* axes,
+                    const double* axes_inv);
+int b2n_friends_overlap(b2n_ctx* ctx, const double* x, int64_t M, int32_t n, int32_t* q);
+int b2n_friends_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, double* v, double* logl, int32_t* ncall,
+                           int32_t* nprop, uint32_t* flags);
 
 /* ---- multi-GPU exchange over NVLink peer memory ------------------------------
  * The path shards by CHAINS: rank r of W runs rows [row0, row0 + nchain) of a `total_rows`-chain

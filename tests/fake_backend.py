@@ -105,6 +105,7 @@ class FakeContext:
     serial = 0
     device = 0
     resident_key = None
+    friends_key = None
 
     def __init__(self, device=0):
         self.device = device
@@ -135,6 +136,70 @@ def bound_set(axes, ctrs=None, ams=None, logvols=None, ctx=None, key=None):
     _state['ctrs'] = None if ctrs is None else np.array(ctrs, dtype=float).reshape(len(axes), -1)
     _state['ams'] = None if ams is None else np.array(ams, dtype=float).reshape(axes.shape)
     _state['logvols'] = None if logvols is None else np.array(logvols, dtype=float).reshape(-1)
+
+
+# ---- RadFriends / SupFriends backed by oracle.friends ------------------------------------------------
+def friends_update(points, kind, am_prev=None, use_clustering=True, nboot=0, seed=0, chain0=0, ctx=None):
+    from oracle import friends as OF
+    points = np.asarray(points, dtype=float)
+    f = OF.Friends(points.shape[1], kind)
+    if am_prev is not None:
+        f.am = np.asarray(am_prev, dtype=float)
+    idxs = None
+    if nboot:
+        idxs = [philox.ChainStream(seed, chain0 + r).integers(len(points), len(points)) for r in range(nboot)]
+    ncl = int(OF.components_within(points, f.am).max()) + 1 if (use_clustering and am_prev is not None) else 1
+    r = f.update(points, bootstrap_idxs=idxs, use_clustering=bool(use_clustering and am_prev is not None))
+    return dict(cov=f.cov, am=f.am, axes=f.axes, axes_inv=f.axes_inv, logvol=float(f.logvol), radius=r, nclusters=ncl)
+
+
+def _friends_obj():
+    from oracle import friends as OF
+    st = _state['friends']
+    f = OF.Friends(st['ctrs'].shape[1], st['kind'])
+    f.ctrs, f.axes, f.axes_inv = st['ctrs'], st['axes'], st['axes_inv']
+    return f
+
+
+def friends_set(kind, ctrs, axes, axes_inv, ctx=None, key=None):
+    _state['friends'] = dict(kind=kind, ctrs=np.array(ctrs, dtype=float), axes=np.array(axes, dtype=float),
+                             axes_inv=np.array(axes_inv, dtype=float))
+    (ctx if ctx is not None else _fake_ctx).friends_key = key
+
+
+def friends_overlap(x, ctx=None):
+    f = _friends_obj()
+    return np.array([f.overlap(r) for r in np.atleast_2d(x)], dtype=np.int32)
+
+
+def friends_unif_batch(model, nchain, ndim, loglstar, seed, chain0=0, dimflags=None, ctx=None, draw_only=False,
+                       mixture=False):
+    f = _friends_obj()
+    Q, n = int(nchain), int(ndim)
+    o = dict(u=np.empty((Q, n)), v=np.empty((Q, n)), logl=np.zeros(Q), ncall=np.zeros(Q, dtype=np.int32),
+             nprop=np.zeros(Q, dtype=np.int32), flags=np.zeros(Q, dtype=np.uint32))
+    m = None if draw_only else _models[model]
+    for i in range(Q):
+        s = philox.ChainStream(seed, chain0 + i)
+        if draw_only:
+            r = f.sample(s, return_q=bool(mixture))
+            x, q = r if mixture else (r, 1)
+            o['u'][i] = o['v'][i] = x
+            o['ncall'][i], o['nprop'][i] = q, 1
+            continue
+        nc = npr = 0
+        while True:
+            x = f.sample(s)
+            npr += 1
+            if not OS.unitcheck(x, None):
+                continue
+            v = m.prior_transform(x)
+            l = float(m.loglike(v))
+            nc += 1
+            if l > loglstar:
+                break
+        o['u'][i], o['v'][i], o['logl'][i], o['ncall'][i], o['nprop'][i] = x, v, l, nc, npr
+    return o
 
 
 def dimflags_from(ndim, periodic=None, reflective=None):
@@ -356,9 +421,11 @@ def ns_get_live(nlive, ndim, ctx=None, only_u=False):
     return b.live_u.copy(), b.live_v.copy(), b.live_logl.copy()
 
 
-def ns_get_dead(first, count, ndim, ctx=None):
+def ns_get_dead(first, count, ndim, ctx=None, positions=True):
     u, v, l, lv, nc = _state['ns'].dead_arrays()
     sl = slice(first, first + count)
+    if not positions:
+        return np.empty((0, ndim)), np.empty((0, ndim)), l[sl], lv[sl], nc[sl].astype(np.int32)
     return u[sl], v[sl], l[sl], lv[sl], nc[sl].astype(np.int32)
 
 
@@ -367,7 +434,8 @@ def ns_destroy(ctx=None):
 
 
 FUNCS = ['ns_set_counters', 'ns_create', 'ns_set_state', 'ns_status', 'ns_run', 'ns_bound_updated', 'ns_reserve_dead',
-         'ns_get_live', 'ns_get_dead', 'ns_destroy', 'ns_update_bound', 'ns_get_bound', 'unitcube_batch', 'model_eval', 'membership', 'bounding_ellipsoid', 'multi_decompose', 'scale_to_logvol',
+         'ns_get_live', 'ns_get_dead', 'ns_destroy', 'ns_update_bound', 'ns_get_bound', 'unitcube_batch', 'friends_update', 'friends_set', 'friends_overlap',
+         'friends_unif_batch', 'model_eval', 'membership', 'bounding_ellipsoid', 'multi_decompose', 'scale_to_logvol',
          'bootstrap_expand', 'bound_set', 'ensure_resident', 'dimflags_from', 'rwalk_batch', 'rslice_batch', 'slice_batch',
          'unif_batch']
 

@@ -136,3 +136,24 @@ def test_pool_size_sets_the_queue(dynesty, fake_ops):
     assert ns.queue_size == 24
     ns.run_nested(maxiter=300, dlogz=1e-9, print_progress=False, add_live=False)
     assert ns.internal_sampler.last_batch is not None and len(ns.internal_sampler.last_batch['logl']) == 24
+
+
+@pytest.mark.parametrize('kind,sample', [('balls', 'unif'), ('cubes', 'unif'), ('balls', 'rwalk')])
+def test_dropin_friends(dynesty, fake_ops, kind, sample):
+    """B200RadFriends / B200SupFriends under the unmodified dynesty.NestedSampler: ``need_centers`` makes the Sampler
+    assign its live points to ``bound.ctrs`` (sampler.py:479-482); ``contains`` of a start point (a centre) is True."""
+    c, b, s = _classes()
+    from dynesty_b200 import likelihoods as DL
+    from dynesty_b200.pool import B200Pool
+    from dynesty import bounding as RB
+    m = DL.gauss_test3d()
+    bnd = (b.B200RadFriends if kind == 'balls' else b.B200SupFriends)(3)
+    assert isinstance(bnd, RB.Bound) and bnd.need_centers
+    smp = s.B200UniformSampler(model=m) if sample == 'unif' else s.B200RWalkSampler(model=m, walks=10)
+    ns = dynesty.NestedSampler(m.loglikelihood, m.prior_transform, 3, nlive=80, bound=bnd, sample=smp,
+                               pool=B200Pool(16), queue_size=16, rstate=np.random.default_rng(3), bootstrap=0,
+                               use_pool={'prior_transform': False, 'loglikelihood': False})
+    ns.run_nested(dlogz=0.5, print_progress=False)
+    res = ns.results
+    assert abs(res['logz'][-1] - 3 * (-np.log(20.))) < 5 * res['logzerr'][-1] + 0.1
+    assert ns.nbound > 1 and isinstance(ns.bound, type(bnd)) and ns.bound.ctrs is ns.live_u

@@ -90,7 +90,7 @@ def test_diamond_rwalk():
 
 def test_diamond_rwalk_lockstep_kernel():
     """Same region on the first two of 16 dimensions: the lock-step DMMA kernel (16 <= n <= 64)."""
-    check_diamond(run_chains(DL.region2d('diamond', 16), 'rwalk', 48, 20, 0.6, ndim=16, walks=12))
+    check_diamond(run_chains(DL.region2d('diamond', 16), 'rwalk', 60, 24, 0.6, ndim=16, walks=30))
 
 
 def test_diamond_rslice():

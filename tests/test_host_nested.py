@@ -142,3 +142,19 @@ def test_resident_bound_is_tracked_per_context(fake_ops):
     d = pickle.loads(pickle.dumps(a.bound))
     assert len({a.bound.version, c.version, d.version}) == 3
     assert c._ctx is a.bound._ctx                           # a deepcopy stays on its context
+
+
+@pytest.mark.parametrize('bound,sample,kw', [('balls', 'unif', {}), ('cubes', 'unif', {}), ('balls', 'rwalk', dict(walks=10)),
+                                              ('cubes', 'rslice', dict(slices=3))])
+def test_friends_bounds_host_loop(fake_ops, bound, sample, kw):
+    """bound='balls' / 'cubes' (RadFriends / SupFriends, bounding.py:734-1263) through the host loop: centres follow
+    the live points (need_centers, sampler.py:479-482), the uniform sampler draws from the union of balls / cubes, the
+    chain samplers use the common axes."""
+    from dynesty_b200 import nested, likelihoods as DL, bounding as B
+    m = DL.gauss_test3d()
+    s = nested.NestedSampler(m, nlive=80, bound=bound, sample=sample, queue_size=16, seed=9, **kw)
+    res = s.run_nested(dlogz=0.5)
+    assert isinstance(s.bound, (B.B200RadFriends, B.B200SupFriends)) and s.nbound > 2
+    assert s.bound.ctrs is s.live_u
+    truth = 3 * (-np.log(20.))
+    assert abs(res.logz[-1] - truth) < 4 * res.logzerr[-1] + 0.1
