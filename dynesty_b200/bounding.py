@@ -378,6 +378,50 @@ class B200Ellipsoid(BoundBase):
         """bounding.py:336-343."""
         return self._m.unitcube_overlap(ndraws, rstate=rstate)
 
+    def update_sharded(self, points_shard, comm):
+        """``bounding_ellipsoid`` (bounding.py:1387-1461) of a live set whose ROWS are sharded over the ranks of
+        `comm`: every rank reduces its own rows on its GPU, two small all-reduces carry
+        (count, sum x, scatter) and max_i delta^T am delta, and every rank finishes the identical ellipsoid (the
+        repair ladder and the eigen-decomposition are deterministic, so no broadcast is needed).
+        Communication per update: n^2 + n + 1 doubles (sum) and 1 double (max) per pass, instead of N n doubles."""
+        pts = np.ascontiguousarray(points_shard, dtype=float)
+        n = self.ndim
+        m = self._m
+        mean_r, cov_r = ops.moments(pts, ctx=m.ctx)                                   # this rank's rows, on its GPU
+        nr = float(len(pts))
+        tot = comm.allreduce_sum(np.concatenate([[nr], nr * mean_r]))                  # (count, sum x)
+        N = tot[0]
+        if N < 2:
+            raise ValueError('Cannot compute a bounding ellipsoid of a single point.')
+        mean = tot[1:] / N
+        d = mean_r - mean
+        S = comm.allreduce_sum((nr - 1.0) * cov_r + nr * np.outer(d, d))               # scatter about the global mean
+        covar = S / (N - 1.0)
+        for i in range(2):                                                              # bounding.py:1424-1457
+            good, covar, am, axes, warn = ops.improve_covar(covar, ctx=m.ctx)
+            if warn & _lib.WARN_IDENTITY_FALLBACK:
+                warnings.warn("Failed to guarantee the ellipsoid axes will be non-singular. Defaulting to a sphere.")
+            d2 = ops.membership(pts, mean[None], am[None], want_d2=True, ctx=m.ctx)[2][:, 0]
+            fmax = comm.max(float(d2.max()))
+            one_minus_a_bit = 1. - 1e-3
+            if i == 0 and fmax > one_minus_a_bit:
+                mult = fmax / one_minus_a_bit
+                covar = covar * mult
+                am = am / mult
+                axes = axes * math.sqrt(mult)
+            if i == 1 and fmax >= 1:
+                raise RuntimeError("Failed to initialize the ellipsoid to contain all the points")
+            if good:
+                break
+        axlens = np.linalg.norm(axes, axis=0)                                           # axes = V sqrt(lambda) (:227-230)
+        from scipy.special import gammaln
+        pref = n * math.log(2.) + n * gammaln(1.5) - gammaln(n / 2. + 1)
+        m.nells = 1
+        m.ctrs, m.covs, m.ams = mean[None], covar[None], am[None]
+        m.axes_all, m.axlens_all = axes[None], axlens[None]
+        m.logvol_ells = np.array([pref + float(np.log(axlens).sum())])
+        m._refresh_logvol()
+
 
 class _B200Friends(BoundBase):
     """``RadFriends`` / ``SupFriends`` (bounding.py:734-996 / 999-1263): one ball / cube of common shape around every

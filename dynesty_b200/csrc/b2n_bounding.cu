@@ -890,6 +890,27 @@ extern "C" int b2n_bounding_ellipsoid(b2n_ctx* ctx, const double* points, int64_
     return B2N_OK;
 }
 
+// Moments of a block of points: count-weighted building blocks of the covariance of a row-SHARDED live set
+// (all-reduce of (count, sum x, sum x x^T) at the bound update).  mean = np.mean(points, 0),
+// cov = np.cov(points, rowvar=False) (ddof = 1) of THIS block; blocks combine exactly through
+//   S = sum_r [ (N_r - 1) cov_r + N_r (mean_r - mean)(mean_r - mean)^T ],  cov = S / (N - 1).
+extern "C" int b2n_moments(b2n_ctx* ctx, const double* points, int64_t N, int32_t n, double* mean, double* cov) {
+    if (!ctx || !points || N < 1 || n < 1 || !mean || !cov) return B2N_ERR_ARG;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* dP;
+    B2N_TRY(b2n_in(ctx, ctx->in0, points, (size_t)N * n * sizeof(double), &dP));
+    BoundWork w;
+    B2N_TRY(b2n_boundwork_init(ctx, w, (const double*)dP, N, n, 1));
+    B2N_TRY(init_identity_perm(w));
+    B2N_TRY(b2n_node_moments(w, (int)N));
+    if (N == 1) B2N_CUDA(ctx, cudaMemsetAsync(w.na.covraw, 0, (size_t)n * n * sizeof(double), ctx->stream));   // (ddof = 1)
+    B2N_TRY(emit_node(w, 0, 0, mean, nullptr, nullptr, nullptr, nullptr));
+    const cudaMemcpyKind kind = ctx->ptr_mode == B2N_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    B2N_CUDA(ctx, cudaMemcpyAsync(cov, w.na.covraw, (size_t)n * n * sizeof(double), kind, ctx->stream));
+    B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B2N_OK;
+}
+
 // improve_covar_mat (bounding.py:1311-1384) on a caller-supplied matrix: the repair ladder of the fit
 // kernels exposed on its own (the same eig_ladder_kernel / sliced solver, fed through `covraw`).
 extern "C" int b2n_improve_covar(b2n_ctx* ctx, const double* covar, int32_t n, double* cov_out, double* am,

@@ -88,12 +88,16 @@ __global__ void __launch_bounds__(1024) eig_sliced_kernel(NodeArrays na, const i
     __syncthreads();
     int sweep = 0;
     for (; sweep < 40; sweep++) {
-        double all = 0.0, dg = 0.0;
-        for (int e = tid; e < np; e += T) all = fma(A[e], A[e], all);
+        // off-diagonal mass summed DIRECTLY (as a difference "all - diagonal" it drowns in round-off as soon as it
+        // is below eps * total, i.e. at a relative off-norm of 1e-8, and the convergence test fired there: eigenvectors
+        // good to 1e-11 for well-conditioned covariances, useless for repaired ones with condition 1e11)
+        double offh = 0.0, dg = 0.0;
+        for (int i = warp; i < n; i += nw)
+            for (int j = i + 1 + lane; j < n; j += 32) { const double a = A[pidx(i, j, n)]; offh = fma(a, a, offh); }
         for (int i = tid; i < n; i += T) { const double a = A[pidx(i, i, n)]; dg = fma(a, a, dg); }
-        all = block_sum2(all, red);
+        offh = block_sum2(offh, red);
         dg = block_sum2(dg, red);
-        const double off = 2.0 * (all - dg), tot = off + dg;
+        const double off = 2.0 * offh, tot = off + dg;
         if (!(tot < INFINITY) || tot == 0.0) break;
         if (off <= (double)n * (double)n * 2.5e-32 * tot) break;
         for (int r = 0; r < m - 1; r++) {

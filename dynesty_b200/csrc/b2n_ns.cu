@@ -79,6 +79,12 @@ struct b2n_ns {
     std::vector<void*> allocs;
     void* dead_alloc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int phase = 1;                     // host copy of NsScalars::phase (transitions are host-mediated)
+    // CUDA graph of B2N_NS_GRAPH_ROUNDS rounds ([commit+propose | chains] x G): every per-round argument of these
+    // kernels lives in HBM (B2nDyn, NsScalars), so the launch sequence is STATIC and a block of rounds is one
+    // cudaGraphLaunch instead of 2 G kernel launches -- the host-side launch rate is what limits an ensemble of
+    // replicas (dynesty_b200/replicas.py).  Re-captured when anything baked into the kernel arguments changes.
+    cudaGraphExec_t gexec = nullptr;
+    unsigned long long gkey = 0, warm_key = 0;
     bool active = false;               // between b2n_ns_create and b2n_ns_destroy.  The device allocations OUTLIVE a run
                                        // (released by b2n_free, or by a b2n_ns_create of another shape): cudaMalloc /
                                        // cudaFree synchronise the whole device, which would stall every other replica
@@ -466,8 +472,15 @@ __device__ __forceinline__ void ns_commit_body(const NsDev& s) {
             if (s_or & 0x40000000u) { sc->error = B2N_ERR_Q0; sc->done = 1; }            // bounding.py:570-574
             if (s_or & 0x80000000u) { sc->error = B2N_ERR_UNSUPPORTED; sc->done = 1; }   // draw limit
         } else if (s.sampler == 0) {                         // internal_samplers.py:460-493
+            // The reference tunes after EVERY iteration (queue_size 1): scale *= exp((a_t - f) / (n f)) with the
+            // acceptance a_t of that iteration's chain.  A round is K such iterations at one scale, i.e. the product
+            // exp(K (abar - f) / (n f)); the power is capped at n so that the loop gain stays below 1 / f whatever
+            // batch the caller picks.  K = 1 is the reference's rule.  (One pooled update per round -- what the
+            // reference does per queue -- adapts K times slower: at C4, K = n = 200, the scale could not follow
+            // the shrinking live set, chains froze and the live set collapsed onto clones.)
             const double facc = (double)ha / (double)(ha + hb);
-            sc->scale *= exp((facc - s.facc) / (double)s.nc / s.facc);
+            const double pw = (double)(K < s.nc ? K : s.nc);
+            sc->scale *= exp(pw * (facc - s.facc) / (double)s.nc / s.facc);
         } else {                                             // tune_slice :1209-1239
             if (s_or & B2N_WARN_DOUBLING) sc->doubling = 1;
             const double ne = (double)(ha > 1 ? ha : 1), ncn = (double)hb;
@@ -541,6 +554,7 @@ static int ns_alloc_dead(b2n_ctx* ctx, b2n_ns* ns, long long cap) {
 
 void b2n_ns_release(b2n_ctx* ctx) {
     if (!ctx || !ctx->ns) return;
+    if (ctx->ns->gexec) cudaGraphExecDestroy(ctx->ns->gexec);
     for (void* p : ctx->ns->allocs) cudaFree(p);
     for (void* p : ctx->ns->dead_alloc) if (p) cudaFree(p);
     delete ctx->ns;
@@ -578,6 +592,20 @@ static int ns_chain_call(b2n_ctx* ctx, b2n_ns* ns, bool plan_only) {
     ctx->dyn.plan_only = false;
     ctx->ptr_mode = mode;
     return st;
+}
+
+#define B2N_NS_GRAPH_ROUNDS 16
+
+// everything that is baked into the arguments of the kernels of a round
+static unsigned long long ns_launch_key(b2n_ctx* ctx, b2n_ns* ns, size_t smem) {
+    unsigned long long h = 1469598103934665603ULL;
+    auto mix = [&](unsigned long long v) { h ^= v; h *= 1099511628211ULL; };
+    const unsigned char* raw = reinterpret_cast<const unsigned char*>(&ns->d);      // NsDev is passed BY VALUE to the step
+    for (size_t i = 0; i < sizeof(NsDev); i++) mix(raw[i]);                         // kernel (zero-initialised: no stray padding)
+    mix((unsigned long long)ns->phase); mix((unsigned long long)(uintptr_t)ctx->b_axesT.p); mix((unsigned long long)smem);
+    mix((unsigned long long)(uintptr_t)ctx->stream); mix((unsigned long long)ns->cfg.steps);
+    mix((unsigned long long)ns->cfg.model_id); mix((unsigned long long)ctx->min_cpc); mix((unsigned long long)ctx->bK);
+    return h ? h : 1;
 }
 
 static size_t ns_propose_smem(const NsDev& d) {
@@ -662,6 +690,8 @@ int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* c, int64_t dead_capacity) {
     } else if (ns->dead_cap < want_cap) {
         for (void*& pp : ns->dead_alloc) { if (pp) cudaFree(pp); pp = nullptr; }     // (nothing to keep from the last run)
         B2N_TRY(ns_alloc_dead(ctx, ns, want_cap));
+    } else {
+        d.dead_cap = want_cap;          // the capacity the caller asked for (the allocation may be larger)
     }
     cudaStream_t st = ctx->stream;      // stream-ordered clears (no device-wide synchronisation)
     B2N_CUDA(ctx, cudaMemsetAsync(d.o_i0, 0, K * 4, st));          // (the unit-cube sampler writes no counters)
@@ -759,14 +789,46 @@ int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_sta
     int left = max_rounds;
     b2n_ns_status st;
     memset(&st, 0, sizeof(st));
+    // graphs: chain samplers without per-dimension flags (their entry points then issue no copies), timing off
+    const char* genv = getenv("B2N_NS_GRAPH");
+    const bool graph_ok = !(genv && genv[0] == '0') && !ns->has_flags && !ctx->timing && (ns->phase == 0 || d.sampler != 3);
+    const unsigned long long key = ns_launch_key(ctx, ns, smem);
     while (left > 0) {
         const int chunk = std::min(left, (int)check_every);
-        // propose | chains | commit + propose | chains | ... | commit : chunk + 1 single-CTA launches
-        for (int r = 0; r < chunk; r++) {
-            ns_step_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d, r == 0 ? 2 : 3);
+        // R rounds = R x ( commit of the pending round + proposal of the next | chains ) + one closing commit
+        int r = 0;
+        if (graph_ok && ns->warm_key == key && chunk >= B2N_NS_GRAPH_ROUNDS) {
+            if (!ns->gexec || ns->gkey != key) {
+                if (ns->gexec) { cudaGraphExecDestroy(ns->gexec); ns->gexec = nullptr; }
+                cudaGraph_t g = nullptr;
+                B2N_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+                int cst = B2N_OK;
+                for (int q = 0; q < B2N_NS_GRAPH_ROUNDS && cst == B2N_OK; q++) {
+                    ns_step_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d, 3);
+                    cst = ns_chain_call(ctx, ns, false);
+                }
+                const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+                if (cst != B2N_OK || ce != cudaSuccess || !g) {
+                    if (g) cudaGraphDestroy(g);
+                    cudaGetLastError();
+                    return cst != B2N_OK ? cst : b2n_fail(ctx, B2N_ERR_CUDA, "stream capture of the round graph failed");
+                }
+                const cudaError_t ie = cudaGraphInstantiate(&ns->gexec, g, 0);
+                cudaGraphDestroy(g);
+                if (ie != cudaSuccess) { ns->gexec = nullptr; cudaGetLastError(); return b2n_fail(ctx, B2N_ERR_CUDA, "cudaGraphInstantiate failed"); }
+                ns->gkey = key;
+            }
+            for (; r + B2N_NS_GRAPH_ROUNDS <= chunk; r += B2N_NS_GRAPH_ROUNDS) {
+                B2N_CUDA(ctx, cudaGraphLaunch(ns->gexec, ctx->stream));
+                ctx->launches += 2 * B2N_NS_GRAPH_ROUNDS;
+            }
+        }
+        for (; r < chunk; r++) {
+            ns_step_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d, 3);
             B2N_LAUNCH_CHECK(ctx);
             B2N_TRY(ns_chain_call(ctx, ns, false));
         }
+        ns->warm_key = key;             // these very launches have been issued once outside a capture (buffers exist)
         ns_step_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d, 1);
         B2N_LAUNCH_CHECK(ctx);
         left -= chunk;
@@ -888,6 +950,7 @@ int b2n_ns_reserve_dead(b2n_ctx* ctx, int64_t capacity) {
     if (!ctx || !ctx->ns || !ctx->ns->active) return B2N_ERR_ARG;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
     if (capacity > ctx->ns->dead_cap) B2N_TRY(ns_alloc_dead(ctx, ctx->ns, capacity));
+    else if (capacity > ctx->ns->d.dead_cap) ctx->ns->d.dead_cap = capacity;          // allocation already large enough
     ns_clear_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ns->d.sc, ctx->ns->d.dyn, 0);   // clears need_bound == 3
     B2N_LAUNCH_CHECK(ctx);
     return B2N_OK;

@@ -212,6 +212,14 @@ class NestedSampler:
         """sampler.py:493-510."""
         if getattr(self.bound, 'need_centers', False):
             self.bound.ctrs = self.live_u
+        if self.comm is not None and isinstance(self.bound, B.B200Ellipsoid) and self.bound_bootstrap == 0 and \
+                isinstance(subset, slice) and getattr(self, 'shard_bound_update', True):
+            # the rows of the live set are dealt over the ranks: each reduces its share, all-reduce of the moments
+            lo, hi = (self.nlive * self.comm.rank) // self.comm.world, (self.nlive * (self.comm.rank + 1)) // self.comm.world
+            self.bound.update_sharded(self.live_u[lo:hi, :self.ncdim], self.comm)
+            if self.bound_enlarge != 1.:
+                self.bound.scale_to_logvol(self.bound.logvol + math.log(self.bound_enlarge))
+            return
         self.bound.update(self.live_u[subset, :self.ncdim], rstate=self.rstate, bootstrap=self.bound_bootstrap)
         if self.bound_enlarge != 1.:
             self.bound.scale_to_logvol(self.bound.logvol + math.log(self.bound_enlarge))

@@ -82,6 +82,16 @@ def multi_decompose(points, max_ells=None, ctx=None):
     return o
 
 
+def moments(points, ctx=None):
+    """(mean, cov) = (np.mean(points, 0), np.cov(points, rowvar=False)) of one shard of the live set."""
+    ctx = _ctx(ctx)
+    points = f64(points)
+    N, n = points.shape
+    mean, cov = np.empty(n), np.empty((n, n))
+    ctx.check(ctx.lib.b2n_moments(ctx.h, ptr(points), N, n, ptr(mean), ptr(cov)))
+    return mean, cov
+
+
 def improve_covar(covar, ctx=None):
     """(good, cov, am, axes, warn) = improve_covar_mat(covar)  (bounding.py:1311-1384)."""
     ctx = _ctx(ctx)

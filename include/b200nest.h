@@ -155,6 +155,13 @@ int b2n_multi_decompose(b2n_ctx* ctx, const double* points, int64_t N, int32_t n
                         double* ctrs, double* covs, double* ams, double* axes,
                         double* axlens, double* logvols, uint32_t* warn);
 
+/* Block moments for a row-SHARDED live set: mean (n) and sample covariance (n x n, ddof = 1; zeros
+ * for a single row) of `points` (N x n) -- np.mean / np.cov of bounding.py:1410-1412 for one shard.  Shards combine
+ * exactly: S = sum_r [(N_r - 1) cov_r + N_r (mean_r - mean)(mean_r - mean)^T], cov = S / (N - 1); the ellipsoid then
+ * follows from b2n_improve_covar on the combined covariance and an all-reduce(max) of the shard-local
+ * max_i delta_i^T am delta_i (b2n_membership's d2).  Synchronises. */
+int b2n_moments(b2n_ctx* ctx, const double* points, int64_t N, int32_t n, double* mean, double* cov);
+
 /* improve_covar_mat (bounding.py:1311-1384) on its own: the <= 100-trial repair ladder (eigenvalue clamp at
  * 10 max/1e12, then the identity blend, then the identity fallback) applied to `covar` (n x n).  Outputs:
  * the repaired covariance, its inverse `am`, `axes` = V sqrt(lambda) (columns, ascending eigenvalue);
@@ -326,6 +333,9 @@ uint64_t b2n_peer_window_bytes(int64_t total_rows, int32_t ndim);
  * DESIGN.md 9.4) no chain is ever discarded, so there is no selection effect; the live-point
  * count N, N-1, .., N-batch+1 seen by the removed points enters the quadrature the way the
  * reference treats a shrinking live set (ln X -= ln((m+1)/m) at a point with m live points).
+ * Tuning (internal_samplers.py:460-493, 1209-1239) happens once per round; for rwalk the update is the product of the
+ * `batch` per-iteration updates the reference would have made at that scale, exp(min(batch, ncdim) (abar - facc) /
+ * (ncdim facc)) -- batch = 1 is the reference's rule.
  * Launches of R rounds: propose | chains | commit+propose | chains | ... | commit (R chain launches and R + 1
  * single-CTA step launches), no host synchronisation in between;
  * b2n_ns_run enqueues rounds until a stop flag is raised on the device:

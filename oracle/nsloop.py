@@ -174,7 +174,9 @@ class BatchNS:
         if self.sampler == 'rwalk':
             a, r_ = sum(o['n_accept'] for o in out), sum(o['n_reject'] for o in out)
             nc = b['ctrs'].shape[1]
-            self.scale *= math.exp((a / (a + r_) - self.facc) / nc / self.facc)
+            # K serial updates of the reference (one per iteration, internal_samplers.py:486-493) at one scale are the
+            # K-th power of one update; capped at nc (loop gain).  K = 1: the reference's rule.
+            self.scale *= math.exp(min(self.K, nc) * (a / (a + r_) - self.facc) / nc / self.facc)
             self.last = dict(starts=starts, ell=ell, thr=thr, n_accept=a, n_reject=r_)
         else:
             ne, ncn = sum(o['n_expand'] for o in out), sum(o['n_contract'] for o in out)

@@ -82,6 +82,17 @@ def multi_decompose(points, max_ells=None, ctx=None):
                 axlens=np.array([o['axlens'] for o in outs]), logvols=np.array([o['logvol'] for o in outs]))
 
 
+def moments(points, ctx=None):
+    points = np.asarray(points, dtype=float)
+    cov = np.cov(points, rowvar=False) if len(points) > 1 else np.zeros((points.shape[1],) * 2)
+    return points.mean(axis=0), np.atleast_2d(cov)
+
+
+def improve_covar(covar, ctx=None):
+    good, cov, am, axes, st = OB.improve_covar_mat(np.asarray(covar, dtype=float))
+    return good, cov, am, axes, (1 if st else 0)
+
+
 def scale_to_logvol(covs, ams, axes, axlens, logvols, targets, ctx=None):
     for k in range(len(logvols)):
         e = OB.Ell.__new__(OB.Ell)
@@ -435,7 +446,7 @@ def ns_destroy(ctx=None):
 
 FUNCS = ['ns_set_counters', 'ns_create', 'ns_set_state', 'ns_status', 'ns_run', 'ns_bound_updated', 'ns_reserve_dead',
          'ns_get_live', 'ns_get_dead', 'ns_destroy', 'ns_update_bound', 'ns_get_bound', 'unitcube_batch', 'friends_update', 'friends_set', 'friends_overlap',
-         'friends_unif_batch', 'model_eval', 'membership', 'bounding_ellipsoid', 'multi_decompose', 'scale_to_logvol',
+         'friends_unif_batch', 'moments', 'improve_covar', 'model_eval', 'membership', 'bounding_ellipsoid', 'multi_decompose', 'scale_to_logvol',
          'bootstrap_expand', 'bound_set', 'ensure_resident', 'dimflags_from', 'rwalk_batch', 'rslice_batch', 'slice_batch',
          'unif_batch']
 

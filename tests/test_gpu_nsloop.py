@@ -316,7 +316,12 @@ def test_unitcube_phase_rounds_match_oracle():
         e = OB.bounding_ellipsoid(o.live_u)
         e.scale_to_logvol(e.logvol + math.log(1.25))
         assert nells == 1 and lv == pytest.approx(e.logvol, abs=1e-8)
-        o.bound_updated(dict(ctrs=e.ctr[None], ams=e.am[None], axes=e.axes[None], logvols=np.array([e.logvol]), strict=True))
+        # the oracle continues with the DEVICE-built bound (same ellipsoid, but the Jacobi solver's eigenvector signs /
+        # order -- hence the directions `axes @ z` of the chains -- are its own)
+        db = ops.ns_get_bound(nells, n)
+        close(db['ctrs'][0], e.ctr, rtol=1e-9)
+        close(db['covs'][0], e.cov, rtol=1e-9)
+        o.bound_updated(dict(ctrs=db['ctrs'], ams=db['ams'], axes=db['axes'], logvols=db['logvols'], strict=True))
         assert o.step()
         st = ops.ns_run(1, 0)
         assert (st['rounds'], st['ncall'], st['need_bound']) == (nr + 1, o.ncall, o.need_bound)
@@ -372,9 +377,12 @@ def test_device_bound_update_equals_host_path(bound, sample, kw):
     """b2n_ns_update_bound (fit + enlarge + make resident without leaving the device) runs the same kernels on the
     same live points as the host route (b2n_ns_get_live -> b2n_multi_decompose -> b2n_scale_to_logvol ->
     b2n_bound_set): whole runs are bit-identical."""
+    from dynesty_b200 import _lib
     out = []
     for dev in (True, False):
-        s = nested.NestedSampler(DL.gauss_corr(6, 0.4, 5.0), nlive=200, bound=bound, sample=sample, seed=12, **kw)
+        ctx = _lib.Context(0)       # a fresh context per run: a ctx remembers whether the Cholesky candidate path failed
+        s = nested.NestedSampler(DL.gauss_corr(6, 0.4, 5.0), nlive=200, bound=bound, sample=sample, seed=12, ctx=ctx,
+                                 **kw)                          # recently (bound_fast_skip) -- run history, not input
         s.device_bound = dev
         r = s.run_nested(loop='device', batch=10, dlogz=0.5)
         out.append((r, s))
