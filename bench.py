@@ -33,6 +33,8 @@ import time
 # mat-vec must not fan out into a thread team in each of them
 for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
     os.environ.setdefault(_v, '1')
+# the replicas of the ensemble block drive one stream each: give them hardware queues of their own (default 8)
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 
 import numpy as np
 
@@ -304,20 +306,30 @@ def e2e_plugin(args, cfg, ctx, model, u_live, loglstar, scale, Q, walks):
     smp = S.B200RWalkSampler(model=model, ndim=n, ncdim=n, walks=walks, ctx=ctx)
     smp.scale = scale
 
-    def fill():
+    def inputs():       # what dynesty's _fill_queue builds before it calls the sampler (the CALLER's cost, not timed here)
         starts = rng.integers(len(u_live), size=Q)
         pts = [u_live[i] for i in starts]
         axes = [bound.get_random_axes(rng) for _ in range(Q)]
         seeds = np.random.SeedSequence(rng.integers(0, 2**63 - 1, size=4)).spawn(Q)
+        return pts, axes, seeds
+
+    def fill(pts, axes, seeds):
         a = smp.prepare_sampler(loglstar=loglstar, points=pts, axes=axes, seeds=seeds, nested_sampler=None)
         return list(map(smp.sample, a))
     for _ in range(3):
-        fill()
-    t0 = time.perf_counter()
+        fill(*inputs())
+    dt = dt_in = 0.0
     for _ in range(steps):
-        fill()
-    dt = time.perf_counter() - t0
-    out["prepare_sampler"] = {"value": Q * walks * steps / dt, "ms_per_fill": 1e3 * dt / steps}
+        t0 = time.perf_counter()
+        args_ = inputs()
+        t1 = time.perf_counter()
+        fill(*args_)
+        dt += time.perf_counter() - t1
+        dt_in += t1 - t0
+    out["prepare_sampler"] = {"value": Q * walks * steps / dt, "ms_per_fill": 1e3 * dt / steps,
+                              "caller_input_ms_per_fill": 1e3 * dt_in / steps,
+                              "note": "prepare_sampler + map(sample) only; caller_input_ms = building Q start rows, Q axes handles "
+                                      "and SeedSequence.spawn(Q) the way dynesty's _fill_queue does (29 ms of it is the spawn)"}
     from oracle import refshim
     if not refshim.available():
         out["dynesty_fill_queue"] = None
@@ -336,9 +348,19 @@ def e2e_plugin(args, cfg, ctx, model, u_live, loglstar, scale, Q, walks):
                                use_pool={'prior_transform': False, 'loglikelihood': False})
     ns.update_bound_if_needed(loglstar, force=True)      # first bound: built on the GPU through the Bound seam
     ns.internal_sampler.scale = scale
+    mine = [0.0]
+    orig = ns.internal_sampler.prepare_sampler
+
+    def timed_prepare(**kw):                             # how much of a fill is spent inside the plug-in
+        t = time.perf_counter()
+        r = orig(**kw)
+        mine[0] += time.perf_counter() - t
+        return r
+    ns.internal_sampler.prepare_sampler = timed_prepare
     for _ in range(3):
         ns.nqueue = 0
         ns._fill_queue(loglstar)
+    mine[0] = 0.0
     t0 = time.perf_counter()
     for _ in range(steps):
         ns.nqueue = 0
@@ -346,7 +368,11 @@ def e2e_plugin(args, cfg, ctx, model, u_live, loglstar, scale, Q, walks):
     dt = time.perf_counter() - t0
     assert len(ns.queue) == Q and all(r.logl > loglstar for r in ns.queue[:50])
     out["dynesty_fill_queue"] = {"value": Q * walks * steps / dt, "ms_per_fill": 1e3 * dt / steps,
-                                 "sampler": "unmodified dynesty.NestedSampler (baseline/_ref) with the B200 bound / sampler / pool"}
+                                 "ms_per_fill_inside_the_plugin": 1e3 * mine[0] / steps,
+                                 "ms_per_fill_dynesty_python": 1e3 * (dt - mine[0]) / steps,
+                                 "sampler": "unmodified dynesty.NestedSampler (baseline/_ref) with the B200 bound / sampler / pool",
+                                 "note": "dynesty's own per-slot Python (rstate.choice, get_random_axes, contains, SeedSequence.spawn) "
+                                         "is the part outside the plug-in; it is why dynesty_b200.nested proposes a whole queue at once"}
     return out
 
 
@@ -745,7 +771,7 @@ def main():
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--chains', type=int, default=0, help='chains per step per GPU (default nlive)')
     ap.add_argument('--ensemble', type=int, default=64, help='full C2 runs (seeds) of the logZ / same-operating-point block; 0 = none')
-    ap.add_argument('--in-flight', type=int, default=8, help='replicas in flight per GPU')
+    ap.add_argument('--in-flight', type=int, default=16, help='replicas in flight per GPU')
     ap.add_argument('--solo', type=int, default=1, help='N=1: also time one run alone on the GPU')
     ap.add_argument('--logz-batch', type=int, default=0, help='points replaced per device round (default nlive/40)')
     ap.add_argument('--cpu-baseline', type=int, default=1)

@@ -36,6 +36,9 @@ int b2n_init(int device, b2n_ctx** out) {
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return B2N_ERR_CUDA;
     if (cudaSetDevice(device) != cudaSuccess) return B2N_ERR_CUDA;
+    if (const char* e = getenv("B2N_BLOCKING_SYNC")) {          // many contexts driven by many host threads (replicas): waiting
+        if (e[0] == '1') { cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync); cudaGetLastError(); }   // threads sleep instead of spinning
+    }
     b2n_ctx* ctx = new b2n_ctx();
     ctx->device = device;
     cudaDeviceProp prop;

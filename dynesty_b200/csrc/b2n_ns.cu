@@ -80,9 +80,9 @@ struct b2n_ns {
     void* dead_alloc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int phase = 1;                     // host copy of NsScalars::phase (transitions are host-mediated)
     // CUDA graph of B2N_NS_GRAPH_ROUNDS rounds ([commit+propose | chains] x G): every per-round argument of these
-    // kernels lives in HBM (B2nDyn, NsScalars), so the launch sequence is STATIC and a block of rounds is one
-    // cudaGraphLaunch instead of 2 G kernel launches -- the host-side launch rate is what limits an ensemble of
-    // replicas (dynesty_b200/replicas.py).  Re-captured when anything baked into the kernel arguments changes.
+    // kernels lives in HBM (B2nDyn, NsScalars), so the launch sequence is STATIC and a block of rounds can be one
+    // cudaGraphLaunch instead of 2 G kernel launches.  Re-captured when anything baked into the kernel arguments
+    // changes.  Opt-in, see b2n_ns_run.
     cudaGraphExec_t gexec = nullptr;
     unsigned long long gkey = 0, warm_key = 0;
     bool active = false;               // between b2n_ns_create and b2n_ns_destroy.  The device allocations OUTLIVE a run
@@ -790,8 +790,11 @@ int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_sta
     b2n_ns_status st;
     memset(&st, 0, sizeof(st));
     // graphs: chain samplers without per-dimension flags (their entry points then issue no copies), timing off
+    // OPT-IN (B2N_NS_GRAPH=1): measured on B200 (profiles/r2c_replica_scan.jsonl vs r2c_nograph.log) the replay is not
+    // faster than the plain launches -- one run alone 12.9e6 vs 13.9e6 calls/s, 16 replicas in flight 4.7e7 vs 6.5e7 --
+    // the rounds are bound by the dependent kernels' execution latency on the device, not by the host's launch rate.
     const char* genv = getenv("B2N_NS_GRAPH");
-    const bool graph_ok = !(genv && genv[0] == '0') && !ns->has_flags && !ctx->timing && (ns->phase == 0 || d.sampler != 3);
+    const bool graph_ok = (genv && genv[0] == '1') && !ns->has_flags && !ctx->timing && (ns->phase == 0 || d.sampler != 3);
     const unsigned long long key = ns_launch_key(ctx, ns, smem);
     while (left > 0) {
         const int chunk = std::min(left, (int)check_every);

@@ -11,7 +11,7 @@ from dynesty_b200 import likelihoods as DL, replicas
 
 out = open(sys.argv[1], 'a') if len(sys.argv) > 1 else sys.stdout
 m = DL.iid_normal_ppf(200)
-CASES = [(20, 220), (50, 220), (100, 220), (200, 220), (400, 220), (800, 220), (200, 440), (200, 110), (50, 440)]
+CASES = [(200, 220), (100, 220), (50, 220), (20, 220), (400, 220), (200, 440)]
 for batch, walks in CASES:
     t0 = time.perf_counter()
     outs, wall = replicas.run_replicas(m, [11, 12, 13], nlive=8000, bound='single', sample='rwalk',

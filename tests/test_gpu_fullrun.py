@@ -45,19 +45,22 @@ def test_c2_logz_matches_reference_runs():
 
 
 def test_c4_logz_single_ellipsoid_200d():
-    """C4: 200-D iid normal, normal-ppf prior, single / rwalk (walks 220), nlive 8000.  Truth -253.102; the
-    unmodified reference gives -250.18 / -249.75 (profiles/ref_c4_rwalk_nlive8000.jsonl: +3 from the truth --
-    chains of 220 steps do not decorrelate in 200-D); the device rounds at batch nlive/40 stay within 2 of the
-    truth and on the OTHER side of it (DESIGN.md 9.5 explains the sign through the batch sweep)."""
+    """C4: 200-D iid normal, normal-ppf prior, single / rwalk (walks 220), nlive 8000.  Analytic value -253.102; the
+    UNMODIFIED reference gives -250.18 / -249.75 (profiles/ref_c4_rwalk_nlive8000.jsonl): +3 from the truth, chains of
+    220 steps do not decorrelate in 200-D -- the reference's bias, not the kernels' (with walks = 440 the device rounds
+    give -252.1, profiles/r2c_c4_sweep.jsonl).  The device rounds reproduce the REFERENCE's value at any round size
+    (batch 20 .. 400: -249.5 .. -250.1, same file): that is the parity statement, tolerance 1.0 (the runs' quoted
+    logzerr is 1.4, the scatter of the sweep 0.3)."""
     m = DL.iid_normal_ppf(200)
     outs, wall = replicas.run_replicas(m, [1, 2, 3, 4], nlive=8000, bound='single', sample='rwalk',
                                        sampler_kwargs=dict(walks=220), max_in_flight=4)
     lz = np.array([o['logz'] for o in outs])
-    assert abs(lz.mean() - m.logz_truth) < 2.0, lz
     ref = _ref('ref_c4_rwalk_nlive8000.jsonl')
-    if ref:
-        rz = np.array([r['logz'] for r in ref])
-        assert abs(lz.mean() - m.logz_truth) <= abs(rz.mean() - m.logz_truth) + 0.5     # no worse than the reference
+    assert ref
+    rz = np.array([r['logz'] for r in ref])
+    assert abs(lz.mean() - rz.mean()) < 1.0, (lz, rz)
+    assert lz.std(ddof=1) < 1.0
+    assert all(1.2e5 < o['niter'] < 1.9e5 for o in outs)               # the reference: 1.48e5 iterations
 
 
 def test_c5_static_shells_10d():
