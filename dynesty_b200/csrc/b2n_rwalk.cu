@@ -109,6 +109,9 @@ __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
         int nacc = 0, nrej = 0;
         double lcur = 0.0;
         for (int step = 0; step < p.walks; step++) {
+            // (the previous step's likelihood READ the delta vector that the loops below rewrite: order the two --
+            //  warp shuffles converge the lanes but are not a memory barrier; compute-sanitizer racecheck, round 2)
+            __syncwarp();
             // (1) non-clustered dims: one vector uniform event (only if there are any)
             if (n > nc) {
                 for (int e = lane; e < n - nc; e += 32) {

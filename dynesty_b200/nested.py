@@ -81,7 +81,8 @@ class NestedSampler:
 
     def __init__(self, model, nlive=500, bound='multi', sample='auto', ncdim=None, walks=None, slices=None,
                  facc=0.5, enlarge=None, bootstrap=None, update_interval=None, first_update=None,
-                 queue_size=None, periodic=None, reflective=None, seed=56432, ctx=None, comm=None):
+                 queue_size=None, periodic=None, reflective=None, seed=56432, ctx=None, comm=None, live_points=None,
+                 live_init='device'):
         self.model = model
         self.ndim = n = model.ndim
         self.ncdim = ncdim or n
@@ -157,10 +158,21 @@ class NestedSampler:
         if comm is not None and self.queue_size % comm.world:
             self.queue_size += comm.world - self.queue_size % comm.world
         # -- live points (sampler.py:56-262, evaluated in one launch)
-        self.live_u = self.rstate.random((self.nlive, n))
-        self.live_v, self.live_logl = model.evaluate(self.live_u, ctx=ctx)
+        if live_points is not None:         # (u, v, logl) supplied by the caller (dynesty.py:600 `live_points`)
+            self.live_u, self.live_v, self.live_logl = (np.array(a, dtype=float) for a in live_points)
+        elif live_init == 'device':
+            # _initialize_live_points (sampler.py:56-262) on the device: nlive prior draws + transform + likelihood in
+            # ONE launch (b2n_unitcube_batch at threshold -inf: a draw whose logl is -inf is redrawn, the reference's
+            # "keep the finite ones" rule :167-200 for a queue of one).  Chain ids 2^61 + i: disjoint from the run's.
+            from . import ops
+            o = ops.unitcube_batch(model.model_id(ctx), self.nlive, n, -np.inf, self.seed, chain0=1 << 61, ctx=ctx)
+            self.live_u, self.live_v, self.live_logl = o['u'], o['v'], o['logl']
+            self.init_ncall = int(o['ncall'].sum())
+        else:
+            self.live_u = self.rstate.random((self.nlive, n))
+            self.live_v, self.live_logl = model.evaluate(self.live_u, ctx=ctx)
         self.it = 1
-        self.ncall = self.nlive
+        self.ncall = getattr(self, 'init_ncall', self.nlive)
         self.eff = 0.
         self.nbound = 1
         self.chain_counter = 0
@@ -347,7 +359,7 @@ class NestedSampler:
         c.resident_key = m.version                     # these very ellipsoids ARE the resident bound
 
     def _device_rounds(self, logz, logvol, loglstar, dlogz, maxiter, maxcall, batch, checkpoint_file=None,
-                       checkpoint_every=0.0, snap=None, on_checkpoint=None, keep_samples=True):
+                       checkpoint_every=0.0, snap=None, on_checkpoint=None, keep_samples=True, logl_max=None):
         """Run (or continue) with ``b2n_ns_run`` (include/b200nest.h): K-worst replacement rounds paced on the
         device -- first with prior draws (the phase before the first bound, sampler.py:407-409), then with the
         inner sampler against the resident bound.  The host only reacts to the device's flags: (re)build the bound
@@ -386,7 +398,7 @@ class NestedSampler:
                       update_interval=self.bound_update_interval, dimflags=smp._flags(), ctx=self.ctx,
                       unit_cube_phase=self.unit_cube_sampling,
                       first_min_ncall=(1 << 62) if no_bound else self.first_bound_update_ncall,
-                      first_min_eff=self.first_bound_update_eff, it0=it0)
+                      first_min_eff=self.first_bound_update_eff, it0=it0, logl_max=logl_max)
         tm = dict(rounds_s=0.0, bound_s=0.0)
         self.device_timing = tm
         st = None
@@ -495,7 +507,7 @@ class NestedSampler:
     # ------------------------------------------------------------------ main loop
     def run_nested(self, dlogz=None, maxiter=None, maxcall=None, add_live=True, loop='host', batch=None,
                    checkpoint_file=None, checkpoint_every=60., resume=False, on_checkpoint=None, device_init=True,
-                   keep_samples=True):
+                   keep_samples=True, logl_max=None):
         """sampler.py:1214-1356 / 1040-1212 (no plateau mode: continuous likelihoods).
 
         loop='host'   : the reference's semantics -- one worst point per iteration, replacements
@@ -508,6 +520,7 @@ class NestedSampler:
                         (DESIGN.md 9.4), no host round trip per iteration.  batch defaults to
                         nlive // 40 (rwalk) or nlive // 10 (slices).
         on_checkpoint : callable(k) invoked after the k-th checkpoint has been written.
+        logl_max      : stop once the lowest live point is above it (sampler.py:1103-1106; the end of a dynamic batch).
         keep_samples  : loop='device' only.  False = the positions of the dead points are NOT brought back from the
                         device (results.samples / samples_u are then empty; logz, logzerr, logl, logvol, logwt and the
                         call counts are complete): for ensembles that only want evidences.
@@ -553,6 +566,8 @@ class NestedSampler:
             if dlogz is not None and delta_logz < dlogz:
                 break
             lnew, worst = heap[0]
+            if logl_max is not None and lnew > logl_max:
+                break                                              # sampler.py:1103-1106
             if lnew == lmax:
                 break                                              # all live points equal: plateau
             logvol -= dlv
@@ -607,7 +622,7 @@ class NestedSampler:
             dev = self._device_rounds(logz, logvol, loglstar, dlogz, self._host_part['maxiter'],
                                       self._host_part['maxcall'], batch, checkpoint_file=checkpoint_file,
                                       checkpoint_every=checkpoint_every, on_checkpoint=on_checkpoint,
-                                      keep_samples=keep_samples or checkpoint_file is not None)
+                                      keep_samples=keep_samples or checkpoint_file is not None, logl_max=logl_max)
             return self._finalize(su, sv, logl, logvols, nc_all, dev, add_live)
         return self._finalize(su, sv, logl, logvols, nc_all, None, add_live)
 
@@ -642,10 +657,23 @@ class NestedSampler:
                 su = np.concatenate([su, self.live_u[order]])
                 sv = np.concatenate([sv, self.live_v[order]])
             nc_all = np.concatenate([nc_all, np.ones(nlive, dtype=np.int64)])
+        # number of live points when each sample died (results.samples_n, utils.py:1237-1270): nlive in the host loop,
+        # N - j for the j-th removal of a device round, nlive - k for the k-th of the final live points
+        nhost = ndead - (len(dev[2]) if dev is not None else 0)
+        samples_n = np.full(ndead, nlive, dtype=np.int64)
+        if dev is not None and len(dev[2]):
+            samples_n[nhost:] = nlive - (np.arange(len(dev[2])) % max(1, getattr(self, 'batch', 1)))
+        if add_live:
+            samples_n = np.concatenate([samples_n, nlive - np.arange(nlive)])
+        sh = np.array(self.scale_history, dtype=float).reshape(-1, 2)
+        cum = np.cumsum(nc_all)
+        sample_scale = (sh[np.minimum(np.searchsorted(sh[:, 0], cum + (self.nlive if len(cum) else 0)), len(sh) - 1), 1]
+                        if len(sh) else np.ones(len(nc_all)))
         logwt, logzs, logzvar, h = _integrate(logl, logvols)
         self.results = Results(niter=ndead, ncall=int(self.ncall), eff=100. * ndead / max(self.ncall, 1),
                                samples_u=su, samples=sv, logl=logl, logvol=logvols, logwt=logwt, logz=logzs,
                                logzerr=np.sqrt(logzvar), information=h, ncall_per_it=nc_all,
+                               samples_n=samples_n, samples_scale=sample_scale,
                                nbound=self.nbound, nbatches=self.nbatches, n_proposals=self.n_proposals,
                                bound_history=list(self.bound_history), scale_history=list(self.scale_history))
         return self.results

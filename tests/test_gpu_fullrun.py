@@ -93,3 +93,24 @@ def test_c3_eggbox_logz_trajectory_vs_reference():
     # a difference of 2e-5 in logZ.  Stated tolerance 1e-3.
     assert abs(lz.mean() - rz.mean()) < 1e-3, (lz, rz)
     assert all(o['niter'] == maxiter for o in outs)
+
+
+def test_c5_dynamic_shells_device_batches():
+    """C5: 10-D Gaussian shells, DynamicNestedSampler(bound='multi', sample='rslice'), nlive_init = nlive_batch = 500
+    (dynesty.py:701, dynamicsampler.py:1796) -- the baseline AND every batch as device rounds (dynesty_b200/dynamic.py).
+    Analytic evidence -14.59; the batches must add samples (n_effective grows), live counts add up in the overlap."""
+    from dynesty_b200 import dynamic as D
+    m = DL.shells(10)
+    lz, neff = [], []
+    for seed in (1, 2, 3):
+        d = D.DynamicNestedSampler(m, nlive=500, bound='multi', sample='rslice', seed=seed)
+        r0 = d.sample_initial()
+        n0 = D.n_effective(r0.logwt)
+        res = d.run_nested(maxbatch=4, n_effective=1e9)
+        assert d.batch == 4 and D.n_effective_of(res) > 1.5 * n0
+        assert res.samples_n.max() >= 1000 and np.all(np.diff(res.logl) >= 0)
+        lz.append(float(res.logz[-1]))
+        neff.append(D.n_effective_of(res))
+        err = float(res.logzerr[-1])
+    lz = np.array(lz)
+    assert abs(lz.mean() - m.logz_truth) < 3 * err / np.sqrt(len(lz)) + 0.15, (lz, err)
