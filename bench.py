@@ -770,7 +770,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--chains', type=int, default=0, help='chains per step per GPU (default nlive)')
-    ap.add_argument('--ensemble', type=int, default=64, help='full C2 runs (seeds) of the logZ / same-operating-point block; 0 = none')
+    ap.add_argument('--ensemble', type=int, default=256, help='full C2 runs (seeds) of the logZ / same-operating-point block; 0 = none')
     ap.add_argument('--in-flight', type=int, default=16, help='replicas in flight per GPU')
     ap.add_argument('--solo', type=int, default=1, help='N=1: also time one run alone on the GPU')
     ap.add_argument('--logz-batch', type=int, default=0, help='points replaced per device round (default nlive/40)')
