@@ -647,7 +647,11 @@ int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* c, int64_t dead_capacity) {
     d.Npad = Npad;
     d.Kpad = 2;
     while (d.Kpad < c->batch) d.Kpad <<= 1;
-    d.threads = B2N_NS_THREADS;
+    // threads of the single-CTA step kernel.  1024 threads x 64 registers is a WHOLE SM's register file: alone on the
+    // GPU that is the fastest, but with other contexts' chain CTAs resident everywhere (replicas) such a CTA waits for
+    // an SM to drain completely -- b2n_set_chain_pack(k > 1) ("this context shares the GPU") selects 256 threads.
+    d.threads = ctx->min_cpc > 1 ? 256 : B2N_NS_THREADS;
+    if (const char* e = getenv("B2N_NS_THREADS")) d.threads = atoi(e) >= 1024 ? 1024 : (atoi(e) >= 512 ? 512 : 256);
     d.dlogz = c->dlogz; d.facc = c->facc; d.maxiter = c->maxiter; d.maxcall = c->maxcall;
     d.update_interval = c->update_interval; d.seed = c->seed; d.chain0 = c->chain0;
     d.first_min_ncall = c->first_min_ncall; d.first_min_eff = c->first_min_eff; d.it0 = c->it0;
@@ -807,7 +811,7 @@ int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_sta
                 B2N_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
                 int cst = B2N_OK;
                 for (int q = 0; q < B2N_NS_GRAPH_ROUNDS && cst == B2N_OK; q++) {
-                    ns_step_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d, 3);
+                    ns_step_kernel<<<1, d.threads, smem, ctx->stream>>>(d, 3);
                     cst = ns_chain_call(ctx, ns, false);
                 }
                 const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
@@ -827,12 +831,12 @@ int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_sta
             }
         }
         for (; r < chunk; r++) {
-            ns_step_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d, 3);
+            ns_step_kernel<<<1, d.threads, smem, ctx->stream>>>(d, 3);
             B2N_LAUNCH_CHECK(ctx);
             B2N_TRY(ns_chain_call(ctx, ns, false));
         }
         ns->warm_key = key;             // these very launches have been issued once outside a capture (buffers exist)
-        ns_step_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d, 1);
+        ns_step_kernel<<<1, d.threads, smem, ctx->stream>>>(d, 1);
         B2N_LAUNCH_CHECK(ctx);
         left -= chunk;
         B2N_TRY(ns_status(ctx, &st));
