@@ -68,6 +68,7 @@ SYMBOLS = {
     'b2n_set_pointer_mode': (C.c_int, [_P, C.c_int]),
     'b2n_synchronize': (C.c_int, [_P]),
     'b2n_set_chain_pack': (C.c_int, [_P, _I]),
+    'b2n_debug_launch_rate': (C.c_int, [_P, _I, C.POINTER(_D)]),
     'b2n_strerror': (C.c_char_p, [C.c_int]),
     'b2n_last_error': (C.c_char_p, [_P]),
     'b2n_version': (C.c_char_p, []),

@@ -691,7 +691,7 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
         B2N_CUDA(ctx, ctx->scratch2.ensure((size_t)nnodes * mats_b));
         gwork = ctx->scratch2.as<double>();
     }
-    B2N_CUDA(ctx, cudaFuncSetAttribute(eig_ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem));
+    B2N_TRY(b2n_func_smem(ctx, (const void*)(eig_ladder_kernel), (size_t)(eig_smem)));
     // one warp per rotation pair of a Jacobi round (n/2 pairs), at least 4 warps for the O(n^2) loops
     const int eig_threads = 32 * std::max(4, std::min(32, half));
     const size_t fm_smem = (size_t)8 * n * sizeof(double);
@@ -734,7 +734,7 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
         int sliced = 0;
         if (candidate) {            // Cholesky path (pass 0 only: certified nodes never need the second pass)
             const size_t csm = (size_t)(2 * n * ld + 3 * n + 32) * sizeof(double);
-            B2N_CUDA(ctx, cudaFuncSetAttribute(chol_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+            B2N_TRY(b2n_func_smem(ctx, (const void*)(chol_node_kernel), (size_t)(csm)));
             chol_node_kernel<<<pn, 512, csm, st>>>(w.na, (const int*)plist);
             B2N_LAUNCH_CHECK(ctx);
         } else if (!use_smem) B2N_TRY(b2n_eig_sliced(w, (const int*)plist, pn, pass, 0, &sliced));
@@ -749,7 +749,7 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
         // read back the node stats (one copy of the whole small array)
         B2N_CUDA(ctx, cudaStreamSynchronize(st));
         std::vector<NodeStat> all(w.cap);
-        B2N_CUDA(ctx, cudaMemcpy(all.data(), w.na.stat, (size_t)w.cap * sizeof(NodeStat), cudaMemcpyDeviceToHost));
+        B2N_CUDA(ctx, b2n_copy_sync(ctx, all.data(), w.na.stat, (size_t)w.cap * sizeof(NodeStat), cudaMemcpyDeviceToHost));
         for (int i = 0; i < nnodes; i++) {
             if (pass == 1 && (hs[i].good || hs[i].error)) continue;
             hs[i] = all[refs[i].node];
@@ -789,7 +789,7 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
             scale_finish_kernel<<<(unsigned)refs3.size(), 1024, 0, st>>>(w.na, (const NodeRef*)r3, partial, pass, w.logvol_pref, B2N_FMAX_SUB);
             B2N_LAUNCH_CHECK(ctx);
             B2N_CUDA(ctx, cudaStreamSynchronize(st));
-            B2N_CUDA(ctx, cudaMemcpy(all.data(), w.na.stat, (size_t)w.cap * sizeof(NodeStat), cudaMemcpyDeviceToHost));
+            B2N_CUDA(ctx, b2n_copy_sync(ctx, all.data(), w.na.stat, (size_t)w.cap * sizeof(NodeStat), cudaMemcpyDeviceToHost));
             for (int i : which) hs[i] = all[refs[i].node];
         }
     }
@@ -938,7 +938,7 @@ extern "C" int b2n_improve_covar(b2n_ctx* ctx, const double* covar, int32_t n, d
         B2N_TRY(b2n_eig_sliced(w, (const int*)dlist, 1, 0, 0, &sliced));
         for (int attempt = 1; sliced && attempt <= 100; attempt++) {        // one decomposition per launch
             B2N_CUDA(ctx, cudaStreamSynchronize(st));
-            B2N_CUDA(ctx, cudaMemcpy(&hs, w.na.stat, sizeof(NodeStat), cudaMemcpyDeviceToHost));
+            B2N_CUDA(ctx, b2n_copy_sync(ctx, &hs, w.na.stat, sizeof(NodeStat), cudaMemcpyDeviceToHost));
             if (!hs.retry) break;
             int used = 0;
             B2N_TRY(b2n_eig_sliced(w, (const int*)dlist, 1, 0, 1, &used));
@@ -951,12 +951,12 @@ extern "C" int b2n_improve_covar(b2n_ctx* ctx, const double* covar, int32_t n, d
             B2N_CUDA(ctx, ctx->scratch2.ensure(mats_b));
             gwork = ctx->scratch2.as<double>();
         }
-        B2N_CUDA(ctx, cudaFuncSetAttribute(eig_ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem));
+        B2N_TRY(b2n_func_smem(ctx, (const void*)(eig_ladder_kernel), (size_t)(eig_smem)));
         eig_ladder_kernel<<<1, 32 * std::max(4, std::min(32, half)), eig_smem, st>>>(w.na, (const int*)dlist, 0, gwork, use_smem);
         B2N_LAUNCH_CHECK(ctx);
     }
     B2N_CUDA(ctx, cudaStreamSynchronize(st));
-    B2N_CUDA(ctx, cudaMemcpy(&hs, w.na.stat, sizeof(NodeStat), cudaMemcpyDeviceToHost));
+    B2N_CUDA(ctx, b2n_copy_sync(ctx, &hs, w.na.stat, sizeof(NodeStat), cudaMemcpyDeviceToHost));
     if (good) *good = hs.good;
     if (warn) *warn = hs.fallback ? B2N_WARN_IDENTITY_FALLBACK : 0u;
     B2N_TRY(emit_node(w, 0, 0, nullptr, cov_out, am, axes, nullptr));

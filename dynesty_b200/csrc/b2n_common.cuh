@@ -120,6 +120,10 @@ struct b2n_ctx {
     int64_t wl_Q = -1;
     int wl_cpc = 0, wl_ncta = 0;
 };
+// cudaFuncAttributeMaxDynamicSharedMemorySize, raised ONCE per (device, kernel) and never lowered: the attribute is
+// process-wide per device, so two contexts of different problem sizes must not shrink each other's limit, and a driver
+// call per launch is a lock every replica thread would queue on (b2n_ctx.cu)
+int b2n_func_smem(b2n_ctx* ctx, const void* func, size_t bytes);
 void b2n_ns_release(b2n_ctx* ctx);
 void b2n_friends_release(b2n_ctx* ctx);
 int b2n_bound_set_dev(b2n_ctx* ctx, int K, int nc, const double* dctrs, const double* dams, const double* daxes,
@@ -158,6 +162,14 @@ void b2n_peer_release(b2n_ctx* ctx);
         (ctx)->launches++;                    \
         B2N_CUDA(ctx, cudaGetLastError());    \
     } while (0)
+
+// Blocking copy ON THE CONTEXT'S STREAM (cudaMemcpy proper runs on the legacy default stream, a process-wide object
+// every replica thread would serialise on).
+static inline cudaError_t b2n_copy_sync(b2n_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(ctx->stream);
+}
 
 static inline int b2n_fail(b2n_ctx* ctx, int status, const char* msg) {
     snprintf(ctx->err, sizeof(ctx->err), "%s", msg);

@@ -2,6 +2,22 @@
 // evaluation.  Part of libb200nest.so (C ABI in include/b200nest.h).
 #include "b2n_device.cuh"
 #include <algorithm>
+#include <time.h>
+#include <map>
+#include <mutex>
+
+static std::mutex g_smem_mu;
+static std::map<std::pair<int, const void*>, size_t> g_smem_limit;
+
+int b2n_func_smem(b2n_ctx* ctx, const void* func, size_t bytes) {
+    if (bytes <= 48 * 1024) return B2N_OK;                      // the default limit needs no opt-in
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    size_t& cur = g_smem_limit[std::make_pair(ctx->device, func)];
+    if (bytes <= cur) return B2N_OK;
+    B2N_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+    return B2N_OK;
+}
 
 extern "C" {
 
@@ -98,6 +114,25 @@ int b2n_set_stream(b2n_ctx* ctx, void* s) {
 int b2n_set_pointer_mode(b2n_ctx* ctx, int mode) {
     if (!ctx || (mode != B2N_PTR_HOST && mode != B2N_PTR_DEVICE)) return B2N_ERR_ARG;
     ctx->ptr_mode = mode;
+    return B2N_OK;
+}
+
+}  // extern "C"
+__global__ void b2n_noop_kernel(int* p) { if (p && threadIdx.x == 9999) *p = 0; }
+extern "C" {
+
+int b2n_debug_launch_rate(b2n_ctx* ctx, int32_t nlaunch, double* us_per_launch) {
+    if (!ctx || nlaunch < 1 || !us_per_launch) return B2N_ERR_ARG;
+    B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int i = 0; i < nlaunch; i++) b2n_noop_kernel<<<1, 32, 0, ctx->stream>>>(nullptr);
+    clock_gettime(CLOCK_MONOTONIC, &t1);                     // host time to ENQUEUE (the queue may back-pressure)
+    B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B2N_CUDA(ctx, cudaGetLastError());
+    ctx->launches += nlaunch;
+    *us_per_launch = ((t1.tv_sec - t0.tv_sec) * 1e6 + (t1.tv_nsec - t0.tv_nsec) * 1e-3) / nlaunch;
     return B2N_OK;
 }
 
@@ -286,8 +321,7 @@ extern "C" int b2n_model_eval(b2n_ctx* ctx, int32_t id, const double* u, int64_t
     if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
 #define CALL(L)                                                                                   \
     if (smem > 48 * 1024)                                                                          \
-        B2N_CUDA(ctx, cudaFuncSetAttribute(model_eval_kernel<L>,                                   \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        B2N_TRY(b2n_func_smem(ctx, (const void*)(model_eval_kernel<L>), (size_t)(smem))); \
     model_eval_kernel<L><<<(unsigned)blocks, threads, smem, ctx->stream>>>(                         \
         m, (const double*)du, M, (double*)dv, (double*)dl);
     B2N_DISPATCH_LIKE(m.like_kind, CALL)

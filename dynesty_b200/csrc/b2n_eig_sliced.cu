@@ -354,7 +354,7 @@ int b2n_eig_sliced(BoundWork& w, const int* dlist, int pn, int pass, int retry_o
         eig_init_kernel<<<pn, 256, 0, st>>>(w.na, dlist, pass);
         B2N_LAUNCH_CHECK(ctx);
     }
-    B2N_CUDA(ctx, cudaFuncSetAttribute(eig_sliced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2N_TRY(b2n_func_smem(ctx, (const void*)(eig_sliced_kernel), (size_t)(smem)));
     const int threads = 32 * std::max(8, std::min(32, half));
     eig_sliced_kernel<<<dim3(pn, EIG_SLICES), threads, smem, st>>>(w.na, dlist, retry_only, gVT, gLam, gSweeps);
     B2N_LAUNCH_CHECK(ctx);

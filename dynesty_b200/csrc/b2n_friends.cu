@@ -402,7 +402,7 @@ int b2n_friends_update(b2n_ctx* ctx, const double* points, int64_t N, int32_t n,
     const size_t nn = (size_t)n * n;
     const double* dP;
     B2N_TRY(friends_dev_in(ctx, ctx->in0, points, (size_t)N * n * sizeof(double), &dP));
-    B2N_CUDA(ctx, cudaFuncSetAttribute(friends_metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)met_smem));
+    B2N_TRY(b2n_func_smem(ctx, (const void*)(friends_metric_kernel), (size_t)(met_smem)));
     // scratch: [metric out 3nn | scal 2 | y N*n | over N*n | dist N | rmax 1]
     const size_t words = 3 * nn + 2 + 2 * (size_t)N * n + (size_t)N + 2;
     B2N_CUDA(ctx, ctx->out0.ensure(words * sizeof(double)));
@@ -448,7 +448,7 @@ int b2n_friends_update(b2n_ctx* ctx, const double* points, int64_t N, int32_t n,
             B2N_CUDA(ctx, cudaStreamSynchronize(st));
             if (!*hchg) break;
         }
-        B2N_CUDA(ctx, cudaMemcpy(lab.data(), lin, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost));
+        B2N_CUDA(ctx, b2n_copy_sync(ctx, lab.data(), lin, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost));
         // ---- clusters as segments of a permutation (ordered by root label = smallest member, members in index order)
         std::vector<int> order(N);
         for (int64_t i = 0; i < N; i++) order[i] = (int)i;
@@ -632,7 +632,7 @@ int b2n_friends_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, dou
     const int64_t blocks = (Q + wpb - 1) / wpb;
 #define CALL(L)                                                                                                   \
     if (smem > 48 * 1024)                                                                                         \
-        B2N_CUDA(ctx, cudaFuncSetAttribute(friends_unif_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        B2N_TRY(b2n_func_smem(ctx, (const void*)(friends_unif_kernel<L>), (size_t)(smem))); \
     friends_unif_kernel<L><<<(unsigned)blocks, threads, smem, ctx->stream>>>(p);
     B2N_DISPATCH_LIKE(m.like_kind, CALL)
 #undef CALL

@@ -58,7 +58,7 @@ int b2n_membership_dev(b2n_ctx* ctx, const double* x, int64_t M, int n, const do
     int64_t blocks = (M + wpb - 1) / wpb;
     if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
     if (smem > 48 * 1024)
-        B2N_CUDA(ctx, cudaFuncSetAttribute(membership_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2N_TRY(b2n_func_smem(ctx, (const void*)(membership_kernel), (size_t)(smem)));
     membership_kernel<<<(unsigned)blocks, threads, smem, ctx->stream>>>(x, M, n, ctrs, ams, K, strict, mask, q, d2);
     B2N_LAUNCH_CHECK(ctx);
     return B2N_OK;

@@ -275,7 +275,7 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
         nwarps >>= 1;
     const size_t km_smem = (size_t)(4 * n + (size_t)nwarps * 2 * n) * sizeof(double) + nwarps * 2 * sizeof(int);
     if (km_smem > (size_t)ctx->max_smem_optin) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for k-means kernel");
-    B2N_CUDA(ctx, cudaFuncSetAttribute(kmeans2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)km_smem));
+    B2N_TRY(b2n_func_smem(ctx, (const void*)(kmeans2_kernel), (size_t)(km_smem)));
 
     while (!frontier.empty()) {
         std::vector<int> split;

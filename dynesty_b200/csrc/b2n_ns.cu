@@ -536,11 +536,11 @@ static int ns_alloc_dead(b2n_ctx* ctx, b2n_ns* ns, long long cap) {
     if (ns->dead_alloc[0]) {
         NsScalars h;
         B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        B2N_CUDA(ctx, cudaMemcpy(&h, d.sc, sizeof(h), cudaMemcpyDeviceToHost));
+        B2N_CUDA(ctx, b2n_copy_sync(ctx, &h, d.sc, sizeof(h), cudaMemcpyDeviceToHost));
         const size_t rows = (size_t)std::min<long long>(h.it, ns->dead_cap);
         const size_t keep[5] = {rows * n * 8, rows * n * 8, rows * 8, rows * 8, rows * 4};
         for (int i = 0; i < 5; i++) {
-            if (keep[i]) B2N_CUDA(ctx, cudaMemcpy(nu[i], ns->dead_alloc[i], keep[i], cudaMemcpyDeviceToDevice));
+            if (keep[i]) B2N_CUDA(ctx, b2n_copy_sync(ctx, nu[i], ns->dead_alloc[i], keep[i], cudaMemcpyDeviceToDevice));
             cudaFree(ns->dead_alloc[i]);
         }
     }
@@ -723,9 +723,9 @@ int b2n_ns_set_state(b2n_ctx* ctx, const double* live_u, const double* live_v, c
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
     B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const size_t N = d.N, n = d.n;
-    B2N_CUDA(ctx, cudaMemcpy(d.live_u, live_u, N * n * 8, cudaMemcpyHostToDevice));
-    B2N_CUDA(ctx, cudaMemcpy(d.live_v, live_v, N * n * 8, cudaMemcpyHostToDevice));
-    B2N_CUDA(ctx, cudaMemcpy(d.live_logl, live_logl, N * 8, cudaMemcpyHostToDevice));
+    B2N_CUDA(ctx, b2n_copy_sync(ctx, d.live_u, live_u, N * n * 8, cudaMemcpyHostToDevice));
+    B2N_CUDA(ctx, b2n_copy_sync(ctx, d.live_v, live_v, N * n * 8, cudaMemcpyHostToDevice));
+    B2N_CUDA(ctx, b2n_copy_sync(ctx, d.live_logl, live_logl, N * 8, cudaMemcpyHostToDevice));
     NsScalars h;
     memset(&h, 0, sizeof(h));
     h.it = 0;                       // rows of the device dead buffer; the caller keeps its own offset
@@ -734,11 +734,13 @@ int b2n_ns_set_state(b2n_ctx* ctx, const double* live_u, const double* live_v, c
     h.logvol = logvol; h.logz = logz; h.loglstar = loglstar; h.scale = scale;
     h.lmax = -1e300; h.delta_logz = 1e300;
     h.phase = ns->phase;
-    B2N_CUDA(ctx, cudaMemcpy(d.sc, &h, sizeof(h), cudaMemcpyHostToDevice));
-    B2N_CUDA(ctx, cudaMemset(d.dyn, 0, sizeof(B2nDyn)));
+    B2N_CUDA(ctx, b2n_copy_sync(ctx, d.sc, &h, sizeof(h), cudaMemcpyHostToDevice));
+    // (stream-ordered: a legacy-default-stream memset is NOT ordered against this context's non-blocking stream -- under
+    //  load it landed between a proposal and its chain launch and zeroed the round's threshold: round 2, 32 replicas)
+    B2N_CUDA(ctx, cudaMemsetAsync(d.dyn, 0, sizeof(B2nDyn), ctx->stream));
     const size_t smem = ns_sort_smem(d);
     if (smem > (size_t)ctx->max_smem_optin) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "nlive too large for the one-CTA sort of b2n_ns");
-    B2N_CUDA(ctx, cudaFuncSetAttribute(ns_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2N_TRY(b2n_func_smem(ctx, (const void*)(ns_sort_kernel), (size_t)(smem)));
     ns_sort_kernel<<<1, B2N_NS_THREADS, smem, ctx->stream>>>(d);
     B2N_LAUNCH_CHECK(ctx);
     return B2N_OK;
@@ -788,7 +790,7 @@ int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_sta
     const size_t smem = std::max(ns_propose_smem(d), ns_commit_smem(d));
     if (smem + 2048 > (size_t)ctx->max_smem_optin)
         return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "nlive / batch too large for the one-CTA kernels of b2n_ns_run");
-    B2N_CUDA(ctx, cudaFuncSetAttribute(ns_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2N_TRY(b2n_func_smem(ctx, (const void*)(ns_step_kernel), (size_t)(smem)));
     if (check_every < 1) check_every = max_rounds > 0 ? max_rounds : 1;
     int left = max_rounds;
     b2n_ns_status st;
@@ -844,7 +846,11 @@ int b2n_ns_run(b2n_ctx* ctx, int32_t max_rounds, int32_t check_every, b2n_ns_sta
     }
     if (max_rounds == 0) B2N_TRY(ns_status(ctx, &st));
     if (out) *out = st;
-    if (st.error) return st.error;
+    if (st.error) {
+        snprintf(ctx->err, sizeof(ctx->err), "device rounds stopped with status %d after round %lld (phase %d, sampler %d, it %lld, ncall %lld)",
+                 st.error, (long long)st.rounds, ns->phase, d.sampler, (long long)st.it, (long long)st.ncall);
+        return st.error;
+    }
     return B2N_OK;
 }
 
@@ -944,11 +950,11 @@ int b2n_ns_get_bound(b2n_ctx* ctx, int32_t max_ells, double* ctrs, double* covs,
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
     B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const size_t K = ns->bK, nc = ns->d.nc, nn = nc * nc;
-    if (ctrs) B2N_CUDA(ctx, cudaMemcpy(ctrs, ns->bd_ctrs, K * nc * 8, cudaMemcpyDeviceToHost));
-    if (covs) B2N_CUDA(ctx, cudaMemcpy(covs, ns->bd_covs, K * nn * 8, cudaMemcpyDeviceToHost));
-    if (ams) B2N_CUDA(ctx, cudaMemcpy(ams, ns->bd_ams, K * nn * 8, cudaMemcpyDeviceToHost));
-    if (axes) B2N_CUDA(ctx, cudaMemcpy(axes, ns->bd_axes, K * nn * 8, cudaMemcpyDeviceToHost));
-    if (axlens) B2N_CUDA(ctx, cudaMemcpy(axlens, ns->bd_axlens, K * nc * 8, cudaMemcpyDeviceToHost));
+    if (ctrs) B2N_CUDA(ctx, b2n_copy_sync(ctx, ctrs, ns->bd_ctrs, K * nc * 8, cudaMemcpyDeviceToHost));
+    if (covs) B2N_CUDA(ctx, b2n_copy_sync(ctx, covs, ns->bd_covs, K * nn * 8, cudaMemcpyDeviceToHost));
+    if (ams) B2N_CUDA(ctx, b2n_copy_sync(ctx, ams, ns->bd_ams, K * nn * 8, cudaMemcpyDeviceToHost));
+    if (axes) B2N_CUDA(ctx, b2n_copy_sync(ctx, axes, ns->bd_axes, K * nn * 8, cudaMemcpyDeviceToHost));
+    if (axlens) B2N_CUDA(ctx, b2n_copy_sync(ctx, axlens, ns->bd_axlens, K * nc * 8, cudaMemcpyDeviceToHost));
     if (logvols) memcpy(logvols, ns->bd_hlogvols.data(), K * 8);
     return B2N_OK;
 }
@@ -969,9 +975,9 @@ int b2n_ns_get_live(b2n_ctx* ctx, double* live_u, double* live_v, double* live_l
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
     B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const size_t N = d.N, n = d.n;
-    if (live_u) B2N_CUDA(ctx, cudaMemcpy(live_u, d.live_u, N * n * 8, cudaMemcpyDeviceToHost));
-    if (live_v) B2N_CUDA(ctx, cudaMemcpy(live_v, d.live_v, N * n * 8, cudaMemcpyDeviceToHost));
-    if (live_logl) B2N_CUDA(ctx, cudaMemcpy(live_logl, d.live_logl, N * 8, cudaMemcpyDeviceToHost));
+    if (live_u) B2N_CUDA(ctx, b2n_copy_sync(ctx, live_u, d.live_u, N * n * 8, cudaMemcpyDeviceToHost));
+    if (live_v) B2N_CUDA(ctx, b2n_copy_sync(ctx, live_v, d.live_v, N * n * 8, cudaMemcpyDeviceToHost));
+    if (live_logl) B2N_CUDA(ctx, b2n_copy_sync(ctx, live_logl, d.live_logl, N * 8, cudaMemcpyDeviceToHost));
     return B2N_OK;
 }
 
@@ -984,11 +990,11 @@ int b2n_ns_get_dead(b2n_ctx* ctx, int64_t first, int64_t count, double* u, doubl
     if (first + count > ctx->ns->dead_cap) return B2N_ERR_ARG;
     const size_t n = d.n, f = (size_t)first, c = (size_t)count;
     if (c == 0) return B2N_OK;
-    if (u) B2N_CUDA(ctx, cudaMemcpy(u, d.dead_u + f * n, c * n * 8, cudaMemcpyDeviceToHost));
-    if (v) B2N_CUDA(ctx, cudaMemcpy(v, d.dead_v + f * n, c * n * 8, cudaMemcpyDeviceToHost));
-    if (logl) B2N_CUDA(ctx, cudaMemcpy(logl, d.dead_logl + f, c * 8, cudaMemcpyDeviceToHost));
-    if (logvol) B2N_CUDA(ctx, cudaMemcpy(logvol, d.dead_logvol + f, c * 8, cudaMemcpyDeviceToHost));
-    if (ncall) B2N_CUDA(ctx, cudaMemcpy(ncall, d.dead_ncall + f, c * 4, cudaMemcpyDeviceToHost));
+    if (u) B2N_CUDA(ctx, b2n_copy_sync(ctx, u, d.dead_u + f * n, c * n * 8, cudaMemcpyDeviceToHost));
+    if (v) B2N_CUDA(ctx, b2n_copy_sync(ctx, v, d.dead_v + f * n, c * n * 8, cudaMemcpyDeviceToHost));
+    if (logl) B2N_CUDA(ctx, b2n_copy_sync(ctx, logl, d.dead_logl + f, c * 8, cudaMemcpyDeviceToHost));
+    if (logvol) B2N_CUDA(ctx, b2n_copy_sync(ctx, logvol, d.dead_logvol + f, c * 8, cudaMemcpyDeviceToHost));
+    if (ncall) B2N_CUDA(ctx, b2n_copy_sync(ctx, ncall, d.dead_ncall + f, c * 4, cudaMemcpyDeviceToHost));
     return B2N_OK;
 }
 

@@ -53,7 +53,8 @@ int b2n_peer_export(b2n_ctx* ctx, uint64_t bytes, unsigned char* handle) {
     PeerState& P = ctx->peer;
     B2N_CUDA(ctx, cudaMalloc((void**)&P.win, bytes));
     P.win_bytes = bytes;
-    B2N_CUDA(ctx, cudaMemset(P.win, 0, bytes));
+    B2N_CUDA(ctx, cudaMemsetAsync(P.win, 0, bytes, ctx->stream));
+    B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     B2N_CUDA(ctx, cudaDeviceSynchronize());          // header is zero before any peer can store
     B2N_CUDA(ctx, cudaHostAlloc((void**)&P.err_host, 64, cudaHostAllocDefault));
     *P.err_host = 0;

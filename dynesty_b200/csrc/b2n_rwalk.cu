@@ -806,8 +806,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     const unsigned grid = dyn ? (unsigned)ctx->dyn.max_cta : ncta;
 #define LAUNCH(L, AXS, PRS)                                                                       \
     do {                                                                                          \
-        B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_kernel<L, AXS, PRS>,                             \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        B2N_TRY(b2n_func_smem(ctx, (const void*)(rwalk_kernel<L, AXS, PRS>), (size_t)(smem))); \
         rwalk_kernel<L, AXS, PRS><<<grid, warps * 32, smem, ctx->stream>>>(p);                    \
     } while (0)
 #define CALL(L)                                                        \
@@ -817,8 +816,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     else LAUNCH(L, false, false);
 #define LAUNCH_MMA2(L, K, D, F)                                                                      \
     do {                                                                                            \
-        B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_mma_kernel<L, K, 8, D, F>,                          \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        B2N_TRY(b2n_func_smem(ctx, (const void*)(rwalk_mma_kernel<L, K, 8, D, F>), (size_t)(smem))); \
         rwalk_mma_kernel<L, K, 8, D, F><<<grid, 256, smem, ctx->stream>>>(p);                        \
     } while (0)
 #define LAUNCH_MMA(L, K)                        \
@@ -830,8 +828,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     else if (KT == 13) { LAUNCH_MMA(L, 13) } \
     else { LAUNCH_MMA(L, 16) }
 #define CALL_MMAS(L)                                                                                  \
-    B2N_CUDA(ctx, cudaFuncSetAttribute(rwalk_mmas_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                       (int)smem));                                                  \
+    B2N_TRY(b2n_func_smem(ctx, (const void*)(rwalk_mmas_kernel<L>), (size_t)(smem)));                                                  \
     rwalk_mmas_kernel<L><<<grid, 512, smem, ctx->stream>>>(p, sXS, sYS);
     B2N_TIME_BEGIN(ctx);
     if (use_mma) {

@@ -330,8 +330,7 @@ static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slice
     const unsigned grid = dyn ? (unsigned)ctx->dyn.max_cta : ncta;
 #define LAUNCH(L, AXS, PRS)                                                                          \
     do {                                                                                             \
-        B2N_CUDA(ctx, cudaFuncSetAttribute(slice_kernel<L, RANDOM_DIR, AXS, PRS>,                     \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        B2N_TRY(b2n_func_smem(ctx, (const void*)(slice_kernel<L, RANDOM_DIR, AXS, PRS>), (size_t)(smem))); \
         slice_kernel<L, RANDOM_DIR, AXS, PRS><<<grid, warps * 32, smem, ctx->stream>>>(p);            \
     } while (0)
 #define CALL(L)                                \

@@ -290,7 +290,7 @@ extern "C" int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, 
     int64_t blocks = (Q + wpb - 1) / wpb;
 #define CALL(L)                                                                                         \
     if (smem > 48 * 1024)                                                                               \
-        B2N_CUDA(ctx, cudaFuncSetAttribute(unif_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        B2N_TRY(b2n_func_smem(ctx, (const void*)(unif_kernel<L>), (size_t)(smem))); \
     unif_kernel<L><<<(unsigned)blocks, threads, smem, ctx->stream>>>(p);
     B2N_TIME_BEGIN(ctx);
     B2N_DISPATCH_LIKE(m.like_kind, CALL)
@@ -373,7 +373,7 @@ extern "C" int b2n_unitcube_batch(b2n_ctx* ctx, const b2n_chain_args* a, double*
     const int64_t blocks = (Q + wpb - 1) / wpb;
 #define CALL(L)                                                                                             \
     if (smem > 48 * 1024)                                                                                   \
-        B2N_CUDA(ctx, cudaFuncSetAttribute(unitcube_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        B2N_TRY(b2n_func_smem(ctx, (const void*)(unitcube_kernel<L>), (size_t)(smem))); \
     unitcube_kernel<L><<<(unsigned)blocks, threads, smem, ctx->stream>>>(p);
     B2N_TIME_BEGIN(ctx);
     B2N_DISPATCH_LIKE(m.like_kind, CALL)

@@ -79,6 +79,9 @@ int  b2n_synchronize(b2n_ctx* ctx);
  * (replicas), packing k chains into a CTA (lock-step, k <= 8 / 16 depending on the kernel) leaves the SMs to the
  * other contexts at a small cost in per-launch latency.  Results do not depend on it. */
 int  b2n_set_chain_pack(b2n_ctx* ctx, int32_t chains_per_cta);
+/* diagnostic: host microseconds per launch when `nlaunch` empty kernels are enqueued back to back on the ctx stream
+ * (call it from several threads / contexts at once to see what the driver's launch path sustains) */
+int  b2n_debug_launch_rate(b2n_ctx* ctx, int32_t nlaunch, double* us_per_launch);
 const char* b2n_strerror(int status);
 const char* b2n_last_error(b2n_ctx* ctx);
 const char* b2n_version(void);
