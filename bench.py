@@ -692,7 +692,7 @@ def run_b200(args, cfg):
         batch = args.logz_batch or max(1, nlive // 40)
         seeds = list(range(SEED, SEED + args.ensemble))
         rkw = dict(nlive=nlive, bound=cfg['bound'], sample=cfg['sample'], sampler_kwargs=dict(walks=walks), device=local,
-                   max_in_flight=args.in_flight, comm=comm, batch=batch)
+                   max_in_flight=args.in_flight, chain_pack=args.chain_pack, comm=comm, batch=batch)
         replicas.run_replicas(model, seeds[:min(len(seeds), 2 * world)], **rkw)          # warm-up (allocations, clocks)
         barrier()
         t0 = time.perf_counter()
@@ -710,7 +710,8 @@ def run_b200(args, cfg):
                          "replicas in flight per GPU; proposals/s and logZ come from THE SAME runs" %
                          (len(seeds), seeds[0], seeds[-1], batch, args.in_flight)),
                 "scaling": "strong (the ensemble is fixed; ranks take seeds[rank::world])",
-                "batch": batch, "replicas": len(seeds), "in_flight_per_gpu": args.in_flight, "n_gpus": world,
+                "batch": batch, "replicas": len(seeds), "in_flight_per_gpu": args.in_flight, "chains_per_cta": args.chain_pack,
+                "n_gpus": world,
                 "wall_s": ens_wall, "proposals_per_s": summ["calls_per_s"], "calls_per_s": summ["calls_per_s"],
                 "iterations_per_s": summ["niter"] / ens_wall, "run_wall_s_mean": summ["run_wall_s_mean"],
                 "logz_mean": summ["logz_mean"], "logz_std": summ["logz_std"], "truth": model.logz_truth,
@@ -729,7 +730,7 @@ def run_b200(args, cfg):
             except Exception:
                 pass
         if world == 1 and args.solo:          # latency of ONE run with nothing else on the GPU
-            o1, w1 = replicas.run_replicas(model, [SEED], **dict(rkw, max_in_flight=1))
+            o1, w1 = replicas.run_replicas(model, [SEED], **dict(rkw, max_in_flight=1, chain_pack=1))
             line["full_runs"]["solo_run"] = {"wall_s": w1, "calls_per_s": o1[0]["ncall"] / w1, "logz": o1[0]["logz"],
                                              "rounds_s": o1[0]["rounds_s"], "bound_s": o1[0]["bound_s"],
                                              "nbound": o1[0]["nbound"], "rounds": o1[0]["rounds"]}
@@ -771,7 +772,8 @@ def main():
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--chains', type=int, default=0, help='chains per step per GPU (default nlive)')
     ap.add_argument('--ensemble', type=int, default=256, help='full C2 runs (seeds) of the logZ / same-operating-point block; 0 = none')
-    ap.add_argument('--in-flight', type=int, default=16, help='replicas in flight per GPU')
+    ap.add_argument('--in-flight', type=int, default=32, help='replicas in flight per GPU')
+    ap.add_argument('--chain-pack', type=int, default=4, help='chains per CTA of the replicas (b2n_set_chain_pack)')
     ap.add_argument('--solo', type=int, default=1, help='N=1: also time one run alone on the GPU')
     ap.add_argument('--logz-batch', type=int, default=0, help='points replaced per device round (default nlive/40)')
     ap.add_argument('--cpu-baseline', type=int, default=1)

@@ -86,6 +86,7 @@ struct b2n_ns;                   // device-resident nested-sampling run (b2n_ns.
 struct b2n_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_hi = nullptr;   // highest-priority twin of the own stream: bound updates of a device-resident run
     bool own_stream = true;
     int ptr_mode = B2N_PTR_HOST;
     int sm_count = 148;
@@ -93,6 +94,7 @@ struct b2n_ctx {
     int64_t launches = 0;
     int timing = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_block = nullptr;     // blocking-sync event: long waits of a context that shares the GPU sleep, not spin
     bool ev_valid = false;
     char err[512] = {0};
     std::vector<B2nModel> models;

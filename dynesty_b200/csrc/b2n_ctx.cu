@@ -66,6 +66,14 @@ int b2n_init(int device, b2n_ctx** out) {
         return B2N_ERR_CUDA;
     }
     ctx->own_stream = true;
+    {   // (a failure here only costs the priority)
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, hi) != cudaSuccess) {
+            ctx->stream_hi = nullptr;
+            cudaGetLastError();
+        }
+    }
     ctx->pinned_cap = 1 << 16;
     if (cudaHostAlloc(&ctx->pinned, ctx->pinned_cap, cudaHostAllocDefault) != cudaSuccess) {
         cudaStreamDestroy(ctx->stream);
@@ -93,6 +101,8 @@ void b2n_free(b2n_ctx* ctx) {
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream_hi) cudaStreamDestroy(ctx->stream_hi);
+    if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
     delete ctx;
 }
 

@@ -647,10 +647,9 @@ int b2n_ns_create(b2n_ctx* ctx, const b2n_ns_config* c, int64_t dead_capacity) {
     d.Npad = Npad;
     d.Kpad = 2;
     while (d.Kpad < c->batch) d.Kpad <<= 1;
-    // threads of the single-CTA step kernel.  1024 threads x 64 registers is a WHOLE SM's register file: alone on the
-    // GPU that is the fastest, but with other contexts' chain CTAs resident everywhere (replicas) such a CTA waits for
-    // an SM to drain completely -- b2n_set_chain_pack(k > 1) ("this context shares the GPU") selects 256 threads.
-    d.threads = ctx->min_cpc > 1 ? 256 : B2N_NS_THREADS;
+    // threads of the single-CTA step kernel (B2N_NS_THREADS=256|512 for experiments: no consistent effect measured,
+    // profiles/r2*_scan*.jsonl)
+    d.threads = B2N_NS_THREADS;
     if (const char* e = getenv("B2N_NS_THREADS")) d.threads = atoi(e) >= 1024 ? 1024 : (atoi(e) >= 512 ? 512 : 256);
     d.dlogz = c->dlogz; d.facc = c->facc; d.maxiter = c->maxiter; d.maxcall = c->maxcall;
     d.update_interval = c->update_interval; d.seed = c->seed; d.chain0 = c->chain0;
@@ -749,7 +748,15 @@ int b2n_ns_set_state(b2n_ctx* ctx, const double* live_u, const double* live_v, c
 static int ns_status(b2n_ctx* ctx, b2n_ns_status* out) {
     NsScalars* h = reinterpret_cast<NsScalars*>(ctx->pinned);
     B2N_CUDA(ctx, cudaMemcpyAsync(h, ctx->ns->d.sc, sizeof(NsScalars), cudaMemcpyDeviceToHost, ctx->stream));
-    B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->min_cpc > 1) {
+        // a context that shares the GPU (b2n_set_chain_pack > 1: replicas) waits for its block of rounds -- milliseconds --
+        // ASLEEP: dozens of host threads spinning in cudaStreamSynchronize starve the ones that have work to do
+        if (!ctx->ev_block) B2N_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
+        B2N_CUDA(ctx, cudaEventRecord(ctx->ev_block, ctx->stream));
+        B2N_CUDA(ctx, cudaEventSynchronize(ctx->ev_block));
+    } else {
+        B2N_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     if (out) {
         out->it = h->it; out->ncall = h->ncall; out->rounds = h->round;
         out->logz = h->logz; out->logvol = h->logvol; out->loglstar = h->loglstar; out->lmax = h->lmax;
@@ -882,6 +889,17 @@ int b2n_ns_update_bound(b2n_ctx* ctx, int32_t multi, double enlarge, int32_t* ne
     b2n_ns* ns = ctx->ns;
     NsDev& d = ns->d;
     B2N_CUDA(ctx, cudaSetDevice(ctx->device));
+    // The update is a chain of ~45 small dependent kernels with a dozen host round trips; with other replicas' chain
+    // CTAs filling every SM each of them used to wait its turn (68 updates cost 2.5 s per run at 48 replicas in
+    // flight against 0.18 s alone).  It runs on the context's HIGH-PRIORITY stream: its CTAs are placed before the
+    // pending CTAs of normal-priority grids.  The main stream is idle here (the rounds were synchronised).
+    struct StreamSwap {
+        b2n_ctx* c; cudaStream_t keep; bool on;
+        explicit StreamSwap(b2n_ctx* ctx) : c(ctx), keep(ctx->stream), on(ctx->own_stream && ctx->stream_hi != nullptr) {
+            if (on) { cudaStreamSynchronize(keep); c->stream = c->stream_hi; }
+        }
+        ~StreamSwap() { if (on) { cudaStreamSynchronize(c->stream_hi); c->stream = keep; } }
+    } swap_(ctx);
     const int n = d.n, nc = d.nc, N = d.N;
     const double* pts = d.live_u;
     if (nc != n) {                  // the bound lives in the first ncdim coordinates (sampler.py:497)
