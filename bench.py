@@ -692,7 +692,7 @@ def run_b200(args, cfg):
         batch = args.logz_batch or max(1, nlive // 40)
         seeds = list(range(SEED, SEED + args.ensemble))
         rkw = dict(nlive=nlive, bound=cfg['bound'], sample=cfg['sample'], sampler_kwargs=dict(walks=walks), device=local,
-                   max_in_flight=args.in_flight, chain_pack=args.chain_pack, comm=comm, batch=batch)
+                   max_in_flight=args.in_flight, chain_pack=args.chain_pack, comm=comm, batch=batch, errors='record')
         replicas.run_replicas(model, seeds[:min(len(seeds), 2 * world)], **rkw)          # warm-up (allocations, clocks)
         barrier()
         t0 = time.perf_counter()
@@ -704,13 +704,15 @@ def run_b200(args, cfg):
         ens_wall = float(tens[0])
         if rank == 0:
             summ = replicas.summarize(outs, ens_wall)
+            failed = [o for o in outs if 'error' in o]
+            outs = [o for o in outs if 'error' not in o]
             runs = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in o.items()} for o in outs]
             line["full_runs"] = {
                 "what": ("%d full C2 nested-sampling runs (seeds %d..%d), device rounds (b2n_ns_run) with batch = %d, %d "
                          "replicas in flight per GPU; proposals/s and logZ come from THE SAME runs" %
                          (len(seeds), seeds[0], seeds[-1], batch, args.in_flight)),
                 "scaling": "strong (the ensemble is fixed; ranks take seeds[rank::world])",
-                "batch": batch, "replicas": len(seeds), "in_flight_per_gpu": args.in_flight, "chains_per_cta": args.chain_pack,
+                "batch": batch, "replicas": len(seeds), "failed_replicas": [f["error"] for f in failed][:4], "in_flight_per_gpu": args.in_flight, "chains_per_cta": args.chain_pack,
                 "n_gpus": world,
                 "wall_s": ens_wall, "proposals_per_s": summ["calls_per_s"], "calls_per_s": summ["calls_per_s"],
                 "iterations_per_s": summ["niter"] / ens_wall, "run_wall_s_mean": summ["run_wall_s_mean"],

@@ -230,8 +230,8 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // which is the longest dependency chain of a step (Philox -> log -> sqrt -> sincospi).
 // FAST = the draws use the branch-free math of b2n_fastmath.cuh, two ring items at a time per warp
 // (the default; B2N_RWALK_DRAWS=libm selects libdevice math, results differ by a few ulp in the directions).
-template <int LIKE, int KT, int CH, int DEPTH, bool FAST>
-__global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(const RwalkParams p) {
+template <int LIKE, int KT, int CH, int DEPTH, bool FAST, int OCC = 2>
+__global__ void __launch_bounds__(CH * 32, CH == 8 ? OCC : 1) rwalk_mma_kernel(const RwalkParams p) {
     constexpr int B2N_MMA_CH = CH;
     constexpr int RS = 8 * ((4 * KT + 7) / 8);                    // rows padded to whole 8-row slabs
     constexpr int XS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16));   // chain stride == 4 (mod 16):
@@ -725,9 +725,12 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     // log / sqrt / sincospi, one item at a time (measured 3.6 % slower per C2 launch, results differ by a few ulp)
     const char* denv = getenv("B2N_RWALK_DRAWS");
     const bool fast_draws = !(denv && !strcmp(denv, "libm")) && DU == 8;
+    // experiment (B2N_RWALK_OCC=3): three CTAs per SM at <= 85 registers (the matrix fragments spill to local memory)
+    int occ = 2;
+    if (const char* e = getenv("B2N_RWALK_OCC")) occ = atoi(e) == 3 ? 3 : 2;
     size_t mma_smem = 0;
     if (use_mma) {
-        const int ctas = 2 * ctx->sm_count;                 // 8-chain CTAs, two resident per SM
+        const int ctas = occ * ctx->sm_count;               // 8-chain CTAs, two (three) resident per SM
         chains_per_cta = (int)std::max<int64_t>(std::min(ctx->min_cpc, 8), (Q + ctas - 1) / ctas);
         warps = 8;
         const int RS = 8 * ((4 * KT + 7) / 8);
@@ -819,8 +822,14 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         B2N_TRY(b2n_func_smem(ctx, (const void*)(rwalk_mma_kernel<L, K, 8, D, F>), (size_t)(smem))); \
         rwalk_mma_kernel<L, K, 8, D, F><<<grid, 256, smem, ctx->stream>>>(p);                        \
     } while (0)
+#define LAUNCH_MMA3(L, K)                                                                            \
+    do {                                                                                            \
+        B2N_TRY(b2n_func_smem(ctx, (const void*)(rwalk_mma_kernel<L, K, 8, 8, true, 3>), (size_t)(smem))); \
+        rwalk_mma_kernel<L, K, 8, 8, true, 3><<<grid, 256, smem, ctx->stream>>>(p);                  \
+    } while (0)
 #define LAUNCH_MMA(L, K)                        \
     if (DU == 1) LAUNCH_MMA2(L, K, 1, false);   \
+    else if (fast_draws && occ == 3 && L == B2N_LIKE_GAUSS_PREC && K == 13) LAUNCH_MMA3(L, K); \
     else if (fast_draws) LAUNCH_MMA2(L, K, 8, true); \
     else LAUNCH_MMA2(L, K, 8, false);
 #define CALL_MMA(L)                      \

@@ -28,7 +28,7 @@ import numpy as np
 from . import _lib, nested
 
 
-def _one(pool, make_sampler, run_kwargs, seed, keep_results):
+def _one(pool, make_sampler, run_kwargs, seed, keep_results, errors='raise'):
     ctx = pool.get()                     # a context is reused by the replicas that follow each other on it: its device
     try:                                 # allocations (scratch, run state) are made once, not once per run
         t0 = time.perf_counter()
@@ -41,6 +41,10 @@ def _one(pool, make_sampler, run_kwargs, seed, keep_results):
         if keep_results:
             out['results'] = res
         return out
+    except Exception as e:                # errors='record': one failed replica must not lose the ensemble
+        if errors == 'raise':
+            raise
+        return dict(seed=int(seed), error=repr(e)[:300])
     finally:
         pool.put(ctx)
 
@@ -70,7 +74,7 @@ class ContextPool:
 
 
 def run_replicas(model, seeds, nlive=500, bound='multi', sample='rwalk', device=None, max_in_flight=16, comm=None,
-                 keep_results=False, sampler_kwargs=None, chain_pack=1, pool=None, **run_kwargs):
+                 keep_results=False, sampler_kwargs=None, chain_pack=1, pool=None, errors='raise', **run_kwargs):
     """Run one device-resident nested-sampling run per seed, `max_in_flight` at a time on this GPU.
 
     model / nlive / bound / sample / sampler_kwargs : as for ``nested.NestedSampler``.
@@ -100,7 +104,7 @@ def run_replicas(model, seeds, nlive=500, bound='multi', sample='rwalk', device=
     try:
         if mine:
             with ThreadPoolExecutor(max_workers=nthr) as ex:
-                futs = [ex.submit(_one, pool, make, run_kwargs, s, keep_results) for s in mine]
+                futs = [ex.submit(_one, pool, make, run_kwargs, s, keep_results, errors) for s in mine]
                 outs = [f.result() for f in futs]
         wall = time.perf_counter() - t0
     finally:
@@ -120,8 +124,10 @@ def run_replicas(model, seeds, nlive=500, bound='multi', sample='rwalk', device=
 
 def summarize(outs, wall):
     """Ensemble statistics: logZ mean / scatter, aggregate calls per second over the ensemble's wall time."""
+    failed = [o for o in outs if 'error' in o]
+    outs = [o for o in outs if 'error' not in o]
     lz = np.array([o['logz'] for o in outs])
     ncall = int(sum(o['ncall'] for o in outs))
-    return dict(replicas=len(outs), logz_mean=float(lz.mean()), logz_std=float(lz.std(ddof=1)) if len(lz) > 1 else None,
+    return dict(replicas=len(outs), failed=len(failed), logz_mean=float(lz.mean()), logz_std=float(lz.std(ddof=1)) if len(lz) > 1 else None,
                 ncall=ncall, niter=int(sum(o['niter'] for o in outs)), wall_s=wall, calls_per_s=ncall / wall,
                 run_wall_s_mean=float(np.mean([o['wall_s'] for o in outs])))
