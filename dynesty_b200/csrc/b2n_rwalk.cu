@@ -442,6 +442,544 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? OCC : 1) rwalk_mma_kernel(c
 }
 
 // =====================================================================================
+// rwalk_mma16_kernel -- the lock-step kernel above re-cut for SIXTEEN warps per 8 chains (GAUSS_PREC models).
+//
+// Why (profiles/r1n, r2n): rwalk_mma_kernel is bound by dependent-instruction latency -- 2 CTAs x 8 warps per SM
+// (128 registers) issue on 44 % of the cycles, each warp one instruction per ~8 cycles -- and the queue has only
+// 13.5 chains per SM, so more CTAs cannot be made resident.  The same work is therefore dealt over twice the warps,
+// and the instruction count per step is cut:
+//   * contractions: item = (8-row slab, HALF of the k-tiles) -> 2 S <= 16 item warps with 7 instead of 13 dependent
+//     DMMAs, and 7 + 7 instead of 13 + 13 fragment registers per thread (<= 64 registers: 2 CTAs x 512 threads);
+//     the two partial sums meet in shared memory (phase 3 adds the halves of y, phase 5 the 2 S partial forms);
+//   * chain phases: two warps per chain, lane = component, so a thread owns ONE component of its chain for the whole
+//     kernel: the chain state (u, v, and the proposal) lives in registers, not in shared memory;
+//   * every shared-memory offset is a compile-time constant (the layout depends on KT only, not on n);
+//   * two CTA barriers per step instead of three: the item warps run phase 4 of step s and phase 2 of step s + 1
+//     back to back, the chain warps phase 5 of step s and phase 3 of step s + 1 (phase 2 does not depend on the
+//     accept / reject of the step before: the directions are in the ring);
+//   * draws: the ring items are dealt over 16 warps, and the step factor scale * U^(1/n) / |z| (exp, divide, sqrt) is
+//     no longer computed on all 32 lanes per item but for the whole ring at once with one LANE per item, by the two
+//     warps that have no contraction item (the first two when S = 8) while the others run phase 2 of the first step.
+// Draw events, ticks and the arithmetic of every draw are those of rwalk_mma_kernel; only the summation order of the
+// two contractions differs (round-off).
+// =====================================================================================
+template <int KT>
+struct Mma16Layout {
+    static constexpr int CH = 8, NW = 16, DEPTH = 8;
+    static constexpr int KH = (KT + 1) / 2;                              // k-tiles per half
+    static constexpr int RS = 8 * ((4 * KT + 7) / 8);                    // rows padded to whole slabs (>= n)
+    static constexpr int XS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16));
+    static constexpr int YS = RS + 2;
+    static constexpr int XB = CH * XS;
+    static constexpr int O_P0 = 0, O_P1 = RS;                            // prior vectors (mean, flags: registers)
+    static constexpr int O_X = 2 * RS;                                   // ring: direction z of step s, later delta = v - mean
+    static constexpr int O_Y = O_X + DEPTH * XB;                         // the two k-halves of axes @ z (chain-major)
+    static constexpr int O_Q = O_Y + 2 * CH * YS;                        // partial quadratic forms per (slab, half)
+    static constexpr int O_F = O_Q + 16 * CH;                            // step factors per ring slot
+    static constexpr int O_SS = O_F + DEPTH * CH;                        // |z|^2 per ring slot
+    static constexpr int O_LG = O_SS + DEPTH * CH;                       // log U of the radius per ring slot
+    static constexpr int O_OK = O_LG + DEPTH * CH;                       // in-cube flags [step parity][chain][half]
+    static constexpr int TOTAL = O_OK + 16;                              // doubles
+};
+
+template <int KT>
+__global__ void __launch_bounds__(512, 2) rwalk_mma16_kernel(const RwalkParams p) {
+    using L = Mma16Layout<KT>;
+    constexpr int CH = L::CH, NW = L::NW, DEPTH = L::DEPTH, KH = L::KH, XS = L::XS, YS = L::YS, XB = L::XB;
+    const int n = p.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    B2N_DYN_PROLOGUE(p)
+    const int3 cd = p.cta[blockIdx.x];
+    const int S = (n + 7) >> 3;
+    int* okf = reinterpret_cast<int*>(&b2n_sm[L::O_OK]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        b2n_sm[L::O_P0 + i] = p.m.pp0 ? p.m.pp0[i] : 0.0;
+        b2n_sm[L::O_P1 + i] = p.m.pp1 ? p.m.pp1[i] : 1.0;
+    }
+    for (int e = threadIdx.x; e < DEPTH * XB; e += blockDim.x) b2n_sm[L::O_X + e] = 0.0;
+    // ---- fragments: item (slab s_it, half h_it) of both matrices
+    const int s_it = warp % S, h_it = warp / S;
+    const bool has_item = warp < 2 * S;
+    double fragA[KH], fragP[KH];
+    {
+        const double* Ag = p.axesT + (size_t)cd.z * n * n;
+        const double* Pg = p.m.lmat;
+        const int row = 8 * s_it + (lane >> 2);
+#pragma unroll
+        for (int j = 0; j < KH; j++) {
+            const int col = 4 * (h_it * KH + j) + (lane & 3);
+            const bool in = has_item && row < n && col < n;
+            fragA[j] = in ? Ag[(size_t)col * n + row] : 0.0;
+            fragP[j] = in ? Pg[(size_t)row * n + col] : 0.0;
+        }
+    }
+    // item-phase addresses (relative to the ring slot of the step)
+    const int xb_it = (lane >> 2) * XS + (lane & 3) + 4 * h_it * KH;           // B fragment of k-tile 0 of the half
+    const int yst_it = L::O_Y + (h_it * CH + 2 * (lane & 3)) * YS + 8 * s_it + (lane >> 2);
+    const int xr_it = 2 * (lane & 3) * XS + 8 * s_it + (lane >> 2);            // delta[row] of chain c0
+    // the two warps that turn (|z|^2, log U) of the ring into step factors: those without an item, else the first two
+    const int fw = (2 * S <= NW - 2) ? warp - (NW - 2) : warp;
+    const double inv_n = 1.0 / (double)n;
+    const int pk = p.m.prior_kind;
+    const int c = warp >> 1, hh = warp & 1;                       // chain slot and component half of this warp
+    const int ci = 32 * hh + lane;                                // the component this thread owns
+    const bool cin = ci < n;
+    const uint32_t myfl = cin ? (p.dimflags ? p.dimflags[ci] : 0u) : 0u;
+    const double mymu = cin && p.m.lv0 ? p.m.lv0[ci] : 0.0;
+    __syncthreads();
+
+    for (int g0 = 0; g0 < cd.y; g0 += CH) {
+        const int nlc = (cd.y - g0) < CH ? (cd.y - g0) : CH;
+        const bool live = c < nlc;
+        const int q = live ? p.order[cd.x + g0 + c] : 0;
+        double ucur = (live && cin) ? p.u0[(size_t)q * n + ci] : 0.0, vcur = 0.0, uprop = 0.0, vprop = 0.0;
+        int nacc = 0, nrej = 0;
+        double lcur = 0.0;
+
+        // phase 2 of ring slot s: Y_h[rows of slab][chains] = A_slab[:, half h] @ X[half h]
+        auto phase2 = [&](int oXs) {
+            double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+            const int xb = oXs + xb_it;
+#pragma unroll
+            for (int j = 0; j + 1 < KH; j += 2) {
+                dmma884(d0, d1, fragA[j], b2n_sm[xb + 4 * j]);
+                dmma884(e0, e1, fragA[j + 1], b2n_sm[xb + 4 * j + 4]);
+            }
+            if (KH & 1) dmma884(d0, d1, fragA[KH - 1], b2n_sm[xb + 4 * (KH - 1)]);
+            b2n_sm[yst_it] = d0 + e0;
+            b2n_sm[yst_it + YS] = d1 + e1;
+        };
+        // phase 3 of ring slot s: u' = u + fac*y, wrap / reflect / cube test, prior, delta -> X[s][c]
+        auto phase3 = [&](int s) {
+            bool ok = true;
+            if (cin) {
+                const double fac = b2n_sm[L::O_F + s * CH + c];
+                const double y = b2n_sm[L::O_Y + c * YS + ci] + b2n_sm[L::O_Y + (CH + c) * YS + ci];
+                double t = fma(fac, y, ucur);
+                if (myfl & B2N_DIM_PERIODIC) t = mod1(t);
+                if (myfl & B2N_DIM_REFLECTIVE) t = reflect1(t);
+                ok = in_cube(t, myfl);
+                uprop = t;
+                vprop = prior_sm(pk, L::O_P0, L::O_P1, ci, t);
+                b2n_sm[L::O_X + s * XB + c * XS + ci] = vprop - mymu;
+            }
+            ok = __all_sync(B2N_FULL, ok);
+            if (lane == 0) okf[(s & 1) * 16 + warp] = ok ? 1 : 0;
+        };
+        // phase 4 of ring slot s: partial delta^T P delta over (rows of the slab) x (columns of the half)
+        auto phase4 = [&](int oXs) {
+            double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+            const int xb = oXs + xb_it;
+#pragma unroll
+            for (int j = 0; j + 1 < KH; j += 2) {
+                dmma884(d0, d1, fragP[j], b2n_sm[xb + 4 * j]);
+                dmma884(e0, e1, fragP[j + 1], b2n_sm[xb + 4 * j + 4]);
+            }
+            if (KH & 1) dmma884(d0, d1, fragP[KH - 1], b2n_sm[xb + 4 * (KH - 1)]);
+            double q0 = (d0 + e0) * b2n_sm[oXs + xr_it], q1 = (d1 + e1) * b2n_sm[oXs + xr_it + XS];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                q0 += __shfl_xor_sync(B2N_FULL, q0, o);
+                q1 += __shfl_xor_sync(B2N_FULL, q1, o);
+            }
+            if (lane < 4) {
+                b2n_sm[L::O_Q + warp * CH + 2 * lane] = q0;
+                b2n_sm[L::O_Q + warp * CH + 2 * lane + 1] = q1;
+            }
+        };
+        // phase 5 of ring slot s (both warps of the chain, identically): logl, accept / reject
+        auto phase5 = [&](int s) {
+            double qf = (lane < 2 * S) ? b2n_sm[L::O_Q + lane * CH + c] : 0.0;     // 2 S <= 16 partials
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) qf += __shfl_xor_sync(B2N_FULL, qf, o);
+            qf = __shfl_sync(B2N_FULL, qf, 0);
+            const double l = fma(-0.5, qf, p.m.s0);
+            const int* ok2 = &okf[(s & 1) * 16 + 2 * c];
+            const bool ok = (ok2[0] & ok2[1]) != 0;
+            if (ok && l > loglstar_) {
+                ucur = uprop;
+                vcur = vprop;
+                lcur = l;
+                nacc++;
+            } else {
+                nrej++;
+            }
+        };
+
+        for (int step0 = 0; step0 < p.walks; step0 += DEPTH) {
+            const int nd = (p.walks - step0) < DEPTH ? (p.walks - step0) : DEPTH;
+            const int nit = nd * nlc;
+            // ---- phase 1 (all warps): the directions of the next nd steps of every live chain
+            if (nit > NW) {
+                for (int w = warp; w < nit; w += 2 * NW) {        // two items side by side (their chains interleave)
+                    const int w2 = w + NW;
+                    const bool two = w2 < nit;
+                    int sa, ca, sb, cb;
+                    if (nlc == CH) { sa = w >> 3; ca = w & 7; sb = w2 >> 3; cb = w2 & 7; }
+                    else { sa = w / nlc; ca = w - sa * nlc; sb = w2 / nlc; cb = w2 - sb * nlc; }
+                    if (!two) { sb = sa; cb = ca; }
+                    ChainRng ga, gb;
+                    ga.init(p.seed, chain0_ + (uint64_t)p.order[cd.x + g0 + ca]);
+                    gb.init(p.seed, chain0_ + (uint64_t)p.order[cd.x + g0 + cb]);
+                    ga.tick = 2u * (uint32_t)(step0 + sa);
+                    gb.tick = 2u * (uint32_t)(step0 + sb);
+                    double ssa, lga, ssb, lgb;
+                    ball_draw_fast(ga, L::O_X + sa * XB + ca * XS, true, n, lane, ssa, lga);
+                    ball_draw_fast(gb, L::O_X + sb * XB + cb * XS, two, n, lane, ssb, lgb);
+                    if (lane == 0) {
+                        b2n_sm[L::O_SS + sa * CH + ca] = ssa;
+                        b2n_sm[L::O_LG + sa * CH + ca] = lga;
+                        if (two) {
+                            b2n_sm[L::O_SS + sb * CH + cb] = ssb;
+                            b2n_sm[L::O_LG + sb * CH + cb] = lgb;
+                        }
+                    }
+                }
+            } else if (warp < nit) {                              // few chains (b2n_ns_run's rounds): one item per warp
+                const int sa = warp / nlc, ca = warp - sa * nlc;
+                ChainRng ga;
+                ga.init(p.seed, chain0_ + (uint64_t)p.order[cd.x + g0 + ca]);
+                ga.tick = 2u * (uint32_t)(step0 + sa);
+                double ssa, lga;
+                ball_draw_fast(ga, L::O_X + sa * XB + ca * XS, true, n, lane, ssa, lga);
+                if (lane == 0) {
+                    b2n_sm[L::O_SS + sa * CH + ca] = ssa;
+                    b2n_sm[L::O_LG + sa * CH + ca] = lga;
+                }
+            }
+            __syncthreads();
+            // ---- step factors of the whole ring, one lane per ring slot (step e / CH, chain e % CH)
+            if (fw == 0 || fw == 1) {
+                const int e = 32 * fw + lane;
+                if (e < nd * CH && (e & (CH - 1)) < nlc)
+                    b2n_sm[L::O_F + e] = scale_ * b2n_div(exp(b2n_sm[L::O_LG + e] * inv_n), b2n_sqrt(b2n_sm[L::O_SS + e]));
+            }
+            if (has_item) phase2(L::O_X);
+            __syncthreads();
+            if (live) phase3(0);
+            __syncthreads();
+            for (int s = 0; s < nd; s++) {
+                if (has_item) {
+                    phase4(L::O_X + s * XB);
+                    if (s + 1 < nd) phase2(L::O_X + (s + 1) * XB);
+                }
+                __syncthreads();
+                if (live) phase5(s);
+                if (s + 1 < nd) {
+                    if (live) phase3(s + 1);
+                    __syncthreads();
+                }
+            }
+            // (the next ring is drawn in the same barrier interval as phase 5 of the last step: every read of the ring
+            //  -- phase 4 of that step -- sits before the barrier above)
+        }
+        // no accept: (v, logl) of the start point are recomputed (:970-975); every thread its own component of v
+        if (live && nacc == 0 && cin) {
+            vcur = prior_sm(pk, L::O_P0, L::O_P1, ci, ucur);
+            b2n_sm[L::O_Y + c * YS + ci] = vcur - mymu;
+        }
+        __syncthreads();
+        if (live) {
+            if (nacc == 0 && hh == 0)
+                lcur = fma(-0.5, quadform_full<false>(p.m.lmat, 0, n, n, L::O_Y + c * YS, lane), p.m.s0);
+            if (cin) {
+                peer_put(p.peer, &p.u[(size_t)q * n + ci], ucur);
+                peer_put(p.peer, &p.v[(size_t)q * n + ci], vcur);
+            }
+            if (lane == 0 && hh == 0) {
+                peer_put(p.peer, &p.logl[q], lcur);
+                peer_put(p.peer, &p.nacc[q], nacc);
+                peer_put(p.peer, &p.nrej[q], nrej);
+                peer_put(p.peer, &p.ncall[q], (int)p.walks);
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < DEPTH * XB; e += blockDim.x) b2n_sm[L::O_X + e] = 0.0;
+        __syncthreads();
+    }
+    peer_finish(p.peer);
+}
+
+// =====================================================================================
+// rwalk_mmaws_kernel -- the lock-step kernel, WARP-SPECIALISED (GAUSS_PREC models): 8 step warps + 4 draw warps.
+//
+// Why (profiles/r2n): the draws are ~40 % of the instructions of rwalk_mma_kernel and the only part of it that is
+// bound by instruction issue; the step phases are chains of dependent shared-memory loads, DMMAs, shuffles and
+// barriers that leave the schedulers idle most of the time.  The draws of a step do not depend on the chain state, so
+// they do not have to sit in the same instruction stream at all:
+//   * warps 8..11 (one per scheduler) do nothing but draw: they fill a DOUBLE-BUFFERED ring of directions (8 steps x 8
+//     chains per buffer) one buffer ahead of the step warps and issue into the cycles the step warps leave empty;
+//     the step factors scale * U^(1/n) / |z| of a buffer are formed with one LANE per ring slot;
+//   * warps 0..7 run the step phases of rwalk_mma_kernel on register-resident DMMA fragments, with every shared-memory
+//     offset a compile-time constant and TWO barriers per step instead of three (phase 4 of step s and phase 2 of
+//     step s + 1 run back to back, then phase 5 of step s and phase 3 of step s + 1);
+//   * the two roles meet at named barriers only (FULL / EMPTY per ring buffer: bar.arrive on one side, bar.sync on
+//     the other), the step warps synchronise among themselves on a 256-thread named barrier;
+//   * setmaxnreg moves registers from the draw warps to the step warps (the fragments alone are 52 registers).
+// Draw events, ticks and arithmetic are those of rwalk_mma_kernel (the step factor is the same expression); the
+// contractions are summed in the same order: results are bit-identical to rwalk_mma_kernel with fast draws.
+// =====================================================================================
+template <int KT>
+struct MmaWsLayout {
+    static constexpr int CH = 8, DEPTH = 8, NSW = 8, NDW = 4;
+    static constexpr int RS = 8 * ((4 * KT + 7) / 8);                    // rows padded to whole slabs (>= n)
+    static constexpr int XS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16));
+    static constexpr int YS = RS + 2;
+    static constexpr int XB = CH * XS;
+    static constexpr int RING = DEPTH * XB;
+    static constexpr int O_P0 = 0, O_P1 = RS, O_MU = 2 * RS;            // prior vectors, likelihood mean
+    static constexpr int O_FL = 3 * RS;                                  // dimension flags (RS uint32)
+    static constexpr int O_X = O_FL + RS / 2;                            // two rings: direction z, later delta = v - mean
+    static constexpr int O_Y = O_X + 2 * RING;                           // axes @ z (chain-major)
+    static constexpr int O_Q = O_Y + CH * YS;                            // partial quadratic forms per slab
+    static constexpr int O_F = O_Q + 8 * CH;                             // step factors, two rings
+    static constexpr int O_SS = O_F + 2 * DEPTH * CH;                    // |z|^2 per ring slot (draw warps' scratch)
+    static constexpr int O_LG = O_SS + DEPTH * CH;                       // log U of the radius per ring slot
+    static constexpr int O_ST = O_LG + DEPTH * CH;                       // chain state: ucur, uprop, vcur, vprop
+    static constexpr int TOTAL = O_ST + CH * 4 * RS;                     // doubles
+};
+__device__ __forceinline__ void nbar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void nbar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// SETREG: 0 = every warp keeps the 80 registers of the launch; 1 = 88 (step) / 64 (draw); 2 = 96 / 48
+// (256 x step + 128 x draw must not exceed the 384 x 80 registers the CTA is launched with)
+template <int KT, int SETREG>
+__global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p) {
+    using L = MmaWsLayout<KT>;
+    constexpr int CH = L::CH, DEPTH = L::DEPTH, XS = L::XS, YS = L::YS, XB = L::XB, RS = L::RS;
+    constexpr int BAR_STEP = 1, BAR_FULL = 2, BAR_EMPTY = 4;      // named barriers (0 = __syncthreads)
+    const int n = p.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    B2N_DYN_PROLOGUE(p)
+    const int3 cd = p.cta[blockIdx.x];
+    uint32_t* fl = reinterpret_cast<uint32_t*>(&b2n_sm[L::O_FL]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        b2n_sm[L::O_P0 + i] = p.m.pp0 ? p.m.pp0[i] : 0.0;
+        b2n_sm[L::O_P1 + i] = p.m.pp1 ? p.m.pp1[i] : 1.0;
+        b2n_sm[L::O_MU + i] = p.m.lv0 ? p.m.lv0[i] : 0.0;
+        fl[i] = p.dimflags ? p.dimflags[i] : 0u;
+    }
+    for (int e = threadIdx.x; e < 2 * L::RING; e += blockDim.x) b2n_sm[L::O_X + e] = 0.0;
+    __syncthreads();
+    const int NB = (p.walks + DEPTH - 1) / DEPTH;                 // ring buffers per group of chains
+
+    if (warp >= L::NSW) {
+        // =============================== draw warps ===============================
+        if (SETREG == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (SETREG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        const int dw = warp - L::NSW;
+        const double inv_n = 1.0 / (double)n;
+        for (int g0 = 0; g0 < cd.y; g0 += CH) {
+            const int nlc = (cd.y - g0) < CH ? (cd.y - g0) : CH;
+            for (int blk = 0; blk < NB; blk++) {
+                const int b = blk & 1, step0 = blk * DEPTH;
+                const int nd = (p.walks - step0) < DEPTH ? (p.walks - step0) : DEPTH;
+                const int nit = nd * nlc;
+                const int oXb = L::O_X + b * L::RING;
+                if (blk >= 2) nbar_sync(BAR_EMPTY + b, 384);      // the step warps have finished with this buffer
+                for (int w = dw; w < nit; w += 2 * L::NDW) {      // two items side by side (their chains interleave)
+                    const int w2 = w + L::NDW;
+                    const bool two = w2 < nit;
+                    int sa, ca, sb, cb;
+                    if (nlc == CH) { sa = w >> 3; ca = w & 7; sb = w2 >> 3; cb = w2 & 7; }
+                    else { sa = w / nlc; ca = w - sa * nlc; sb = w2 / nlc; cb = w2 - sb * nlc; }
+                    if (!two) { sb = sa; cb = ca; }
+                    ChainRng ga, gb;
+                    ga.init(p.seed, chain0_ + (uint64_t)p.order[cd.x + g0 + ca]);
+                    gb.init(p.seed, chain0_ + (uint64_t)p.order[cd.x + g0 + cb]);
+                    ga.tick = 2u * (uint32_t)(step0 + sa);
+                    gb.tick = 2u * (uint32_t)(step0 + sb);
+                    double ssa, lga, ssb, lgb;
+                    ball_draw_fast(ga, oXb + sa * XB + ca * XS, true, n, lane, ssa, lga);
+                    ball_draw_fast(gb, oXb + sb * XB + cb * XS, two, n, lane, ssb, lgb);
+                    if (lane == 0) {
+                        b2n_sm[L::O_SS + sa * CH + ca] = ssa;
+                        b2n_sm[L::O_LG + sa * CH + ca] = lga;
+                        if (two) {
+                            b2n_sm[L::O_SS + sb * CH + cb] = ssb;
+                            b2n_sm[L::O_LG + sb * CH + cb] = lgb;
+                        }
+                    }
+                }
+                __syncwarp();
+                {   // step factors of this warp's items, one lane per item: item w = dw + NDW * lane
+                    const int w = dw + L::NDW * lane;
+                    if (lane < 16 && w < nit) {
+                        int sa, ca;
+                        if (nlc == CH) { sa = w >> 3; ca = w & 7; }
+                        else { sa = w / nlc; ca = w - sa * nlc; }
+                        const int e = sa * CH + ca;
+                        b2n_sm[L::O_F + b * DEPTH * CH + e] =
+                            scale_ * b2n_div(exp(b2n_sm[L::O_LG + e] * inv_n), b2n_sqrt(b2n_sm[L::O_SS + e]));
+                    }
+                }
+                __threadfence_block();
+                nbar_arrive(BAR_FULL + b, 384);
+            }
+            // group boundary: both roles meet, the rings are cleared (rows of chains that are not live in the next group)
+            __syncthreads();
+            for (int e = threadIdx.x; e < 2 * L::RING; e += blockDim.x) b2n_sm[L::O_X + e] = 0.0;
+            __syncthreads();
+        }
+    } else {
+        // =============================== step warps ===============================
+        if (SETREG == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+        if (SETREG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+        const int S = (n + 7) >> 3;
+        const int s_it = warp;                                    // slab of this warp's contraction items
+        const bool has_item = warp < S;
+        double fragA[KT], fragP[KT];
+        {
+            const double* Ag = p.axesT + (size_t)cd.z * n * n;
+            const double* Pg = p.m.lmat;
+            const int row = 8 * s_it + (lane >> 2);
+#pragma unroll
+            for (int kt = 0; kt < KT; kt++) {
+                const int col = 4 * kt + (lane & 3);
+                const bool in = has_item && row < n && col < n;
+                fragA[kt] = in ? Ag[(size_t)col * n + row] : 0.0;
+                fragP[kt] = in ? Pg[(size_t)row * n + col] : 0.0;
+            }
+        }
+        const int xb_it = (lane >> 2) * XS + (lane & 3);                          // B fragment of k-tile 0
+        const int yst_it = L::O_Y + 2 * (lane & 3) * YS + 8 * s_it + (lane >> 2);
+        const int xr_it = 2 * (lane & 3) * XS + 8 * s_it + (lane >> 2);           // delta[row] of chain c0
+        const int pk = p.m.prior_kind;
+        const int c = warp;                                       // chain slot owned by this warp
+        const int oy = L::O_Y + c * YS;
+
+        for (int g0 = 0; g0 < cd.y; g0 += CH) {
+            const int nlc = (cd.y - g0) < CH ? (cd.y - g0) : CH;
+            const bool live = c < nlc;
+            const int q = live ? p.order[cd.x + g0 + c] : 0;
+            int oucur = L::O_ST + c * 4 * RS, ouprop = oucur + RS, ovcur = ouprop + RS, ovprop = ovcur + RS;
+            if (live)
+                for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)q * n + i];
+            int nacc = 0, nrej = 0;
+            double lcur = 0.0;
+            bool ok = true;
+
+            auto phase2 = [&](int oXs) {          // Y[rows of slab][chains] = A_slab @ X
+                double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+                const int xb = oXs + xb_it;
+#pragma unroll
+                for (int kt = 0; kt + 1 < KT; kt += 2) {
+                    dmma884(d0, d1, fragA[kt], b2n_sm[xb + 4 * kt]);
+                    dmma884(e0, e1, fragA[kt + 1], b2n_sm[xb + 4 * kt + 4]);
+                }
+                if (KT & 1) dmma884(d0, d1, fragA[KT - 1], b2n_sm[xb + 4 * (KT - 1)]);
+                b2n_sm[yst_it] = d0 + e0;
+                b2n_sm[yst_it + YS] = d1 + e1;
+            };
+            auto phase3 = [&](int oXs, double fac) {   // u' = u + fac*y, wrap / reflect / cube test, prior, delta -> X[s][c]
+                bool good = true;
+                for (int i = lane; i < n; i += 32) {
+                    double t = fma(fac, b2n_sm[oy + i], b2n_sm[oucur + i]);
+                    const uint32_t f = fl[i];
+                    if (f & B2N_DIM_PERIODIC) t = mod1(t);
+                    if (f & B2N_DIM_REFLECTIVE) t = reflect1(t);
+                    good = good && in_cube(t, f);
+                    const double vi = prior_sm(pk, L::O_P0, L::O_P1, i, t);
+                    b2n_sm[ouprop + i] = t;
+                    b2n_sm[ovprop + i] = vi;
+                    b2n_sm[oXs + c * XS + i] = vi - b2n_sm[L::O_MU + i];
+                }
+                ok = __all_sync(B2N_FULL, good);
+            };
+            auto phase4 = [&](int oXs) {          // partial delta^T P delta over the rows of the slab
+                double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+                const int xb = oXs + xb_it;
+#pragma unroll
+                for (int kt = 0; kt + 1 < KT; kt += 2) {
+                    dmma884(d0, d1, fragP[kt], b2n_sm[xb + 4 * kt]);
+                    dmma884(e0, e1, fragP[kt + 1], b2n_sm[xb + 4 * kt + 4]);
+                }
+                if (KT & 1) dmma884(d0, d1, fragP[KT - 1], b2n_sm[xb + 4 * (KT - 1)]);
+                double q0 = (d0 + e0) * b2n_sm[oXs + xr_it], q1 = (d1 + e1) * b2n_sm[oXs + xr_it + XS];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    q0 += __shfl_xor_sync(B2N_FULL, q0, o);
+                    q1 += __shfl_xor_sync(B2N_FULL, q1, o);
+                }
+                if (lane < 4) {
+                    b2n_sm[L::O_Q + s_it * CH + 2 * lane] = q0;
+                    b2n_sm[L::O_Q + s_it * CH + 2 * lane + 1] = q1;
+                }
+            };
+            auto phase5 = [&]() {                 // logl, accept / reject
+                double qf = 0.0;
+                for (int s2 = 0; s2 < S; s2++) qf += b2n_sm[L::O_Q + s2 * CH + c];
+                const double l = fma(-0.5, qf, p.m.s0);
+                if (ok && l > loglstar_) {
+                    int t = oucur; oucur = ouprop; ouprop = t;
+                    t = ovcur; ovcur = ovprop; ovprop = t;
+                    lcur = l;
+                    nacc++;
+                } else {
+                    nrej++;
+                }
+            };
+
+            for (int blk = 0; blk < NB; blk++) {
+                const int b = blk & 1, step0 = blk * DEPTH;
+                const int nd = (p.walks - step0) < DEPTH ? (p.walks - step0) : DEPTH;
+                const int oXb = L::O_X + b * L::RING, oFb = L::O_F + b * DEPTH * CH;
+                nbar_sync(BAR_FULL + b, 384);                     // the draw warps have filled this buffer
+                if (has_item) phase2(oXb);
+                nbar_sync(BAR_STEP, 256);
+                if (live) phase3(oXb, b2n_sm[oFb + c]);
+                nbar_sync(BAR_STEP, 256);
+                for (int s = 0; s < nd; s++) {
+                    if (has_item) {
+                        phase4(oXb + s * XB);
+                        if (s + 1 < nd) phase2(oXb + (s + 1) * XB);
+                    }
+                    nbar_sync(BAR_STEP, 256);
+                    // every read of this ring buffer is done: hand it back to the draw warps (if they will ask for it)
+                    if (s == nd - 1 && blk + 2 < NB) nbar_arrive(BAR_EMPTY + b, 384);
+                    if (live) phase5();
+                    if (s + 1 < nd) {
+                        if (live) phase3(oXb + (s + 1) * XB, b2n_sm[oFb + (s + 1) * CH + c]);
+                        nbar_sync(BAR_STEP, 256);
+                    }
+                }
+            }
+            if (live) {
+                if (nacc == 0) {   // recompute (v, logl) of the start point (:970-975), warp-local
+                    __syncwarp();
+                    for (int i = lane; i < n; i += 32) {
+                        const double vi = prior_sm(pk, L::O_P0, L::O_P1, i, b2n_sm[oucur + i]);
+                        b2n_sm[ovcur + i] = vi;
+                        b2n_sm[oy + i] = vi - b2n_sm[L::O_MU + i];
+                    }
+                    __syncwarp();
+                    lcur = fma(-0.5, quadform_full<false>(p.m.lmat, 0, n, n, oy, lane), p.m.s0);
+                }
+                __syncwarp();
+                for (int i = lane; i < n; i += 32) {
+                    peer_put(p.peer, &p.u[(size_t)q * n + i], b2n_sm[oucur + i]);
+                    peer_put(p.peer, &p.v[(size_t)q * n + i], b2n_sm[ovcur + i]);
+                }
+                if (lane == 0) {
+                    peer_put(p.peer, &p.logl[q], lcur);
+                    peer_put(p.peer, &p.nacc[q], nacc);
+                    peer_put(p.peer, &p.nrej[q], nrej);
+                    peer_put(p.peer, &p.ncall[q], (int)p.walks);
+                }
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < 2 * L::RING; e += blockDim.x) b2n_sm[L::O_X + e] = 0.0;
+            __syncthreads();
+        }
+    }
+    peer_finish(p.peer);
+}
+
+// =====================================================================================
 // rwalk_mmas_kernel -- lock-step DMMA kernel for LARGE n (64 < n: the matrix fragments do not
 // fit in registers, and at n = 200 the 320 KB axes matrix does not even fit in shared memory).
 // Same phases as rwalk_mma_kernel with 16 chains per CTA, but the A-operand fragments are
@@ -728,6 +1266,18 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     // experiment (B2N_RWALK_OCC=3): three CTAs per SM at <= 85 registers (the matrix fragments spill to local memory)
     int occ = 2;
     if (const char* e = getenv("B2N_RWALK_OCC")) occ = atoi(e) == 3 ? 3 : 2;
+    // sixteen warps per 8 chains (rwalk_mma16_kernel) for the precision-matrix Gaussian; B2N_RWALK_WARPS=8: the 8-warp kernel
+    bool use_mma16 = use_mma && m.like_kind == B2N_LIKE_GAUSS_PREC && fast_draws && occ == 2;
+    if (const char* e = getenv("B2N_RWALK_WARPS")) use_mma16 = use_mma16 && atoi(e) == 16;
+    // warp-specialised kernel (8 step warps + 4 draw warps, rwalk_mmaws_kernel): B2N_RWALK_WARPS=12 (88 / 64 registers), 14 (96 / 48), 13 (no setmaxnreg)
+    int use_ws = 0;
+    if (const char* e = getenv("B2N_RWALK_WARPS")) {
+        const int w = atoi(e);
+        if ((w == 12 || w == 13 || w == 14) && use_mma && m.like_kind == B2N_LIKE_GAUSS_PREC && fast_draws && occ == 2) {
+            use_ws = w;
+            use_mma16 = false;
+        }
+    }
     size_t mma_smem = 0;
     if (use_mma) {
         const int ctas = occ * ctx->sm_count;               // 8-chain CTAs, two (three) resident per SM
@@ -736,6 +1286,10 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         const int RS = 8 * ((4 * KT + 7) / 8);
         const int XS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16)), YS = RS + 2;
         mma_smem = (size_t)(4 * npad + (((n + 3) >> 2) << 1) + DU * 8 * XS + 8 * YS + 8 * 8 + DU * 8 + 8 * 4 * npad) * sizeof(double);
+        if (use_ws)
+            mma_smem = (size_t)(KT == 8 ? MmaWsLayout<8>::TOTAL : (KT == 13 ? MmaWsLayout<13>::TOTAL : MmaWsLayout<16>::TOTAL)) * sizeof(double);
+        if (use_mma16)
+            mma_smem = (size_t)(KT == 8 ? Mma16Layout<8>::TOTAL : (KT == 13 ? Mma16Layout<13>::TOTAL : Mma16Layout<16>::TOTAL)) * sizeof(double);
     }
     // large n: lock-step kernel with matrix fragments streamed from L2 (16 chains share each load)
     bool use_mmas = false;
@@ -839,8 +1393,27 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
 #define CALL_MMAS(L)                                                                                  \
     B2N_TRY(b2n_func_smem(ctx, (const void*)(rwalk_mmas_kernel<L>), (size_t)(smem)));                                                  \
     rwalk_mmas_kernel<L><<<grid, 512, smem, ctx->stream>>>(p, sXS, sYS);
+#define LAUNCH_MMA16(K)                                                                             \
+    do {                                                                                            \
+        B2N_TRY(b2n_func_smem(ctx, (const void*)(rwalk_mma16_kernel<K>), (size_t)(smem)));          \
+        rwalk_mma16_kernel<K><<<grid, 512, smem, ctx->stream>>>(p);                                 \
+    } while (0)
+#define LAUNCH_MMAWS(K, R)                                                                          \
+    do {                                                                                            \
+        B2N_TRY(b2n_func_smem(ctx, (const void*)(rwalk_mmaws_kernel<K, R>), (size_t)(smem)));       \
+        rwalk_mmaws_kernel<K, R><<<grid, 384, smem, ctx->stream>>>(p);                              \
+    } while (0)
     B2N_TIME_BEGIN(ctx);
-    if (use_mma) {
+    if (use_ws) {
+        const int sr = use_ws == 12 ? 1 : (use_ws == 14 ? 2 : 0);
+        if (KT == 8) { if (sr == 1) LAUNCH_MMAWS(8, 1); else if (sr == 2) LAUNCH_MMAWS(8, 2); else LAUNCH_MMAWS(8, 0); }
+        else if (KT == 13) { if (sr == 1) LAUNCH_MMAWS(13, 1); else if (sr == 2) LAUNCH_MMAWS(13, 2); else LAUNCH_MMAWS(13, 0); }
+        else { if (sr == 1) LAUNCH_MMAWS(16, 1); else if (sr == 2) LAUNCH_MMAWS(16, 2); else LAUNCH_MMAWS(16, 0); }
+    } else if (use_mma16) {
+        if (KT == 8) LAUNCH_MMA16(8);
+        else if (KT == 13) LAUNCH_MMA16(13);
+        else LAUNCH_MMA16(16);
+    } else if (use_mma) {
         B2N_DISPATCH_LIKE(m.like_kind, CALL_MMA)
     } else if (use_mmas) {
         B2N_DISPATCH_LIKE(m.like_kind, CALL_MMAS)
@@ -848,6 +1421,8 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         B2N_DISPATCH_LIKE(m.like_kind, CALL)
     }
     B2N_TIME_END(ctx);
+#undef LAUNCH_MMAWS
+#undef LAUNCH_MMA16
 #undef CALL_MMAS
 #undef CALL_MMA
 #undef LAUNCH_MMA
