@@ -727,17 +727,82 @@ struct MmaWsLayout {
     static constexpr int YS = RS + 2;
     static constexpr int XB = CH * XS;
     static constexpr int RING = DEPTH * XB;
+    static constexpr int SMAX = RS / 8;                                  // slabs at the largest n of this KT
+    static constexpr int NTMAX = SMAX * KT - SMAX * (SMAX - 1);          // tiles on or above the diagonal: sum (KT - 2 s)
+    static constexpr int TPW = (NTMAX + NSW - 1) / NSW;                  // of them per step warp
     static constexpr int O_P0 = 0, O_P1 = RS, O_MU = 2 * RS;            // prior vectors, likelihood mean
     static constexpr int O_FL = 3 * RS;                                  // dimension flags (RS uint32)
     static constexpr int O_X = O_FL + RS / 2;                            // two rings: direction z, later delta = v - mean
-    static constexpr int O_Y = O_X + 2 * RING;                           // axes @ z (chain-major)
-    static constexpr int O_Q = O_Y + CH * YS;                            // partial quadratic forms per slab
+    static constexpr int O_Y = O_X + 2 * RING;                           // axes @ z (chain-major), two buffers (slot parity)
+    static constexpr int O_Q = O_Y + 2 * CH * YS;                        // partial quadratic forms per step warp
     static constexpr int O_F = O_Q + 8 * CH;                             // step factors, two rings
     static constexpr int O_SS = O_F + 2 * DEPTH * CH;                    // |z|^2 per ring slot (draw warps' scratch)
     static constexpr int O_LG = O_SS + DEPTH * CH;                       // log U of the radius per ring slot
     static constexpr int O_ST = O_LG + DEPTH * CH;                       // chain state: ucur, uprop, vcur, vprop
     static constexpr int TOTAL = O_ST + CH * 4 * RS;                     // doubles
 };
+// Static schedule of the symmetric quadratic form (largest n of a KT: S = SMAX slabs): the tiles (slab s, k-tile k)
+// with k >= 2 s, in (s, k) order, TPW consecutive ones per step warp.  Everything below is resolved at compile time
+// (W = warp index through a switch), so a warp's phase 4 is straight-line code: its DMMAs with immediate offsets and
+// one multiply by delta[rows of the slab] at the end of each run of tiles of one slab.
+template <int KT>
+struct SymSched {
+    using L = MmaWsLayout<KT>;
+    static constexpr int NT = L::NTMAX, TPW = L::TPW;
+    static constexpr __host__ __device__ int slab(int t) { int s = 0; while (t >= KT - 2 * s) { t -= KT - 2 * s; s++; } return s; }
+    static constexpr __host__ __device__ int ktile(int t) { int s = 0; while (t >= KT - 2 * s) { t -= KT - 2 * s; s++; } return 2 * s + t; }
+    // position of tile t inside the run of tiles of its slab that belongs to warp t / TPW
+    static constexpr __host__ __device__ int runpos(int t) {
+        const int first = (t / TPW) * TPW;
+        return slab(first) == slab(t) ? t - first : ktile(t) - 2 * slab(t);
+    }
+    static constexpr __host__ __device__ bool runend(int t) { return (t + 1) % TPW == 0 || t + 1 == NT || slab(t + 1) != slab(t); }
+};
+template <int KT, int W, int J>
+__device__ __forceinline__ void sym_load(double (&fragU)[MmaWsLayout<KT>::TPW], const double* __restrict__ Pg, int n, int lane) {
+    using Sch = SymSched<KT>;
+    if constexpr (J < Sch::TPW) {
+        constexpr int t = W * Sch::TPW + J;
+        double u = 0.0;
+        if constexpr (t < Sch::NT) {
+            constexpr int ts = Sch::slab(t), tk = Sch::ktile(t);
+            const int row = 8 * ts + (lane >> 2), col = 4 * tk + (lane & 3);
+            if (row < n && col < n && col >= row) u = (col == row ? 0.5 : 1.0) * Pg[(size_t)row * n + col];
+        }
+        fragU[J] = u;
+        sym_load<KT, W, J + 1>(fragU, Pg, n, lane);
+    }
+}
+template <int KT, int W, int J>
+__device__ __forceinline__ void sym_tiles(const double (&fragU)[MmaWsLayout<KT>::TPW], int xt, int xr, double& d0, double& d1,
+                                          double& e0, double& e1, double& q0, double& q1) {
+    using Sch = SymSched<KT>;
+    constexpr int XS = MmaWsLayout<KT>::XS;
+    constexpr int t = W * Sch::TPW + J;
+    if constexpr (J < Sch::TPW && t < Sch::NT) {
+        constexpr int s = Sch::slab(t), k = Sch::ktile(t), pos = Sch::runpos(t);
+        if constexpr (pos & 1) dmma884(e0, e1, fragU[J], b2n_sm[xt + 4 * k]);
+        else dmma884(d0, d1, fragU[J], b2n_sm[xt + 4 * k]);
+        if constexpr (Sch::runend(t)) {       // multiply the slab's rows by delta[rows], start the next run from zero
+            if constexpr (pos >= 1) {
+                q0 = fma(d0 + e0, b2n_sm[xr + 8 * s], q0);
+                q1 = fma(d1 + e1, b2n_sm[xr + XS + 8 * s], q1);
+                e0 = 0.0; e1 = 0.0;
+            } else {
+                q0 = fma(d0, b2n_sm[xr + 8 * s], q0);
+                q1 = fma(d1, b2n_sm[xr + XS + 8 * s], q1);
+            }
+            d0 = 0.0; d1 = 0.0;
+        }
+        sym_tiles<KT, W, J + 1>(fragU, xt, xr, d0, d1, e0, e1, q0, q1);
+    }
+}
+#define B2N_WARP_SWITCH(W_, CALL)                                                                      \
+    switch (W_) {                                                                                      \
+        case 0: CALL(0); break; case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break; \
+        case 4: CALL(4); break; case 5: CALL(5); break; case 6: CALL(6); break; default: CALL(7); break; \
+    }
+
 __device__ __forceinline__ void nbar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
@@ -746,8 +811,11 @@ __device__ __forceinline__ void nbar_arrive(int id, int count) {
 }
 
 // SETREG: 0 = every warp keeps the 80 registers of the launch; 1 = 88 (step) / 64 (draw); 2 = 96 / 48
-// (256 x step + 128 x draw must not exceed the 384 x 80 registers the CTA is launched with)
-template <int KT, int SETREG>
+// (256 x step + 128 x draw must not exceed the 384 x 80 registers the CTA is launched with; measured at C2, profiles/r2o:
+// 0.226 / 0.2045 / 0.2086 ms -- only 1 is instantiated).
+// PLAIN: no periodic / reflective dimension and a prior that is affine per component (uniform, identity): phase 3 is
+// then straight-line code for the (at most) two components of a lane.
+template <int KT, int SETREG, bool PLAIN>
 __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p) {
     using L = MmaWsLayout<KT>;
     constexpr int CH = L::CH, DEPTH = L::DEPTH, XS = L::XS, YS = L::YS, XB = L::XB, RS = L::RS;
@@ -830,27 +898,30 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
         if (SETREG == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
         if (SETREG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         const int S = (n + 7) >> 3;
-        const int s_it = warp;                                    // slab of this warp's contraction items
+        const int s_it = warp;                                    // slab of this warp's item of axes @ z
         const bool has_item = warp < S;
-        double fragA[KT], fragP[KT];
+        double fragA[KT];
         {
             const double* Ag = p.axesT + (size_t)cd.z * n * n;
-            const double* Pg = p.m.lmat;
             const int row = 8 * s_it + (lane >> 2);
 #pragma unroll
             for (int kt = 0; kt < KT; kt++) {
                 const int col = 4 * kt + (lane & 3);
-                const bool in = has_item && row < n && col < n;
-                fragA[kt] = in ? Ag[(size_t)col * n + row] : 0.0;
-                fragP[kt] = in ? Pg[(size_t)row * n + col] : 0.0;
+                fragA[kt] = (has_item && row < n && col < n) ? Ag[(size_t)col * n + row] : 0.0;
             }
         }
+        // The precision matrix is symmetric: delta^T P delta = 2 delta^T U delta with U = its upper triangle and HALF
+        // its diagonal, so only the (slab, k-tile) tiles on or above the diagonal are contracted -- 49 of the 91 at
+        // n = 50 -- dealt over all 8 warps by the static schedule SymSched (this kernel runs for S == SMAX only).
+        double fragU[L::TPW];
+#define B2N_SYM_LOAD(W_) sym_load<KT, W_, 0>(fragU, p.m.lmat, n, lane)
+        B2N_WARP_SWITCH(warp, B2N_SYM_LOAD)
+#undef B2N_SYM_LOAD
         const int xb_it = (lane >> 2) * XS + (lane & 3);                          // B fragment of k-tile 0
         const int yst_it = L::O_Y + 2 * (lane & 3) * YS + 8 * s_it + (lane >> 2);
-        const int xr_it = 2 * (lane & 3) * XS + 8 * s_it + (lane >> 2);           // delta[row] of chain c0
+        const int xr_it = 2 * (lane & 3) * XS + (lane >> 2);                      // delta[row 0 of a slab] of chain c0
         const int pk = p.m.prior_kind;
         const int c = warp;                                       // chain slot owned by this warp
-        const int oy = L::O_Y + c * YS;
 
         for (int g0 = 0; g0 < cd.y; g0 += CH) {
             const int nlc = (cd.y - g0) < CH ? (cd.y - g0) : CH;
@@ -863,8 +934,11 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
             double lcur = 0.0;
             bool ok = true;
 
-            auto phase2 = [&](int oXs) {          // Y[rows of slab][chains] = A_slab @ X
-                double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+            // phase 2 of a ring slot: Y[rows of slab][chains] = A_slab @ X -- the DMMAs are issued here, their result
+            // is stored by phase2_store AFTER the chain phases of the same barrier interval (the tensor pipe works on
+            // the next-but-one step while the warp walks through the latency chains of phases 5 and 3)
+            auto phase2_issue = [&](int oXs, double& d0, double& d1, double& e0, double& e1) {
+                d0 = 0.0; d1 = 0.0; e0 = 0.0; e1 = 0.0;
                 const int xb = oXs + xb_it;
 #pragma unroll
                 for (int kt = 0; kt + 1 < KT; kt += 2) {
@@ -872,10 +946,34 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
                     dmma884(e0, e1, fragA[kt + 1], b2n_sm[xb + 4 * kt + 4]);
                 }
                 if (KT & 1) dmma884(d0, d1, fragA[KT - 1], b2n_sm[xb + 4 * (KT - 1)]);
-                b2n_sm[yst_it] = d0 + e0;
-                b2n_sm[yst_it + YS] = d1 + e1;
             };
-            auto phase3 = [&](int oXs, double fac) {   // u' = u + fac*y, wrap / reflect / cube test, prior, delta -> X[s][c]
+            auto phase2_store = [&](int buf, double d0, double d1, double e0, double e1) {
+                b2n_sm[yst_it + buf * CH * YS] = d0 + e0;
+                b2n_sm[yst_it + buf * CH * YS + YS] = d1 + e1;
+            };
+            auto phase3 = [&](int oXs, double fac, int oy) {   // u' = u + fac*y, wrap / reflect / cube test, prior, delta -> X[s][c]
+                if (PLAIN) {
+                    const int i0 = lane, i1 = lane + 32;
+                    const bool v0 = i0 < n, v1 = i1 < n;
+                    double t0 = 0.5, t1 = 0.5;
+                    if (v0) t0 = fma(fac, b2n_sm[oy + i0], b2n_sm[oucur + i0]);
+                    if (v1) t1 = fma(fac, b2n_sm[oy + i1], b2n_sm[oucur + i1]);
+                    const bool good = (t0 > 0.0 && t0 < 1.0) && (t1 > 0.0 && t1 < 1.0);
+                    if (v0) {
+                        const double vi = fma(b2n_sm[L::O_P1 + i0], t0, b2n_sm[L::O_P0 + i0]);
+                        b2n_sm[ouprop + i0] = t0;
+                        b2n_sm[ovprop + i0] = vi;
+                        b2n_sm[oXs + c * XS + i0] = vi - b2n_sm[L::O_MU + i0];
+                    }
+                    if (v1) {
+                        const double vi = fma(b2n_sm[L::O_P1 + i1], t1, b2n_sm[L::O_P0 + i1]);
+                        b2n_sm[ouprop + i1] = t1;
+                        b2n_sm[ovprop + i1] = vi;
+                        b2n_sm[oXs + c * XS + i1] = vi - b2n_sm[L::O_MU + i1];
+                    }
+                    ok = __all_sync(B2N_FULL, good);
+                    return;
+                }
                 bool good = true;
                 for (int i = lane; i < n; i += 32) {
                     double t = fma(fac, b2n_sm[oy + i], b2n_sm[oucur + i]);
@@ -890,30 +988,27 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
                 }
                 ok = __all_sync(B2N_FULL, good);
             };
-            auto phase4 = [&](int oXs) {          // partial delta^T P delta over the rows of the slab
-                double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
-                const int xb = oXs + xb_it;
-#pragma unroll
-                for (int kt = 0; kt + 1 < KT; kt += 2) {
-                    dmma884(d0, d1, fragP[kt], b2n_sm[xb + 4 * kt]);
-                    dmma884(e0, e1, fragP[kt + 1], b2n_sm[xb + 4 * kt + 4]);
-                }
-                if (KT & 1) dmma884(d0, d1, fragP[KT - 1], b2n_sm[xb + 4 * (KT - 1)]);
-                double q0 = (d0 + e0) * b2n_sm[oXs + xr_it], q1 = (d1 + e1) * b2n_sm[oXs + xr_it + XS];
+            auto phase4 = [&](int oXs) {          // this warp's tiles of delta^T U delta
+                double q0 = 0.0, q1 = 0.0, d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+                const int xt = oXs + xb_it, xr = oXs + xr_it;
+#define B2N_SYM_TILES(W_) sym_tiles<KT, W_, 0>(fragU, xt, xr, d0, d1, e0, e1, q0, q1)
+                B2N_WARP_SWITCH(warp, B2N_SYM_TILES)
+#undef B2N_SYM_TILES
 #pragma unroll
                 for (int o = 4; o < 32; o <<= 1) {
                     q0 += __shfl_xor_sync(B2N_FULL, q0, o);
                     q1 += __shfl_xor_sync(B2N_FULL, q1, o);
                 }
                 if (lane < 4) {
-                    b2n_sm[L::O_Q + s_it * CH + 2 * lane] = q0;
-                    b2n_sm[L::O_Q + s_it * CH + 2 * lane + 1] = q1;
+                    b2n_sm[L::O_Q + warp * CH + 2 * lane] = q0;
+                    b2n_sm[L::O_Q + warp * CH + 2 * lane + 1] = q1;
                 }
             };
-            auto phase5 = [&]() {                 // logl, accept / reject
+            auto phase5 = [&]() {                 // logl = s0 - delta^T U delta, accept / reject
                 double qf = 0.0;
-                for (int s2 = 0; s2 < S; s2++) qf += b2n_sm[L::O_Q + s2 * CH + c];
-                const double l = fma(-0.5, qf, p.m.s0);
+#pragma unroll
+                for (int w2 = 0; w2 < L::NSW; w2++) qf += b2n_sm[L::O_Q + w2 * CH + c];
+                const double l = p.m.s0 - qf;
                 if (ok && l > loglstar_) {
                     int t = oucur; oucur = ouprop; ouprop = t;
                     t = ovcur; ovcur = ovprop; ovprop = t;
@@ -929,27 +1024,37 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
                 const int nd = (p.walks - step0) < DEPTH ? (p.walks - step0) : DEPTH;
                 const int oXb = L::O_X + b * L::RING, oFb = L::O_F + b * DEPTH * CH;
                 nbar_sync(BAR_FULL + b, 384);                     // the draw warps have filled this buffer
-                if (has_item) phase2(oXb);
+                if (has_item) {
+                    double d0, d1, e0, e1;
+                    phase2_issue(oXb, d0, d1, e0, e1);
+                    phase2_store(0, d0, d1, e0, e1);
+                    if (nd > 1) {
+                        phase2_issue(oXb + XB, d0, d1, e0, e1);
+                        phase2_store(1, d0, d1, e0, e1);
+                    }
+                }
                 nbar_sync(BAR_STEP, 256);
-                if (live) phase3(oXb, b2n_sm[oFb + c]);
+                if (live) phase3(oXb, b2n_sm[oFb + c], L::O_Y + c * YS);
                 nbar_sync(BAR_STEP, 256);
                 for (int s = 0; s < nd; s++) {
-                    if (has_item) {
-                        phase4(oXb + s * XB);
-                        if (s + 1 < nd) phase2(oXb + (s + 1) * XB);
-                    }
+                    phase4(oXb + s * XB);
                     nbar_sync(BAR_STEP, 256);
                     // every read of this ring buffer is done: hand it back to the draw warps (if they will ask for it)
                     if (s == nd - 1 && blk + 2 < NB) nbar_arrive(BAR_EMPTY + b, 384);
+                    const bool p2 = has_item && s + 2 < nd;
+                    double d0, d1, e0, e1;
+                    if (p2) phase2_issue(oXb + (s + 2) * XB, d0, d1, e0, e1);
                     if (live) phase5();
                     if (s + 1 < nd) {
-                        if (live) phase3(oXb + (s + 1) * XB, b2n_sm[oFb + (s + 1) * CH + c]);
+                        if (live) phase3(oXb + (s + 1) * XB, b2n_sm[oFb + (s + 1) * CH + c], L::O_Y + (((s + 1) & 1) * CH + c) * YS);
+                        if (p2) phase2_store(s & 1, d0, d1, e0, e1);
                         nbar_sync(BAR_STEP, 256);
                     }
                 }
             }
             if (live) {
                 if (nacc == 0) {   // recompute (v, logl) of the start point (:970-975), warp-local
+                    const int oy = L::O_Y + c * YS;
                     __syncwarp();
                     for (int i = lane; i < n; i += 32) {
                         const double vi = prior_sm(pk, L::O_P0, L::O_P1, i, b2n_sm[oucur + i]);
@@ -1266,18 +1371,18 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     // experiment (B2N_RWALK_OCC=3): three CTAs per SM at <= 85 registers (the matrix fragments spill to local memory)
     int occ = 2;
     if (const char* e = getenv("B2N_RWALK_OCC")) occ = atoi(e) == 3 ? 3 : 2;
-    // sixteen warps per 8 chains (rwalk_mma16_kernel) for the precision-matrix Gaussian; B2N_RWALK_WARPS=8: the 8-warp kernel
-    bool use_mma16 = use_mma && m.like_kind == B2N_LIKE_GAUSS_PREC && fast_draws && occ == 2;
-    if (const char* e = getenv("B2N_RWALK_WARPS")) use_mma16 = use_mma16 && atoi(e) == 16;
-    // warp-specialised kernel (8 step warps + 4 draw warps, rwalk_mmaws_kernel): B2N_RWALK_WARPS=12 (88 / 64 registers), 14 (96 / 48), 13 (no setmaxnreg)
-    int use_ws = 0;
-    if (const char* e = getenv("B2N_RWALK_WARPS")) {
-        const int w = atoi(e);
-        if ((w == 12 || w == 13 || w == 14) && use_mma && m.like_kind == B2N_LIKE_GAUSS_PREC && fast_draws && occ == 2) {
-            use_ws = w;
-            use_mma16 = false;
-        }
-    }
+    // Lock-step variants for the precision-matrix Gaussian (B2N_RWALK_WARPS forces one; measured at C2, profiles/r2n-r2q):
+    //   12 = rwalk_mmaws_kernel, 8 step + 4 draw warps -- the default where it applies: its static schedule of the
+    //        symmetric quadratic form is laid out for the largest slab count of a KT, and the draws need an idle lane 31
+    //        for the radius (n <= 62): n in 25..32, 49..52, 57..62;
+    //    8 = rwalk_mma_kernel (every other shape and likelihood);
+    //   16 = rwalk_mma16_kernel, sixteen warps per 8 chains (slower: kept as the measured counter-example).
+    int want = 12;
+    if (const char* e = getenv("B2N_RWALK_WARPS")) want = atoi(e);
+    const bool ws_base = use_mma && n <= 62 && m.like_kind == B2N_LIKE_GAUSS_PREC && fast_draws && occ == 2;
+    const bool full_slabs = ((n + 7) >> 3) == (8 * ((4 * KT + 7) / 8)) / 8;
+    const int use_ws = (want == 12 && ws_base && full_slabs) ? 12 : 0;
+    const bool use_mma16 = want == 16 && ws_base;
     size_t mma_smem = 0;
     if (use_mma) {
         const int ctas = occ * ctx->sm_count;               // 8-chain CTAs, two (three) resident per SM
@@ -1398,17 +1503,20 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         B2N_TRY(b2n_func_smem(ctx, (const void*)(rwalk_mma16_kernel<K>), (size_t)(smem)));          \
         rwalk_mma16_kernel<K><<<grid, 512, smem, ctx->stream>>>(p);                                 \
     } while (0)
-#define LAUNCH_MMAWS(K, R)                                                                          \
+#define LAUNCH_MMAWS(K, PL)                                                                        \
     do {                                                                                            \
-        B2N_TRY(b2n_func_smem(ctx, (const void*)(rwalk_mmaws_kernel<K, R>), (size_t)(smem)));       \
-        rwalk_mmaws_kernel<K, R><<<grid, 384, smem, ctx->stream>>>(p);                              \
+        B2N_TRY(b2n_func_smem(ctx, (const void*)(rwalk_mmaws_kernel<K, 1, PL>), (size_t)(smem)));   \
+        rwalk_mmaws_kernel<K, 1, PL><<<grid, 384, smem, ctx->stream>>>(p);                          \
     } while (0)
     B2N_TIME_BEGIN(ctx);
     if (use_ws) {
-        const int sr = use_ws == 12 ? 1 : (use_ws == 14 ? 2 : 0);
-        if (KT == 8) { if (sr == 1) LAUNCH_MMAWS(8, 1); else if (sr == 2) LAUNCH_MMAWS(8, 2); else LAUNCH_MMAWS(8, 0); }
-        else if (KT == 13) { if (sr == 1) LAUNCH_MMAWS(13, 1); else if (sr == 2) LAUNCH_MMAWS(13, 2); else LAUNCH_MMAWS(13, 0); }
-        else { if (sr == 1) LAUNCH_MMAWS(16, 1); else if (sr == 2) LAUNCH_MMAWS(16, 2); else LAUNCH_MMAWS(16, 0); }
+        // plain = no wrapped dimension and an affine prior: straight-line phase 3
+        bool plain = m.prior_kind != B2N_PRIOR_NORMAL_PPF;
+        if (a->dimflags)
+            for (int i = 0; i < n; i++) plain = plain && a->dimflags[i] == 0u;
+        if (KT == 8) { if (plain) LAUNCH_MMAWS(8, true); else LAUNCH_MMAWS(8, false); }
+        else if (KT == 13) { if (plain) LAUNCH_MMAWS(13, true); else LAUNCH_MMAWS(13, false); }
+        else { if (plain) LAUNCH_MMAWS(16, true); else LAUNCH_MMAWS(16, false); }
     } else if (use_mma16) {
         if (KT == 8) LAUNCH_MMA16(8);
         else if (KT == 13) LAUNCH_MMA16(13);

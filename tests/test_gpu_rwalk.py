@@ -246,6 +246,69 @@ def test_rwalk_mma_matches_warp_kernel(like):
     assert 0.002 < b['n_accept'].mean() / 30 < 0.98      # (eggbox at 32-D accepts ~1 %)
 
 
+class _Warps:
+    """B2N_RWALK_WARPS for the duration of a call: 8 = lock-step kernel, 12 = warp-specialised (8 step + 4 draw
+    warps), 16 = sixteen warps per 8 chains."""
+
+    def __init__(self, w):
+        self.w = w
+
+    def __enter__(self):
+        import os
+        self.old = os.environ.get('B2N_RWALK_WARPS')
+        os.environ['B2N_RWALK_WARPS'] = str(self.w)
+
+    def __exit__(self, *a):
+        import os
+        if self.old is None:
+            os.environ.pop('B2N_RWALK_WARPS', None)
+        else:
+            os.environ['B2N_RWALK_WARPS'] = self.old
+
+
+@pytest.mark.parametrize('n,walks', [(50, 30), (62, 17), (64, 17), (32, 8), (52, 70)])
+def test_rwalk_lockstep_variants_agree(n, walks):
+    """The three lock-step kernels for the precision-matrix Gaussian -- 8 warps, 8 step + 4 draw warps (symmetric
+    quadratic form, static tile schedule: n at the largest slab count of each KT), 16 warps -- on one queue with 3
+    ellipsoids, several groups of chains per CTA and a ring that is not a multiple of 8 steps: same draws, so the same
+    accept counts (up to proposals within round-off of the threshold) and end points equal to round-off."""
+    from oracle import likelihoods as OL
+    m = OL.gauss_corr(n, 0.4, 5.)
+    dm = device_model(m)
+    rng = np.random.default_rng(100 + n)
+    pts = 0.5 + 0.03 * rng.standard_normal((3000, n))
+    logl = m.loglike(m.prior_transform(pts))
+    loglstar = float(np.quantile(logl, 0.3))
+    good = pts[logl > loglstar]
+    ells = [OB.bounding_ellipsoid(good[i::3]) for i in range(3)]
+    ops.bound_set(np.array([e.axes for e in ells]))
+    Q = 5003
+    u0 = good[rng.integers(len(good), size=Q)]
+    ell = rng.integers(3, size=Q).astype(np.int32)
+    out = {}
+    for w in (8, 12, 16):
+        with _Impl('mma'), _Warps(w):
+            out[w] = ops.rwalk_batch(dm.model_id(), u0, loglstar, 0.4, walks, 777, chain0=11, ell=ell)
+    a = out[8]
+    assert np.all(a['n_accept'] + a['n_reject'] == walks) and a['n_accept'].mean() > 0.05 * walks
+    for w in (12, 16):
+        b = out[w]
+        same = a['n_accept'] == b['n_accept']
+        assert same.mean() > 0.999, w
+        close(b['u'][same], a['u'][same], rtol=1e-9)
+        close(b['v'][same], a['v'][same], rtol=1e-9)
+        np.testing.assert_allclose(b['logl'][same], a['logl'][same], rtol=1e-9, atol=1e-9)
+        assert np.all(b['logl'] > loglstar) and np.all(b['n_accept'] + b['n_reject'] == walks)
+    # a start point that never moves keeps its (recomputed) v and logl in every kernel
+    hi = 1e300
+    for w in (8, 12, 16):
+        with _Impl('mma'), _Warps(w):
+            o = ops.rwalk_batch(dm.model_id(), u0[:64], hi, 0.4, 9, 5, chain0=0, ell=ell[:64])
+        assert np.all(o['n_accept'] == 0)
+        np.testing.assert_array_equal(o['u'], u0[:64])
+        np.testing.assert_allclose(o['logl'], m.loglike(m.prior_transform(u0[:64])), rtol=1e-10)
+
+
 @pytest.mark.parametrize('sampler', ['rwalk', 'rslice'])
 def test_pinned_buffers_are_used_in_place(sampler):
     """Host-pointer mode with PINNED caller buffers: the chain kernels read the start points and write the
