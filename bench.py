@@ -620,10 +620,15 @@ def run_b200(args, cfg):
             peak = 6650.0
         kms = float(np.mean(kern_ms))
         achieved = algorithmic_bytes(n) * Q * walks / (kms * 1e-3) / 1e9
+        # which lock-step kernel the library runs for this shape (csrc/b2n_rwalk.cu: B2N_RWALK_WARPS, default 12)
+        ws = os.environ.get('B2N_RWALK_WARPS', '12') == '12'
+        kernel_key = 'rwalk_mmaws_kernel' if ws else 'rwalk_mma_kernel'
+        kernel_name = ("rwalk_mmaws_kernel<KT=13, setmaxnreg 88/64, plain>: 8 step + 4 draw warps per 8 chains, ring 2 x 8" if ws
+                       else "rwalk_mma_kernel<GAUSS_PREC, KT=13, 8 chains/CTA, ring 8>")
         traffic = None          # DRAM bytes per launch of this kernel from the committed ncu --set full capture
         try:                    # (profiles/traffic.json: a constant of the capture, NOT measured in this run)
             with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
-                traffic = json.load(f)['rwalk_mma_kernel']['dram_bytes_per_launch'] if Q == 2000 else None
+                traffic = json.load(f)[kernel_key]['dram_bytes_per_launch'] if Q == 2000 else None
         except Exception:
             pass
         flops_pp = 4 * n * n + 7 * n                      # flop per proposal
@@ -655,15 +660,15 @@ def run_b200(args, cfg):
                          "frac": ach_tf / fp64["mma_tflops"], "traffic": traffic, "traffic_unit": "bytes/launch",
                          "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel at this size; a "
                                            "constant, not measured in this run)",
-                         "kernel": "rwalk_mma_kernel<GAUSS_PREC, KT=13, 8 chains/CTA, ring 8>", "kernel_ms": kms,
+                         "kernel": kernel_name, "kernel_ms": kms,
                          "flops_per_proposal": flops_pp, "flops_per_launch": flops_pp * Q * walks,
                          "peak_source": "measured in this run: FP64 mma.m8n8k4 rate of this GPU (b2n_fp64_peak kind 1)",
                          "fp64_fma_peak_tflops": fp64["fma_tflops"], "fp64_mma_peak_tflops": fp64["mma_tflops"],
                          "pipes_floor_ms": t_floor_ms, "frac_of_pipes_floor": t_floor_ms / kms,
                          "note": ("MEASURED_PEAKS.json holds HBM and bf16 numbers only; this kernel computes in FP64, so the "
                                   "FP64 ceilings are measured here.  pipes_floor_ms = launch time with both FP64 pipes at their "
-                                  "measured ceilings; the rest is the draw latency chain (Philox + Box-Muller) and barriers, "
-                                  "DESIGN.md 9.1")},
+                                  "measured ceilings; the rest is the FP64 of the draws (Philox + Box-Muller) and the serial chain "
+                                  "phases of a step, DESIGN.md 9.6")},
             # SURVEY 8(d)'s no-reuse byte model (both 20 KB matrices charged to every proposal) against the measured
             # HBM copy peak.  > 1 by construction for a kernel that keeps the matrices in registers: kept as the
             # figure the survey defines, not as evidence.
@@ -780,7 +785,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--chains', type=int, default=0, help='chains per step per GPU (default nlive)')
-    ap.add_argument('--ensemble', type=int, default=256, help='full C2 runs (seeds) of the logZ / same-operating-point block; 0 = none')
+    ap.add_argument('--ensemble', type=int, default=512, help='full C2 runs (seeds) of the logZ / same-operating-point block; 0 = none')
     ap.add_argument('--in-flight', type=int, default=32, help='replicas in flight per GPU')
     ap.add_argument('--chain-pack', type=int, default=4, help='chains per CTA of the replicas (b2n_set_chain_pack)')
     ap.add_argument('--solo', type=int, default=1, help='N=1: also time one run alone on the GPU')

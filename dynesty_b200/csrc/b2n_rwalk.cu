@@ -927,7 +927,13 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
             const int nlc = (cd.y - g0) < CH ? (cd.y - g0) : CH;
             const bool live = c < nlc;
             const int q = live ? p.order[cd.x + g0 + c] : 0;
-            int oucur = L::O_ST + c * 4 * RS, ouprop = oucur + RS, ovcur = ouprop + RS, ovprop = ovcur + RS;
+            // chain state in shared memory: [u_a | u_b | v_a | v_b]; `par` says which half holds the current point
+            const int ost = L::O_ST + c * 4 * RS;
+            int par = 0;
+#define oucur (ost + par * RS)
+#define ouprop (ost + (par ^ 1) * RS)
+#define ovcur (ost + 2 * RS + par * RS)
+#define ovprop (ost + 2 * RS + (par ^ 1) * RS)
             if (live)
                 for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)q * n + i];
             int nacc = 0, nrej = 0;
@@ -1010,8 +1016,7 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
                 for (int w2 = 0; w2 < L::NSW; w2++) qf += b2n_sm[L::O_Q + w2 * CH + c];
                 const double l = p.m.s0 - qf;
                 if (ok && l > loglstar_) {
-                    int t = oucur; oucur = ouprop; ouprop = t;
-                    t = ovcur; ovcur = ovprop; ovprop = t;
+                    par ^= 1;
                     lcur = l;
                     nacc++;
                 } else {
@@ -1019,6 +1024,12 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
                 }
             };
 
+            // Per ring buffer (nd <= 8 slots): two barrier intervals per step,
+            //   I(s) = phase 4 of slot s                          C(s) = [issue phase 2 of slot s + 2] phase 5 of slot s,
+            //                                                            phase 3 of slot s + 1, [store phase 2]
+            // (one pipeline over ALL slots, waiting for the next buffer where it is first touched -- two steps early --
+            //  was measured slower, 0.200 against 0.192 ms at C2: with two buffers the draw warps then have 6 instead of
+            //  8 steps to refill one, and both roles wait for each other; profiles/r2r)
             for (int blk = 0; blk < NB; blk++) {
                 const int b = blk & 1, step0 = blk * DEPTH;
                 const int nd = (p.walks - step0) < DEPTH ? (p.walks - step0) : DEPTH;
@@ -1079,6 +1090,10 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
             __syncthreads();
             for (int e = threadIdx.x; e < 2 * L::RING; e += blockDim.x) b2n_sm[L::O_X + e] = 0.0;
             __syncthreads();
+#undef oucur
+#undef ouprop
+#undef ovcur
+#undef ovprop
         }
     }
     peer_finish(p.peer);
