@@ -815,11 +815,16 @@ __device__ __forceinline__ void nbar_arrive(int id, int count) {
 // 0.226 / 0.2045 / 0.2086 ms -- only 1 is instantiated).
 // PLAIN: no periodic / reflective dimension and a prior that is affine per component (uniform, identity): phase 3 is
 // then straight-line code for the (at most) two components of a lane.
+// Ring: RB = 2 buffers of DB = 8 steps; the step warps start every buffer with a two-interval prologue.  Measured and not
+// kept (profiles/r2r, r2t): ONE pipeline over all ring slots, the next buffer awaited where it is first touched (two steps
+// early) -- on 2 x 8 slots 0.200 ms, on 4 x 4 slots 0.207 ms against 0.193 ms: the draw warps are ~80 % busy, and taking
+// two steps of slack away from them makes both roles wait for each other.
 template <int KT, int SETREG, bool PLAIN>
 __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p) {
     using L = MmaWsLayout<KT>;
     constexpr int CH = L::CH, DEPTH = L::DEPTH, XS = L::XS, YS = L::YS, XB = L::XB, RS = L::RS;
-    constexpr int BAR_STEP = 1, BAR_FULL = 2, BAR_EMPTY = 4;      // named barriers (0 = __syncthreads)
+    constexpr int DB = 8, RB = 2;
+    constexpr int BAR_STEP = 1, BAR_FULL = 2, BAR_EMPTY = 2 + RB;  // named barriers (0 = __syncthreads)
     const int n = p.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     B2N_DYN_PROLOGUE(p)
@@ -833,7 +838,7 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
     }
     for (int e = threadIdx.x; e < 2 * L::RING; e += blockDim.x) b2n_sm[L::O_X + e] = 0.0;
     __syncthreads();
-    const int NB = (p.walks + DEPTH - 1) / DEPTH;                 // ring buffers per group of chains
+    const int NB = (p.walks + DB - 1) / DB;                       // ring buffers filled per group of chains
 
     if (warp >= L::NSW) {
         // =============================== draw warps ===============================
@@ -844,11 +849,11 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
         for (int g0 = 0; g0 < cd.y; g0 += CH) {
             const int nlc = (cd.y - g0) < CH ? (cd.y - g0) : CH;
             for (int blk = 0; blk < NB; blk++) {
-                const int b = blk & 1, step0 = blk * DEPTH;
-                const int nd = (p.walks - step0) < DEPTH ? (p.walks - step0) : DEPTH;
+                const int b = blk & (RB - 1), step0 = blk * DB;
+                const int nd = (p.walks - step0) < DB ? (p.walks - step0) : DB;
                 const int nit = nd * nlc;
-                const int oXb = L::O_X + b * L::RING;
-                if (blk >= 2) nbar_sync(BAR_EMPTY + b, 384);      // the step warps have finished with this buffer
+                const int oXb = L::O_X + b * DB * XB;
+                if (blk >= RB) nbar_sync(BAR_EMPTY + b, 384);     // the step warps have finished with this buffer
                 for (int w = dw; w < nit; w += 2 * L::NDW) {      // two items side by side (their chains interleave)
                     const int w2 = w + L::NDW;
                     const bool two = w2 < nit;
@@ -876,15 +881,16 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
                 __syncwarp();
                 {   // step factors of this warp's items, one lane per item: item w = dw + NDW * lane
                     const int w = dw + L::NDW * lane;
-                    if (lane < 16 && w < nit) {
+                    if (lane < 2 * DB && w < nit) {
                         int sa, ca;
                         if (nlc == CH) { sa = w >> 3; ca = w & 7; }
                         else { sa = w / nlc; ca = w - sa * nlc; }
                         const int e = sa * CH + ca;
-                        b2n_sm[L::O_F + b * DEPTH * CH + e] =
+                        b2n_sm[L::O_F + b * DB * CH + e] =
                             scale_ * b2n_div(exp(b2n_sm[L::O_LG + e] * inv_n), b2n_sqrt(b2n_sm[L::O_SS + e]));
                     }
                 }
+                __syncwarp();             // lane 0 rewrites the scratch in the next buffer's first pass (racecheck, r2t)
                 __threadfence_block();
                 nbar_arrive(BAR_FULL + b, 384);
             }
@@ -1024,16 +1030,14 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
                 }
             };
 
-            // Per ring buffer (nd <= 8 slots): two barrier intervals per step,
-            //   I(s) = phase 4 of slot s                          C(s) = [issue phase 2 of slot s + 2] phase 5 of slot s,
-            //                                                            phase 3 of slot s + 1, [store phase 2]
-            // (one pipeline over ALL slots, waiting for the next buffer where it is first touched -- two steps early --
-            //  was measured slower, 0.200 against 0.192 ms at C2: with two buffers the draw warps then have 6 instead of
-            //  8 steps to refill one, and both roles wait for each other; profiles/r2r)
+            // Two barrier intervals per step,
+            //   I(g) = phase 4 of slot g                          C(g) = [issue phase 2 of slot g + 2] phase 5 of slot g,
+            //                                                            phase 3 of slot g + 1, [store phase 2]
+            // per ring buffer (nd <= 8 slots), with a prologue
             for (int blk = 0; blk < NB; blk++) {
-                const int b = blk & 1, step0 = blk * DEPTH;
-                const int nd = (p.walks - step0) < DEPTH ? (p.walks - step0) : DEPTH;
-                const int oXb = L::O_X + b * L::RING, oFb = L::O_F + b * DEPTH * CH;
+                const int b = blk & 1, step0 = blk * DB;
+                const int nd = (p.walks - step0) < DB ? (p.walks - step0) : DB;
+                const int oXb = L::O_X + b * DB * XB, oFb = L::O_F + b * DB * CH;
                 nbar_sync(BAR_FULL + b, 384);                     // the draw warps have filled this buffer
                 if (has_item) {
                     double d0, d1, e0, e1;
@@ -1047,18 +1051,18 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
                 nbar_sync(BAR_STEP, 256);
                 if (live) phase3(oXb, b2n_sm[oFb + c], L::O_Y + c * YS);
                 nbar_sync(BAR_STEP, 256);
-                for (int s = 0; s < nd; s++) {
-                    phase4(oXb + s * XB);
+                for (int s2 = 0; s2 < nd; s2++) {
+                    phase4(oXb + s2 * XB);
                     nbar_sync(BAR_STEP, 256);
                     // every read of this ring buffer is done: hand it back to the draw warps (if they will ask for it)
-                    if (s == nd - 1 && blk + 2 < NB) nbar_arrive(BAR_EMPTY + b, 384);
-                    const bool p2 = has_item && s + 2 < nd;
+                    if (s2 == nd - 1 && blk + 2 < NB) nbar_arrive(BAR_EMPTY + b, 384);
+                    const bool p2 = has_item && s2 + 2 < nd;
                     double d0, d1, e0, e1;
-                    if (p2) phase2_issue(oXb + (s + 2) * XB, d0, d1, e0, e1);
+                    if (p2) phase2_issue(oXb + (s2 + 2) * XB, d0, d1, e0, e1);
                     if (live) phase5();
-                    if (s + 1 < nd) {
-                        if (live) phase3(oXb + (s + 1) * XB, b2n_sm[oFb + (s + 1) * CH + c], L::O_Y + (((s + 1) & 1) * CH + c) * YS);
-                        if (p2) phase2_store(s & 1, d0, d1, e0, e1);
+                    if (s2 + 1 < nd) {
+                        if (live) phase3(oXb + (s2 + 1) * XB, b2n_sm[oFb + (s2 + 1) * CH + c], L::O_Y + (((s2 + 1) & 1) * CH + c) * YS);
+                        if (p2) phase2_store(s2 & 1, d0, d1, e0, e1);
                         nbar_sync(BAR_STEP, 256);
                     }
                 }
