@@ -230,8 +230,8 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // which is the longest dependency chain of a step (Philox -> log -> sqrt -> sincospi).
 // FAST = the draws use the branch-free math of b2n_fastmath.cuh, two ring items at a time per warp
 // (the default; B2N_RWALK_DRAWS=libm selects libdevice math, results differ by a few ulp in the directions).
-template <int LIKE, int KT, int CH, int DEPTH, bool FAST, int OCC = 2>
-__global__ void __launch_bounds__(CH * 32, CH == 8 ? OCC : 1) rwalk_mma_kernel(const RwalkParams p) {
+template <int LIKE, int KT, int CH, int DEPTH, bool FAST>
+__global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(const RwalkParams p) {
     constexpr int B2N_MMA_CH = CH;
     constexpr int RS = 8 * ((4 * KT + 7) / 8);                    // rows padded to whole 8-row slabs
     constexpr int XS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16));   // chain stride == 4 (mod 16):
@@ -822,8 +822,8 @@ __device__ __forceinline__ void nbar_arrive(int id, int count) {
 template <int KT, int SETREG, bool PLAIN>
 __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p) {
     using L = MmaWsLayout<KT>;
-    constexpr int CH = L::CH, DEPTH = L::DEPTH, XS = L::XS, YS = L::YS, XB = L::XB, RS = L::RS;
-    constexpr int DB = 8, RB = 2;
+    constexpr int CH = L::CH, XS = L::XS, YS = L::YS, XB = L::XB, RS = L::RS;
+    constexpr int DB = L::DEPTH, RB = 2;
     constexpr int BAR_STEP = 1, BAR_FULL = 2, BAR_EMPTY = 2 + RB;  // named barriers (0 = __syncthreads)
     const int n = p.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1387,9 +1387,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     // log / sqrt / sincospi, one item at a time (measured 3.6 % slower per C2 launch, results differ by a few ulp)
     const char* denv = getenv("B2N_RWALK_DRAWS");
     const bool fast_draws = !(denv && !strcmp(denv, "libm")) && DU == 8;
-    // experiment (B2N_RWALK_OCC=3): three CTAs per SM at <= 85 registers (the matrix fragments spill to local memory)
-    int occ = 2;
-    if (const char* e = getenv("B2N_RWALK_OCC")) occ = atoi(e) == 3 ? 3 : 2;
+    const int occ = 2;                                      // 8-chain CTAs resident per SM
     // Lock-step variants for the precision-matrix Gaussian (B2N_RWALK_WARPS forces one; measured at C2, profiles/r2n-r2q):
     //   12 = rwalk_mmaws_kernel, 8 step + 4 draw warps -- the default where it applies: its static schedule of the
     //        symmetric quadratic form is laid out for the largest slab count of a KT, and the draws need an idle lane 31
@@ -1500,14 +1498,8 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         B2N_TRY(b2n_func_smem(ctx, (const void*)(rwalk_mma_kernel<L, K, 8, D, F>), (size_t)(smem))); \
         rwalk_mma_kernel<L, K, 8, D, F><<<grid, 256, smem, ctx->stream>>>(p);                        \
     } while (0)
-#define LAUNCH_MMA3(L, K)                                                                            \
-    do {                                                                                            \
-        B2N_TRY(b2n_func_smem(ctx, (const void*)(rwalk_mma_kernel<L, K, 8, 8, true, 3>), (size_t)(smem))); \
-        rwalk_mma_kernel<L, K, 8, 8, true, 3><<<grid, 256, smem, ctx->stream>>>(p);                  \
-    } while (0)
 #define LAUNCH_MMA(L, K)                        \
     if (DU == 1) LAUNCH_MMA2(L, K, 1, false);   \
-    else if (fast_draws && occ == 3 && L == B2N_LIKE_GAUSS_PREC && K == 13) LAUNCH_MMA3(L, K); \
     else if (fast_draws) LAUNCH_MMA2(L, K, 8, true); \
     else LAUNCH_MMA2(L, K, 8, false);
 #define CALL_MMA(L)                      \

@@ -299,6 +299,16 @@ def test_rwalk_lockstep_variants_agree(n, walks):
         close(b['v'][same], a['v'][same], rtol=1e-9)
         np.testing.assert_allclose(b['logl'][same], a['logl'][same], rtol=1e-9, atol=1e-9)
         assert np.all(b['logl'] > loglstar) and np.all(b['n_accept'] + b['n_reject'] == walks)
+    # wrapped dimensions: the generic (not straight-line) chain phase of the warp-specialised kernel
+    flags = ops.dimflags_from(n, [0, 3, n - 1], [5, 6])
+    fo = {}
+    for w in (8, 12):
+        with _Impl('mma'), _Warps(w):
+            fo[w] = ops.rwalk_batch(dm.model_id(), u0[:777], loglstar, 0.4, walks, 778, chain0=3, ell=ell[:777], dimflags=flags)
+    same = fo[8]['n_accept'] == fo[12]['n_accept']
+    assert same.mean() > 0.995
+    close(fo[12]['u'][same], fo[8]['u'][same], rtol=1e-9)
+    np.testing.assert_allclose(fo[12]['logl'][same], fo[8]['logl'][same], rtol=1e-9, atol=1e-9)
     # a start point that never moves keeps its (recomputed) v and logl in every kernel
     hi = 1e300
     for w in (8, 12, 16):
