@@ -20,9 +20,6 @@
 // ------------------------------------------------------------------ moments
 #define B2N_FMAX_SUB 4     // CTAs per 128-row job in the fmax scan
 
-struct JobL {   // MomentJob + perm level
-    int node, r0, r1, slot, level, pad0, pad1, pad2;
-};
 
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const double* __restrict__ P, const int* __restrict__ perm,
                                                              int64_t N, int n, const JobL* __restrict__ jobs,
@@ -263,6 +260,11 @@ __global__ void __launch_bounds__(1024) eig_ladder_kernel(NodeArrays na, const i
 // break-down, condition bound, slow power iteration: near-degenerate leading eigenvalues) is flagged
 // `suspect` and the caller redoes the whole update with the eigen path.  Accepted leaves are always
 // re-fitted with the eigen path (they need axes / axlens), so outputs never come from this kernel.
+// PART 0: the whole candidate fit in one launch.  The fit is two INDEPENDENT latency chains that both start from the
+// raw covariance -- (1) Cholesky -> L^-1 -> am, pivots, conditioning; (2) repeated squaring -> major axis -- so the
+// caller may run them as two launches on two streams (PART 1 on the main stream, PART 2 on a side stream; they
+// write disjoint outputs and disjoint words of the node's NodeStat: `suspect` / `pad`), b2n_process_nodes.
+template <int PART>
 __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int* __restrict__ nodelist) {
     extern __shared__ double sm[];
     const int n = na.n, ld = na.ld, tid = threadIdx.x, T = blockDim.x;
@@ -279,13 +281,15 @@ __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int
     const double* src = na.covraw + (size_t)node * nn;
     double* Cm = na.cov + (size_t)node * nn;
     NodeStat* st = na.stat + node;
+    if (tid == 0) { s_bad = 0; s_it = 0; }
+    double cnorm = 0.0, anorm = 0.0;
+    if (PART != 2) {
     for (size_t e = tid; e < nn; e += T) {
         const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
         const double c = src[e];
         Cm[e] = c;
         L[(size_t)i * ld + j] = c;
     }
-    if (tid == 0) { s_bad = 0; s_it = 0; }
     __syncthreads();
     // ---- |cov|_inf
     double rs = 0.0;
@@ -297,7 +301,6 @@ __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int
     rs = warp_max(rs);
     if ((tid & 31) == 0) red[tid >> 5] = rs;
     __syncthreads();
-    double cnorm = 0.0;
     for (int w = 0; w < ((T + 31) >> 5); w++) cnorm = fmax(cnorm, red[w]);
     __syncthreads();
     // ---- right-looking Cholesky, two barriers per column
@@ -323,7 +326,10 @@ __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int
     }
     __syncthreads();
     if (s_bad) {
-        if (tid == 0) { st->suspect = 1; st->good = 1; st->fallback = 0; st->retry = 0; st->sweeps = 0; }
+        if (tid == 0) {
+            st->suspect = 1; st->good = 1; st->fallback = 0; st->retry = 0;
+            if (PART == 0) { st->sweeps = 0; st->pad = 0; }
+        }
         for (int k = tid; k < n; k += T) na.lam[(size_t)node * n + k] = 1.0;
         return;
     }
@@ -362,8 +368,14 @@ __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int
     rs = warp_max(rs);
     if ((tid & 31) == 0) red[tid >> 5] = rs;
     __syncthreads();
-    double anorm = 0.0;
     for (int w = 0; w < ((T + 31) >> 5); w++) anorm = fmax(anorm, red[w]);
+    __syncthreads();
+    for (int k = tid; k < n; k += T) na.lam[(size_t)node * n + k] = dg[k] * dg[k];
+    if (PART == 1) {
+        if (tid == 0) { st->suspect = (cnorm * anorm < 1e10) ? 0 : 1; st->good = 1; st->fallback = 0; st->retry = 0; }
+        return;
+    }
+    }   // PART != 2
     __syncthreads();
     // ---- major axis.  Plain power iteration stalls on the deep nodes of the tree (a half of a half of a
     //      Gaussian cloud has a leading eigenvalue within a few % of the next ones), so the dominant
@@ -495,14 +507,19 @@ __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int
         const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
         AX[e] = (j == n - 1) ? sgn * v[i] * ax : 0.0;
     }
-    for (int k = tid; k < n; k += T) na.lam[(size_t)node * n + k] = dg[k] * dg[k];
     if (tid == 0) {
-        const bool ok = conv && (cnorm * anorm < 1e10) && (lam > 0.0);
-        st->suspect = ok ? 0 : 1;
-        st->good = 1;
-        st->fallback = 0;
-        st->sweeps = it;
-        st->retry = 0;
+        if (PART == 2) {            // the major-axis half reports through its own word
+            st->pad = (conv && lam > 0.0) ? 0 : 1;
+            st->sweeps = it;
+        } else {
+            const bool ok = conv && (cnorm * anorm < 1e10) && (lam > 0.0);
+            st->suspect = ok ? 0 : 1;
+            st->good = 1;
+            st->fallback = 0;
+            st->sweeps = it;
+            st->retry = 0;
+            st->pad = 0;
+        }
     }
 }
 
@@ -732,11 +749,36 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
         }
         // large n: packed-triangle / column-sliced Jacobi (b2n_eig_sliced.cu); else the single-CTA kernel
         int sliced = 0;
+        bool chol_split = false;
         if (candidate) {            // Cholesky path (pass 0 only: certified nodes never need the second pass)
             const size_t csm = (size_t)(2 * n * ld + 3 * n + 32) * sizeof(double);
-            B2N_TRY(b2n_func_smem(ctx, (const void*)(chol_node_kernel), (size_t)(csm)));
-            chol_node_kernel<<<pn, 512, csm, st>>>(w.na, (const int*)plist);
-            B2N_LAUNCH_CHECK(ctx);
+            const char* cenv = getenv("B2N_CHOL_SPLIT");
+            chol_split = !(cenv && cenv[0] == '0');
+            if (chol_split && !ctx->stream_side2) {
+                int lo = 0, hi = 0;
+                if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { cudaGetLastError(); hi = 0; }
+                B2N_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream_side2, cudaStreamNonBlocking, hi));
+                B2N_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_side2, cudaEventDisableTiming));
+                B2N_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_side2_go, cudaEventDisableTiming));
+            }
+            if (chol_split) {
+                // the two halves of the candidate fit side by side: the major axes (repeated squaring) on the side
+                // stream, Cholesky / precision matrix / fmax scan on the main one; they meet before scale_finish
+                // (which rescales the axes)
+                B2N_TRY(b2n_func_smem(ctx, (const void*)(chol_node_kernel<1>), (size_t)(csm)));
+                B2N_TRY(b2n_func_smem(ctx, (const void*)(chol_node_kernel<2>), (size_t)(csm)));
+                B2N_CUDA(ctx, cudaEventRecord(ctx->ev_side2_go, st));
+                B2N_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_side2, ctx->ev_side2_go, 0));
+                chol_node_kernel<2><<<pn, 512, csm, ctx->stream_side2>>>(w.na, (const int*)plist);
+                B2N_LAUNCH_CHECK(ctx);
+                B2N_CUDA(ctx, cudaEventRecord(ctx->ev_side2, ctx->stream_side2));
+                chol_node_kernel<1><<<pn, 512, csm, st>>>(w.na, (const int*)plist);
+                B2N_LAUNCH_CHECK(ctx);
+            } else {
+                B2N_TRY(b2n_func_smem(ctx, (const void*)(chol_node_kernel<0>), (size_t)(csm)));
+                chol_node_kernel<0><<<pn, 512, csm, st>>>(w.na, (const int*)plist);
+                B2N_LAUNCH_CHECK(ctx);
+            }
         } else if (!use_smem) B2N_TRY(b2n_eig_sliced(w, (const int*)plist, pn, pass, 0, &sliced));
         if (!candidate && !sliced) {
             eig_ladder_kernel<<<pn, eig_threads, eig_smem, st>>>(w.na, (const int*)plist, pass, gwork, use_smem);
@@ -744,6 +786,7 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
         }
         fmax_partial_kernel<<<dim3(pj, B2N_FMAX_SUB), 256, fm_smem, st>>>(w.P, w.perm, w.N, w.na, (const JobL*)pjobs, partial);
         B2N_LAUNCH_CHECK(ctx);
+        if (chol_split) B2N_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_side2, 0));
         scale_finish_kernel<<<pn, 1024, 0, st>>>(w.na, (const NodeRef*)prefs, partial, pass, w.logvol_pref, B2N_FMAX_SUB);
         B2N_LAUNCH_CHECK(ctx);
         // read back the node stats (one copy of the whole small array)
@@ -795,6 +838,111 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
     }
     stats = hs;
     return B2N_OK;
+}
+
+// ------------------------------------------------------------------ speculative fit of the root node
+// _bounding_ellipsoids (bounding.py:1464-1563) returns the ROOT ellipsoid whenever no split of the candidate tree
+// is accepted -- every update of a unimodal live set (C2).  An accepted leaf needs the full eigen fit (axes,
+// axlens, the reference's repair ladder): moments + eig_ladder + fmax + finish = 0.75 ms of single-CTA latency
+// at n = 50 that used to FOLLOW the ~1.9 ms of the candidate tree.  The root's fit depends on the root's moments
+// only, and those exist after the first candidate launch: it is issued on a second (high-priority) stream into
+// SHADOW arrays, occupies one SM while the tree is expanded on the others, and is adopted at the end if the root
+// is the accepted leaf and its covariance needed no repair (otherwise the ordinary re-fit runs, as before).
+// Reads shared with the main stream are read-only there (points, mean / covraw of node 0); the row order is a
+// private copy of perm level 0 (the ping-pong buffer is overwritten two levels down).
+int b2n_spec_root_launch(BoundWork& w, int count, SpecRoot& sp) {
+    b2n_ctx* ctx = w.ctx;
+    const int n = w.n;
+    const size_t nn = (size_t)n * n;
+    sp.launched = false;
+    const int ld = w.na.ld, half = ((n + 1) & ~1) / 2;
+    const size_t small_b = (size_t)(2 * half + 2 * n + 32) * sizeof(double);
+    const size_t eig_smem = small_b + (size_t)2 * n * ld * sizeof(double);
+    if (eig_smem > (size_t)ctx->max_smem_optin) return B2N_OK;          // sliced solver territory: no speculation
+    if (!ctx->stream_side) {
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { cudaGetLastError(); hi = 0; }
+        B2N_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream_side, cudaStreamNonBlocking, hi));
+        B2N_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming));
+        B2N_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_side_go, cudaEventDisableTiming));
+    }
+    cudaStream_t side = ctx->stream_side;
+    sp.jobs.clear();
+    for (int a = 0; a < count; a += B2N_ROWS_PER_JOB) {
+        JobL j;
+        memset(&j, 0, sizeof(j));
+        j.node = 0; j.r0 = a; j.r1 = std::min(a + B2N_ROWS_PER_JOB, count); j.slot = (int)sp.jobs.size(); j.level = 0;
+        sp.jobs.push_back(j);
+    }
+    const int njobs = (int)sp.jobs.size();
+    memset(&sp.ref, 0, sizeof(sp.ref));
+    sp.ref.node = 0; sp.ref.start = 0; sp.ref.count = count; sp.ref.slot0 = 0; sp.ref.nslots = njobs; sp.ref.level = 0;
+    sp.node0 = 0;
+    size_t bytes = 0;
+    auto take = [&bytes](size_t b) { const size_t o = bytes; bytes += (b + 255) & ~(size_t)255; return o; };
+    const size_t o_perm = take((size_t)w.N * sizeof(int));
+    const size_t o_jobs = take((size_t)njobs * sizeof(JobL));
+    const size_t o_ref = take(sizeof(NodeRef));
+    const size_t o_list = take(sizeof(int));
+    const size_t o_part = take((size_t)njobs * B2N_FMAX_SUB * sizeof(double));
+    const size_t o_cov = take(nn * sizeof(double)), o_am = take(nn * sizeof(double)), o_axes = take(nn * sizeof(double));
+    const size_t o_lam = take((size_t)n * sizeof(double)), o_axl = take((size_t)n * sizeof(double));
+    const size_t o_stat = take(sizeof(NodeStat));
+    B2N_CUDA(ctx, ctx->spec.ensure(bytes));
+    char* b = ctx->spec.as<char>();
+    sp.perm = (int*)(b + o_perm);
+    sp.na = w.na;                          // mean / covraw: the main arrays (node 0, read-only from here on)
+    sp.na.cov = (double*)(b + o_cov); sp.na.am = (double*)(b + o_am); sp.na.axes = (double*)(b + o_axes);
+    sp.na.lam = (double*)(b + o_lam); sp.na.axlens = (double*)(b + o_axl); sp.na.stat = (NodeStat*)(b + o_stat);
+    // the row order of the root: copied on the MAIN stream (ordered before the partitions that recycle the buffer)
+    B2N_CUDA(ctx, cudaMemcpyAsync(sp.perm, w.perm, (size_t)w.N * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    B2N_CUDA(ctx, cudaEventRecord(ctx->ev_side_go, ctx->stream));
+    B2N_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_side_go, 0));
+    B2N_CUDA(ctx, cudaMemcpyAsync(b + o_jobs, sp.jobs.data(), (size_t)njobs * sizeof(JobL), cudaMemcpyHostToDevice, side));
+    B2N_CUDA(ctx, cudaMemcpyAsync(b + o_ref, &sp.ref, sizeof(NodeRef), cudaMemcpyHostToDevice, side));
+    B2N_CUDA(ctx, cudaMemcpyAsync(b + o_list, &sp.node0, sizeof(int), cudaMemcpyHostToDevice, side));
+    B2N_CUDA(ctx, cudaMemsetAsync(b + o_stat, 0, sizeof(NodeStat), side));
+    B2N_TRY(b2n_func_smem(ctx, (const void*)(eig_ladder_kernel), eig_smem));
+    const int eig_threads = 32 * std::max(4, std::min(32, half));
+    eig_ladder_kernel<<<1, eig_threads, eig_smem, side>>>(sp.na, (const int*)(b + o_list), 0, nullptr, 1);
+    B2N_LAUNCH_CHECK(ctx);
+    fmax_partial_kernel<<<dim3(njobs, B2N_FMAX_SUB), 256, (size_t)8 * n * sizeof(double), side>>>(
+        w.P, sp.perm, w.N, sp.na, (const JobL*)(b + o_jobs), (double*)(b + o_part));
+    B2N_LAUNCH_CHECK(ctx);
+    scale_finish_kernel<<<1, 1024, 0, side>>>(sp.na, (const NodeRef*)(b + o_ref), (const double*)(b + o_part), 0,
+                                              w.logvol_pref, B2N_FMAX_SUB);
+    B2N_LAUNCH_CHECK(ctx);
+    B2N_CUDA(ctx, cudaEventRecord(ctx->ev_side, side));
+    sp.launched = true;
+    return B2N_OK;
+}
+
+// Wait for the speculative fit; *ok = it is the fit the ordinary path would have produced for node 0 (covariance
+// accepted untouched, no error) and its arrays are now node 0's.
+int b2n_spec_root_adopt(BoundWork& w, SpecRoot& sp, NodeStat* stat, bool* ok) {
+    b2n_ctx* ctx = w.ctx;
+    *ok = false;
+    if (!sp.launched) return B2N_OK;
+    B2N_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+    NodeStat hs;
+    B2N_CUDA(ctx, b2n_copy_sync(ctx, &hs, sp.na.stat, sizeof(NodeStat), cudaMemcpyDeviceToHost));
+    if (!hs.good || hs.fallback || hs.error || hs.retry) return B2N_OK;
+    const size_t n = w.n, nn = n * n;
+    cudaStream_t st = ctx->stream;
+    B2N_CUDA(ctx, cudaMemcpyAsync(w.na.cov, sp.na.cov, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    B2N_CUDA(ctx, cudaMemcpyAsync(w.na.am, sp.na.am, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    B2N_CUDA(ctx, cudaMemcpyAsync(w.na.axes, sp.na.axes, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    B2N_CUDA(ctx, cudaMemcpyAsync(w.na.lam, sp.na.lam, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    B2N_CUDA(ctx, cudaMemcpyAsync(w.na.axlens, sp.na.axlens, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    B2N_CUDA(ctx, cudaMemcpyAsync(w.na.stat, sp.na.stat, sizeof(NodeStat), cudaMemcpyDeviceToDevice, st));
+    *stat = hs;
+    *ok = true;
+    return B2N_OK;
+}
+
+void b2n_spec_root_wait(b2n_ctx* ctx, SpecRoot& sp) {
+    if (sp.launched && ctx->stream_side) cudaStreamSynchronize(ctx->stream_side);
+    sp.launched = false;
 }
 
 // np.mean / np.cov(ddof=1) of one node (rows [0, count) of perm level 0): the moment kernels of b2n_process_nodes

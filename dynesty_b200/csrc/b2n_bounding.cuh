@@ -71,6 +71,21 @@ int b2n_boundwork_init(b2n_ctx* ctx, BoundWork& w, const double* dP, int64_t N, 
 // returns few): Cholesky-based precision / log-volume + power-iteration major axis, see chol_node_kernel.
 int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs, std::vector<NodeStat>& stats,
                       bool candidate = false);
+// speculative eigen fit of the root node on the context's side stream (b2n_bounding.cu)
+struct JobL {   // MomentJob + perm level
+    int node, r0, r1, slot, level, pad0, pad1, pad2;
+};
+struct SpecRoot {
+    bool launched = false;
+    NodeArrays na;               // shadow arrays of node 0 (mean / covraw alias the main arrays)
+    int* perm = nullptr;         // private copy of the root's row order
+    std::vector<JobL> jobs;      // host copies live as long as the copies they feed
+    NodeRef ref;
+    int node0 = 0;
+};
+int b2n_spec_root_launch(BoundWork& w, int count, SpecRoot& sp);
+int b2n_spec_root_adopt(BoundWork& w, SpecRoot& sp, NodeStat* stat, bool* ok);
+void b2n_spec_root_wait(b2n_ctx* ctx, SpecRoot& sp);
 int b2n_emit_node(BoundWork& w, int node, int k, double* ctr, double* cov, double* am, double* axes, double* axlens);
 int b2n_init_identity_perm(BoundWork& w);
 // mean + sample covariance (ddof = 1) of node 0 = rows [0, count) of perm level 0 -> w.na.mean / w.na.covraw

@@ -115,6 +115,10 @@ struct b2n_ctx {
     void* friends = nullptr;    // resident RadFriends / SupFriends bound (b2n_friends.cu)
     int min_cpc = 1;            // b2n_set_chain_pack: at least this many chains per CTA (see include/b200nest.h)
     int bound_fast_skip = 0;    // b2n_multi_decompose: updates left to skip the Cholesky candidate path
+    // speculative eigen fit of the root node, concurrent with the candidate tree (b2n_bounding.cu: b2n_spec_root_*)
+    cudaStream_t stream_side = nullptr, stream_side2 = nullptr;   // side2: the major-axis half of the candidate fits
+    cudaEvent_t ev_side = nullptr, ev_side_go = nullptr, ev_side2 = nullptr, ev_side2_go = nullptr;
+    DevBuf spec;
     bool zc_enabled = false;    // chain entry points, host-pointer mode: pinned caller buffers are used in place
     // cached chain worklist of the single-ellipsoid case (identity order, equal CTAs): rebuilt only when
     // (Q, chains per CTA) change -- saves two small pageable H2D copies per queue fill

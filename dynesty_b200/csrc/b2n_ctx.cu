@@ -92,7 +92,9 @@ void b2n_free(b2n_ctx* ctx) {
                       &ctx->in2, &ctx->in3, &ctx->out0, &ctx->out1, &ctx->out2, &ctx->out3,
                       &ctx->out4, &ctx->out5, &ctx->out6, &ctx->out7, &ctx->scratch0,
                       &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->scratch4,
-                      &ctx->scratch5, &ctx->work0, &ctx->work1, &ctx->wl_order, &ctx->wl_cta};
+                      &ctx->scratch5, &ctx->work0, &ctx->work1, &ctx->wl_order, &ctx->wl_cta, &ctx->spec};
+    if (ctx->stream_side) cudaStreamSynchronize(ctx->stream_side);
+    if (ctx->stream_side2) cudaStreamSynchronize(ctx->stream_side2);
     for (DevBuf* b : bufs) b->release();
     b2n_peer_release(ctx);
     b2n_ns_release(ctx);
@@ -103,6 +105,12 @@ void b2n_free(b2n_ctx* ctx) {
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream_hi) cudaStreamDestroy(ctx->stream_hi);
     if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
+    if (ctx->stream_side) cudaStreamDestroy(ctx->stream_side);
+    if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
+    if (ctx->ev_side_go) cudaEventDestroy(ctx->ev_side_go);
+    if (ctx->stream_side2) cudaStreamDestroy(ctx->stream_side2);
+    if (ctx->ev_side2) cudaEventDestroy(ctx->ev_side2);
+    if (ctx->ev_side2_go) cudaEventDestroy(ctx->ev_side2_go);
     delete ctx;
 }
 

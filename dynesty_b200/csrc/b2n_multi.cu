@@ -47,7 +47,7 @@ __global__ void scale_points_kernel(const double* __restrict__ P, int64_t total,
 __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
     kmeans2_kernel(const double* __restrict__ P, const int* __restrict__ perm, NodeArrays na,
                    const NodeRef* __restrict__ refs, const double* __restrict__ scale,
-                   unsigned char* __restrict__ labels, int* __restrict__ counts) {
+                   unsigned char* __restrict__ labels, int* __restrict__ counts, int stage_cap) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ double sm[];
@@ -59,6 +59,10 @@ __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
     double* part = c + 2 * n;              // 2 x n partial sums of this CTA (read by the peers)
     double* acc = part + 2 * n;            // nw x 2 x n
     int* cnt = reinterpret_cast<int*>(acc + (size_t)nw * 2 * n);   // nw x 2
+    // the first `stage_cap` rows of this CTA's share of the node, staged ONCE: the ten Lloyd iterations used to
+    // re-read every row through perm[] from L2 -- two dependent long-latency loads per trip, 15 us per iteration
+    // at 250 rows per CTA; rows beyond the capacity (large nodes) keep coming from L2
+    double* stg = reinterpret_cast<double*>(cnt + (size_t)nw * 2 + ((nw * 2) & 1));
     __shared__ int pcnt[2];                // this CTA's member counts (read by the peers)
     __shared__ int tot[2];
     const int lo = nr.start + (int)((long long)nr.count * rank / KM_CLUSTER);
@@ -69,6 +73,11 @@ __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
         c[i] = (ctr - v) / scale[i];
         c[n + i] = (ctr + v) / scale[i];
     }
+    const int nst = min(hi - lo, stage_cap);
+    for (int r = warp; r < nst; r += nw) {
+        const size_t row = (size_t)perm[lo + r] * n;
+        for (int i = lane; i < n; i += 32) stg[(size_t)r * n + i] = P[row + i];
+    }
     __syncthreads();
     for (int it = 0; it < 10; it++) {
         for (int i = lane; i < 2 * n; i += 32) acc[(size_t)warp * 2 * n + i] = 0.0;
@@ -78,12 +87,13 @@ __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
         for (int r = lo + warp; r < hi; r += 2 * nw) {
             const int r2 = r + nw;
             const bool two = r2 < hi;
-            const size_t row = (size_t)perm[r] * n;
-            const size_t row2 = two ? (size_t)perm[r2] * n : row;
+            // P = points / scale (scaled once per update); a staged row is the same doubles from shared memory
+            const double* p1 = (r - lo < nst) ? stg + (size_t)(r - lo) * n : P + (size_t)perm[r] * n;
+            const double* p2 = !two ? p1 : ((r2 - lo < nst) ? stg + (size_t)(r2 - lo) * n : P + (size_t)perm[r2] * n);
             double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
             for (int i = lane; i < n; i += 32) {
-                const double o = P[row + i];          // P = points / scale (scaled once per update)
-                const double o2 = P[row2 + i];
+                const double o = p1[i];
+                const double o2 = p2[i];
                 const double a = o - c[i], b = o - c[n + i];
                 const double a2 = o2 - c[i], b2 = o2 - c[n + i];
                 d0 = fma(a, a, d0);
@@ -98,11 +108,11 @@ __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
             const int lab = (d1 < d0) ? 1 : 0;
             const int lab2 = (e1 < e0) ? 1 : 0;
             double* dst = acc + (size_t)warp * 2 * n + (size_t)lab * n;
-            for (int i = lane; i < n; i += 32) dst[i] += P[row + i];
+            for (int i = lane; i < n; i += 32) dst[i] += p1[i];
             if (lane == 0) { cnt[warp * 2 + lab]++; labels[r] = (unsigned char)lab; }
             if (two) {
                 double* dst2 = acc + (size_t)warp * 2 * n + (size_t)lab2 * n;
-                for (int i = lane; i < n; i += 32) dst2[i] += P[row2 + i];
+                for (int i = lane; i < n; i += 32) dst2[i] += p2[i];
                 if (lane == 0) { cnt[warp * 2 + lab2]++; labels[r2] = (unsigned char)lab2; }
             }
         }
@@ -242,10 +252,22 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
     refs[0].node = 0; refs[0].start = 0; refs[0].count = count; refs[0].level = 0;
     std::vector<NodeStat> hs;
     B2N_TRY(b2n_process_nodes(w, refs, hs, fast));
-    if (fast && hs[0].suspect) return B2N_RETRY_FULL;
+    if (fast && (hs[0].suspect || hs[0].pad)) return B2N_RETRY_FULL;
     if (hs[0].fallback && warn) *warn |= B2N_WARN_IDENTITY_FALLBACK;
     if (hs[0].error) return fast ? B2N_RETRY_FULL : hs[0].error;
     tree[0].logvol = hs[0].logvol;
+    // the root's full (eigen) fit, speculatively, on the side stream while the tree is expanded (b2n_bounding.cu);
+    // whatever way this function is left, the side stream has drained first
+    struct SpecScope {
+        b2n_ctx* c; SpecRoot sp;
+        explicit SpecScope(b2n_ctx* ctx) : c(ctx) {}
+        ~SpecScope() { b2n_spec_root_wait(c, sp); }
+    } spec(ctx);
+    {
+        const char* senv = getenv("B2N_BOUND_SPEC");
+        if (fast && count >= 4 * n && count == (int)w.N && !(senv && senv[0] == '0'))
+            B2N_TRY(b2n_spec_root_launch(w, count, spec.sp));
+    }
 
     // scale = std of the ROOT points, reused at every depth (:1503-1504, 1548-1549)
     B2N_CUDA(ctx, ctx->work1.ensure((size_t)n * sizeof(double)));
@@ -273,9 +295,13 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
     int nwarps = 16;
     while ((size_t)(4 * n + (size_t)nwarps * 2 * n) * sizeof(double) + nwarps * 2 * sizeof(int) > (size_t)ctx->max_smem_optin && nwarps > 1)
         nwarps >>= 1;
-    const size_t km_smem = (size_t)(4 * n + (size_t)nwarps * 2 * n) * sizeof(double) + nwarps * 2 * sizeof(int);
-    if (km_smem > (size_t)ctx->max_smem_optin) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for k-means kernel");
-    B2N_TRY(b2n_func_smem(ctx, (const void*)(kmeans2_kernel), (size_t)(km_smem)));
+    const size_t km_base = (size_t)(4 * n + (size_t)nwarps * 2 * n) * sizeof(double) + (size_t)(nwarps * 2 + 2) * sizeof(int);
+    if (km_base > (size_t)ctx->max_smem_optin) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for k-means kernel");
+    // rows a CTA may stage in shared memory (its eighth of the largest node of a level), within half an SM's
+    // shared memory so that the chain kernels of other replicas keep their place next to it
+    const size_t km_room = std::min((size_t)ctx->max_smem_optin, (size_t)120 * 1024);
+    int km_stage_max = km_room > km_base ? (int)((km_room - km_base) / ((size_t)n * sizeof(double))) : 0;
+    if (const char* e = getenv("B2N_KM_STAGE")) if (e[0] == '0') km_stage_max = 0;     // A/B switch: every row from L2, as before
 
     while (!frontier.empty()) {
         std::vector<int> split;
@@ -292,8 +318,13 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
         B2N_TRY(b2n_in_host(ctx, ctx->scratch5, srefs.data(), srefs.size() * sizeof(NodeRef), &drefs));
         const int* pin = w.perm + (size_t)cur * w.N;
         int* pout = w.perm + (size_t)(1 - cur) * w.N;
+        int maxcount = 0;
+        for (int id : split) maxcount = std::max(maxcount, tree[id].count);
+        const int stage_cap = std::min(km_stage_max, (maxcount + KM_CLUSTER - 1) / KM_CLUSTER + 1);
+        const size_t km_smem = km_base + (size_t)stage_cap * n * sizeof(double);
+        B2N_TRY(b2n_func_smem(ctx, (const void*)(kmeans2_kernel), km_smem));
         kmeans2_kernel<<<(unsigned)split.size() * KM_CLUSTER, nwarps * 32, km_smem, st>>>(Pscaled, pin, w.na, (const NodeRef*)drefs, scale,
-                                                                           dlab, dcounts);
+                                                                           dlab, dcounts, stage_cap);
         B2N_LAUNCH_CHECK(ctx);
         // carry every segment forward, then overwrite the split ones with their partition
         B2N_CUDA(ctx, cudaMemcpyAsync(pout, pin, (size_t)w.N * sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -327,7 +358,7 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
         if (!crefs.empty()) {
             B2N_TRY(b2n_process_nodes(w, crefs, hs, fast));
             for (size_t i = 0; i < crefs.size(); i++) {
-                if (fast && (hs[i].suspect || hs[i].error)) return B2N_RETRY_FULL;
+                if (fast && (hs[i].suspect || hs[i].pad || hs[i].error)) return B2N_RETRY_FULL;
                 if (hs[i].fallback && warn) *warn |= B2N_WARN_IDENTITY_FALLBACK;
                 if (hs[i].error) return hs[i].error;
                 tree[crefs[i].node].logvol = hs[i].logvol;
@@ -338,7 +369,14 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
     leaves.clear();
     resolve(tree, 0, n, leaves);
     final_level = cur;
-    if (fast) {
+    bool adopted = false;
+    if (fast && leaves.size() == 1 && leaves[0] == 0) {
+        // nothing was split for good: the root's speculative fit is the result
+        NodeStat rs;
+        B2N_TRY(b2n_spec_root_adopt(w, spec.sp, &rs, &adopted));
+        if (adopted) tree[0].logvol = rs.logvol;
+    }
+    if (fast && !adopted) {
         // the accepted leaves get the full fit (eigen-decomposition: axes, axlens, and the reference's exact
         // ladder / rescale); a leaf's points are the segment [start, start+count) of EITHER index buffer as a
         // set (partitions only permute inside segments), so the last buffer serves all of them

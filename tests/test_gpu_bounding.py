@@ -179,6 +179,72 @@ def test_candidate_path_equals_eigen_path(case, monkeypatch):
         assert fast['nells'] == 8
 
 
+def _clouds(case):
+    rng = np.random.default_rng(SEED)
+    if case == 'gauss2000x50':
+        Cm = np.full((50, 50), 0.4)
+        np.fill_diagonal(Cm, 1.0)
+        return 0.5 + 0.02 * rng.standard_normal((2000, 50)) @ np.linalg.cholesky(Cm).T
+    if case == 'clusters4000x25':
+        ctrs = 0.2 + 0.6 * rng.random((8, 25))
+        return np.concatenate([c + 0.01 * rng.standard_normal((500, 25)) for c in ctrs])
+    if case == 'two20000x8':            # 2500 rows per k-means CTA: more than its shared-memory stage holds
+        return np.concatenate([0.3 + 0.02 * rng.standard_normal((12000, 8)), 0.7 + 0.02 * rng.standard_normal((8000, 8))])
+    if case == 'illcond600x12':         # the root's covariance needs the repair ladder: its speculative fit is not adopted
+        p = 0.5 + 0.05 * rng.standard_normal((600, 12))
+        p[:, 11] = p[:, 0] + 1e-9 * rng.standard_normal(600)
+        return p
+    raise KeyError(case)
+
+
+@pytest.mark.parametrize('case', ['gauss2000x50', 'clusters4000x25', 'two20000x8', 'illcond600x12'])
+def test_speculative_root_fit_equals_refit(case, monkeypatch):
+    """b2n_spec_root_*: the root's eigen fit runs on a side stream while the candidate tree is expanded and is
+    adopted when the root is the accepted leaf (B2N_BOUND_SPEC=0: the ordinary re-fit after the tree).  Same
+    kernels on the same rows in a different ORDER (identity against the last permutation): equal to round-off."""
+    pts = _clouds(case)
+    monkeypatch.setenv('B2N_BOUND_FAST', '1')           # attempt the candidate path whatever this context saw before
+    monkeypatch.setenv('B2N_BOUND_SPEC', '0')
+    a = ops.multi_decompose(pts)
+    monkeypatch.setenv('B2N_BOUND_SPEC', '1')
+    b = ops.multi_decompose(pts)
+    b2 = ops.multi_decompose(pts)                       # and reproducible call to call
+    assert a['nells'] == b['nells'] == b2['nells']
+    assert np.array_equal(a['labels'], b['labels'])
+    for k in ('ctrs', 'covs', 'ams', 'axes', 'logvols'):
+        assert np.array_equal(b[k], b2[k]), k
+    close(b['ctrs'], a['ctrs'], rtol=1e-12)
+    close(b['covs'], a['covs'], rtol=1e-9)
+    close(b['logvols'], a['logvols'], rtol=1e-11)
+    close(b['ams'], a['ams'], rtol=1e-6 if case.startswith('illcond') else 1e-8)
+    for k in range(b['nells']):
+        close(b['axes'][k] @ b['axes'][k].T, b['covs'][k], rtol=1e-9)
+    mask = ops.membership(pts, b['ctrs'], b['ams'])[0]
+    assert mask[np.arange(len(pts)), b['labels']].all()
+
+
+@pytest.mark.parametrize('case', ['gauss2000x50', 'clusters4000x25', 'two20000x8'])
+@pytest.mark.parametrize('switch', ['B2N_KM_STAGE', 'B2N_CHOL_SPLIT'])
+def test_update_variants_bit_identical(case, switch, monkeypatch):
+    """Two re-arrangements that must not change a bit: (i) the k-means CTAs stage their rows in shared memory once
+    instead of re-reading them through perm[] in each of the ten Lloyd iterations (two20000x8: only part of a CTA's
+    rows fit); (ii) the two halves of the candidate fit (Cholesky / major axis) as two launches on two streams."""
+    pts = _clouds(case)
+    monkeypatch.setenv('B2N_BOUND_FAST', '1')
+    monkeypatch.setenv('B2N_BOUND_SPEC', '0')
+    monkeypatch.setenv(switch, '0')
+    a = ops.multi_decompose(pts)
+    monkeypatch.setenv(switch, '1')
+    b = ops.multi_decompose(pts)
+    assert a['nells'] == b['nells'] and a['warn'] == b['warn']
+    for k in ('labels', 'ctrs', 'covs', 'ams', 'axes', 'axlens', 'logvols'):
+        assert np.array_equal(a[k], b[k]), k
+    if case == 'clusters4000x25':
+        assert b['nells'] == 8
+    if case == 'two20000x8':
+        assert b['nells'] == 2
+
+
 # ---- improve_covar_mat on its own (b2n_improve_covar): the reference's test matrices (tests/test_ellipsoid.py:242-255)
 @pytest.mark.parametrize('name', ['zero', 'rank1', 'neg', 'good'])
 def test_improve_covar_mat_fixtures(golden, name):
