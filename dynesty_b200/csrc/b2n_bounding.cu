@@ -653,7 +653,7 @@ int b2n_boundwork_init(b2n_ctx* ctx, BoundWork& w, const double* dP, int64_t N, 
 // Full bounding_ellipsoid (bounding.py:1387-1461) for every node in `refs`.
 // On return `stats` holds the per-node NodeStat (host copy); the stream is synchronised.
 int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::vector<NodeStat>& stats,
-                      bool candidate) {
+                      bool candidate, bool defer) {
     b2n_ctx* ctx = w.ctx;
     const int n = w.n;
     const size_t nn = (size_t)n * n;
@@ -789,6 +789,10 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
         if (chol_split) B2N_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_side2, 0));
         scale_finish_kernel<<<pn, 1024, 0, st>>>(w.na, (const NodeRef*)prefs, partial, pass, w.logvol_pref, B2N_FMAX_SUB);
         B2N_LAUNCH_CHECK(ctx);
+        // candidates of a tree being expanded: nothing on the host depends on their stats before the end of the
+        // expansion (a certified candidate never takes the second pass) -- the caller reads them all at once
+        // (b2n_read_stats) and the next level's launches queue behind these without a host round trip
+        if (candidate && defer) return B2N_OK;
         // read back the node stats (one copy of the whole small array)
         B2N_CUDA(ctx, cudaStreamSynchronize(st));
         std::vector<NodeStat> all(w.cap);
@@ -943,6 +947,13 @@ int b2n_spec_root_adopt(BoundWork& w, SpecRoot& sp, NodeStat* stat, bool* ok) {
 void b2n_spec_root_wait(b2n_ctx* ctx, SpecRoot& sp) {
     if (sp.launched && ctx->stream_side) cudaStreamSynchronize(ctx->stream_side);
     sp.launched = false;
+}
+
+// host copy of every node's NodeStat (the stream is synchronised on return)
+int b2n_read_stats(BoundWork& w, std::vector<NodeStat>& all) {
+    all.resize(w.cap);
+    B2N_CUDA(w.ctx, b2n_copy_sync(w.ctx, all.data(), w.na.stat, (size_t)w.cap * sizeof(NodeStat), cudaMemcpyDeviceToHost));
+    return B2N_OK;
 }
 
 // np.mean / np.cov(ddof=1) of one node (rows [0, count) of perm level 0): the moment kernels of b2n_process_nodes

@@ -69,8 +69,10 @@ int b2n_boundwork_init(b2n_ctx* ctx, BoundWork& w, const double* dP, int64_t N, 
 // candidate = false: the full path (eigen-decomposition + repair ladder).  candidate = true: nodes that
 // are only CANDIDATES of the multi-ellipsoid tree (bounding.py:1464-1563 evaluates every candidate but
 // returns few): Cholesky-based precision / log-volume + power-iteration major axis, see chol_node_kernel.
+// defer (candidates only): return after the launches, without the host read-back of the stats -> b2n_read_stats.
 int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs, std::vector<NodeStat>& stats,
-                      bool candidate = false);
+                      bool candidate = false, bool defer = false);
+int b2n_read_stats(BoundWork& w, std::vector<NodeStat>& all);
 // speculative eigen fit of the root node on the context's side stream (b2n_bounding.cu)
 struct JobL {   // MomentJob + perm level
     int node, r0, r1, slot, level, pad0, pad1, pad2;

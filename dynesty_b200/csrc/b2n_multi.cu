@@ -63,6 +63,8 @@ __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
     // re-read every row through perm[] from L2 -- two dependent long-latency loads per trip, 15 us per iteration
     // at 250 rows per CTA; rows beyond the capacity (large nodes) keep coming from L2
     double* stg = reinterpret_cast<double*>(cnt + (size_t)nw * 2 + ((nw * 2) & 1));
+    const int ns = n | 1;                  // odd row stride: a thread per row walks the columns bank-conflict free
+    unsigned char* slab = reinterpret_cast<unsigned char*>(stg + (size_t)stage_cap * ns);   // labels of the staged rows
     __shared__ int pcnt[2];                // this CTA's member counts (read by the peers)
     __shared__ int tot[2];
     const int lo = nr.start + (int)((long long)nr.count * rank / KM_CLUSTER);
@@ -76,9 +78,84 @@ __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
     const int nst = min(hi - lo, stage_cap);
     for (int r = warp; r < nst; r += nw) {
         const size_t row = (size_t)perm[lo + r] * n;
-        for (int i = lane; i < n; i += 32) stg[(size_t)r * n + i] = P[row + i];
+        for (int i = lane; i < n; i += 32) stg[(size_t)r * ns + i] = P[row + i];
     }
     __syncthreads();
+    // Every row of this CTA staged (the usual case): the THREAD-PER-ROW form of the Lloyd iteration.  The
+    // warp-per-row form below spends ~400 instructions per pair of rows, most of them shuffles and addressing, and
+    // is issue bound (ncu: 4.1e6 warp instructions per launch at 2000 x 50, 43 % of the issue slots with 4 warps
+    // per scheduler).  Here two adjacent lanes own a row (half of the columns each, one shuffle to combine), the
+    // distances are sequential sums with no reduction tree, and the centroid sums are formed by (chunk, cluster,
+    // column) threads walking the staged rows -- ~20 x fewer instructions per iteration.  Same barriers, same
+    // DSMEM exchange, same scipy semantics as below; all sums in a fixed order.
+    if (nst == hi - lo) {
+        const int rows = nst, T = blockDim.x, tid = threadIdx.x;
+        const int nh = (n + 1) >> 1;
+        const int CH = max(1, min(nw, T / (2 * n)));            // row chunks of the centroid pass (acc holds nw x 2n)
+        for (int it = 0; it < 10; it++) {
+            for (int base = 0; base < rows; base += T >> 1) {
+                const int r = base + (tid >> 1), h = tid & 1;
+                const bool valid = r < rows;
+                double d0 = 0.0, d1 = 0.0;
+                if (valid) {
+                    const double* pr = stg + (size_t)r * ns;
+                    const int i1 = min(n, (h + 1) * nh);
+                    for (int i = h * nh; i < i1; i++) {
+                        const double o = pr[i];
+                        const double a = o - c[i], b = o - c[n + i];
+                        d0 = fma(a, a, d0);
+                        d1 = fma(b, b, d1);
+                    }
+                }
+                const double q0 = __shfl_xor_sync(B2N_FULL, d0, 1), q1 = __shfl_xor_sync(B2N_FULL, d1, 1);
+                if (valid && h == 0) {
+                    const int lab = ((d1 + q1) < (d0 + q0)) ? 1 : 0;       // lower half + upper half, ties -> cluster 0
+                    slab[r] = (unsigned char)lab;
+                    labels[lo + r] = (unsigned char)lab;
+                }
+            }
+            __syncthreads();
+            for (int e = tid; e < CH * 2 * n; e += T) {
+                const int ch = e / (2 * n), f = e - ch * 2 * n, k = f / n, i = f - k * n;
+                const int r0 = (int)((long long)rows * ch / CH), r1 = (int)((long long)rows * (ch + 1) / CH);
+                double sacc = 0.0;
+                int m = 0;
+                for (int r = r0; r < r1; r++)
+                    if (slab[r] == k) { sacc += stg[(size_t)r * ns + i]; m++; }
+                acc[(size_t)ch * 2 * n + f] = sacc;
+                if (i == 0) cnt[ch * 2 + k] = m;
+            }
+            __syncthreads();
+            for (int e = tid; e < 2 * n; e += T) {
+                double t = 0.0;
+                for (int ch = 0; ch < CH; ch++) t += acc[(size_t)ch * 2 * n + e];
+                part[e] = t;
+            }
+            if (tid < 2) {
+                int t = 0;
+                for (int ch = 0; ch < CH; ch++) t += cnt[ch * 2 + tid];
+                pcnt[tid] = t;
+            }
+            cluster.sync();
+            if (tid < 2) {
+                int t = 0;
+                for (int rk = 0; rk < KM_CLUSTER; rk++) t += *cluster.map_shared_rank(&pcnt[tid], rk);
+                tot[tid] = t;
+            }
+            __syncthreads();
+            for (int e = tid; e < 2 * n; e += T) {
+                const int cl = e / n;
+                if (tot[cl] > 0) {
+                    double t = 0.0;
+                    for (int rk = 0; rk < KM_CLUSTER; rk++) t += cluster.map_shared_rank(part, rk)[e];
+                    c[e] = t / (double)tot[cl];
+                }
+            }
+            cluster.sync();
+        }
+        if (rank == 0 && tid < 2) counts[nodei * 2 + tid] = tot[tid];
+        return;
+    }
     for (int it = 0; it < 10; it++) {
         for (int i = lane; i < 2 * n; i += 32) acc[(size_t)warp * 2 * n + i] = 0.0;
         if (lane < 2) cnt[warp * 2 + lane] = 0;
@@ -88,8 +165,8 @@ __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
             const int r2 = r + nw;
             const bool two = r2 < hi;
             // P = points / scale (scaled once per update); a staged row is the same doubles from shared memory
-            const double* p1 = (r - lo < nst) ? stg + (size_t)(r - lo) * n : P + (size_t)perm[r] * n;
-            const double* p2 = !two ? p1 : ((r2 - lo < nst) ? stg + (size_t)(r2 - lo) * n : P + (size_t)perm[r2] * n);
+            const double* p1 = (r - lo < nst) ? stg + (size_t)(r - lo) * ns : P + (size_t)perm[r] * n;
+            const double* p2 = !two ? p1 : ((r2 - lo < nst) ? stg + (size_t)(r2 - lo) * ns : P + (size_t)perm[r2] * n);
             double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
             for (int i = lane; i < n; i += 32) {
                 const double o = p1[i];
@@ -251,11 +328,18 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
     memset(&refs[0], 0, sizeof(NodeRef));
     refs[0].node = 0; refs[0].start = 0; refs[0].count = count; refs[0].level = 0;
     std::vector<NodeStat> hs;
-    B2N_TRY(b2n_process_nodes(w, refs, hs, fast));
-    if (fast && (hs[0].suspect || hs[0].pad)) return B2N_RETRY_FULL;
-    if (hs[0].fallback && warn) *warn |= B2N_WARN_IDENTITY_FALLBACK;
-    if (hs[0].error) return fast ? B2N_RETRY_FULL : hs[0].error;
-    tree[0].logvol = hs[0].logvol;
+    // fast: the candidates' stats are read ONCE, after the expansion (nothing on the host needs them earlier:
+    // the k-means start centres, the partitions and the children's fits read the node arrays on the device) --
+    // a level's launches queue behind the previous level's without a host round trip
+    const char* denv = getenv("B2N_BOUND_DEFER");
+    const bool defer = fast && !(denv && denv[0] == '0');
+    B2N_TRY(b2n_process_nodes(w, refs, hs, fast, defer));
+    if (!defer) {
+        if (fast && (hs[0].suspect || hs[0].pad)) return B2N_RETRY_FULL;
+        if (hs[0].fallback && warn) *warn |= B2N_WARN_IDENTITY_FALLBACK;
+        if (hs[0].error) return fast ? B2N_RETRY_FULL : hs[0].error;
+        tree[0].logvol = hs[0].logvol;
+    }
     // the root's full (eigen) fit, speculatively, on the side stream while the tree is expanded (b2n_bounding.cu);
     // whatever way this function is left, the side stream has drained first
     struct SpecScope {
@@ -300,7 +384,7 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
     // rows a CTA may stage in shared memory (its eighth of the largest node of a level), within half an SM's
     // shared memory so that the chain kernels of other replicas keep their place next to it
     const size_t km_room = std::min((size_t)ctx->max_smem_optin, (size_t)120 * 1024);
-    int km_stage_max = km_room > km_base ? (int)((km_room - km_base) / ((size_t)n * sizeof(double))) : 0;
+    int km_stage_max = km_room > km_base ? (int)((km_room - km_base) / ((size_t)(n | 1) * sizeof(double) + 1)) : 0;
     if (const char* e = getenv("B2N_KM_STAGE")) if (e[0] == '0') km_stage_max = 0;     // A/B switch: every row from L2, as before
 
     while (!frontier.empty()) {
@@ -321,7 +405,7 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
         int maxcount = 0;
         for (int id : split) maxcount = std::max(maxcount, tree[id].count);
         const int stage_cap = std::min(km_stage_max, (maxcount + KM_CLUSTER - 1) / KM_CLUSTER + 1);
-        const size_t km_smem = km_base + (size_t)stage_cap * n * sizeof(double);
+        const size_t km_smem = km_base + (size_t)stage_cap * (n | 1) * sizeof(double) + (((size_t)stage_cap + 15) & ~(size_t)15);
         B2N_TRY(b2n_func_smem(ctx, (const void*)(kmeans2_kernel), km_smem));
         kmeans2_kernel<<<(unsigned)split.size() * KM_CLUSTER, nwarps * 32, km_smem, st>>>(Pscaled, pin, w.na, (const NodeRef*)drefs, scale,
                                                                            dlab, dcounts, stage_cap);
@@ -356,8 +440,8 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
             }
         }
         if (!crefs.empty()) {
-            B2N_TRY(b2n_process_nodes(w, crefs, hs, fast));
-            for (size_t i = 0; i < crefs.size(); i++) {
+            B2N_TRY(b2n_process_nodes(w, crefs, hs, fast, defer));
+            for (size_t i = 0; !defer && i < crefs.size(); i++) {
                 if (fast && (hs[i].suspect || hs[i].pad || hs[i].error)) return B2N_RETRY_FULL;
                 if (hs[i].fallback && warn) *warn |= B2N_WARN_IDENTITY_FALLBACK;
                 if (hs[i].error) return hs[i].error;
@@ -365,6 +449,14 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
             }
         }
         frontier = next;
+    }
+    if (defer) {
+        std::vector<NodeStat> all;
+        B2N_TRY(b2n_read_stats(w, all));
+        for (size_t id = 0; id < tree.size(); id++) {
+            if (all[id].suspect || all[id].pad || all[id].error) return B2N_RETRY_FULL;
+            tree[id].logvol = all[id].logvol;
+        }
     }
     leaves.clear();
     resolve(tree, 0, n, leaves);

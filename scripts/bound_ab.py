@@ -1,5 +1,6 @@
 """A/B timing of the multi-ellipsoid bound update (GPU box): speculative root fit (B2N_BOUND_SPEC), k-means rows staged
-in shared memory (B2N_KM_STAGE), the candidate fit as two stream-parallel halves (B2N_CHOL_SPLIT).
+in shared memory + thread-per-row iteration (B2N_KM_STAGE), the candidate fit as two stream-parallel halves
+(B2N_CHOL_SPLIT), candidates' stats read once per update (B2N_BOUND_DEFER).
 usage: python scripts/bound_ab.py > gpurun_out/bound_ab.jsonl"""
 import json
 import math
@@ -39,11 +40,10 @@ def timed(fn, reps):
 
 def main():
     ctx = _lib.default_context()
-    combos = [('all off', dict(B2N_BOUND_SPEC='0', B2N_KM_STAGE='0', B2N_CHOL_SPLIT='0')),
-              ('spec', dict(B2N_BOUND_SPEC='1', B2N_KM_STAGE='0', B2N_CHOL_SPLIT='0')),
-              ('km stage', dict(B2N_BOUND_SPEC='0', B2N_KM_STAGE='1', B2N_CHOL_SPLIT='0')),
-              ('chol split', dict(B2N_BOUND_SPEC='0', B2N_KM_STAGE='0', B2N_CHOL_SPLIT='1')),
-              ('all on', dict(B2N_BOUND_SPEC='1', B2N_KM_STAGE='1', B2N_CHOL_SPLIT='1'))]
+    off = dict(B2N_BOUND_SPEC='0', B2N_KM_STAGE='0', B2N_CHOL_SPLIT='0', B2N_BOUND_DEFER='0')
+    combos = [('all off', off), ('spec', dict(off, B2N_BOUND_SPEC='1')), ('km stage', dict(off, B2N_KM_STAGE='1')),
+              ('chol split', dict(off, B2N_CHOL_SPLIT='1')), ('defer', dict(off, B2N_BOUND_DEFER='1')),
+              ('all on', {k: '1' for k in off})]
     for tag, pts in clouds():
         N, n = pts.shape
         d = torch.from_numpy(pts).cuda()

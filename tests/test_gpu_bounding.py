@@ -224,11 +224,13 @@ def test_speculative_root_fit_equals_refit(case, monkeypatch):
 
 
 @pytest.mark.parametrize('case', ['gauss2000x50', 'clusters4000x25', 'two20000x8'])
-@pytest.mark.parametrize('switch', ['B2N_KM_STAGE', 'B2N_CHOL_SPLIT'])
-def test_update_variants_bit_identical(case, switch, monkeypatch):
-    """Two re-arrangements that must not change a bit: (i) the k-means CTAs stage their rows in shared memory once
-    instead of re-reading them through perm[] in each of the ten Lloyd iterations (two20000x8: only part of a CTA's
-    rows fit); (ii) the two halves of the candidate fit (Cholesky / major axis) as two launches on two streams."""
+@pytest.mark.parametrize('switch', ['B2N_KM_STAGE', 'B2N_CHOL_SPLIT', 'B2N_BOUND_DEFER'])
+def test_update_variants_equal(case, switch, monkeypatch):
+    """Re-arrangements of the update.  Bit for bit: (i) B2N_CHOL_SPLIT, the two halves of the candidate fit (Cholesky /
+    major axis) as two launches on two streams; (ii) B2N_BOUND_DEFER, the candidates' stats read back once after the
+    expansion instead of once per level.  Same splits, sums in another order: (iii) B2N_KM_STAGE, the k-means CTAs
+    stage their rows in shared memory and run the thread-per-row Lloyd iteration (0: warp per row from L2;
+    two20000x8: the root's CTAs hold 2500 rows each, more than the stage takes, deeper nodes fit)."""
     pts = _clouds(case)
     monkeypatch.setenv('B2N_BOUND_FAST', '1')
     monkeypatch.setenv('B2N_BOUND_SPEC', '0')
@@ -237,12 +239,19 @@ def test_update_variants_bit_identical(case, switch, monkeypatch):
     monkeypatch.setenv(switch, '1')
     b = ops.multi_decompose(pts)
     assert a['nells'] == b['nells'] and a['warn'] == b['warn']
-    for k in ('labels', 'ctrs', 'covs', 'ams', 'axes', 'axlens', 'logvols'):
-        assert np.array_equal(a[k], b[k]), k
+    if switch == 'B2N_KM_STAGE':
+        # leaves come out in tree order; a centroid that differs in its last bits may flip a point exactly on a
+        # bisecting plane, nothing else
+        assert np.mean(a['labels'] != b['labels']) < 1e-3
+        close(b['ctrs'], a['ctrs'], rtol=1e-3 if np.any(a['labels'] != b['labels']) else 1e-12)
+        close(b['logvols'], a['logvols'], rtol=1e-2 if np.any(a['labels'] != b['labels']) else 1e-11)
+    else:
+        for k in ('labels', 'ctrs', 'covs', 'ams', 'axes', 'axlens', 'logvols'):
+            assert np.array_equal(a[k], b[k]), k
     if case == 'clusters4000x25':
         assert b['nells'] == 8
-    if case == 'two20000x8':
-        assert b['nells'] == 2
+    mask = ops.membership(pts, b['ctrs'], b['ams'])[0]
+    assert mask[np.arange(len(pts)), b['labels']].all()
 
 
 # ---- improve_covar_mat on its own (b2n_improve_covar): the reference's test matrices (tests/test_ellipsoid.py:242-255)
