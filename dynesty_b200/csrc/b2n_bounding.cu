@@ -251,11 +251,12 @@ __global__ void __launch_bounds__(1024) eig_ladder_kernel(NodeArrays na, const i
 // log-volume, (ii) its precision matrix (for the fmax rescale, :1438-1450) and (iii) its major axis
 // (k-means start centres, :278-284, 1500-1501); none of that needs the full eigen-decomposition, which
 // is the latency-bound part of a bound update (0.66 ms per tree level at n = 50).  For a candidate:
-//   Cholesky cov = L L^T  ->  ln det = 2 sum ln L_ii, am = L^-T L^-1;
+//   symmetric sweeps of cov (the Cholesky pivots d_k = L_kk^2 without the factor)  ->  ln det = sum ln d_k,
+//   am = -(swept matrix);
 //   improve_covar_mat's test (all eigenvalues finite, max > 0, min >= max/1e12, :1343-1352) is certified
 //   by cond_2 <= |cov|_inf |am|_inf < 1e10 (a sufficient condition: then the ladder is a no-op);
 //   major axis by power iteration to 1e-13, written as the LAST column of `axes` (largest eigenvalue).
-// The pivots L_ii^2 are stored where the eigenvalues go (`lam`): scale_finish_kernel's sum of logs is then
+// The pivots d_k are stored where the eigenvalues go (`lam`): scale_finish_kernel's sum of logs is then
 // ln det, and its rescale / singularity test apply unchanged.  A node that cannot be certified (Cholesky
 // break-down, condition bound, slow power iteration: near-degenerate leading eigenvalues) is flagged
 // `suspect` and the caller redoes the whole update with the eigen path.  Accepted leaves are always
@@ -270,9 +271,9 @@ __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int
     const int n = na.n, ld = na.ld, tid = threadIdx.x, T = blockDim.x;
     const int node = nodelist[blockIdx.x];
     const size_t nn = (size_t)n * n;
-    double* L = sm;                          // n x ld: lower triangle = Cholesky factor (diag kept apart)
-    double* Li = L + (size_t)n * ld;         // n x ld: L^-1 (lower)
-    double* dg = Li + (size_t)n * ld;        // n: pivots L_ii
+    double* L = sm;                          // n x ld: the matrix being swept (-> -cov^-1); then squaring workspace
+    double* Li = L + (size_t)n * ld;         // n x ld: squaring workspace
+    double* dg = Li + (size_t)n * ld;        // n: pivots d_k = L_kk^2 of the sweeps
     double* v = dg + n;                      // n: power-iteration vector
     double* y = v + n;                       // n
     double* red = y + n;                     // 32
@@ -303,26 +304,39 @@ __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int
     __syncthreads();
     for (int w = 0; w < ((T + 31) >> 5); w++) cnorm = fmax(cnorm, red[w]);
     __syncthreads();
-    // ---- right-looking Cholesky, two barriers per column
-    for (int k = 0; k < n; k++) {
-        const double d = L[(size_t)k * ld + k];
-        if (!(d > 0.0) || !(d < INFINITY)) {       // same value for every thread: uniform exit
-            if (tid == 0) s_bad = 1;
-            break;
-        }
-        const double r = rsqrt(d);
-        if (tid == 0) dg[k] = d * r;               // sqrt(d)
-        for (int i = k + 1 + tid; i < n; i += T) L[(size_t)i * ld + k] *= r;
-        __syncthreads();
-        const int m = n - k - 1;                   // trailing (lower incl. diagonal) update
-        for (int e = tid; e < m * m; e += T) {
-            const int a = e / m, b = e - a * m;
-            if (b <= a) {
-                const int i = k + 1 + a, j = k + 1 + b;
-                L[(size_t)i * ld + j] = fma(-L[(size_t)i * ld + k], L[(size_t)j * ld + k], L[(size_t)i * ld + j]);
+    // ---- precision matrix and pivots by the symmetric SWEEP operator: sweeping pivot k of an SPD matrix,
+    //        A_ij -= A_ik A_kj / d  (i, j != k),   A_ik = A_ki = A_ik / d,   A_kk = -1 / d,   d = A_kk,
+    // leaves the Schur complement of the swept block in the rest (d is the k-th Cholesky pivot L_kk^2: same
+    // positivity test, same ln det = sum ln d), and after all n sweeps A = -cov^-1.  Every sweep is one full-matrix
+    // rank-1 update -- n^2 / T elements per thread, two barriers -- instead of Cholesky + a forward substitution of
+    // one column per thread + a triangular product (80 us at n = 50, most of it in ~50 busy threads); warp w owns
+    // rows w, w + nw, ..., its lanes the columns: no integer division.  (i, j) and (j, i) see the same operands in
+    // the same order, so the matrix stays symmetric to the bit.
+    {
+        const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+        for (int k = 0; k < n; k++) {
+            const double d = L[(size_t)k * ld + k];
+            if (!(d > 0.0) || !(d < INFINITY)) {       // same value for every thread: uniform exit
+                if (tid == 0) s_bad = 1;
+                break;
             }
+            if (tid == 0) dg[k] = d;
+            for (int i = tid; i < n; i += T) y[i] = L[(size_t)i * ld + k];
+            __syncthreads();
+            const double rinv = 1.0 / d;
+            for (int i = warp; i < n; i += nw) {
+                const double yi = y[i];
+                double* Lr = L + (size_t)i * ld;
+                for (int j = lane; j < n; j += 32) {
+                    double v;
+                    if (i == k) v = (j == k) ? -rinv : y[j] * rinv;
+                    else if (j == k) v = yi * rinv;
+                    else v = fma(-(yi * y[j]), rinv, Lr[j]);
+                    Lr[j] = v;
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
     __syncthreads();
     if (s_bad) {
@@ -333,30 +347,11 @@ __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int
         for (int k = tid; k < n; k += T) na.lam[(size_t)node * n + k] = 1.0;
         return;
     }
-    // ---- L^-1 by forward substitution, one column per thread
-    for (int j = tid; j < n; j += T) {
-        for (int i = 0; i < j; i++) Li[(size_t)i * ld + j] = 0.0;
-        Li[(size_t)j * ld + j] = 1.0 / dg[j];
-        for (int i = j + 1; i < n; i++) {
-            double a0 = 0.0, a1 = 0.0;
-            int m = j;
-            for (; m + 1 < i; m += 2) {
-                a0 = fma(L[(size_t)i * ld + m], Li[(size_t)m * ld + j], a0);
-                a1 = fma(L[(size_t)i * ld + m + 1], Li[(size_t)(m + 1) * ld + j], a1);
-            }
-            if (m < i) a0 = fma(L[(size_t)i * ld + m], Li[(size_t)m * ld + j], a0);
-            Li[(size_t)i * ld + j] = -(a0 + a1) / dg[i];
-        }
-    }
-    __syncthreads();
-    // ---- am = L^-T L^-1 (symmetric), |am|_inf
+    // ---- am = -(swept matrix), |am|_inf
     double* AM = na.am + (size_t)node * nn;
     for (size_t e = tid; e < nn; e += T) {
         const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
-        const int m0 = i > j ? i : j;
-        double a = 0.0;
-        for (int m = m0; m < n; m++) a = fma(Li[(size_t)m * ld + i], Li[(size_t)m * ld + j], a);
-        AM[e] = a;
+        AM[e] = -L[(size_t)i * ld + j];
     }
     __syncthreads();
     rs = 0.0;
@@ -370,7 +365,7 @@ __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int
     __syncthreads();
     for (int w = 0; w < ((T + 31) >> 5); w++) anorm = fmax(anorm, red[w]);
     __syncthreads();
-    for (int k = tid; k < n; k += T) na.lam[(size_t)node * n + k] = dg[k] * dg[k];
+    for (int k = tid; k < n; k += T) na.lam[(size_t)node * n + k] = dg[k];
     if (PART == 1) {
         if (tid == 0) { st->suspect = (cnorm * anorm < 1e10) ? 0 : 1; st->good = 1; st->fallback = 0; st->retry = 0; }
         return;
@@ -662,10 +657,10 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
     int slot = 0;
     for (auto& r : refs) {
         r.slot0 = slot;
-        for (int a = r.start; a < r.start + r.count; a += B2N_ROWS_PER_JOB) {
+        for (int a = r.start; a < r.start + r.count; a += b2n_rows_per_job(w.N)) {
             JobL j;
             memset(&j, 0, sizeof(j));
-            j.node = r.node; j.r0 = a; j.r1 = std::min(a + B2N_ROWS_PER_JOB, r.start + r.count);
+            j.node = r.node; j.r0 = a; j.r1 = std::min(a + b2n_rows_per_job(w.N), r.start + r.count);
             j.slot = slot++; j.level = r.level;
             jobs.push_back(j);
         }
@@ -729,10 +724,10 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
                 if (hs[i].good || hs[i].error) continue;
                 NodeRef r = refs[i];
                 r.slot0 = s2;
-                for (int a = r.start; a < r.start + r.count; a += B2N_ROWS_PER_JOB) {
+                for (int a = r.start; a < r.start + r.count; a += b2n_rows_per_job(w.N)) {
                     JobL j;
                     memset(&j, 0, sizeof(j));
-                    j.node = r.node; j.r0 = a; j.r1 = std::min(a + B2N_ROWS_PER_JOB, r.start + r.count);
+                    j.node = r.node; j.r0 = a; j.r1 = std::min(a + b2n_rows_per_job(w.N), r.start + r.count);
                     j.slot = s2++; j.level = r.level;
                     jobs2.push_back(j);
                 }
@@ -812,10 +807,10 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
                 if (!hs[i].retry) continue;
                 NodeRef r = refs[i];
                 r.slot0 = s3;
-                for (int a = r.start; a < r.start + r.count; a += B2N_ROWS_PER_JOB) {
+                for (int a = r.start; a < r.start + r.count; a += b2n_rows_per_job(w.N)) {
                     JobL j;
                     memset(&j, 0, sizeof(j));
-                    j.node = r.node; j.r0 = a; j.r1 = std::min(a + B2N_ROWS_PER_JOB, r.start + r.count);
+                    j.node = r.node; j.r0 = a; j.r1 = std::min(a + b2n_rows_per_job(w.N), r.start + r.count);
                     j.slot = s3++; j.level = r.level;
                     jobs3.push_back(j);
                 }
@@ -872,10 +867,10 @@ int b2n_spec_root_launch(BoundWork& w, int count, SpecRoot& sp) {
     }
     cudaStream_t side = ctx->stream_side;
     sp.jobs.clear();
-    for (int a = 0; a < count; a += B2N_ROWS_PER_JOB) {
+    for (int a = 0; a < count; a += b2n_rows_per_job(w.N)) {
         JobL j;
         memset(&j, 0, sizeof(j));
-        j.node = 0; j.r0 = a; j.r1 = std::min(a + B2N_ROWS_PER_JOB, count); j.slot = (int)sp.jobs.size(); j.level = 0;
+        j.node = 0; j.r0 = a; j.r1 = std::min(a + b2n_rows_per_job(w.N), count); j.slot = (int)sp.jobs.size(); j.level = 0;
         sp.jobs.push_back(j);
     }
     const int njobs = (int)sp.jobs.size();
@@ -966,10 +961,10 @@ int b2n_node_moments(BoundWork& w, int count) {
     memset(&ref, 0, sizeof(ref));
     ref.node = 0; ref.start = 0; ref.count = count; ref.level = 0; ref.slot0 = 0;
     std::vector<JobL> jobs;
-    for (int a = 0; a < count; a += B2N_ROWS_PER_JOB) {
+    for (int a = 0; a < count; a += b2n_rows_per_job(w.N)) {
         JobL j;
         memset(&j, 0, sizeof(j));
-        j.node = 0; j.r0 = a; j.r1 = std::min(a + B2N_ROWS_PER_JOB, count); j.slot = (int)jobs.size(); j.level = 0;
+        j.node = 0; j.r0 = a; j.r1 = std::min(a + b2n_rows_per_job(w.N), count); j.slot = (int)jobs.size(); j.level = 0;
         jobs.push_back(j);
     }
     ref.nslots = (int)jobs.size();
