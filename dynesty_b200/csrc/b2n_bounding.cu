@@ -244,6 +244,103 @@ __global__ void __launch_bounds__(1024) eig_ladder_kernel(NodeArrays na, const i
     }
 }
 
+// ------------------------------------------------------------------ symmetric sweeps in registers
+// cov^-1 and the Cholesky pivots of an n x n SPD matrix by n symmetric SWEEPS: sweeping pivot k,
+//     A_ij -= A_ik A_kj / d  (i, j != k),   A_ik = A_ki = A_ik / d,   A_kk = -1 / d,   d = A_kk,
+// leaves the Schur complement of the swept block in the rest (d is the k-th Cholesky pivot L_kk^2: same positivity
+// test, ln det = sum ln d) and after n sweeps A = -cov^-1.  The matrix lives in REGISTERS for all n sweeps: 512
+// threads, warp w owns rows w, w + 16, ... (R of them), lane l the columns l, l + 32, ... (C of them).  A sweep
+// needs only the pivot column -- published to shared memory by its owners (double buffered) -- so it costs ONE
+// barrier, no matrix traffic, no integer division.  (i, j) and (j, i) see the same operands in the same order: the
+// matrix stays symmetric to the bit.  Also returns |cov|_inf and |cov^-1|_inf (row sums = warp reductions).
+template <int R, int C>
+static __device__ __forceinline__ bool sweep_inverse_regs(const double* __restrict__ src, double* __restrict__ Cm,
+                                                          double* __restrict__ AM, int n, double* ybuf, double* dg,
+                                                          double* red, int* s_bad, double& cnorm, double& anorm) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;        // blockDim.x == 512
+    const int npad = (n + 1) & ~1;
+    double v[R][C];
+#pragma unroll
+    for (int a = 0; a < R; a++)
+#pragma unroll
+        for (int b = 0; b < C; b++) {
+            const int i = w + 16 * a, j = lane + 32 * b;
+            double c = 0.0;
+            if (i < n && j < n) { c = src[(size_t)i * n + j]; Cm[(size_t)i * n + j] = c; }
+            v[a][b] = c;
+        }
+    double rmax = 0.0;
+#pragma unroll
+    for (int a = 0; a < R; a++) {
+        double t = 0.0;
+#pragma unroll
+        for (int b = 0; b < C; b++) t += fabs(v[a][b]);
+        rmax = fmax(rmax, warp_sum(t));
+    }
+    if (lane == 0) red[w] = rmax;
+    if (lane == 0) {                                   // column 0
+#pragma unroll
+        for (int a = 0; a < R; a++) if (w + 16 * a < n) ybuf[w + 16 * a] = v[a][0];
+    }
+    __syncthreads();
+    cnorm = 0.0;
+    for (int q = 0; q < 16; q++) cnorm = fmax(cnorm, red[q]);
+    for (int k = 0; k < n; k++) {
+        const double* cur = ybuf + (k & 1) * npad;
+        double* nxt = ybuf + ((k + 1) & 1) * npad;
+        const double d = cur[k];
+        if (!(d > 0.0) || !(d < INFINITY)) {           // the same value in every thread: uniform exit
+            if (tid == 0) *s_bad = 1;
+            break;
+        }
+        if (tid == 0) dg[k] = d;
+        const double rinv = 1.0 / d;
+        double yj[C];
+#pragma unroll
+        for (int b = 0; b < C; b++) yj[b] = (lane + 32 * b < n) ? cur[lane + 32 * b] : 0.0;
+        const int bsel = (k + 1) >> 5;
+        const bool pub = (k + 1 < n) && (lane == ((k + 1) & 31));
+#pragma unroll
+        for (int a = 0; a < R; a++) {
+            const int i = w + 16 * a;
+            if (i < n) {
+                const double yi = cur[i];
+#pragma unroll
+                for (int b = 0; b < C; b++) {
+                    const int j = lane + 32 * b;
+                    double x;
+                    if (i == k) x = (j == k) ? -rinv : yj[b] * rinv;
+                    else if (j == k) x = yi * rinv;
+                    else x = fma(-(yi * yj[b]), rinv, v[a][b]);
+                    v[a][b] = x;
+                    if (pub && b == bsel) nxt[i] = x;          // column k + 1 as the next sweep needs it
+                }
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (*s_bad) return false;
+    rmax = 0.0;
+#pragma unroll
+    for (int a = 0; a < R; a++) {
+        double t = 0.0;
+#pragma unroll
+        for (int b = 0; b < C; b++) {
+            const int i = w + 16 * a, j = lane + 32 * b;
+            if (i < n && j < n) AM[(size_t)i * n + j] = -v[a][b]; else v[a][b] = 0.0;
+            t += fabs(v[a][b]);
+        }
+        rmax = fmax(rmax, warp_sum(t));
+    }
+    if (lane == 0) red[w] = rmax;
+    __syncthreads();
+    anorm = 0.0;
+    for (int q = 0; q < 16; q++) anorm = fmax(anorm, red[q]);
+    __syncthreads();
+    return true;
+}
+
 // ------------------------------------------------------------------ candidate nodes: Cholesky path
 // _bounding_ellipsoids (bounding.py:1464-1563) fits an ellipsoid to EVERY node of the candidate tree --
 // it always recurses into both children before its two volume tests -- but returns only the accepted
@@ -277,6 +374,7 @@ __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int
     double* v = dg + n;                      // n: power-iteration vector
     double* y = v + n;                       // n
     double* red = y + n;                     // 32
+    double* ybuf = red + 32;                 // 2 x (n + 2): pivot columns of the sweeps (double buffered)
     __shared__ int s_bad, s_it;
     __shared__ double s_lam, s_diff;
     const double* src = na.covraw + (size_t)node * nn;
@@ -285,61 +383,13 @@ __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int
     if (tid == 0) { s_bad = 0; s_it = 0; }
     double cnorm = 0.0, anorm = 0.0;
     if (PART != 2) {
-    for (size_t e = tid; e < nn; e += T) {
-        const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
-        const double c = src[e];
-        Cm[e] = c;
-        L[(size_t)i * ld + j] = c;
-    }
+    // ---- precision matrix, pivots, |cov|_inf |am|_inf: symmetric sweeps on a register-resident matrix
+    //      (sweep_inverse_regs above)
+    double* AM = na.am + (size_t)node * nn;
     __syncthreads();
-    // ---- |cov|_inf
-    double rs = 0.0;
-    for (int i = tid; i < n; i += T) {
-        double a = 0.0;
-        for (int j = 0; j < n; j++) a += fabs(L[(size_t)i * ld + j]);
-        rs = fmax(rs, a);
-    }
-    rs = warp_max(rs);
-    if ((tid & 31) == 0) red[tid >> 5] = rs;
-    __syncthreads();
-    for (int w = 0; w < ((T + 31) >> 5); w++) cnorm = fmax(cnorm, red[w]);
-    __syncthreads();
-    // ---- precision matrix and pivots by the symmetric SWEEP operator: sweeping pivot k of an SPD matrix,
-    //        A_ij -= A_ik A_kj / d  (i, j != k),   A_ik = A_ki = A_ik / d,   A_kk = -1 / d,   d = A_kk,
-    // leaves the Schur complement of the swept block in the rest (d is the k-th Cholesky pivot L_kk^2: same
-    // positivity test, same ln det = sum ln d), and after all n sweeps A = -cov^-1.  Every sweep is one full-matrix
-    // rank-1 update -- n^2 / T elements per thread, two barriers -- instead of Cholesky + a forward substitution of
-    // one column per thread + a triangular product (80 us at n = 50, most of it in ~50 busy threads); warp w owns
-    // rows w, w + nw, ..., its lanes the columns: no integer division.  (i, j) and (j, i) see the same operands in
-    // the same order, so the matrix stays symmetric to the bit.
-    {
-        const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
-        for (int k = 0; k < n; k++) {
-            const double d = L[(size_t)k * ld + k];
-            if (!(d > 0.0) || !(d < INFINITY)) {       // same value for every thread: uniform exit
-                if (tid == 0) s_bad = 1;
-                break;
-            }
-            if (tid == 0) dg[k] = d;
-            for (int i = tid; i < n; i += T) y[i] = L[(size_t)i * ld + k];
-            __syncthreads();
-            const double rinv = 1.0 / d;
-            for (int i = warp; i < n; i += nw) {
-                const double yi = y[i];
-                double* Lr = L + (size_t)i * ld;
-                for (int j = lane; j < n; j += 32) {
-                    double v;
-                    if (i == k) v = (j == k) ? -rinv : y[j] * rinv;
-                    else if (j == k) v = yi * rinv;
-                    else v = fma(-(yi * y[j]), rinv, Lr[j]);
-                    Lr[j] = v;
-                }
-            }
-            __syncthreads();
-        }
-    }
-    __syncthreads();
-    if (s_bad) {
+    const bool okA = (n <= 64) ? sweep_inverse_regs<4, 2>(src, Cm, AM, n, ybuf, dg, red, &s_bad, cnorm, anorm)
+                               : sweep_inverse_regs<8, 4>(src, Cm, AM, n, ybuf, dg, red, &s_bad, cnorm, anorm);
+    if (!okA) {
         if (tid == 0) {
             st->suspect = 1; st->good = 1; st->fallback = 0; st->retry = 0;
             if (PART == 0) { st->sweeps = 0; st->pad = 0; }
@@ -347,24 +397,6 @@ __global__ void __launch_bounds__(512) chol_node_kernel(NodeArrays na, const int
         for (int k = tid; k < n; k += T) na.lam[(size_t)node * n + k] = 1.0;
         return;
     }
-    // ---- am = -(swept matrix), |am|_inf
-    double* AM = na.am + (size_t)node * nn;
-    for (size_t e = tid; e < nn; e += T) {
-        const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
-        AM[e] = -L[(size_t)i * ld + j];
-    }
-    __syncthreads();
-    rs = 0.0;
-    for (int i = tid; i < n; i += T) {
-        double a = 0.0;
-        for (int j = 0; j < n; j++) a += fabs(AM[(size_t)i * n + j]);
-        rs = fmax(rs, a);
-    }
-    rs = warp_max(rs);
-    if ((tid & 31) == 0) red[tid >> 5] = rs;
-    __syncthreads();
-    for (int w = 0; w < ((T + 31) >> 5); w++) anorm = fmax(anorm, red[w]);
-    __syncthreads();
     for (int k = tid; k < n; k += T) na.lam[(size_t)node * n + k] = dg[k];
     if (PART == 1) {
         if (tid == 0) { st->suspect = (cnorm * anorm < 1e10) ? 0 : 1; st->good = 1; st->fallback = 0; st->retry = 0; }
@@ -746,7 +778,7 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
         int sliced = 0;
         bool chol_split = false;
         if (candidate) {            // Cholesky path (pass 0 only: certified nodes never need the second pass)
-            const size_t csm = (size_t)(2 * n * ld + 3 * n + 32) * sizeof(double);
+            const size_t csm = (size_t)(2 * n * ld + 3 * n + 32 + 2 * (n + 2)) * sizeof(double);
             const char* cenv = getenv("B2N_CHOL_SPLIT");
             chol_split = !(cenv && cenv[0] == '0');
             if (chol_split && !ctx->stream_side2) {

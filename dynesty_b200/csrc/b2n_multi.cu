@@ -56,8 +56,8 @@ __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
     const NodeRef nr = refs[nodei];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     double* c = sm;                        // 2 x n centres (scaled space)
-    double* part = c + 2 * n;              // 2 x n partial sums of this CTA (read by the peers)
-    double* acc = part + 2 * n;            // nw x 2 x n
+    double* part0 = c + 2 * n;             // 2 x (2 x n) partial sums of this CTA (read by the peers), by iteration parity
+    double* acc = part0 + 4 * n;           // nw x 2 x n
     int* cnt = reinterpret_cast<int*>(acc + (size_t)nw * 2 * n);   // nw x 2
     // the first `stage_cap` rows of this CTA's share of the node, staged ONCE: the ten Lloyd iterations used to
     // re-read every row through perm[] from L2 -- two dependent long-latency loads per trip, 15 us per iteration
@@ -65,7 +65,7 @@ __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
     double* stg = reinterpret_cast<double*>(cnt + (size_t)nw * 2 + ((nw * 2) & 1));
     const int ns = n | 1;                  // odd row stride: a thread per row walks the columns bank-conflict free
     unsigned char* slab = reinterpret_cast<unsigned char*>(stg + (size_t)stage_cap * ns);   // labels of the staged rows
-    __shared__ int pcnt[2];                // this CTA's member counts (read by the peers)
+    __shared__ int pcnt2[2][2];            // this CTA's member counts (read by the peers), by iteration parity
     __shared__ int tot[2];
     const int lo = nr.start + (int)((long long)nr.count * rank / KM_CLUSTER);
     const int hi = nr.start + (int)((long long)nr.count * (rank + 1) / KM_CLUSTER);
@@ -126,6 +126,11 @@ __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
                 if (i == 0) cnt[ch * 2 + k] = m;
             }
             __syncthreads();
+            // the partials alternate between two buffers: a peer reads buffer (it & 1) between the cluster barriers
+            // of iterations it and it + 1, and this CTA writes it again only after the barrier of it + 1 -- ONE
+            // cluster barrier per Lloyd iteration instead of two
+            double* part = part0 + (it & 1) * 2 * n;
+            int* pcnt = pcnt2[it & 1];
             for (int e = tid; e < 2 * n; e += T) {
                 double t = 0.0;
                 for (int ch = 0; ch < CH; ch++) t += acc[(size_t)ch * 2 * n + e];
@@ -151,9 +156,10 @@ __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
                     c[e] = t / (double)tot[cl];
                 }
             }
-            cluster.sync();
+            __syncthreads();
         }
         if (rank == 0 && tid < 2) counts[nodei * 2 + tid] = tot[tid];
+        cluster.sync();          // no CTA leaves while a peer may still read its partials
         return;
     }
     for (int it = 0; it < 10; it++) {
@@ -195,6 +201,8 @@ __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
         }
         __syncthreads();
         // CTA partials (fixed warp order)
+        double* part = part0 + (it & 1) * 2 * n;       // alternating buffers: one cluster barrier per iteration (see above)
+        int* pcnt = pcnt2[it & 1];
         for (int e = threadIdx.x; e < 2 * n; e += blockDim.x) {
             double s = 0.0;
             for (int w = 0; w < nw; w++) s += acc[(size_t)w * 2 * n + e];
@@ -221,9 +229,10 @@ __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
                 c[e] = s / (double)tot[cl];
             }
         }
-        cluster.sync();      // peers have read this CTA's partials before they are overwritten
+        __syncthreads();
     }
     if (rank == 0 && threadIdx.x < 2) counts[nodei * 2 + threadIdx.x] = tot[threadIdx.x];
+    cluster.sync();          // no CTA leaves while a peer may still read its partials
 }
 
 // ---- stable partition of a node's segment by label: [label 0 ..., label 1 ...]
@@ -377,9 +386,9 @@ static int decompose(BoundWork& w, int count, std::vector<HNode>& tree, std::vec
     int cur = 0;
     const int min_size = 2 * n;
     int nwarps = 16;
-    while ((size_t)(4 * n + (size_t)nwarps * 2 * n) * sizeof(double) + nwarps * 2 * sizeof(int) > (size_t)ctx->max_smem_optin && nwarps > 1)
+    while ((size_t)(6 * n + (size_t)nwarps * 2 * n) * sizeof(double) + nwarps * 2 * sizeof(int) > (size_t)ctx->max_smem_optin && nwarps > 1)
         nwarps >>= 1;
-    const size_t km_base = (size_t)(4 * n + (size_t)nwarps * 2 * n) * sizeof(double) + (size_t)(nwarps * 2 + 2) * sizeof(int);
+    const size_t km_base = (size_t)(6 * n + (size_t)nwarps * 2 * n) * sizeof(double) + (size_t)(nwarps * 2 + 2) * sizeof(int);
     if (km_base > (size_t)ctx->max_smem_optin) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "ndim too large for k-means kernel");
     // rows a CTA may stage in shared memory (its eighth of the largest node of a level), within half an SM's
     // shared memory so that the chain kernels of other replicas keep their place next to it
@@ -525,7 +534,7 @@ extern "C" int b2n_multi_decompose(b2n_ctx* ctx, const double* points, int64_t N
     const char* fenv = getenv("B2N_BOUND_FAST");
     const int ldw = n | 1;
     bool fast = !(fenv && !strcmp(fenv, "0")) && N >= 4 * (int64_t)n &&
-                (size_t)(2 * n * ldw + 3 * n + 32) * sizeof(double) <= (size_t)ctx->max_smem_optin;
+                (size_t)(2 * n * ldw + 3 * n + 32 + 2 * (n + 2)) * sizeof(double) <= (size_t)ctx->max_smem_optin;
     if (fast && ctx->bound_fast_skip > 0 && !(fenv && fenv[0] == '1')) { ctx->bound_fast_skip--; fast = false; }   // "1" forces the attempt
     int dst = decompose(w, (int)N, tree, leaves, level, warn, fast);
     if (dst == B2N_RETRY_FULL) {
