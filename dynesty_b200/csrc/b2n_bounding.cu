@@ -601,9 +601,17 @@ __global__ void __launch_bounds__(1024) scale_finish_kernel(NodeArrays na, const
     const size_t nn = (size_t)n * n;
     NodeStat* st = na.stat + nr.node;
     if (st->retry) return;          // covariance still being repaired: decomposed again first
+    // max over the node's job partials: all threads, then one warp (a maximum does not depend on the order)
+    {
+        double m = -INFINITY;
+        for (int k = tid; k < nr.nslots * nsub; k += T) m = fmax(m, partial[(size_t)nr.slot0 * nsub + k]);
+        m = warp_max(m);
+        if ((tid & 31) == 0) red[tid >> 5] = m;
+        __syncthreads();
+    }
     if (tid == 0) {
         double fm = -INFINITY;
-        for (int k = 0; k < nr.nslots * nsub; k++) fm = fmax(fm, partial[(size_t)nr.slot0 * nsub + k]);
+        for (int k = 0; k < ((T + 31) >> 5); k++) fm = fmax(fm, red[k]);
         st->fmax = fm;
         double mult = 1.0;
         if (pass == 0) {
@@ -736,8 +744,8 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
         gwork = ctx->scratch2.as<double>();
     }
     B2N_TRY(b2n_func_smem(ctx, (const void*)(eig_ladder_kernel), (size_t)(eig_smem)));
-    // one warp per rotation pair of a Jacobi round (n/2 pairs), at least 4 warps for the O(n^2) loops
-    const int eig_threads = 32 * std::max(4, std::min(32, half));
+    // one HALF-warp per rotation pair of a Jacobi round (n/2 pairs), at least 4 warps for the O(n^2) loops
+    const int eig_threads = 32 * std::max(4, std::min(32, (half + 1) / 2));
     const size_t fm_smem = (size_t)8 * n * sizeof(double);
 
     std::vector<NodeStat> hs(nnodes);
@@ -934,7 +942,7 @@ int b2n_spec_root_launch(BoundWork& w, int count, SpecRoot& sp) {
     B2N_CUDA(ctx, cudaMemcpyAsync(b + o_list, &sp.node0, sizeof(int), cudaMemcpyHostToDevice, side));
     B2N_CUDA(ctx, cudaMemsetAsync(b + o_stat, 0, sizeof(NodeStat), side));
     B2N_TRY(b2n_func_smem(ctx, (const void*)(eig_ladder_kernel), eig_smem));
-    const int eig_threads = 32 * std::max(4, std::min(32, half));
+    const int eig_threads = 32 * std::max(4, std::min(32, (half + 1) / 2));
     eig_ladder_kernel<<<1, eig_threads, eig_smem, side>>>(sp.na, (const int*)(b + o_list), 0, nullptr, 1);
     B2N_LAUNCH_CHECK(ctx);
     fmax_partial_kernel<<<dim3(njobs, B2N_FMAX_SUB), 256, (size_t)8 * n * sizeof(double), side>>>(
@@ -1138,7 +1146,7 @@ extern "C" int b2n_improve_covar(b2n_ctx* ctx, const double* covar, int32_t n, d
             gwork = ctx->scratch2.as<double>();
         }
         B2N_TRY(b2n_func_smem(ctx, (const void*)(eig_ladder_kernel), (size_t)(eig_smem)));
-        eig_ladder_kernel<<<1, 32 * std::max(4, std::min(32, half)), eig_smem, st>>>(w.na, (const int*)dlist, 0, gwork, use_smem);
+        eig_ladder_kernel<<<1, 32 * std::max(4, std::min(32, (half + 1) / 2)), eig_smem, st>>>(w.na, (const int*)dlist, 0, gwork, use_smem);
         B2N_LAUNCH_CHECK(ctx);
     }
     B2N_CUDA(ctx, cudaStreamSynchronize(st));

@@ -49,17 +49,22 @@ static __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* c
         // converged at the round-off floor of the off-diagonal mass (n^2 entries of size
         // ~eps*||A||): the same absolute accuracy LAPACK's eigh delivers
         if (off <= (double)n * (double)n * 2.5e-32 * tot) break;
-        // One round = m/2 disjoint rotations.  WARP k owns pair k: it derives the rotation from
-        // its own three matrix entries (warp-uniform, no staging / no barrier), rotates rows p,q of
-        // A and of V^T with its lanes across the columns; after one barrier the same warp rotates
-        // columns p,q of A with its lanes down the rows.  Two barriers per round.
-        const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+        // One round = m/2 disjoint rotations.  A HALF-WARP owns a pair: it derives the rotation from its own three
+        // matrix entries (uniform in the half-warp, no staging / no barrier), rotates rows p,q of A and of V^T with
+        // its 16 lanes across the columns; after one barrier the same half-warp rotates columns p,q of A with its
+        // lanes down the rows.  Two barriers per round.  (A full warp per pair spent a third of its ~350
+        // instructions per round on the rotation's scalar arithmetic -- a division and two reciprocal square
+        // roots, the same in all 32 lanes; two pairs per warp issue that sequence once for both.  The kernel is
+        // issue bound: 3.0e6 warp instructions at n = 50.  Element by element the arithmetic is unchanged.)
+        const int lane = tid & 31, sub = lane & 15, grp = tid >> 4, ng = T >> 4;
         for (int r = 0; r < m - 1; r++) {
-            for (int k = warp; k < half; k += nw) {
-                int p, q;
-                rr_pair(m, r, k, p, q);
+            for (int k0 = (tid >> 5) * 2; k0 < half; k0 += (T >> 5) * 2) {       // warp-uniform trip count
+                const int k = k0 + (lane >> 4);
+                const bool act = k < half;
+                int p = 0, q = 0;
+                if (act) rr_pair(m, r, k, p, q);
                 double c = 1.0, s = 0.0;
-                if (q < n) {
+                if (act && q < n) {
                     const double app = A[(size_t)p * ld + p], aqq = A[(size_t)q * ld + q], apq = A[(size_t)p * ld + q];
                     // skip test |apq| <= 1e-17 sqrt(|app aqq|) without a square root
                     if (apq != 0.0 && apq * apq > 1e-34 * fabs(app * aqq)) {
@@ -83,13 +88,13 @@ static __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* c
                     }
                 }
                 __syncwarp();                      // every lane has read app/aqq/apq before rows change
-                if (lane == 0) { cc[k] = c; ss[k] = s; }
+                if (act && sub == 0) { cc[k] = c; ss[k] = s; }
                 if (s != 0.0) {
                     double* Ap = A + (size_t)p * ld;
                     double* Aq = A + (size_t)q * ld;
                     double* Vp = VT + (size_t)p * ld;
                     double* Vq = VT + (size_t)q * ld;
-                    for (int j = lane; j < n; j += 32) {
+                    for (int j = sub; j < n; j += 16) {
                         double a = Ap[j], b = Aq[j];
                         Ap[j] = c * a - s * b;
                         Aq[j] = s * a + c * b;
@@ -101,13 +106,13 @@ static __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* c
                 }
             }
             __syncthreads();
-            for (int k = warp; k < half; k += nw) {
+            for (int k = grp; k < half; k += ng) {
                 const double s = ss[k];
                 if (s != 0.0) {
                     int p, q;
                     rr_pair(m, r, k, p, q);
                     const double c = cc[k];
-                    for (int i = lane; i < n; i += 32) {
+                    for (int i = sub; i < n; i += 16) {
                         const double a = A[(size_t)i * ld + p], b = A[(size_t)i * ld + q];
                         A[(size_t)i * ld + p] = c * a - s * b;
                         A[(size_t)i * ld + q] = s * a + c * b;

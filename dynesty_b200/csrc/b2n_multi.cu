@@ -76,9 +76,18 @@ __global__ void __cluster_dims__(KM_CLUSTER, 1, 1) __launch_bounds__(512)
         c[n + i] = (ctr + v) / scale[i];
     }
     const int nst = min(hi - lo, stage_cap);
-    for (int r = warp; r < nst; r += nw) {
-        const size_t row = (size_t)perm[lo + r] * n;
-        for (int i = lane; i < n; i += 32) stg[(size_t)r * ns + i] = P[row + i];
+    // (row indices first, one coalesced load per 32 rows of the warp: a row's loads then do not wait for its
+    //  perm[] entry, and the rows of a warp are in flight together instead of one dependent pair after another)
+    for (int r0 = warp; r0 < nst; r0 += 32 * nw) {
+        const int mine = r0 + lane * nw;
+        const int idx = mine < nst ? perm[lo + mine] : 0;
+        const int cntw = min(32, (nst - r0 + nw - 1) / nw);
+#pragma unroll 4
+        for (int t = 0; t < cntw; t++) {
+            const size_t row = (size_t)__shfl_sync(B2N_FULL, idx, t) * n;
+            const int r = r0 + t * nw;
+            for (int i = lane; i < n; i += 32) stg[(size_t)r * ns + i] = P[row + i];
+        }
     }
     __syncthreads();
     // Every row of this CTA staged (the usual case): the THREAD-PER-ROW form of the Lloyd iteration.  The
