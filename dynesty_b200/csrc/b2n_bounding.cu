@@ -129,8 +129,12 @@ __global__ void cov_finalize_kernel(const NodeRef* __restrict__ refs, int n, con
 
 // improve_covar_mat (bounding.py:1311-1384) for one node per CTA.
 // pass 0: input = covraw ; pass 1: input = current cov (after the pass-0 rescale).
+// SMEM: the two work matrices live in the CTA's shared memory (every n the single-CTA path takes in practice) and are
+// addressed as such -- through the generic pointer of the global-memory fallback a third of the instructions of a
+// Jacobi round were 64-bit address arithmetic.
+template <bool SMEM>
 __global__ void __launch_bounds__(1024) eig_ladder_kernel(NodeArrays na, const int* __restrict__ nodelist, int pass,
-                                                         double* __restrict__ gwork, int use_smem) {
+                                                         double* __restrict__ gwork) {
     extern __shared__ double sm[];
     const int n = na.n, ld = na.ld, tid = threadIdx.x, T = blockDim.x;
     const int node = nodelist[blockIdx.x];
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(1024) eig_ladder_kernel(NodeArrays na, const i
     double* lamv = ss + half;
     double* tmpv = lamv + n;
     double* red = tmpv + n;
-    double* A = use_smem ? red + 32 : gwork + (size_t)blockIdx.x * 2 * n * ld;
+    double* A = SMEM ? red + 32 : gwork + (size_t)blockIdx.x * 2 * n * ld;
     double* VT = A + (size_t)n * ld;
     __shared__ int s_failed, s_sweeps;
     __shared__ double s_mx;
@@ -743,7 +747,7 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
         B2N_CUDA(ctx, ctx->scratch2.ensure((size_t)nnodes * mats_b));
         gwork = ctx->scratch2.as<double>();
     }
-    B2N_TRY(b2n_func_smem(ctx, (const void*)(eig_ladder_kernel), (size_t)(eig_smem)));
+    B2N_TRY(b2n_func_smem(ctx, use_smem ? (const void*)(eig_ladder_kernel<true>) : (const void*)(eig_ladder_kernel<false>), (size_t)(eig_smem)));
     // one HALF-warp per rotation pair of a Jacobi round (n/2 pairs), at least 4 warps for the O(n^2) loops
     const int eig_threads = 32 * std::max(4, std::min(32, (half + 1) / 2));
     const size_t fm_smem = (size_t)8 * n * sizeof(double);
@@ -816,7 +820,8 @@ int b2n_process_nodes(BoundWork& w, const std::vector<NodeRef>& refs_in, std::ve
             }
         } else if (!use_smem) B2N_TRY(b2n_eig_sliced(w, (const int*)plist, pn, pass, 0, &sliced));
         if (!candidate && !sliced) {
-            eig_ladder_kernel<<<pn, eig_threads, eig_smem, st>>>(w.na, (const int*)plist, pass, gwork, use_smem);
+            if (use_smem) eig_ladder_kernel<true><<<pn, eig_threads, eig_smem, st>>>(w.na, (const int*)plist, pass, gwork);
+            else eig_ladder_kernel<false><<<pn, eig_threads, eig_smem, st>>>(w.na, (const int*)plist, pass, gwork);
             B2N_LAUNCH_CHECK(ctx);
         }
         fmax_partial_kernel<<<dim3(pj, B2N_FMAX_SUB), 256, fm_smem, st>>>(w.P, w.perm, w.N, w.na, (const JobL*)pjobs, partial);
@@ -941,9 +946,9 @@ int b2n_spec_root_launch(BoundWork& w, int count, SpecRoot& sp) {
     B2N_CUDA(ctx, cudaMemcpyAsync(b + o_ref, &sp.ref, sizeof(NodeRef), cudaMemcpyHostToDevice, side));
     B2N_CUDA(ctx, cudaMemcpyAsync(b + o_list, &sp.node0, sizeof(int), cudaMemcpyHostToDevice, side));
     B2N_CUDA(ctx, cudaMemsetAsync(b + o_stat, 0, sizeof(NodeStat), side));
-    B2N_TRY(b2n_func_smem(ctx, (const void*)(eig_ladder_kernel), eig_smem));
+    B2N_TRY(b2n_func_smem(ctx, (const void*)(eig_ladder_kernel<true>), eig_smem));
     const int eig_threads = 32 * std::max(4, std::min(32, (half + 1) / 2));
-    eig_ladder_kernel<<<1, eig_threads, eig_smem, side>>>(sp.na, (const int*)(b + o_list), 0, nullptr, 1);
+    eig_ladder_kernel<true><<<1, eig_threads, eig_smem, side>>>(sp.na, (const int*)(b + o_list), 0, nullptr);
     B2N_LAUNCH_CHECK(ctx);
     fmax_partial_kernel<<<dim3(njobs, B2N_FMAX_SUB), 256, (size_t)8 * n * sizeof(double), side>>>(
         w.P, sp.perm, w.N, sp.na, (const JobL*)(b + o_jobs), (double*)(b + o_part));
@@ -1145,8 +1150,14 @@ extern "C" int b2n_improve_covar(b2n_ctx* ctx, const double* covar, int32_t n, d
             B2N_CUDA(ctx, ctx->scratch2.ensure(mats_b));
             gwork = ctx->scratch2.as<double>();
         }
-        B2N_TRY(b2n_func_smem(ctx, (const void*)(eig_ladder_kernel), (size_t)(eig_smem)));
-        eig_ladder_kernel<<<1, 32 * std::max(4, std::min(32, (half + 1) / 2)), eig_smem, st>>>(w.na, (const int*)dlist, 0, gwork, use_smem);
+        const int ethreads = 32 * std::max(4, std::min(32, (half + 1) / 2));
+        if (use_smem) {
+            B2N_TRY(b2n_func_smem(ctx, (const void*)(eig_ladder_kernel<true>), (size_t)(eig_smem)));
+            eig_ladder_kernel<true><<<1, ethreads, eig_smem, st>>>(w.na, (const int*)dlist, 0, gwork);
+        } else {
+            B2N_TRY(b2n_func_smem(ctx, (const void*)(eig_ladder_kernel<false>), (size_t)(eig_smem)));
+            eig_ladder_kernel<false><<<1, ethreads, eig_smem, st>>>(w.na, (const int*)dlist, 0, gwork);
+        }
         B2N_LAUNCH_CHECK(ctx);
     }
     B2N_CUDA(ctx, cudaStreamSynchronize(st));

@@ -31,7 +31,9 @@ static __device__ double block_sum(double v, double* red) {
 }
 
 // In-place: A (n x n, ld) -> diagonal ; VT rows = eigenvectors.  Returns sweeps used.
-static __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* cc, double* ss, double* red) {
+// (force-inlined: called with pointers into the CTA's shared memory the loads / stores become LDS / STS with 32-bit
+//  addresses; through a generic pointer a third of the instructions of a round were 64-bit address arithmetic)
+static __device__ __forceinline__ int jacobi_eig(double* A, double* VT, int n, int ld, double* cc, double* ss, double* red) {
     const int T = blockDim.x, tid = threadIdx.x;
     const int m = (n + 1) & ~1, half = m >> 1;
     int sweep = 0;
@@ -39,7 +41,7 @@ static __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* c
         double off = 0.0, dg = 0.0;
         for (int e = tid; e < n * n; e += T) {
             const int i = e / n, j = e - i * n;
-            const double a = A[(size_t)i * ld + j];
+            const double a = A[i * ld + j];
             if (i == j) dg = fma(a, a, dg); else off = fma(a, a, off);
         }
         off = block_sum(off, red);
@@ -65,7 +67,7 @@ static __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* c
                 if (act) rr_pair(m, r, k, p, q);
                 double c = 1.0, s = 0.0;
                 if (act && q < n) {
-                    const double app = A[(size_t)p * ld + p], aqq = A[(size_t)q * ld + q], apq = A[(size_t)p * ld + q];
+                    const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
                     // skip test |apq| <= 1e-17 sqrt(|app aqq|) without a square root
                     if (apq != 0.0 && apq * apq > 1e-34 * fabs(app * aqq)) {
                         // t = tan(theta) = sgn(tau) / (|tau| + sqrt(tau^2 + 1)), tau = (aqq-app)/(2 apq),
@@ -90,10 +92,10 @@ static __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* c
                 __syncwarp();                      // every lane has read app/aqq/apq before rows change
                 if (act && sub == 0) { cc[k] = c; ss[k] = s; }
                 if (s != 0.0) {
-                    double* Ap = A + (size_t)p * ld;
-                    double* Aq = A + (size_t)q * ld;
-                    double* Vp = VT + (size_t)p * ld;
-                    double* Vq = VT + (size_t)q * ld;
+                    double* Ap = A + p * ld;
+                    double* Aq = A + q * ld;
+                    double* Vp = VT + p * ld;
+                    double* Vq = VT + q * ld;
                     for (int j = sub; j < n; j += 16) {
                         double a = Ap[j], b = Aq[j];
                         Ap[j] = c * a - s * b;
@@ -113,9 +115,9 @@ static __device__ int jacobi_eig(double* A, double* VT, int n, int ld, double* c
                     rr_pair(m, r, k, p, q);
                     const double c = cc[k];
                     for (int i = sub; i < n; i += 16) {
-                        const double a = A[(size_t)i * ld + p], b = A[(size_t)i * ld + q];
-                        A[(size_t)i * ld + p] = c * a - s * b;
-                        A[(size_t)i * ld + q] = s * a + c * b;
+                        const double a = A[i * ld + p], b = A[i * ld + q];
+                        A[i * ld + p] = c * a - s * b;
+                        A[i * ld + q] = s * a + c * b;
                     }
                 }
             }
