@@ -1140,23 +1140,69 @@ __global__ void __launch_bounds__(512, 1) rwalk_mmas_kernel(const RwalkParams p,
     const int pk = p.m.prior_kind;
     const int lr = lane >> 2, lc = lane & 3;
 
+    // ---- helper scratch: step factor, U^(1/n), which state buffer is current, per-helper cube flags
+    const int oH = ost + CH * 4 * npad;
+    double* facbuf = &b2n_sm[oH];
+    double* pwbuf = &b2n_sm[oH + CH];
+    int* selbuf = reinterpret_cast<int*>(&b2n_sm[oH + 2 * CH]);
+    int* okbuf = reinterpret_cast<int*>(&b2n_sm[oH + 3 * CH]);            // CH x CH
+
     for (int g0 = 0; g0 < cd.y; g0 += CH) {
-        const int c = warp;
-        const bool live = g0 + c < cd.y;
-        const int q = live ? p.order[cd.x + g0 + c] : 0;
-        int oucur = ost + c * 4 * npad, ouprop = oucur + npad, ovcur = ouprop + npad, ovprop = ovcur + npad;
+        // L chains are live in this pass.  A pass with few chains (the rounds of b2n_ns_run put 1-2 chains on a CTA)
+        // used to leave 14 of the 16 warps idle outside the contraction while the chain's own warp generated its
+        // 200 normals (4 Philox / log / sincos rounds), U^(1/n) and 200 ndtri's one after the other: H = 16 / L
+        // warps now serve a chain -- the owner (h = 0: chain state, accept test, counters) and H - 1 helpers that
+        // take their share of the ELEMENTWISE work (normal blocks, the radius power, wrap / cube test / prior / delta
+        // of their elements).  Every element is computed by the same instructions as before and every sum is still
+        // formed by the owner in the old order (|z|^2 from the stored z), so a chain's result does not depend on
+        // how many warps worked on it -- nor, therefore, on the batch it is part of.
+        const int L = min(CH, cd.y - g0);
+        const int H = CH / L;
+        const int c = warp % L, h = warp / L;
+        const bool owner = h == 0, helper = h < H;
+        const int q = p.order[cd.x + g0 + c];
+        const int sbase = ost + c * 4 * npad;
+        int oucur = sbase, ouprop = sbase + npad, ovcur = ouprop + npad, ovprop = ovcur + npad;
         const int ox = oX + c * XS, oy = oY + c * YS;
+        const bool two = L > 8;                   // chains 8..15 exist: second column tile of the contractions
         ChainRng g;
         g.init(p.seed, chain0_ + (uint64_t)q);
-        if (live)
+        if (owner) {
             for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)q * n + i];
+            if (lane == 0) selbuf[c] = 0;
+        }
         int nacc = 0, nrej = 0;
         double lcur = 0.0;
+        const int nb = (n + 1) >> 1;
         __syncthreads();
         for (int step = 0; step < p.walks; step++) {
-            double fac = 0.0;
-            if (live) fac = scale_ * ball_direction(g, ox, n, lane, inv_n);
+            // ---- draw events of the step: normal vector (tick 2 step), radius uniform (tick 2 step + 1)
+            if (helper) {
+                g.tick = 2u * (uint32_t)step;
+                for (int b = 32 * h + lane; b < nb; b += 32 * H) {
+                    double z0, z1;
+                    rng_normal_pair(g, b, z0, z1);
+                    if (2 * b + 1 < n) *reinterpret_cast<double2*>(&b2n_sm[ox + 2 * b]) = make_double2(z0, z1);
+                    else b2n_sm[ox + 2 * b] = z0;
+                }
+                if (h == H - 1) {
+                    g.tick = 2u * (uint32_t)step + 1u;
+                    const double U = rng_uniform(g);
+                    const double pw = pow(U, inv_n);
+                    if (lane == 0) pwbuf[c] = pw;
+                }
+            }
             __syncthreads();
+            if (owner) {                              // |z|^2 in normals_sm's order, then the step factor
+                double ss = 0.0;
+                for (int b = lane; b < nb; b += 32) {
+                    const double z0 = b2n_sm[ox + 2 * b];
+                    ss = fma(z0, z0, ss);
+                    if (2 * b + 1 < n) { const double z1 = b2n_sm[ox + 2 * b + 1]; ss = fma(z1, z1, ss); }
+                }
+                ss = warp_sum(ss);
+                if (lane == 0) facbuf[c] = scale_ * (pwbuf[c] / sqrt(ss));
+            }
             // ---- Y = A X, fragments of A streamed from L2
             for (int s = warp; s < S; s += CH) {
                 const int row = 8 * s + lr;
@@ -1164,38 +1210,58 @@ __global__ void __launch_bounds__(512, 1) rwalk_mmas_kernel(const RwalkParams p,
                 const double* ap = Ag + (rv ? row : 0) + (size_t)lc * n;
                 const int xb0 = oX + lr * XS + lc, xb1 = xb0 + 8 * XS;
                 double d00 = 0, d01 = 0, d10 = 0, d11 = 0;
+                if (two) {
 #pragma unroll 8
-                for (int kt = 0; kt < KT; kt++) {
-                    const bool in = rv && (4 * kt + lc) < n;
-                    const double a = in ? __ldg(ap + (size_t)(4 * kt) * n) : 0.0;
-                    dmma884(d00, d01, a, b2n_sm[xb0 + 4 * kt]);
-                    dmma884(d10, d11, a, b2n_sm[xb1 + 4 * kt]);
+                    for (int kt = 0; kt < KT; kt++) {
+                        const bool in = rv && (4 * kt + lc) < n;
+                        const double a = in ? __ldg(ap + (size_t)(4 * kt) * n) : 0.0;
+                        dmma884(d00, d01, a, b2n_sm[xb0 + 4 * kt]);
+                        dmma884(d10, d11, a, b2n_sm[xb1 + 4 * kt]);
+                    }
+                } else {
+#pragma unroll 8
+                    for (int kt = 0; kt < KT; kt++) {
+                        const bool in = rv && (4 * kt + lc) < n;
+                        const double a = in ? __ldg(ap + (size_t)(4 * kt) * n) : 0.0;
+                        dmma884(d00, d01, a, b2n_sm[xb0 + 4 * kt]);
+                    }
                 }
                 const int c0 = 2 * lc;
                 b2n_sm[oY + c0 * YS + row] = d00;
                 b2n_sm[oY + (c0 + 1) * YS + row] = d01;
-                b2n_sm[oY + (8 + c0) * YS + row] = d10;
-                b2n_sm[oY + (9 + c0) * YS + row] = d11;
+                if (two) {
+                    b2n_sm[oY + (8 + c0) * YS + row] = d10;
+                    b2n_sm[oY + (9 + c0) * YS + row] = d11;
+                }
             }
             __syncthreads();
-            bool ok = true;
-            if (live) {
-                for (int i = lane; i < n; i += 32) {
-                    double t = fma(fac, b2n_sm[oy + i], b2n_sm[oucur + i]);
+            // ---- proposal u' = u + fac y, wrap / reflect / cube test, prior, delta: elements dealt over the H warps
+            if (helper) {
+                const double fac = facbuf[c];
+                const int sel = selbuf[c];
+                const int ucur_ = sel ? sbase + npad : sbase, uprop_ = sel ? sbase : sbase + npad;
+                const int vprop_ = sel ? sbase + 2 * npad : sbase + 3 * npad;
+                bool okp = true;
+                for (int i = 32 * h + lane; i < n; i += 32 * H) {
+                    double t = fma(fac, b2n_sm[oy + i], b2n_sm[ucur_ + i]);
                     const uint32_t f = fl[i];
                     if (f & B2N_DIM_PERIODIC) t = mod1(t);
                     if (f & B2N_DIM_REFLECTIVE) t = reflect1(t);
-                    ok = ok && in_cube(t, f);
+                    okp = okp && in_cube(t, f);
                     const double vi = prior_sm(pk, op0, op1, i, t);
-                    b2n_sm[ouprop + i] = t;
-                    b2n_sm[ovprop + i] = vi;
+                    b2n_sm[uprop_ + i] = t;
+                    b2n_sm[vprop_ + i] = vi;
                     b2n_sm[ox + i] = vi - b2n_sm[omu + i];
                 }
-                ok = __all_sync(B2N_FULL, ok);
+                okp = __all_sync(B2N_FULL, okp);
+                if (lane == 0) okbuf[c * CH + h] = okp ? 1 : 0;
             }
+            __syncthreads();
+            bool ok = true;
+            if (owner)
+                for (int k = 0; k < H; k++) ok = ok && (okbuf[c * CH + k] != 0);
             double l = 0.0;
             if (LIKE == B2N_LIKE_GAUSS_PREC) {
-                __syncthreads();
                 for (int s = warp; s < S; s += CH) {
                     const int row = 8 * s + lr;
                     const bool rv = row < n;
@@ -1207,7 +1273,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_mmas_kernel(const RwalkParams p,
                         const bool in = rv && (4 * kt + lc) < n;
                         const double a = in ? __ldg(pp + (size_t)(4 * kt) * n) : 0.0;
                         dmma884(d00, d01, a, b2n_sm[xb0 + 4 * kt]);
-                        dmma884(d10, d11, a, b2n_sm[xb1 + 4 * kt]);
+                        if (two) dmma884(d10, d11, a, b2n_sm[xb1 + 4 * kt]);
                     }
                     const int c0 = 2 * lc;
                     double q00 = d00 * b2n_sm[oX + c0 * XS + row], q01 = d01 * b2n_sm[oX + (c0 + 1) * XS + row];
@@ -1230,11 +1296,10 @@ __global__ void __launch_bounds__(512, 1) rwalk_mmas_kernel(const RwalkParams p,
                 double qf = 0.0;
                 for (int s = 0; s < S; s++) qf += b2n_sm[oQ + s * CH + c];
                 l = fma(-0.5, qf, p.m.s0);
-            } else if (live && ok) {
-                __syncwarp();
+            } else if (owner && ok) {
                 l = loglike_sm<LIKE, false>(p.m, ms, nullptr, 0, n, n, ovprop, oy, lane);
             }
-            if (live) {
+            if (owner) {
                 if (!ok) {
                     nrej++;
                 } else if (l > loglstar_) {
@@ -1242,12 +1307,13 @@ __global__ void __launch_bounds__(512, 1) rwalk_mmas_kernel(const RwalkParams p,
                     t = ovcur; ovcur = ovprop; ovprop = t;
                     lcur = l;
                     nacc++;
+                    if (lane == 0) selbuf[c] ^= 1;
                 } else {
                     nrej++;
                 }
             }
         }
-        if (live) {
+        if (owner) {
             if (nacc == 0) {
                 for (int i = lane; i < n; i += 32) b2n_sm[ovcur + i] = prior_sm(pk, op0, op1, i, b2n_sm[oucur + i]);
                 __syncwarp();
@@ -1421,7 +1487,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         sXS = RS + ((RS % 16 == 4) ? 0 : ((20 - RS % 16) % 16));
         sYS = RS + 2;
         const size_t need = (size_t)(4 * npad + (((n + 3) >> 2) << 1) + 16 * sXS + 16 * sYS + (RS / 8) * 16 +
-                                     16 * 4 * npad) * sizeof(double);
+                                     16 * 4 * npad + 3 * 16 + 16 * 16 / 2) * sizeof(double);      // + the helper scratch
         if (need <= limit) {
             use_mmas = true;
             mma_smem = need;
