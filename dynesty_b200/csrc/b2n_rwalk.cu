@@ -1219,7 +1219,9 @@ __global__ void __launch_bounds__(512, 1) rwalk_mmas_kernel(const RwalkParams p,
                         dmma884(d10, d11, a, b2n_sm[xb1 + 4 * kt]);
                     }
                 } else {
-#pragma unroll 8
+                    // (one column tile: the loop is a load and a DMMA -- 25 loads in flight per warp instead of 8,
+                    //  the phase is bound by the L2 round trips of its fragment loads)
+#pragma unroll 25
                     for (int kt = 0; kt < KT; kt++) {
                         const bool in = rv && (4 * kt + lc) < n;
                         const double a = in ? __ldg(ap + (size_t)(4 * kt) * n) : 0.0;
