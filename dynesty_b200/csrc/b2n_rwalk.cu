@@ -1203,8 +1203,9 @@ __global__ void __launch_bounds__(512, 1) rwalk_mmas_kernel(const RwalkParams p,
                 ss = warp_sum(ss);
                 if (lane == 0) facbuf[c] = scale_ * (pwbuf[c] / sqrt(ss));
             }
-            // ---- Y = A X, fragments of A streamed from L2
-            for (int s = warp; s < S; s += CH) {
+            // ---- Y = A X, fragments of A streamed from L2 (slabs dealt from the LAST warp down: the owners -- warps
+            //      0 .. L-1, which have just formed the step factors -- get the fewest)
+            for (int s = CH - 1 - warp; s < S; s += CH) {
                 const int row = 8 * s + lr;
                 const bool rv = row < n;
                 const double* ap = Ag + (rv ? row : 0) + (size_t)lc * n;
