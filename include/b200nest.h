@@ -152,7 +152,10 @@ int b2n_bounding_ellipsoid(b2n_ctx* ctx, const double* points, int64_t N, int32_
  * 2-means split _bounding_ellipsoids (bounding.py:665-686, 1464-1563) + the
  * all-points-contained check (:683-685).  labels[N] = index of the leaf
  * ellipsoid each point was assigned to.  nells: host int out.  Arrays sized
- * for max_ells.  Synchronises. */
+ * for max_ells.  Synchronises.  Internally the update uses two more streams of the
+ * context besides its own (the root's eigen fit runs speculatively beside the expansion of
+ * the candidate tree, the two halves of a candidate fit run side by side);
+ * they are drained before the call returns, the caller sees one synchronous call. */
 int b2n_multi_decompose(b2n_ctx* ctx, const double* points, int64_t N, int32_t n,
                         int32_t max_ells, int32_t* nells, int32_t* labels,
                         double* ctrs, double* covs, double* ams, double* axes,
