@@ -419,6 +419,8 @@ def run_b200(args, cfg):
     # ---- buffers
     pin = lambda *s, dt=torch.float64: torch.empty(*s, dtype=dt).pin_memory()
     h_u0 = pin(Q, n)
+    h_live = pin(nlive, n)                      # the live set, pinned: the kernels read their start rows from it in place
+    h_live.numpy()[:] = u_live
     h_out = dict(u=pin(Q, n), v=pin(Q, n), logl=pin(Q), n_accept=pin(Q, dt=torch.int32),
                  n_reject=pin(Q, dt=torch.int32), ncall=pin(Q, dt=torch.int32))
     h_np = {k: t.numpy() for k, t in h_out.items()}
@@ -459,22 +461,28 @@ def run_b200(args, cfg):
         return starts, ell
 
     def step_host():
-        """The plug-in call with host buffers (what Sampler._fill_queue does per fill)."""
+        """The plug-in call with host buffers (what Sampler._fill_queue does per fill): the start rows are named by
+        index and read by the kernel from the (pinned) live set in place -- b2n_set_start_rows -- instead of being
+        gathered into a block by the caller first (np.take: 40 us of a 0.32 ms step); --gather-starts restores that."""
         starts, ell = propose()
-        np.take(u_live, starts, axis=0, out=h_u0.numpy(), mode='clip')    # ('raise' buffers `out`: 3x slower)
+        if args.gather_starts:
+            np.take(u_live, starts, axis=0, out=h_u0.numpy(), mode='clip')    # ('raise' buffers `out`: 3x slower)
+            src, kw = h_u0.numpy(), {}
+        else:
+            src, kw = h_live.numpy(), dict(start_rows=starts.astype(np.int32, copy=False))
         ctx.set_pointer_mode(_lib.PTR_HOST)
         c0 = state['chain']
         state['chain'] += Q * world
         if fused:
             # every rank's WINDOW (HBM) receives the whole queue inside the kernel; only rank 0 -- the owner of the
             # nested-sampling bookkeeping -- copies it to its host, the other ranks' hosts receive nothing
-            o = ops.rwalk_batch(mid, h_u0.numpy(), loglstar, state['scale'], walks, SEED, chain0=c0 + rank * Q,
-                                ell=ell, ctx=ctx, out=hg_np if rank == 0 else ops.NO_OUT, peer=(rank * Q, world * Q))
+            o = ops.rwalk_batch(mid, src, loglstar, state['scale'], walks, SEED, chain0=c0 + rank * Q,
+                                ell=ell, ctx=ctx, out=hg_np if rank == 0 else ops.NO_OUT, peer=(rank * Q, world * Q), **kw)
             if rank != 0:
                 return None
             return {k: v[rank * Q:(rank + 1) * Q] for k, v in o.items()}
-        o = ops.rwalk_batch(mid, h_u0.numpy(), loglstar, state['scale'], walks, SEED, chain0=c0 + rank * Q,
-                            ell=ell, ctx=ctx, out=h_np)
+        o = ops.rwalk_batch(mid, src, loglstar, state['scale'], walks, SEED, chain0=c0 + rank * Q,
+                            ell=ell, ctx=ctx, out=h_np, **kw)
         return o
 
     def prep_dev():
@@ -646,7 +654,9 @@ def run_b200(args, cfg):
                                  ("NCCL all-gather after the kernel" if world > 1 else "none (1 GPU)")),
                     "bound_update_ms": round(bound_ms, 3), "bound_update_first_ms": round(bound_ms_first, 2)},
             "e2e": {"value": e2e, "unit": "proposals/s",
-                    "h2d_bytes_per_step": Q * n * 8 + Q * 4 + 16 * (Q // 8 + 1),
+                    "h2d_bytes_per_step": Q * n * 8 + Q * 4 + 16 * (Q // 8 + 1) + (0 if args.gather_starts else Q * 4),
+                    "start_points": ("gathered by the caller into a pinned block (np.take)" if args.gather_starts else
+                                     "by index: the kernel reads rows idx[q] of the pinned live set in place (b2n_set_start_rows)"),
                     "d2h_bytes_per_step": (world if fused else 1) * (2 * Q * n * 8 + Q * 8 + 3 * Q * 4),
                     "bytes_are": ("rank 0 (the owner of the sampler state receives the whole queue; the other ranks' hosts "
                                   "receive nothing)" if fused else "per rank")},
@@ -791,6 +801,7 @@ def main():
     ap.add_argument('--solo', type=int, default=1, help='N=1: also time one run alone on the GPU')
     ap.add_argument('--logz-batch', type=int, default=0, help='points replaced per device round (default nlive/40)')
     ap.add_argument('--cpu-baseline', type=int, default=1)
+    ap.add_argument('--gather-starts', type=int, default=0, help='e2e: 1 = the caller gathers the start rows (np.take) instead of passing indices')
     ap.add_argument('--ramp', type=float, default=0.7, help='seconds of untimed steps before timing (clock ramp; 0 under ncu)')
     ap.add_argument('--exchange', default='fused', choices=['fused', 'nccl'],
                     help='N>1: how the finished chains reach every rank')

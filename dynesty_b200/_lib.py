@@ -68,6 +68,7 @@ SYMBOLS = {
     'b2n_set_pointer_mode': (C.c_int, [_P, C.c_int]),
     'b2n_synchronize': (C.c_int, [_P]),
     'b2n_set_chain_pack': (C.c_int, [_P, _I]),
+    'b2n_set_start_rows': (C.c_int, [_P, _P, C.c_int64]),
     'b2n_debug_launch_rate': (C.c_int, [_P, _I, C.POINTER(_D)]),
     'b2n_strerror': (C.c_char_p, [C.c_int]),
     'b2n_last_error': (C.c_char_p, [_P]),
@@ -213,6 +214,10 @@ class Context:
 
     def set_chain_pack(self, chains_per_cta):
         self.check(self.lib.b2n_set_chain_pack(self.h, int(chains_per_cta)))
+
+    def set_start_rows(self, idx_ptr, nrows):
+        """the next rwalk call takes its start points as rows idx[q] of its u0 (= the whole live set)"""
+        self.check(self.lib.b2n_set_start_rows(self.h, idx_ptr, int(nrows)))
 
     def synchronize(self):
         self.check(self.lib.b2n_synchronize(self.h))

@@ -113,6 +113,8 @@ struct b2n_ctx {
     DynLaunch dyn;
     b2n_ns* ns = nullptr;
     void* friends = nullptr;    // resident RadFriends / SupFriends bound (b2n_friends.cu)
+    const int32_t* start_idx = nullptr;   // b2n_set_start_rows: the NEXT rwalk call reads its start points as rows of u0
+    int64_t start_nrows = 0;
     int min_cpc = 1;            // b2n_set_chain_pack: at least this many chains per CTA (see include/b200nest.h)
     int bound_fast_skip = 0;    // b2n_multi_decompose: updates left to skip the Cholesky candidate path
     // speculative eigen fit of the root node, concurrent with the candidate tree (b2n_bounding.cu: b2n_spec_root_*)

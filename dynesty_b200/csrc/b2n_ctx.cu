@@ -154,6 +154,13 @@ int b2n_debug_launch_rate(b2n_ctx* ctx, int32_t nlaunch, double* us_per_launch) 
     return B2N_OK;
 }
 
+int b2n_set_start_rows(b2n_ctx* ctx, const int32_t* idx, int64_t nrows) {
+    if (!ctx || (idx && nrows < 1)) return B2N_ERR_ARG;
+    ctx->start_idx = idx;
+    ctx->start_nrows = idx ? nrows : 0;
+    return B2N_OK;
+}
+
 int b2n_set_chain_pack(b2n_ctx* ctx, int32_t chains_per_cta) {
     if (!ctx || chains_per_cta < 1) return B2N_ERR_ARG;
     ctx->min_cpc = chains_per_cta;

@@ -32,6 +32,7 @@ struct RwalkParams {
     int n, nc, walks;
     int ldA, ldP;          // leading dims of axes^T / precision as seen by the kernel
     const double* u0;
+    const int* start;      // optional: chain q starts from row start[q] of u0 (b2n_set_start_rows); NULL: row q
     const int* order;      // chains grouped by ellipsoid
     const int3* cta;       // (first, count, ell) per CTA
     const double* axesT;   // K x nc x nc, transposed (column-major axes)
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_kernel(const RwalkParams p) {
         const int q = p.order[cd.x + c];
         ChainRng g;
         g.init(p.seed, chain0_ + (uint64_t)q);
-        for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)q * n + i];
+        for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)(p.start ? p.start[q] : q) * n + i];
         __syncwarp();
         int nacc = 0, nrej = 0;
         double lcur = 0.0;
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(CH * 32, CH == 8 ? 2 : 1) rwalk_mma_kernel(con
         int oucur = ost + c * 4 * npad, ouprop = oucur + npad, ovcur = ouprop + npad, ovprop = ovcur + npad;
         const int oy = oY + c * YS;
         if (live)
-            for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)q * n + i];
+            for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)(p.start ? p.start[q] : q) * n + i];
         int nacc = 0, nrej = 0;
         double lcur = 0.0;
         for (int step0 = 0; step0 < p.walks; step0 += DEPTH) {
@@ -532,7 +533,7 @@ __global__ void __launch_bounds__(512, 2) rwalk_mma16_kernel(const RwalkParams p
         const int nlc = (cd.y - g0) < CH ? (cd.y - g0) : CH;
         const bool live = c < nlc;
         const int q = live ? p.order[cd.x + g0 + c] : 0;
-        double ucur = (live && cin) ? p.u0[(size_t)q * n + ci] : 0.0, vcur = 0.0, uprop = 0.0, vprop = 0.0;
+        double ucur = (live && cin) ? p.u0[(size_t)(p.start ? p.start[q] : q) * n + ci] : 0.0, vcur = 0.0, uprop = 0.0, vprop = 0.0;
         int nacc = 0, nrej = 0;
         double lcur = 0.0;
 
@@ -941,7 +942,7 @@ __global__ void __launch_bounds__(384, 2) rwalk_mmaws_kernel(const RwalkParams p
 #define ovcur (ost + 2 * RS + par * RS)
 #define ovprop (ost + 2 * RS + (par ^ 1) * RS)
             if (live)
-                for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)q * n + i];
+                for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)(p.start ? p.start[q] : q) * n + i];
             int nacc = 0, nrej = 0;
             double lcur = 0.0;
             bool ok = true;
@@ -1168,7 +1169,7 @@ __global__ void __launch_bounds__(512, 1) rwalk_mmas_kernel(const RwalkParams p,
         ChainRng g;
         g.init(p.seed, chain0_ + (uint64_t)q);
         if (owner) {
-            for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)q * n + i];
+            for (int i = lane; i < n; i += 32) b2n_sm[oucur + i] = p.u0[(size_t)(p.start ? p.start[q] : q) * n + i];
             if (lane == 0) selbuf[c] = 0;
         }
         int nacc = 0, nrej = 0;
@@ -1415,6 +1416,10 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
                                double* v, double* logl, int32_t* n_accept, int32_t* n_reject,
                                int32_t* ncall) {
     if (!ctx || !a) return B2N_ERR_ARG;
+    // start points by index (b2n_set_start_rows): consumed by THIS call, however it ends
+    const int32_t* sidx = ctx->start_idx;
+    const int64_t srows = ctx->start_nrows;
+    ctx->start_idx = nullptr; ctx->start_nrows = 0;
     const bool gather = ctx->peer.total > 0;      // outputs may be NULL in gather mode (b2n_peer_result)
     if (!gather && (!u || !v || !logl || !n_accept || !n_reject || !ncall)) return B2N_ERR_ARG;
     if (a->model_id < 0 || a->model_id >= (int)ctx->models.size()) return B2N_ERR_ARG;
@@ -1518,8 +1523,18 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
     p.m = m; p.n = n; p.nc = nc; p.walks = walks; p.ldA = ldA; p.ldP = ldP;
     p.loglstar = a->loglstar; p.scale = a->scale; p.seed = a->seed; p.chain0 = a->chain0;
     p.axesT = ctx->b_axesT.as<double>();
-    const void *du0, *dorder, *dcta, *dfl = nullptr;
-    B2N_TRY(b2n_in(ctx, ctx->in0, a->u0, (size_t)Q * n * sizeof(double), &du0));
+    const void *du0, *dorder, *dcta, *dfl = nullptr, *dstart = nullptr;
+    // start points by index: u0 is then the whole live set
+    if (sidx) {
+        if (dyn) return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "start rows by index: not in a device-paced launch");
+        if (ctx->ptr_mode == B2N_PTR_DEVICE) dstart = sidx;
+        else {
+            for (int64_t i = 0; i < Q; i++)
+                if (sidx[i] < 0 || sidx[i] >= srows) return b2n_fail(ctx, B2N_ERR_ARG, "start row index out of range");
+            B2N_TRY(b2n_in_host(ctx, ctx->in1, sidx, (size_t)Q * sizeof(int32_t), &dstart));
+        }
+    }
+    B2N_TRY(b2n_in(ctx, ctx->in0, a->u0, (size_t)(sidx ? srows : Q) * n * sizeof(double), &du0));
     unsigned ncta = 0;
     if (dyn) {
         dorder = ctx->dyn.order; dcta = ctx->dyn.cta;
@@ -1546,7 +1561,7 @@ extern "C" int b2n_rwalk_batch(b2n_ctx* ctx, const b2n_chain_args* a, int32_t wa
         B2N_TRY(b2n_out(ctx, ctx->out4, n_reject, (size_t)Q * sizeof(int), &dnr));
         B2N_TRY(b2n_out(ctx, ctx->out5, ncall, (size_t)Q * sizeof(int), &dncl));
     }
-    p.u0 = (const double*)du0; p.order = (const int*)dorder; p.cta = (const int3*)dcta;
+    p.u0 = (const double*)du0; p.start = (const int*)dstart; p.order = (const int*)dorder; p.cta = (const int3*)dcta;
     p.dimflags = (const uint32_t*)dfl;
     p.u = (double*)du; p.v = (double*)dv; p.logl = (double*)dl;
     p.nacc = (int*)dna; p.nrej = (int*)dnr; p.ncall = (int*)dncl;

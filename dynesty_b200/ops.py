@@ -267,13 +267,22 @@ NO_OUT = _NO_OUT
 
 
 def rwalk_batch(model, u0, loglstar, scale, walks, seed, chain0=0, ncdim=None, ell=None,
-                dimflags=None, ctx=None, out=None, peer=None):
+                dimflags=None, ctx=None, out=None, peer=None, start_rows=None):
     """RWalkSampler.sample for every row of u0 (internal_samplers.py:505-561).
     `out`: optional dict of preallocated buffers (numpy, or torch tensors on the ctx device
     when the ctx is in device-pointer mode) with keys u, v, logl, n_accept, n_reject, ncall.
-    `peer=(row0, total)`: fused multi-GPU gather, outputs have `total` rows."""
+    `peer=(row0, total)`: fused multi-GPU gather, outputs have `total` rows.
+    `start_rows`: int32 indices -- `u0` is then the whole live set and chain q starts from row start_rows[q]
+    (b2n_set_start_rows: the gather of Sampler._fill_queue done by the kernel)."""
     ctx = _ctx(ctx)
     a, keep, Q, n = _chain_args(model, u0, ncdim, loglstar, scale, seed, chain0, ell, dimflags)
+    if start_rows is not None:
+        if not hasattr(start_rows, 'data_ptr'):
+            start_rows = np.ascontiguousarray(start_rows, dtype=np.int32)
+        keep.append(start_rows)
+        a.nchain = int(start_rows.shape[0])
+        ctx.set_start_rows(ptr(start_rows), Q)          # Q rows of u0 = the live set
+        Q = a.nchain
     R = Q if peer is None else int(peer[1])
     o = out if out is not None else dict(
         u=np.empty((R, n)), v=np.empty((R, n)), logl=np.empty(R),

@@ -351,3 +351,43 @@ def test_pinned_buffers_are_used_in_place(sampler):
         o = ops.rslice_batch(dm.model_id(), h_u0.numpy(), loglstar, 0.3, 4, SEED, chain0=7)   # pinned input only
     for k in ref:
         assert np.array_equal(np.asarray(o[k]), ref[k]), k
+
+
+@pytest.mark.parametrize('name,ncdim', [('g6', 4), ('g6', None), ('g50', None), ('n200', None)])
+@pytest.mark.parametrize('pinned', [False, True])
+def test_start_points_by_index(name, ncdim, pinned):
+    """b2n_set_start_rows: the chain kernels read their start points as rows idx[q] of the whole live set (the
+    gather of Sampler.propose_live / _fill_queue, sampler.py:469-491, 708-717, done by the kernel).  Every rwalk
+    kernel (warp per chain, lock-step DMMA, warp-specialised, streamed) must give exactly the chains it gives for
+    the gathered rows; pageable and pinned (zero-copy) live sets; the setting lasts for one call; a bad index is an
+    argument error."""
+    import torch
+    m = MODELS[name]
+    dm = device_model(m)
+    n = m.ndim
+    rng = np.random.default_rng(3)
+    pts = 0.5 + (0.02 if n > 6 else 0.06) * rng.standard_normal((500, n))
+    nc = ncdim or n
+    e = OB.bounding_ellipsoid(pts[:, :nc])
+    logl = m.loglike(m.prior_transform(pts))
+    loglstar = float(np.quantile(logl, 0.3))
+    ok = np.flatnonzero(logl > loglstar)
+    starts = rng.choice(ok, size=300).astype(np.int32)
+    ops.bound_set(e.axes)
+    ref = ops.rwalk_batch(dm.model_id(), pts[starts], loglstar, 0.4, 12, SEED, chain0=40, ncdim=ncdim)
+    live = pts
+    if pinned:
+        t = torch.empty(pts.shape, dtype=torch.float64).pin_memory()
+        t.numpy()[:] = pts
+        live = t.numpy()
+    o = ops.rwalk_batch(dm.model_id(), live, loglstar, 0.4, 12, SEED, chain0=40, ncdim=ncdim, start_rows=starts)
+    for k in ref:
+        assert o[k].shape == ref[k].shape and np.array_equal(o[k], ref[k]), k
+    again = ops.rwalk_batch(dm.model_id(), pts[starts], loglstar, 0.4, 12, SEED, chain0=40, ncdim=ncdim)   # plain call: not sticky
+    assert np.array_equal(again['u'], ref['u'])
+    bad = starts.copy()
+    bad[5] = len(pts)
+    with pytest.raises(Exception):
+        ops.rwalk_batch(dm.model_id(), live, loglstar, 0.4, 12, SEED, chain0=40, ncdim=ncdim, start_rows=bad)
+    after = ops.rwalk_batch(dm.model_id(), pts[starts], loglstar, 0.4, 12, SEED, chain0=40, ncdim=ncdim)   # and the failed call left nothing behind
+    assert np.array_equal(after['u'], ref['u'])
