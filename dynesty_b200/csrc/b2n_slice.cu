@@ -262,6 +262,10 @@ static int slice_batch_impl(b2n_ctx* ctx, const b2n_chain_args* a, int32_t slice
                             double* v, double* logl, int32_t* n_expand, int32_t* n_contract, int32_t* ncall,
                             uint32_t* flags) {
     if (!ctx || !a) return B2N_ERR_ARG;
+    if (ctx->start_idx) {       // b2n_set_start_rows is for the next b2n_rwalk_batch only: do not let it linger
+        ctx->start_idx = nullptr; ctx->start_nrows = 0;
+        return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "start rows by index (b2n_set_start_rows) are read by b2n_rwalk_batch only");
+    }
     const bool gather = ctx->peer.total > 0;      // outputs may be NULL in gather mode (b2n_peer_result)
     if (!gather && (!u || !v || !logl || !n_expand || !n_contract || !ncall || !flags)) return B2N_ERR_ARG;
     if (a->model_id < 0 || a->model_id >= (int)ctx->models.size()) return B2N_ERR_ARG;

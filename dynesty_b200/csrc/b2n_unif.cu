@@ -222,6 +222,10 @@ __global__ void unif_error_kernel(const uint32_t* flags, int64_t Q, int* out) {
 extern "C" int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, double* v, double* logl,
                               int32_t* ncall, int32_t* nprop, uint32_t* flags) {
     if (!ctx || !a) return B2N_ERR_ARG;
+    if (ctx->start_idx) {       // b2n_set_start_rows is for the next b2n_rwalk_batch only: do not let it linger
+        ctx->start_idx = nullptr; ctx->start_nrows = 0;
+        return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "start rows by index (b2n_set_start_rows) are read by b2n_rwalk_batch only");
+    }
     const bool gather = ctx->peer.total > 0;      // outputs may be NULL in gather mode (b2n_peer_result)
     if (!gather && (!u || !v || !logl || !ncall || !nprop || !flags)) return B2N_ERR_ARG;
     const int draw_only = (a->reserved & B2N_OPT_DRAW_ONLY) ? ((a->reserved & B2N_OPT_DRAW_MIXTURE) ? 3 : 1) : 0;
@@ -332,6 +336,10 @@ extern "C" int b2n_unif_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, 
 extern "C" int b2n_unitcube_batch(b2n_ctx* ctx, const b2n_chain_args* a, double* u, double* v, double* logl,
                                   int32_t* ncall, uint32_t* flags) {
     if (!ctx || !a) return B2N_ERR_ARG;
+    if (ctx->start_idx) {       // b2n_set_start_rows is for the next b2n_rwalk_batch only: do not let it linger
+        ctx->start_idx = nullptr; ctx->start_nrows = 0;
+        return b2n_fail(ctx, B2N_ERR_UNSUPPORTED, "start rows by index (b2n_set_start_rows) are read by b2n_rwalk_batch only");
+    }
     const bool gather = ctx->peer.total > 0;
     if (!gather && (!u || !v || !logl || !ncall)) return B2N_ERR_ARG;
     if (a->model_id < 0 || a->model_id >= (int)ctx->models.size()) return B2N_ERR_ARG;

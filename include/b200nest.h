@@ -83,7 +83,8 @@ int  b2n_set_chain_pack(b2n_ctx* ctx, int32_t chains_per_cta);
  * whole live set, `nrows` x ndim, and chain q starts from row idx[q] -- what Sampler.propose_live / _fill_queue do
  * with `self.live_u[i, :]` (sampler.py:469-491, 708-717) moved into the kernel: the caller no longer gathers the Q
  * start rows into a contiguous block (40 us of a 0.32 ms end-to-end step at C2).  idx: nchain int32 in [0, nrows),
- * host or device memory like the other arrays of the call; NULL cancels. */
+ * host or device memory like the other arrays of the call; NULL cancels.  Any other chain entry point called with
+ * the setting pending clears it and returns B2N_ERR_UNSUPPORTED. */
 int  b2n_set_start_rows(b2n_ctx* ctx, const int32_t* idx, int64_t nrows);
 /* diagnostic: host microseconds per launch when `nlaunch` empty kernels are enqueued back to back on the ctx stream
  * (call it from several threads / contexts at once to see what the driver's launch path sustains) */

@@ -391,3 +391,12 @@ def test_start_points_by_index(name, ncdim, pinned):
         ops.rwalk_batch(dm.model_id(), live, loglstar, 0.4, 12, SEED, chain0=40, ncdim=ncdim, start_rows=bad)
     after = ops.rwalk_batch(dm.model_id(), pts[starts], loglstar, 0.4, 12, SEED, chain0=40, ncdim=ncdim)   # and the failed call left nothing behind
     assert np.array_equal(after['u'], ref['u'])
+    if ncdim is None and n == 6:
+        # a pending setting is for the next rwalk call only: another chain entry point refuses it and clears it
+        from dynesty_b200 import _lib
+        ctx = _lib.default_context()
+        ctx.set_start_rows(_lib.ptr(starts), len(pts))
+        with pytest.raises(Exception):
+            ops.rslice_batch(dm.model_id(), pts[starts], loglstar, 0.4, 2, SEED)
+        again = ops.rwalk_batch(dm.model_id(), pts[starts], loglstar, 0.4, 12, SEED, chain0=40)
+        assert np.array_equal(again['u'], ref['u'])
