@@ -225,9 +225,14 @@ def dimflags_from(ndim, periodic=None, reflective=None):
 
 
 def rwalk_batch(model, u0, loglstar, scale, walks, seed, chain0=0, ncdim=None, ell=None, dimflags=None,
-                ctx=None, peer=None):
+                ctx=None, peer=None, out=None, start_rows=None):
     m = _models[model]
     u0 = np.atleast_2d(u0)
+    if start_rows is not None:          # b2n_set_start_rows: u0 is the live set, chain q starts from row start_rows[q]
+        idx = np.asarray(start_rows)
+        if idx.min() < 0 or idx.max() >= len(u0):
+            raise ValueError("start row index out of range")
+        u0 = u0[idx]
     Q, n = u0.shape
     per = ref = nb = None
     if dimflags is not None:
