@@ -75,3 +75,29 @@ def test_product_path_fails_loudly_without_a_gpu():
     import numpy as np
     with pytest.raises(_lib.B200Unavailable):
         ops.bounding_ellipsoid(np.random.default_rng(0).random((20, 3)))
+
+
+def test_header_is_plain_c_and_the_library_links(lib, tmp_path):
+    """The drop-in boundary is a C ABI: include/b200nest.h must compile as strict C99 (no C++, no torch) and a C
+    program must link against libb200nest.so and reach its host-only entry points without a GPU -- what a cgo / JNI /
+    ctypes binding on the reference's side relies on."""
+    import shutil
+    import subprocess
+    cc = shutil.which('gcc') or shutil.which('cc')
+    if cc is None:
+        pytest.skip('no C compiler')
+    libdir = os.path.dirname(_lib.LIBPATH)
+    src = tmp_path / 'abi.c'
+    src.write_text('#include "b200nest.h"\n#include <stddef.h>\n#include <string.h>\n'
+                   'int main(void) {\n'
+                   '    b2n_chain_args a; memset(&a, 0, sizeof a);\n'
+                   '    if (strcmp(b2n_strerror(B2N_OK), "ok") != 0) return 1;\n'
+                   '    if (b2n_set_start_rows(NULL, NULL, 0) != B2N_ERR_ARG) return 2;\n'
+                   '    if (b2n_rwalk_batch(NULL, &a, 1, NULL, NULL, NULL, NULL, NULL, NULL) != B2N_ERR_ARG) return 3;\n'
+                   '    return 0;\n}\n')
+    exe = tmp_path / 'abi'
+    cmd = [cc, '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', os.path.dirname(HEADER), str(src),
+           '-L', libdir, '-lb200nest', '-Wl,-rpath,' + os.path.abspath(libdir), '-o', str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
